@@ -1,0 +1,95 @@
+"""ctypes binding of libhq_b200.so (include/hq_b200.h).  No CPU fallback: importing this
+module without a loadable CUDA library raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+_i64, _i32, _p, _dbl = C.c_int64, C.c_int, C.c_void_p, C.c_double
+
+
+class IndexLayout(C.Structure):
+    """struct hq_index_layout"""
+    _fields_ = [("L", C.c_int32), ("Lsum", C.c_int32), ("lvl_off", C.c_int32 * 8),
+                ("lvl_w", C.c_int32 * 8), ("lvl_keff", C.c_int32 * 8)]
+
+
+# name -> (restype, argtypes); mirrors include/hq_b200.h declaration by declaration
+SIGNATURES = {
+    "hq_version": (_i32, []),
+    "hq_last_error": (C.c_char_p, []),
+    "hq_sm_count": (_i32, []),
+    "hq_d2xy_batch": (_i32, [_i32, _i64, _i64, _p, _p, _p]),
+    "hq_xy2d_batch": (_i32, [_i32, _p, _p, _i64, _p, _p]),
+    "hq_map_to_2d": (_i32, [_p, _i64, _i64, _i64, _i32, _i32, _p, _i64, _p]),
+    "hq_map_from_2d": (_i32, [_p, _i64, _i32, _i64, _i64, _i32, _p, _i64, _p]),
+    "hq_fused_scratch_bytes": (_i64, [_i64, _i32, _i32]),
+    "hq_fused_scratch_bytes_min_level": (_i64, [_i64, _i32, _i32, _i32]),
+    "hq_map_index_fused": (_i32, [_p, _i32, _i64, _i64, _i64, _i32, _p, _i64, _p, _i64, _p, _i32, _i32, _p, _i64, _p, _i64, _p]),
+    "hq_map_index_fused_ml": (_i32, [_p, _i32, _i64, _i64, _i64, _i32, _p, _i64, _p, _i64, _p, _i32, _i32, _i32, _p, _i64, _p, _i64, _p]),
+    "hq_block_means": (_i32, [_p, _i64, _i32, _i32, _i64, _i32, _i32, _p, _p, _i32, _p, _i64, _p]),
+    "hq_quantize_u8": (_i32, [_p, _i64, _i64, _i64, _p, _i64, _p, _p]),
+    "hq_dequantize_u8": (_i32, [_p, _i64, _i64, _i64, _p, _p, _i64, _p]),
+    "hq_index_row_lengths": (_i32, [_p, _i64, C.POINTER(IndexLayout), _p, _p]),
+    "hq_filter_level": (_i32, [_p, _p, _i64, C.POINTER(IndexLayout), _i32, _p, _p, _i32, _p, _i64, _dbl, _p, _i64, _p, _p, _p, _p]),
+    "hq_filter_select": (_i32, [_p, _i64, _i64, _i32, _p, _p, _dbl, _p, _i64, _p, _p]),
+    "hq_row_norms": (_i32, [_p, _i64, _i64, _i64, _p, _p]),
+    "hq_rerank_scores_f32": (_i32, [_p, _p, _i64, _i64, _i64, _p, _p, _i32, _i64, _p, _i64, _p, _i64, _p]),
+    "hq_topk_from_scores": (_i32, [_p, _i64, _i64, _i32, _i32, _i64, _p, _p, _p]),
+    "hq_rerank_scratch_bytes": (_i64, [_i64, _i32]),
+    "hq_rerank_topk_f32": (_i32, [_p, _p, _i64, _i64, _i64, _p, _p, _i32, _i64, _p, _i64, _i32, _i64, _p, _p, _p, _i64, _p]),
+    "hq_topk_merge": (_i32, [_p, _p, _i32, _i32, _i32, _p, _p, _p]),
+    "hq_core_level_sims": (_i32, [_p, _i64, _i32, _i64, _p, _p, _p, _p, _i32, _p, _p]),
+}
+
+HQ_OK, HQ_EINVAL, HQ_ECUDA, HQ_EUNSUPPORTED = 0, -1, -2, -3
+
+
+class HQLibraryError(RuntimeError):
+    """The CUDA library is missing, unloadable or returned HQ_ECUDA."""
+
+
+def _load():
+    path = _build.LIB_PATH
+    if not os.path.exists(path) or _build.needs_build():
+        try:
+            _build.build()
+        except Exception as e:  # no nvcc on this machine and no prebuilt library
+            if not os.path.exists(path):
+                raise HQLibraryError(
+                    f"libhq_b200.so is not built ({path}) and could not be compiled here: {e}. "
+                    "There is no CPU fallback; run `python -m hilbert_quantization_b200.build`.") from e
+    try:
+        lib = C.CDLL(path)
+    except OSError as e:
+        raise HQLibraryError(f"cannot load {path}: {e}") from e
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise HQLibraryError(f"{path} does not export {name}; rebuild it") from e
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+LIB_PATH = _build.LIB_PATH
+
+
+def last_error() -> str:
+    return lib.hq_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, exc=None):
+    """Map a status code to an exception (HQ_EINVAL -> `exc` or ValueError)."""
+    if rc == HQ_OK:
+        return
+    msg = last_error()
+    if rc == HQ_EINVAL:
+        raise (exc or ValueError)(msg)
+    if rc == HQ_EUNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise HQLibraryError(msg)

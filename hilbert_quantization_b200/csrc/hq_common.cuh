@@ -1,0 +1,75 @@
+// Shared device helpers and host-side error plumbing for libhq_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/hq_b200.h"
+
+void hq_set_error(const char* fmt, ...);
+
+#define HQ_REQUIRE(cond, ...)                         \
+    do {                                              \
+        if (!(cond)) {                                \
+            hq_set_error(__VA_ARGS__);                \
+            return HQ_EINVAL;                         \
+        }                                             \
+    } while (0)
+
+#define HQ_CUDA_OK(expr)                                                            \
+    do {                                                                            \
+        cudaError_t _e = (expr);                                                    \
+        if (_e != cudaSuccess) {                                                    \
+            hq_set_error("%s failed: %s", #expr, cudaGetErrorString(_e));           \
+            return HQ_ECUDA;                                                        \
+        }                                                                           \
+    } while (0)
+
+#define HQ_LAUNCH_OK(name)                                                          \
+    do {                                                                            \
+        cudaError_t _e = cudaGetLastError();                                        \
+        if (_e != cudaSuccess) {                                                    \
+            hq_set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));  \
+            return HQ_ECUDA;                                                        \
+        }                                                                           \
+    } while (0)
+
+static inline bool hq_is_pow2(int64_t n) { return n > 0 && (n & (n - 1)) == 0; }
+static inline int hq_log2(int64_t n) { int k = 0; while ((int64_t(1) << k) < n) ++k; return k; }
+int hq_cached_sm_count();
+
+// ---- Hilbert curve, the reference's variant (core/hilbert_mapper.py:42-113) ----
+// d -> (x, y), low bit-pairs first.
+__host__ __device__ __forceinline__ void hq_d2xy(int log2n, uint64_t d, uint32_t& x, uint32_t& y) {
+    uint32_t xx = 0, yy = 0;
+    uint64_t t = d;
+    for (int i = 0; i < log2n; ++i) {
+        const uint32_t s = 1u << i;
+        const uint32_t rx = 1u & (uint32_t)(t >> 1);
+        const uint32_t ry = 1u & ((uint32_t)t ^ rx);
+        if (ry == 0) {
+            if (rx == 1) { xx = s - 1 - xx; yy = s - 1 - yy; }
+            const uint32_t tmp = xx; xx = yy; yy = tmp;
+        }
+        xx += s * rx;
+        yy += s * ry;
+        t >>= 2;
+    }
+    x = xx; y = yy;
+}
+
+// (x, y) -> d, high bits first (core/hilbert_mapper.py:68-90).
+__host__ __device__ __forceinline__ uint64_t hq_xy2d(int log2n, uint32_t x, uint32_t y) {
+    uint64_t d = 0;
+    for (int i = log2n - 1; i >= 0; --i) {
+        const uint32_t s = 1u << i;
+        const uint32_t rx = (x & s) ? 1u : 0u;
+        const uint32_t ry = (y & s) ? 1u : 0u;
+        d += (uint64_t)s * s * ((3u * rx) ^ ry);
+        if (ry == 0) {
+            if (rx == 1) { x = s - 1 - x; y = s - 1 - y; }
+            const uint32_t tmp = x; x = y; y = tmp;
+        }
+    }
+    return d;
+}

@@ -1,0 +1,676 @@
+// K5 coarse filter (per-level index-row cosine + threshold + exact ratio cut), the exact
+// fp32 rerank path, per-query top-k and the multi-shard top-k merge.
+//
+// Reference semantics: rag/search/engine.py:178-287 (filter), :622-660 (cosine), :512 (sort).
+#include "hq_common.cuh"
+#include <float.h>
+
+namespace {
+
+// ------------------------------------------------------------------------------------
+// stripped row lengths and row norms
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_row_lengths(const float* __restrict__ idx, int64_t N, hq_index_layout lay,
+                                                     uint16_t* __restrict__ lens) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < N * lay.L; w += warps) {
+        const int64_t row = w / lay.L;
+        const int l = (int)(w - row * lay.L);
+        const float* r = idx + row * lay.Lsum + lay.lvl_off[l];
+        int last = 0;                                            // 1-based position of the last non-zero
+        for (int i = lane; i < lay.lvl_w[l]; i += 32)
+            if (__ldg(r + i) != 0.f) last = i + 1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+        if (lane == 0) lens[row * lay.L + l] = (uint16_t)(last > 0 ? last : 1);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_row_norms(const float* __restrict__ x, int64_t N, int64_t D, int64_t stride,
+                                                   float* __restrict__ norms) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const bool vec = (D % 4 == 0) && (stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < N; row += warps) {
+        const float* r = x + row * stride;
+        float acc = 0.f;
+        if (vec) {
+            for (int64_t i = lane; i < D / 4; i += 32) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(r) + i);
+                acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc); acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
+            }
+        } else {
+            for (int64_t i = lane; i < D; i += 32) { const float v = __ldg(r + i); acc = fmaf(v, v, acc); }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) norms[row] = sqrtf(acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// K5a: one filter level.  CTA = 256 rows x QT queries; a thread owns one row (K floats
+// in registers) and sweeps the query tile four queries at a time out of shared memory.
+// ------------------------------------------------------------------------------------
+constexpr int kFilterRows = 256;
+constexpr int kFilterQT = 64;
+
+template <int K>
+__global__ void __launch_bounds__(kFilterRows) k_filter_level(const float* __restrict__ idx, const uint16_t* __restrict__ lens,
+                                                              int64_t N, hq_index_layout lay, int level, int keff,
+                                                              const float* __restrict__ q_idx, const uint16_t* __restrict__ q_lens, int Q,
+                                                              const uint32_t* __restrict__ mask_in, int64_t mask_stride, double thr,
+                                                              float* __restrict__ scores, int64_t scores_stride,
+                                                              uint32_t* __restrict__ mask_out, int32_t* __restrict__ n_alive,
+                                                              int32_t* __restrict__ n_pass) {
+    extern __shared__ __align__(16) unsigned char fl_smem[];
+    float (*s_q)[kFilterQT] = reinterpret_cast<float (*)[kFilterQT]>(fl_smem);                       // [K][QT] transposed query tile
+    float (*s_qcum)[K + 1] = reinterpret_cast<float (*)[K + 1]>(fl_smem + sizeof(float) * K * kFilterQT);   // [QT][K+1] prefix sums of squares
+    float (*s_c)[K + 1] = reinterpret_cast<float (*)[K + 1]>(fl_smem + sizeof(float) * (K * kFilterQT + kFilterQT * (K + 1)));  // [rows][K+1]
+    __shared__ int s_qlen[kFilterQT];
+    __shared__ int s_alive[kFilterQT], s_pass[kFilterQT];
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int64_t row0 = (int64_t)blockIdx.x * kFilterRows;
+    const int q0 = blockIdx.y * kFilterQT;
+    const int off = lay.lvl_off[level];
+
+    // stage rows (coalesced segments) and queries
+    for (int e = tid; e < kFilterRows * K; e += kFilterRows) {
+        const int r = e / K, j = e - r * K;
+        const int64_t row = row0 + r;
+        s_c[r][j] = (row < N && j < keff) ? __ldg(idx + row * lay.Lsum + off + j) : 0.f;
+    }
+    for (int e = tid; e < kFilterQT * K; e += kFilterRows) {
+        const int qq = e / K, j = e - qq * K;
+        const int q = q0 + qq;
+        s_q[j][qq] = (q < Q && j < keff) ? __ldg(q_idx + (int64_t)q * lay.Lsum + off + j) : 0.f;
+    }
+    if (tid < kFilterQT) {
+        const int q = q0 + tid;
+        s_qlen[tid] = q < Q ? (int)q_lens[(int64_t)q * lay.L + level] : 1;
+        s_alive[tid] = 0;
+        s_pass[tid] = 0;
+    }
+    __syncthreads();
+    if (tid < kFilterQT) {
+        float c = 0.f;
+        s_qcum[tid][0] = 0.f;
+        for (int j = 0; j < K; ++j) { c = fmaf(s_q[j][tid], s_q[j][tid], c); s_qcum[tid][j + 1] = c; }
+    }
+    float c[K];
+    float cn2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < K; ++j) { c[j] = s_c[tid][j]; cn2 = fmaf(c[j], c[j], cn2); }
+    const int64_t row = row0 + tid;
+    const bool in_range = row < N;
+    int len_c = in_range ? (int)lens[row * lay.L + level] : 1;
+    if (len_c > K) len_c = K;
+    __syncthreads();
+
+    for (int qq = 0; qq < kFilterQT; qq += 4) {
+        if (q0 + qq >= Q) break;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const float4 qv = *reinterpret_cast<const float4*>(&s_q[j][qq]);
+            acc[0] = fmaf(c[j], qv.x, acc[0]);
+            acc[1] = fmaf(c[j], qv.y, acc[1]);
+            acc[2] = fmaf(c[j], qv.z, acc[2]);
+            acc[3] = fmaf(c[j], qv.w, acc[3]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int q = q0 + qq + u;
+            if (q >= Q) break;                                   // warp-uniform
+            bool alive = in_range;
+            if (alive && mask_in) alive = (__ldg(mask_in + (int64_t)q * mask_stride + (row >> 5)) >> (row & 31)) & 1u;
+            int len_q = s_qlen[qq + u];
+            if (len_q > K) len_q = K;
+            float nq2, nc2;
+            if (len_c <= len_q) {
+                nc2 = cn2;
+                nq2 = s_qcum[qq + u][len_c];
+            } else {
+                nq2 = s_qcum[qq + u][len_q];
+                nc2 = 0.f;
+#pragma unroll
+                for (int j = 0; j < K; ++j) nc2 = j < len_q ? fmaf(c[j], c[j], nc2) : nc2;
+            }
+            const float nq = sqrtf(nq2), nc = sqrtf(nc2);
+            float s = 0.f;
+            if (nq != 0.f && nc != 0.f) s = __fmul_rn(__fadd_rn(__fdiv_rn(acc[u], __fmul_rn(nq, nc)), 1.0f), 0.5f);
+            const bool pass = alive && ((double)s >= thr);
+            if (in_range) scores[(int64_t)q * scores_stride + row] = alive ? s : -1.0f;
+            const uint32_t b_alive = __ballot_sync(0xffffffffu, alive);
+            const uint32_t b_pass = __ballot_sync(0xffffffffu, pass);
+            if (lane == 0) {
+                if (row0 + (tid & ~31) < N) mask_out[(int64_t)q * mask_stride + ((row0 + tid) >> 5)] = b_pass;
+                if (b_alive) atomicAdd(&s_alive[qq + u], __popc(b_alive));
+                if (b_pass) atomicAdd(&s_pass[qq + u], __popc(b_pass));
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < kFilterQT && q0 + tid < Q) {
+        if (s_alive[tid]) atomicAdd(n_alive + q0 + tid, s_alive[tid]);
+        if (s_pass[tid]) atomicAdd(n_pass + q0 + tid, s_pass[tid]);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// exact k-th largest of the non-negative entries of s[0..N) (block-wide radix select on
+// the float bit pattern, 11 + 11 + 10 bits).  Returns the key of the k-th largest and how
+// many entries equal to it belong to the top k.
+// ------------------------------------------------------------------------------------
+struct SelectResult { uint32_t key; uint32_t take_ties; uint32_t ties_total; };
+
+__device__ SelectResult block_radix_select(const float* __restrict__ s, int64_t N, uint32_t k, uint32_t* hist /*2048*/,
+                                           uint32_t* sh /*4*/) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    uint32_t prefix = 0, pmask = 0, remaining = k;
+    const int shifts[3] = {21, 10, 0};
+    const int bits[3] = {11, 11, 10};
+    uint32_t ties_total = 0;
+    for (int pass = 0; pass < 3; ++pass) {
+        const int shift = shifts[pass];
+        const uint32_t nb = 1u << bits[pass];
+        for (uint32_t i = tid; i < nb; i += nt) hist[i] = 0;
+        __syncthreads();
+        for (int64_t i = tid; i < N; i += nt) {
+            const float v = __ldg(s + i);
+            if (v >= 0.f) {
+                const uint32_t key = __float_as_uint(v);
+                if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & (nb - 1)], 1u);
+            }
+        }
+        __syncthreads();
+        if (tid < 32) {
+            // lane l owns bins [hi - (l+1)*seg, hi - l*seg) counted from the top
+            const uint32_t seg = nb / 32;
+            uint32_t sum = 0;
+            const uint32_t top = nb - tid * seg;                 // exclusive upper bin of this lane's segment
+            for (uint32_t b = 0; b < seg; ++b) sum += hist[top - 1 - b];
+            uint32_t incl = sum;                                 // inclusive scan over lanes (lane 0 = highest bins)
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (tid >= o) incl += t;
+            }
+            const uint32_t excl = incl - sum;
+            const bool mine = excl < remaining && remaining <= incl;
+            if (mine) {
+                uint32_t above = excl, b = top;
+                for (;;) {
+                    --b;
+                    const uint32_t h = hist[b];
+                    if (above + h >= remaining) break;
+                    above += h;
+                }
+                sh[0] = b;
+                sh[1] = remaining - above;                       // rank inside the bin (1-based)
+                sh[2] = hist[b];
+            }
+        }
+        __syncthreads();
+        const uint32_t b = sh[0];
+        remaining = sh[1];
+        ties_total = sh[2];
+        prefix |= b << shift;
+        pmask |= (nb - 1) << shift;
+        __syncthreads();
+    }
+    SelectResult r;
+    r.key = prefix;
+    r.take_ties = remaining;
+    r.ties_total = ties_total;
+    return r;
+}
+
+// block-wide exclusive prefix of a 0/1 flag for threads in row order; returns the rank
+// and adds the block total to `running` (kept identical in every thread).
+__device__ __forceinline__ uint32_t block_flag_rank(bool flag, uint32_t& running, uint32_t* s_warp /*32*/) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const uint32_t bal = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) s_warp[w] = __popc(bal);
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+    for (int i = 0; i < nw; ++i) {
+        const uint32_t c = s_warp[i];
+        if (i < w) before += c;
+        total += c;
+    }
+    __syncthreads();
+    const uint32_t rank = running + before + __popc(bal & ((1u << lane) - 1));
+    running += total;
+    return rank;
+}
+
+// K5b: ratio cut.  One CTA per query.
+__global__ void __launch_bounds__(1024) k_filter_select(const float* __restrict__ scores, int64_t scores_stride, int64_t N,
+                                                        const int32_t* __restrict__ n_alive, const int32_t* __restrict__ n_pass,
+                                                        double ratio, uint32_t* __restrict__ mask, int64_t mask_stride,
+                                                        int32_t* __restrict__ n_out) {
+    __shared__ uint32_t hist[2048];
+    __shared__ uint32_t sh[4];
+    __shared__ uint32_t s_warp[32];
+    const int q = blockIdx.x;
+    const int64_t na = n_alive[q], np = n_pass[q];
+    int64_t cap = (int64_t)((double)na * ratio);                 // int(len * ratio), Python float semantics
+    if (cap < 1) cap = 1;
+    if (np <= cap) {
+        if (threadIdx.x == 0) n_out[q] = (int32_t)np;
+        return;
+    }
+    const float* s = scores + (int64_t)q * scores_stride;
+    const SelectResult r = block_radix_select(s, N, (uint32_t)cap, hist, sh);
+    uint32_t* m = mask + (int64_t)q * mask_stride;
+    const bool ordered = r.take_ties < r.ties_total;
+    uint32_t running = 0;
+    const int lane = threadIdx.x & 31;
+    for (int64_t base = 0; base < N; base += blockDim.x) {
+        const int64_t i = base + threadIdx.x;
+        const float v = i < N ? __ldg(s + i) : -1.f;
+        const uint32_t key = __float_as_uint(v);
+        bool keep = v >= 0.f && key > r.key;
+        const bool tie = v >= 0.f && key == r.key;
+        if (ordered) {
+            const uint32_t rank = block_flag_rank(tie, running, s_warp);
+            keep = keep || (tie && rank < r.take_ties);
+        } else {
+            keep = keep || tie;
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0 && i < N) m[i >> 5] = bal;
+    }
+    if (threadIdx.x == 0) n_out[q] = (int32_t)cap;
+}
+
+// ------------------------------------------------------------------------------------
+// exact fp32 rerank scores: tiled FMA GEMM (64 queries x 128 rows x 16 k per step)
+// ------------------------------------------------------------------------------------
+constexpr int kBM = 64, kBN = 128, kBK = 16;
+
+__global__ void __launch_bounds__(256) k_rerank_scores(const float* __restrict__ db, const float* __restrict__ db_norm, int64_t N,
+                                                       int64_t D, int64_t db_stride, const float* __restrict__ qm,
+                                                       const float* __restrict__ q_norm, int Q, int64_t q_stride,
+                                                       const uint32_t* __restrict__ mask, int64_t mask_stride,
+                                                       float* __restrict__ scores, int64_t scores_stride, int vec) {
+    __shared__ __align__(16) float sA[kBK][kBM + 4];
+    __shared__ __align__(16) float sB[kBK][kBN + 4];
+    const int tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;                      // ty: 16 groups of 4 queries; tx: 16 groups of 2x4 rows
+    const int64_t row0 = (int64_t)blockIdx.x * kBN;
+    const int q0 = blockIdx.y * kBM;
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    const int lr = tid >> 2, lk = (tid & 3) * 4;                 // loader: row lr (+64), k offset lk
+    for (int64_t k0 = 0; k0 < D; k0 += kBK) {
+        {   // queries
+            const int q = q0 + lr;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q < Q) {
+                const float* p = qm + (int64_t)q * q_stride + k0 + lk;
+                if (vec && k0 + lk + 3 < D) v = __ldg(reinterpret_cast<const float4*>(p));
+                else {
+                    if (k0 + lk < D) v.x = __ldg(p);
+                    if (k0 + lk + 1 < D) v.y = __ldg(p + 1);
+                    if (k0 + lk + 2 < D) v.z = __ldg(p + 2);
+                    if (k0 + lk + 3 < D) v.w = __ldg(p + 3);
+                }
+            }
+            sA[lk][lr] = v.x; sA[lk + 1][lr] = v.y; sA[lk + 2][lr] = v.z; sA[lk + 3][lr] = v.w;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = lr + 64 * h;
+            const int64_t row = row0 + r;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < N) {
+                const float* p = db + row * db_stride + k0 + lk;
+                if (vec && k0 + lk + 3 < D) v = __ldg(reinterpret_cast<const float4*>(p));
+                else {
+                    if (k0 + lk < D) v.x = __ldg(p);
+                    if (k0 + lk + 1 < D) v.y = __ldg(p + 1);
+                    if (k0 + lk + 2 < D) v.z = __ldg(p + 2);
+                    if (k0 + lk + 3 < D) v.w = __ldg(p + 3);
+                }
+            }
+            sB[lk][r] = v.x; sB[lk + 1][r] = v.y; sB[lk + 2][r] = v.z; sB[lk + 3][r] = v.w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kBK; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(&sA[k][ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&sB[k][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&sB[k][64 + tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int q = q0 + ty * 4 + i;
+        if (q >= Q) continue;
+        const float nq = __ldg(q_norm + q);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t rbase = row0 + 64 * h + tx * 4;
+            uint32_t mw = 0xffffffffu;
+            if (mask && rbase < N) mw = __ldg(mask + (int64_t)q * mask_stride + (rbase >> 5));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t row = rbase + j;
+                if (row >= N) continue;
+                const bool alive = (mw >> (row & 31)) & 1u;
+                const float nc = __ldg(db_norm + row);
+                float s = 0.f;
+                if (nq != 0.f && nc != 0.f) s = __fmul_rn(__fadd_rn(__fdiv_rn(acc[i][4 * h + j], __fmul_rn(nq, nc)), 1.0f), 0.5f);
+                scores[(int64_t)q * scores_stride + row] = alive ? s : -1.0f;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// per-query top-k of a score row (exact; ties -> lower row id).  One CTA per query.
+// ------------------------------------------------------------------------------------
+constexpr int kMaxK = 1024;
+
+__global__ void __launch_bounds__(1024) k_topk_scores(const float* __restrict__ scores, int64_t scores_stride, int64_t N, int k,
+                                                      int64_t id_base, int64_t* __restrict__ ids, float* __restrict__ out_scores) {
+    __shared__ uint32_t hist[2048];
+    __shared__ uint32_t sh[4];
+    __shared__ uint32_t s_warp[32];
+    __shared__ float s_val[kMaxK];
+    __shared__ int64_t s_id[kMaxK];
+    __shared__ uint32_t s_cnt;
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const float* s = scores + (int64_t)q * scores_stride;
+
+    // how many live entries are there?  (needed when fewer than k survive)
+    uint32_t live = 0;
+    for (int64_t i = tid; i < N; i += blockDim.x) live += __ldg(s + i) >= 0.f ? 1u : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) live += __shfl_xor_sync(0xffffffffu, live, o);
+    if ((tid & 31) == 0) s_warp[tid >> 5] = live;
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    uint32_t total_live = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) total_live += s_warp[i];
+    __syncthreads();
+    const uint32_t kk = total_live < (uint32_t)k ? total_live : (uint32_t)k;
+    for (int i = tid; i < kMaxK; i += blockDim.x) { s_val[i] = -2.f; s_id[i] = INT64_MAX; }
+    __syncthreads();
+    if (kk > 0) {
+        const SelectResult r = block_radix_select(s, N, kk, hist, sh);
+        const bool ordered = r.take_ties < r.ties_total;
+        uint32_t running = 0;
+        for (int64_t base = 0; base < N; base += blockDim.x) {
+            const int64_t i = base + tid;
+            const float v = i < N ? __ldg(s + i) : -1.f;
+            const uint32_t key = __float_as_uint(v);
+            bool keep = v >= 0.f && key > r.key;
+            const bool tie = v >= 0.f && key == r.key;
+            if (ordered) {
+                const uint32_t rank = block_flag_rank(tie, running, s_warp);
+                keep = keep || (tie && rank < r.take_ties);
+            } else {
+                keep = keep || tie;
+            }
+            if (keep) {
+                const uint32_t slot = atomicAdd(&s_cnt, 1u);
+                if (slot < (uint32_t)kMaxK) { s_val[slot] = v; s_id[slot] = i; }
+            }
+        }
+        __syncthreads();
+    }
+    // rank by (score desc, id asc) -- k <= 1024, one thread per entry
+    if (tid < kMaxK && tid < (int)kk) {
+        const float v = s_val[tid];
+        const int64_t id = s_id[tid];
+        int rank = 0;
+        for (uint32_t j = 0; j < kk; ++j) {
+            const float vj = s_val[j];
+            const int64_t idj = s_id[j];
+            rank += (vj > v || (vj == v && idj < id)) ? 1 : 0;
+        }
+        ids[(int64_t)q * k + rank] = id + id_base;
+        out_scores[(int64_t)q * k + rank] = v;
+    }
+    for (int i = (int)kk + tid; i < k; i += blockDim.x) {
+        ids[(int64_t)q * k + i] = -1;
+        out_scores[(int64_t)q * k + i] = -1.0f;
+    }
+}
+
+// merge of P per-shard lists per query; ties -> lower id; id < 0 = empty slot
+__global__ void __launch_bounds__(256) k_topk_merge(const int64_t* __restrict__ in_ids, const float* __restrict__ in_scores, int P,
+                                                    int Q, int k, int64_t* __restrict__ out_ids, float* __restrict__ out_scores) {
+    extern __shared__ unsigned char smraw[];
+    const int M = P * k;
+    int64_t* s_id = reinterpret_cast<int64_t*>(smraw);
+    float* s_val = reinterpret_cast<float*>(s_id + M);
+    const int q = blockIdx.x;
+    for (int e = threadIdx.x; e < M; e += blockDim.x) {
+        const int p = e / k, j = e - p * k;
+        s_id[e] = in_ids[((int64_t)p * Q + q) * k + j];
+        s_val[e] = in_scores[((int64_t)p * Q + q) * k + j];
+    }
+    for (int j = threadIdx.x; j < k; j += blockDim.x) { out_ids[(int64_t)q * k + j] = -1; out_scores[(int64_t)q * k + j] = -1.0f; }
+    __syncthreads();
+    for (int e = threadIdx.x; e < M; e += blockDim.x) {
+        const int64_t id = s_id[e];
+        if (id < 0) continue;
+        const float v = s_val[e];
+        int rank = 0;
+        for (int j = 0; j < M; ++j) {
+            const int64_t idj = s_id[j];
+            if (idj < 0) continue;
+            const float vj = s_val[j];
+            rank += (vj > v || (vj == v && (idj < id || (idj == id && j < e)))) ? 1 : 0;
+        }
+        if (rank < k) { out_ids[(int64_t)q * k + rank] = id; out_scores[(int64_t)q * k + rank] = v; }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// a11: core per-level similarity (core/search_engine.py:151-189), float64 like NumPy
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_core_level_sims(const double* __restrict__ cand, int64_t N, int S, int64_t cand_stride,
+                                                         const double* __restrict__ q, const int32_t* __restrict__ q_start,
+                                                         const int32_t* __restrict__ c_start, const int32_t* __restrict__ lvl_len,
+                                                         int n_levels, double* __restrict__ sims) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < N * n_levels; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = t / n_levels;
+        const int l = (int)(t - row * n_levels);
+        const int m = lvl_len[l];
+        const double* c = cand + row * cand_stride + c_start[l];
+        const double* qq = q + q_start[l];
+        double out = 0.0;
+        if (m > 0) {
+            double qs = 0, cs = 0;
+            for (int j = 0; j < m; ++j) { qs += qq[j]; cs += c[j]; }
+            const double qm = qs / m, cm = cs / m;
+            double qv = 0, cv = 0, q2 = 0, c2 = 0, mse = 0;
+            for (int j = 0; j < m; ++j) {
+                const double dq = qq[j] - qm, dc = c[j] - cm;
+                qv += dq * dq; cv += dc * dc;
+                q2 += qq[j] * qq[j]; c2 += c[j] * c[j];
+                const double e = qq[j] - c[j];
+                mse += e * e;
+            }
+            const double qstd = sqrt(qv / m), cstd = sqrt(cv / m);
+            if (qstd == 0.0 && cstd == 0.0) out = fabs(qm - cm) < 1e-6 ? 1.0 : 0.0;
+            else if (qstd == 0.0 || cstd == 0.0) out = 0.1;
+            else {
+                double corr = 0;
+                for (int j = 0; j < m; ++j) corr += ((qq[j] - qm) / qstd) * ((c[j] - cm) / cstd);
+                corr /= m;
+                const double sim = (corr + 1.0) / 2.0;
+                const double mx = q2 / m + c2 / m;
+                double dist = 1.0;
+                if (mx > 0) { dist = 1.0 - (mse / m) / mx; if (dist < 0) dist = 0; }
+                out = 0.7 * sim + 0.3 * dist;
+                out = out < 0 ? 0 : (out > 1 ? 1 : out);
+            }
+        }
+        sims[row * n_levels + l] = out;
+    }
+}
+
+int grid_cap(int64_t blocks, int per_sm) {
+    const int64_t cap = (int64_t)hq_cached_sm_count() * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+bool layout_ok(const hq_index_layout* l) {
+    if (!l || l->L < 1 || l->L > 8 || l->Lsum < 1) return false;
+    for (int i = 0; i < l->L; ++i)
+        if (l->lvl_off[i] < 0 || l->lvl_w[i] < 1 || l->lvl_off[i] + l->lvl_w[i] > l->Lsum || l->lvl_keff[i] < 1 ||
+            l->lvl_keff[i] > l->lvl_w[i])
+            return false;
+    return true;
+}
+
+}  // namespace
+
+extern "C" int hq_index_row_lengths(const float* idx, int64_t N, const hq_index_layout* layout, uint16_t* lens, void* stream) {
+    HQ_REQUIRE(layout_ok(layout), "bad index layout");
+    HQ_REQUIRE(N >= 0, "negative N");
+    if (N == 0) return HQ_OK;
+    HQ_REQUIRE(idx && lens, "null pointer");
+    k_row_lengths<<<grid_cap((N * layout->L + 7) / 8, 16), 256, 0, (cudaStream_t)stream>>>(idx, N, *layout, lens);
+    HQ_LAUNCH_OK("k_row_lengths");
+    return HQ_OK;
+}
+
+extern "C" int hq_row_norms(const float* x, int64_t N, int64_t D, int64_t stride, float* norms, void* stream) {
+    HQ_REQUIRE(N >= 0 && D > 0 && stride >= D, "bad shape");
+    if (N == 0) return HQ_OK;
+    HQ_REQUIRE(x && norms, "null pointer");
+    k_row_norms<<<grid_cap((N + 7) / 8, 16), 256, 0, (cudaStream_t)stream>>>(x, N, D, stride, norms);
+    HQ_LAUNCH_OK("k_row_norms");
+    return HQ_OK;
+}
+
+extern "C" int hq_filter_level(const float* idx, const uint16_t* lens, int64_t N, const hq_index_layout* layout, int level,
+                               const float* q_idx, const uint16_t* q_lens, int Q, const uint32_t* mask_in, int64_t mask_stride,
+                               double thr, float* scores, int64_t scores_stride, uint32_t* mask_out, int32_t* n_alive,
+                               int32_t* n_pass, void* stream) {
+    HQ_REQUIRE(layout_ok(layout), "bad index layout");
+    HQ_REQUIRE(level >= 0 && level < layout->L, "level %d out of range", level);
+    HQ_REQUIRE(N >= 0 && Q >= 0, "negative size");
+    if (N == 0 || Q == 0) return HQ_OK;
+    HQ_REQUIRE(idx && lens && q_idx && q_lens && scores && mask_out && n_alive && n_pass, "null pointer");
+    HQ_REQUIRE(mask_stride * 32 >= N && scores_stride >= N, "mask/scores stride too small");
+    const int keff = layout->lvl_keff[level];
+    HQ_REQUIRE(keff <= 64, "filter level wider than 64 values (%d) is not supported", keff);
+    dim3 g((unsigned)((N + kFilterRows - 1) / kFilterRows), (unsigned)((Q + kFilterQT - 1) / kFilterQT));
+    cudaStream_t st = (cudaStream_t)stream;
+#define HQ_FL(KK)                                                                                                              \
+    do {                                                                                                                       \
+        const size_t smem = sizeof(float) * ((size_t)KK * kFilterQT + (size_t)kFilterQT * (KK + 1) + (size_t)kFilterRows * (KK + 1)); \
+        if (smem > 48 * 1024)                                                                                                  \
+            HQ_CUDA_OK(cudaFuncSetAttribute(k_filter_level<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+        k_filter_level<KK><<<g, kFilterRows, smem, st>>>(idx, lens, N, *layout, level, keff, q_idx, q_lens, Q, mask_in,         \
+                                                         mask_stride, thr, scores, scores_stride, mask_out, n_alive, n_pass);  \
+    } while (0)
+    if (keff <= 4) HQ_FL(4);
+    else if (keff <= 8) HQ_FL(8);
+    else if (keff <= 16) HQ_FL(16);
+    else if (keff <= 24) HQ_FL(24);
+    else if (keff <= 32) HQ_FL(32);
+    else if (keff <= 48) HQ_FL(48);
+    else HQ_FL(64);
+#undef HQ_FL
+    HQ_LAUNCH_OK("k_filter_level");
+    return HQ_OK;
+}
+
+extern "C" int hq_filter_select(const float* scores, int64_t scores_stride, int64_t N, int Q, const int32_t* n_alive,
+                                const int32_t* n_pass, double ratio, uint32_t* mask, int64_t mask_stride, int32_t* n_out,
+                                void* stream) {
+    HQ_REQUIRE(N >= 0 && Q >= 0, "negative size");
+    if (N == 0 || Q == 0) return HQ_OK;
+    HQ_REQUIRE(scores && n_alive && n_pass && mask && n_out, "null pointer");
+    HQ_REQUIRE(N < ((int64_t)1 << 31), "N too large for one shard");
+    k_filter_select<<<Q, 1024, 0, (cudaStream_t)stream>>>(scores, scores_stride, N, n_alive, n_pass, ratio, mask, mask_stride, n_out);
+    HQ_LAUNCH_OK("k_filter_select");
+    return HQ_OK;
+}
+
+extern "C" int hq_rerank_scores_f32(const float* db, const float* db_norm, int64_t N, int64_t D, int64_t db_stride, const float* q,
+                                    const float* q_norm, int Q, int64_t q_stride, const uint32_t* mask, int64_t mask_stride,
+                                    float* scores, int64_t scores_stride, void* stream) {
+    HQ_REQUIRE(N >= 0 && Q >= 0 && D > 0, "bad shape");
+    if (N == 0 || Q == 0) return HQ_OK;
+    HQ_REQUIRE(db && db_norm && q && q_norm && scores, "null pointer");
+    HQ_REQUIRE(db_stride >= D && q_stride >= D && scores_stride >= N, "stride too small");
+    HQ_REQUIRE(!mask || mask_stride * 32 >= N, "mask stride too small");
+    const int vec = (db_stride % 4 == 0) && (q_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(db) & 15) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(q) & 15) == 0);
+    dim3 g((unsigned)((N + kBN - 1) / kBN), (unsigned)((Q + kBM - 1) / kBM));
+    k_rerank_scores<<<g, 256, 0, (cudaStream_t)stream>>>(db, db_norm, N, D, db_stride, q, q_norm, Q, q_stride, mask, mask_stride,
+                                                         scores, scores_stride, vec);
+    HQ_LAUNCH_OK("k_rerank_scores");
+    return HQ_OK;
+}
+
+extern "C" int hq_topk_from_scores(const float* scores, int64_t scores_stride, int64_t N, int Q, int k, int64_t id_base,
+                                   int64_t* ids, float* out_scores, void* stream) {
+    HQ_REQUIRE(k >= 1 && k <= kMaxK, "k must be in [1, %d]", kMaxK);
+    HQ_REQUIRE(N >= 0 && Q >= 0, "negative size");
+    if (Q == 0) return HQ_OK;
+    HQ_REQUIRE(ids && out_scores && (scores || N == 0), "null pointer");
+    HQ_REQUIRE(N < ((int64_t)1 << 31), "N too large for one shard");
+    k_topk_scores<<<Q, 1024, 0, (cudaStream_t)stream>>>(scores, scores_stride, N, k, id_base, ids, out_scores);
+    HQ_LAUNCH_OK("k_topk_scores");
+    return HQ_OK;
+}
+
+extern "C" int64_t hq_rerank_scratch_bytes(int64_t N, int Q) { return N * (int64_t)Q * 4; }
+
+extern "C" int hq_rerank_topk_f32(const float* db, const float* db_norm, int64_t N, int64_t D, int64_t db_stride, const float* q,
+                                  const float* q_norm, int Q, int64_t q_stride, const uint32_t* mask, int64_t mask_stride, int k,
+                                  int64_t id_base, int64_t* ids, float* scores, void* scratch, int64_t scratch_bytes, void* stream) {
+    HQ_REQUIRE(scratch && scratch_bytes >= hq_rerank_scratch_bytes(N, Q), "scratch too small");
+    int rc = hq_rerank_scores_f32(db, db_norm, N, D, db_stride, q, q_norm, Q, q_stride, mask, mask_stride, (float*)scratch, N, stream);
+    if (rc != HQ_OK) return rc;
+    return hq_topk_from_scores((const float*)scratch, N, N, Q, k, id_base, ids, scores, stream);
+}
+
+extern "C" int hq_topk_merge(const int64_t* in_ids, const float* in_scores, int P, int Q, int k, int64_t* out_ids, float* out_scores,
+                             void* stream) {
+    HQ_REQUIRE(P >= 1 && Q >= 0 && k >= 1, "bad shape");
+    if (Q == 0) return HQ_OK;
+    HQ_REQUIRE(in_ids && in_scores && out_ids && out_scores, "null pointer");
+    const size_t smem = (size_t)P * k * 12;
+    HQ_REQUIRE(smem <= 48 * 1024, "P*k too large for the merge kernel");
+    k_topk_merge<<<Q, 256, smem, (cudaStream_t)stream>>>(in_ids, in_scores, P, Q, k, out_ids, out_scores);
+    HQ_LAUNCH_OK("k_topk_merge");
+    return HQ_OK;
+}
+
+extern "C" int hq_core_level_sims(const double* cand, int64_t N, int S, int64_t cand_stride, const double* q, const int32_t* q_start,
+                                  const int32_t* c_start, const int32_t* lvl_len, int n_levels, double* sims, void* stream) {
+    HQ_REQUIRE(N >= 0 && S > 0 && n_levels >= 0 && cand_stride >= S, "bad shape");
+    if (N == 0 || n_levels == 0) return HQ_OK;
+    HQ_REQUIRE(cand && q && q_start && c_start && lvl_len && sims, "null pointer");
+    k_core_level_sims<<<grid_cap((N * n_levels + 255) / 256, 16), 256, 0, (cudaStream_t)stream>>>(cand, N, S, cand_stride, q, q_start,
+                                                                                                 c_start, lvl_len, n_levels, sims);
+    HQ_LAUNCH_OK("k_core_level_sims");
+    return HQ_OK;
+}

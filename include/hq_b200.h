@@ -1,0 +1,188 @@
+/*
+ * hq_b200.h -- C ABI of libhq_b200.so, the sm_100a implementation of the
+ * hilbert-quantization hot path (Hilbert map/unmap -> hierarchical index (+u8
+ * quantise) -> progressive search).
+ *
+ * Rules of the boundary
+ *   - every entry point is extern "C", returns an int status (0 = HQ_OK,
+ *     negative = error, text via hq_last_error()), never aborts, never
+ *     allocates device memory, never takes ownership;
+ *   - all data pointers are DEVICE pointers unless the name says host;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *     calls are asynchronous on that stream;
+ *   - element strides are counted in elements, not bytes.
+ *
+ * Each declaration cites the reference interface it replaces (paths relative
+ * to the reference checkout, Tylerlhess/hilbert-quantization v1.3.0).
+ */
+#ifndef HQ_B200_H
+#define HQ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HQ_OK            0
+#define HQ_EINVAL       (-1)   /* bad argument (message in hq_last_error)      */
+#define HQ_ECUDA        (-2)   /* CUDA runtime error                           */
+#define HQ_EUNSUPPORTED (-3)   /* valid request this build does not implement  */
+
+#define HQ_ABI_VERSION  1
+
+/* ---- library ---------------------------------------------------------- */
+int         hq_version(void);
+const char* hq_last_error(void);              /* thread-local, never NULL   */
+int         hq_sm_count(void);                /* SMs of the current device  */
+
+/* ---- a1/a2: Hilbert coordinates ---------------------------------------
+ * hilbert_quantization/core/hilbert_mapper.py:17-66 (generate_hilbert_coordinates,
+ * _hilbert_index_to_xy) and :68-90 (_xy_to_hilbert_index); RAG twin
+ * rag/embedding_generation/hilbert_mapper.py:122-230.
+ * x[i], y[i] = d2xy(n, d0 + i);  d[i] = xy2d(n, x[i], y[i]).  n power of two. */
+int hq_d2xy_batch(int n, int64_t d0, int64_t count, int32_t* x, int32_t* y, void* stream);
+int hq_xy2d_batch(int n, const int32_t* x, const int32_t* y, int64_t count, int64_t* d, void* stream);
+
+/* ---- a3/a4: map_to_2d / map_from_2d (pure permutation + zero pad) -----
+ * core/hilbert_mapper.py:115-174 (map_to_2d) and :176-205 (map_from_2d); RAG twin
+ * rag/embedding_generation/hilbert_mapper.py:16-120.  Any element width in
+ * {1,2,4,8} bytes (dtype preserved, tests/test_hilbert_mapper.py:359-378).
+ *   map_to_2d  : src [N, D] (row stride src_stride) -> dst [N, n, n] (item stride dst_stride)
+ *   map_from_2d: src [N, n, n]                      -> dst [N, D_out] (first D_out curve cells) */
+int hq_map_to_2d(const void* src, int64_t N, int64_t D, int64_t src_stride, int n, int elem_bytes,
+                 void* dst, int64_t dst_stride, void* stream);
+int hq_map_from_2d(const void* src, int64_t N, int n, int64_t src_stride, int64_t D_out, int elem_bytes,
+                   void* dst, int64_t dst_stride, void* stream);
+
+/* ---- a3/a4 + a6/a7/a8 fused: one pass over fp32 items -------------------
+ * Replaces the map_to_2d -> generate_*_indices -> embed sequence of
+ * core/pipeline.py:129-140 and the RAG sequence
+ * rag/embedding_generation/hilbert_mapper.py:16 ->
+ * rag/embedding_generation/hierarchical_index_generator.py:103 (variant C),
+ * core/streaming_index_builder.py:315 (variant B), core/index_generator.py:313 (variant A).
+ *
+ * direction 0: src = streams [N, D]  (map):   optional grid_out
+ * direction 1: src = grids  [N, n, n] (unmap): optional stream_out (first D values)
+ * Index values are a gather (`plan`, length plan_len, device int32) out of the
+ * per-item run-mean pyramid: plan[i] < 0 -> 0.0; plan[i] < n*n -> grid cell
+ * plan[i] (row-major); otherwise pyramid level k>=1, position j encoded as
+ * n*n + level_base(k) + j with level_base(1)=0, level_base(k+1)=level_base(k)+n*n/4^k.
+ * pyr_mode 0: float32 pairwise tree means -> idx_out float32 (variants A, C);
+ * pyr_mode 1: float64 strict ((a+b)+c)+d)*0.25 -> idx_out float64 (variant B, bit-exact).
+ * Any of grid_out / stream_out / idx_out may be NULL.  n <= 64 runs as one
+ * fused launch; larger n is tiled 64x64 and finished by a second small launch
+ * that needs `scratch` (hq_fused_scratch_bytes). */
+int64_t hq_fused_scratch_bytes(int64_t N, int n, int pyr_mode);
+/* same, when the caller knows the lowest pyramid level (>= 1) its plan references */
+int64_t hq_fused_scratch_bytes_min_level(int64_t N, int n, int pyr_mode, int min_level);
+int hq_map_index_fused_ml(const float* src, int direction, int64_t N, int64_t D, int64_t src_stride, int n,
+                          float* grid_out, int64_t grid_stride,
+                          float* stream_out, int64_t stream_stride,
+                          const int32_t* plan, int plan_len, int pyr_mode, int min_level,
+                          void* idx_out, int64_t idx_stride,
+                          void* scratch, int64_t scratch_bytes, void* stream);
+int hq_map_index_fused(const float* src, int direction, int64_t N, int64_t D, int64_t src_stride, int n,
+                       float* grid_out, int64_t grid_stride,
+                       float* stream_out, int64_t stream_stride,
+                       const int32_t* plan, int plan_len, int pyr_mode,
+                       void* idx_out, int64_t idx_stride,
+                       void* scratch, int64_t scratch_bytes, void* stream);
+
+/* ---- a8 general: block means over arbitrary (H, W) images -------------
+ * rag/embedding_generation/hierarchical_index_generator.py:204-244 for images
+ * that are not power-of-two squares.  out[item, s] = mean(img[r0:r0+sh, c0:c0+sw])
+ * with (r0, c0) = (rows[s]*sh, cols[s]*sw). */
+int hq_block_means(const float* img, int64_t N, int H, int W, int64_t img_stride, int sh, int sw,
+                   const int32_t* rows, const int32_t* cols, int count,
+                   float* out, int64_t out_stride, void* stream);
+
+/* ---- a10: uint8 quantise / dequantise ---------------------------------
+ * core/compressor.py:256-280 (_normalize_for_compression: truncating cast,
+ * constant image -> 128) and :282-303 (_denormalize_from_compression).
+ * minmax [N, 2] float32 is written by quantise and read by dequantise. */
+int hq_quantize_u8(const float* src, int64_t N, int64_t elems, int64_t src_stride,
+                   uint8_t* dst, int64_t dst_stride, float* minmax, void* stream);
+int hq_dequantize_u8(const uint8_t* src, int64_t N, int64_t elems, int64_t src_stride,
+                     const float* minmax, float* dst, int64_t dst_stride, void* stream);
+
+/* ---- a12: RAG progressive filter ---------------------------------------
+ * rag/search/engine.py:51-95 (progressive_hierarchical_search), :178-241
+ * (_filter_candidates_at_level), :243-287 (_apply_progressive_threshold),
+ * :1025-1051 (_compare_single_level_indices).
+ *
+ * Index rows are stored compact: idx [N, Lsum] float32, level l occupying
+ * columns [lvl_off[l], lvl_off[l] + lvl_w[l]); lvl_keff[l] <= lvl_w[l] bounds the
+ * non-zero prefix of every row and query of the level (columns beyond it are
+ * structurally zero because d >= D is padding).  lens [N, L] uint16 are the
+ * trailing-zero-stripped lengths (>= 1) written by hq_index_row_lengths.
+ *
+ * hq_filter_level scores ONE level for Q queries against N rows, restricted to
+ * rows alive in mask_in (bit `row` of the query's mask_stride uint32 words;
+ * NULL = all alive):
+ *   score = (cos(q[:m], c[:m]) + 1) / 2,  m = min(len_q, len_c), 0 if a norm is 0
+ * It writes scores [Q, N] (float32, -1 for dead rows), the tentative survivor
+ * mask (alive AND score >= thr) into mask_out, and per-query counts n_alive[q],
+ * n_pass[q] (both must be zeroed by the caller).
+ * hq_filter_select applies the ratio cut: cap[q] = max(1, int(n_alive[q]*ratio));
+ * queries with n_pass <= cap keep the tentative mask, the others keep exactly the
+ * cap best rows (score desc, ties -> lower row id) found by an exact radix select. */
+typedef struct hq_index_layout {
+    int32_t L;              /* number of levels (<= 8)              */
+    int32_t Lsum;           /* row pitch of idx in floats           */
+    int32_t lvl_off[8];
+    int32_t lvl_w[8];
+    int32_t lvl_keff[8];
+} hq_index_layout;
+
+int hq_index_row_lengths(const float* idx, int64_t N, const hq_index_layout* layout,
+                         uint16_t* lens, void* stream);
+int hq_filter_level(const float* idx, const uint16_t* lens, int64_t N, const hq_index_layout* layout, int level,
+                    const float* q_idx, const uint16_t* q_lens, int Q,
+                    const uint32_t* mask_in, int64_t mask_stride, double thr,
+                    float* scores, int64_t scores_stride, uint32_t* mask_out,
+                    int32_t* n_alive, int32_t* n_pass, void* stream);
+int hq_filter_select(const float* scores, int64_t scores_stride, int64_t N, int Q,
+                     const int32_t* n_alive, const int32_t* n_pass, double ratio,
+                     uint32_t* mask, int64_t mask_stride, int32_t* n_out, void* stream);
+
+/* ---- a13/a15: cosine rerank + top-k --------------------------------------
+ * rag/search/engine.py:622-660 (_calculate_embedding_cosine_similarity),
+ * :512 / :778-781 (stable descending sort, first k).
+ * score = (dot(q, c) / (|q| |c|) + 1) / 2, 0 if a norm is 0.  Rows dead in
+ * `mask` are skipped.  Ties -> lower row id.  ids are int64 row ids + id_base
+ * (-1 = no result), scores float32.
+ *   hq_rerank_scores_f32 : exact fp32 FMA scores [Q, N] (-1 for dead rows)
+ *   hq_topk_from_scores  : per-query top-k of a score matrix
+ *   hq_rerank_topk_f32   : the two above through `scratch` (Q*N floats)            */
+int hq_row_norms(const float* x, int64_t N, int64_t D, int64_t stride, float* norms, void* stream);
+int hq_rerank_scores_f32(const float* db, const float* db_norm, int64_t N, int64_t D, int64_t db_stride,
+                         const float* q, const float* q_norm, int Q, int64_t q_stride,
+                         const uint32_t* mask, int64_t mask_stride,
+                         float* scores, int64_t scores_stride, void* stream);
+int hq_topk_from_scores(const float* scores, int64_t scores_stride, int64_t N, int Q, int k, int64_t id_base,
+                        int64_t* ids, float* out_scores, void* stream);
+int64_t hq_rerank_scratch_bytes(int64_t N, int Q);
+int hq_rerank_topk_f32(const float* db, const float* db_norm, int64_t N, int64_t D, int64_t db_stride,
+                       const float* q, const float* q_norm, int Q, int64_t q_stride,
+                       const uint32_t* mask, int64_t mask_stride, int k, int64_t id_base,
+                       int64_t* ids, float* scores, void* scratch, int64_t scratch_bytes, void* stream);
+
+/* ---- a15 multi-GPU: merge of per-shard top-k ---------------------------
+ * in_ids/in_scores [P, Q, k] (all-gathered) -> out [Q, k]; ties -> lower id;
+ * entries with id < 0 are empty. */
+int hq_topk_merge(const int64_t* in_ids, const float* in_scores, int P, int Q, int k,
+                  int64_t* out_ids, float* out_scores, void* stream);
+
+/* ---- a11: core progressive search, per-level similarity ------------------
+ * core/search_engine.py:111-189 (compare_indices_at_level): sims [N, n_levels]
+ * float64; level l compares q[q_start[l] : +lvl_len[l]] with
+ * cand[row, c_start[l] : +lvl_len[l]] (lvl_len = common length of the level). */
+int hq_core_level_sims(const double* cand, int64_t N, int S, int64_t cand_stride, const double* q,
+                       const int32_t* q_start, const int32_t* c_start, const int32_t* lvl_len, int n_levels,
+                       double* sims, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HQ_B200_H */

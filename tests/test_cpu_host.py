@@ -1,0 +1,167 @@
+"""CPU suite: host logic, planning, the C-ABI surface (load + exported symbols, no compute),
+and the multi-rank merge path over gloo."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import hilbert_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    from hilbert_quantization_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "hq_b200.h")).read()
+    declared = set(re.findall(r"\b(hq_[a-z0-9_]+)\s*\(", header))
+    declared -= {"hq_index_layout"}
+    assert len(declared) >= 24
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/hq_b200.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert _lib.lib.hq_version() == 1
+    assert isinstance(_lib.last_error(), str)
+
+
+def test_argument_validation_without_gpu():
+    """HQ_EINVAL paths return before any CUDA call, so they are checkable on the CPU box."""
+    from hilbert_quantization_b200._lib import lib, last_error, HQ_EINVAL
+    assert lib.hq_d2xy_batch(3, 0, 1, None, None, None) == HQ_EINVAL and "power of 2" in last_error()
+    assert lib.hq_map_to_2d(None, 1, 20, 20, 4, 4, None, 16, None) == HQ_EINVAL and "Too many parameters" in last_error()
+    assert lib.hq_map_to_2d(None, 1, 4, 4, 4, 3, None, 16, None) == HQ_EINVAL
+    assert lib.hq_topk_from_scores(None, 0, 0, 1, 0, 0, None, None, None) == HQ_EINVAL
+
+
+def test_product_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import hilbert_quantization_b200 as hq
+    with pytest.raises(hq.HQLibraryError, match="no CPU fallback"):
+        hq.HilbertCurveMapper().map_to_2d(np.arange(4, dtype=np.float32), (2, 2))
+    with pytest.raises(hq.HQLibraryError):
+        hq.EmbeddingDatabase(np.zeros((4, 16), dtype=np.float32))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "hilbert_quantization_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def _emulate(img, plan, mode):
+    """CPU model of the kernel's pyramid + gather (fp32 pairwise tree / fp64 strict)."""
+    stream = O.map_from_2d(img)
+    cur = stream.astype(np.float64 if mode else np.float32)
+    levels = []
+    while len(cur) >= 4:
+        g = cur.reshape(-1, 4)
+        if mode:
+            cur = (((g[:, 0] + g[:, 1]) + g[:, 2]) + g[:, 3]) * 0.25
+        else:
+            cur = (((g[:, 0] + g[:, 1]) + (g[:, 2] + g[:, 3])) * np.float32(0.25)).astype(np.float32)
+        levels.append(cur)
+    addr = np.concatenate([img.reshape(-1).astype(np.float64)] + [l.astype(np.float64) for l in levels])
+    return np.where(plan >= 0, addr[np.maximum(plan, 0)], 0.0)
+
+
+@pytest.mark.parametrize("n,D", [(4, 16), (8, 50), (16, 200), (32, 768), (64, 1536), (128, 16384)])
+def test_gather_plans_reproduce_the_oracle(n, D):
+    from hilbert_quantization_b200 import plans as P
+    rng = np.random.default_rng(n)
+    img = O.map_to_2d(rng.standard_normal(D).astype(np.float32), (n, n))
+    plan, widths, ml = P.c_plan(n, "compact")
+    assert widths == [min(g * g, n) for g in O.c_granularity_levels(n)]
+    assert np.abs(_emulate(img, plan, 0) - O.index_c_batch_compact(img[None])[0]).max() <= 2e-7
+    rows_plan, _, _ = P.c_plan(n, "rows")
+    assert np.abs(_emulate(img, rows_plan, 0).reshape(-1, n) - O.index_c(img)[n:]).max() <= 2e-7
+    for S in (n, 7, 100, 1024):
+        pb, _ = P.b_plan(n, S)
+        assert np.array_equal(_emulate(img, pb, 1), O.index_b(img, S))            # bit exact
+        pa, _ = P.a_plan(n, S)
+        assert np.abs(_emulate(img, pa, 0) - O.index_a(img, S)).max() <= 2e-7
+    assert P.a_allocation(64) == O.a_level_allocation(64)
+    assert P.core_levels(64, 64) == O.core_parse_levels(64, 64)
+
+
+def test_host_planning_matches_oracle_scalars():
+    from hilbert_quantization_b200 import plans as P
+    from hilbert_quantization_b200.dimension import PowerOf4DimensionCalculator, rag_optimal_dimensions
+    from hilbert_quantization_b200.search import make_layout, rag_ratio, rag_threshold
+    calc = PowerOf4DimensionCalculator()
+    for c in (1, 4, 5, 768, 1024, 1025, 1536, 4096, 16385, 16777216):
+        assert calc.calculate_optimal_dimensions(c) == O.optimal_dimensions(c)
+        assert rag_optimal_dimensions(c) == O.rag_optimal_dimensions(c)
+    with pytest.raises(ValueError, match="below minimum"):
+        calc.calculate_padding_strategy(1536, (64, 64))
+    assert calc.calculate_padding_strategy(768, (32, 32)).efficiency_ratio == 0.75
+    with pytest.raises(ValueError, match="must be positive"):
+        calc.calculate_optimal_dimensions(0)
+    for w in (2, 4, 8, 16, 32, 64, 100, 128, 1024, 4096):
+        assert P.c_levels(w) == O.c_granularity_levels(w)
+    for l in range(6):
+        assert rag_threshold(l) == O.rag_threshold(l) and rag_ratio(l) == O.rag_ratio(l)
+    for n in (2, 4, 8, 16, 32, 64):
+        d = np.arange(n * n)
+        x, y = P._d2xy(n, d)
+        ox, oy = O.d2xy(n, d)
+        assert np.array_equal(x, ox) and np.array_equal(y, oy) and np.array_equal(P._xy2d(n, x, y), d)
+    lay, levels = make_layout(64, 1536)
+    assert levels == [8, 4, 2] and lay.Lsum == 84 and list(lay.lvl_keff)[:3] == [24, 6, 4]
+    lay, _ = make_layout(32, 768)
+    assert lay.Lsum == 20 and list(lay.lvl_keff)[:2] == [12, 4]
+    lay, _ = make_layout(32, 200)
+    assert list(lay.lvl_keff)[:2] == [4, 1]
+
+
+def test_shard_bounds_cover_rows():
+    from hilbert_quantization_b200.distributed import shard_bounds
+    for total, world in ((100, 8), (7, 8), (1000000, 3), (0, 2)):
+        spans = [shard_bounds(total, world, r) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+_WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from hilbert_quantization_b200.distributed import allgather_merge, shard_bounds, merge_topk_host
+from oracle import hilbert_oracle as O
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{sys.argv[2]}", rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+rng = np.random.default_rng(0)
+N, D, Q, k = 400, 64, 6, 5
+db = rng.standard_normal((N, D)).astype(np.float32); db[300] = db[10]
+qs = rng.standard_normal((Q, D)).astype(np.float32); qs[0] = db[10]
+lo, hi = shard_bounds(N, 2, rank)
+ids = np.full((Q, k), -1, dtype=np.int64); sc = np.full((Q, k), -1, dtype=np.float32)
+for j in range(Q):                        # local exact top-k stands in for the device shard
+    i, s = O.topk_stable(np.arange(lo, hi), O.cosine01(qs[j], db[lo:hi]), k)
+    ids[j, :len(i)] = i; sc[j, :len(i)] = s.astype(np.float32)
+gi, gs = allgather_merge(torch.from_numpy(ids), torch.from_numpy(sc), k, merge_on_host=True)
+for j in range(Q):
+    i, s = O.topk_stable(np.arange(N), O.cosine01(qs[j], db).astype(np.float32), k)
+    assert list(gi[j].numpy()) == list(i), (rank, j, gi[j], i)
+assert list(gi[0][:2].numpy()) == [10, 300]
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_two_rank_merge_over_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)

@@ -1,0 +1,429 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle and the fixtures
+frozen from the real reference.  Bit-exact for coordinates, permutations, uint8 frames and
+variant-B indices; float tolerances are written next to each assertion."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import hilbert_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hq():
+    import hilbert_quantization_b200 as m
+    return m
+
+
+def dev_t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ------------------------------------------------------------------ a1/a2 coordinates
+@pytest.mark.parametrize("n", [1, 2, 4, 8, 16, 32, 64, 128])
+def test_coordinates_bit_exact(hq, n):
+    m = hq.HilbertCurveMapper()
+    got = m.generate_hilbert_coordinates(n)
+    assert isinstance(got, list) and isinstance(got[0], tuple)
+    want = load_golden("coords.npz")[f"xy_n{n}"]
+    assert got == [tuple(r) for r in want.tolist()]
+    assert hq.HilbertCurveMapperImpl(None).generate_hilbert_coordinates(n) == got
+
+
+def test_coordinates_large_and_inverse(hq):
+    m = hq.HilbertCurveMapper()
+    for n in (256, 1024, 4096):
+        x, y = m._coords_device(n)
+        d = torch.arange(n * n, device="cuda")
+        # inverse on device, bit exact
+        from hilbert_quantization_b200._lib import lib, check
+        from hilbert_quantization_b200 import _device as dv
+        out = torch.empty(n * n, dtype=torch.int64, device="cuda")
+        check(lib.hq_xy2d_batch(n, dv.ptr(x), dv.ptr(y), n * n, dv.ptr(out), dv.stream_ptr()))
+        assert torch.equal(out, d)
+        # sample against the oracle
+        idx = np.random.default_rng(n).integers(0, n * n, 5000)
+        ox, oy = O.d2xy(n, idx)
+        assert np.array_equal(x.cpu().numpy()[idx], ox) and np.array_equal(y.cpu().numpy()[idx], oy)
+        # consecutive positions are 4-neighbours (curve continuity)
+        dx = (x[1:] - x[:-1]).abs() + (y[1:] - y[:-1]).abs()
+        assert int(dx.max()) == 1 and int(dx.min()) == 1
+    assert m._hilbert_index_to_xy(5, 4) == tuple(int(v[0]) for v in O.d2xy(4, [5]))
+    assert m._xy_to_hilbert_index(3, 2, 8) == int(O.xy2d(8, [3], [2])[0])
+
+
+def test_coordinate_errors(hq):
+    with pytest.raises(hq.HilbertQuantizationError, match="must be a power of 2"):
+        hq.HilbertCurveMapper().generate_hilbert_coordinates(3)
+    with pytest.raises(ValueError, match="must be a power of 2"):
+        hq.HilbertCurveMapperImpl(None).generate_hilbert_coordinates(6)
+
+
+# ------------------------------------------------------------------ a3/a4 map / unmap
+def test_map_unmap_golden(hq):
+    g = load_golden("maps.npz")
+    m, r = hq.HilbertCurveMapper(), hq.HilbertCurveMapperImpl(None)
+    for key in [k[3:] for k in g.files if k.startswith("in_")]:
+        n = int(key.split("_")[0][1:])
+        p = g[f"in_{key}"]
+        img = m.map_to_2d(p, (n, n))
+        assert img.dtype == p.dtype and np.array_equal(img, g[f"map_to_2d_{key}"])
+        assert np.array_equal(r.map_to_2d(p, (n, n)), img)
+        back = m.map_from_2d(img)
+        assert back.dtype == p.dtype and np.array_equal(back, g[f"map_from_2d_{key}"])
+        assert np.array_equal(r.map_from_2d(img), back)
+    assert list(m.map_from_2d(g["golden_from_in"])) == [1, 2, 3, 4]
+    assert list(r.map_from_2d(g["golden_rag_from_in"])) == [1, 3, 4, 2]
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.int16, np.float16, np.int32, np.float32, np.int64, np.float64])
+@pytest.mark.parametrize("n,D", [(4, 16), (8, 37), (32, 768), (64, 1536), (128, 10000)])
+def test_map_unmap_dtypes(hq, dtype, n, D):
+    rng = np.random.default_rng(D)
+    p = (rng.standard_normal((3, D)) * 50).astype(dtype)
+    m = hq.HilbertCurveMapper()
+    words = np.ascontiguousarray(p).view({1: np.uint8, 2: np.int16, 4: np.int32, 8: np.int64}[p.dtype.itemsize])
+    grids = m.map_to_2d_batch(dev_t(words), n)
+    got = grids.cpu().numpy().view(dtype)
+    assert np.array_equal(got.view(np.uint8), O.map_to_2d_batch(p, n).view(np.uint8))
+    back = m.map_from_2d_batch(grids).cpu().numpy().view(dtype)
+    assert np.array_equal(back.view(np.uint8), O.map_from_2d_batch(O.map_to_2d_batch(p, n)).view(np.uint8))
+    trimmed = m.map_from_2d_batch(grids, length=D).cpu().numpy().view(dtype)
+    assert np.array_equal(trimmed.view(np.uint8), p.view(np.uint8))
+
+
+@pytest.mark.parametrize("n,D,N", [(4, 5, 300), (8, 64, 77), (16, 255, 50), (32, 1024, 1000), (64, 1536, 500),
+                                   (64, 4096, 33), (128, 16384, 3), (256, 40001, 2), (512, 262144, 1), (1024, 600000, 1)])
+def test_map_batch_fp32_bit_exact(hq, n, D, N):
+    rng = np.random.default_rng(n + D)
+    p = rng.standard_normal((N, D)).astype(np.float32)
+    m = hq.HilbertCurveMapper()
+    grids = m.map_to_2d_batch(dev_t(p), n)
+    want = O.map_to_2d_batch(p, n)
+    assert np.array_equal(grids.cpu().numpy(), want)
+    assert np.array_equal(m.map_from_2d_batch(grids).cpu().numpy(), O.map_from_2d_batch(want))
+    assert np.array_equal(m.map_from_2d_batch(grids, length=D).cpu().numpy(), p)
+
+
+def test_map_unaligned_rows(hq):
+    # row pitch not a multiple of 4 floats -> scalar access path
+    rng = np.random.default_rng(5)
+    p = rng.standard_normal((9, 1001)).astype(np.float32)
+    m = hq.HilbertCurveMapper()
+    grids = m.map_to_2d_batch(dev_t(p), 32)
+    assert np.array_equal(grids.cpu().numpy(), O.map_to_2d_batch(p, 32))
+    assert np.array_equal(m.map_from_2d_batch(grids, length=1001).cpu().numpy(), p)
+
+
+def test_round_trip_property_large(hq):
+    # SURVEY C3 shape (scaled down): 200k x 1024 -> 32x32 -> back, bitwise
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn((200_000, 1024), device="cuda", generator=g)
+    m = hq.HilbertCurveMapper()
+    back = m.map_from_2d_batch(m.map_to_2d_batch(x, 32))
+    assert torch.equal(back, x)
+
+
+def test_mapper_errors(hq):
+    m, r = hq.HilbertCurveMapper(), hq.HilbertCurveMapperImpl(None)
+    p = np.arange(5, dtype=np.float32)
+    with pytest.raises(hq.HilbertQuantizationError, match="requires square dimensions"):
+        m.map_to_2d(p, (4, 8))
+    with pytest.raises(hq.HilbertQuantizationError, match="must be a power of 2"):
+        m.map_to_2d(p, (3, 3))
+    with pytest.raises(hq.HilbertQuantizationError, match="Too many parameters"):
+        m.map_to_2d(np.arange(20, dtype=np.float32), (4, 4))
+    with pytest.raises(hq.HilbertQuantizationError, match="requires square dimensions"):
+        m.map_from_2d(np.zeros((4, 8), dtype=np.float32))
+    with pytest.raises(ValueError, match="Dimensions must be positive"):
+        r.map_to_2d(p, (0, 0))
+    with pytest.raises(ValueError, match="Input must be 2D array"):
+        r.map_from_2d(np.zeros(16, dtype=np.float32))
+    assert np.array_equal(r.map_to_2d(np.array([], dtype=np.float32), (4, 4)), np.zeros((4, 4), dtype=np.float32))
+
+
+# ------------------------------------------------------------------ a6/a7/a8 indices
+def test_index_golden(hq):
+    g = load_golden("index.npz")
+    a_gen = hq.HierarchicalIndexGeneratorImpl()
+    b_gen = hq.StreamingHilbertIndexGenerator()
+    c_gen = hq.HierarchicalIndexGenerator()
+    for key in [k[3:] for k in g.files if k.startswith("in_n")]:
+        n = int(key.split("_")[0][1:])
+        img = O.map_to_2d(g[f"in_{key}"], (n, n))
+        b = b_gen.generate_optimized_indices(img, n)
+        assert b.dtype == np.float64 and np.array_equal(b, g[f"B_{key}"])              # bit exact
+        a = a_gen.generate_optimized_indices(img, n)
+        assert a.dtype == np.float32 and np.abs(a - g[f"A_{key}"]).max() <= 3e-7        # fp32 tree vs numpy pairwise
+        c = c_gen.generate_multi_level_indices(img)
+        assert c.shape == g[f"C_{key}"].shape and c.dtype == np.float32
+        assert np.array_equal(c[:n], img) and np.abs(c - g[f"C_{key}"]).max() <= 3e-7
+    img = O.map_to_2d(g["in_n128_D16384"], (128, 128))
+    assert np.abs(a_gen.generate_optimized_indices(img, 1024) - g["A_S1024_n128"]).max() <= 3e-7
+    _, idx, stats = b_gen.generate_indices_during_mapping(g["B_during_mapping_in"], (32, 32), 32)
+    assert np.array_equal(idx, g["B_during_mapping_out"]) and stats["total_values_processed"] == 1000
+
+
+@pytest.mark.parametrize("n,D,N", [(4, 16, 600), (8, 50, 130), (16, 256, 70), (32, 768, 333), (32, 1024, 64),
+                                   (64, 1536, 257), (64, 4096, 9), (128, 9000, 5), (256, 65536, 2), (512, 200000, 1)])
+def test_fused_map_index_batch(hq, n, D, N):
+    rng = np.random.default_rng(n * 7 + D)
+    p = rng.standard_normal((N, D)).astype(np.float32)
+    grids_want = O.map_to_2d_batch(p, n)
+    t = dev_t(p)
+    # C compact + grid in one pass
+    grids, idx = hq.map_and_index(t, n, variant="C")
+    assert np.array_equal(grids.cpu().numpy(), grids_want)
+    want = O.index_c_batch_compact(grids_want)
+    assert idx.shape == want.shape
+    assert np.abs(idx.cpu().numpy() - want).max() <= 3e-7                              # fp32 tree means, N(0,1) data
+    # enhanced frames (grid + zero padded index rows)
+    frames, _ = hq.map_and_index(t, n, variant="C", enhanced=True)
+    fw = np.stack([O.index_c(gw) for gw in grids_want[: min(N, 8)]])
+    f = frames.cpu().numpy()
+    assert np.array_equal(f[:, :n], grids_want) and np.abs(f[: fw.shape[0]] - fw).max() <= 3e-7
+    # B (float64, bit exact) and A
+    for S in (n, 37):
+        _, b = hq.map_and_index(t, n, variant="B", index_space=S, want_grid=False)
+        bw = np.stack([O.index_b(gw, S) for gw in grids_want[: min(N, 6)]])
+        assert b.dtype == torch.float64 and np.array_equal(b.cpu().numpy()[: bw.shape[0]], bw)
+        _, a = hq.map_and_index(t, n, variant="A", index_space=S, want_grid=False)
+        aw = np.stack([O.index_a(gw, S) for gw in grids_want[: min(N, 6)]])
+        assert np.abs(a.cpu().numpy()[: aw.shape[0]] - aw).max() <= 3e-7
+    # from already-mapped grids (direction 1)
+    idx2 = hq.index_from_grids(grids, variant="C")
+    assert torch.equal(idx2, idx)
+
+
+def test_index_c_general_shapes(hq):
+    rng = np.random.default_rng(11)
+    c_gen = hq.HierarchicalIndexGenerator()
+    for shape in ((2, 2), (6, 10), (12, 12), (16, 32), (2, 4)):
+        img = rng.standard_normal(shape).astype(np.float32)
+        got = c_gen.generate_multi_level_indices(img)
+        want = O.index_c(img)
+        assert got.shape == want.shape and np.abs(got - want).max() <= 3e-7
+    quad = np.zeros((4, 4), dtype=np.float32)
+    quad[:2, :2], quad[:2, 2:], quad[2:, 2:], quad[2:, :2] = 2, 3, 4, 5
+    assert np.array_equal(c_gen._calculate_hilbert_order_averages(quad, 2), np.array([2, 3, 4, 5], dtype=np.float32))
+    ramp = np.arange(16, dtype=np.float32).reshape(4, 4)
+    assert np.allclose(hq.HierarchicalIndexGeneratorImpl().calculate_spatial_averages(ramp, 2), [2.5, 4.5, 10.5, 12.5])
+
+
+# ------------------------------------------------------------------ a10 uint8
+def test_quantize_bit_exact(hq):
+    g = load_golden("index.npz")
+    fq = hq.FrameQuantizer()
+    for key in [k[3:] for k in g.files if k.startswith("in_n")]:
+        enh = g[f"enhB_{key}"]
+        q = fq._normalize_for_compression(enh)
+        assert q.dtype == np.uint8 and np.array_equal(q, g[f"u8_{key}"])
+        assert np.array_equal(fq._denormalize_from_compression(q), g[f"deq_{key}"])
+    const = np.full((5, 4), 2.5, dtype=np.float32)
+    assert np.array_equal(hq.FrameQuantizer()._normalize_for_compression(const), np.full((5, 4), 128, dtype=np.uint8))
+
+
+def test_quantize_batch_and_large(hq):
+    rng = np.random.default_rng(2)
+    frames = (rng.standard_normal((300, 65, 64)) * 3).astype(np.float32)
+    frames[7] = 1.0
+    q, mm = hq.quantize_u8_batch(dev_t(frames))
+    qn, mmn = q.cpu().numpy(), mm.cpu().numpy()
+    for i in (0, 7, 150, 299):
+        want, mn, mx = O.normalize_u8(frames[i])
+        assert np.array_equal(qn[i], want) and mmn[i, 0] == mn and mmn[i, 1] == mx
+    deq = hq.dequantize_u8_batch(q, mm).cpu().numpy()
+    for i in (0, 7, 299):
+        _, mn, mx = O.normalize_u8(frames[i])
+        assert np.array_equal(deq[i], O.denormalize_u8(qn[i], mn, mx))
+    big = (rng.standard_normal((2, 513, 512)) * 2).astype(np.float32)       # multi-block path
+    q, mm = hq.quantize_u8_batch(dev_t(big))
+    for i in range(2):
+        want, mn, mx = O.normalize_u8(big[i])
+        assert np.array_equal(q[i].cpu().numpy(), want) and float(mm[i, 0]) == mn and float(mm[i, 1]) == mx
+
+
+# ------------------------------------------------------------------ a12/a13/a15 search
+def _oracle_rows(db, n):
+    levels = O.c_granularity_levels(n)
+    compact = O.index_c_batch_compact(O.map_to_2d_batch(db, n))
+    rows, o = [], 0
+    for gr in levels:
+        r = np.zeros((db.shape[0], n), dtype=np.float32)
+        r[:, : gr * gr] = compact[:, o:o + gr * gr]
+        rows.append(r)
+        o += gr * gr
+    return rows
+
+
+def _check_query(hq, db, rows, q, n, k, ids, scores, mask_row):
+    """Compare one query's device result with the oracle, tolerating only borderline cases."""
+    from hilbert_quantization_b200 import search as S
+    qc = O.index_c_batch_compact(O.map_to_2d_batch(q[None], n))[0]
+    q_rows, o = [], 0
+    for gr in O.c_granularity_levels(n):
+        r = np.zeros(n, dtype=np.float32)
+        r[: gr * gr] = qc[o:o + gr * gr]
+        q_rows.append(r)
+        o += gr * gr
+    surv, trace = O.rag_progressive_filter(q_rows, rows, return_scores=True)
+    got = set(np.nonzero(mask_row)[0].tolist())
+    diff = got ^ set(surv.tolist())
+    if diff:
+        # a differing row must sit within 2e-6 of a threshold or of the rank-cut score at some level
+        border = set()
+        for cand, s, thr, cap in trace:
+            border |= set(cand[np.abs(s - thr) < 2e-6].tolist())
+            if len(s) > cap:
+                cut = np.sort(s)[::-1][cap - 1]
+                border |= set(cand[np.abs(s - cut) < 2e-6].tolist())
+        assert diff <= border, f"{len(diff)} non-borderline filter differences"
+        return False
+    ids_w, sc_w = O.progressive_search(q, db, n, k, db_rows=rows)
+    m = len(ids_w)
+    assert list(ids[:m]) == list(ids_w) and all(i == -1 for i in ids[m:])
+    assert np.abs(scores[:m] - sc_w).max() < 5e-7                      # (cos+1)/2 in fp32 vs fp64 oracle
+    return True
+
+
+def test_search_golden(hq):
+    g = load_golden("rag_search.npz")
+    for tag in "abc":
+        db, qs, n = g[f"{tag}_db"], g[f"{tag}_queries"], int(g[f"{tag}_n"])
+        d = hq.EmbeddingDatabase(db, n=n)
+        ids, scores, mask = hq.search_batch(d, qs, 10, return_mask=True)
+        from hilbert_quantization_b200.search import unpack_mask
+        alive = unpack_mask(mask, db.shape[0])
+        ids, scores = ids.cpu().numpy(), scores.cpu().numpy()
+        for j in range(len(qs)):
+            want = g[f"{tag}_survivors_q{j}"]
+            assert set(np.nonzero(alive[j])[0].tolist()) == set(want.tolist())
+            kk = len(g[f"{tag}_topk_ids_q{j}"])
+            assert list(ids[j, :kk]) == list(g[f"{tag}_topk_ids_q{j}"])
+            assert np.abs(scores[j, :kk] - g[f"{tag}_topk_scores_q{j}"]).max() < 5e-7
+
+
+@pytest.mark.parametrize("n,D,N,Q", [(16, 256, 3000, 12), (32, 768, 5000, 20), (32, 1024, 4097, 9), (64, 1536, 6000, 16)])
+def test_search_vs_oracle(hq, n, D, N, Q):
+    from hilbert_quantization_b200.search import unpack_mask
+    rng = np.random.default_rng(N + D)
+    db = rng.standard_normal((N, D)).astype(np.float32)
+    db /= np.linalg.norm(db, axis=1, keepdims=True)
+    db[100] = db[50]                                                   # duplicates: tie -> lower id
+    db[N - 1] = db[50]
+    qs = []
+    for j in range(Q):
+        q = db[(j * 37) % N] + 0.1 * rng.standard_normal(D).astype(np.float32) if j % 2 == 0 else rng.standard_normal(D).astype(np.float32)
+        qs.append((q / np.linalg.norm(q)).astype(np.float32))
+    qs = np.stack(qs)
+    qs[2] = db[50]
+    d = hq.EmbeddingDatabase(db, n=n)
+    ids, scores, mask = hq.search_batch(d, qs, 10, return_mask=True)
+    alive = unpack_mask(mask, N)
+    ids, scores = ids.cpu().numpy(), scores.cpu().numpy()
+    rows = _oracle_rows(db, n)
+    exact = sum(_check_query(hq, db, rows, qs[j], n, 10, ids[j], scores[j], alive[j]) for j in range(Q))
+    assert exact >= Q - 1                                              # borderline survivor sets are rare
+    assert ids[2, 0] == 50 and list(ids[2, :3]) == [50, 100, N - 1]    # exact ties resolve to the lower id
+    for j in range(0, Q, 2):
+        if j != 2:
+            assert ids[j, 0] == (j * 37) % N                           # perturbed rows find their source
+
+
+def test_search_chunked_and_unfiltered(hq):
+    rng = np.random.default_rng(9)
+    db = rng.standard_normal((2000, 768)).astype(np.float32)
+    qs = rng.standard_normal((7, 768)).astype(np.float32)
+    d = hq.EmbeddingDatabase(db)
+    a = hq.search_batch(d, qs, 5)
+    b = hq.search_batch(d, qs, 5, work_bytes=3 * 4 * 2000)             # forces 3-query chunks
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    ids, scores = hq.search_batch(d, qs, 5, use_filter=False)
+    for j in range(7):
+        iw, sw = O.topk_stable(np.arange(2000), O.cosine01(qs[j], db), 5)
+        assert list(ids[j].cpu().numpy()) == list(iw) and np.abs(scores[j].cpu().numpy() - sw).max() < 5e-7
+
+
+def test_filter_ratio_cut_binds(hq):
+    # all-positive data: every row passes every threshold, so the ratio cut (exact radix select) decides
+    from hilbert_quantization_b200.search import unpack_mask
+    rng = np.random.default_rng(4)
+    N, D, n = 5000, 768, 32
+    db = (rng.random((N, D)) + 0.5).astype(np.float32)
+    db[10] = db[20]
+    qs = (rng.random((5, D)) + 0.5).astype(np.float32)
+    d = hq.EmbeddingDatabase(db, n=n)
+    ids, scores, mask = hq.search_batch(d, qs, 10, return_mask=True)
+    alive = unpack_mask(mask, N)
+    rows = _oracle_rows(db, n)
+    for j in range(5):
+        assert alive[j].sum() == max(1, int(max(1, int(N * 0.3)) * 0.5))
+        _check_query(hq, db, rows, qs[j], n, 10, ids[j].cpu().numpy(), scores[j].cpu().numpy(), alive[j])
+
+
+def test_rag_engine_surface(hq):
+    rng = np.random.default_rng(21)
+    n, D, N = 32, 768, 150
+    db = rng.standard_normal((N, D)).astype(np.float32)
+    frames = [O.index_c(O.map_to_2d(v, (n, n))) for v in db]
+    q = db[5] + 0.05 * rng.standard_normal(D).astype(np.float32)
+    qf = O.index_c(O.map_to_2d(q.astype(np.float32), (n, n)))
+    eng = hq.RAGSearchEngineImpl(None)
+    eng._get_all_candidate_embeddings = lambda: frames
+    got = eng.progressive_hierarchical_search(qf)
+    L = len(O.c_granularity_levels(n))
+    want = O.rag_progressive_filter([qf[n + l] for l in range(L)], [np.stack([f[n + l] for f in frames]) for l in range(L)])
+    assert got == list(want)
+    assert abs(eng._calculate_embedding_cosine_similarity(qf[:n], frames[5][:n]) - O.cosine01(q, db[5:6])[0]) < 5e-7
+    assert eng.progressive_hierarchical_search(np.array([])) == []
+
+
+def test_core_search_golden(hq):
+    g = load_golden("core_search.npz")
+
+    class M:
+        def __init__(self, idx, i):
+            self.hierarchical_indices, self.i = idx, i
+    for S in (32, 64):
+        c, q = g[f"S{S}_cands"], g[f"S{S}_query"]
+        eng = hq.ProgressiveSimilaritySearchEngine(similarity_threshold=0.1, max_candidates_per_level=20)
+        sims = eng._level_sims(q, list(c))
+        assert np.abs(sims - g[f"S{S}_level_sims"]).max() < 1e-12
+        res = eng.progressive_search(q, [M(c[i], i) for i in range(len(c))], 10)
+        assert [r.model.i for r in res] == list(g[f"S{S}_ids"])
+        assert np.abs(np.array([r.similarity_score for r in res]) - g[f"S{S}_scores"]).max() < 1e-12
+        assert abs(eng.compare_indices_at_level(q, c[3], 1) - g[f"S{S}_level_sims"][3, 1]) < 1e-12
+
+
+def test_topk_merge_kernel(hq):
+    from hilbert_quantization_b200._lib import lib, check
+    from hilbert_quantization_b200 import _device as dv
+    from hilbert_quantization_b200.distributed import merge_topk_host
+    rng = np.random.default_rng(8)
+    P, Q, k = 8, 50, 10
+    ids = rng.permutation(P * Q * k).reshape(P, Q, k).astype(np.int64)
+    sc = np.round(rng.random((P, Q, k)), 2).astype(np.float32)          # many exact ties
+    ids[3, :, 7:] = -1
+    ti, ts = dev_t(ids), dev_t(sc)
+    oi = torch.empty((Q, k), dtype=torch.int64, device="cuda")
+    os_ = torch.empty((Q, k), dtype=torch.float32, device="cuda")
+    check(lib.hq_topk_merge(dv.ptr(ti), dv.ptr(ts), P, Q, k, dv.ptr(oi), dv.ptr(os_), dv.stream_ptr()))
+    wi, ws = merge_topk_host(ids, sc, k)
+    assert np.array_equal(oi.cpu().numpy(), wi) and np.array_equal(os_.cpu().numpy(), ws)
+
+
+def test_readme_surface(hq):
+    rng = np.random.default_rng(1)
+    eng = hq.ProgressiveSearchEngine(use_frame_caching=True)
+    vecs = rng.standard_normal((200, 384)).astype(np.float32)
+    for i, v in enumerate(vecs):
+        eng.add_document({"document_id": f"doc{i}", "content": f"text {i}", "embedding": v})
+    res = eng.search(vecs[17] + 0.01 * rng.standard_normal(384).astype(np.float32), max_results=5)
+    assert res and res[0].document_id == "doc17" and 0.0 <= res[0].similarity_score <= 1.0001
+    rag = hq.RAGSystem(embedding_dimension=256)
+    rag.add_document("a", "hilbert curves preserve locality of reference")
+    rag.add_document("b", "completely different words about cooking pasta")
+    out = rag.search("locality of hilbert curves", max_results=2)
+    assert out and out[0].document_id == "a" and out[0].content.startswith("hilbert")
