@@ -21,6 +21,7 @@ SIGNATURES = {
     "hq_version": (_i32, []),
     "hq_last_error": (C.c_char_p, []),
     "hq_sm_count": (_i32, []),
+    "hq_launch_count": (_i64, [_i32]),
     "hq_d2xy_batch": (_i32, [_i32, _i64, _i64, _p, _p, _p]),
     "hq_xy2d_batch": (_i32, [_i32, _p, _p, _i64, _p, _p]),
     "hq_map_to_2d": (_i32, [_p, _i64, _i64, _i64, _i32, _i32, _p, _i64, _p]),

@@ -7,6 +7,7 @@
 #include "../../include/hq_b200.h"
 
 void hq_set_error(const char* fmt, ...);
+void hq_note_launch(int n);     // bookkeeping for hq_launch_count (bench.py reports it)
 
 #define HQ_REQUIRE(cond, ...)                         \
     do {                                              \
@@ -32,6 +33,7 @@ void hq_set_error(const char* fmt, ...);
             hq_set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));  \
             return HQ_ECUDA;                                                        \
         }                                                                           \
+        hq_note_launch(1);                                                          \
     } while (0)
 
 static inline bool hq_is_pow2(int64_t n) { return n > 0 && (n & (n - 1)) == 0; }

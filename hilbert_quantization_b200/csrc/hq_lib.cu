@@ -1,6 +1,7 @@
 // Library-level entry points: version, error text, device properties.
 #include "hq_common.cuh"
 #include <mutex>
+#include <atomic>
 
 static thread_local char g_err[512] = "";
 
@@ -23,6 +24,12 @@ int hq_cached_sm_count() {
         sms[dev] = v;
     }
     return sms[dev];
+}
+
+static std::atomic<long long> g_launches{0};
+void hq_note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" int64_t hq_launch_count(int reset) {
+    return reset ? g_launches.exchange(0, std::memory_order_relaxed) : g_launches.load(std::memory_order_relaxed);
 }
 
 extern "C" int hq_version(void) { return HQ_ABI_VERSION; }

@@ -166,6 +166,7 @@ extern "C" int hq_quantize_u8(const float* src, int64_t N, int64_t elems, int64_
     k_minmax_big<<<g, 256, 0, st>>>(src, elems, src_stride, keys);
     k_quant_big<<<g, 256, 0, st>>>(src, elems, src_stride, dst, dst_stride, keys);
     k_minmax_decode<<<(unsigned)((2 * N + 255) / 256), 256, 0, st>>>(keys, N);
+    hq_note_launch(3);
     HQ_LAUNCH_OK("k_quant_big");
     return HQ_OK;
 }

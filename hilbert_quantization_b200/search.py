@@ -20,6 +20,43 @@ from .dimension import rag_optimal_dimensions
 from .index import map_and_index
 
 
+class PhaseTimer:
+    """Optional CUDA-event timing of the phases of search_batch (bench.py installs one in
+    `PHASE_TIMER`; events are recorded on the stream the kernels are launched on)."""
+
+    def __init__(self):
+        self.events = []
+
+    def start(self, name):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream())
+        self.events.append((name, e0, e1))
+        return e1
+
+    @staticmethod
+    def stop(e1):
+        e1.record(torch.cuda.current_stream())
+
+    def totals_ms(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1 in self.events:
+            out[name] = out.get(name, 0.0) + e0.elapsed_time(e1)
+        return out
+
+
+PHASE_TIMER: Optional[PhaseTimer] = None
+
+
+def _phase(name):
+    return PHASE_TIMER.start(name) if PHASE_TIMER is not None else None
+
+
+def _end(tok):
+    if tok is not None:
+        PhaseTimer.stop(tok)
+
+
 def rag_threshold(level: int) -> float:
     """rag/search/engine.py:262-268"""
     base_threshold = 0.3
@@ -155,7 +192,9 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
 
     Returns (ids int64 [Q, k] (-1 = fewer than k survivors), scores float32 [Q, k]).  Scores are
     (cos + 1) / 2 of the full embeddings; ties resolve to the lower row id."""
+    tok = _phase("query_index")
     q, q_idx, q_lens, q_norms = prepare_queries(db, queries)
+    _end(tok)
     Q, N, d = q.shape[0], db.N, db.device
     ids = torch.empty((Q, k), dtype=torch.int64, device=d)
     out_scores = torch.empty((Q, k), dtype=torch.float32, device=d)
@@ -174,14 +213,20 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
             nq = e - s
             m = None
             if use_filter:
+                tok = _phase("filter")
                 m = progressive_filter(db, q_idx[s:e], q_lens[s:e], scores[:nq], mask[:nq], trace)
+                _end(tok)
                 if return_mask:
                     masks.append(m.clone())
-            check(lib.hq_rerank_topk_f32(dev.ptr(db.emb), dev.ptr(db.norms), N, db.D, db.emb.stride(0),
-                                         dev.ptr(q[s:e]), dev.ptr(q_norms[s:e]), nq, q.stride(0),
-                                         dev.ptr(m), mask.stride(0), k, db.id_base,
-                                         dev.ptr(ids[s:e]), dev.ptr(out_scores[s:e]),
-                                         dev.ptr(scores), scores.numel() * 4, dev.stream_ptr()))
+            tok = _phase("rerank_gemm")
+            check(lib.hq_rerank_scores_f32(dev.ptr(db.emb), dev.ptr(db.norms), N, db.D, db.emb.stride(0),
+                                           dev.ptr(q[s:e]), dev.ptr(q_norms[s:e]), nq, q.stride(0),
+                                           dev.ptr(m), mask.stride(0), dev.ptr(scores), scores.stride(0), dev.stream_ptr()))
+            _end(tok)
+            tok = _phase("topk")
+            check(lib.hq_topk_from_scores(dev.ptr(scores), scores.stride(0), N, nq, k, db.id_base,
+                                          dev.ptr(ids[s:e]), dev.ptr(out_scores[s:e]), dev.stream_ptr()))
+            _end(tok)
     if return_mask:
         return ids, out_scores, (torch.cat(masks) if masks else None)
     return ids, out_scores
@@ -206,8 +251,9 @@ def cosine01(a, b, device=None) -> float:
     ta = dev.f32_device(a[:m].reshape(1, m), d)
     tb = dev.f32_device(b[:m].reshape(1, m), d)
     out = torch.empty((1, 1), dtype=torch.float32, device=d)
+    nb, na = row_norms(tb), row_norms(ta)          # keep both alive until the kernel has run
     with torch.cuda.device(d):
-        check(lib.hq_rerank_scores_f32(dev.ptr(tb), dev.ptr(row_norms(tb)), 1, m, m, dev.ptr(ta), dev.ptr(row_norms(ta)),
+        check(lib.hq_rerank_scores_f32(dev.ptr(tb), dev.ptr(nb), 1, m, m, dev.ptr(ta), dev.ptr(na),
                                        1, m, None, 0, dev.ptr(out), 1, dev.stream_ptr()))
     return float(out.item())
 

@@ -35,6 +35,7 @@ extern "C" {
 int         hq_version(void);
 const char* hq_last_error(void);              /* thread-local, never NULL   */
 int         hq_sm_count(void);                /* SMs of the current device  */
+int64_t     hq_launch_count(int reset);       /* kernels launched by this library so far */
 
 /* ---- a1/a2: Hilbert coordinates ---------------------------------------
  * hilbert_quantization/core/hilbert_mapper.py:17-66 (generate_hilbert_coordinates,

@@ -315,7 +315,8 @@ def test_search_vs_oracle(hq, n, D, N, Q):
     db[N - 1] = db[50]
     qs = []
     for j in range(Q):
-        q = db[(j * 37) % N] + 0.1 * rng.standard_normal(D).astype(np.float32) if j % 2 == 0 else rng.standard_normal(D).astype(np.float32)
+        # near-duplicate of a stored row (noise norm 0.3) or a fresh random direction
+        q = db[(j * 37) % N] + (0.3 / np.sqrt(D)) * rng.standard_normal(D).astype(np.float32) if j % 2 == 0 else rng.standard_normal(D).astype(np.float32)
         qs.append((q / np.linalg.norm(q)).astype(np.float32))
     qs = np.stack(qs)
     qs[2] = db[50]
