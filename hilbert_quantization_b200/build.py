@@ -54,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(out)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
-    cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-lcudart", "-lcuda"]
+    cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-lcudart"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")

@@ -1,0 +1,513 @@
+// K6: tensor-core rerank.  scores = Q x N x D cosine contraction on tcgen05 (bf16 in, fp32
+// accumulate in TMEM) with the survivor mask and a streaming per-query top-k' fused into the
+// epilogue, followed by an exact fp32 re-score of the k' shortlisted rows.
+//
+//   warp 0      : TMA producer   (cp.async.bulk.tensor, 128B-swizzled K-major tiles, 4 stages)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (M=128 queries, N=256 rows, K=16)
+//   warps 2..5  : epilogue, one thread per query row: tcgen05.ld 32 columns at a time, apply
+//                 mask / 1/|c|, keep the best KP (value, row) pairs in registers
+// Work unit = (query tile of 128, contiguous range of 256-row tiles); units are laid out so
+// that neighbouring CTAs stream the same database rows at the same time (L2 reuse), the
+// query tile comes from L2.  Two TMEM accumulators (2 x 256 columns) overlap the epilogue of
+// tile i with the MMAs of tile i+1.
+#include "hq_common.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <float.h>
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int UMMA_K = 16;
+constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;      // 16 KB
+constexpr uint32_t B_STAGE_BYTES = BN * BK * 2;      // 32 KB
+constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int TC_THREADS = 192;
+constexpr uint32_t TMEM_COLS = 512;
+
+// ---- raw PTX wrappers ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1;\n\t"
+        "@P bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate));
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: 8-row atoms of 1024 B, SBO = 1024, version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);           // start address
+    d |= (uint64_t)0 << 16;                             // leading byte offset (unused: one atom along K)
+    d |= (uint64_t)(1024u >> 4) << 32;                  // stride byte offset between 8-row atoms
+    d |= (uint64_t)1 << 46;                             // descriptor version
+    d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+    return d;
+}
+constexpr uint32_t kIdesc = (1u << 4) /*D=f32*/ | (1u << 7) /*A=bf16*/ | (1u << 10) /*B=bf16*/ | ((uint32_t)(BN >> 3) << 17) |
+                            ((uint32_t)(BM >> 4) << 24);
+
+struct TcParams {
+    int64_t N;
+    int Q, D;
+    int m_tiles, n_tiles, n_ranges, tiles_per_range, num_units;
+    const float* db_norm;
+    const uint32_t* mask;
+    int64_t mask_stride;
+    float* part_val;      // [num_units][128][KP]
+    int32_t* part_idx;
+};
+
+template <int KP>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_rerank_tc(const __grid_constant__ CUtensorMap map_q,
+                                                            const __grid_constant__ CUtensorMap map_db, const TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 128B-swizzled tiles need 1024-byte alignment in the shared window
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+    float* s_inv = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);          // [2][BN]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_inv + 2 * BN);
+    uint64_t* full_bar = bars;                  // [STAGES]
+    uint64_t* empty_bar = bars + STAGES;        // [STAGES]
+    uint64_t* tfull_bar = bars + 2 * STAGES;    // [2]
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int k_blocks = (p.D + BK - 1) / BK;
+
+    if (warp == 0 && elect_one()) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_db)) : "memory");
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (elect_one()) {
+            uint32_t stage = 0, phase = 0;
+            for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+                const int m_tile = u % p.m_tiles, range = u / p.m_tiles;
+                const int t0 = range * p.tiles_per_range;
+                const int t1 = min(p.n_tiles, t0 + p.tiles_per_range);
+                for (int t = t0; t < t1; ++t) {
+                    for (int kb = 0; kb < k_blocks; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                        tma_load_2d(&map_q, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb * BK, m_tile * BM);
+                        tma_load_2d(&map_db, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BK, t * BN);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        uint32_t stage = 0, phase = 0, it = 0;
+        for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+            const int range = u / p.m_tiles;
+            const int t0 = range * p.tiles_per_range;
+            const int t1 = min(p.n_tiles, t0 + p.tiles_per_range);
+            for (int t = t0; t < t1; ++t, ++it) {
+                const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t da = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
+                        const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * B_STAGE_BYTES));
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            umma_bf16(tmem_base + acc * BN, da + (uint64_t)(k * UMMA_K * 2 >> 4), db + (uint64_t)(k * UMMA_K * 2 >> 4),
+                                      kIdesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        umma_commit(&empty_bar[stage]);                       // frees the smem slot when the MMAs retire
+                        if (kb == k_blocks - 1) umma_commit(&tfull_bar[acc]); // accumulator complete
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ================= epilogue: streaming top-KP per query row =================
+        const int ew = warp & 3;                         // TMEM lane quarter this warp may read
+        const int row_in_tile = ew * 32 + lane;
+        const int et = (warp - 2) * 32 + lane;           // 0..127 index among the epilogue threads
+        uint32_t it = 0;
+        for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+            const int m_tile = u % p.m_tiles, range = u / p.m_tiles;
+            const int t0 = range * p.tiles_per_range;
+            const int t1 = min(p.n_tiles, t0 + p.tiles_per_range);
+            const int q = m_tile * BM + row_in_tile;
+            const bool q_ok = q < p.Q;
+            float bv[KP];
+            int32_t bi[KP];
+#pragma unroll
+            for (int j = 0; j < KP; ++j) { bv[j] = -FLT_MAX; bi[j] = -1; }
+            for (int t = t0; t < t1; ++t, ++it) {
+                const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+                // 1/|c| of this tile's rows (0 marks a zero-norm or out-of-range row)
+                float* inv = s_inv + acc * BN;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int64_t r = (int64_t)t * BN + et + 128 * h;
+                    float v = 0.f;
+                    if (r < p.N) { const float nc = __ldg(p.db_norm + r); v = nc > 0.f ? 1.0f / nc : 0.f; }
+                    inv[et + 128 * h] = v;
+                }
+                uint32_t mw[8];
+#pragma unroll
+                for (int w = 0; w < 8; ++w) {
+                    uint32_t m = 0xffffffffu;
+                    const int64_t r0 = (int64_t)t * BN + 32 * w;
+                    if (!q_ok || r0 >= p.N) m = 0;
+                    else {
+                        if (p.mask) m = __ldg(p.mask + (int64_t)q * p.mask_stride + (r0 >> 5));
+                        if (r0 + 32 > p.N) m &= (1u << (uint32_t)(p.N - r0)) - 1u;
+                    }
+                    mw[w] = m;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+#pragma unroll
+                for (int w = 0; w < 8; ++w) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + 32 * w, r);
+                    tmem_ld_wait();
+                    const uint32_t m = mw[w];
+                    if (m != 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if ((m >> j) & 1u) {
+                                const float iv = inv[32 * w + j];
+                                const float v = iv > 0.f ? __uint_as_float(r[j]) * iv : -FLT_MAX * 0.5f;
+                                if (v > bv[KP - 1]) {
+                                    bv[KP - 1] = v;
+                                    bi[KP - 1] = t * BN + 32 * w + j;
+#pragma unroll
+                                    for (int s = KP - 1; s > 0; --s) {
+                                        if (bv[s] > bv[s - 1]) {
+                                            const float tv = bv[s]; bv[s] = bv[s - 1]; bv[s - 1] = tv;
+                                            const int32_t ti = bi[s]; bi[s] = bi[s - 1]; bi[s - 1] = ti;
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&tempty_bar[acc]);
+            }
+            if (q_ok) {
+                float* pv = p.part_val + ((int64_t)u * BM + row_in_tile) * KP;
+                int32_t* pi = p.part_idx + ((int64_t)u * BM + row_in_tile) * KP;
+#pragma unroll
+                for (int j = 0; j < KP; ++j) { pv[j] = bv[j]; pi[j] = bi[j]; }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    }
+}
+
+// merge the per-unit shortlists of one query, re-score the best KP exactly in fp32, emit top-k
+template <int KP>
+__global__ void __launch_bounds__(128) k_rerank_tc_merge(const TcParams p, const float* __restrict__ db_f32, int64_t db_stride,
+                                                         const float* __restrict__ q_f32, int64_t q_stride,
+                                                         const float* __restrict__ q_norm, int k, int64_t id_base,
+                                                         int64_t* __restrict__ ids, float* __restrict__ scores) {
+    extern __shared__ unsigned char sm[];
+    const int M = p.n_ranges * KP;
+    float* c_val = reinterpret_cast<float*>(sm);
+    int32_t* c_idx = reinterpret_cast<int32_t*>(c_val + M);
+    __shared__ float top_val[KP];
+    __shared__ int32_t top_idx[KP];
+    __shared__ float ex_val[KP];
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m_tile = q / BM, row = q % BM;
+    for (int e = tid; e < M; e += blockDim.x) {
+        const int r = e / KP, j = e - r * KP;
+        const int64_t u = (int64_t)r * p.m_tiles + m_tile;
+        c_val[e] = p.part_val[(u * BM + row) * KP + j];
+        c_idx[e] = p.part_idx[(u * BM + row) * KP + j];
+    }
+    if (tid < KP) { top_val[tid] = -FLT_MAX; top_idx[tid] = -1; }
+    __syncthreads();
+    for (int e = tid; e < M; e += blockDim.x) {
+        const int32_t id = c_idx[e];
+        if (id < 0) continue;
+        const float v = c_val[e];
+        int rank = 0;
+        for (int j = 0; j < M; ++j) {
+            const int32_t idj = c_idx[j];
+            if (idj < 0) continue;
+            const float vj = c_val[j];
+            rank += (vj > v || (vj == v && idj < id)) ? 1 : 0;
+        }
+        if (rank < KP) { top_val[rank] = v; top_idx[rank] = id; }
+    }
+    __syncthreads();
+    // exact fp32 cosine of the shortlisted rows (one warp per candidate)
+    const float nq = q_norm[q];
+    const float* qv = q_f32 + (int64_t)q * q_stride;
+    const bool vec = (p.D % 4 == 0) && (db_stride % 4 == 0) && (q_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(db_f32) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(q_f32) & 15) == 0);
+    for (int c = warp; c < KP; c += 4) {
+        const int32_t id = top_idx[c];
+        float s = -1.0f;
+        if (id >= 0) {
+            const float* rv = db_f32 + (int64_t)id * db_stride;
+            float acc = 0.f;
+            if (vec) {
+                for (int i = lane; i < p.D / 4; i += 32) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(qv) + i);
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(rv) + i);
+                    acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+                }
+            } else {
+                for (int i = lane; i < p.D; i += 32) acc = fmaf(__ldg(qv + i), __ldg(rv + i), acc);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            const float nc = __ldg(p.db_norm + id);
+            s = 0.f;
+            if (nq != 0.f && nc != 0.f) s = __fmul_rn(__fadd_rn(__fdiv_rn(acc, __fmul_rn(nq, nc)), 1.0f), 0.5f);
+        }
+        if (lane == 0) ex_val[c] = s;
+    }
+    __syncthreads();
+    if (tid < KP) {
+        const int32_t id = top_idx[tid];
+        const float v = ex_val[tid];
+        if (id >= 0) {
+            int rank = 0;
+            for (int j = 0; j < KP; ++j) {
+                const int32_t idj = top_idx[j];
+                if (idj < 0) continue;
+                rank += (ex_val[j] > v || (ex_val[j] == v && idj < id)) ? 1 : 0;
+            }
+            if (rank < k) { ids[(int64_t)q * k + rank] = (int64_t)id + id_base; scores[(int64_t)q * k + rank] = v; }
+        }
+    }
+    // fewer than k survivors: fill the tail
+    if (tid == 0) {
+        int cnt = 0;
+        for (int j = 0; j < KP; ++j) cnt += top_idx[j] >= 0 ? 1 : 0;
+        for (int j = cnt; j < k; ++j) { ids[(int64_t)q * k + j] = -1; scores[(int64_t)q * k + j] = -1.0f; }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_to_bf16(const float* __restrict__ src, int64_t N, int64_t D, int64_t src_stride,
+                                                 __nv_bfloat16* __restrict__ dst, int64_t dst_pitch) {
+    const int64_t total = N * dst_pitch;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / dst_pitch, c = i - r * dst_pitch;
+        dst[i] = __float2bfloat16_rn(c < D ? __ldg(src + r * src_stride + c) : 0.f);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// The driver entry point is resolved through the runtime so that the library has no link-time
+// dependency on libcuda.so (it must load on machines without a driver, e.g. for build checks).
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t pitch_elems, int box_rows) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) {
+        hq_set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return HQ_ECUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        hq_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return HQ_ECUDA;
+    }
+    return HQ_OK;
+}
+
+void plan_units(int64_t N, int Q, int sms, TcParams& p) {
+    p.m_tiles = (Q + BM - 1) / BM;
+    p.n_tiles = (int)((N + BN - 1) / BN);
+    int best_s = 1;
+    double best_eff = -1.0;
+    for (int waves = 1; waves <= 4; ++waves) {
+        int s = (waves * sms) / p.m_tiles;
+        if (s < 1) s = 1;
+        if (s > p.n_tiles) s = p.n_tiles;
+        const int tiles_per = (p.n_tiles + s - 1) / s;
+        s = (p.n_tiles + tiles_per - 1) / tiles_per;                 // ranges actually needed
+        const int units = s * p.m_tiles;
+        const int rounds = (units + sms - 1) / sms;
+        const double eff = (double)p.n_tiles * p.m_tiles / ((double)rounds * tiles_per * sms);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best_s = s; }
+    }
+    p.n_ranges = best_s;
+    p.tiles_per_range = (p.n_tiles + best_s - 1) / best_s;
+    p.n_ranges = (p.n_tiles + p.tiles_per_range - 1) / p.tiles_per_range;
+    p.num_units = p.n_ranges * p.m_tiles;
+}
+
+int pick_kp(int k) { return k <= 10 ? 16 : (k <= 20 ? 32 : 0); }
+
+template <int KP>
+int launch_tc(const CUtensorMap& mq, const CUtensorMap& mdb, const TcParams& p, const float* db_f32, int64_t db_stride,
+              const float* q_f32, int64_t q_stride, const float* q_norm, int k, int64_t id_base, int64_t* ids, float* scores,
+              cudaStream_t st) {
+    const size_t smem = STAGES * STAGE_BYTES + 2 * BN * sizeof(float) + (2 * STAGES + 4) * sizeof(uint64_t) + 16 + 1024;
+    static bool attr = false;
+    if (!attr) {
+        HQ_CUDA_OK(cudaFuncSetAttribute(k_rerank_tc<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    int grid = hq_cached_sm_count();
+    if (grid > p.num_units) grid = p.num_units;
+    k_rerank_tc<KP><<<grid, TC_THREADS, smem, st>>>(mq, mdb, p);
+    HQ_LAUNCH_OK("k_rerank_tc");
+    const size_t msm = (size_t)p.n_ranges * KP * 8;
+    if (msm > 48 * 1024) HQ_CUDA_OK(cudaFuncSetAttribute(k_rerank_tc_merge<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
+    k_rerank_tc_merge<KP><<<p.Q, 128, msm, st>>>(p, db_f32, db_stride, q_f32, q_stride, q_norm, k, id_base, ids, scores);
+    HQ_LAUNCH_OK("k_rerank_tc_merge");
+    return HQ_OK;
+}
+
+}  // namespace
+
+extern "C" int hq_to_bf16(const float* src, int64_t N, int64_t D, int64_t src_stride, void* dst, int64_t dst_pitch, void* stream) {
+    HQ_REQUIRE(N >= 0 && D > 0 && src_stride >= D && dst_pitch >= D, "bad shape");
+    if (N == 0) return HQ_OK;
+    HQ_REQUIRE(src && dst, "null pointer");
+    int64_t blocks = (N * dst_pitch + 255) / 256;
+    const int64_t cap = (int64_t)hq_cached_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    k_to_bf16<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, N, D, src_stride, (__nv_bfloat16*)dst, dst_pitch);
+    HQ_LAUNCH_OK("k_to_bf16");
+    return HQ_OK;
+}
+
+extern "C" int64_t hq_rerank_bf16_scratch_bytes(int64_t N, int Q, int k) {
+    const int kp = pick_kp(k);
+    if (kp == 0 || N <= 0 || Q <= 0) return 0;
+    TcParams p{};
+    plan_units(N, Q, hq_cached_sm_count(), p);
+    return (int64_t)p.num_units * BM * kp * 8;
+}
+
+extern "C" int hq_rerank_topk_bf16(const void* db_bf16, int64_t db_pitch, const float* db_f32, int64_t db_stride, const float* db_norm,
+                                   int64_t N, int64_t D, const void* q_bf16, int64_t q_pitch, const float* q_f32, int64_t q_stride,
+                                   const float* q_norm, int Q, const uint32_t* mask, int64_t mask_stride, int k, int64_t id_base,
+                                   int64_t* ids, float* scores, void* scratch, int64_t scratch_bytes, void* stream) {
+    HQ_REQUIRE(N >= 0 && Q >= 0 && D > 0, "bad shape");
+    const int kp = pick_kp(k);
+    HQ_REQUIRE(k >= 1 && kp != 0, "k must be in [1, 20] for the tensor-core rerank (got %d)", k);
+    if (Q == 0) return HQ_OK;
+    HQ_REQUIRE(ids && scores, "null output");
+    if (N == 0) return hq_topk_from_scores(nullptr, 0, 0, Q, k, id_base, ids, scores, stream);
+    HQ_REQUIRE(db_bf16 && db_f32 && db_norm && q_bf16 && q_f32 && q_norm, "null pointer");
+    HQ_REQUIRE(db_pitch % 8 == 0 && q_pitch % 8 == 0 && db_pitch >= D && q_pitch >= D, "bf16 row pitch must be a multiple of 8 and >= D");
+    HQ_REQUIRE((reinterpret_cast<uintptr_t>(db_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(q_bf16) & 15) == 0, "bf16 operands must be 16-byte aligned");
+    HQ_REQUIRE(N < ((int64_t)1 << 31), "N too large for one shard");
+    HQ_REQUIRE(!mask || mask_stride * 32 >= N, "mask stride too small");
+    TcParams p{};
+    p.N = N; p.Q = Q; p.D = (int)D; p.db_norm = db_norm; p.mask = mask; p.mask_stride = mask_stride;
+    plan_units(N, Q, hq_cached_sm_count(), p);
+    const int64_t need = (int64_t)p.num_units * BM * kp * 8;
+    HQ_REQUIRE(scratch && scratch_bytes >= need, "scratch too small: need %lld bytes", (long long)need);
+    p.part_val = reinterpret_cast<float*>(scratch);
+    p.part_idx = reinterpret_cast<int32_t*>(p.part_val + (int64_t)p.num_units * BM * kp);
+    CUtensorMap mq, mdb;
+    int rc = make_map(&mq, q_bf16, Q, D, q_pitch, BM);
+    if (rc != HQ_OK) return rc;
+    rc = make_map(&mdb, db_bf16, N, D, db_pitch, BN);
+    if (rc != HQ_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (kp == 16) return launch_tc<16>(mq, mdb, p, db_f32, db_stride, q_f32, q_stride, q_norm, k, id_base, ids, scores, st);
+    return launch_tc<32>(mq, mdb, p, db_f32, db_stride, q_f32, q_stride, q_norm, k, id_base, ids, scores, st);
+}

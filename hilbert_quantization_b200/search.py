@@ -96,7 +96,8 @@ class EmbeddingDatabase:
     and their stripped lengths.  Built by ONE fused map+index pass over the embeddings
     (the 2-D grids are produced only if `keep_grids`)."""
 
-    def __init__(self, embeddings, n: Optional[int] = None, device=None, keep_grids: bool = False, id_base: int = 0):
+    def __init__(self, embeddings, n: Optional[int] = None, device=None, keep_grids: bool = False, id_base: int = 0,
+                 bf16: bool = True):
         d = dev.require_cuda(device if device is not None else (embeddings.device if isinstance(embeddings, torch.Tensor)
                                                                  and embeddings.is_cuda else None))
         self.device = d
@@ -111,10 +112,21 @@ class EmbeddingDatabase:
         self.grids = grids if keep_grids else None
         self.lens = row_lengths(self.idx, self.layout)
         self.norms = row_norms(self.emb)
+        self.emb_bf16 = to_bf16(self.emb) if bf16 else None       # operand of the tensor-core rerank
 
     @property
     def num_levels(self) -> int:
         return int(self.layout.L)
+
+
+def to_bf16(x: torch.Tensor) -> torch.Tensor:
+    """float32 [N, D] -> bf16 [N, pitch] (round to nearest even, pitch = D rounded up to 8, zero padded)."""
+    N, D = x.shape
+    pitch = (D + 7) // 8 * 8
+    out = torch.empty((N, pitch), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.hq_to_bf16(dev.ptr(x), N, D, x.stride(0) if N else D, dev.ptr(out), pitch, dev.stream_ptr()))
+    return out
 
 
 def row_lengths(idx: torch.Tensor, layout: IndexLayout) -> torch.Tensor:
@@ -187,7 +199,8 @@ def prepare_queries(db: EmbeddingDatabase, queries) -> Tuple[torch.Tensor, torch
 
 
 def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: bool = True,
-                 work_bytes: int = 4 << 30, return_mask: bool = False, trace: Optional[FilterTrace] = None):
+                 work_bytes: int = 4 << 30, return_mask: bool = False, trace: Optional[FilterTrace] = None,
+                 rerank: str = "auto"):
     """Progressive top-k of a batch of query embeddings against one shard.
 
     Returns (ids int64 [Q, k] (-1 = fewer than k survivors), scores float32 [Q, k]).  Scores are
@@ -202,6 +215,17 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
         ids.fill_(-1)
         out_scores.fill_(-1.0)
         return (ids, out_scores, None) if return_mask else (ids, out_scores)
+    if rerank == "auto":
+        rerank = "bf16" if (db.emb_bf16 is not None and k <= 20) else "f32"
+    if rerank not in ("bf16", "f32"):
+        raise ValueError("rerank must be 'auto', 'bf16' or 'f32'")
+    if rerank == "bf16" and (db.emb_bf16 is None or k > 20):
+        raise ValueError("the tensor-core rerank needs a bf16 database copy and k <= 20")
+    q_bf16 = None
+    if rerank == "bf16":
+        tok = _phase("query_index")
+        q_bf16 = to_bf16(q)
+        _end(tok)
     words = _mask_words(N)
     qc = int(max(1, min(Q, work_bytes // (4 * N))))
     scores = torch.empty((qc, N), dtype=torch.float32, device=d)
@@ -218,6 +242,17 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
                 _end(tok)
                 if return_mask:
                     masks.append(m.clone())
+            if rerank == "bf16":
+                tok = _phase("rerank_gemm")
+                sb = int(lib.hq_rerank_bf16_scratch_bytes(N, nq, k))
+                scratch = torch.empty(sb, dtype=torch.uint8, device=d)
+                check(lib.hq_rerank_topk_bf16(dev.ptr(db.emb_bf16), db.emb_bf16.stride(0), dev.ptr(db.emb), db.emb.stride(0),
+                                              dev.ptr(db.norms), N, db.D, dev.ptr(q_bf16[s:e]), q_bf16.stride(0),
+                                              dev.ptr(q[s:e]), q.stride(0), dev.ptr(q_norms[s:e]), nq,
+                                              dev.ptr(m), mask.stride(0), k, db.id_base,
+                                              dev.ptr(ids[s:e]), dev.ptr(out_scores[s:e]), dev.ptr(scratch), sb, dev.stream_ptr()))
+                _end(tok)
+                continue
             tok = _phase("rerank_gemm")
             check(lib.hq_rerank_scores_f32(dev.ptr(db.emb), dev.ptr(db.norms), N, db.D, db.emb.stride(0),
                                            dev.ptr(q[s:e]), dev.ptr(q_norms[s:e]), nq, q.stride(0),

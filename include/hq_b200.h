@@ -169,6 +169,20 @@ int hq_rerank_topk_f32(const float* db, const float* db_norm, int64_t N, int64_t
                        const uint32_t* mask, int64_t mask_stride, int k, int64_t id_base,
                        int64_t* ids, float* scores, void* scratch, int64_t scratch_bytes, void* stream);
 
+/* Tensor-core rerank (the one true dense GEMM of the path): bf16 tcgen05 contraction with
+ * the survivor mask and a streaming top-k' (k' = 16 for k <= 10, 32 for k <= 20) fused
+ * into the epilogue, then an exact fp32 re-score of the k' shortlisted rows from db_f32,
+ * so the returned scores are the same fp32 (cos+1)/2 values as the exact path.
+ * db_bf16 / q_bf16: row-major bf16 copies (hq_to_bf16), row pitch a multiple of 8. */
+int hq_to_bf16(const float* src, int64_t N, int64_t D, int64_t src_stride, void* dst, int64_t dst_pitch, void* stream);
+int64_t hq_rerank_bf16_scratch_bytes(int64_t N, int Q, int k);
+int hq_rerank_topk_bf16(const void* db_bf16, int64_t db_pitch, const float* db_f32, int64_t db_stride,
+                        const float* db_norm, int64_t N, int64_t D,
+                        const void* q_bf16, int64_t q_pitch, const float* q_f32, int64_t q_stride,
+                        const float* q_norm, int Q, const uint32_t* mask, int64_t mask_stride,
+                        int k, int64_t id_base, int64_t* ids, float* scores,
+                        void* scratch, int64_t scratch_bytes, void* stream);
+
 /* ---- a15 multi-GPU: merge of per-shard top-k ---------------------------
  * in_ids/in_scores [P, Q, k] (all-gathered) -> out [Q, k]; ties -> lower id;
  * entries with id < 0 are empty. */

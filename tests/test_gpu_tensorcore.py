@@ -1,0 +1,55 @@
+"""GPU: the tcgen05 rerank (bf16 shortlist + exact fp32 re-score) against the exact fp32 path
+and the oracle.  Returned scores are fp32-exact, so ids must match and scores agree to 1e-6."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import hilbert_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hq():
+    import hilbert_quantization_b200 as m
+    return m
+
+
+@pytest.mark.parametrize("N,D,Q,k", [(1000, 768, 5, 10), (4096, 1536, 128, 10), (5000, 1536, 130, 10), (777, 256, 33, 5),
+                                     (20000, 1024, 300, 10), (3000, 1000, 17, 20), (256, 64, 1, 10), (300, 1536, 4, 10)])
+def test_tc_rerank_matches_exact_path(hq, N, D, Q, k):
+    rng = np.random.default_rng(N + D + Q)
+    db = rng.standard_normal((N, D)).astype(np.float32)
+    db[N // 2] = db[3]
+    db[7] = 0.0                                                 # zero-norm row
+    qs = rng.standard_normal((Q, D)).astype(np.float32)
+    qs[0] = db[3]
+    d = hq.EmbeddingDatabase(db)
+    for use_filter in (False, True):
+        i32, s32 = hq.search_batch(d, qs, k, use_filter=use_filter, rerank="f32")
+        itc, stc = hq.search_batch(d, qs, k, use_filter=use_filter, rerank="bf16")
+        assert torch.equal(itc, i32), (use_filter, (itc != i32).sum().item())
+        valid = i32 >= 0
+        assert (stc[valid] - s32[valid]).abs().max().item() <= 1e-6
+        assert torch.equal(stc[~valid], s32[~valid])
+    assert itc[0, 0].item() == 3 and itc[0, 1].item() == N // 2     # exact ties resolve to the lower id
+    iu, su = hq.search_batch(d, qs[: min(Q, 4)], k, use_filter=False, rerank="bf16")
+    for j in range(min(Q, 4)):
+        iw, sw = O.topk_stable(np.arange(N), O.cosine01(qs[j], db), k)
+        assert list(iu[j].cpu().numpy()) == list(iw)
+        assert np.abs(su[j].cpu().numpy() - sw).max() < 5e-7
+
+
+def test_tc_rerank_sharded_id_base(hq):
+    rng = np.random.default_rng(3)
+    db = rng.standard_normal((2048, 512)).astype(np.float32)
+    qs = rng.standard_normal((9, 512)).astype(np.float32)
+    full = hq.EmbeddingDatabase(db)
+    a = hq.EmbeddingDatabase(db[:1000], id_base=0)
+    b = hq.EmbeddingDatabase(db[1000:], id_base=1000)
+    ia, sa = hq.search_batch(a, qs, 10, use_filter=False)
+    ib, sb = hq.search_batch(b, qs, 10, use_filter=False)
+    from hilbert_quantization_b200.distributed import merge_topk_host
+    mi, ms = merge_topk_host(np.stack([ia.cpu().numpy(), ib.cpu().numpy()]), np.stack([sa.cpu().numpy(), sb.cpu().numpy()]), 10)
+    fi, fs = hq.search_batch(full, qs, 10, use_filter=False)
+    assert np.array_equal(mi, fi.cpu().numpy())
