@@ -116,7 +116,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rerank_tc(const __grid_consta
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
     float* s_inv = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);          // [2][BN]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_inv + 2 * BN);
+    float* s_vals = s_inv + 2 * BN;                                                // [32][128] spill column per epilogue thread
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_vals + 32 * 128);             // [8][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_mask + 8 * 128);
     uint64_t* full_bar = bars;                  // [STAGES]
     uint64_t* empty_bar = bars + STAGES;        // [STAGES]
     uint64_t* tfull_bar = bars + 2 * STAGES;    // [2]
@@ -193,6 +195,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rerank_tc(const __grid_consta
         }
     } else {
         // ================= epilogue: streaming top-KP per query row =================
+        // Code size matters here (the first version unrolled 256 insertion sites into 1.3 MB
+        // of SASS and ran at 6 % tensor utilisation out of the instruction cache): the column
+        // loop is rolled, each 32-column chunk computes a hit mask against the thread's current
+        // k'-th best, and only chunks with hits spill their values to a private shared-memory
+        // column and walk the set bits through ONE insertion site.
         const int ew = warp & 3;                         // TMEM lane quarter this warp may read
         const int row_in_tile = ew * 32 + lane;
         const int et = (warp - 2) * 32 + lane;           // 0..127 index among the epilogue threads
@@ -207,6 +214,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rerank_tc(const __grid_consta
             int32_t bi[KP];
 #pragma unroll
             for (int j = 0; j < KP; ++j) { bv[j] = -FLT_MAX; bi[j] = -1; }
+            float thr = -FLT_MAX;
             for (int t = t0; t < t1; ++t, ++it) {
                 const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
                 // 1/|c| of this tile's rows (0 marks a zero-norm or out-of-range row)
@@ -218,7 +226,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rerank_tc(const __grid_consta
                     if (r < p.N) { const float nc = __ldg(p.db_norm + r); v = nc > 0.f ? 1.0f / nc : 0.f; }
                     inv[et + 128 * h] = v;
                 }
-                uint32_t mw[8];
 #pragma unroll
                 for (int w = 0; w < 8; ++w) {
                     uint32_t m = 0xffffffffu;
@@ -228,36 +235,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rerank_tc(const __grid_consta
                         if (p.mask) m = __ldg(p.mask + (int64_t)q * p.mask_stride + (r0 >> 5));
                         if (r0 + 32 > p.N) m &= (1u << (uint32_t)(p.N - r0)) - 1u;
                     }
-                    mw[w] = m;
+                    s_mask[w * 128 + et] = m;            // thread-private slot, read back below
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
-#pragma unroll
+#pragma unroll 1
                 for (int w = 0; w < 8; ++w) {
                     uint32_t r[32];
                     tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + 32 * w, r);
                     tmem_ld_wait();
-                    const uint32_t m = mw[w];
-                    if (m != 0) {
+                    const uint32_t m = s_mask[w * 128 + et];
+                    uint32_t hits = 0;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if ((m >> j) & 1u) {
-                                const float iv = inv[32 * w + j];
-                                const float v = iv > 0.f ? __uint_as_float(r[j]) * iv : -FLT_MAX * 0.5f;
-                                if (v > bv[KP - 1]) {
-                                    bv[KP - 1] = v;
-                                    bi[KP - 1] = t * BN + 32 * w + j;
+                    for (int j = 0; j < 32; ++j) {
+                        const float iv = inv[32 * w + j];
+                        const float v = iv > 0.f ? __uint_as_float(r[j]) * iv : -FLT_MAX * 0.5f;
+                        r[j] = __float_as_uint(v);
+                        hits |= (v > thr ? 1u : 0u) << j;
+                    }
+                    hits &= m;
+                    if (hits) {
 #pragma unroll
-                                    for (int s = KP - 1; s > 0; --s) {
-                                        if (bv[s] > bv[s - 1]) {
-                                            const float tv = bv[s]; bv[s] = bv[s - 1]; bv[s - 1] = tv;
-                                            const int32_t ti = bi[s]; bi[s] = bi[s - 1]; bi[s - 1] = ti;
-                                        }
+                        for (int j = 0; j < 32; ++j) s_vals[j * 128 + et] = __uint_as_float(r[j]);
+                        while (hits) {
+                            const int j = __ffs(hits) - 1;
+                            hits &= hits - 1;
+                            const float v = s_vals[j * 128 + et];
+                            if (v > bv[KP - 1]) {
+                                bv[KP - 1] = v;
+                                bi[KP - 1] = t * BN + 32 * w + j;
+#pragma unroll
+                                for (int s = KP - 1; s > 0; --s) {
+                                    if (bv[s] > bv[s - 1]) {
+                                        const float tv = bv[s]; bv[s] = bv[s - 1]; bv[s - 1] = tv;
+                                        const int32_t ti = bi[s]; bi[s] = bi[s - 1]; bi[s - 1] = ti;
                                     }
                                 }
                             }
                         }
+                        thr = bv[KP - 1];
                     }
                 }
                 tc_fence_before();
@@ -441,7 +458,7 @@ template <int KP>
 int launch_tc(const CUtensorMap& mq, const CUtensorMap& mdb, const TcParams& p, const float* db_f32, int64_t db_stride,
               const float* q_f32, int64_t q_stride, const float* q_norm, int k, int64_t id_base, int64_t* ids, float* scores,
               cudaStream_t st) {
-    const size_t smem = STAGES * STAGE_BYTES + 2 * BN * sizeof(float) + (2 * STAGES + 4) * sizeof(uint64_t) + 16 + 1024;
+    const size_t smem = STAGES * STAGE_BYTES + (2 * BN + 32 * 128 + 8 * 128) * sizeof(float) + (2 * STAGES + 4) * sizeof(uint64_t) + 16 + 1024;
     static bool attr = false;
     if (!attr) {
         HQ_CUDA_OK(cudaFuncSetAttribute(k_rerank_tc<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -418,6 +418,8 @@ __global__ void __launch_bounds__(256) k_pyramid_top(const TileParams p) {
     }
 }
 
+#include "hq_item_pass.cuh"
+
 size_t tile_smem_bytes(int log2t, int mode) {
     const uint32_t T = 1u << log2t;
     const uint32_t pitch = T + (T >= 32 ? 4u : 0u);
@@ -511,7 +513,15 @@ static int fused_impl(const float* src, int direction, int64_t N, int64_t D, int
         HQ_REQUIRE(scratch_bytes >= need2, "scratch too small: need %lld bytes", (long long)need2);
     }
     int rc;
-    if (direction == 0) rc = pyr_mode ? launch_tile<0, 1>(p, st) : launch_tile<0, 0>(p, st);
+    // grids up to 64x64 with 128-bit aligned rows take the register-resident fast path
+    const bool fast = !tiled && (D % 4 == 0) && p.vec_src && (direction == 0 ? (!grid_out || p.vec_grid) : (!stream_out || p.vec_stream)) &&
+                      N * (direction == 0 ? (grid_out ? grid_stride : src_stride) : src_stride) < ((int64_t)1 << 62) &&
+                      (int64_t)256 * (src_stride > grid_stride ? src_stride : grid_stride) < ((int64_t)1 << 31) &&
+                      (int64_t)256 * stream_stride < ((int64_t)1 << 31);
+    if (fast) {
+        if (direction == 0) rc = pyr_mode ? item_pass::launch<0, 1>(p, st) : item_pass::launch<0, 0>(p, st);
+        else rc = pyr_mode ? item_pass::launch<1, 1>(p, st) : item_pass::launch<1, 0>(p, st);
+    } else if (direction == 0) rc = pyr_mode ? launch_tile<0, 1>(p, st) : launch_tile<0, 0>(p, st);
     else rc = pyr_mode ? launch_tile<1, 1>(p, st) : launch_tile<1, 0>(p, st);
     if (rc != HQ_OK) return rc;
     if (tiled && plan_len > 0) {
