@@ -1,0 +1,462 @@
+// K5 fast path: the RAG progressive filter without a score matrix.
+//
+//   k_filter_bits     one pass over (queries x rows): the per-level threshold tests of ALL levels
+//                     as three independent bit planes P_l[q][row] = (score_l(q,row) >= thr_l).
+//                     A thread owns one row (all its index values in registers) and sweeps a
+//                     128-query tile out of shared memory, four queries per 128-bit load.
+//                     The test is the multiplication form  dot >= (x*_l * |q|) * |c|  of
+//                     (dot / (|q||c|) + 1) / 2 >= thr_l  (x*_l = smallest float whose score
+//                     reaches thr_l), so no division / square root per pair.
+//   k_filter_cascade  one CTA per query walks the levels: alive &= P_l, counts, and ONLY when the
+//                     ratio cut binds (count > cap) ranks the surviving rows exactly: their fp32
+//                     scores are recomputed from the index rows (same arithmetic as the exact
+//                     path in hq_search.cu), compacted to a scratch list, and the (count - cap)
+//                     lowest (score asc, row id desc) are cleared with an exact radix select.
+//
+// Valid when every row / query index length equals the structural length of its level
+// (dense data: hq_index_row_lengths == lvl_keff everywhere); otherwise the caller uses the
+// exact per-level path (hq_filter_level / hq_filter_select).
+// Reference semantics: rag/search/engine.py:178-287.
+#include "hq_common.cuh"
+#include <float.h>
+
+namespace {
+
+constexpr int kRows = 256;       // rows per CTA (one per thread)
+constexpr int kQT = 128;         // queries per CTA
+
+struct BitsParams {
+    const float* idx;            // [N, Lsum]
+    const float* rnorm;          // [N, L] row norms per level, NaN where the norm is 0
+    int64_t N;
+    hq_index_layout lay;
+    const float* q_idx;          // [Q, Lsum]
+    int Q;
+    float xstar[3];
+    uint32_t* bits;              // [L][Q][words]
+    int64_t words;
+    int q_tiles;
+};
+
+template <int K>
+__device__ __forceinline__ void load_row(const float* __restrict__ p, int keff, float (&c)[K]) {
+#pragma unroll
+    for (int j = 0; j < K; j += 4) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < keff) v = __ldg(reinterpret_cast<const float4*>(p + j));
+        c[j] = v.x; c[j + 1] = v.y; c[j + 2] = v.z; c[j + 3] = v.w;
+    }
+}
+
+template <int K>
+__device__ __forceinline__ void dot4(const float (&c)[K], const float* __restrict__ sq /*[K][kQT]*/, int qq, float (&acc)[4]) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const float4 qv = *reinterpret_cast<const float4*>(sq + j * kQT + qq);
+        acc[0] = fmaf(c[j], qv.x, acc[0]);
+        acc[1] = fmaf(c[j], qv.y, acc[1]);
+        acc[2] = fmaf(c[j], qv.z, acc[2]);
+        acc[3] = fmaf(c[j], qv.w, acc[3]);
+    }
+}
+
+template <int K0, int K1, int K2>
+__global__ void __launch_bounds__(kRows, 2) k_filter_bits(const BitsParams p) {
+    constexpr int KT = K0 + K1 + K2;
+    extern __shared__ __align__(16) float sm[];
+    float* s_q = sm;                         // [KT][kQT] transposed query tile, levels stacked
+    float* s_tq = sm + KT * kQT;             // [3][kQT]   x*_l * |q_l|  (NaN when |q_l| == 0)
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int q_tile = blockIdx.x % p.q_tiles;
+    const int64_t row0 = (int64_t)(blockIdx.x / p.q_tiles) * kRows;
+    const int q0 = q_tile * kQT;
+    const int L = p.lay.L;
+
+    // stage the query tile
+    for (int e = tid; e < kQT * KT; e += kRows) {
+        const int qq = e / KT, j = e - qq * KT;
+        const int q = q0 + qq;
+        int l = 0, jj = j;
+        if (j >= K0) { l = 1; jj = j - K0; }
+        if (j >= K0 + K1) { l = 2; jj = j - K0 - K1; }
+        float v = 0.f;
+        if (q < p.Q && l < L && jj < p.lay.lvl_keff[l]) v = __ldg(p.q_idx + (int64_t)q * p.lay.Lsum + p.lay.lvl_off[l] + jj);
+        s_q[j * kQT + qq] = v;
+    }
+    __syncthreads();
+    if (tid < kQT) {
+        const int kk[3] = {K0, K1, K2};
+        int base = 0;
+        for (int l = 0; l < 3; ++l) {
+            float c = 0.f;
+            for (int j = 0; j < kk[l]; ++j) { const float v = s_q[(base + j) * kQT + tid]; c = fmaf(v, v, c); }
+            const float nq = sqrtf(c);
+            s_tq[l * kQT + tid] = nq > 0.f ? __fmul_rn(p.xstar[l], nq) : __int_as_float(0x7fc00000);
+            base += kk[l];
+        }
+    }
+
+    const int64_t row = row0 + tid;
+    const bool in_range = row < p.N;
+    const int64_t rr = in_range ? row : 0;
+    float c0[K0], c1[K1 > 0 ? K1 : 4], c2[K2 > 0 ? K2 : 4];
+    load_row<K0>(p.idx + rr * p.lay.Lsum + p.lay.lvl_off[0], p.lay.lvl_keff[0], c0);
+    float n0 = __ldg(p.rnorm + rr * L), n1 = 0.f, n2 = 0.f;
+    if constexpr (K1 > 0) { load_row<K1>(p.idx + rr * p.lay.Lsum + p.lay.lvl_off[1], p.lay.lvl_keff[1], c1); n1 = __ldg(p.rnorm + rr * L + 1); }
+    if constexpr (K2 > 0) { load_row<K2>(p.idx + rr * p.lay.Lsum + p.lay.lvl_off[2], p.lay.lvl_keff[2], c2); n2 = __ldg(p.rnorm + rr * L + 2); }
+    __syncthreads();
+
+    const int64_t word = row >> 5;
+    const bool word_ok = (row0 + (tid & ~31)) < p.N;
+    uint32_t* b0 = p.bits;
+    uint32_t* b1 = p.bits + (int64_t)p.Q * p.words;
+    uint32_t* b2 = p.bits + 2 * (int64_t)p.Q * p.words;
+    for (int qq = 0; qq < kQT; qq += 4) {
+        if (q0 + qq >= p.Q) break;
+        float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
+        dot4<K0>(c0, s_q, qq, a0);
+        if constexpr (K1 > 0) dot4<K1>(c1, s_q + K0 * kQT, qq, a1);
+        if constexpr (K2 > 0) dot4<K2>(c2, s_q + (K0 + K1) * kQT, qq, a2);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int q = q0 + qq + u;
+            if (q >= p.Q) break;
+            const bool p0 = in_range && (a0[u] >= __fmul_rn(s_tq[qq + u], n0));
+            const uint32_t w0 = __ballot_sync(0xffffffffu, p0);
+            uint32_t w1 = 0, w2 = 0;
+            if (K1 > 0) w1 = __ballot_sync(0xffffffffu, in_range && (a1[u] >= __fmul_rn(s_tq[kQT + qq + u], n1)));
+            if (K2 > 0) w2 = __ballot_sync(0xffffffffu, in_range && (a2[u] >= __fmul_rn(s_tq[2 * kQT + qq + u], n2)));
+            if (lane == 0 && word_ok) {
+                b0[(int64_t)q * p.words + word] = w0;
+                if (K1 > 0) b1[(int64_t)q * p.words + word] = w1;
+                if (K2 > 0) b2[(int64_t)q * p.words + word] = w2;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// row norms per level (sequential fmaf order, identical to the exact path); NaN marks zero
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_level_norms(const float* __restrict__ idx, int64_t N, hq_index_layout lay,
+                                                     float* __restrict__ rnorm, int32_t* __restrict__ nonuniform,
+                                                     const uint16_t* __restrict__ lens) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < N * lay.L; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = t / lay.L;
+        const int l = (int)(t - row * lay.L);
+        const float* r = idx + row * lay.Lsum + lay.lvl_off[l];
+        float c = 0.f;
+        for (int j = 0; j < lay.lvl_keff[l]; ++j) { const float v = __ldg(r + j); c = fmaf(v, v, c); }
+        const float nrm = sqrtf(c);
+        rnorm[t] = nrm > 0.f ? nrm : __int_as_float(0x7fc00000);
+        if (lens && (int)lens[t] != lay.lvl_keff[l]) atomicOr(nonuniform, 1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// block-wide exact selection on a compact key list (k-th SMALLEST), warp-aggregated histograms
+// ---------------------------------------------------------------------------------------
+struct SelSmall { uint32_t key; uint32_t below; uint32_t equal; };   // #keys < key, #keys == key
+
+__device__ SelSmall block_select_smallest(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ filt, uint32_t filt_val,
+                                          uint32_t n, uint32_t k, uint32_t* hist /*2048*/, uint32_t* sh /*4*/) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    uint32_t prefix = 0, pmask = 0, remaining = k, below_total = 0, equal = 0;
+    const int shifts[3] = {21, 10, 0};
+    const int nbits[3] = {11, 11, 10};
+    const uint32_t n_pad = (n + 31u) & ~31u;
+    for (int pass = 0; pass < 3; ++pass) {
+        const int shift = shifts[pass];
+        const uint32_t nb = 1u << nbits[pass];
+        for (uint32_t i = tid; i < nb; i += nt) hist[i] = 0;
+        __syncthreads();
+        for (uint32_t i = tid; i < n_pad; i += nt) {
+            bool valid = i < n;
+            uint32_t key = 0;
+            if (valid) {
+                key = keys[i];
+                valid = (key & pmask) == prefix && (!filt || filt[i] == filt_val);
+            }
+            const uint32_t bin = (key >> shift) & (nb - 1);
+            const uint32_t act = __ballot_sync(0xffffffffu, valid);
+            if (valid) {
+                const uint32_t peers = __match_any_sync(act, bin);
+                if (lane == __ffs(peers) - 1) atomicAdd(&hist[bin], (uint32_t)__popc(peers));
+            }
+        }
+        __syncthreads();
+        if (tid < 32) {
+            const uint32_t seg = nb / 32;
+            uint32_t sum = 0;
+            for (uint32_t b = 0; b < seg; ++b) sum += hist[tid * seg + b];
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (tid >= o) incl += t;
+            }
+            const uint32_t excl = incl - sum;
+            if (excl < remaining && remaining <= incl) {
+                uint32_t below = excl, b = tid * seg;
+                for (;; ++b) {
+                    const uint32_t h = hist[b];
+                    if (below + h >= remaining) break;
+                    below += h;
+                }
+                sh[0] = b; sh[1] = remaining - below; sh[2] = hist[b]; sh[3] = below;
+            }
+        }
+        __syncthreads();
+        prefix |= sh[0] << shift;
+        pmask |= (nb - 1) << shift;
+        remaining = sh[1];
+        equal = sh[2];
+        below_total += sh[3];
+        __syncthreads();
+    }
+    SelSmall r;
+    r.key = prefix; r.below = below_total; r.equal = equal;
+    return r;
+}
+
+struct CascadeParams {
+    const uint32_t* bits;        // [L][Q][words]
+    int64_t words;
+    const float* idx;            // [N, Lsum]
+    int64_t N;
+    hq_index_layout lay;
+    const float* q_idx;          // [Q, Lsum]
+    int Q;
+    double ratio[8];
+    uint32_t* mask;              // [Q, mask_stride] out
+    int64_t mask_stride;
+    int32_t* counts;             // [L][3][Q] (n_alive, n_pass, n_out) or null
+    int32_t* n_out;              // [Q]
+    uint32_t* scratch_keys;      // [gridDim][N]
+    uint32_t* scratch_rows;      // [gridDim][N]
+};
+
+__device__ __forceinline__ uint32_t block_sum(uint32_t v, uint32_t* s_warp) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_warp[w] = v;
+    __syncthreads();
+    uint32_t t = 0;
+    for (int i = 0; i < nw; ++i) t += s_warp[i];
+    __syncthreads();
+    return t;
+}
+
+__global__ void __launch_bounds__(1024, 1) k_filter_cascade(const CascadeParams p) {
+    __shared__ uint32_t hist[2048];
+    __shared__ uint32_t sh[4];
+    __shared__ uint32_t s_warp[32];
+    __shared__ float s_q[64];
+    __shared__ float s_nq;
+    __shared__ uint32_t s_count;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int L = p.lay.L;
+    uint32_t* keys = p.scratch_keys + (int64_t)blockIdx.x * p.N;
+    uint32_t* rows = p.scratch_rows + (int64_t)blockIdx.x * p.N;
+
+    for (int q = blockIdx.x; q < p.Q; q += gridDim.x) {
+        uint32_t* M = p.mask + (int64_t)q * p.mask_stride;
+        int64_t n_alive = p.N;
+        for (int l = 0; l < L; ++l) {
+            const uint32_t* P = p.bits + ((int64_t)l * p.Q + q) * p.words;
+            uint32_t c = 0;
+            for (int64_t w = tid; w < p.words; w += blockDim.x) {
+                uint32_t a;
+                if (l == 0) {
+                    const int64_t r0 = w * 32;
+                    a = r0 + 32 <= p.N ? 0xffffffffu : (r0 < p.N ? ((1u << (uint32_t)(p.N - r0)) - 1u) : 0u);
+                } else {
+                    a = __ldcg(M + w);               // rows cleared by other threads' atomics live in L2
+                }
+                const uint32_t cand = a & __ldg(P + w);
+                M[w] = cand;
+                c += __popc(cand);
+            }
+            const uint32_t c_total = block_sum(c, s_warp);       // barriers inside: M is complete
+            int64_t cap = (int64_t)((double)n_alive * p.ratio[l]);
+            if (cap < 1) cap = 1;
+            if (p.counts && tid == 0) {
+                p.counts[((int64_t)l * 3 + 0) * p.Q + q] = (int32_t)n_alive;
+                p.counts[((int64_t)l * 3 + 1) * p.Q + q] = (int32_t)c_total;
+                p.counts[((int64_t)l * 3 + 2) * p.Q + q] = (int32_t)((int64_t)c_total > cap ? cap : c_total);
+            }
+            if ((int64_t)c_total > cap) {
+                const uint32_t drop = c_total - (uint32_t)cap;
+                // ---- query row of this level + its norm (sequential fmaf order) ----
+                const int keff = p.lay.lvl_keff[l];
+                if (tid < 64) s_q[tid] = tid < keff ? __ldg(p.q_idx + (int64_t)q * p.lay.Lsum + p.lay.lvl_off[l] + tid) : 0.f;
+                if (tid == 0) s_count = 0;
+                __syncthreads();
+                if (tid == 0) {
+                    float cq = 0.f;
+                    for (int j = 0; j < keff; ++j) cq = fmaf(s_q[j], s_q[j], cq);
+                    s_nq = sqrtf(cq);
+                }
+                __syncthreads();
+                const float nq = s_nq;
+                // ---- compact (key, row) of every surviving row ----
+                const int64_t words_pad = (p.words + 31) & ~(int64_t)31;
+                for (int64_t w = tid; w < words_pad; w += blockDim.x) {
+                    uint32_t cand = w < p.words ? __ldcg(M + w) : 0u;
+                    const uint32_t cnt = __popc(cand);
+                    uint32_t incl = cnt;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += t;
+                    }
+                    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                    uint32_t base = 0;
+                    if (lane == 0 && total) base = atomicAdd(&s_count, total);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    uint32_t pos = base + incl - cnt;
+                    while (cand) {
+                        const int b = __ffs(cand) - 1;
+                        cand &= cand - 1;
+                        const int64_t row = w * 32 + b;
+                        const float* rp = p.idx + row * p.lay.Lsum + p.lay.lvl_off[l];
+                        float dot = 0.f, cn2 = 0.f;
+                        for (int j = 0; j < keff; j += 4) {
+                            const float4 v = __ldg(reinterpret_cast<const float4*>(rp + j));
+                            dot = fmaf(v.x, s_q[j], dot); cn2 = fmaf(v.x, v.x, cn2);
+                            dot = fmaf(v.y, s_q[j + 1], dot); cn2 = fmaf(v.y, v.y, cn2);
+                            dot = fmaf(v.z, s_q[j + 2], dot); cn2 = fmaf(v.z, v.z, cn2);
+                            dot = fmaf(v.w, s_q[j + 3], dot); cn2 = fmaf(v.w, v.w, cn2);
+                        }
+                        const float nc = sqrtf(cn2);
+                        float s = 0.f;
+                        if (nq != 0.f && nc != 0.f) s = __fmul_rn(__fadd_rn(__fdiv_rn(dot, __fmul_rn(nq, nc)), 1.0f), 0.5f);
+                        if (s < 0.f) s = 0.f;
+                        keys[pos] = __float_as_uint(s);
+                        rows[pos] = (uint32_t)row;
+                        ++pos;
+                    }
+                }
+                __syncthreads();
+                const uint32_t n_list = s_count;
+                // ---- the `drop` lowest by (score asc, row id desc) go ----
+                const SelSmall sel = block_select_smallest(keys, nullptr, 0, n_list, drop, hist, sh);
+                const uint32_t t_d = drop - sel.below;                 // ties to drop (1..equal)
+                uint32_t id_cut = 0;                                   // ties with row >= id_cut are dropped
+                if (t_d < sel.equal) {
+                    const SelSmall ids = block_select_smallest(rows, keys, sel.key, n_list, sel.equal - t_d + 1, hist, sh);
+                    id_cut = ids.key;
+                }
+                for (uint32_t i = tid; i < n_list; i += blockDim.x) {
+                    const uint32_t key = keys[i], row = rows[i];
+                    if (key < sel.key || (key == sel.key && row >= id_cut)) atomicAnd(&M[row >> 5], ~(1u << (row & 31)));
+                }
+                __syncthreads();
+                n_alive = cap;
+            } else {
+                n_alive = c_total;
+            }
+        }
+        if (tid == 0) p.n_out[q] = (int32_t)n_alive;
+        __syncthreads();
+    }
+}
+
+template <int K0, int K1, int K2>
+int launch_bits(const BitsParams& p, cudaStream_t st) {
+    constexpr int KT = K0 + K1 + K2;
+    const size_t smem = sizeof(float) * ((size_t)KT * kQT + 3 * kQT);
+    static bool attr = false;
+    if (!attr && smem > 48 * 1024) {
+        HQ_CUDA_OK(cudaFuncSetAttribute(k_filter_bits<K0, K1, K2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    const int64_t row_tiles = (p.N + kRows - 1) / kRows;
+    const int64_t blocks = row_tiles * p.q_tiles;
+    HQ_REQUIRE(blocks < ((int64_t)1 << 31), "filter grid too large");
+    k_filter_bits<K0, K1, K2><<<(unsigned)blocks, kRows, smem, st>>>(p);
+    HQ_LAUNCH_OK("k_filter_bits");
+    return HQ_OK;
+}
+
+}  // namespace
+
+extern "C" int hq_filter_level_norms(const float* idx, const uint16_t* lens, int64_t N, const hq_index_layout* layout, float* rnorm,
+                                     int32_t* nonuniform, void* stream) {
+    HQ_REQUIRE(layout && layout->L >= 1 && layout->L <= 8, "bad index layout");
+    HQ_REQUIRE(N >= 0, "negative N");
+    if (N == 0) return HQ_OK;
+    HQ_REQUIRE(idx && rnorm && nonuniform, "null pointer");
+    int64_t blocks = (N * layout->L + 255) / 256;
+    const int64_t cap = (int64_t)hq_cached_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    k_level_norms<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(idx, N, *layout, rnorm, nonuniform, lens);
+    HQ_LAUNCH_OK("k_level_norms");
+    return HQ_OK;
+}
+
+extern "C" int hq_filter_fast_supported(const hq_index_layout* layout) {
+    if (!layout || layout->L < 1 || layout->L > 3 || layout->Lsum % 4 != 0) return 0;
+    for (int l = 0; l < layout->L; ++l)
+        if (layout->lvl_off[l] % 4 != 0 || layout->lvl_w[l] % 4 != 0) return 0;
+    const int k0 = layout->lvl_keff[0], k1 = layout->L > 1 ? layout->lvl_keff[1] : 0, k2 = layout->L > 2 ? layout->lvl_keff[2] : 0;
+    if (k0 > 64 || k1 > 16 || k2 > 4) return 0;
+    return 1;
+}
+
+extern "C" int64_t hq_filter_fast_scratch_bytes(int64_t N, int Q, const hq_index_layout* layout) {
+    if (!layout || N <= 0 || Q <= 0) return 0;
+    const int64_t words = (N + 31) / 32;
+    int grid = hq_cached_sm_count();
+    if (grid > Q) grid = Q;
+    return (int64_t)layout->L * Q * words * 4 + (int64_t)grid * N * 8;
+}
+
+extern "C" int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, const hq_index_layout* layout, const float* q_idx, int Q,
+                              const float* xstar, const double* ratio, uint32_t* mask, int64_t mask_stride, int32_t* n_out,
+                              int32_t* counts, void* scratch, int64_t scratch_bytes, void* stream) {
+    HQ_REQUIRE(hq_filter_fast_supported(layout), "index layout not supported by the fast filter");
+    HQ_REQUIRE(N >= 0 && Q >= 0, "negative size");
+    if (N == 0 || Q == 0) return HQ_OK;
+    HQ_REQUIRE(idx && rnorm && q_idx && xstar && ratio && mask && n_out, "null pointer");
+    HQ_REQUIRE(N < ((int64_t)1 << 31), "N too large for one shard");
+    HQ_REQUIRE(mask_stride * 32 >= N, "mask stride too small");
+    const int64_t need = hq_filter_fast_scratch_bytes(N, Q, layout);
+    HQ_REQUIRE(scratch && scratch_bytes >= need, "scratch too small: need %lld bytes", (long long)need);
+    const int64_t words = (N + 31) / 32;
+    const int L = layout->L;
+    cudaStream_t st = (cudaStream_t)stream;
+
+    BitsParams bp{};
+    bp.idx = idx; bp.rnorm = rnorm; bp.N = N; bp.lay = *layout; bp.q_idx = q_idx; bp.Q = Q;
+    for (int l = 0; l < 3; ++l) bp.xstar[l] = l < L ? xstar[l] : 0.f;
+    bp.bits = reinterpret_cast<uint32_t*>(scratch); bp.words = words; bp.q_tiles = (Q + kQT - 1) / kQT;
+    const int k0 = layout->lvl_keff[0], k1 = L > 1 ? layout->lvl_keff[1] : 0, k2 = L > 2 ? layout->lvl_keff[2] : 0;
+    int rc;
+    if (L == 3) {
+        if (k0 <= 24 && k1 <= 8) rc = launch_bits<24, 8, 4>(bp, st);
+        else if (k0 <= 32 && k1 <= 8) rc = launch_bits<32, 8, 4>(bp, st);
+        else rc = launch_bits<64, 16, 4>(bp, st);
+    } else if (L == 2) {
+        if (k0 <= 8 && k1 <= 4) rc = launch_bits<8, 4, 0>(bp, st);
+        else if (k0 <= 16 && k1 <= 4) rc = launch_bits<16, 4, 0>(bp, st);
+        else rc = launch_bits<64, 16, 0>(bp, st);
+    } else {
+        rc = k0 <= 16 ? launch_bits<16, 0, 0>(bp, st) : launch_bits<64, 0, 0>(bp, st);
+    }
+    if (rc != HQ_OK) return rc;
+
+    CascadeParams cp{};
+    cp.bits = bp.bits; cp.words = words; cp.idx = idx; cp.N = N; cp.lay = *layout; cp.q_idx = q_idx; cp.Q = Q;
+    for (int l = 0; l < 8; ++l) cp.ratio[l] = l < L ? ratio[l] : 1.0;
+    cp.mask = mask; cp.mask_stride = mask_stride; cp.counts = counts; cp.n_out = n_out;
+    int grid = hq_cached_sm_count();
+    if (grid > Q) grid = Q;
+    cp.scratch_keys = bp.bits + (int64_t)L * Q * words;
+    cp.scratch_rows = cp.scratch_keys + (int64_t)grid * N;
+    k_filter_cascade<<<grid, 1024, 0, st>>>(cp);
+    HQ_LAUNCH_OK("k_filter_cascade");
+    return HQ_OK;
+}

@@ -69,6 +69,32 @@ def rag_ratio(level: int) -> float:
     return 0.3 if level == 0 else (0.5 if level == 1 else 0.7)
 
 
+def xstar_for(thr: float) -> np.float32:
+    """Smallest float32 x whose float32-evaluated score (x + 1) * 0.5 reaches `thr` (compared as
+    float64, like `score >= threshold` in rag/search/engine.py:284): the cosine cut of a level.
+    Bisection over the ordered float32 bit patterns (the score is monotone in x)."""
+    one, half = np.float32(1.0), np.float32(0.5)
+
+    def from_ord(i: int) -> np.float32:          # order-preserving int -> float32
+        bits = i if i >= 0 else (-(i + 1)) | 0x80000000
+        return np.array([bits & 0xffffffff], dtype=np.uint32).view(np.float32)[0]
+
+    def ok(i: int) -> bool:
+        return float((from_ord(i) + one) * half) >= thr
+    lo, hi = -0x40400000, 0x40400000              # -3.0 .. 3.0
+    if ok(lo):
+        return from_ord(lo)
+    if not ok(hi):
+        return np.float32(np.inf)
+    while hi - lo > 1:                            # invariant: not ok(lo), ok(hi)
+        mid = (lo + hi) // 2
+        if ok(mid):
+            hi = mid
+        else:
+            lo = mid
+    return np.float32(from_ord(hi))
+
+
 def make_layout(n: int, D: int) -> Tuple[IndexLayout, List[int]]:
     """Compact variant-C layout of an n x n grid holding D real values."""
     levels = plans.c_levels(n)
@@ -113,6 +139,19 @@ class EmbeddingDatabase:
         self.lens = row_lengths(self.idx, self.layout)
         self.norms = row_norms(self.emb)
         self.emb_bf16 = to_bf16(self.emb) if bf16 else None       # operand of the tensor-core rerank
+        # fast filter: per-level row norms + "every stored length is the structural one" check
+        self.level_norms = torch.empty((self.N, int(self.layout.L)), dtype=torch.float32, device=d)
+        flag = torch.zeros(1, dtype=torch.int32, device=d)
+        with torch.cuda.device(d):
+            check(lib.hq_filter_level_norms(dev.ptr(self.idx), dev.ptr(self.lens), self.N, C.byref(self.layout),
+                                            dev.ptr(self.level_norms), dev.ptr(flag), dev.stream_ptr()))
+        self.fast_filter_ok = bool(lib.hq_filter_fast_supported(C.byref(self.layout))) and (self.N == 0 or int(flag.item()) == 0)
+        self._keff = torch.tensor([int(self.layout.lvl_keff[l]) for l in range(int(self.layout.L))], dtype=torch.int16, device=d)
+        self._xstar = torch.tensor([float(xstar_for(rag_threshold(l))) for l in range(int(self.layout.L))], dtype=torch.float32, device=d)
+        self._ratio = torch.tensor([rag_ratio(l) for l in range(int(self.layout.L))], dtype=torch.float64, device=d)
+        self._ratio_host = (C.c_double * 8)(*([rag_ratio(l) for l in range(int(self.layout.L))] + [1.0] * (8 - int(self.layout.L))))
+        self._xstar_host = (C.c_float * 3)(*([float(xstar_for(rag_threshold(l))) for l in range(min(3, int(self.layout.L)))] + [0.0] * (3 - min(3, int(self.layout.L)))))
+        self._filter_scratch = None
 
     @property
     def num_levels(self) -> int:
@@ -187,6 +226,29 @@ def progressive_filter(db: EmbeddingDatabase, q_idx: torch.Tensor, q_lens: torch
     return mask
 
 
+def progressive_filter_fast(db: EmbeddingDatabase, q_idx: torch.Tensor, mask: torch.Tensor,
+                            trace: Optional[FilterTrace] = None):
+    """All filter levels for a query batch through hq_filter_fast (no score matrix)."""
+    Q, N, d = q_idx.shape[0], db.N, db.device
+    L = db.num_levels
+    need = int(lib.hq_filter_fast_scratch_bytes(N, Q, C.byref(db.layout)))
+    if db._filter_scratch is None or db._filter_scratch.numel() < need:
+        db._filter_scratch = torch.empty(need, dtype=torch.uint8, device=d)
+    n_out = torch.empty(Q, dtype=torch.int32, device=d)
+    counts = torch.zeros((L, 3, Q), dtype=torch.int32, device=d) if trace is not None else None
+    with torch.cuda.device(d):
+        check(lib.hq_filter_fast(dev.ptr(db.idx), dev.ptr(db.level_norms), N, C.byref(db.layout), dev.ptr(q_idx), Q,
+                                 C.cast(db._xstar_host, C.c_void_p), C.cast(db._ratio_host, C.c_void_p),
+                                 dev.ptr(mask), mask.stride(0), dev.ptr(n_out), dev.ptr(counts),
+                                 dev.ptr(db._filter_scratch), db._filter_scratch.numel(), dev.stream_ptr()))
+    if trace is not None:
+        for level in range(L):
+            trace.n_alive.append(counts[level, 0])
+            trace.n_pass.append(counts[level, 1])
+            trace.n_out.append(counts[level, 2])
+    return mask
+
+
 def prepare_queries(db: EmbeddingDatabase, queries) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """queries [Q, D] -> (q float32 on device, q_idx compact rows, q_lens, q_norms)."""
     q = dev.f32_device(queries, db.device)
@@ -200,7 +262,7 @@ def prepare_queries(db: EmbeddingDatabase, queries) -> Tuple[torch.Tensor, torch
 
 def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: bool = True,
                  work_bytes: int = 4 << 30, return_mask: bool = False, trace: Optional[FilterTrace] = None,
-                 rerank: str = "auto"):
+                 rerank: str = "auto", filter_impl: str = "auto"):
     """Progressive top-k of a batch of query embeddings against one shard.
 
     Returns (ids int64 [Q, k] (-1 = fewer than k survivors), scores float32 [Q, k]).  Scores are
@@ -227,8 +289,18 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
         q_bf16 = to_bf16(q)
         _end(tok)
     words = _mask_words(N)
-    qc = int(max(1, min(Q, work_bytes // (4 * N))))
-    scores = torch.empty((qc, N), dtype=torch.float32, device=d)
+    if filter_impl not in ("auto", "fast", "exact"):
+        raise ValueError("filter_impl must be 'auto', 'fast' or 'exact'")
+    fast = False
+    if use_filter and filter_impl != "exact":
+        fast = db.fast_filter_ok and bool((q_lens == db._keff).all().item())
+        if filter_impl == "fast" and not fast:
+            raise ValueError("the fast filter needs dense index rows (all stored lengths structural) and L <= 3")
+    if fast or not use_filter:
+        work_bytes = max(work_bytes, 4 * N * Q) if rerank == "bf16" else work_bytes
+    qc = int(max(1, min(Q, work_bytes // (4 * N)))) if not (rerank == "bf16" and (fast or not use_filter)) else Q
+    need_scores = not (rerank == "bf16" and (fast or not use_filter))
+    scores = torch.empty((qc, N), dtype=torch.float32, device=d) if need_scores else None
     mask = torch.zeros((qc, words), dtype=torch.int32, device=d)
     masks = [] if return_mask else None
     with torch.cuda.device(d):
@@ -238,7 +310,10 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
             m = None
             if use_filter:
                 tok = _phase("filter")
-                m = progressive_filter(db, q_idx[s:e], q_lens[s:e], scores[:nq], mask[:nq], trace)
+                if fast:
+                    m = progressive_filter_fast(db, q_idx[s:e], mask[:nq], trace)
+                else:
+                    m = progressive_filter(db, q_idx[s:e], q_lens[s:e], scores[:nq], mask[:nq], trace)
                 _end(tok)
                 if return_mask:
                     masks.append(m.clone())

@@ -147,6 +147,24 @@ int hq_filter_select(const float* scores, int64_t scores_stride, int64_t N, int 
                      const int32_t* n_alive, const int32_t* n_pass, double ratio,
                      uint32_t* mask, int64_t mask_stride, int32_t* n_out, void* stream);
 
+/* Fast path of the same filter (no score matrix): one pass computes the threshold tests of
+ * all levels as bit planes, then one CTA per query walks the levels and ranks rows exactly
+ * (fp32 scores recomputed from the index rows, exact radix select, ties -> lower row id) only
+ * where the ratio cut binds.  Requires L <= 3, level widths multiples of 4 and every stored /
+ * query index length equal to lvl_keff (hq_filter_level_norms reports violations through
+ * *nonuniform); otherwise use hq_filter_level / hq_filter_select.
+ *   rnorm [N, L]   per-level row norms (NaN where 0), written by hq_filter_level_norms
+ *   xstar [L]      smallest float x with ((x + 1) / 2 evaluated in float32) >= thr_l
+ *   counts         optional [L][3][Q] (n_alive, n_pass, n_out) per level                       */
+int hq_filter_fast_supported(const hq_index_layout* layout);
+int hq_filter_level_norms(const float* idx, const uint16_t* lens, int64_t N, const hq_index_layout* layout,
+                          float* rnorm, int32_t* nonuniform, void* stream);
+int64_t hq_filter_fast_scratch_bytes(int64_t N, int Q, const hq_index_layout* layout);
+int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, const hq_index_layout* layout,
+                   const float* q_idx, int Q, const float* xstar, const double* ratio,
+                   uint32_t* mask, int64_t mask_stride, int32_t* n_out, int32_t* counts,
+                   void* scratch, int64_t scratch_bytes, void* stream);
+
 /* ---- a13/a15: cosine rerank + top-k --------------------------------------
  * rag/search/engine.py:622-660 (_calculate_embedding_cosine_similarity),
  * :512 / :778-781 (stable descending sort, first k).

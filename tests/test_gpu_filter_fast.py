@@ -1,0 +1,64 @@
+"""GPU: the fast filter (bit planes + per-query cascade) against the exact per-level path."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hq():
+    import hilbert_quantization_b200 as m
+    return m
+
+
+def _data(rng, N, D, Q, positive):
+    if positive:        # every row passes every threshold -> the ratio cut (exact select) decides at each level
+        db = (rng.random((N, D)) + 0.25).astype(np.float32)
+        qs = (rng.random((Q, D)) + 0.25).astype(np.float32)
+    else:
+        db = rng.standard_normal((N, D)).astype(np.float32)
+        qs = rng.standard_normal((Q, D)).astype(np.float32)
+    db[N // 3] = db[5]
+    db[N - 2] = db[5]
+    qs[0] = db[5]
+    return db, qs
+
+
+@pytest.mark.parametrize("N,D,Q,positive", [(3000, 1536, 20, False), (3000, 1536, 20, True), (5000, 768, 33, False),
+                                            (5000, 768, 33, True), (4097, 1024, 9, True), (2000, 256, 130, False),
+                                            (70000, 1536, 6, False), (70000, 768, 6, True), (1500, 4096, 7, True)])
+def test_fast_filter_equals_exact_filter(hq, N, D, Q, positive):
+    from hilbert_quantization_b200.search import FilterTrace, unpack_mask
+    rng = np.random.default_rng(N + D + Q)
+    db, qs = _data(rng, N, D, Q, positive)
+    d = hq.EmbeddingDatabase(db)
+    assert d.fast_filter_ok
+    tf, te = FilterTrace([], [], []), FilterTrace([], [], [])
+    i_f, s_f, m_f = hq.search_batch(d, qs, 10, return_mask=True, filter_impl="fast", trace=tf)
+    i_e, s_e, m_e = hq.search_batch(d, qs, 10, return_mask=True, filter_impl="exact", trace=te)
+    a_f, a_e = unpack_mask(m_f, N), unpack_mask(m_e, N)
+    same = (a_f == a_e).all(axis=1)
+    # the two paths evaluate the threshold in different (equally valid) fp32 forms: allow one
+    # borderline query, and only single-row differences in it
+    assert same.sum() >= Q - 1, f"{(~same).sum()} queries differ"
+    for j in np.nonzero(~same)[0]:
+        assert (a_f[j] != a_e[j]).sum() <= 2
+    ok = torch.from_numpy(same).cuda()
+    assert torch.equal(i_f[ok], i_e[ok]) and torch.equal(s_f[ok], s_e[ok])
+    for l in range(len(tf.n_out)):
+        assert torch.equal(tf.n_out[l][ok], te.n_out[l][ok])
+    if positive:
+        assert int(tf.n_out[0][0]) == max(1, int(N * 0.3))
+
+
+def test_fast_filter_falls_back_on_sparse_rows(hq):
+    rng = np.random.default_rng(0)
+    db = rng.standard_normal((500, 768)).astype(np.float32)
+    db[17, 700:] = 0.0                       # a trailing zero run shortens this row's finest index row
+    d = hq.EmbeddingDatabase(db)
+    assert not d.fast_filter_ok
+    with pytest.raises(ValueError, match="fast filter"):
+        hq.search_batch(d, db[:3], 5, filter_impl="fast")
+    ids, _ = hq.search_batch(d, db[:3], 5)   # auto -> exact path
+    assert ids.shape == (3, 5)
