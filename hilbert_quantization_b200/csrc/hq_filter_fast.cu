@@ -19,6 +19,7 @@
 // Reference semantics: rag/search/engine.py:178-287.
 #include "hq_common.cuh"
 #include <float.h>
+#include <string.h>
 
 namespace {
 
@@ -224,11 +225,15 @@ struct CascadeParams {
     const uint32_t* bits;        // [L][Q][words]
     int64_t words;
     const float* idx;            // [N, Lsum]
+    const float* lvl[3];         // optional per-level copies [N, lvl_pitch[l]] (small enough to stay in L2)
+    int lvl_pitch[3];
     int64_t N;
     hq_index_layout lay;
     const float* q_idx;          // [Q, Lsum]
     int Q;
     double ratio[8];
+    uint32_t key_lo[8];          // smallest score bit pattern a surviving row of the level can have
+    uint32_t shift_a[8];         // right shift that maps (key - key_lo) of the level onto 2048 bins
     uint32_t* mask;              // [Q, mask_stride] out
     int64_t mask_stride;
     int32_t* counts;             // [L][3][Q] (n_alive, n_pass, n_out) or null
@@ -249,35 +254,67 @@ __device__ __forceinline__ uint32_t block_sum(uint32_t v, uint32_t* s_warp) {
     return t;
 }
 
+// exact fp32 score of one (query level row, database row) pair -- same arithmetic as hq_search.cu
+__device__ __forceinline__ uint32_t level_key(const float* __restrict__ rp, const float* __restrict__ s_q, int keff, float nq) {
+    float dot = 0.f, cn2 = 0.f;
+    for (int j = 0; j < keff; j += 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(rp + j));
+        dot = fmaf(v.x, s_q[j], dot); cn2 = fmaf(v.x, v.x, cn2);
+        dot = fmaf(v.y, s_q[j + 1], dot); cn2 = fmaf(v.y, v.y, cn2);
+        dot = fmaf(v.z, s_q[j + 2], dot); cn2 = fmaf(v.z, v.z, cn2);
+        dot = fmaf(v.w, s_q[j + 3], dot); cn2 = fmaf(v.w, v.w, cn2);
+    }
+    const float nc = sqrtf(cn2);
+    float sc = 0.f;
+    if (nq != 0.f && nc != 0.f) sc = __fmul_rn(__fadd_rn(__fdiv_rn(dot, __fmul_rn(nq, nc)), 1.0f), 0.5f);
+    if (sc < 0.f) sc = 0.f;
+    return __float_as_uint(sc);
+}
+
+constexpr int kBufCap = 4096;     // candidates of the cut bin that are ranked in shared memory
+
 __global__ void __launch_bounds__(1024, 1) k_filter_cascade(const CascadeParams p) {
     __shared__ uint32_t hist[2048];
     __shared__ uint32_t sh[4];
     __shared__ uint32_t s_warp[32];
     __shared__ float s_q[64];
     __shared__ float s_nq;
-    __shared__ uint32_t s_count;
-    const int tid = threadIdx.x, lane = tid & 31;
+    __shared__ uint32_t s_count, s_bufn;
+    __shared__ uint32_t b_key[kBufCap], b_row[kBufCap];
+    const int tid = threadIdx.x, lane = tid & 31, nt = blockDim.x;
     const int L = p.lay.L;
     uint32_t* keys = p.scratch_keys + (int64_t)blockIdx.x * p.N;
     uint32_t* rows = p.scratch_rows + (int64_t)blockIdx.x * p.N;
+    const int64_t words_pad = (p.words + 31) & ~(int64_t)31;
 
     for (int q = blockIdx.x; q < p.Q; q += gridDim.x) {
         uint32_t* M = p.mask + (int64_t)q * p.mask_stride;
         int64_t n_alive = p.N;
         for (int l = 0; l < L; ++l) {
+            // ---- alive &= P_l, count (4 independent word pairs in flight per thread) ----
             const uint32_t* P = p.bits + ((int64_t)l * p.Q + q) * p.words;
             uint32_t c = 0;
-            for (int64_t w = tid; w < p.words; w += blockDim.x) {
-                uint32_t a;
-                if (l == 0) {
-                    const int64_t r0 = w * 32;
-                    a = r0 + 32 <= p.N ? 0xffffffffu : (r0 < p.N ? ((1u << (uint32_t)(p.N - r0)) - 1u) : 0u);
-                } else {
-                    a = __ldcg(M + w);               // rows cleared by other threads' atomics live in L2
+            for (int64_t w0 = tid; w0 < p.words; w0 += 4 * (int64_t)nt) {
+                uint32_t a[4], pb[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int64_t w = w0 + (int64_t)u * nt;
+                    a[u] = 0; pb[u] = 0;
+                    if (w < p.words) {
+                        pb[u] = __ldg(P + w);
+                        if (l == 0) {
+                            const int64_t r0 = w * 32;
+                            a[u] = r0 + 32 <= p.N ? 0xffffffffu : (r0 < p.N ? ((1u << (uint32_t)(p.N - r0)) - 1u) : 0u);
+                        } else {
+                            a[u] = __ldcg(M + w);            // rows cleared by other threads' atomics live in L2
+                        }
+                    }
                 }
-                const uint32_t cand = a & __ldg(P + w);
-                M[w] = cand;
-                c += __popc(cand);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int64_t w = w0 + (int64_t)u * nt;
+                    if (w < p.words) { const uint32_t cand = a[u] & pb[u]; M[w] = cand; c += __popc(cand); }
+                }
             }
             const uint32_t c_total = block_sum(c, s_warp);       // barriers inside: M is complete
             int64_t cap = (int64_t)((double)n_alive * p.ratio[l]);
@@ -287,61 +324,139 @@ __global__ void __launch_bounds__(1024, 1) k_filter_cascade(const CascadeParams 
                 p.counts[((int64_t)l * 3 + 1) * p.Q + q] = (int32_t)c_total;
                 p.counts[((int64_t)l * 3 + 2) * p.Q + q] = (int32_t)((int64_t)c_total > cap ? cap : c_total);
             }
-            if ((int64_t)c_total > cap) {
-                const uint32_t drop = c_total - (uint32_t)cap;
-                // ---- query row of this level + its norm (sequential fmaf order) ----
-                const int keff = p.lay.lvl_keff[l];
-                if (tid < 64) s_q[tid] = tid < keff ? __ldg(p.q_idx + (int64_t)q * p.lay.Lsum + p.lay.lvl_off[l] + tid) : 0.f;
-                if (tid == 0) s_count = 0;
-                __syncthreads();
-                if (tid == 0) {
-                    float cq = 0.f;
-                    for (int j = 0; j < keff; ++j) cq = fmaf(s_q[j], s_q[j], cq);
-                    s_nq = sqrtf(cq);
-                }
-                __syncthreads();
-                const float nq = s_nq;
-                // ---- compact (key, row) of every surviving row ----
-                const int64_t words_pad = (p.words + 31) & ~(int64_t)31;
-                for (int64_t w = tid; w < words_pad; w += blockDim.x) {
-                    uint32_t cand = w < p.words ? __ldcg(M + w) : 0u;
-                    const uint32_t cnt = __popc(cand);
-                    uint32_t incl = cnt;
+            if ((int64_t)c_total <= cap) { n_alive = c_total; continue; }
+
+            // ======== the ratio cut binds: drop the (c_total - cap) lowest (score asc, row id desc) ========
+            const uint32_t drop = c_total - (uint32_t)cap;
+            const int keff = p.lay.lvl_keff[l];
+            if (tid < 64) s_q[tid] = tid < keff ? __ldg(p.q_idx + (int64_t)q * p.lay.Lsum + p.lay.lvl_off[l] + tid) : 0.f;
+            if (tid == 0) { s_count = 0; s_bufn = 0; }
+            for (int i = tid; i < 2048; i += nt) hist[i] = 0;
+            __syncthreads();
+            if (tid == 0) {
+                float cq = 0.f;
+                for (int j = 0; j < keff; ++j) cq = fmaf(s_q[j], s_q[j], cq);
+                s_nq = sqrtf(cq);
+            }
+            // ---- A: compact the surviving row ids (bits only) ----
+            for (int64_t w = tid; w < words_pad; w += nt) {
+                uint32_t cand = w < p.words ? __ldcg(M + w) : 0u;
+                const uint32_t cnt = __popc(cand);
+                uint32_t incl = cnt;
 #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane >= o) incl += t;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                uint32_t base = 0;
+                if (lane == 0 && total) base = atomicAdd(&s_count, total);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                uint32_t pos = base + incl - cnt;
+                while (cand) {
+                    const int b = __ffs(cand) - 1;
+                    cand &= cand - 1;
+                    rows[pos++] = (uint32_t)(w * 32 + b);
+                }
+            }
+            __syncthreads();
+            const uint32_t n_list = s_count;
+            const float nq = s_nq;
+            const float* lvl_base = l < 3 ? p.lvl[l] : nullptr;
+            const int64_t lvl_pitch = l < 3 ? p.lvl_pitch[l] : 0;
+            // ---- B: exact keys (4 independent rows in flight per thread) + histogram of the top digit ----
+            // scores live in [thr - eps, 1]: bin on the offset from the smallest possible key so that the
+            // 11-bit digit spreads; clamping only affects binning, never the order (true keys are kept)
+            const uint32_t key_lo = p.key_lo[l], shiftA = p.shift_a[l];
+            const uint32_t n_pad4 = (n_list + 4 * nt - 1) / (4 * nt) * (4 * nt);
+            for (uint32_t i0 = tid; i0 < n_pad4; i0 += 4 * nt) {
+                uint32_t k4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t i = i0 + u * nt;
+                    k4[u] = 0;
+                    if (i < n_list) {
+                        const int64_t row = __ldcg(rows + i);
+                        const float* rp = lvl_base ? lvl_base + row * lvl_pitch : p.idx + row * p.lay.Lsum + p.lay.lvl_off[l];
+                        k4[u] = level_key(rp, s_q, keff, nq);
                     }
-                    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-                    uint32_t base = 0;
-                    if (lane == 0 && total) base = atomicAdd(&s_count, total);
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    uint32_t pos = base + incl - cnt;
-                    while (cand) {
-                        const int b = __ffs(cand) - 1;
-                        cand &= cand - 1;
-                        const int64_t row = w * 32 + b;
-                        const float* rp = p.idx + row * p.lay.Lsum + p.lay.lvl_off[l];
-                        float dot = 0.f, cn2 = 0.f;
-                        for (int j = 0; j < keff; j += 4) {
-                            const float4 v = __ldg(reinterpret_cast<const float4*>(rp + j));
-                            dot = fmaf(v.x, s_q[j], dot); cn2 = fmaf(v.x, v.x, cn2);
-                            dot = fmaf(v.y, s_q[j + 1], dot); cn2 = fmaf(v.y, v.y, cn2);
-                            dot = fmaf(v.z, s_q[j + 2], dot); cn2 = fmaf(v.z, v.z, cn2);
-                            dot = fmaf(v.w, s_q[j + 3], dot); cn2 = fmaf(v.w, v.w, cn2);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t i = i0 + u * nt;
+                    const bool valid = i < n_list;
+                    if (valid) keys[i] = k4[u];
+                    uint32_t offk = k4[u] > key_lo ? k4[u] - key_lo : 0u;
+                    uint32_t bin = offk >> shiftA;
+                    if (bin > 2047u) bin = 2047u;
+                    const uint32_t act = __ballot_sync(0xffffffffu, valid);
+                    if (valid) {
+                        const uint32_t peers = __match_any_sync(act, bin);
+                        if (lane == __ffs(peers) - 1) atomicAdd(&hist[bin], (uint32_t)__popc(peers));
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- locate the bin holding the drop-th smallest ----
+            if (tid < 32) {
+                uint32_t sum = 0;
+                for (uint32_t b = 0; b < 64; ++b) sum += hist[tid * 64 + b];
+                uint32_t incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (tid >= o) incl += t;
+                }
+                const uint32_t excl = incl - sum;
+                if (excl < drop && drop <= incl) {
+                    uint32_t below = excl, b = tid * 64;
+                    for (;; ++b) {
+                        const uint32_t h = hist[b];
+                        if (below + h >= drop) break;
+                        below += h;
+                    }
+                    sh[0] = b; sh[1] = drop - below; sh[2] = hist[b];
+                }
+            }
+            __syncthreads();
+            const uint32_t cut_bin = sh[0], r_in_bin = sh[1], n_in_bin = sh[2];
+            if (n_in_bin <= (uint32_t)kBufCap) {
+                // ---- C: lower bins are dropped outright, the cut bin is ranked in shared memory ----
+                for (uint32_t i0 = tid; i0 < n_pad4; i0 += 4 * nt) {
+                    uint32_t k4[4], r4[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t i = i0 + u * nt;
+                        k4[u] = 0; r4[u] = 0;
+                        if (i < n_list) { k4[u] = __ldcg(keys + i); r4[u] = __ldcg(rows + i); }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t i = i0 + u * nt;
+                        if (i >= n_list) continue;
+                        uint32_t offk = k4[u] > key_lo ? k4[u] - key_lo : 0u;
+                        uint32_t bin = offk >> shiftA;
+                        if (bin > 2047u) bin = 2047u;
+                        if (bin < cut_bin) atomicAnd(&M[r4[u] >> 5], ~(1u << (r4[u] & 31)));
+                        else if (bin == cut_bin) {
+                            const uint32_t slot = atomicAdd(&s_bufn, 1u);
+                            b_key[slot] = k4[u]; b_row[slot] = r4[u];
                         }
-                        const float nc = sqrtf(cn2);
-                        float s = 0.f;
-                        if (nq != 0.f && nc != 0.f) s = __fmul_rn(__fadd_rn(__fdiv_rn(dot, __fmul_rn(nq, nc)), 1.0f), 0.5f);
-                        if (s < 0.f) s = 0.f;
-                        keys[pos] = __float_as_uint(s);
-                        rows[pos] = (uint32_t)row;
-                        ++pos;
                     }
                 }
                 __syncthreads();
-                const uint32_t n_list = s_count;
-                // ---- the `drop` lowest by (score asc, row id desc) go ----
+                const uint32_t nb = s_bufn;
+                for (uint32_t e = tid; e < nb; e += nt) {
+                    const uint32_t key = b_key[e], row = b_row[e];
+                    uint32_t rank = 0;                                    // entries that go before this one
+                    for (uint32_t j = 0; j < nb; ++j) {
+                        const uint32_t kj = b_key[j], rj = b_row[j];
+                        rank += (kj < key || (kj == key && rj > row)) ? 1u : 0u;
+                    }
+                    if (rank < r_in_bin) atomicAnd(&M[row >> 5], ~(1u << (row & 31)));
+                }
+            } else {
+                // ---- heavily tied scores: generic exact selection over the whole list ----
                 const SelSmall sel = block_select_smallest(keys, nullptr, 0, n_list, drop, hist, sh);
                 const uint32_t t_d = drop - sel.below;                 // ties to drop (1..equal)
                 uint32_t id_cut = 0;                                   // ties with row >= id_cut are dropped
@@ -349,15 +464,13 @@ __global__ void __launch_bounds__(1024, 1) k_filter_cascade(const CascadeParams 
                     const SelSmall ids = block_select_smallest(rows, keys, sel.key, n_list, sel.equal - t_d + 1, hist, sh);
                     id_cut = ids.key;
                 }
-                for (uint32_t i = tid; i < n_list; i += blockDim.x) {
+                for (uint32_t i = tid; i < n_list; i += nt) {
                     const uint32_t key = keys[i], row = rows[i];
                     if (key < sel.key || (key == sel.key && row >= id_cut)) atomicAnd(&M[row >> 5], ~(1u << (row & 31)));
                 }
-                __syncthreads();
-                n_alive = cap;
-            } else {
-                n_alive = c_total;
             }
+            __syncthreads();
+            n_alive = cap;
         }
         if (tid == 0) p.n_out[q] = (int32_t)n_alive;
         __syncthreads();
@@ -415,8 +528,9 @@ extern "C" int64_t hq_filter_fast_scratch_bytes(int64_t N, int Q, const hq_index
 }
 
 extern "C" int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, const hq_index_layout* layout, const float* q_idx, int Q,
-                              const float* xstar, const double* ratio, uint32_t* mask, int64_t mask_stride, int32_t* n_out,
-                              int32_t* counts, void* scratch, int64_t scratch_bytes, void* stream) {
+                              const float* xstar, const double* ratio, const float* const* lvl_rows, const int32_t* lvl_pitch,
+                              uint32_t* mask, int64_t mask_stride, int32_t* n_out, int32_t* counts, void* scratch,
+                              int64_t scratch_bytes, void* stream) {
     HQ_REQUIRE(hq_filter_fast_supported(layout), "index layout not supported by the fast filter");
     HQ_REQUIRE(N >= 0 && Q >= 0, "negative size");
     if (N == 0 || Q == 0) return HQ_OK;
@@ -450,7 +564,28 @@ extern "C" int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, c
 
     CascadeParams cp{};
     cp.bits = bp.bits; cp.words = words; cp.idx = idx; cp.N = N; cp.lay = *layout; cp.q_idx = q_idx; cp.Q = Q;
-    for (int l = 0; l < 8; ++l) cp.ratio[l] = l < L ? ratio[l] : 1.0;
+    for (int l = 0; l < 8; ++l) {
+        cp.ratio[l] = l < L ? ratio[l] : 1.0;
+        // survivors of level l score >= (x*_l + 1) / 2 (up to rounding): offset keys from a little below it
+        float lo = l < L && l < 3 ? (xstar[l] + 1.0f) * 0.5f : 0.f;
+        if (!(lo > 0.f)) lo = 0.f;
+        uint32_t klo;
+        memcpy(&klo, &lo, 4);
+        klo = klo > 64 ? klo - 64 : 0;
+        const float one = 1.0f;
+        uint32_t khi;
+        memcpy(&khi, &one, 4);
+        khi += 64;
+        uint32_t range = khi > klo ? khi - klo : 1, sh_a = 0;
+        while ((range >> sh_a) > 2047u) ++sh_a;
+        cp.key_lo[l] = klo;
+        cp.shift_a[l] = sh_a;
+    }
+    for (int l = 0; l < 3; ++l) {
+        cp.lvl[l] = (lvl_rows && lvl_pitch && l < L) ? lvl_rows[l] : nullptr;
+        cp.lvl_pitch[l] = (lvl_rows && lvl_pitch && l < L) ? lvl_pitch[l] : 0;
+        HQ_REQUIRE(!cp.lvl[l] || (cp.lvl_pitch[l] % 4 == 0 && cp.lvl_pitch[l] >= ((layout->lvl_keff[l] + 3) & ~3)), "bad level pitch");
+    }
     cp.mask = mask; cp.mask_stride = mask_stride; cp.counts = counts; cp.n_out = n_out;
     int grid = hq_cached_sm_count();
     if (grid > Q) grid = Q;

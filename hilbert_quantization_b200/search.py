@@ -152,6 +152,15 @@ class EmbeddingDatabase:
         self._ratio_host = (C.c_double * 8)(*([rag_ratio(l) for l in range(int(self.layout.L))] + [1.0] * (8 - int(self.layout.L))))
         self._xstar_host = (C.c_float * 3)(*([float(xstar_for(rag_threshold(l))) for l in range(min(3, int(self.layout.L)))] + [0.0] * (3 - min(3, int(self.layout.L)))))
         self._filter_scratch = None
+        # per-level copies of the index rows (pitch rounded to 4 floats): 48 MB for 1M x 1536, L2 resident
+        self._lvl_rows, pitches = [], []
+        for l in range(int(self.layout.L)):
+            off, keff = int(self.layout.lvl_off[l]), int(self.layout.lvl_keff[l])
+            pitch = (keff + 3) // 4 * 4
+            self._lvl_rows.append(self.idx[:, off:off + pitch].contiguous())
+            pitches.append(pitch)
+        self._lvl_ptrs = (C.c_void_p * 3)(*([t.data_ptr() for t in self._lvl_rows[:3]] + [None] * (3 - min(3, len(self._lvl_rows)))))
+        self._lvl_pitch = (C.c_int32 * 3)(*(pitches[:3] + [0] * (3 - min(3, len(pitches)))))
 
     @property
     def num_levels(self) -> int:
@@ -239,6 +248,7 @@ def progressive_filter_fast(db: EmbeddingDatabase, q_idx: torch.Tensor, mask: to
     with torch.cuda.device(d):
         check(lib.hq_filter_fast(dev.ptr(db.idx), dev.ptr(db.level_norms), N, C.byref(db.layout), dev.ptr(q_idx), Q,
                                  C.cast(db._xstar_host, C.c_void_p), C.cast(db._ratio_host, C.c_void_p),
+                                 C.cast(db._lvl_ptrs, C.c_void_p), C.cast(db._lvl_pitch, C.c_void_p),
                                  dev.ptr(mask), mask.stride(0), dev.ptr(n_out), dev.ptr(counts),
                                  dev.ptr(db._filter_scratch), db._filter_scratch.numel(), dev.stream_ptr()))
     if trace is not None:

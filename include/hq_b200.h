@@ -155,13 +155,18 @@ int hq_filter_select(const float* scores, int64_t scores_stride, int64_t N, int 
  * *nonuniform); otherwise use hq_filter_level / hq_filter_select.
  *   rnorm [N, L]   per-level row norms (NaN where 0), written by hq_filter_level_norms
  *   xstar [L]      smallest float x with ((x + 1) / 2 evaluated in float32) >= thr_l
- *   counts         optional [L][3][Q] (n_alive, n_pass, n_out) per level                       */
+ *   counts         optional [L][3][Q] (n_alive, n_pass, n_out) per level
+ */
 int hq_filter_fast_supported(const hq_index_layout* layout);
 int hq_filter_level_norms(const float* idx, const uint16_t* lens, int64_t N, const hq_index_layout* layout,
                           float* rnorm, int32_t* nonuniform, void* stream);
 int64_t hq_filter_fast_scratch_bytes(int64_t N, int Q, const hq_index_layout* layout);
+/* lvl_rows / lvl_pitch: optional HOST arrays [L] of device pointers / pitches of per-level
+ * copies [N, pitch] of the index rows (pitch % 4 == 0); they are small enough to stay in the
+ * 126 MB L2 while every query re-ranks its candidates. */
 int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, const hq_index_layout* layout,
                    const float* q_idx, int Q, const float* xstar, const double* ratio,
+                   const float* const* lvl_rows, const int32_t* lvl_pitch,
                    uint32_t* mask, int64_t mask_stride, int32_t* n_out, int32_t* counts,
                    void* scratch, int64_t scratch_bytes, void* stream);
 
