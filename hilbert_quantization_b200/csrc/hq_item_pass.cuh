@@ -12,7 +12,8 @@
 
 namespace item_pass {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 256;          // data threads (own the quads / row segments)
+constexpr int kBlock = kThreads + 32;  // + one index warp: levels >= 4 and the entries that read them
 constexpr int kQPT = 4;               // quads per thread per chunk (1024 quads = 4096 positions)
 
 template <int MODE> struct PT { using type = float; };
@@ -33,7 +34,7 @@ struct Geo {
 };
 
 template <int DIR, int MODE, int LOG2T>
-__global__ void __launch_bounds__(kThreads, 3) k_item_pass(const TileParams p) {
+__global__ void __launch_bounds__(kBlock, 3) k_item_pass(const TileParams p) {
     using P = typename PT<MODE>::type;
     using G = Geo<LOG2T>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -41,6 +42,11 @@ __global__ void __launch_bounds__(kThreads, 3) k_item_pass(const TileParams p) {
     P* const s_pyr0 = reinterpret_cast<P*>(s_img0 + 2 * G::img_floats + ((2 * G::img_floats) & 1));   // two pyramids
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // Warp 8 never touches global data rows: it finishes the pyramid of chunk i (levels >= 4) and
+    // writes the index entries that read those levels while warps 0-7 already store chunk i and
+    // scatter chunk i+1.  ncu showed the data warps waiting ~17 % of the time at the chunk barrier
+    // for the one warp that carried this serial tail.
+    const bool idx_warp = warp == kThreads / 32;
     const bool want_pyr = p.plan_len > 0 && p.min_level <= 32;
     const bool low_levels = p.min_level <= 2;
     const int64_t side2d_stride = DIR == 0 ? p.grid_stride : p.src_stride;
@@ -68,12 +74,12 @@ __global__ void __launch_bounds__(kThreads, 3) k_item_pass(const TileParams p) {
         row_s[r] = il * G::T * G::pitch + vy * G::pitch + vx;
         row_g[r] = (int32_t)(il * side2d_stride + vy * G::T + vx);
         cur_off[r] = (int32_t)(il * curve_stride + 4 * q);
-        if (DIR == 1 || (int64_t)4 * q < p.D) live_bits |= 1u << r;
-        if (DIR == 1 || (int64_t)4 * (q & ~31u) < p.D) wlive_bits |= 1u << r;
+        if (!idx_warp && (DIR == 1 || (int64_t)4 * q < p.D)) live_bits |= 1u << r;
+        if (!idx_warp && (DIR == 1 || (int64_t)4 * (q & ~31u) < p.D)) wlive_bits |= 1u << r;
     }
 
-    for (uint32_t i = tid; i < 2 * G::img_floats; i += kThreads) s_img0[i] = 0.f;
-    for (uint32_t i = tid; i < 2 * G::pyr_vals; i += kThreads) s_pyr0[i] = (P)0;
+    for (uint32_t i = tid; i < 2 * G::img_floats; i += kBlock) s_img0[i] = 0.f;
+    for (uint32_t i = tid; i < 2 * G::pyr_vals; i += kBlock) s_pyr0[i] = (P)0;
     __syncthreads();
 
     // 2-D side (DIR 1) or curve side (DIR 0) quads of one chunk; `left` = items remaining
@@ -92,17 +98,29 @@ __global__ void __launch_bounds__(kThreads, 3) k_item_pass(const TileParams p) {
         }
     };
 
+    // hand-off counters between the data warps and the index warp (monotonic, per CTA):
+    //   s_ready = number of data-warp arrivals (8 per chunk) after their pyramid levels are in smem
+    //   s_done  = number of chunks whose index entries the index warp has finished
+    __shared__ volatile uint32_t s_ready, s_done;
+    if (tid == 0) { s_ready = 0; s_done = 0; }
+    __syncthreads();
+
     float4 v[kQPT];
     int64_t chunk = blockIdx.x;
     if (chunk < p.num_chunks) load_chunk(chunk, v);
-    uint32_t buf = 0;
-    for (; chunk < p.num_chunks; chunk += gridDim.x, buf ^= 1u) {
+    uint32_t buf = 0, iter = 0;
+    for (; chunk < p.num_chunks; chunk += gridDim.x, buf ^= 1u, ++iter) {
         const int64_t item0 = chunk * G::ipc;
         const int64_t left = p.N - item0;
         const bool full = left >= (int64_t)G::ipc;
         float* img = s_img0 + buf * G::img_floats;
         P* pyrb = s_pyr0 + buf * G::pyr_vals;
 
+        // the buffers of this chunk were last used by chunk iter-2: its index entries must be out
+        if (!idx_warp && p.plan_len > 0 && iter >= 2) {
+            while (s_done + 1 < iter) { }
+        }
+        // ---- data warps: curve-side quads -> tile image (or tile image -> quads for DIR 1) ----
         if (DIR == 0) {
 #pragma unroll
             for (int r = 0; r < kQPT; ++r) {
@@ -115,44 +133,69 @@ __global__ void __launch_bounds__(kThreads, 3) k_item_pass(const TileParams p) {
             }
         } else {
 #pragma unroll
-            for (int r = 0; r < kQPT; ++r) *reinterpret_cast<float4*>(img + row_s[r]) = v[r];
-            __syncthreads();
-            float* sbase = p.stream_out ? p.stream_out + item0 * p.stream_stride : nullptr;
-#pragma unroll
-            for (int r = 0; r < kQPT; ++r) {
-                v[r] = make_float4(img[slot01[r] & 0xffffu], img[slot01[r] >> 16], img[slot23[r] & 0xffffu], img[slot23[r] >> 16]);
-                const uint32_t qi = tid + r * kThreads;
-                const uint32_t il = qi >> G::log2qpi, q = qi & (G::qpi - 1);
-                if (sbase && (full || (int64_t)il < left) && (int64_t)4 * q < p.D)
-                    __stcs(reinterpret_cast<float4*>(sbase + cur_off[r]), v[r]);
-            }
+            for (int r = 0; r < kQPT; ++r)
+                if (!idx_warp) *reinterpret_cast<float4*>(img + row_s[r]) = v[r];
         }
-
-        if (want_pyr) {
-#pragma unroll
-            for (int r = 0; r < kQPT; ++r) {
-                if (!((wlive_bits >> r) & 1u)) continue;                   // warp-uniform
-                const uint32_t qi = tid + r * kThreads;
-                const uint32_t il = qi >> G::log2qpi, q = qi & (G::qpi - 1);
-                P* pyr = pyrb + il * G::pyr_items;
-                const P m1 = mean4<MODE>(v[r].x, v[r].y, v[r].z, v[r].w);
-                if (LOG2T < 2) { pyr[q] = m1; continue; }
-                if (low_levels && p.min_level <= 1) pyr[q] = m1;
-                const P m2 = group_mean<MODE>(m1, 1);
-                if (LOG2T < 3) { if ((lane & 3) == 0) pyr[G::base2 + (q >> 2)] = m2; continue; }
-                if (low_levels && (lane & 3) == 0) pyr[G::base2 + (q >> 2)] = m2;
-                const P m3 = group_mean<MODE>(m2, 4);
-                if ((lane & 15) == 0) pyr[G::base3 + (q >> 4)] = m3;
-            }
-        }
-        __syncthreads();
+        if (!idx_warp) asm volatile("bar.sync 2, %0;" ::"n"(kThreads) : "memory");   // image complete (data warps only)
 
         // next chunk's loads go out now; they land while this chunk is finished and stored
         float4 nv[kQPT];
         const int64_t next = chunk + gridDim.x;
-        if (next < p.num_chunks) load_chunk(next, nv);
+        if (next < p.num_chunks && !idx_warp) load_chunk(next, nv);
 
-        if (p.plan_len > 0 && warp == 0) {
+        if (!idx_warp) {
+            // ---- 2-D / curve side out first (fire and forget), the pyramid chain afterwards ----
+            if (DIR == 0) {
+                if (p.grid_out) {
+                    float* gbase = p.grid_out + item0 * p.grid_stride;
+#pragma unroll
+                    for (int r = 0; r < kQPT; ++r) {
+                        const uint32_t il = (tid + r * kThreads) >> G::log2qpi;
+                        if (full || (int64_t)il < left) {
+                            const float4 val = *reinterpret_cast<const float4*>(img + row_s[r]);
+                            __stcs(reinterpret_cast<float4*>(gbase + row_g[r]), val);
+                        }
+                    }
+                }
+            } else {
+                float* sbase = p.stream_out ? p.stream_out + item0 * p.stream_stride : nullptr;
+#pragma unroll
+                for (int r = 0; r < kQPT; ++r) {
+                    v[r] = make_float4(img[slot01[r] & 0xffffu], img[slot01[r] >> 16], img[slot23[r] & 0xffffu], img[slot23[r] >> 16]);
+                    const uint32_t qi = tid + r * kThreads;
+                    const uint32_t il = qi >> G::log2qpi, q = qi & (G::qpi - 1);
+                    if (sbase && (full || (int64_t)il < left) && (int64_t)4 * q < p.D)
+                        __stcs(reinterpret_cast<float4*>(sbase + cur_off[r]), v[r]);
+                }
+            }
+            if (want_pyr) {
+#pragma unroll
+                for (int r = 0; r < kQPT; ++r) {
+                    if (!((wlive_bits >> r) & 1u)) continue;                   // warp-uniform
+                    const uint32_t qi = tid + r * kThreads;
+                    const uint32_t il = qi >> G::log2qpi, q = qi & (G::qpi - 1);
+                    P* pyr = pyrb + il * G::pyr_items;
+                    const P m1 = mean4<MODE>(v[r].x, v[r].y, v[r].z, v[r].w);
+                    if (LOG2T < 2) { pyr[q] = m1; continue; }
+                    if (low_levels && p.min_level <= 1) pyr[q] = m1;
+                    const P m2 = group_mean<MODE>(m1, 1);
+                    if (LOG2T < 3) { if ((lane & 3) == 0) pyr[G::base2 + (q >> 2)] = m2; continue; }
+                    if (low_levels && (lane & 3) == 0) pyr[G::base2 + (q >> 2)] = m2;
+                    const P m3 = group_mean<MODE>(m2, 4);
+                    if ((lane & 15) == 0) pyr[G::base3 + (q >> 4)] = m3;
+                }
+            }
+            // levels 1..3 (and the tile image) of this chunk are in shared memory: hand them to the index
+            // warp without waiting for it
+            if (p.plan_len > 0) {
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) atomicAdd(const_cast<uint32_t*>(&s_ready), 1u);
+            }
+        } else if (p.plan_len > 0) {
+            // ---- index warp: wait for the 8 data warps of this chunk, finish the pyramid, write the entries ----
+            while (s_ready < (kThreads / 32) * (iter + 1)) { }
+            __threadfence_block();
             if (want_pyr && LOG2T >= 4) {
                 uint32_t base_prev = G::base3, cnt_prev = G::qpi >> 4;
 #pragma unroll
@@ -186,18 +229,8 @@ __global__ void __launch_bounds__(kThreads, 3) k_item_pass(const TileParams p) {
                     out[il * p.idx_stride + i] = val;
                 }
             }
-        }
-
-        if (DIR == 0 && p.grid_out) {
-            float* gbase = p.grid_out + item0 * p.grid_stride;
-#pragma unroll
-            for (int r = 0; r < kQPT; ++r) {
-                const uint32_t il = (tid + r * kThreads) >> G::log2qpi;
-                if (full || (int64_t)il < left) {
-                    const float4 val = *reinterpret_cast<const float4*>(img + row_s[r]);
-                    __stcs(reinterpret_cast<float4*>(gbase + row_g[r]), val);
-                }
-            }
+            __syncwarp();
+            if (lane == 0) s_done = iter + 1;
         }
 #pragma unroll
         for (int r = 0; r < kQPT; ++r) v[r] = nv[r];
@@ -216,12 +249,12 @@ int launch_t(const TileParams& p, cudaStream_t st) {
     static int per_sm = 0;
     if (per_sm == 0) {
         HQ_CUDA_OK(cudaFuncSetAttribute(k_item_pass<DIR, MODE, LOG2T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        HQ_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_item_pass<DIR, MODE, LOG2T>, kThreads, smem));
+        HQ_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_item_pass<DIR, MODE, LOG2T>, kBlock, smem));
         if (per_sm < 1) per_sm = 1;
     }
     int64_t blocks = (int64_t)hq_cached_sm_count() * per_sm;
     if (blocks > p.num_chunks) blocks = p.num_chunks;
-    k_item_pass<DIR, MODE, LOG2T><<<(unsigned)blocks, kThreads, smem, st>>>(p);
+    k_item_pass<DIR, MODE, LOG2T><<<(unsigned)blocks, kBlock, smem, st>>>(p);
     HQ_LAUNCH_OK("k_item_pass");
     return HQ_OK;
 }
