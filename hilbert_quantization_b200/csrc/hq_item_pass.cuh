@@ -15,6 +15,7 @@ namespace item_pass {
 constexpr int kThreads = 256;          // data threads (own the quads / row segments)
 constexpr int kBlock = kThreads + 32;  // + one index warp: levels >= 4 and the entries that read them
 constexpr int kQPT = 4;               // quads per thread per chunk (1024 quads = 4096 positions)
+constexpr int kPlanCap = 1024;        // gather plans up to this many entries are staged in shared memory
 
 template <int MODE> struct PT { using type = float; };
 template <> struct PT<1> { using type = double; };
@@ -40,6 +41,7 @@ __global__ void __launch_bounds__(kBlock, 3) k_item_pass(const TileParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* const s_img0 = reinterpret_cast<float*>(smem_raw);                                   // two tile images
     P* const s_pyr0 = reinterpret_cast<P*>(s_img0 + 2 * G::img_floats + ((2 * G::img_floats) & 1));   // two pyramids
+    int32_t* const s_plan = reinterpret_cast<int32_t*>(s_pyr0 + 2 * G::pyr_vals);                 // gather plan (<= kPlanCap)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // Warp 8 never touches global data rows: it finishes the pyramid of chunk i (levels >= 4) and
@@ -48,7 +50,6 @@ __global__ void __launch_bounds__(kBlock, 3) k_item_pass(const TileParams p) {
     // for the one warp that carried this serial tail.
     const bool idx_warp = warp == kThreads / 32;
     const bool want_pyr = p.plan_len > 0 && p.min_level <= 32;
-    const bool low_levels = p.min_level <= 2;
     const int64_t side2d_stride = DIR == 0 ? p.grid_stride : p.src_stride;
     const int64_t curve_stride = DIR == 0 ? p.src_stride : p.stream_stride;
 
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(kBlock, 3) k_item_pass(const TileParams p) {
     uint32_t slot01[kQPT], slot23[kQPT];      // tile-image offsets of the quad's four cells (16 bit each)
     uint32_t row_s[kQPT];                     // tile-image offset of the row segment this thread stores / loads
     int32_t cur_off[kQPT], row_g[kQPT];       // global offsets (curve side / 2-D side) from the chunk's first item
-    uint32_t live_bits = 0, wlive_bits = 0;   // bit r: quad r holds data (d < D) / its warp does
+    uint32_t live_bits = 0;                   // bit r: quad r holds data (d < D)
 #pragma unroll
     for (int r = 0; r < kQPT; ++r) {
         const uint32_t qi = tid + r * kThreads;
@@ -75,9 +76,11 @@ __global__ void __launch_bounds__(kBlock, 3) k_item_pass(const TileParams p) {
         row_g[r] = (int32_t)(il * side2d_stride + vy * G::T + vx);
         cur_off[r] = (int32_t)(il * curve_stride + 4 * q);
         if (!idx_warp && (DIR == 1 || (int64_t)4 * q < p.D)) live_bits |= 1u << r;
-        if (!idx_warp && (DIR == 1 || (int64_t)4 * (q & ~31u) < p.D)) wlive_bits |= 1u << r;
     }
 
+    const bool plan_in_smem = p.plan_len <= kPlanCap;
+    if (plan_in_smem)
+        for (int i = tid; i < p.plan_len; i += kBlock) s_plan[i] = __ldg(p.plan + i);
     for (uint32_t i = tid; i < 2 * G::img_floats; i += kBlock) s_img0[i] = 0.f;
     for (uint32_t i = tid; i < 2 * G::pyr_vals; i += kBlock) s_pyr0[i] = (P)0;
     __syncthreads();
@@ -99,10 +102,9 @@ __global__ void __launch_bounds__(kBlock, 3) k_item_pass(const TileParams p) {
     };
 
     // hand-off counters between the data warps and the index warp (monotonic, per CTA):
-    //   s_ready = number of data-warp arrivals (8 per chunk) after their pyramid levels are in smem
     //   s_done  = number of chunks whose index entries the index warp has finished
-    __shared__ volatile uint32_t s_ready, s_done;
-    if (tid == 0) { s_ready = 0; s_done = 0; }
+    __shared__ volatile uint32_t s_done;
+    if (tid == 0) s_done = 0;
     __syncthreads();
 
     float4 v[kQPT];
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(kBlock, 3) k_item_pass(const TileParams p) {
 
         // the buffers of this chunk were last used by chunk iter-2: its index entries must be out
         if (!idx_warp && p.plan_len > 0 && iter >= 2) {
-            while (s_done + 1 < iter) { }
+            while (s_done + 1 < iter) __nanosleep(64);
         }
         // ---- data warps: curve-side quads -> tile image (or tile image -> quads for DIR 1) ----
         if (DIR == 0) {
@@ -169,41 +171,41 @@ __global__ void __launch_bounds__(kBlock, 3) k_item_pass(const TileParams p) {
                 }
             }
             if (want_pyr) {
+                // level 1 only (four adds, no shuffle chain on the data warps); the index warp builds
+                // every higher level from shared memory, off the critical path
 #pragma unroll
                 for (int r = 0; r < kQPT; ++r) {
-                    if (!((wlive_bits >> r) & 1u)) continue;                   // warp-uniform
+                    if (!((live_bits >> r) & 1u)) continue;
                     const uint32_t qi = tid + r * kThreads;
                     const uint32_t il = qi >> G::log2qpi, q = qi & (G::qpi - 1);
-                    P* pyr = pyrb + il * G::pyr_items;
-                    const P m1 = mean4<MODE>(v[r].x, v[r].y, v[r].z, v[r].w);
-                    if (LOG2T < 2) { pyr[q] = m1; continue; }
-                    if (low_levels && p.min_level <= 1) pyr[q] = m1;
-                    const P m2 = group_mean<MODE>(m1, 1);
-                    if (LOG2T < 3) { if ((lane & 3) == 0) pyr[G::base2 + (q >> 2)] = m2; continue; }
-                    if (low_levels && (lane & 3) == 0) pyr[G::base2 + (q >> 2)] = m2;
-                    const P m3 = group_mean<MODE>(m2, 4);
-                    if ((lane & 15) == 0) pyr[G::base3 + (q >> 4)] = m3;
+                    pyrb[il * G::pyr_items + q] = mean4<MODE>(v[r].x, v[r].y, v[r].z, v[r].w);
                 }
             }
             // levels 1..3 (and the tile image) of this chunk are in shared memory: hand them to the index
             // warp without waiting for it
+            // Hand-off = named barrier, alternating ids 1 / 3 per chunk: the data warps arrive without
+            // waiting (bar.arrive orders their shared-memory writes for the thread that syncs), the index
+            // warp blocks in hardware -- no polling, no fence on the data warps.  Two ids are enough
+            // because the s_done wait above keeps the data warps at most two chunks ahead.
             if (p.plan_len > 0) {
-                __threadfence_block();
-                __syncwarp();
-                if (lane == 0) atomicAdd(const_cast<uint32_t*>(&s_ready), 1u);
+                if (iter & 1u) asm volatile("bar.arrive 3, %0;" ::"n"(kBlock) : "memory");
+                else asm volatile("bar.arrive 1, %0;" ::"n"(kBlock) : "memory");
             }
         } else if (p.plan_len > 0) {
             // ---- index warp: wait for the 8 data warps of this chunk, finish the pyramid, write the entries ----
-            while (s_ready < (kThreads / 32) * (iter + 1)) { }
-            __threadfence_block();
-            if (want_pyr && LOG2T >= 4) {
-                uint32_t base_prev = G::base3, cnt_prev = G::qpi >> 4;
+            if (iter & 1u) asm volatile("bar.sync 3, %0;" ::"n"(kBlock) : "memory");
+            else asm volatile("bar.sync 1, %0;" ::"n"(kBlock) : "memory");
+            if (want_pyr) {
+                // runs at d >= D are never touched: they stay zero from the one-time clear
+                uint32_t base_prev = 0, cnt_prev = G::qpi;
+                uint32_t live_prev = DIR == 1 ? G::qpi : (uint32_t)((p.D + 3) >> 2);
 #pragma unroll
-                for (int k = 4; k <= LOG2T; ++k) {
+                for (int k = 2; k <= LOG2T; ++k) {
                     const uint32_t cnt = cnt_prev >> 2, base = base_prev + cnt_prev;
+                    const uint32_t live = (live_prev + 3) >> 2;
                     for (uint32_t il = 0; il < G::ipc; ++il) {
                         P* pyr = pyrb + il * G::pyr_items;
-                        for (uint32_t j = lane; j < cnt; j += 32) {
+                        for (uint32_t j = lane; j < live; j += 32) {
                             const P a = pyr[base_prev + 4 * j], b = pyr[base_prev + 4 * j + 1];
                             const P c = pyr[base_prev + 4 * j + 2], d = pyr[base_prev + 4 * j + 3];
                             pyr[base + j] = MODE == 0 ? (P)(((a + b) + (c + d)) * (P)0.25) : (P)((((a + b) + c) + d) * (P)0.25);
@@ -212,6 +214,7 @@ __global__ void __launch_bounds__(kBlock, 3) k_item_pass(const TileParams p) {
                     __syncwarp();
                     base_prev = base;
                     cnt_prev = cnt;
+                    live_prev = live;
                 }
             }
             P* out = reinterpret_cast<P*>(p.idx_out) + item0 * p.idx_stride;
@@ -220,13 +223,13 @@ __global__ void __launch_bounds__(kBlock, 3) k_item_pass(const TileParams p) {
                 const float* im = img + il * G::T * G::pitch;
                 const P* pyr = pyrb + il * G::pyr_items;
                 for (int i = lane; i < p.plan_len; i += 32) {
-                    const int32_t off = __ldg(p.plan + i);
+                    const int32_t off = plan_in_smem ? s_plan[i] : __ldg(p.plan + i);
                     P val = (P)0;
                     if (off >= 0) {
                         if ((uint32_t)off < G::cells) val = (P)im[((uint32_t)off >> LOG2T) * G::pitch + ((uint32_t)off & (G::T - 1))];
                         else val = pyr[(uint32_t)off - G::cells];
                     }
-                    out[il * p.idx_stride + i] = val;
+                    __stcs(out + il * p.idx_stride + i, val);
                 }
             }
             __syncwarp();
@@ -240,7 +243,7 @@ __global__ void __launch_bounds__(kBlock, 3) k_item_pass(const TileParams p) {
 template <int LOG2T>
 inline size_t smem_bytes(int mode) {
     using G = Geo<LOG2T>;
-    return (size_t)2 * G::img_floats * 4 + 8 + (size_t)2 * G::pyr_vals * (mode ? 8 : 4) + 16;
+    return (size_t)2 * G::img_floats * 4 + 8 + (size_t)2 * G::pyr_vals * (mode ? 8 : 4) + (size_t)kPlanCap * 4 + 16;
 }
 
 template <int DIR, int MODE, int LOG2T>
