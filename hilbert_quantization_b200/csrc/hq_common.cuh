@@ -39,6 +39,10 @@ void hq_note_launch(int n);     // bookkeeping for hq_launch_count (bench.py rep
 static inline bool hq_is_pow2(int64_t n) { return n > 0 && (n & (n - 1)) == 0; }
 static inline int hq_log2(int64_t n) { int k = 0; while ((int64_t(1) << k) < n) ++k; return k; }
 int hq_cached_sm_count();
+// tensor-core bit-plane pass of the coarse filter (hq_filter_tc.cu), used by hq_filter_fast
+int hq_filter_bits_tc_launch(const float* db_packed, const uint32_t* valid, int64_t valid_pitch, int64_t N,
+                             const hq_index_layout* layout, const float* q_idx, int Q, const float* xstar, float* q_packed,
+                             float* tq, uint32_t* bits, int64_t bits_pitch, cudaStream_t st);
 
 // ---- Hilbert curve, the reference's variant (core/hilbert_mapper.py:42-113) ----
 // d -> (x, y), low bit-pairs first.

@@ -34,8 +34,8 @@ struct BitsParams {
     const float* q_idx;          // [Q, Lsum]
     int Q;
     float xstar[3];
-    uint32_t* bits;              // [L][Q][words]
-    int64_t words;
+    uint32_t* bits;              // [L][Q][pitch]
+    int64_t words, pitch;
     int q_tiles;
 };
 
@@ -111,8 +111,8 @@ __global__ void __launch_bounds__(kRows, 2) k_filter_bits(const BitsParams p) {
     const int64_t word = row >> 5;
     const bool word_ok = (row0 + (tid & ~31)) < p.N;
     uint32_t* b0 = p.bits;
-    uint32_t* b1 = p.bits + (int64_t)p.Q * p.words;
-    uint32_t* b2 = p.bits + 2 * (int64_t)p.Q * p.words;
+    uint32_t* b1 = p.bits + (int64_t)p.Q * p.pitch;
+    uint32_t* b2 = p.bits + 2 * (int64_t)p.Q * p.pitch;
     for (int qq = 0; qq < kQT; qq += 4) {
         if (q0 + qq >= p.Q) break;
         float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
@@ -129,9 +129,9 @@ __global__ void __launch_bounds__(kRows, 2) k_filter_bits(const BitsParams p) {
             if (K1 > 0) w1 = __ballot_sync(0xffffffffu, in_range && (a1[u] >= __fmul_rn(s_tq[kQT + qq + u], n1)));
             if (K2 > 0) w2 = __ballot_sync(0xffffffffu, in_range && (a2[u] >= __fmul_rn(s_tq[2 * kQT + qq + u], n2)));
             if (lane == 0 && word_ok) {
-                b0[(int64_t)q * p.words + word] = w0;
-                if (K1 > 0) b1[(int64_t)q * p.words + word] = w1;
-                if (K2 > 0) b2[(int64_t)q * p.words + word] = w2;
+                b0[(int64_t)q * p.pitch + word] = w0;
+                if (K1 > 0) b1[(int64_t)q * p.pitch + word] = w1;
+                if (K2 > 0) b2[(int64_t)q * p.pitch + word] = w2;
             }
         }
     }
@@ -222,8 +222,8 @@ __device__ SelSmall block_select_smallest(const uint32_t* __restrict__ keys, con
 }
 
 struct CascadeParams {
-    const uint32_t* bits;        // [L][Q][words]
-    int64_t words;
+    const uint32_t* bits;        // [L][Q][bits_pitch]
+    int64_t words, bits_pitch;
     const float* idx;            // [N, Lsum]
     const float* lvl[3];         // optional per-level copies [N, lvl_pitch[l]] (small enough to stay in L2)
     int lvl_pitch[3];
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(1024, 1) k_filter_cascade(const CascadeParams 
         int64_t n_alive = p.N;
         for (int l = 0; l < L; ++l) {
             // ---- alive &= P_l, count (4 independent word pairs in flight per thread) ----
-            const uint32_t* P = p.bits + ((int64_t)l * p.Q + q) * p.words;
+            const uint32_t* P = p.bits + ((int64_t)l * p.Q + q) * p.bits_pitch;
             uint32_t c = 0;
             for (int64_t w0 = tid; w0 < p.words; w0 += 4 * (int64_t)nt) {
                 uint32_t a[4], pb[4];
@@ -519,18 +519,22 @@ extern "C" int hq_filter_fast_supported(const hq_index_layout* layout) {
     return 1;
 }
 
+static inline int64_t plane_pitch(int64_t N) { return ((N + 31) / 32 + 7) & ~(int64_t)7; }      // words, 32-byte rows
+static inline int64_t up16(int64_t b) { return (b + 15) & ~(int64_t)15; }
+
 extern "C" int64_t hq_filter_fast_scratch_bytes(int64_t N, int Q, const hq_index_layout* layout) {
     if (!layout || N <= 0 || Q <= 0) return 0;
-    const int64_t words = (N + 31) / 32;
     int grid = hq_cached_sm_count();
     if (grid > Q) grid = Q;
-    return (int64_t)layout->L * Q * words * 4 + (int64_t)grid * N * 8;
+    // bit planes | cascade key / row lists | packed query operand + thresholds of the tensor-core pass
+    return (int64_t)layout->L * Q * plane_pitch(N) * 4 + up16((int64_t)grid * N * 8) + (int64_t)Q * 128 * 4 + up16((int64_t)3 * Q * 4);
 }
 
 extern "C" int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, const hq_index_layout* layout, const float* q_idx, int Q,
                               const float* xstar, const double* ratio, const float* const* lvl_rows, const int32_t* lvl_pitch,
-                              uint32_t* mask, int64_t mask_stride, int32_t* n_out, int32_t* counts, void* scratch,
-                              int64_t scratch_bytes, void* stream) {
+                              const float* db_packed, const uint32_t* valid, int64_t valid_pitch, uint32_t* mask,
+                              int64_t mask_stride, int32_t* n_out, int32_t* counts, void* scratch, int64_t scratch_bytes,
+                              void* stream) {
     HQ_REQUIRE(hq_filter_fast_supported(layout), "index layout not supported by the fast filter");
     HQ_REQUIRE(N >= 0 && Q >= 0, "negative size");
     if (N == 0 || Q == 0) return HQ_OK;
@@ -539,17 +543,28 @@ extern "C" int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, c
     HQ_REQUIRE(mask_stride * 32 >= N, "mask stride too small");
     const int64_t need = hq_filter_fast_scratch_bytes(N, Q, layout);
     HQ_REQUIRE(scratch && scratch_bytes >= need, "scratch too small: need %lld bytes", (long long)need);
-    const int64_t words = (N + 31) / 32;
+    const int64_t words = (N + 31) / 32, pitch = plane_pitch(N);
     const int L = layout->L;
     cudaStream_t st = (cudaStream_t)stream;
+    int grid = hq_cached_sm_count();
+    if (grid > Q) grid = Q;
+    uint32_t* const planes = reinterpret_cast<uint32_t*>(scratch);
+    uint32_t* const sc_keys = planes + (int64_t)L * Q * pitch;
+    uint32_t* const sc_rows = sc_keys + (int64_t)grid * N;
+    float* const q_packed = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(sc_keys) + up16((int64_t)grid * N * 8));
+    float* const tq = q_packed + (int64_t)Q * 128;
 
     BitsParams bp{};
     bp.idx = idx; bp.rnorm = rnorm; bp.N = N; bp.lay = *layout; bp.q_idx = q_idx; bp.Q = Q;
     for (int l = 0; l < 3; ++l) bp.xstar[l] = l < L ? xstar[l] : 0.f;
-    bp.bits = reinterpret_cast<uint32_t*>(scratch); bp.words = words; bp.q_tiles = (Q + kQT - 1) / kQT;
+    bp.bits = planes; bp.words = words; bp.pitch = pitch; bp.q_tiles = (Q + kQT - 1) / kQT;
     const int k0 = layout->lvl_keff[0], k1 = L > 1 ? layout->lvl_keff[1] : 0, k2 = L > 2 ? layout->lvl_keff[2] : 0;
     int rc;
-    if (L == 3) {
+    if (db_packed) {
+        // tensor-core pass (hq_filter_tc.cu): same planes, 8x fewer SM cycles
+        HQ_REQUIRE(valid, "the tensor-core filter needs the validity words of hq_filter_tc_valid");
+        rc = hq_filter_bits_tc_launch(db_packed, valid, valid_pitch, N, layout, q_idx, Q, xstar, q_packed, tq, planes, pitch, st);
+    } else if (L == 3) {
         if (k0 <= 24 && k1 <= 8) rc = launch_bits<24, 8, 4>(bp, st);
         else if (k0 <= 32 && k1 <= 8) rc = launch_bits<32, 8, 4>(bp, st);
         else rc = launch_bits<64, 16, 4>(bp, st);
@@ -563,7 +578,7 @@ extern "C" int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, c
     if (rc != HQ_OK) return rc;
 
     CascadeParams cp{};
-    cp.bits = bp.bits; cp.words = words; cp.idx = idx; cp.N = N; cp.lay = *layout; cp.q_idx = q_idx; cp.Q = Q;
+    cp.bits = bp.bits; cp.words = words; cp.bits_pitch = pitch; cp.idx = idx; cp.N = N; cp.lay = *layout; cp.q_idx = q_idx; cp.Q = Q;
     for (int l = 0; l < 8; ++l) {
         cp.ratio[l] = l < L ? ratio[l] : 1.0;
         // survivors of level l score >= (x*_l + 1) / 2 (up to rounding): offset keys from a little below it
@@ -587,10 +602,8 @@ extern "C" int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, c
         HQ_REQUIRE(!cp.lvl[l] || (cp.lvl_pitch[l] % 4 == 0 && cp.lvl_pitch[l] >= ((layout->lvl_keff[l] + 3) & ~3)), "bad level pitch");
     }
     cp.mask = mask; cp.mask_stride = mask_stride; cp.counts = counts; cp.n_out = n_out;
-    int grid = hq_cached_sm_count();
-    if (grid > Q) grid = Q;
-    cp.scratch_keys = bp.bits + (int64_t)L * Q * words;
-    cp.scratch_rows = cp.scratch_keys + (int64_t)grid * N;
+    cp.scratch_keys = sc_keys;
+    cp.scratch_rows = sc_rows;
     k_filter_cascade<<<grid, 1024, 0, st>>>(cp);
     HQ_LAUNCH_OK("k_filter_cascade");
     return HQ_OK;

@@ -1,0 +1,428 @@
+// K5 on the tensor cores: the per-level threshold tests of the RAG progressive filter
+// (rag/search/engine.py:178-287) for Q queries x N rows as one tcgen05 pass that writes bit
+// planes P_l[q][row] = (score_l(q, row) >= thr_l).  It replaces k_filter_bits (CUDA-core FMAs,
+// 4.0 ms for 1024 x 1 M x 36 values, issue bound) and feeds the same cascade kernel.
+//
+// Accuracy.  The test must agree with the fp32 reference except for rows whose score lies
+// within ~2e-6 of the threshold, so a plain tf32 contraction (10-bit mantissa) is not enough.
+// Every operand value x is split exactly: hi = x with the low 13 mantissa bits cleared (a tf32
+// number), lo = (x - hi) truncated the same way; the contraction runs over the three products
+// hi*hi + hi*lo + lo*hi, laid out along K as  A = [q_hi | q_hi | q_lo],  B = [c_hi | c_lo | c_hi].
+// The dropped terms are below 2^-21 relative per product (score error < 3e-7).  Database
+// rows are pre-scaled by 1/|c_l|, so the test is  dot >= x*_l * |q_l|  with a per-thread
+// constant; zero-norm rows are all-zero operands and are cleared through a per-level validity
+// word, zero-norm queries carry a NaN threshold.
+//
+//   warp 0     : TMA producer (query tile once per unit, 64-row database tiles, 4 stages)
+//   warp 1     : TMEM allocator + tcgen05.mma.kind::tf32 issuer: M = 128 queries, N = 64 rows,
+//                K = 8 per instruction; one [128 x 64] accumulator per level, two sets
+//   warps 2..9 : epilogue, thread = (query, 32-row half of the tile): tcgen05.ld 32 columns per
+//                level, FADD + funnel shift per element builds the 32-bit pass word, words are
+//                staged in shared memory and flushed as 32-byte runs (8 words = 4 tiles)
+#include "hq_tc.cuh"
+#include <string.h>
+
+using namespace hq_tc;
+
+namespace {
+
+constexpr int FM = 128;                        // queries per tile (MMA M)
+constexpr int FR = 64;                         // database rows per tile (MMA N)
+constexpr int KS = 128;                        // packed floats per row: 4 slabs of 32 (128 B)
+constexpr int F_STAGES = 4;
+constexpr uint32_t A_SLAB_BYTES = FM * 128;    // 16 KB
+constexpr uint32_t B_SLAB_BYTES = FR * 128;    // 8 KB
+constexpr uint32_t A_BYTES = 4 * A_SLAB_BYTES;
+constexpr uint32_t B_STAGE_BYTES = 4 * B_SLAB_BYTES;
+constexpr int F_THREADS = 320;
+constexpr int EPI_THREADS = 256;
+constexpr uint32_t ACC_COLS = 3 * FR;          // one accumulator set: 3 levels x 64 columns
+constexpr uint32_t F_TMEM_COLS = 512;
+constexpr uint32_t kIdescTf32 = make_idesc(2 /*tf32*/, FM, FR);
+constexpr int TILE_GROUP = 4;                  // tiles per flush: 8 words = one 32-byte sector per query and level
+constexpr int STAGE_PITCH = 2 * TILE_GROUP + 1;
+
+struct Segs {
+    int L;
+    int off[3];        // first packed column of the level
+    int kp[3];         // level width padded to 8 (one tf32 k-step)
+    int n_slabs;       // 128-byte slabs that hold data
+};
+
+bool make_segs(const hq_index_layout* lay, Segs& s) {
+    if (!lay || lay->L < 1 || lay->L > 3) return false;
+    int off = 0;
+    s.L = lay->L;
+    for (int l = 0; l < 3; ++l) { s.off[l] = 0; s.kp[l] = 0; }
+    for (int l = 0; l < lay->L; ++l) {
+        if (lay->lvl_keff[l] < 1) return false;
+        s.kp[l] = (lay->lvl_keff[l] + 7) & ~7;
+        s.off[l] = off;
+        off += 3 * s.kp[l];
+    }
+    if (off > KS) return false;
+    s.n_slabs = (off + 31) / 32;
+    return true;
+}
+
+struct FtcParams {
+    int64_t N;
+    int Q, L;
+    int seg_off[3], ksteps[3];
+    int n_slabs;
+    int m_tiles, n_tiles, n_ranges, tiles_per_range, num_units;
+    const float* tq;            // [3][Q]  x*_l * |q_l| (NaN when |q_l| == 0)
+    const uint32_t* valid;      // [L][valid_pitch] bit r: row r has a non-zero level norm
+    int64_t valid_pitch;
+    uint32_t* bits;             // [L][Q][bits_pitch]
+    int64_t words, bits_pitch;
+};
+
+__device__ __forceinline__ uint32_t pass_word(const uint32_t (&r)[32], float tq) {
+    // bit j = (r[j] >= tq): the sign of (r[j] - tq) is shifted in element by element
+    uint32_t w = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const float d = __fadd_rn(__uint_as_float(r[j]), -tq);
+        w = __funnelshift_l(__float_as_uint(d), w, 1);
+    }
+    return ~__brev(w);
+}
+
+__global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_constant__ CUtensorMap map_q,
+                                                                 const __grid_constant__ CUtensorMap map_db, const FtcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* smem_a = smem;                                        // query tile, resident for a unit
+    uint8_t* smem_b = smem + A_BYTES;                              // F_STAGES database tiles
+    uint32_t* s_stage = reinterpret_cast<uint32_t*>(smem_b + F_STAGES * B_STAGE_BYTES);   // [3][128][STAGE_PITCH]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + ((3 * FM * STAGE_PITCH + 1) & ~1));
+    uint64_t* full_bar = bars;                      // [F_STAGES]
+    uint64_t* empty_bar = bars + F_STAGES;          // [F_STAGES]
+    uint64_t* tfull_bar = bars + 2 * F_STAGES;      // [2]
+    uint64_t* tempty_bar = bars + 2 * F_STAGES + 2; // [2]
+    uint64_t* qfull_bar = bars + 2 * F_STAGES + 4;
+    uint64_t* qempty_bar = bars + 2 * F_STAGES + 5;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * F_STAGES + 6);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && elect_one()) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_db)) : "memory");
+        for (int i = 0; i < F_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_THREADS); }
+        mbar_init(qfull_bar, 1);
+        mbar_init(qempty_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(F_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (elect_one()) {
+            uint32_t stage = 0, phase = 0, uq = 0;
+            for (int u = blockIdx.x; u < p.num_units; u += gridDim.x, ++uq) {
+                const int m_tile = u % p.m_tiles, range = u / p.m_tiles;
+                const int t0 = range * p.tiles_per_range;
+                const int t1 = min(p.n_tiles, t0 + p.tiles_per_range);
+                mbar_wait(qempty_bar, (uq & 1u) ^ 1u);                  // MMAs of the previous unit have retired
+                mbar_expect_tx(qfull_bar, (uint32_t)p.n_slabs * A_SLAB_BYTES);
+                for (int s = 0; s < p.n_slabs; ++s) tma_load_2d(&map_q, qfull_bar, smem_a + s * A_SLAB_BYTES, s * 32, m_tile * FM);
+                for (int t = t0; t < t1; ++t) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], (uint32_t)p.n_slabs * B_SLAB_BYTES);
+                    for (int s = 0; s < p.n_slabs; ++s)
+                        tma_load_2d(&map_db, &full_bar[stage], smem_b + stage * B_STAGE_BYTES + s * B_SLAB_BYTES, s * 32, t * FR);
+                    if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        uint32_t stage = 0, phase = 0, it = 0, uq = 0;
+        for (int u = blockIdx.x; u < p.num_units; u += gridDim.x, ++uq) {
+            const int range = u / p.m_tiles;
+            const int t0 = range * p.tiles_per_range;
+            const int t1 = min(p.n_tiles, t0 + p.tiles_per_range);
+            mbar_wait(qfull_bar, uq & 1u);
+            tc_fence_after();
+            for (int t = t0; t < t1; ++t, ++it) {
+                const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t a0 = smem_u32(smem_a), b0 = smem_u32(smem_b + stage * B_STAGE_BYTES);
+#pragma unroll
+                    for (int l = 0; l < 3; ++l) {
+                        if (l < p.L) {
+                            for (int s = 0; s < p.ksteps[l]; ++s) {
+                                const uint32_t off = (uint32_t)p.seg_off[l] + 8u * s;          // packed column of this k-step
+                                const uint32_t slab = off >> 5, byte = (off & 31u) * 4u;
+                                const uint64_t da = make_smem_desc(a0 + slab * A_SLAB_BYTES + byte);
+                                const uint64_t db = make_smem_desc(b0 + slab * B_SLAB_BYTES + byte);
+                                umma_tf32(tmem_base + acc * ACC_COLS + l * FR, da, db, kIdescTf32, s > 0 ? 1u : 0u);
+                            }
+                        }
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    umma_commit(&tfull_bar[acc]);
+                    if (t == t1 - 1) umma_commit(qempty_bar);
+                }
+                __syncwarp();
+                if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ================= epilogue =================
+        const int ew = warp & 3;                         // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;                // which 32 rows of the 64-row tile
+        const int q_in = ew * 32 + lane;
+        const int et = (warp - 2) * 32 + lane;           // 0..255
+        uint32_t it = 0;
+        for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+            const int m_tile = u % p.m_tiles, range = u / p.m_tiles;
+            const int t0 = range * p.tiles_per_range;
+            const int t1 = min(p.n_tiles, t0 + p.tiles_per_range);
+            const int q = m_tile * FM + q_in;
+            const bool q_ok = q < p.Q;
+            float tq[3];
+#pragma unroll
+            for (int l = 0; l < 3; ++l) tq[l] = (q_ok && l < p.L) ? __ldg(p.tq + (int64_t)l * p.Q + q) : __int_as_float(0x7fc00000);
+            for (int t = t0; t < t1; ++t, ++it) {
+                const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+                const int tl = (t - t0) & (TILE_GROUP - 1);
+                uint32_t vw[3];
+#pragma unroll
+                for (int l = 0; l < 3; ++l) vw[l] = l < p.L ? __ldg(p.valid + (int64_t)l * p.valid_pitch + 2 * t + half) : 0u;
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+                uint32_t r0[32], r1[32], r2[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * ACC_COLS + half * 32;
+                tmem_ld32(taddr, r0);
+                if (p.L > 1) tmem_ld32(taddr + FR, r1);
+                if (p.L > 2) tmem_ld32(taddr + 2 * FR, r2);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&tempty_bar[acc]);           // the values are in registers: the accumulators are free
+                uint32_t w0 = pass_word(r0, tq[0]) & vw[0];
+                if (!(tq[0] == tq[0])) w0 = 0;
+                s_stage[(0 * FM + q_in) * STAGE_PITCH + tl * 2 + half] = w0;
+                if (p.L > 1) {
+                    uint32_t w1 = pass_word(r1, tq[1]) & vw[1];
+                    if (!(tq[1] == tq[1])) w1 = 0;
+                    s_stage[(1 * FM + q_in) * STAGE_PITCH + tl * 2 + half] = w1;
+                }
+                if (p.L > 2) {
+                    uint32_t w2 = pass_word(r2, tq[2]) & vw[2];
+                    if (!(tq[2] == tq[2])) w2 = 0;
+                    s_stage[(2 * FM + q_in) * STAGE_PITCH + tl * 2 + half] = w2;
+                }
+                if (tl == TILE_GROUP - 1 || t == t1 - 1) {
+                    asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+                    const int64_t wb = 2 * (int64_t)(t - tl);
+                    const int n_w = 2 * (tl + 1);
+                    for (int e = et; e < 3 * FM * 2 * TILE_GROUP; e += EPI_THREADS) {
+                        const int l = e / (FM * 2 * TILE_GROUP);
+                        const int qq = (e / (2 * TILE_GROUP)) % FM;
+                        const int wi = e % (2 * TILE_GROUP);
+                        const int gq = m_tile * FM + qq;
+                        if (l < p.L && gq < p.Q && wi < n_w && wb + wi < p.words)
+                            p.bits[((int64_t)l * p.Q + gq) * p.bits_pitch + wb + wi] = s_stage[(l * FM + qq) * STAGE_PITCH + wi];
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(F_TMEM_COLS));
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// operand packing
+// ---------------------------------------------------------------------------------------
+struct PackParams {
+    const float* idx;       // [N, Lsum]
+    const float* rnorm;     // [N, L] (NaN = zero norm); null for queries
+    int64_t N;
+    hq_index_layout lay;
+    int is_query;
+    int seg_off[3], kp[3];
+    float* out;             // [N, KS]
+};
+
+__device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+__global__ void __launch_bounds__(256) k_pack_rows(const PackParams p) {
+    const int64_t total = p.N * KS;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i >> 7;
+        const int c = (int)(i & (KS - 1));
+        float outv = 0.f;
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            if (l < p.lay.L && c >= p.seg_off[l] && c < p.seg_off[l] + 3 * p.kp[l]) {
+                const int rel = c - p.seg_off[l];
+                const int part = rel / p.kp[l], j = rel - part * p.kp[l];
+                float x = j < p.lay.lvl_keff[l] ? __ldg(p.idx + row * p.lay.Lsum + p.lay.lvl_off[l] + j) : 0.f;
+                if (!p.is_query) {
+                    const float nrm = __ldg(p.rnorm + row * p.lay.L + l);
+                    x = (nrm == nrm) ? __fdiv_rn(x, nrm) : 0.f;
+                }
+                const float hi = trunc_tf32(x);
+                const float lo = trunc_tf32(__fadd_rn(x, -hi));
+                const bool want_lo = p.is_query ? (part == 2) : (part == 1);
+                outv = want_lo ? lo : hi;
+            }
+        }
+        p.out[i] = outv;
+    }
+}
+
+// tq[l][q] = x*_l * |q_l| (sequential fmaf norm, like the CUDA-core path); NaN for a zero query level
+__global__ void __launch_bounds__(256) k_query_tq(const float* __restrict__ q_idx, int Q, hq_index_layout lay, float x0, float x1, float x2,
+                                                  float* __restrict__ tq) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= Q * lay.L) return;
+    const int l = t / Q, q = t - l * Q;
+    const float* r = q_idx + (int64_t)q * lay.Lsum + lay.lvl_off[l];
+    float c = 0.f;
+    for (int j = 0; j < lay.lvl_keff[l]; ++j) { const float v = __ldg(r + j); c = fmaf(v, v, c); }
+    const float nq = sqrtf(c);
+    const float xs = l == 0 ? x0 : (l == 1 ? x1 : x2);
+    tq[(int64_t)l * Q + q] = nq > 0.f ? __fmul_rn(xs, nq) : __int_as_float(0x7fc00000);
+}
+
+__global__ void __launch_bounds__(256) k_valid_bits(const float* __restrict__ rnorm, int64_t N, int L, uint32_t* __restrict__ valid,
+                                                    int64_t valid_pitch) {
+    const int64_t n_pad = valid_pitch * 32;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n_pad * L; t += (int64_t)gridDim.x * blockDim.x) {
+        const int l = (int)(t / n_pad);
+        const int64_t row = t - (int64_t)l * n_pad;
+        bool ok = false;
+        if (row < N) { const float v = __ldg(rnorm + row * L + l); ok = v == v; }
+        const uint32_t w = __ballot_sync(0xffffffffu, ok);
+        if ((threadIdx.x & 31) == 0) valid[(int64_t)l * valid_pitch + (row >> 5)] = w;
+    }
+}
+
+void plan_units(int64_t N, int Q, int sms, FtcParams& p) {
+    p.m_tiles = (Q + FM - 1) / FM;
+    p.n_tiles = (int)((N + FR - 1) / FR);
+    int best_tp = p.n_tiles;
+    double best_eff = -1.0;
+    for (int waves = 1; waves <= 4; ++waves) {
+        int s = (waves * sms) / p.m_tiles;
+        if (s < 1) s = 1;
+        int tiles_per = (p.n_tiles + s - 1) / s;
+        tiles_per = (tiles_per + TILE_GROUP - 1) / TILE_GROUP * TILE_GROUP;     // flush groups stay sector aligned
+        s = (p.n_tiles + tiles_per - 1) / tiles_per;
+        const int units = s * p.m_tiles;
+        const int rounds = (units + sms - 1) / sms;
+        const double eff = (double)p.n_tiles * p.m_tiles / ((double)rounds * tiles_per * sms);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best_tp = tiles_per; }
+    }
+    p.tiles_per_range = best_tp;
+    p.n_ranges = (p.n_tiles + best_tp - 1) / best_tp;
+    p.num_units = p.n_ranges * p.m_tiles;
+}
+
+}  // namespace
+
+extern "C" int hq_filter_tc_supported(const hq_index_layout* layout) {
+    Segs s;
+    return make_segs(layout, s) ? 1 : 0;
+}
+
+extern "C" int64_t hq_filter_tc_valid_pitch(int64_t N) {
+    // words, rounded up to whole 64-row tiles
+    return (N + FR - 1) / FR * 2;
+}
+
+extern "C" int hq_filter_tc_pack(const float* idx, const float* rnorm, int64_t N, const hq_index_layout* layout, int is_query,
+                                 float* packed, void* stream) {
+    Segs s;
+    HQ_REQUIRE(make_segs(layout, s), "index layout not supported by the tensor-core filter");
+    HQ_REQUIRE(N >= 0, "negative N");
+    if (N == 0) return HQ_OK;
+    HQ_REQUIRE(idx && packed && (is_query || rnorm), "null pointer");
+    PackParams p{};
+    p.idx = idx; p.rnorm = rnorm; p.N = N; p.lay = *layout; p.is_query = is_query ? 1 : 0; p.out = packed;
+    for (int l = 0; l < 3; ++l) { p.seg_off[l] = s.off[l]; p.kp[l] = s.kp[l]; }
+    int64_t blocks = (N * KS + 255) / 256;
+    const int64_t cap = (int64_t)hq_cached_sm_count() * 32;
+    if (blocks > cap) blocks = cap;
+    k_pack_rows<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    HQ_LAUNCH_OK("k_pack_rows");
+    return HQ_OK;
+}
+
+extern "C" int hq_filter_tc_valid(const float* rnorm, int64_t N, const hq_index_layout* layout, uint32_t* valid, int64_t valid_pitch,
+                                  void* stream) {
+    HQ_REQUIRE(layout && layout->L >= 1 && layout->L <= 3, "bad index layout");
+    HQ_REQUIRE(N >= 0 && valid_pitch >= hq_filter_tc_valid_pitch(N), "valid pitch too small");
+    if (N == 0) return HQ_OK;
+    HQ_REQUIRE(rnorm && valid, "null pointer");
+    int64_t blocks = (valid_pitch * 32 * layout->L + 255) / 256;
+    const int64_t cap = (int64_t)hq_cached_sm_count() * 32;
+    if (blocks > cap) blocks = cap;
+    k_valid_bits<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rnorm, N, layout->L, valid, valid_pitch);
+    HQ_LAUNCH_OK("k_valid_bits");
+    return HQ_OK;
+}
+
+// Bit planes for a query batch.  q_packed [Q, 128] and tq [3, Q] are caller-provided scratch.
+int hq_filter_bits_tc_launch(const float* db_packed, const uint32_t* valid, int64_t valid_pitch, int64_t N,
+                             const hq_index_layout* layout, const float* q_idx, int Q, const float* xstar, float* q_packed,
+                             float* tq, uint32_t* bits, int64_t bits_pitch, cudaStream_t st) {
+    Segs s;
+    HQ_REQUIRE(make_segs(layout, s), "index layout not supported by the tensor-core filter");
+    HQ_REQUIRE(db_packed && valid && q_idx && q_packed && tq && bits, "null pointer");
+    HQ_REQUIRE((reinterpret_cast<uintptr_t>(db_packed) & 15) == 0 && (reinterpret_cast<uintptr_t>(q_packed) & 15) == 0,
+               "packed operands must be 16-byte aligned");
+    HQ_REQUIRE(valid_pitch >= hq_filter_tc_valid_pitch(N), "valid pitch too small");
+    const int64_t words = (N + 31) / 32;
+    HQ_REQUIRE(bits_pitch >= words, "bit plane pitch too small");
+    int rc = hq_filter_tc_pack(q_idx, nullptr, Q, layout, 1, q_packed, st);
+    if (rc != HQ_OK) return rc;
+    k_query_tq<<<(Q * layout->L + 255) / 256, 256, 0, st>>>(q_idx, Q, *layout, xstar[0], layout->L > 1 ? xstar[1] : 0.f,
+                                                            layout->L > 2 ? xstar[2] : 0.f, tq);
+    HQ_LAUNCH_OK("k_query_tq");
+
+    FtcParams p{};
+    p.N = N; p.Q = Q; p.L = s.L; p.n_slabs = s.n_slabs;
+    for (int l = 0; l < 3; ++l) { p.seg_off[l] = s.off[l]; p.ksteps[l] = 3 * s.kp[l] / 8; }
+    p.tq = tq; p.valid = valid; p.valid_pitch = valid_pitch; p.bits = bits; p.words = words; p.bits_pitch = bits_pitch;
+    plan_units(N, Q, hq_cached_sm_count(), p);
+    CUtensorMap mq, mdb;
+    rc = make_map_2d(&mq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, q_packed, Q, KS, KS, 32, FM);
+    if (rc != HQ_OK) return rc;
+    rc = make_map_2d(&mdb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, db_packed, N, KS, KS, 32, FR);
+    if (rc != HQ_OK) return rc;
+    const size_t smem = 1024 + A_BYTES + F_STAGES * B_STAGE_BYTES + (3 * FM * STAGE_PITCH + 2) * sizeof(uint32_t) +
+                        (2 * F_STAGES + 6) * sizeof(uint64_t) + 16;
+    static bool attr = false;
+    if (!attr) {
+        HQ_CUDA_OK(cudaFuncSetAttribute(k_filter_bits_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    int grid = hq_cached_sm_count();
+    if (grid > p.num_units) grid = p.num_units;
+    k_filter_bits_tc<<<grid, F_THREADS, smem, st>>>(mq, mdb, p);
+    HQ_LAUNCH_OK("k_filter_bits_tc");
+    return HQ_OK;
+}

@@ -240,6 +240,241 @@ __global__ void __launch_bounds__(kBlock, 3) k_item_pass(const TileParams p) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// v5 (map direction, dense grid output): the 2-D side leaves the SM as ONE 16 KB bulk copy
+// per chunk (cp.async.bulk shared -> global).  A microbenchmark with this kernel's traffic
+// shape (tools/microbench/hbm_mix.cu: 6144 B in, 16720 B out per item) reaches 5.8-6.0 TB/s
+// with LSU stores and 6.25 TB/s with bulk stores out of shared memory: the 4 LDS.128 +
+// 4 STG.128 per thread and chunk of v3 were what kept it at 5.4 TB/s.  The tile image is
+// therefore kept in plain global order (row pitch T, no padding): the scatter pays 4-5-way
+// bank conflicts, which at ~0.2 shared-memory wavefronts per clock is irrelevant.  (A first
+// attempt with 128B-swizzled tensor stores, 2 boxes of 32 x 64 floats, was slower than v3:
+// 4.6 TB/s -- 128-byte inner extents are a poor shape for the TMA store path.)
+// RING images: the bulk store of chunk i must have finished reading its image before chunk
+// i + RING scatters into it; with RING = 3 that knowledge rides on the existing barrier.
+// ---------------------------------------------------------------------------------------
+template <int MODE, int LOG2T, int RING>
+__global__ void __launch_bounds__(kBlock, RING == 2 ? 4 : 3) k_item_pass_bulk(const TileParams p) {
+    using P = typename PT<MODE>::type;
+    using G = Geo<LOG2T>;
+    constexpr uint32_t kImg = 4096;                                 // floats per chunk image (ipc items of T x T)
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* const s_img0 = reinterpret_cast<float*>(smem_raw);                                    // RING dense tile images
+    P* const s_pyr0 = reinterpret_cast<P*>(s_img0 + RING * kImg);                                // two pyramids
+    int32_t* const s_plan = reinterpret_cast<int32_t*>(s_pyr0 + 2 * G::pyr_vals);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool idx_warp = warp == kThreads / 32;
+    const bool want_pyr = p.plan_len > 0 && p.min_level <= 32;
+
+    uint32_t slot01[kQPT], slot23[kQPT];
+    int32_t cur_off[kQPT];
+    uint32_t live_bits = 0;
+#pragma unroll
+    for (int r = 0; r < kQPT; ++r) {
+        const uint32_t qi = tid + r * kThreads;
+        const uint32_t il = qi >> G::log2qpi, q = qi & (G::qpi - 1);
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint32_t x, y;
+            hq_d2xy(LOG2T, 4ull * q + i, x, y);
+            o[i] = il * G::cells + y * G::T + x;
+        }
+        slot01[r] = o[0] | (o[1] << 16);
+        slot23[r] = o[2] | (o[3] << 16);
+        cur_off[r] = (int32_t)(il * p.src_stride + 4 * q);
+        if (!idx_warp && (int64_t)4 * q < p.D) live_bits |= 1u << r;
+    }
+
+    const bool plan_in_smem = p.plan_len <= kPlanCap;
+    if (plan_in_smem)
+        for (int i = tid; i < p.plan_len; i += kBlock) s_plan[i] = __ldg(p.plan + i);
+    for (uint32_t i = tid; i < RING * kImg; i += kBlock) s_img0[i] = 0.f;
+    for (uint32_t i = tid; i < 2 * G::pyr_vals; i += kBlock) s_pyr0[i] = (P)0;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the zero fill is read by the bulk stores too
+
+    auto load_chunk = [&](int64_t chunk, float4 (&v)[kQPT]) {
+        const int64_t item0 = chunk * G::ipc;
+        const int64_t left = p.N - item0;
+        const float* base = p.src + item0 * p.src_stride;
+        const bool full = left >= (int64_t)G::ipc;
+#pragma unroll
+        for (int r = 0; r < kQPT; ++r) {
+            float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+            const uint32_t il = (tid + r * kThreads) >> G::log2qpi;
+            if (((live_bits >> r) & 1u) && (full || (int64_t)il < left))
+                val = __ldcs(reinterpret_cast<const float4*>(base + cur_off[r]));
+            v[r] = val;
+        }
+    };
+
+    __shared__ volatile uint32_t s_done;
+    if (tid == 0) s_done = 0;
+    __syncthreads();
+
+    float4 v[kQPT];
+    int64_t chunk = blockIdx.x;
+    if (chunk < p.num_chunks) load_chunk(chunk, v);
+    uint32_t ring = 0, iter = 0;
+    for (; chunk < p.num_chunks; chunk += gridDim.x, ring = (ring + 1 == RING ? 0 : ring + 1), ++iter) {
+        const int64_t item0 = chunk * G::ipc;
+        const int64_t left = p.N - item0;
+        const bool full = left >= (int64_t)G::ipc;
+        float* img = s_img0 + ring * kImg;
+        P* pyrb = s_pyr0 + (iter & 1u) * G::pyr_vals;
+
+        // the index warp reads pyramid (iter & 1) and image ring: it must be done with chunk iter-2
+        // (pyramid) and, for RING == 2, that is also the image; for RING == 3 the image of chunk
+        // iter-3 was released even earlier
+        if (!idx_warp && p.plan_len > 0 && iter >= 2) {
+            while (s_done + 1 < iter) __nanosleep(64);
+        }
+        if (!idx_warp) {
+            if (RING == 2) {
+                // store(iter-2) has finished reading this image
+                if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                asm volatile("bar.sync 2, %0;" ::"n"(kThreads) : "memory");
+            }
+#pragma unroll
+            for (int r = 0; r < kQPT; ++r) {
+                if ((live_bits >> r) & 1u) {
+                    img[slot01[r] & 0xffffu] = v[r].x;
+                    img[slot01[r] >> 16] = v[r].y;
+                    img[slot23[r] & 0xffffu] = v[r].z;
+                    img[slot23[r] >> 16] = v[r].w;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            // RING == 3: store(iter-2) has finished reading its image before anybody passes this
+            // barrier, so chunk iter+1 may scatter into it
+            if (RING == 3 && tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            asm volatile("bar.sync 2, %0;" ::"n"(kThreads) : "memory");
+            if (tid == 0) {
+                const uint32_t bytes = full ? kImg * 4u : (uint32_t)left * G::cells * 4u;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.grid_out + item0 * (int64_t)G::cells),
+                             "r"(hq_tc::smem_u32(img)), "r"(bytes)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+
+        float4 nv[kQPT];
+        const int64_t next = chunk + gridDim.x;
+        if (next < p.num_chunks && !idx_warp) load_chunk(next, nv);
+
+        if (!idx_warp) {
+            if (want_pyr) {
+#pragma unroll
+                for (int r = 0; r < kQPT; ++r) {
+                    if (!((live_bits >> r) & 1u)) continue;
+                    const uint32_t qi = tid + r * kThreads;
+                    const uint32_t il = qi >> G::log2qpi, q = qi & (G::qpi - 1);
+                    pyrb[il * G::pyr_items + q] = mean4<MODE>(v[r].x, v[r].y, v[r].z, v[r].w);
+                }
+            }
+            if (p.plan_len > 0) {
+                if (iter & 1u) asm volatile("bar.arrive 3, %0;" ::"n"(kBlock) : "memory");
+                else asm volatile("bar.arrive 1, %0;" ::"n"(kBlock) : "memory");
+            }
+        } else if (p.plan_len > 0) {
+            if (iter & 1u) asm volatile("bar.sync 3, %0;" ::"n"(kBlock) : "memory");
+            else asm volatile("bar.sync 1, %0;" ::"n"(kBlock) : "memory");
+            if (want_pyr) {
+                uint32_t base_prev = 0, cnt_prev = G::qpi;
+                uint32_t live_prev = (uint32_t)((p.D + 3) >> 2);
+#pragma unroll
+                for (int k = 2; k <= LOG2T; ++k) {
+                    const uint32_t cnt = cnt_prev >> 2, base = base_prev + cnt_prev;
+                    const uint32_t live = (live_prev + 3) >> 2;
+                    for (uint32_t il = 0; il < G::ipc; ++il) {
+                        P* pyr = pyrb + il * G::pyr_items;
+                        for (uint32_t j = lane; j < live; j += 32) {
+                            const P a = pyr[base_prev + 4 * j], b = pyr[base_prev + 4 * j + 1];
+                            const P c = pyr[base_prev + 4 * j + 2], d = pyr[base_prev + 4 * j + 3];
+                            pyr[base + j] = MODE == 0 ? (P)(((a + b) + (c + d)) * (P)0.25) : (P)((((a + b) + c) + d) * (P)0.25);
+                        }
+                    }
+                    __syncwarp();
+                    base_prev = base;
+                    cnt_prev = cnt;
+                    live_prev = live;
+                }
+            }
+            P* out = reinterpret_cast<P*>(p.idx_out) + item0 * p.idx_stride;
+            const uint32_t n_items = full ? G::ipc : (uint32_t)left;
+            for (uint32_t il = 0; il < n_items; ++il) {
+                const float* im = img + il * G::cells;
+                const P* pyr = pyrb + il * G::pyr_items;
+                for (int i = lane; i < p.plan_len; i += 32) {
+                    const int32_t off = plan_in_smem ? s_plan[i] : __ldg(p.plan + i);
+                    P val = (P)0;
+                    if (off >= 0) {
+                        if ((uint32_t)off < G::cells) val = (P)im[off];
+                        else val = pyr[(uint32_t)off - G::cells];
+                    }
+                    __stcs(out + il * p.idx_stride + i, val);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) s_done = iter + 1;
+        }
+#pragma unroll
+        for (int r = 0; r < kQPT; ++r) v[r] = nv[r];
+    }
+    // the images must outlive the stores that read them
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+template <int LOG2T>
+inline size_t smem_bytes_bulk(int mode, int ring) {
+    using G = Geo<LOG2T>;
+    return (size_t)ring * 4096 * 4 + (size_t)2 * G::pyr_vals * (mode ? 8 : 4) + (size_t)kPlanCap * 4 + 16;
+}
+
+// true when the bulk-store variant can take this call (dense, 16-byte aligned grid output)
+inline bool bulk_eligible(const TileParams& p) {
+    return p.direction == 0 && p.grid_out && p.vec_grid && p.grid_stride == ((int64_t)1 << (2 * p.log2t));
+}
+
+template <int MODE, int LOG2T, int RING>
+int launch_bulk_t(const TileParams& p, cudaStream_t st) {
+    const size_t smem = smem_bytes_bulk<LOG2T>(MODE, RING);
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        HQ_CUDA_OK(cudaFuncSetAttribute(k_item_pass_bulk<MODE, LOG2T, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HQ_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_item_pass_bulk<MODE, LOG2T, RING>, kBlock, smem));
+        if (per_sm < 1) per_sm = 1;
+    }
+    int64_t blocks = (int64_t)hq_cached_sm_count() * per_sm;
+    if (blocks > p.num_chunks) blocks = p.num_chunks;
+    k_item_pass_bulk<MODE, LOG2T, RING><<<(unsigned)blocks, kBlock, smem, st>>>(p);
+    HQ_LAUNCH_OK("k_item_pass_bulk");
+    return HQ_OK;
+}
+
+template <int MODE, int RING>
+int launch_bulk_r(const TileParams& p, cudaStream_t st) {
+    switch (p.log2t) {
+        case 2: return launch_bulk_t<MODE, 2, RING>(p, st);
+        case 3: return launch_bulk_t<MODE, 3, RING>(p, st);
+        case 4: return launch_bulk_t<MODE, 4, RING>(p, st);
+        case 5: return launch_bulk_t<MODE, 5, RING>(p, st);
+        default: return launch_bulk_t<MODE, 6, RING>(p, st);
+    }
+}
+
+template <int MODE>
+int launch_bulk(const TileParams& p, cudaStream_t st) {
+    static int ring = 0;
+    if (ring == 0) {
+        const char* e = getenv("HQ_ITEM_RING");
+        ring = (e && e[0] == '2') ? 2 : 3;
+    }
+    return ring == 2 ? launch_bulk_r<MODE, 2>(p, st) : launch_bulk_r<MODE, 3>(p, st);
+}
+
 template <int LOG2T>
 inline size_t smem_bytes(int mode) {
     using G = Geo<LOG2T>;

@@ -10,8 +10,7 @@
 // that neighbouring CTAs stream the same database rows at the same time (L2 reuse), the
 // query tile comes from L2.  Two TMEM accumulators (2 x 256 columns) overlap the epilogue of
 // tile i with the MMAs of tile i+1.
-#include "hq_common.cuh"
-#include <cuda.h>
+#include "hq_tc.cuh"
 #include <cuda_bf16.h>
 #include <float.h>
 
@@ -25,76 +24,9 @@ constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int TC_THREADS = 192;
 constexpr uint32_t TMEM_COLS = 512;
 
-// ---- raw PTX wrappers ---------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+using namespace hq_tc;
 
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred = 0;
-    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred P;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1;\n\t"
-        "@P bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate));
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, 128B-swizzled operand tile: 8-row atoms of 1024 B, SBO = 1024, version 1 (sm_100)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);           // start address
-    d |= (uint64_t)0 << 16;                             // leading byte offset (unused: one atom along K)
-    d |= (uint64_t)(1024u >> 4) << 32;                  // stride byte offset between 8-row atoms
-    d |= (uint64_t)1 << 46;                             // descriptor version
-    d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
-    return d;
-}
-constexpr uint32_t kIdesc = (1u << 4) /*D=f32*/ | (1u << 7) /*A=bf16*/ | (1u << 10) /*B=bf16*/ | ((uint32_t)(BN >> 3) << 17) |
-                            ((uint32_t)(BM >> 4) << 24);
+constexpr uint32_t kIdesc = make_idesc(1 /*bf16*/, BM, BN);
 
 struct TcParams {
     int64_t N;
@@ -183,7 +115,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rerank_tc(const __grid_consta
                         const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * B_STAGE_BYTES));
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k)
-                            umma_bf16(tmem_base + acc * BN, da + (uint64_t)(k * UMMA_K * 2 >> 4), db + (uint64_t)(k * UMMA_K * 2 >> 4),
+                            umma_f16(tmem_base + acc * BN, da + (uint64_t)(k * UMMA_K * 2 >> 4), db + (uint64_t)(k * UMMA_K * 2 >> 4),
                                       kIdesc, (kb > 0 || k > 0) ? 1u : 0u);
                         umma_commit(&empty_bar[stage]);                       // frees the smem slot when the MMAs retire
                         if (kb == k_blocks - 1) umma_commit(&tfull_bar[acc]); // accumulator complete
@@ -392,42 +324,8 @@ __global__ void __launch_bounds__(256) k_to_bf16(const float* __restrict__ src, 
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-// The driver entry point is resolved through the runtime so that the library has no link-time
-// dependency on libcuda.so (it must load on machines without a driver, e.g. for build checks).
-EncodeTiledFn encode_tiled_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
 int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t pitch_elems, int box_rows) {
-    EncodeTiledFn enc = encode_tiled_fn();
-    if (!enc) {
-        hq_set_error("cuTensorMapEncodeTiled is not available from this driver");
-        return HQ_ECUDA;
-    }
-    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        hq_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-        return HQ_ECUDA;
-    }
-    return HQ_OK;
+    return make_map_2d(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, cols, pitch_elems, BK, box_rows);
 }
 
 void plan_units(int64_t N, int Q, int sms, TcParams& p) {

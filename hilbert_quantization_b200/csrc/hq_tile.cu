@@ -11,7 +11,8 @@
 // memory image of the tile (row pitch n+4 floats) and is written / read as 128-bit row
 // segments.  The run-mean pyramid (levels 1..3) is reduced in registers with warp
 // shuffles straight from the loaded quads; levels >= 4 are finished from shared memory.
-#include "hq_common.cuh"
+#include "hq_tc.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -519,7 +520,8 @@ static int fused_impl(const float* src, int direction, int64_t N, int64_t D, int
                       (int64_t)256 * (src_stride > grid_stride ? src_stride : grid_stride) < ((int64_t)1 << 31) &&
                       (int64_t)256 * stream_stride < ((int64_t)1 << 31);
     if (fast) {
-        if (direction == 0) rc = pyr_mode ? item_pass::launch<0, 1>(p, st) : item_pass::launch<0, 0>(p, st);
+        if (direction == 0 && item_pass::bulk_eligible(p)) rc = pyr_mode ? item_pass::launch_bulk<1>(p, st) : item_pass::launch_bulk<0>(p, st);
+        else if (direction == 0) rc = pyr_mode ? item_pass::launch<0, 1>(p, st) : item_pass::launch<0, 0>(p, st);
         else rc = pyr_mode ? item_pass::launch<1, 1>(p, st) : item_pass::launch<1, 0>(p, st);
     } else if (direction == 0) rc = pyr_mode ? launch_tile<0, 1>(p, st) : launch_tile<0, 0>(p, st);
     else rc = pyr_mode ? launch_tile<1, 1>(p, st) : launch_tile<1, 0>(p, st);

@@ -123,7 +123,7 @@ class EmbeddingDatabase:
     (the 2-D grids are produced only if `keep_grids`)."""
 
     def __init__(self, embeddings, n: Optional[int] = None, device=None, keep_grids: bool = False, id_base: int = 0,
-                 bf16: bool = True):
+                 bf16: bool = True, tc_filter: bool = True):
         d = dev.require_cuda(device if device is not None else (embeddings.device if isinstance(embeddings, torch.Tensor)
                                                                  and embeddings.is_cuda else None))
         self.device = d
@@ -161,6 +161,18 @@ class EmbeddingDatabase:
             pitches.append(pitch)
         self._lvl_ptrs = (C.c_void_p * 3)(*([t.data_ptr() for t in self._lvl_rows[:3]] + [None] * (3 - min(3, len(self._lvl_rows)))))
         self._lvl_pitch = (C.c_int32 * 3)(*(pitches[:3] + [0] * (3 - min(3, len(pitches)))))
+        # tensor-core threshold pass: tf32 hi/lo-split, norm-scaled copy of the index rows [N, 128] + validity words
+        self.tc_packed = self.tc_valid = None
+        self.tc_valid_pitch = 0
+        if tc_filter and self.fast_filter_ok and self.N > 0 and bool(lib.hq_filter_tc_supported(C.byref(self.layout))):
+            self.tc_valid_pitch = int(lib.hq_filter_tc_valid_pitch(self.N))
+            self.tc_packed = torch.empty((self.N, 128), dtype=torch.float32, device=d)
+            self.tc_valid = torch.empty((int(self.layout.L), self.tc_valid_pitch), dtype=torch.int32, device=d)
+            with torch.cuda.device(d):
+                check(lib.hq_filter_tc_pack(dev.ptr(self.idx), dev.ptr(self.level_norms), self.N, C.byref(self.layout), 0,
+                                            dev.ptr(self.tc_packed), dev.stream_ptr()))
+                check(lib.hq_filter_tc_valid(dev.ptr(self.level_norms), self.N, C.byref(self.layout), dev.ptr(self.tc_valid),
+                                             self.tc_valid_pitch, dev.stream_ptr()))
 
     @property
     def num_levels(self) -> int:
@@ -236,8 +248,10 @@ def progressive_filter(db: EmbeddingDatabase, q_idx: torch.Tensor, q_lens: torch
 
 
 def progressive_filter_fast(db: EmbeddingDatabase, q_idx: torch.Tensor, mask: torch.Tensor,
-                            trace: Optional[FilterTrace] = None):
-    """All filter levels for a query batch through hq_filter_fast (no score matrix)."""
+                            trace: Optional[FilterTrace] = None, tensor_cores: bool = True):
+    """All filter levels for a query batch through hq_filter_fast (no score matrix).  With
+    `tensor_cores` (and a packed operand on the shard) the threshold pass runs on tcgen05."""
+    use_tc = tensor_cores and db.tc_packed is not None
     Q, N, d = q_idx.shape[0], db.N, db.device
     L = db.num_levels
     need = int(lib.hq_filter_fast_scratch_bytes(N, Q, C.byref(db.layout)))
@@ -249,6 +263,8 @@ def progressive_filter_fast(db: EmbeddingDatabase, q_idx: torch.Tensor, mask: to
         check(lib.hq_filter_fast(dev.ptr(db.idx), dev.ptr(db.level_norms), N, C.byref(db.layout), dev.ptr(q_idx), Q,
                                  C.cast(db._xstar_host, C.c_void_p), C.cast(db._ratio_host, C.c_void_p),
                                  C.cast(db._lvl_ptrs, C.c_void_p), C.cast(db._lvl_pitch, C.c_void_p),
+                                 dev.ptr(db.tc_packed) if use_tc else None, dev.ptr(db.tc_valid) if use_tc else None,
+                                 db.tc_valid_pitch if use_tc else 0,
                                  dev.ptr(mask), mask.stride(0), dev.ptr(n_out), dev.ptr(counts),
                                  dev.ptr(db._filter_scratch), db._filter_scratch.numel(), dev.stream_ptr()))
     if trace is not None:
@@ -299,12 +315,12 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
         q_bf16 = to_bf16(q)
         _end(tok)
     words = _mask_words(N)
-    if filter_impl not in ("auto", "fast", "exact"):
-        raise ValueError("filter_impl must be 'auto', 'fast' or 'exact'")
+    if filter_impl not in ("auto", "fast", "fast_fp32", "exact"):
+        raise ValueError("filter_impl must be 'auto', 'fast', 'fast_fp32' or 'exact'")
     fast = False
     if use_filter and filter_impl != "exact":
         fast = db.fast_filter_ok and bool((q_lens == db._keff).all().item())
-        if filter_impl == "fast" and not fast:
+        if filter_impl in ("fast", "fast_fp32") and not fast:
             raise ValueError("the fast filter needs dense index rows (all stored lengths structural) and L <= 3")
     if fast or not use_filter:
         work_bytes = max(work_bytes, 4 * N * Q) if rerank == "bf16" else work_bytes
@@ -321,7 +337,7 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
             if use_filter:
                 tok = _phase("filter")
                 if fast:
-                    m = progressive_filter_fast(db, q_idx[s:e], mask[:nq], trace)
+                    m = progressive_filter_fast(db, q_idx[s:e], mask[:nq], trace, tensor_cores=filter_impl != "fast_fp32")
                 else:
                     m = progressive_filter(db, q_idx[s:e], q_lens[s:e], scores[:nq], mask[:nq], trace)
                 _end(tok)

@@ -167,8 +167,25 @@ int64_t hq_filter_fast_scratch_bytes(int64_t N, int Q, const hq_index_layout* la
 int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, const hq_index_layout* layout,
                    const float* q_idx, int Q, const float* xstar, const double* ratio,
                    const float* const* lvl_rows, const int32_t* lvl_pitch,
+                   const float* db_packed, const uint32_t* valid, int64_t valid_pitch,
                    uint32_t* mask, int64_t mask_stride, int32_t* n_out, int32_t* counts,
                    void* scratch, int64_t scratch_bytes, void* stream);
+
+/* Tensor-core form of the threshold pass of hq_filter_fast (db_packed != NULL): the per-level
+ * dot products run as ONE tcgen05 tf32 contraction per 128-query x 64-row tile with every
+ * value split exactly into tf32 hi + lo parts (three products per term, score error < 3e-7),
+ * rows pre-scaled by 1 / |c_l|, and the comparison + bit packing done in the TMEM epilogue.
+ * Supported when 3 * sum_l pad8(lvl_keff[l]) <= 128 and L <= 3.
+ *   hq_filter_tc_pack  : idx [N, Lsum] (+ rnorm) -> packed [N, 128] float32 operand rows
+ *                        (is_query = 1: unscaled, [hi | hi | lo]; 0: scaled, [hi | lo | hi])
+ *   hq_filter_tc_valid : valid [L][valid_pitch] bit r = row r has a non-zero level norm;
+ *                        valid_pitch >= hq_filter_tc_valid_pitch(N) (whole 64-row tiles) */
+int hq_filter_tc_supported(const hq_index_layout* layout);
+int64_t hq_filter_tc_valid_pitch(int64_t N);
+int hq_filter_tc_pack(const float* idx, const float* rnorm, int64_t N, const hq_index_layout* layout, int is_query,
+                      float* packed, void* stream);
+int hq_filter_tc_valid(const float* rnorm, int64_t N, const hq_index_layout* layout, uint32_t* valid,
+                       int64_t valid_pitch, void* stream);
 
 /* ---- a13/a15: cosine rerank + top-k --------------------------------------
  * rag/search/engine.py:622-660 (_calculate_embedding_cosine_similarity),

@@ -28,14 +28,17 @@ def _data(rng, N, D, Q, positive):
 @pytest.mark.parametrize("N,D,Q,positive", [(3000, 1536, 20, False), (3000, 1536, 20, True), (5000, 768, 33, False),
                                             (5000, 768, 33, True), (4097, 1024, 9, True), (2000, 256, 130, False),
                                             (70000, 1536, 6, False), (70000, 768, 6, True), (1500, 4096, 7, True)])
-def test_fast_filter_equals_exact_filter(hq, N, D, Q, positive):
+@pytest.mark.parametrize("impl", ["fast", "fast_fp32"])        # tensor-core (tf32 hi/lo split) and CUDA-core threshold pass
+def test_fast_filter_equals_exact_filter(hq, N, D, Q, positive, impl):
     from hilbert_quantization_b200.search import FilterTrace, unpack_mask
     rng = np.random.default_rng(N + D + Q)
     db, qs = _data(rng, N, D, Q, positive)
     d = hq.EmbeddingDatabase(db)
     assert d.fast_filter_ok
     tf, te = FilterTrace([], [], []), FilterTrace([], [], [])
-    i_f, s_f, m_f = hq.search_batch(d, qs, 10, return_mask=True, filter_impl="fast", trace=tf)
+    if impl == "fast" and D <= 1536:
+        assert d.tc_packed is not None           # these layouts fit the 128-float packed operand
+    i_f, s_f, m_f = hq.search_batch(d, qs, 10, return_mask=True, filter_impl=impl, trace=tf)
     i_e, s_e, m_e = hq.search_batch(d, qs, 10, return_mask=True, filter_impl="exact", trace=te)
     a_f, a_e = unpack_mask(m_f, N), unpack_mask(m_e, N)
     same = (a_f == a_e).all(axis=1)
