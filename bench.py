@@ -380,7 +380,7 @@ def main():
                          "peak_source": pk["source"] + " (sustained bf16)"},
             "map_index": {"value": map_index_gbs, "unit": "GB/s", "bytes_per_embedding": bytes_per_row,
                           "ms_per_pass": mi_t.item(), "launches_per_pass": launches_per_pass,
-                          "roofline": {"kernel": "k_item_pass<0,0,6> (fused map_to_2d + index pyramid)", "bound": "hbm",
+                          "roofline": {"kernel": "k_item_pass_bulk<0,6> (fused map_to_2d + index pyramid, bulk-copy loads and stores)", "bound": "hbm",
                                        "achieved": mi_kernel_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                        "frac": mi_kernel_gbs / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"]}},
             "clocks": clocks.summary(),

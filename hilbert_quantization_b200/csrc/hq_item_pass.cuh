@@ -34,6 +34,61 @@ struct Geo {
     static constexpr uint32_t base2 = qpi, base3 = qpi + qpi / 4;
 };
 
+
+// Levels 1..3 of the run-mean pyramid straight from the quads a warp holds in registers: a
+// thread's quad is level 1, 4 / 16 consecutive lanes are levels 2 / 3 (two shuffle steps each,
+// same association as the shared-memory tree: ((a+b)+(c+d)) fp32, (((a+b)+c)+d) fp64).  Dead
+// quads (d >= D) hold zeros, exactly what the zero padding contributes.  `warp_live` bit r is
+// set when any lane of the warp holds data for quad slot r (warp-uniform skip).
+template <int MODE, int LOG2T>
+__device__ __forceinline__ void pyramid_levels_123(const float4 (&v)[kQPT], uint32_t live_bits, uint32_t warp_live,
+                                                   typename PT<MODE>::type* pyrb, int tid, int lane) {
+    using P = typename PT<MODE>::type;
+    using G = Geo<LOG2T>;
+#pragma unroll
+    for (int r = 0; r < kQPT; ++r) {
+        if (!((warp_live >> r) & 1u)) continue;
+        const uint32_t qi = tid + r * kThreads;
+        const uint32_t il = qi >> G::log2qpi, q = qi & (G::qpi - 1);
+        const bool live = (live_bits >> r) & 1u;
+        P* pyr = pyrb + il * G::pyr_items;
+        const P m1 = mean4<MODE>(v[r].x, v[r].y, v[r].z, v[r].w);
+        if (live) pyr[q] = m1;
+        const P m2 = group_mean<MODE>(m1, 1);
+        if (live && (lane & 3) == 0) pyr[G::base2 + (q >> 2)] = m2;
+        if (LOG2T >= 3) {
+            const P m3 = group_mean<MODE>(m2, 4);
+            if (live && (lane & 15) == 0) pyr[G::base3 + (q >> 4)] = m3;
+        }
+    }
+}
+
+// Levels >= 4 (from level 3 in shared memory) by one warp, all items of the chunk in one flat loop.
+template <int MODE, int LOG2T>
+__device__ __forceinline__ void pyramid_levels_top(typename PT<MODE>::type* pyrb, uint32_t live1, int lane) {
+    using P = typename PT<MODE>::type;
+    using G = Geo<LOG2T>;
+    if (LOG2T < 4) return;
+    uint32_t base_prev = G::base3, cnt_prev = G::qpi >> 4;
+    uint32_t live_prev = (((live1 + 3) >> 2) + 3) >> 2;          // live runs of level 3
+#pragma unroll
+    for (int k = 4; k <= LOG2T; ++k) {
+        const uint32_t cnt = cnt_prev >> 2, base = base_prev + cnt_prev;
+        const uint32_t live = (live_prev + 3) >> 2;
+        for (uint32_t e = lane; e < G::ipc * live; e += 32) {
+            const uint32_t il = e / live, j = e - il * live;
+            P* pyr = pyrb + il * G::pyr_items;
+            const P a = pyr[base_prev + 4 * j], b = pyr[base_prev + 4 * j + 1];
+            const P c = pyr[base_prev + 4 * j + 2], d = pyr[base_prev + 4 * j + 3];
+            pyr[base + j] = MODE == 0 ? (P)(((a + b) + (c + d)) * (P)0.25) : (P)((((a + b) + c) + d) * (P)0.25);
+        }
+        __syncwarp();
+        base_prev = base;
+        cnt_prev = cnt;
+        live_prev = live;
+    }
+}
+
 template <int DIR, int MODE, int LOG2T>
 __global__ void __launch_bounds__(kBlock, 3) k_item_pass(const TileParams p) {
     using P = typename PT<MODE>::type;
@@ -78,6 +133,11 @@ __global__ void __launch_bounds__(kBlock, 3) k_item_pass(const TileParams p) {
         if (!idx_warp && (DIR == 1 || (int64_t)4 * q < p.D)) live_bits |= 1u << r;
     }
 
+    uint32_t warp_live = 0;
+#pragma unroll
+    for (int r = 0; r < kQPT; ++r)
+        if (__any_sync(0xffffffffu, (live_bits >> r) & 1u)) warp_live |= 1u << r;
+
     const bool plan_in_smem = p.plan_len <= kPlanCap;
     if (plan_in_smem)
         for (int i = tid; i < p.plan_len; i += kBlock) s_plan[i] = __ldg(p.plan + i);
@@ -103,8 +163,15 @@ __global__ void __launch_bounds__(kBlock, 3) k_item_pass(const TileParams p) {
 
     // hand-off counters between the data warps and the index warp (monotonic, per CTA):
     //   s_done  = number of chunks whose index entries the index warp has finished
-    __shared__ volatile uint32_t s_done;
-    if (tid == 0) s_done = 0;
+    // s_free[b]: the index warp has finished the chunk that used pyramid / image buffer b (one phase per
+    // use).  An mbarrier, not a polled flag: __nanosleep granularity (~1 us) used to set the CTA's
+    // iteration time whenever the data warps arrived a little early.
+    __shared__ __align__(8) uint64_t s_free[2];
+    if (tid == 0) {
+        hq_tc::mbar_init(&s_free[0], 1);
+        hq_tc::mbar_init(&s_free[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
 
     float4 v[kQPT];
@@ -119,9 +186,7 @@ __global__ void __launch_bounds__(kBlock, 3) k_item_pass(const TileParams p) {
         P* pyrb = s_pyr0 + buf * G::pyr_vals;
 
         // the buffers of this chunk were last used by chunk iter-2: its index entries must be out
-        if (!idx_warp && p.plan_len > 0 && iter >= 2) {
-            while (s_done + 1 < iter) __nanosleep(64);
-        }
+        if (!idx_warp && p.plan_len > 0 && iter >= 2) hq_tc::mbar_wait(&s_free[iter & 1u], ((iter >> 1) - 1u) & 1u);
         // ---- data warps: curve-side quads -> tile image (or tile image -> quads for DIR 1) ----
         if (DIR == 0) {
 #pragma unroll
@@ -170,17 +235,9 @@ __global__ void __launch_bounds__(kBlock, 3) k_item_pass(const TileParams p) {
                         __stcs(reinterpret_cast<float4*>(sbase + cur_off[r]), v[r]);
                 }
             }
-            if (want_pyr) {
-                // level 1 only (four adds, no shuffle chain on the data warps); the index warp builds
-                // every higher level from shared memory, off the critical path
-#pragma unroll
-                for (int r = 0; r < kQPT; ++r) {
-                    if (!((live_bits >> r) & 1u)) continue;
-                    const uint32_t qi = tid + r * kThreads;
-                    const uint32_t il = qi >> G::log2qpi, q = qi & (G::qpi - 1);
-                    pyrb[il * G::pyr_items + q] = mean4<MODE>(v[r].x, v[r].y, v[r].z, v[r].w);
-                }
-            }
+            // levels 1..3 in registers / shuffles on the data warps (they have slack: the kernel is bound by
+            // the serial tail of the index warp otherwise -- "index only" used to take as long as "map only")
+            if (want_pyr) pyramid_levels_123<MODE, LOG2T>(v, live_bits, warp_live, pyrb, tid, lane);
             // levels 1..3 (and the tile image) of this chunk are in shared memory: hand them to the index
             // warp without waiting for it
             // Hand-off = named barrier, alternating ids 1 / 3 per chunk: the data warps arrive without
@@ -195,45 +252,24 @@ __global__ void __launch_bounds__(kBlock, 3) k_item_pass(const TileParams p) {
             // ---- index warp: wait for the 8 data warps of this chunk, finish the pyramid, write the entries ----
             if (iter & 1u) asm volatile("bar.sync 3, %0;" ::"n"(kBlock) : "memory");
             else asm volatile("bar.sync 1, %0;" ::"n"(kBlock) : "memory");
-            if (want_pyr) {
-                // runs at d >= D are never touched: they stay zero from the one-time clear
-                uint32_t base_prev = 0, cnt_prev = G::qpi;
-                uint32_t live_prev = DIR == 1 ? G::qpi : (uint32_t)((p.D + 3) >> 2);
-#pragma unroll
-                for (int k = 2; k <= LOG2T; ++k) {
-                    const uint32_t cnt = cnt_prev >> 2, base = base_prev + cnt_prev;
-                    const uint32_t live = (live_prev + 3) >> 2;
-                    for (uint32_t il = 0; il < G::ipc; ++il) {
-                        P* pyr = pyrb + il * G::pyr_items;
-                        for (uint32_t j = lane; j < live; j += 32) {
-                            const P a = pyr[base_prev + 4 * j], b = pyr[base_prev + 4 * j + 1];
-                            const P c = pyr[base_prev + 4 * j + 2], d = pyr[base_prev + 4 * j + 3];
-                            pyr[base + j] = MODE == 0 ? (P)(((a + b) + (c + d)) * (P)0.25) : (P)((((a + b) + c) + d) * (P)0.25);
-                        }
-                    }
-                    __syncwarp();
-                    base_prev = base;
-                    cnt_prev = cnt;
-                    live_prev = live;
-                }
-            }
+            // runs at d >= D are never touched: they stay zero from the one-time clear
+            if (want_pyr) pyramid_levels_top<MODE, LOG2T>(pyrb, DIR == 1 ? G::qpi : (uint32_t)((p.D + 3) >> 2), lane);
             P* out = reinterpret_cast<P*>(p.idx_out) + item0 * p.idx_stride;
             const uint32_t n_items = full ? G::ipc : (uint32_t)left;
-            for (uint32_t il = 0; il < n_items; ++il) {
+            for (uint32_t e = lane; e < n_items * (uint32_t)p.plan_len; e += 32) {
+                const uint32_t il = e / (uint32_t)p.plan_len, i = e - il * (uint32_t)p.plan_len;
                 const float* im = img + il * G::T * G::pitch;
                 const P* pyr = pyrb + il * G::pyr_items;
-                for (int i = lane; i < p.plan_len; i += 32) {
-                    const int32_t off = plan_in_smem ? s_plan[i] : __ldg(p.plan + i);
-                    P val = (P)0;
-                    if (off >= 0) {
-                        if ((uint32_t)off < G::cells) val = (P)im[((uint32_t)off >> LOG2T) * G::pitch + ((uint32_t)off & (G::T - 1))];
-                        else val = pyr[(uint32_t)off - G::cells];
-                    }
-                    __stcs(out + il * p.idx_stride + i, val);
+                const int32_t off = plan_in_smem ? s_plan[i] : __ldg(p.plan + i);
+                P val = (P)0;
+                if (off >= 0) {
+                    if ((uint32_t)off < G::cells) val = (P)im[((uint32_t)off >> LOG2T) * G::pitch + ((uint32_t)off & (G::T - 1))];
+                    else val = pyr[(uint32_t)off - G::cells];
                 }
+                __stcs(out + il * p.idx_stride + i, val);
             }
             __syncwarp();
-            if (lane == 0) s_done = iter + 1;
+            if (lane == 0) hq_tc::mbar_arrive(&s_free[iter & 1u]);
         }
 #pragma unroll
         for (int r = 0; r < kQPT; ++r) v[r] = nv[r];
@@ -242,34 +278,46 @@ __global__ void __launch_bounds__(kBlock, 3) k_item_pass(const TileParams p) {
 
 
 // ---------------------------------------------------------------------------------------
-// v5 (map direction, dense grid output): the 2-D side leaves the SM as ONE 16 KB bulk copy
-// per chunk (cp.async.bulk shared -> global).  A microbenchmark with this kernel's traffic
-// shape (tools/microbench/hbm_mix.cu: 6144 B in, 16720 B out per item) reaches 5.8-6.0 TB/s
-// with LSU stores and 6.25 TB/s with bulk stores out of shared memory: the 4 LDS.128 +
-// 4 STG.128 per thread and chunk of v3 were what kept it at 5.4 TB/s.  The tile image is
-// therefore kept in plain global order (row pitch T, no padding): the scatter pays 4-5-way
-// bank conflicts, which at ~0.2 shared-memory wavefronts per clock is irrelevant.  (A first
-// attempt with 128B-swizzled tensor stores, 2 boxes of 32 x 64 floats, was slower than v3:
-// 4.6 TB/s -- 128-byte inner extents are a poor shape for the TMA store path.)
-// RING images: the bulk store of chunk i must have finished reading its image before chunk
-// i + RING scatters into it; with RING = 3 that knowledge rides on the existing barrier.
+// v5/v6 (map direction, dense grid output): both global sides go through the bulk-copy engine.
+//
+// v5: the 2-D side leaves the SM as ONE 16 KB bulk copy per chunk (cp.async.bulk shared ->
+// global).  A microbenchmark with this kernel's traffic shape (tools/microbench/hbm_mix.cu:
+// 6144 B in, 16720 B out per item) reaches 5.8-6.0 TB/s with LSU stores and 6.25 TB/s with
+// bulk stores.  The tile image is kept in plain global order (row pitch T, no padding): the
+// scatter pays 4-5-way bank conflicts, which at ~0.2 shared-memory wavefronts per clock is
+// irrelevant.  (A first attempt with 128B-swizzled tensor stores, 2 boxes of 32 x 64 floats,
+// was slower than v3: 4.6 TB/s -- 128-byte inner extents are a poor shape for the TMA store
+// path.)  Three images: the store of chunk i has finished reading its image before chunk
+// i + 3 scatters into it, and that knowledge rides on the existing barrier.
+//
+// v6: v5 alone stayed at 5.4 TB/s -- with one chunk prefetched in registers per CTA there
+// are only ~3 source rows in flight per SM against ~1.5 us of loaded HBM latency.  The
+// source rows now arrive by bulk loads (global -> shared, mbarrier completion) through a
+// ring of `stages` staging buffers that one thread keeps full, so the loads in flight no
+// longer cost registers or depend on the CTA count.
 // ---------------------------------------------------------------------------------------
-template <int MODE, int LOG2T, int RING>
-__global__ void __launch_bounds__(kBlock, RING == 2 ? 4 : 3) k_item_pass_bulk(const TileParams p) {
+constexpr int kMaxStages = 8;
+
+template <int MODE, int LOG2T>
+__global__ void __launch_bounds__(kBlock, 3) k_item_pass_bulk(const TileParams p, const int kRing, const int stages, const uint32_t stage_floats,
+                                                              const int plan_cap) {
     using P = typename PT<MODE>::type;
     using G = Geo<LOG2T>;
     constexpr uint32_t kImg = 4096;                                 // floats per chunk image (ipc items of T x T)
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* const s_img0 = reinterpret_cast<float*>(smem_raw);                                    // RING dense tile images
-    P* const s_pyr0 = reinterpret_cast<P*>(s_img0 + RING * kImg);                                // two pyramids
+    float* const s_img0 = reinterpret_cast<float*>(smem_raw);                                    // kRing dense tile images
+    float* const s_stage0 = s_img0 + kRing * kImg;                                               // `stages` source staging buffers
+    P* const s_pyr0 = reinterpret_cast<P*>(s_stage0 + (size_t)stages * stage_floats);            // two pyramids
     int32_t* const s_plan = reinterpret_cast<int32_t*>(s_pyr0 + 2 * G::pyr_vals);
+    __shared__ __align__(8) uint64_t s_full[kMaxStages];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool idx_warp = warp == kThreads / 32;
     const bool want_pyr = p.plan_len > 0 && p.min_level <= 32;
+    const uint32_t row_bytes = (uint32_t)p.D * 4u;
 
     uint32_t slot01[kQPT], slot23[kQPT];
-    int32_t cur_off[kQPT];
+    uint32_t st_off[kQPT];                     // float offset of the quad inside a staging buffer
     uint32_t live_bits = 0;
 #pragma unroll
     for (int r = 0; r < kQPT; ++r) {
@@ -284,59 +332,80 @@ __global__ void __launch_bounds__(kBlock, RING == 2 ? 4 : 3) k_item_pass_bulk(co
         }
         slot01[r] = o[0] | (o[1] << 16);
         slot23[r] = o[2] | (o[3] << 16);
-        cur_off[r] = (int32_t)(il * p.src_stride + 4 * q);
+        st_off[r] = il * (uint32_t)p.D + 4 * q;
         if (!idx_warp && (int64_t)4 * q < p.D) live_bits |= 1u << r;
     }
 
-    const bool plan_in_smem = p.plan_len <= kPlanCap;
+    uint32_t warp_live = 0;
+#pragma unroll
+    for (int r = 0; r < kQPT; ++r)
+        if (__any_sync(0xffffffffu, (live_bits >> r) & 1u)) warp_live |= 1u << r;
+
+    const bool plan_in_smem = p.plan_len <= plan_cap;
     if (plan_in_smem)
         for (int i = tid; i < p.plan_len; i += kBlock) s_plan[i] = __ldg(p.plan + i);
-    for (uint32_t i = tid; i < RING * kImg; i += kBlock) s_img0[i] = 0.f;
+    for (uint32_t i = tid; i < (uint32_t)kRing * kImg; i += kBlock) s_img0[i] = 0.f;
     for (uint32_t i = tid; i < 2 * G::pyr_vals; i += kBlock) s_pyr0[i] = (P)0;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the zero fill is read by the bulk stores too
 
-    auto load_chunk = [&](int64_t chunk, float4 (&v)[kQPT]) {
+    // one thread keeps the staging ring full: source rows of chunk `chunk` -> stage buffer `st`
+    auto issue_loads = [&](int64_t chunk, int st) {
         const int64_t item0 = chunk * G::ipc;
         const int64_t left = p.N - item0;
-        const float* base = p.src + item0 * p.src_stride;
-        const bool full = left >= (int64_t)G::ipc;
-#pragma unroll
-        for (int r = 0; r < kQPT; ++r) {
-            float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-            const uint32_t il = (tid + r * kThreads) >> G::log2qpi;
-            if (((live_bits >> r) & 1u) && (full || (int64_t)il < left))
-                val = __ldcs(reinterpret_cast<const float4*>(base + cur_off[r]));
-            v[r] = val;
+        const uint32_t n_items = left >= (int64_t)G::ipc ? G::ipc : (uint32_t)left;
+        const uint32_t bar = hq_tc::smem_u32(&s_full[st]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n_items * row_bytes) : "memory");
+        float* dst = s_stage0 + (size_t)st * stage_floats;
+        if (p.src_stride == p.D || n_items == 1) {
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             hq_tc::smem_u32(dst)),
+                         "l"(p.src + item0 * p.src_stride), "r"(n_items * row_bytes), "r"(bar)
+                         : "memory");
+        } else {
+            for (uint32_t il = 0; il < n_items; ++il)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 hq_tc::smem_u32(dst + il * (uint32_t)p.D)),
+                             "l"(p.src + (item0 + il) * p.src_stride), "r"(row_bytes), "r"(bar)
+                             : "memory");
         }
     };
 
-    __shared__ volatile uint32_t s_done;
-    if (tid == 0) s_done = 0;
+    __shared__ __align__(8) uint64_t s_free[2];         // see k_item_pass
+    if (tid == 0) {
+        hq_tc::mbar_init(&s_free[0], 1);
+        hq_tc::mbar_init(&s_free[1], 1);
+        for (int i = 0; i < stages; ++i) hq_tc::mbar_init(&s_full[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
+    if (tid == 0) {
+        int64_t c = blockIdx.x;
+        for (int i = 0; i < stages && c < p.num_chunks; ++i, c += gridDim.x) issue_loads(c, i);
+    }
 
-    float4 v[kQPT];
-    int64_t chunk = blockIdx.x;
-    if (chunk < p.num_chunks) load_chunk(chunk, v);
-    uint32_t ring = 0, iter = 0;
-    for (; chunk < p.num_chunks; chunk += gridDim.x, ring = (ring + 1 == RING ? 0 : ring + 1), ++iter) {
+    uint32_t ring = 0, iter = 0, st = 0, st_phase = 0;
+    for (int64_t chunk = blockIdx.x; chunk < p.num_chunks; chunk += gridDim.x, ring = (ring + 1 == (uint32_t)kRing ? 0 : ring + 1), ++iter) {
         const int64_t item0 = chunk * G::ipc;
         const int64_t left = p.N - item0;
         const bool full = left >= (int64_t)G::ipc;
         float* img = s_img0 + ring * kImg;
         P* pyrb = s_pyr0 + (iter & 1u) * G::pyr_vals;
+        float4 v[kQPT];
 
-        // the index warp reads pyramid (iter & 1) and image ring: it must be done with chunk iter-2
-        // (pyramid) and, for RING == 2, that is also the image; for RING == 3 the image of chunk
-        // iter-3 was released even earlier
-        if (!idx_warp && p.plan_len > 0 && iter >= 2) {
-            while (s_done + 1 < iter) __nanosleep(64);
-        }
         if (!idx_warp) {
-            if (RING == 2) {
-                // store(iter-2) has finished reading this image
-                if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                asm volatile("bar.sync 2, %0;" ::"n"(kThreads) : "memory");
+            // ---- this chunk's source rows have landed in the staging buffer ----
+            hq_tc::mbar_wait(&s_full[st], st_phase);
+            const float* stg = s_stage0 + (size_t)st * stage_floats;
+#pragma unroll
+            for (int r = 0; r < kQPT; ++r) {
+                float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+                const uint32_t il = (tid + r * kThreads) >> G::log2qpi;
+                if (((live_bits >> r) & 1u) && (full || (int64_t)il < left)) val = *reinterpret_cast<const float4*>(stg + st_off[r]);
+                v[r] = val;
             }
+            // the index warp reads pyramid (iter & 1): it must be done with chunk iter-2 (the image of
+            // chunk iter-3 was released even earlier)
+            if (p.plan_len > 0 && iter >= 2) hq_tc::mbar_wait(&s_free[iter & 1u], ((iter >> 1) - 1u) & 1u);
 #pragma unroll
             for (int r = 0; r < kQPT; ++r) {
                 if ((live_bits >> r) & 1u) {
@@ -347,33 +416,28 @@ __global__ void __launch_bounds__(kBlock, RING == 2 ? 4 : 3) k_item_pass_bulk(co
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            // RING == 3: store(iter-2) has finished reading its image before anybody passes this
-            // barrier, so chunk iter+1 may scatter into it
-            if (RING == 3 && tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            // store(iter - kRing + 1) has finished reading its image before anybody passes this barrier,
+            // so chunk iter+1 may scatter into it
+            if (tid == 0) {
+                if (kRing == 2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                else if (kRing == 3) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                else if (kRing == 4) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+                else asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+            }
             asm volatile("bar.sync 2, %0;" ::"n"(kThreads) : "memory");
             if (tid == 0) {
-                const uint32_t bytes = full ? kImg * 4u : (uint32_t)left * G::cells * 4u;
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.grid_out + item0 * (int64_t)G::cells),
-                             "r"(hq_tc::smem_u32(img)), "r"(bytes)
-                             : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-        }
-
-        float4 nv[kQPT];
-        const int64_t next = chunk + gridDim.x;
-        if (next < p.num_chunks && !idx_warp) load_chunk(next, nv);
-
-        if (!idx_warp) {
-            if (want_pyr) {
-#pragma unroll
-                for (int r = 0; r < kQPT; ++r) {
-                    if (!((live_bits >> r) & 1u)) continue;
-                    const uint32_t qi = tid + r * kThreads;
-                    const uint32_t il = qi >> G::log2qpi, q = qi & (G::qpi - 1);
-                    pyrb[il * G::pyr_items + q] = mean4<MODE>(v[r].x, v[r].y, v[r].z, v[r].w);
+                if (p.grid_out) {
+                    const uint32_t bytes = full ? kImg * 4u : (uint32_t)left * G::cells * 4u;
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.grid_out + item0 * (int64_t)G::cells),
+                                 "r"(hq_tc::smem_u32(img)), "r"(bytes)
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
+                // every data thread has read staging buffer st: refill it
+                const int64_t nx = chunk + (int64_t)stages * gridDim.x;
+                if (nx < p.num_chunks) issue_loads(nx, (int)st);
             }
+            if (want_pyr) pyramid_levels_123<MODE, LOG2T>(v, live_bits, warp_live, pyrb, tid, lane);
             if (p.plan_len > 0) {
                 if (iter & 1u) asm volatile("bar.arrive 3, %0;" ::"n"(kBlock) : "memory");
                 else asm volatile("bar.arrive 1, %0;" ::"n"(kBlock) : "memory");
@@ -381,98 +445,79 @@ __global__ void __launch_bounds__(kBlock, RING == 2 ? 4 : 3) k_item_pass_bulk(co
         } else if (p.plan_len > 0) {
             if (iter & 1u) asm volatile("bar.sync 3, %0;" ::"n"(kBlock) : "memory");
             else asm volatile("bar.sync 1, %0;" ::"n"(kBlock) : "memory");
-            if (want_pyr) {
-                uint32_t base_prev = 0, cnt_prev = G::qpi;
-                uint32_t live_prev = (uint32_t)((p.D + 3) >> 2);
-#pragma unroll
-                for (int k = 2; k <= LOG2T; ++k) {
-                    const uint32_t cnt = cnt_prev >> 2, base = base_prev + cnt_prev;
-                    const uint32_t live = (live_prev + 3) >> 2;
-                    for (uint32_t il = 0; il < G::ipc; ++il) {
-                        P* pyr = pyrb + il * G::pyr_items;
-                        for (uint32_t j = lane; j < live; j += 32) {
-                            const P a = pyr[base_prev + 4 * j], b = pyr[base_prev + 4 * j + 1];
-                            const P c = pyr[base_prev + 4 * j + 2], d = pyr[base_prev + 4 * j + 3];
-                            pyr[base + j] = MODE == 0 ? (P)(((a + b) + (c + d)) * (P)0.25) : (P)((((a + b) + c) + d) * (P)0.25);
-                        }
-                    }
-                    __syncwarp();
-                    base_prev = base;
-                    cnt_prev = cnt;
-                    live_prev = live;
-                }
-            }
+            if (want_pyr) pyramid_levels_top<MODE, LOG2T>(pyrb, (uint32_t)((p.D + 3) >> 2), lane);
             P* out = reinterpret_cast<P*>(p.idx_out) + item0 * p.idx_stride;
             const uint32_t n_items = full ? G::ipc : (uint32_t)left;
-            for (uint32_t il = 0; il < n_items; ++il) {
-                const float* im = img + il * G::cells;
-                const P* pyr = pyrb + il * G::pyr_items;
-                for (int i = lane; i < p.plan_len; i += 32) {
-                    const int32_t off = plan_in_smem ? s_plan[i] : __ldg(p.plan + i);
-                    P val = (P)0;
-                    if (off >= 0) {
-                        if ((uint32_t)off < G::cells) val = (P)im[off];
-                        else val = pyr[(uint32_t)off - G::cells];
-                    }
-                    __stcs(out + il * p.idx_stride + i, val);
+            for (uint32_t e = lane; e < n_items * (uint32_t)p.plan_len; e += 32) {
+                const uint32_t il = e / (uint32_t)p.plan_len, i = e - il * (uint32_t)p.plan_len;
+                const int32_t off = plan_in_smem ? s_plan[i] : __ldg(p.plan + i);
+                P val = (P)0;
+                if (off >= 0) {
+                    if ((uint32_t)off < G::cells) val = (P)img[il * G::cells + off];
+                    else val = pyrb[il * G::pyr_items + (uint32_t)off - G::cells];
                 }
+                __stcs(out + il * p.idx_stride + i, val);
             }
             __syncwarp();
-            if (lane == 0) s_done = iter + 1;
+            if (lane == 0) hq_tc::mbar_arrive(&s_free[iter & 1u]);
         }
-#pragma unroll
-        for (int r = 0; r < kQPT; ++r) v[r] = nv[r];
+        if (++st == (uint32_t)stages) { st = 0; st_phase ^= 1u; }
     }
     // the images must outlive the stores that read them
     if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-template <int LOG2T>
-inline size_t smem_bytes_bulk(int mode, int ring) {
-    using G = Geo<LOG2T>;
-    return (size_t)ring * 4096 * 4 + (size_t)2 * G::pyr_vals * (mode ? 8 : 4) + (size_t)kPlanCap * 4 + 16;
-}
-
-// true when the bulk-store variant can take this call (dense, 16-byte aligned grid output)
+// true when the bulk-copy variant can take this call (no grid output, or a dense 16-byte aligned one;
+// rows that are whole 16-byte units; few enough items per chunk that one thread can issue their loads)
 inline bool bulk_eligible(const TileParams& p) {
-    return p.direction == 0 && p.grid_out && p.vec_grid && p.grid_stride == ((int64_t)1 << (2 * p.log2t));
+    return p.direction == 0 && p.vec_src && p.log2t >= 5 && p.D >= 4 &&
+           (!p.grid_out || (p.vec_grid && p.grid_stride == ((int64_t)1 << (2 * p.log2t))));
 }
 
-template <int MODE, int LOG2T, int RING>
+inline int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e && *e ? atoi(e) : dflt;
+}
+
+template <int MODE, int LOG2T>
 int launch_bulk_t(const TileParams& p, cudaStream_t st) {
-    const size_t smem = smem_bytes_bulk<LOG2T>(MODE, RING);
-    static int per_sm = 0;
-    if (per_sm == 0) {
-        HQ_CUDA_OK(cudaFuncSetAttribute(k_item_pass_bulk<MODE, LOG2T, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        HQ_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_item_pass_bulk<MODE, LOG2T, RING>, kBlock, smem));
-        if (per_sm < 1) per_sm = 1;
+    using G = Geo<LOG2T>;
+    // images: kRing chunk images when a grid is written (the stores read them asynchronously), two otherwise
+    // staging: as many chunk-sized source buffers as fit the per-CTA budget
+    // Measured on B200 (tools/bench_item_pass.py, 262144 items): what matters is CTAs per SM (4 x 55 KB:
+    // 6.2-6.3 TB/s for 1536-D/64x64 and 768-D/32x32; 2 x 110 KB with 7 stages: 5.3 TB/s), so the
+    // default is the smallest footprint: two images, two staging buffers.  Tuning knobs, not API.
+    static const int ring_cfg = env_int("HQ_ITEM_RING", 2), stages_cfg = env_int("HQ_ITEM_STAGES", 0),
+                     budget_kb = env_int("HQ_ITEM_SMEM_KB", 55), ctas_cap = env_int("HQ_ITEM_CTAS", 8);
+    const int ring = p.grid_out ? ring_cfg : 2;
+    const uint32_t stage_floats = (uint32_t)(G::ipc * p.D + 31) & ~31u;
+    const int plan_cap = (p.plan_len <= kPlanCap ? (p.plan_len + 31) & ~31 : 0);
+    const size_t fixed = (size_t)ring * 4096 * 4 + (size_t)2 * G::pyr_vals * (MODE ? 8 : 4) + (size_t)plan_cap * 4 + 64;
+    const size_t budget = (size_t)budget_kb * 1024;
+    int stages = budget > fixed ? (int)((budget - fixed) / ((size_t)stage_floats * 4)) : 2;
+    if (stages_cfg > 0) stages = stages_cfg;
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) stages = 2;
+    const size_t smem = fixed + (size_t)stages * stage_floats * 4;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        HQ_CUDA_OK(cudaFuncSetAttribute(k_item_pass_bulk<MODE, LOG2T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
     }
+    int per_sm = 0;
+    HQ_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_item_pass_bulk<MODE, LOG2T>, kBlock, smem));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > ctas_cap) per_sm = ctas_cap;
     int64_t blocks = (int64_t)hq_cached_sm_count() * per_sm;
     if (blocks > p.num_chunks) blocks = p.num_chunks;
-    k_item_pass_bulk<MODE, LOG2T, RING><<<(unsigned)blocks, kBlock, smem, st>>>(p);
+    k_item_pass_bulk<MODE, LOG2T><<<(unsigned)blocks, kBlock, smem, st>>>(p, ring, stages, stage_floats, plan_cap);
     HQ_LAUNCH_OK("k_item_pass_bulk");
     return HQ_OK;
 }
 
-template <int MODE, int RING>
-int launch_bulk_r(const TileParams& p, cudaStream_t st) {
-    switch (p.log2t) {
-        case 2: return launch_bulk_t<MODE, 2, RING>(p, st);
-        case 3: return launch_bulk_t<MODE, 3, RING>(p, st);
-        case 4: return launch_bulk_t<MODE, 4, RING>(p, st);
-        case 5: return launch_bulk_t<MODE, 5, RING>(p, st);
-        default: return launch_bulk_t<MODE, 6, RING>(p, st);
-    }
-}
-
 template <int MODE>
 int launch_bulk(const TileParams& p, cudaStream_t st) {
-    static int ring = 0;
-    if (ring == 0) {
-        const char* e = getenv("HQ_ITEM_RING");
-        ring = (e && e[0] == '2') ? 2 : 3;
-    }
-    return ring == 2 ? launch_bulk_r<MODE, 2>(p, st) : launch_bulk_r<MODE, 3>(p, st);
+    return p.log2t == 5 ? launch_bulk_t<MODE, 5>(p, st) : launch_bulk_t<MODE, 6>(p, st);
 }
 
 template <int LOG2T>
