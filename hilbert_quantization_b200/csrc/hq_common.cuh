@@ -40,9 +40,18 @@ static inline bool hq_is_pow2(int64_t n) { return n > 0 && (n & (n - 1)) == 0; }
 static inline int hq_log2(int64_t n) { int k = 0; while ((int64_t(1) << k) < n) ++k; return k; }
 int hq_cached_sm_count();
 // tensor-core bit-plane pass of the coarse filter (hq_filter_tc.cu), used by hq_filter_fast
+struct HqFilterLists {          // candidate lists written by the pass (see FtcParams in hq_filter_tc.cu)
+    uint32_t* rows;
+    float* k1;
+    float* k2;
+    int32_t* seg_n;
+    int64_t seg_cap;
+    int n_segs;
+};
 int hq_filter_bits_tc_launch(const float* db_packed, const uint32_t* valid, int64_t valid_pitch, int64_t N,
                              const hq_index_layout* layout, const float* q_idx, int Q, const float* xstar, float* q_packed,
-                             float* tq, uint32_t* bits, int64_t bits_pitch, cudaStream_t st);
+                             float* tq, float* nq, uint32_t* bits, int64_t bits_pitch, const HqFilterLists* lists, cudaStream_t st);
+extern "C" int hq_filter_tc_plan(int64_t N, int Q, int* n_ranges, int* tiles_per_range);
 
 // ---- Hilbert curve, the reference's variant (core/hilbert_mapper.py:42-113) ----
 // d -> (x, y), low bit-pairs first.

@@ -19,6 +19,7 @@
 // Reference semantics: rag/search/engine.py:178-287.
 #include "hq_common.cuh"
 #include <float.h>
+#include <math.h>
 #include <string.h>
 
 namespace {
@@ -240,6 +241,7 @@ struct CascadeParams {
     int32_t* n_out;              // [Q]
     uint32_t* scratch_keys;      // [gridDim][N]
     uint32_t* scratch_rows;      // [gridDim][N]
+    const int32_t* only;         // optional [Q]: process only queries with a non-zero flag
 };
 
 __device__ __forceinline__ uint32_t block_sum(uint32_t v, uint32_t* s_warp) {
@@ -288,6 +290,7 @@ __global__ void __launch_bounds__(1024, 1) k_filter_cascade(const CascadeParams 
     const int64_t words_pad = (p.words + 31) & ~(int64_t)31;
 
     for (int q = blockIdx.x; q < p.Q; q += gridDim.x) {
+        if (p.only && !p.only[q]) continue;
         uint32_t* M = p.mask + (int64_t)q * p.mask_stride;
         int64_t n_alive = p.N;
         for (int l = 0; l < L; ++l) {
@@ -477,6 +480,354 @@ __global__ void __launch_bounds__(1024, 1) k_filter_cascade(const CascadeParams 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Cascade over the candidate lists written by the tensor-core pass (hq_filter_tc.cu).
+//
+// k_filter_cascade re-ranks by GATHERING the index rows of ~200 K survivors per query out of
+// L2 (4.2 ms per 1024-query batch, long-scoreboard bound).  The tensor-core pass already has
+// every level's dot product in registers, so it appends (row, k1, k2) of the rows that pass
+// the level-0 and level-1 thresholds to per-query lists; within a query the dot product
+// orders rows exactly like the score ((dot / |q| + 1) / 2 is monotone), so the ratio cuts
+// become streaming selections over compact, coalesced arrays:
+//     level 1: keep the cap1 best of the list by k1 (ties -> lower row id)
+//     level 2: of those, the rows that pass the level-2 threshold; keep the cap2 best by k2
+// Selection = 2048-bin LINEAR histogram between the level's threshold and |q| (the largest
+// possible dot product), then an exact ranking of the cut bin in shared memory; the result
+// is a boundary (K, R): kept <=> k > K or (k == K and row < R).
+// Queries it cannot handle (level-0 cut binds, list overflow, a cut bin larger than the
+// buffer, L == 1) set fallback[q]; k_filter_cascade then runs for exactly those.
+// ---------------------------------------------------------------------------------------
+struct ListParams {
+    const uint32_t* bits;        // [L][Q][bits_pitch] (plane 0 is counted)
+    int64_t words, bits_pitch;
+    int64_t N;
+    int L, Q;
+    double ratio[8];
+    const float* tq;             // [3][Q] threshold in dot-product units
+    const float* nq;             // [3][Q] |q_l|
+    const uint32_t* l_rows;
+    const float* l_k1;
+    const float* l_k2;
+    const int32_t* seg_n;
+    int64_t seg_cap;
+    int n_segs;
+    uint32_t* mask;              // [Q, mask_stride], zero-filled by the caller
+    int64_t mask_stride;
+    int32_t* counts;             // optional [L][3][Q]
+    int32_t* n_out;              // [Q]
+    int32_t* fallback;           // [Q] out
+    float* tmp_keys;             // [gridDim][N] compacted level-2 candidates of the query in flight
+    uint32_t* tmp_rows;          // [gridDim][N]
+};
+
+constexpr int kMaxSegs = 320;
+constexpr int kCutCap = 2048;
+constexpr int kU = 4;                 // independent list loads in flight per thread
+
+struct Boundary { float K; uint32_t R; };      // kept <=> k > K || (k == K && row < R)
+__device__ __forceinline__ bool kept_by(const Boundary& b, float k, uint32_t row) { return k > b.K || (k == b.K && row < b.R); }
+
+__device__ __forceinline__ uint32_t lin_bin(float k, float lo, float scale) {
+    const float x = (k - lo) * scale;
+    int b = (int)x;
+    b = b < 0 ? 0 : b;
+    return b > 2047 ? 2047u : (uint32_t)b;
+}
+
+// bin holding the drop-th smallest element of a 2048-bin histogram: sh[0] = bin, sh[1] = rank inside it (1-based),
+// sh[2] = population of the bin
+__device__ __forceinline__ void find_cut_bin(const uint32_t* hist, uint32_t drop, uint32_t* sh) {
+    const int tid = threadIdx.x;
+    if (tid < 32) {
+        uint32_t sum = 0;
+        for (uint32_t b = 0; b < 64; ++b) sum += hist[tid * 64 + b];
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (tid >= o) incl += t;
+        }
+        const uint32_t excl = incl - sum;
+        if (excl < drop && drop <= incl) {
+            uint32_t below = excl, b = tid * 64;
+            for (;; ++b) {
+                const uint32_t h = hist[b];
+                if (below + h >= drop) break;
+                below += h;
+            }
+            sh[0] = b; sh[1] = drop - below; sh[2] = hist[b];
+        }
+    }
+    __syncthreads();
+}
+
+// exact boundary inside the cut bin: the r_in_bin lowest (key asc, row desc) entries of the buffer are dropped
+__device__ __forceinline__ void rank_cut_bin(const float* b_key, const uint32_t* b_row, uint32_t nb, uint32_t r_in_bin, float* s_K,
+                                             uint32_t* s_R) {
+    for (uint32_t e = threadIdx.x; e < nb; e += blockDim.x) {
+        const float key = b_key[e];
+        const uint32_t row = b_row[e];
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < nb; ++j) {
+            const float kj = b_key[j];
+            const uint32_t rj = b_row[j];
+            rank += (kj < key || (kj == key && rj > row)) ? 1u : 0u;
+        }
+        if (rank == r_in_bin - 1) { *s_K = key; *s_R = row; }     // the last dropped entry
+    }
+    __syncthreads();
+}
+
+// warp-aggregated append position in a block-wide compact list (count kept in shared memory)
+__device__ __forceinline__ uint32_t compact_slot(bool take, uint32_t* s_count) {
+    const uint32_t m = __ballot_sync(0xffffffffu, take);
+    const int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == 0 && m) base = atomicAdd(s_count, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    return base + __popc(m & ((1u << lane) - 1u));
+}
+
+__global__ void __launch_bounds__(1024, 1) k_filter_cascade_lists(const ListParams p) {
+    __shared__ uint32_t hist[2048];
+    __shared__ uint32_t sh[4];
+    __shared__ uint32_t s_warp[32];
+    __shared__ int32_t s_cnt[kMaxSegs];
+    __shared__ float b_key[kCutCap];
+    __shared__ uint32_t b_row[kCutCap];
+    __shared__ uint32_t s_bufn, s_flag, s_R, s_n2;
+    __shared__ float s_K;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    // level-2 candidates of the query this CTA works on, compacted by the level-1 pass
+    float* const c_k2 = p.tmp_keys + (int64_t)blockIdx.x * p.N;
+    uint32_t* const c_row = p.tmp_rows + (int64_t)blockIdx.x * p.N;
+
+    for (int q = blockIdx.x; q < p.Q; q += gridDim.x) {
+        // ---- segment table, overflow check ----
+        if (tid == 0) { s_flag = 0; s_n2 = 0; s_bufn = 0; }
+        __syncthreads();
+        uint32_t part = 0;
+        for (int i = tid; i < p.n_segs; i += nt) {
+            const int32_t n = p.seg_n[(int64_t)q * p.n_segs + i];
+            if (n > p.seg_cap) s_flag = 1;
+            s_cnt[i] = n;
+            part += (uint32_t)n;
+        }
+        const uint32_t n1 = block_sum(part, s_warp);
+        // ---- level 0: survivors of the threshold; its ratio cut must not bind ----
+        const uint32_t* P0 = p.bits + (int64_t)q * p.bits_pitch;
+        uint32_t c = 0;
+        for (int64_t w = tid; w < p.words; w += nt) {
+            uint32_t v = __ldg(P0 + w);
+            const int64_t r0 = w * 32;
+            if (r0 + 32 > p.N) v &= (1u << (uint32_t)(p.N - r0)) - 1u;
+            c += __popc(v);
+        }
+        const uint32_t c0 = block_sum(c, s_warp);
+        int64_t cap0 = (int64_t)((double)p.N * p.ratio[0]);
+        if (cap0 < 1) cap0 = 1;
+        if (s_flag || (int64_t)c0 > cap0 || p.L < 2) {
+            if (tid == 0) p.fallback[q] = 1;
+            __syncthreads();
+            continue;
+        }
+        const int64_t qbase = (int64_t)q * p.n_segs * p.seg_cap;
+        const uint32_t* const L_rows = p.l_rows + qbase;
+        const float* const L_k1 = p.l_k1 + qbase;
+        const float* const L_k2 = p.l_k2 ? p.l_k2 + qbase : nullptr;
+
+        // ---- level 1: ratio cut over the whole list by k1 ----
+        int64_t cap1 = (int64_t)((double)c0 * p.ratio[1]);
+        if (cap1 < 1) cap1 = 1;
+        Boundary b1;
+        b1.K = -INFINITY; b1.R = 0;
+        bool failed = false;
+        if ((int64_t)n1 > cap1) {
+            const uint32_t drop = n1 - (uint32_t)cap1;
+            const float lo = __ldg(p.tq + (int64_t)1 * p.Q + q), hi = __ldg(p.nq + (int64_t)1 * p.Q + q);
+            const float scale = hi > lo ? 2048.0f / (hi - lo) : 0.f;
+            for (int i = tid; i < 2048; i += nt) hist[i] = 0;
+            __syncthreads();
+            // one batch of kU independent loads per thread and segment (segments hold a few thousand entries)
+            for (int item = warp; item < 2 * p.n_segs; item += nw) {       // a warp owns half a segment at a time
+                const uint32_t cnt = (uint32_t)s_cnt[item >> 1], mid = min(cnt, ((cnt >> 1) + 31u) & ~31u);
+                const uint32_t lo_e = (item & 1) ? mid : 0u, n = (item & 1) ? cnt : mid;
+                const uint32_t off = (uint32_t)(item >> 1) * (uint32_t)p.seg_cap;
+                for (uint32_t e0 = lo_e + lane; e0 - lane < n; e0 += kU * 32) {      // warp-uniform trip count
+
+                    float k[kU];
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) k[u] = e0 + u * 32 < n ? __ldg(L_k1 + off + e0 + u * 32) : -1.0f;
+#pragma unroll
+                    for (int u = 0; u < kU; ++u)
+                        if (e0 + u * 32 < n) atomicAdd(&hist[lin_bin(k[u], lo, scale)], 1u);
+                }
+            }
+            __syncthreads();
+            find_cut_bin(hist, drop, sh);
+            const uint32_t cb = sh[0], r_in_bin = sh[1], n_in_bin = sh[2];
+            if (n_in_bin > (uint32_t)kCutCap) failed = true;
+            else {
+                for (int item = warp; item < 2 * p.n_segs; item += nw) {       // a warp owns half a segment at a time
+                    const uint32_t cnt = (uint32_t)s_cnt[item >> 1], mid = min(cnt, ((cnt >> 1) + 31u) & ~31u);
+                    const uint32_t lo_e = (item & 1) ? mid : 0u, n = (item & 1) ? cnt : mid;
+                    const uint32_t off = (uint32_t)(item >> 1) * (uint32_t)p.seg_cap;
+                    for (uint32_t e0 = lo_e + lane; e0 - lane < n; e0 += kU * 32) {      // warp-uniform trip count
+
+                        float k[kU];
+#pragma unroll
+                        for (int u = 0; u < kU; ++u) k[u] = e0 + u * 32 < n ? __ldg(L_k1 + off + e0 + u * 32) : -1.0f;
+#pragma unroll
+                        for (int u = 0; u < kU; ++u) {
+                            if (e0 + u * 32 < n && lin_bin(k[u], lo, scale) == cb) {
+                                const uint32_t slot = atomicAdd(&s_bufn, 1u);
+                                b_key[slot] = k[u]; b_row[slot] = __ldg(L_rows + off + e0 + u * 32) & 0x7fffffffu;
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+                rank_cut_bin(b_key, b_row, s_bufn, r_in_bin, &s_K, &s_R);
+                b1.K = s_K; b1.R = s_R;
+            }
+        }
+        if (failed) {
+            if (tid == 0) p.fallback[q] = 1;
+            __syncthreads();
+            continue;
+        }
+        const int64_t out1 = (int64_t)n1 > cap1 ? cap1 : (int64_t)n1;
+        if (p.counts && tid == 0) {
+            p.counts[((int64_t)0 * 3 + 0) * p.Q + q] = (int32_t)p.N;
+            p.counts[((int64_t)0 * 3 + 1) * p.Q + q] = (int32_t)c0;
+            p.counts[((int64_t)0 * 3 + 2) * p.Q + q] = (int32_t)c0;
+            p.counts[((int64_t)1 * 3 + 0) * p.Q + q] = (int32_t)c0;
+            p.counts[((int64_t)1 * 3 + 1) * p.Q + q] = (int32_t)n1;
+            p.counts[((int64_t)1 * 3 + 2) * p.Q + q] = (int32_t)out1;
+        }
+        uint32_t* M = p.mask + (int64_t)q * p.mask_stride;
+        if (p.L == 2) {
+            for (int item = warp; item < 2 * p.n_segs; item += nw) {       // a warp owns half a segment at a time
+                const uint32_t cnt = (uint32_t)s_cnt[item >> 1], mid = min(cnt, ((cnt >> 1) + 31u) & ~31u);
+                const uint32_t lo_e = (item & 1) ? mid : 0u, n = (item & 1) ? cnt : mid;
+                const uint32_t off = (uint32_t)(item >> 1) * (uint32_t)p.seg_cap;
+                for (uint32_t e0 = lo_e + lane; e0 - lane < n; e0 += kU * 32) {      // warp-uniform trip count
+
+                    float k[kU];
+                    uint32_t rw[kU];
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) {
+                        const bool ok = e0 + u * 32 < n;
+                        k[u] = ok ? __ldcs(L_k1 + off + e0 + u * 32) : -INFINITY;
+                        rw[u] = ok ? __ldcs(L_rows + off + e0 + u * 32) : 0u;
+                    }
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) {
+                        const uint32_t row = rw[u] & 0x7fffffffu;
+                        if (e0 + u * 32 < n && kept_by(b1, k[u], row)) atomicOr(&M[row >> 5], 1u << (row & 31));
+                    }
+                }
+            }
+            if (tid == 0) p.n_out[q] = (int32_t)out1;
+            __syncthreads();
+            continue;
+        }
+
+        // ---- level 2: survivors of cut 1 that pass the level-2 threshold are compacted; histogram of k2 on the fly ----
+        const float lo2 = __ldg(p.tq + (int64_t)2 * p.Q + q), hi2 = __ldg(p.nq + (int64_t)2 * p.Q + q);
+        const float scale2 = hi2 > lo2 ? 2048.0f / (hi2 - lo2) : 0.f;
+        __syncthreads();
+        for (int i = tid; i < 2048; i += nt) hist[i] = 0;
+        if (tid == 0) s_bufn = 0;
+        __syncthreads();
+        for (int item = warp; item < 2 * p.n_segs; item += nw) {       // a warp owns half a segment at a time
+            const uint32_t cnt = (uint32_t)s_cnt[item >> 1], mid = min(cnt, ((cnt >> 1) + 31u) & ~31u);
+            const uint32_t lo_e = (item & 1) ? mid : 0u, n = (item & 1) ? cnt : mid;
+            const uint32_t off = (uint32_t)(item >> 1) * (uint32_t)p.seg_cap;
+            for (uint32_t e0 = lo_e + lane; e0 - lane < n; e0 += kU * 32) {      // warp-uniform trip count
+
+                float k1[kU], k2[kU];
+                uint32_t rw[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const bool ok = e0 + u * 32 < n;
+                    rw[u] = ok ? __ldcs(L_rows + off + e0 + u * 32) : 0u;            // bit 31 clear -> not a candidate
+                    k1[u] = ok ? __ldcs(L_k1 + off + e0 + u * 32) : 0.f;
+                    k2[u] = ok ? __ldcs(L_k2 + off + e0 + u * 32) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    if ((e0 - lane) + u * 32 >= n) break;                             // whole warp beyond its range
+                    const uint32_t row = rw[u] & 0x7fffffffu;
+                    const bool take = (rw[u] >> 31) && kept_by(b1, k1[u], row);
+                    const uint32_t slot = compact_slot(take, &s_n2);
+                    if (take) {
+                        c_k2[slot] = k2[u];
+                        c_row[slot] = row;
+                        atomicAdd(&hist[lin_bin(k2[u], lo2, scale2)], 1u);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t n2 = s_n2;
+        int64_t cap2 = (int64_t)((double)out1 * p.ratio[2]);
+        if (cap2 < 1) cap2 = 1;
+        Boundary b2;
+        b2.K = -INFINITY; b2.R = 0;
+        if ((int64_t)n2 > cap2) {
+            const uint32_t drop = n2 - (uint32_t)cap2;
+            find_cut_bin(hist, drop, sh);
+            const uint32_t cb = sh[0], r_in_bin = sh[1], n_in_bin = sh[2];
+            if (n_in_bin > (uint32_t)kCutCap) failed = true;
+            else {
+                for (uint32_t e0 = tid; e0 < n2; e0 += kU * nt) {
+                    float k[kU];
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) k[u] = e0 + u * nt < n2 ? __ldcg(c_k2 + e0 + u * nt) : -1.0f;
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) {
+                        if (e0 + u * nt < n2 && lin_bin(k[u], lo2, scale2) == cb) {
+                            const uint32_t slot = atomicAdd(&s_bufn, 1u);
+                            b_key[slot] = k[u]; b_row[slot] = __ldcg(c_row + e0 + u * nt);
+                        }
+                    }
+                }
+                __syncthreads();
+                rank_cut_bin(b_key, b_row, s_bufn, r_in_bin, &s_K, &s_R);
+                b2.K = s_K; b2.R = s_R;
+            }
+        }
+        if (failed) {
+            if (tid == 0) p.fallback[q] = 1;
+            __syncthreads();
+            continue;
+        }
+        const int64_t out2 = (int64_t)n2 > cap2 ? cap2 : (int64_t)n2;
+        if (p.counts && tid == 0) {
+            p.counts[((int64_t)2 * 3 + 0) * p.Q + q] = (int32_t)out1;
+            p.counts[((int64_t)2 * 3 + 1) * p.Q + q] = (int32_t)n2;
+            p.counts[((int64_t)2 * 3 + 2) * p.Q + q] = (int32_t)out2;
+        }
+        for (uint32_t e0 = tid; e0 < n2; e0 += kU * nt) {
+            float k[kU];
+            uint32_t row[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const bool ok = e0 + u * nt < n2;
+                k[u] = ok ? __ldcg(c_k2 + e0 + u * nt) : -INFINITY;
+                row[u] = ok ? __ldcg(c_row + e0 + u * nt) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u)
+                if (e0 + u * nt < n2 && kept_by(b2, k[u], row[u])) atomicOr(&M[row[u] >> 5], 1u << (row[u] & 31));
+        }
+        if (tid == 0) p.n_out[q] = (int32_t)out2;
+        __syncthreads();
+    }
+}
+
 template <int K0, int K1, int K2>
 int launch_bits(const BitsParams& p, cudaStream_t st) {
     constexpr int KT = K0 + K1 + K2;
@@ -521,13 +872,35 @@ extern "C" int hq_filter_fast_supported(const hq_index_layout* layout) {
 
 static inline int64_t plane_pitch(int64_t N) { return ((N + 31) / 32 + 7) & ~(int64_t)7; }      // words, 32-byte rows
 static inline int64_t up16(int64_t b) { return (b + 15) & ~(int64_t)15; }
+static inline int64_t up128(int64_t b) { return (b + 127) & ~(int64_t)127; }
+
+struct ListGeom { int n_segs; int64_t seg_cap; bool on; };
+
+// candidate-list geometry of the tensor-core pass for (N, Q): two segments per row range, each sized
+// for a third of its rows (random data passes ~13-20 % of the rows through levels 0 and 1)
+static ListGeom list_geom(int64_t N, int Q, const hq_index_layout* layout) {
+    ListGeom g{0, 0, false};
+    if (!layout || layout->L < 2 || !hq_filter_tc_supported(layout) || N <= 0 || Q <= 0) return g;
+    int n_ranges = 0, tiles_per = 0;
+    if (hq_filter_tc_plan(N, Q, &n_ranges, &tiles_per) != HQ_OK) return g;
+    g.n_segs = 2 * n_ranges;
+    if (g.n_segs > kMaxSegs) return g;
+    g.seg_cap = (((int64_t)tiles_per * 32 + 2) / 3 + 31) & ~(int64_t)31;
+    g.on = true;
+    return g;
+}
 
 extern "C" int64_t hq_filter_fast_scratch_bytes(int64_t N, int Q, const hq_index_layout* layout) {
     if (!layout || N <= 0 || Q <= 0) return 0;
     int grid = hq_cached_sm_count();
     if (grid > Q) grid = Q;
-    // bit planes | cascade key / row lists | packed query operand + thresholds of the tensor-core pass
-    return (int64_t)layout->L * Q * plane_pitch(N) * 4 + up16((int64_t)grid * N * 8) + (int64_t)Q * 128 * 4 + up16((int64_t)3 * Q * 4);
+    // bit planes | generic cascade key / row lists | packed query operand, thresholds, norms, fallback flags |
+    // candidate lists of the tensor-core pass
+    int64_t b = (int64_t)layout->L * Q * plane_pitch(N) * 4 + up16((int64_t)grid * N * 8) + (int64_t)Q * 128 * 4 +
+                3 * up16((int64_t)3 * Q * 4);
+    const ListGeom g = list_geom(N, Q, layout);
+    if (g.on) b += 256 + up128((int64_t)Q * g.n_segs * 4) + (int64_t)(layout->L > 2 ? 3 : 2) * Q * g.n_segs * g.seg_cap * 4;
+    return b;
 }
 
 extern "C" int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, const hq_index_layout* layout, const float* q_idx, int Q,
@@ -553,6 +926,17 @@ extern "C" int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, c
     uint32_t* const sc_rows = sc_keys + (int64_t)grid * N;
     float* const q_packed = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(sc_keys) + up16((int64_t)grid * N * 8));
     float* const tq = q_packed + (int64_t)Q * 128;
+    float* const nq = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(tq) + up16((int64_t)3 * Q * 4));
+    int32_t* const fallback = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(nq) + up16((int64_t)3 * Q * 4));
+    const ListGeom lg = db_packed ? list_geom(N, Q, layout) : ListGeom{0, 0, false};
+    HqFilterLists lists{};
+    if (lg.on) {
+        lists.n_segs = lg.n_segs; lists.seg_cap = lg.seg_cap;
+        lists.seg_n = reinterpret_cast<int32_t*>((reinterpret_cast<uintptr_t>(fallback) + up16((int64_t)3 * Q * 4) + 127) & ~(uintptr_t)127);
+        lists.rows = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(lists.seg_n) + up128((int64_t)Q * lg.n_segs * 4));
+        lists.k1 = reinterpret_cast<float*>(lists.rows + (int64_t)Q * lg.n_segs * lg.seg_cap);
+        lists.k2 = L > 2 ? lists.k1 + (int64_t)Q * lg.n_segs * lg.seg_cap : nullptr;
+    }
 
     BitsParams bp{};
     bp.idx = idx; bp.rnorm = rnorm; bp.N = N; bp.lay = *layout; bp.q_idx = q_idx; bp.Q = Q;
@@ -563,7 +947,8 @@ extern "C" int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, c
     if (db_packed) {
         // tensor-core pass (hq_filter_tc.cu): same planes, 8x fewer SM cycles
         HQ_REQUIRE(valid, "the tensor-core filter needs the validity words of hq_filter_tc_valid");
-        rc = hq_filter_bits_tc_launch(db_packed, valid, valid_pitch, N, layout, q_idx, Q, xstar, q_packed, tq, planes, pitch, st);
+        rc = hq_filter_bits_tc_launch(db_packed, valid, valid_pitch, N, layout, q_idx, Q, xstar, q_packed, tq, nq, planes, pitch,
+                                      lg.on ? &lists : nullptr, st);
     } else if (L == 3) {
         if (k0 <= 24 && k1 <= 8) rc = launch_bits<24, 8, 4>(bp, st);
         else if (k0 <= 32 && k1 <= 8) rc = launch_bits<32, 8, 4>(bp, st);
@@ -604,6 +989,22 @@ extern "C" int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, c
     cp.mask = mask; cp.mask_stride = mask_stride; cp.counts = counts; cp.n_out = n_out;
     cp.scratch_keys = sc_keys;
     cp.scratch_rows = sc_rows;
+    cp.only = nullptr;
+    if (lg.on) {
+        // streaming cascade over the candidate lists; the generic cascade then runs only for the queries it flags
+        HQ_CUDA_OK(cudaMemsetAsync(fallback, 0, (size_t)Q * 4, st));
+        HQ_CUDA_OK(cudaMemsetAsync(mask, 0, (size_t)((int64_t)(Q - 1) * mask_stride + words) * 4, st));
+        ListParams lp{};
+        lp.bits = planes; lp.words = words; lp.bits_pitch = pitch; lp.N = N; lp.L = L; lp.Q = Q;
+        for (int l = 0; l < 8; ++l) lp.ratio[l] = l < L ? ratio[l] : 1.0;
+        lp.tq = tq; lp.nq = nq; lp.l_rows = lists.rows; lp.l_k1 = lists.k1; lp.l_k2 = lists.k2; lp.seg_n = lists.seg_n;
+        lp.seg_cap = lists.seg_cap; lp.n_segs = lists.n_segs; lp.mask = mask; lp.mask_stride = mask_stride; lp.counts = counts;
+        lp.n_out = n_out; lp.fallback = fallback;
+        lp.tmp_keys = reinterpret_cast<float*>(sc_keys); lp.tmp_rows = sc_rows;        // the generic cascade runs afterwards
+        k_filter_cascade_lists<<<grid, 1024, 0, st>>>(lp);
+        HQ_LAUNCH_OK("k_filter_cascade_lists");
+        cp.only = fallback;
+    }
     k_filter_cascade<<<grid, 1024, 0, st>>>(cp);
     HQ_LAUNCH_OK("k_filter_cascade");
     return HQ_OK;

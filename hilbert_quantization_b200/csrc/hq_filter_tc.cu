@@ -29,7 +29,7 @@ namespace {
 constexpr int FM = 128;                        // queries per tile (MMA M)
 constexpr int FR = 64;                         // database rows per tile (MMA N)
 constexpr int KS = 128;                        // packed floats per row: 4 slabs of 32 (128 B)
-constexpr int F_STAGES = 4;
+constexpr int F_STAGES = 3;
 constexpr uint32_t A_SLAB_BYTES = FM * 128;    // 16 KB
 constexpr uint32_t B_SLAB_BYTES = FR * 128;    // 8 KB
 constexpr uint32_t A_BYTES = 4 * A_SLAB_BYTES;
@@ -41,6 +41,7 @@ constexpr uint32_t F_TMEM_COLS = 512;
 constexpr uint32_t kIdescTf32 = make_idesc(2 /*tf32*/, FM, FR);
 constexpr int TILE_GROUP = 4;                  // tiles per flush: 8 words = one 32-byte sector per query and level
 constexpr int STAGE_PITCH = 2 * TILE_GROUP + 1;
+constexpr int LBUF = 16;                       // per-thread staging slots of the candidate lists (flushed 8 at a time)
 
 struct Segs {
     int L;
@@ -76,17 +77,36 @@ struct FtcParams {
     int64_t valid_pitch;
     uint32_t* bits;             // [L][Q][bits_pitch]
     int64_t words, bits_pitch;
+    // optional candidate lists (L >= 2): rows passing levels 0 and 1, one private segment per
+    // (query, row range, tile half) so that no atomics are needed and rows stay ascending
+    uint32_t* l_rows;           // [Q][n_segs][seg_cap]  row | (passes level 2) << 31
+    float* l_k1;                // [Q][n_segs][seg_cap]  level-1 dot product (order == score order within a query)
+    float* l_k2;                // [Q][n_segs][seg_cap]  level-2 dot product (L == 3)
+    int32_t* seg_n;             // [Q][n_segs] entries produced (may exceed seg_cap: overflow, list invalid)
+    int64_t seg_cap;
+    int n_segs;
 };
 
 __device__ __forceinline__ uint32_t pass_word(const uint32_t (&r)[32], float tq) {
-    // bit j = (r[j] >= tq): the sign of (r[j] - tq) is shifted in element by element
-    uint32_t w = 0;
+    // bit j = (r[j] >= tq): the sign of (r[j] - tq) is shifted in element by element; four independent
+    // chains of eight so that the funnel shifts do not serialise on one register
+    uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        const float d = __fadd_rn(__uint_as_float(r[j]), -tq);
-        w = __funnelshift_l(__float_as_uint(d), w, 1);
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float d = __fadd_rn(__uint_as_float(r[c * 8 + j]), -tq);
+            w[c] = __funnelshift_l(__float_as_uint(d), w[c], 1);
+        }
     }
-    return ~__brev(w);
+    const uint32_t all = (w[0] << 24) | (w[1] << 16) | (w[2] << 8) | w[3];      // bit 31 - j = sign of element j
+    return ~__brev(all);
+}
+
+__device__ __forceinline__ void st_global_256(uint32_t* dst, const uint32_t (&v)[8]) {       // one full 32-byte sector
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
 }
 
 __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_constant__ CUtensorMap map_q,
@@ -96,7 +116,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
     uint8_t* smem_a = smem;                                        // query tile, resident for a unit
     uint8_t* smem_b = smem + A_BYTES;                              // F_STAGES database tiles
     uint32_t* s_stage = reinterpret_cast<uint32_t*>(smem_b + F_STAGES * B_STAGE_BYTES);   // [3][128][STAGE_PITCH]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + ((3 * FM * STAGE_PITCH + 1) & ~1));
+    uint32_t* s_lists = s_stage + ((3 * FM * STAGE_PITCH + 3) & ~3);                      // [3][LBUF][EPI_THREADS]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_lists + 3 * LBUF * EPI_THREADS);
     uint64_t* full_bar = bars;                      // [F_STAGES]
     uint64_t* empty_bar = bars + F_STAGES;          // [F_STAGES]
     uint64_t* tfull_bar = bars + 2 * F_STAGES;      // [2]
@@ -198,6 +219,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
             float tq[3];
 #pragma unroll
             for (int l = 0; l < 3; ++l) tq[l] = (q_ok && l < p.L) ? __ldg(p.tq + (int64_t)l * p.Q + q) : __int_as_float(0x7fc00000);
+            const bool lists = p.l_rows != nullptr && p.L >= 2 && q_ok;
+            const int64_t seg_base = ((int64_t)q * p.n_segs + (range * 2 + half)) * p.seg_cap;
+            int seg_pos = 0, seg_flushed = 0;
+            uint32_t* const sl_base = s_lists + et;
+            const uint32_t sl_addr = smem_u32(sl_base);
             for (int t = t0; t < t1; ++t, ++it) {
                 const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
                 const int tl = (t - t0) & (TILE_GROUP - 1);
@@ -214,18 +240,68 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(&tempty_bar[acc]);           // the values are in registers: the accumulators are free
-                uint32_t w0 = pass_word(r0, tq[0]) & vw[0];
+                uint32_t w0 = pass_word(r0, tq[0]) & vw[0], w1 = 0, w2 = 0;
                 if (!(tq[0] == tq[0])) w0 = 0;
                 s_stage[(0 * FM + q_in) * STAGE_PITCH + tl * 2 + half] = w0;
                 if (p.L > 1) {
-                    uint32_t w1 = pass_word(r1, tq[1]) & vw[1];
+                    w1 = pass_word(r1, tq[1]) & vw[1];
                     if (!(tq[1] == tq[1])) w1 = 0;
                     s_stage[(1 * FM + q_in) * STAGE_PITCH + tl * 2 + half] = w1;
                 }
                 if (p.L > 2) {
-                    uint32_t w2 = pass_word(r2, tq[2]) & vw[2];
+                    w2 = pass_word(r2, tq[2]) & vw[2];
                     if (!(tq[2] == tq[2])) w2 = 0;
                     s_stage[(2 * FM + q_in) * STAGE_PITCH + tl * 2 + half] = w2;
+                }
+                if (lists) {
+                    // Rows that pass the level-0 and level-1 thresholds.  Entries are staged in per-thread
+                    // shared-memory slots and leave as whole 32-byte sectors (8 entries per array): storing
+                    // them one 4-byte value at a time took this kernel from 0.8 to 11.4 ms, 16-byte halves 2.7 ms
+                    // (partial-sector writes are read-modify-write in the ECC-protected L2).
+                    const uint32_t t1w = w0 & w1;
+                    if (t1w) {
+                        const uint32_t row0 = (uint32_t)t * FR + (uint32_t)half * 32u;
+                        const uint32_t pos0 = (uint32_t)seg_pos;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            // Branch-free appends: the slot of bit j follows from a prefix popcount, so the 32
+                            // blocks are independent (the first version chained them through seg_pos and a
+                            // branch per bit: 1235 instructions per thread and tile at 1.7 IPC).
+#pragma unroll
+                            for (int jj = 0; jj < 8; ++jj) {
+                                const int j = g * 8 + jj;
+                                const uint32_t bit = t1w & (1u << j);
+                                const uint32_t sl = (pos0 + (uint32_t)__popc(t1w & ((1u << j) - 1u))) & (LBUF - 1);
+                                const uint32_t addr = sl_addr + sl * (EPI_THREADS * 4);
+                                const uint32_t roww = (row0 + j) | ((w2 << (31 - j)) & 0x80000000u);
+                                asm volatile(
+                                    "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t"
+                                    "@p st.shared.u32 [%1], %2;\n\t"
+                                    "@p st.shared.u32 [%1+%5], %3;\n\t"
+                                    "@p st.shared.u32 [%1+%6], %4;\n\t}" ::"r"(bit),
+                                    "r"(addr), "r"(roww), "r"(r1[j]), "r"(r2[j]), "n"(LBUF * EPI_THREADS * 4), "n"(2 * LBUF * EPI_THREADS * 4)
+                                    : "memory");
+                            }
+                            seg_pos = (int)(pos0 + (uint32_t)__popc(g == 3 ? t1w : (t1w & ((1u << (8 * (g + 1))) - 1u))));
+                            if (seg_pos - seg_flushed >= 8) {
+                                if (seg_flushed + 8 <= p.seg_cap) {
+                                    const int f = seg_flushed & (LBUF - 1);
+#pragma unroll
+                                    for (int a = 0; a < 3; ++a) {
+                                        if (a == 2 && p.L < 3) break;
+                                        uint32_t v[8];
+#pragma unroll
+                                        for (int i = 0; i < 8; ++i) v[i] = sl_base[(a * LBUF + f + i) * EPI_THREADS];
+                                        uint32_t* dst = (a == 0 ? p.l_rows : (a == 1 ? reinterpret_cast<uint32_t*>(p.l_k1)
+                                                                                     : reinterpret_cast<uint32_t*>(p.l_k2))) +
+                                                        seg_base + seg_flushed;
+                                        st_global_256(dst, v);
+                                    }
+                                }
+                                seg_flushed += 8;
+                            }
+                        }
+                    }
                 }
                 if (tl == TILE_GROUP - 1 || t == t1 - 1) {
                     asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
@@ -241,6 +317,16 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
                     }
                     asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
                 }
+            }
+            if (lists) {
+                // tail of the segment (< 8 entries)
+                for (int e = seg_flushed; e < seg_pos && e < p.seg_cap; ++e) {
+                    const int sl = e & (LBUF - 1);
+                    p.l_rows[seg_base + e] = sl_base[(0 * LBUF + sl) * EPI_THREADS];
+                    p.l_k1[seg_base + e] = __uint_as_float(sl_base[(1 * LBUF + sl) * EPI_THREADS]);
+                    if (p.L > 2) p.l_k2[seg_base + e] = __uint_as_float(sl_base[(2 * LBUF + sl) * EPI_THREADS]);
+                }
+                p.seg_n[(int64_t)q * p.n_segs + range * 2 + half] = seg_pos;
             }
         }
     }
@@ -295,7 +381,7 @@ __global__ void __launch_bounds__(256) k_pack_rows(const PackParams p) {
 
 // tq[l][q] = x*_l * |q_l| (sequential fmaf norm, like the CUDA-core path); NaN for a zero query level
 __global__ void __launch_bounds__(256) k_query_tq(const float* __restrict__ q_idx, int Q, hq_index_layout lay, float x0, float x1, float x2,
-                                                  float* __restrict__ tq) {
+                                                  float* __restrict__ tq, float* __restrict__ nq_out) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= Q * lay.L) return;
     const int l = t / Q, q = t - l * Q;
@@ -305,6 +391,7 @@ __global__ void __launch_bounds__(256) k_query_tq(const float* __restrict__ q_id
     const float nq = sqrtf(c);
     const float xs = l == 0 ? x0 : (l == 1 ? x1 : x2);
     tq[(int64_t)l * Q + q] = nq > 0.f ? __fmul_rn(xs, nq) : __int_as_float(0x7fc00000);
+    nq_out[(int64_t)l * Q + q] = nq;
 }
 
 __global__ void __launch_bounds__(256) k_valid_bits(const float* __restrict__ rnorm, int64_t N, int L, uint32_t* __restrict__ valid,
@@ -385,13 +472,23 @@ extern "C" int hq_filter_tc_valid(const float* rnorm, int64_t N, const hq_index_
     return HQ_OK;
 }
 
-// Bit planes for a query batch.  q_packed [Q, 128] and tq [3, Q] are caller-provided scratch.
+extern "C" int hq_filter_tc_plan(int64_t N, int Q, int* n_ranges, int* tiles_per_range) {
+    HQ_REQUIRE(N > 0 && Q > 0 && n_ranges && tiles_per_range, "bad arguments");
+    FtcParams p{};
+    plan_units(N, Q, hq_cached_sm_count(), p);
+    *n_ranges = p.n_ranges;
+    *tiles_per_range = p.tiles_per_range;
+    return HQ_OK;
+}
+
+// Bit planes (and optionally candidate lists) for a query batch.  q_packed [Q, 128], tq [3, Q] and
+// nq [3, Q] are caller-provided scratch; lists may be null.
 int hq_filter_bits_tc_launch(const float* db_packed, const uint32_t* valid, int64_t valid_pitch, int64_t N,
                              const hq_index_layout* layout, const float* q_idx, int Q, const float* xstar, float* q_packed,
-                             float* tq, uint32_t* bits, int64_t bits_pitch, cudaStream_t st) {
+                             float* tq, float* nq, uint32_t* bits, int64_t bits_pitch, const HqFilterLists* lists, cudaStream_t st) {
     Segs s;
     HQ_REQUIRE(make_segs(layout, s), "index layout not supported by the tensor-core filter");
-    HQ_REQUIRE(db_packed && valid && q_idx && q_packed && tq && bits, "null pointer");
+    HQ_REQUIRE(db_packed && valid && q_idx && q_packed && tq && nq && bits, "null pointer");
     HQ_REQUIRE((reinterpret_cast<uintptr_t>(db_packed) & 15) == 0 && (reinterpret_cast<uintptr_t>(q_packed) & 15) == 0,
                "packed operands must be 16-byte aligned");
     HQ_REQUIRE(valid_pitch >= hq_filter_tc_valid_pitch(N), "valid pitch too small");
@@ -400,7 +497,7 @@ int hq_filter_bits_tc_launch(const float* db_packed, const uint32_t* valid, int6
     int rc = hq_filter_tc_pack(q_idx, nullptr, Q, layout, 1, q_packed, st);
     if (rc != HQ_OK) return rc;
     k_query_tq<<<(Q * layout->L + 255) / 256, 256, 0, st>>>(q_idx, Q, *layout, xstar[0], layout->L > 1 ? xstar[1] : 0.f,
-                                                            layout->L > 2 ? xstar[2] : 0.f, tq);
+                                                            layout->L > 2 ? xstar[2] : 0.f, tq, nq);
     HQ_LAUNCH_OK("k_query_tq");
 
     FtcParams p{};
@@ -408,12 +505,18 @@ int hq_filter_bits_tc_launch(const float* db_packed, const uint32_t* valid, int6
     for (int l = 0; l < 3; ++l) { p.seg_off[l] = s.off[l]; p.ksteps[l] = 3 * s.kp[l] / 8; }
     p.tq = tq; p.valid = valid; p.valid_pitch = valid_pitch; p.bits = bits; p.words = words; p.bits_pitch = bits_pitch;
     plan_units(N, Q, hq_cached_sm_count(), p);
+    if (lists && lists->rows) {
+        HQ_REQUIRE(lists->n_segs == 2 * p.n_ranges && lists->seg_cap > 0 && lists->k1 && lists->seg_n && (s.L < 3 || lists->k2),
+                   "candidate list geometry does not match hq_filter_tc_plan");
+        p.l_rows = lists->rows; p.l_k1 = lists->k1; p.l_k2 = lists->k2; p.seg_n = lists->seg_n; p.seg_cap = lists->seg_cap;
+        p.n_segs = lists->n_segs;
+    }
     CUtensorMap mq, mdb;
     rc = make_map_2d(&mq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, q_packed, Q, KS, KS, 32, FM);
     if (rc != HQ_OK) return rc;
     rc = make_map_2d(&mdb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, db_packed, N, KS, KS, 32, FR);
     if (rc != HQ_OK) return rc;
-    const size_t smem = 1024 + A_BYTES + F_STAGES * B_STAGE_BYTES + (3 * FM * STAGE_PITCH + 2) * sizeof(uint32_t) +
+    const size_t smem = 1024 + A_BYTES + F_STAGES * B_STAGE_BYTES + (3 * FM * STAGE_PITCH + 4 + 3 * LBUF * EPI_THREADS) * sizeof(uint32_t) +
                         (2 * F_STAGES + 6) * sizeof(uint64_t) + 16;
     static bool attr = false;
     if (!attr) {

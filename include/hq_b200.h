@@ -179,8 +179,15 @@ int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, const hq_ind
  *   hq_filter_tc_pack  : idx [N, Lsum] (+ rnorm) -> packed [N, 128] float32 operand rows
  *                        (is_query = 1: unscaled, [hi | hi | lo]; 0: scaled, [hi | lo | hi])
  *   hq_filter_tc_valid : valid [L][valid_pitch] bit r = row r has a non-zero level norm;
- *                        valid_pitch >= hq_filter_tc_valid_pitch(N) (whole 64-row tiles) */
+ *                        valid_pitch >= hq_filter_tc_valid_pitch(N) (whole 64-row tiles)
+ *   hq_filter_tc_plan  : work split of the pass for (N, Q) on the current device: n_ranges row ranges of
+ *                        tiles_per_range 64-row tiles (the candidate lists have 2 segments per range)
+ * With L >= 2 the pass also appends, per query, the rows that pass levels 0 and 1 together with their
+ * level-1 / level-2 dot products to candidate lists inside `scratch`; the ratio cuts then run as
+ * streaming selections over those lists (no index-row gathers), and the generic cascade only handles
+ * the queries that path cannot (level-0 cut binds, list overflow, heavily tied cut bin). */
 int hq_filter_tc_supported(const hq_index_layout* layout);
+int hq_filter_tc_plan(int64_t N, int Q, int* n_ranges, int* tiles_per_range);
 int64_t hq_filter_tc_valid_pitch(int64_t N);
 int hq_filter_tc_pack(const float* idx, const float* rnorm, int64_t N, const hq_index_layout* layout, int is_query,
                       float* packed, void* stream);
