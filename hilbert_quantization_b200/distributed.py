@@ -1,10 +1,15 @@
 """Row-sharded search across the GPUs of one box: local progressive top-k per shard, ONE
 all-gather of [Q, k] (score, id) pairs over NCCL, then the merge kernel.
 
-The ratio cut of the filter is applied per shard (`filter_scope="shard"`): every rank runs
-the reference's filter on its own rows, exactly what the oracle does when given the same
-shard boundaries.  Works with the gloo backend on CPU tensors for the host-logic tests
-(`merge_on_host=True`)."""
+Two scopes for the ratio cut of the filter:
+  * `filter_scope="shard"` (default, the benchmarked "single all-gather" path): every rank runs
+    the reference's filter on its own rows, exactly what the oracle does when given the same
+    shard boundaries;
+  * `filter_scope="global"`: parity with the reference's single candidate list.  Per level the
+    ranks all-reduce the candidate / pass counts, find the exact global cut score with two
+    all-reduced histograms over the float32 bit pattern (high then low 16 bits) and resolve
+    exact ties by global row id with one small all-gather (`global_ratio_cut`).
+Works with the gloo backend on CPU tensors for the host-logic tests (`merge_on_host=True`)."""
 from __future__ import annotations
 
 from typing import Optional, Tuple
@@ -62,6 +67,81 @@ def allgather_merge(local_ids: torch.Tensor, local_scores: torch.Tensor, k: int,
     return out_i, out_s
 
 
+def _all_reduce(t: torch.Tensor, op, group) -> torch.Tensor:
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=op, group=group)
+    return t
+
+
+def _all_gather_padded(t: torch.Tensor, fill, group) -> torch.Tensor:
+    """[Q, m_local] -> [Q, world * m_max] (ranks padded to the longest with `fill`)."""
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        return t
+    world = dist.get_world_size(group)
+    m = torch.tensor([t.shape[1]], dtype=torch.int64, device=t.device)
+    dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
+    m_max = int(m.item())
+    pad = torch.full((t.shape[0], m_max), fill, dtype=t.dtype, device=t.device)
+    pad[:, : t.shape[1]] = t
+    out = torch.empty((world * t.shape[0], m_max), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, pad.contiguous(), group=group)
+    return out.view(world, t.shape[0], m_max).permute(1, 0, 2).reshape(t.shape[0], world * m_max)
+
+
+def global_ratio_cut(scores: torch.Tensor, passed: torch.Tensor, n_alive_local: torch.Tensor, ratio: float,
+                     id_base: int, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The reference's ratio cut over the GLOBAL candidate list of each query (rag/search/engine.py:272-287).
+
+    scores [Q, N_local] float32 (>= 0), passed [Q, N_local] bool (alive and score >= threshold),
+    n_alive_local [Q] rows of this shard that entered the level.  Returns (keep [Q, N_local] bool,
+    n_out [Q] int64 global survivors).  keep = passed rows among the cap best of the global list
+    (score desc, ties -> lower global row id), cap = max(1, int(n_alive_global * ratio)).
+    Pure tensor code + three small collectives per level; runs on CPU tensors (gloo) or CUDA (NCCL)."""
+    Q, N = scores.shape
+    dev_ = scores.device
+    n_alive = _all_reduce(n_alive_local.to(torch.int64).clone(), dist.ReduceOp.SUM, group)
+    n_pass = _all_reduce(passed.sum(1).to(torch.int64), dist.ReduceOp.SUM, group)
+    cap = torch.clamp((n_alive.to(torch.float64) * ratio).floor().to(torch.int64), min=1)
+    need = n_pass > cap                                           # identical on every rank
+    keep = passed.clone()
+    n_out = torch.minimum(n_pass, cap)
+    if not bool(need.any()):
+        return keep, n_out
+    rows_q = torch.nonzero(need).flatten()
+    key = scores[rows_q].contiguous().view(torch.int32).to(torch.int64)       # non-negative floats: bit order == value order
+    ok = passed[rows_q]
+    capq = cap[rows_q]
+    nq = rows_q.numel()
+
+    def cut_digit(digit, valid, want, bins):
+        """largest digit d with #(valid, digit >= d) >= want; returns (d, count strictly above d)"""
+        hist = torch.zeros((nq, bins), dtype=torch.int32, device=dev_)
+        hist.scatter_add_(1, torch.where(valid, digit, torch.zeros_like(digit)), valid.to(torch.int32))
+        _all_reduce(hist, dist.ReduceOp.SUM, group)
+        from_top = hist.to(torch.int64).flip(1).cumsum(1).flip(1)                                 # #(digit >= d)
+        d = (from_top >= want[:, None]).to(torch.int64).sum(1) - 1                 # from_top is non-increasing in d
+        above = from_top.gather(1, torch.clamp(d + 1, max=bins - 1)[:, None])[:, 0]
+        above = torch.where(d + 1 < bins, above, torch.zeros_like(above))
+        return d, above
+
+    hi, lo = key >> 16, key & 0xffff
+    d1, above1 = cut_digit(hi, ok, capq, 1 << 15)
+    in1 = ok & (hi == d1[:, None])
+    d2, above2 = cut_digit(lo, in1, capq - above1, 1 << 16)
+    k_star = (d1 << 16) | d2
+    r_ties = capq - above1 - above2                                                 # ties to keep (>= 1), lowest global ids
+    tie = ok & (key == k_star[:, None])
+    gid = torch.arange(N, device=dev_, dtype=torch.int64)[None, :] + id_base
+    big = torch.iinfo(torch.int64).max
+    m_loc = int(tie.sum(1).max().item()) if nq else 0
+    tie_ids = torch.where(tie, gid.expand(nq, N), torch.full((1, 1), big, dtype=torch.int64, device=dev_)).sort(1).values[:, :max(m_loc, 1)]
+    all_ids = _all_gather_padded(tie_ids.contiguous(), big, group).sort(1).values
+    g_star = all_ids.gather(1, torch.clamp(r_ties - 1, min=0, max=all_ids.shape[1] - 1)[:, None])[:, 0]
+    keep_q = ok & ((key > k_star[:, None]) | (tie & (gid <= g_star[:, None])))
+    keep[rows_q] = keep_q
+    return keep, n_out
+
+
 class ShardedSearch:
     """One instance per rank.  `local_embeddings` are this rank's rows [start, end) of the global database."""
 
@@ -70,7 +150,7 @@ class ShardedSearch:
         self.group = group
         self.db = EmbeddingDatabase(local_embeddings, n=n, device=device, id_base=global_row_start)
 
-    def search(self, queries, k: int = 10, **kw):
+    def search(self, queries, k: int = 10, filter_scope: str = "shard", **kw):
         from .search import search_batch
-        ids, scores = search_batch(self.db, queries, k, **kw)
+        ids, scores = search_batch(self.db, queries, k, filter_scope=filter_scope, group=self.group, **kw)
         return allgather_merge(ids, scores, k, self.group)

@@ -247,6 +247,49 @@ def progressive_filter(db: EmbeddingDatabase, q_idx: torch.Tensor, q_lens: torch
     return mask
 
 
+def _unpack_bits(mask: torch.Tensor, N: int) -> torch.Tensor:
+    """[Q, words] int32 bit mask -> bool [Q, N] on the same device."""
+    sh = torch.arange(32, device=mask.device, dtype=torch.int32)
+    return ((mask.unsqueeze(-1) >> sh) & 1).to(torch.bool).reshape(mask.shape[0], -1)[:, :N]
+
+
+def _pack_bits(keep: torch.Tensor, words: int) -> torch.Tensor:
+    """bool [Q, N] -> [Q, words] int32 bit mask."""
+    Q, N = keep.shape
+    pad = torch.zeros((Q, words * 32), dtype=torch.int64, device=keep.device)
+    pad[:, :N] = keep
+    sh = torch.arange(32, device=keep.device, dtype=torch.int64)
+    w = (pad.view(Q, words, 32) << sh).sum(-1)
+    return torch.where(w >= (1 << 31), w - (1 << 32), w).to(torch.int32)
+
+
+def progressive_filter_global(db: EmbeddingDatabase, q_idx: torch.Tensor, q_lens: torch.Tensor, scores: torch.Tensor,
+                              mask: torch.Tensor, group=None, trace: Optional[FilterTrace] = None):
+    """`filter_scope="global"`: level scores and threshold tests by hq_filter_level on this shard, the ratio
+    cut over the GLOBAL candidate list of each query (distributed.global_ratio_cut)."""
+    from .distributed import global_ratio_cut
+    Qc, N, d = q_idx.shape[0], db.N, db.device
+    words = _mask_words(N)
+    with torch.cuda.device(d):
+        st = dev.stream_ptr()
+        for level in range(db.num_levels):
+            n_alive = torch.zeros(Qc, dtype=torch.int32, device=d)
+            n_pass = torch.zeros(Qc, dtype=torch.int32, device=d)
+            check(lib.hq_filter_level(dev.ptr(db.idx), dev.ptr(db.lens), N, C.byref(db.layout), level,
+                                      dev.ptr(q_idx), dev.ptr(q_lens), Qc,
+                                      dev.ptr(mask) if level > 0 else None, mask.stride(0),
+                                      rag_threshold(level), dev.ptr(scores), scores.stride(0), dev.ptr(mask),
+                                      dev.ptr(n_alive), dev.ptr(n_pass), st))
+            passed = _unpack_bits(mask[:Qc, :words], N)
+            keep, n_out = global_ratio_cut(scores[:Qc, :N], passed, n_alive, rag_ratio(level), db.id_base, group)
+            mask[:Qc, :words] = _pack_bits(keep, words)
+            if trace is not None:
+                trace.n_alive.append(n_alive)
+                trace.n_pass.append(n_pass)
+                trace.n_out.append(n_out)
+    return mask
+
+
 def progressive_filter_fast(db: EmbeddingDatabase, q_idx: torch.Tensor, mask: torch.Tensor,
                             trace: Optional[FilterTrace] = None, tensor_cores: bool = True):
     """All filter levels for a query batch through hq_filter_fast (no score matrix).  With
@@ -288,11 +331,13 @@ def prepare_queries(db: EmbeddingDatabase, queries) -> Tuple[torch.Tensor, torch
 
 def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: bool = True,
                  work_bytes: int = 4 << 30, return_mask: bool = False, trace: Optional[FilterTrace] = None,
-                 rerank: str = "auto", filter_impl: str = "auto"):
+                 rerank: str = "auto", filter_impl: str = "auto", filter_scope: str = "shard", group=None):
     """Progressive top-k of a batch of query embeddings against one shard.
 
     Returns (ids int64 [Q, k] (-1 = fewer than k survivors), scores float32 [Q, k]).  Scores are
-    (cos + 1) / 2 of the full embeddings; ties resolve to the lower row id."""
+    (cos + 1) / 2 of the full embeddings; ties resolve to the lower row id.
+    `filter_scope="global"` (row-sharded databases): the ratio cut of every filter level ranks the
+    candidates of ALL shards of `group` together, like the reference's single list."""
     tok = _phase("query_index")
     q, q_idx, q_lens, q_norms = prepare_queries(db, queries)
     _end(tok)
@@ -317,6 +362,10 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
     words = _mask_words(N)
     if filter_impl not in ("auto", "fast", "fast_fp32", "exact"):
         raise ValueError("filter_impl must be 'auto', 'fast', 'fast_fp32' or 'exact'")
+    if filter_scope not in ("shard", "global"):
+        raise ValueError("filter_scope must be 'shard' or 'global'")
+    if filter_scope == "global":
+        filter_impl = "exact"                      # the global cut works on the per-level score matrix
     fast = False
     if use_filter and filter_impl != "exact":
         fast = db.fast_filter_ok and bool((q_lens == db._keff).all().item())
@@ -338,6 +387,8 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
                 tok = _phase("filter")
                 if fast:
                     m = progressive_filter_fast(db, q_idx[s:e], mask[:nq], trace, tensor_cores=filter_impl != "fast_fp32")
+                elif filter_scope == "global":
+                    m = progressive_filter_global(db, q_idx[s:e], q_lens[s:e], scores[:nq], mask[:nq], group, trace)
                 else:
                     m = progressive_filter(db, q_idx[s:e], q_lens[s:e], scores[:nq], mask[:nq], trace)
                 _end(tok)

@@ -165,3 +165,45 @@ def test_two_rank_merge_over_gloo(tmp_path):
                               stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+
+
+_WORKER_GLOBAL_CUT = r'''
+import sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from hilbert_quantization_b200.distributed import global_ratio_cut, shard_bounds
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{sys.argv[2]}", rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+rng = np.random.default_rng(7)
+Q, N = 9, 1000
+scores = rng.random((Q, N)).astype(np.float32)
+scores[:, 700] = scores[:, 3]; scores[:, 701] = scores[:, 3]; scores[:, 40] = scores[:, 3]     # exact ties across shards
+scores[4] = np.float32(0.75)                                                                    # one query: everything tied
+alive = rng.random((Q, N)) < 0.8
+thr, ratio = 0.35, 0.3
+passed = alive & (scores >= thr)
+passed[7] = False; passed[7, 5] = True                                                           # fewer passes than the cap
+lo, hi = shard_bounds(N, 2, rank)
+keep, n_out = global_ratio_cut(torch.from_numpy(scores[:, lo:hi].copy()), torch.from_numpy(passed[:, lo:hi].copy()),
+                               torch.from_numpy(alive[:, lo:hi].sum(1)), ratio, lo)
+for q in range(Q):
+    cap = max(1, int(alive[q].sum() * ratio))
+    ids = np.nonzero(passed[q])[0]
+    order = ids[np.lexsort((ids, -scores[q, ids]))][:cap]             # score desc, ties -> lower global id
+    want = np.zeros(N, bool); want[order] = True
+    assert np.array_equal(keep[q].numpy(), want[lo:hi]), (rank, q)
+    assert int(n_out[q]) == len(order), (rank, q, int(n_out[q]), len(order))
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_two_rank_global_ratio_cut_over_gloo(tmp_path):
+    """filter_scope="global": the distributed exact selection equals the single-list cut (SURVEY 8e-i)."""
+    script = tmp_path / "worker_cut.py"
+    script.write_text(_WORKER_GLOBAL_CUT)
+    port = str(31500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)

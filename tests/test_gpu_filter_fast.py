@@ -65,3 +65,20 @@ def test_fast_filter_falls_back_on_sparse_rows(hq):
         hq.search_batch(d, db[:3], 5, filter_impl="fast")
     ids, _ = hq.search_batch(d, db[:3], 5)   # auto -> exact path
     assert ids.shape == (3, 5)
+
+
+@pytest.mark.parametrize("N,D,Q,positive", [(3000, 1536, 12, False), (4097, 768, 9, True)])
+def test_global_scope_equals_exact_filter_on_one_shard(hq, N, D, Q, positive):
+    """filter_scope="global" with a single shard is the reference's single list: same survivors, ids and
+    scores as the exact per-level path (the distributed selection itself is covered over gloo on CPU)."""
+    from hilbert_quantization_b200.search import FilterTrace, unpack_mask
+    rng = np.random.default_rng(N + Q)
+    db, qs = _data(rng, N, D, Q, positive)
+    d = hq.EmbeddingDatabase(db)
+    tg, te = FilterTrace([], [], []), FilterTrace([], [], [])
+    i_g, s_g, m_g = hq.search_batch(d, qs, 10, return_mask=True, filter_scope="global", trace=tg)
+    i_e, s_e, m_e = hq.search_batch(d, qs, 10, return_mask=True, filter_impl="exact", trace=te)
+    assert np.array_equal(unpack_mask(m_g, N), unpack_mask(m_e, N))
+    assert torch.equal(i_g, i_e) and torch.equal(s_g, s_e)
+    for l in range(len(te.n_out)):
+        assert torch.equal(tg.n_out[l].to(torch.int64), te.n_out[l].to(torch.int64))
