@@ -445,6 +445,51 @@ def cosine01(a, b, device=None) -> float:
     return float(out.item())
 
 
+def granularity_weights(num_levels: int) -> np.ndarray:
+    """rag/search/engine.py:1101-1138: 8^(L-i-1), normalised, first level doubled, renormalised."""
+    if num_levels <= 0:
+        return np.array([])
+    if num_levels == 1:
+        return np.array([1.0])
+    w = np.array([8.0 ** (num_levels - i - 1) for i in range(num_levels)])
+    w = w / w.sum()
+    w[0] *= 2.0
+    return w / w.sum()
+
+
+def comprehensive_scores(frames, query_frames, original_height: Optional[int] = None, cand_ids=None, device=None) -> torch.Tensor:
+    """Comprehensive similarity (0.5 hierarchical + 0.3 cosine + 0.2 spatial locality,
+    rag/search/engine.py:516-575) of Q query frames against enhanced frames [N, H + L, W] on the device.
+    `cand_ids` [Q, M] (int64, -1 = none) restricts every query to a shortlist.  Returns float32 [Q, M or N]."""
+    d = dev.require_cuda(device if device is not None else (frames.device if isinstance(frames, torch.Tensor) and frames.is_cuda else None))
+    f = dev.f32_device(frames, d)
+    qf = dev.f32_device(query_frames, d)
+    if qf.dim() == 2:
+        qf = qf.unsqueeze(0)
+    if f.dim() != 3 or qf.dim() != 3 or f.shape[1:] != qf.shape[1:]:
+        raise ValueError("frames must be [N, H + L, W] and query frames [Q, H + L, W] of the same frame shape")
+    N, rows, W = f.shape
+    H = int(original_height) if original_height is not None else rows - len(plans.c_levels(W))
+    if H != W:
+        raise NotImplementedError("comprehensive similarity is implemented for square grids (original_height == width)")
+    L = rows - H
+    Q = qf.shape[0]
+    ids = None
+    M = N
+    if cand_ids is not None:
+        ids = cand_ids.to(device=d, dtype=torch.int64).contiguous() if isinstance(cand_ids, torch.Tensor) else \
+            torch.from_numpy(np.ascontiguousarray(cand_ids, dtype=np.int64)).to(d)
+        if ids.dim() != 2 or ids.shape[0] != Q:
+            raise ValueError("cand_ids must be [Q, M]")
+        M = ids.shape[1]
+    out = torch.empty((Q, M), dtype=torch.float32, device=d)
+    w = (C.c_float * 8)(*([float(x) for x in granularity_weights(L)] + [0.0] * (8 - L)))
+    with torch.cuda.device(d):
+        check(lib.hq_comprehensive_scores(dev.ptr(f), N, W, L, rows * W, dev.ptr(qf), Q, rows * W, C.cast(w, C.c_void_p),
+                                          dev.ptr(ids), M, dev.ptr(out), dev.stream_ptr()))
+    return out
+
+
 # ------------------------------------------------------------------------------------------
 # RAG engine surface
 # ------------------------------------------------------------------------------------------
@@ -535,6 +580,28 @@ class RAGSearchEngineImpl:
         if embedding1.size == 0 or embedding2.size == 0:
             return 0.0
         return cosine01(embedding1, embedding2, self._device)
+
+    def _get_similarity_weights(self) -> Dict[str, float]:
+        """rag/search/engine.py:716-727"""
+        return {"hierarchical": 0.5, "embedding": 0.3, "spatial": 0.2}
+
+    def _calculate_comprehensive_similarity(self, query_embedding: np.ndarray, query_indices, candidate_frame: np.ndarray,
+                                            frame_number: int = 0) -> float:
+        """rag/search/engine.py:516-575 for one pair (index rows read explicitly, see the class docstring)."""
+        return float(comprehensive_scores(np.asarray(candidate_frame, dtype=np.float32)[None], np.asarray(query_embedding, dtype=np.float32),
+                                          self._split(query_embedding)[0], device=self._device)[0, 0].item())
+
+    def calculate_embedding_similarity(self, query_embedding: np.ndarray, cached_frames: Dict[int, np.ndarray]) -> List[Tuple[int, float]]:
+        """rag/search/engine.py:478-514: comprehensive similarity of every cached frame, sorted descending
+        (stable: ties keep the dictionary order)."""
+        if query_embedding.size == 0 or not cached_frames:
+            return []
+        keys = list(cached_frames.keys())
+        frames = np.stack([np.asarray(cached_frames[k], dtype=np.float32) for k in keys])
+        sc = comprehensive_scores(frames, np.asarray(query_embedding, dtype=np.float32), self._split(query_embedding)[0],
+                                  device=self._device)[0].cpu().numpy()
+        order = np.argsort(-sc, kind="stable")
+        return [(keys[i], float(sc[i])) for i in order]
 
     def compare_hierarchical_indices(self, query_indices: np.ndarray, candidate_indices: np.ndarray) -> float:
         """rag/search/engine.py:994-1023 (+ multi-level weights :1053-1138)."""

@@ -230,6 +230,18 @@ int hq_rerank_topk_bf16(const void* db_bf16, int64_t db_pitch, const float* db_f
                         int k, int64_t id_base, int64_t* ids, float* scores,
                         void* scratch, int64_t scratch_bytes, void* stream);
 
+/* ---- a14: comprehensive similarity blend -----------------------------------
+ * rag/search/engine.py:516-575 (_calculate_comprehensive_similarity):
+ *   0.5 * weighted per-level (cos+1)/2 of the index rows (:994-1099; weights :1101-1138, passed in)
+ * + 0.3 * (cos+1)/2 of the grids (:622-660)
+ * + 0.2 * mean (cos+1)/2 over ws x ws grid windows at stride ws/2, ws = min(4, n/4) (:662-714)
+ * frames / q_frames: enhanced frames, rows [0, n) = n x n grid, rows [n, n+L) = index rows.
+ * cand_ids: optional device [Q, M] row ids per query (-1 = none -> score -1); NULL = every row (M == N).
+ * weights_host: HOST array [L].  out [Q, M] float32. */
+int hq_comprehensive_scores(const float* frames, int64_t N, int n, int L, int64_t frame_stride,
+                            const float* q_frames, int Q, int64_t q_stride, const float* weights_host,
+                            const int64_t* cand_ids, int64_t M, float* out, void* stream);
+
 /* ---- a15 multi-GPU: merge of per-shard top-k ---------------------------
  * in_ids/in_scores [P, Q, k] (all-gathered) -> out [Q, k]; ties -> lower id;
  * entries with id < 0 are empty. */

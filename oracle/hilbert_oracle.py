@@ -677,6 +677,72 @@ def progressive_search(query: np.ndarray, db: np.ndarray, n: int, k: int,
 
 
 # ----------------------------------------------------------------------------
+# a14  comprehensive similarity blend        rag/search/engine.py:516-575, :662-727, :1053-1138
+# ----------------------------------------------------------------------------
+
+def granularity_weights(num_levels: int) -> np.ndarray:
+    """8^(L-i-1), normalised, first level doubled, renormalised.  rag/search/engine.py:1101-1138."""
+    if num_levels <= 0:
+        return np.array([])
+    if num_levels == 1:
+        return np.array([1.0])
+    w = np.array([8.0 ** (num_levels - i - 1) for i in range(num_levels)])
+    w = w / w.sum()
+    w[0] *= 2.0
+    return w / w.sum()
+
+
+def _cos01_rows(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """(cos + 1)/2 along the last axis, 0 where a norm is 0 (float64 accumulate)."""
+    a64, b64 = a.astype(np.float64), b.astype(np.float64)
+    dot = (a64 * b64).sum(-1)
+    na, nb = np.sqrt((a64 * a64).sum(-1)), np.sqrt((b64 * b64).sum(-1))
+    ok = (na > 0) & (nb > 0)
+    return np.where(ok, (dot / np.where(ok, na * nb, 1.0) + 1.0) / 2.0, 0.0)
+
+
+def spatial_locality_similarity(q_grid: np.ndarray, c_grids: np.ndarray) -> np.ndarray:
+    """Mean of (cos + 1)/2 over ws x ws windows at stride ws // 2, ws = min(4, H // 4, W // 4); plain
+    cosine of the grids when ws < 2.  q_grid [H, W], c_grids [N, H, W].  rag/search/engine.py:662-714."""
+    N, H, W = c_grids.shape
+    ws = min(4, H // 4, W // 4)
+    if ws < 2:
+        return _cos01_rows(np.broadcast_to(q_grid.reshape(1, -1), (N, H * W)), c_grids.reshape(N, -1))
+    step = ws // 2
+    acc = np.zeros(N)
+    count = 0
+    for i in range(0, H - ws + 1, step):
+        for j in range(0, W - ws + 1, step):
+            qw = q_grid[i:i + ws, j:j + ws].reshape(1, -1)
+            cw = c_grids[:, i:i + ws, j:j + ws].reshape(N, -1)
+            acc += _cos01_rows(np.broadcast_to(qw, cw.shape), cw)
+            count += 1
+    return acc / count if count else np.zeros(N)
+
+
+def comprehensive_similarity(q_frame: np.ndarray, c_frames: np.ndarray, original_height: int) -> np.ndarray:
+    """0.5 * hierarchical + 0.3 * embedding cosine + 0.2 * spatial locality for one query frame against N
+    candidate frames (enhanced frames: rows [0, H) = grid, rows [H, H + L) = index rows, read explicitly as
+    in SURVEY 8c).  Index rows that are all zero in the query or a candidate are NOT dropped here (the
+    reference's own extractor drops them and thereby shifts the later levels; dense data never hits that).
+    rag/search/engine.py:516-575 (+ :994-1099 for the hierarchical part, weights :1101-1138)."""
+    H = original_height
+    N = c_frames.shape[0]
+    L = q_frame.shape[0] - H
+    if L > 0:
+        w = granularity_weights(L)
+        hier = np.zeros(N)
+        for l in range(L):
+            hier += w[l] * _cos01_rows(np.broadcast_to(q_frame[H + l][None, :], (N, q_frame.shape[1])), c_frames[:, H + l, :])
+        hier /= w.sum()
+    else:
+        hier = np.zeros(N)
+    emb = _cos01_rows(np.broadcast_to(q_frame[:H].reshape(1, -1), (N, H * q_frame.shape[1])), c_frames[:, :H].reshape(N, -1))
+    spatial = spatial_locality_similarity(q_frame[:H], c_frames[:, :H])
+    return 0.5 * hier + 0.3 * emb + 0.2 * spatial
+
+
+# ----------------------------------------------------------------------------
 # a11  core progressive search               core/search_engine.py:42-388
 # ----------------------------------------------------------------------------
 

@@ -428,3 +428,38 @@ def test_readme_surface(hq):
     rag.add_document("b", "completely different words about cooking pasta")
     out = rag.search("locality of hilbert curves", max_results=2)
     assert out and out[0].document_id == "a" and out[0].content.startswith("hilbert")
+
+
+# ---------------------------------------------------------------------------------------
+# a14 comprehensive similarity blend (rag/search/engine.py:516-575)
+# ---------------------------------------------------------------------------------------
+def test_comprehensive_blend_golden_and_oracle(hq):
+    g = load_golden("rag_blend.npz")
+    for tag in ("n64_D1536", "n32_D768", "n16_D200", "n64_D4096"):
+        qf, cfs = g[f"{tag}_query_frame"], g[f"{tag}_cand_frames"]
+        got = hq.comprehensive_scores(cfs, qf).cpu().numpy()[0]
+        assert np.abs(got - g[f"{tag}_comprehensive"]).max() < 2e-6          # fp32 sums vs the reference's NumPy
+        assert np.abs(got - O.comprehensive_similarity(qf, cfs, qf.shape[1])).max() < 2e-6
+        eng = hq.RAGSearchEngineImpl()
+        ranked = eng.calculate_embedding_similarity(qf, {i: c for i, c in enumerate(cfs)})
+        assert [r[0] for r in ranked[:5]] == list(g[f"{tag}_ranked_ids"][:5])
+        assert abs(eng._calculate_comprehensive_similarity(qf, None, cfs[3]) - g[f"{tag}_comprehensive"][3]) < 2e-6
+
+
+def test_comprehensive_blend_batch_and_shortlist(hq):
+    rng = np.random.default_rng(11)
+    N, D, Q, n = 300, 1536, 5, 64
+    db = rng.standard_normal((N, D)).astype(np.float32)
+    qs = rng.standard_normal((Q, D)).astype(np.float32)
+    frames, _ = hq.map_and_index(torch.from_numpy(db).cuda(), n, variant="C", enhanced=True)
+    qframes, _ = hq.map_and_index(torch.from_numpy(qs).cuda(), n, variant="C", enhanced=True)
+    full = hq.comprehensive_scores(frames, qframes).cpu().numpy()
+    fr, qfr = frames.cpu().numpy(), qframes.cpu().numpy()
+    for j in range(Q):
+        assert np.abs(full[j] - O.comprehensive_similarity(qfr[j], fr, n)).max() < 2e-6
+    ids = rng.integers(0, N, size=(Q, 7))
+    ids[2, 4] = -1
+    short = hq.comprehensive_scores(frames, qframes, cand_ids=ids).cpu().numpy()
+    for j in range(Q):
+        for m in range(7):
+            assert short[j, m] == (-1.0 if ids[j, m] < 0 else full[j, ids[j, m]])

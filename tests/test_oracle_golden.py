@@ -135,3 +135,16 @@ def test_filter_constants():
     assert O.c_granularity_levels(32) == [4, 2] and O.c_granularity_levels(64) == [8, 4, 2]
     assert O.c_granularity_levels(4096) == [64, 32, 16, 8, 4, 2]
     assert O.a_level_allocation(64) == [(8, 32), (4, 8), (2, 3), (1, 1), (8, 20)]
+
+
+def test_oracle_comprehensive_blend_matches_reference_golden():
+    """a14: oracle restatement of rag/search/engine.py:516-575 against outputs of the reference itself."""
+    g = load_golden("rag_blend.npz")
+    for tag in ("n64_D1536", "n32_D768", "n16_D200", "n64_D4096"):
+        qf, cfs = g[f"{tag}_query_frame"], g[f"{tag}_cand_frames"]
+        H = qf.shape[1]
+        got = O.comprehensive_similarity(qf, cfs, H)
+        assert np.abs(got - g[f"{tag}_comprehensive"]).max() < 2e-7
+        assert np.abs(O.spatial_locality_similarity(qf[:H], cfs[:, :H]) - g[f"{tag}_spatial"]).max() < 2e-7
+        order = np.argsort(-got, kind="stable")
+        assert list(order[:5]) == list(g[f"{tag}_ranked_ids"][:5])
