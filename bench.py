@@ -39,7 +39,7 @@ UNIT = "queries/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=1_000_000)
@@ -50,6 +50,16 @@ def parse():
     ap.add_argument("--cpu-sample-rows", type=int, default=40000)
     ap.add_argument("--cpu-sample-queries", type=int, default=16)
     return ap.parse_args()
+
+
+def ncu_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture of this benchmark
+    (profiles/r01_traffic.json, written by tools/ncu_summary.py --traffic); None when absent."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        return json.load(open(path)).get(kernel)
+    except Exception:
+        return None
 
 
 def peaks():
@@ -367,7 +377,8 @@ def main():
                        "rows_per_gpu": rows, "sharding": f"row-sharded x{world}, one NCCL all-gather of [Q,k]" if world > 1 else "single shard",
                        "l2": "database (6.1 GB) and score matrix (4.1 GB) exceed the 126 MB L2, no flush needed",
                        "rerank": "tcgen05 bf16 contraction + fused mask/top-16 epilogue, exact fp32 re-score of the shortlist",
-                       "filter": "bit-plane threshold pass + per-query cascade (exact radix select where the ratio cut binds)",
+                       "filter": "tcgen05 tf32 (hi/lo split) threshold pass emitting bit planes + candidate lists, streaming list "
+                                 "cascade with exact selection at the ratio cuts (generic gather cascade as per-query fallback)",
                        "filter_scope": "shard"},
             "p50_ms": float(np.median(per_step)), "p99_ms": float(np.percentile(per_step, 99)),
             "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": int(q_pinned.numel() * 4),
@@ -376,13 +387,18 @@ def main():
             "phases_ms_per_step": {k: v / args.steps for k, v in phases.items()},
             "roofline": {"kernel": "k_rerank_tc<16> + k_rerank_tc_merge<16> (Q x N x D cosine contraction, bf16 tcgen05)", "bound": "tensor",
                          "achieved": achieved_tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                         "frac": (achieved_tf / pk["bf16_tflops"]) if achieved_tf else None, "traffic": None,
-                         "peak_source": pk["source"] + " (sustained bf16)"},
+                         "frac": (achieved_tf / pk["bf16_tflops"]) if achieved_tf else None,
+                         "traffic": ncu_traffic("k_rerank_tc") if world == 1 and args.rows == 1_000_000 else None,
+                         "peak_source": pk["source"] + " (sustained bf16)",
+                         "note": "largest single kernel of the step; the coarse filter (tcgen05 tf32 threshold pass + list "
+                                 "cascade) is issue bound, see DESIGN.md section 5 and profiles/"},
             "map_index": {"value": map_index_gbs, "unit": "GB/s", "bytes_per_embedding": bytes_per_row,
                           "ms_per_pass": mi_t.item(), "launches_per_pass": launches_per_pass,
                           "roofline": {"kernel": "k_item_pass_bulk<0,6> (fused map_to_2d + index pyramid, bulk-copy loads and stores)", "bound": "hbm",
                                        "achieved": mi_kernel_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                                       "frac": mi_kernel_gbs / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"]}},
+                                       "frac": mi_kernel_gbs / pk["hbm_gbs"],
+                                       "traffic": ncu_traffic("k_item_pass_bulk") if chunk == 262144 else None,
+                                       "peak_source": pk["source"]}},
             "clocks": clocks.summary(),
             "top1_hit_rate_perturbed": float((ids[: args.queries // 2, 0].cpu().numpy() == np.arange(args.queries // 2)).mean())
             if lo == 0 else None,

@@ -581,6 +581,64 @@ __device__ __forceinline__ void rank_cut_bin(const float* b_key, const uint32_t*
     __syncthreads();
 }
 
+// Exact boundary of "drop the `drop` lowest (key asc, row desc) candidates": 2048-bin linear histogram over
+// [lo, hi), then either an exact ranking of the cut bin in shared memory (<= kCutCap members) or a refinement
+// of that bin into 2048 sub-bins (large shards put thousands of candidates into one bin).  `for_each(visit)`
+// must call visit(key, token) for every candidate of the calling thread, `row_of(token)` returns its row id.
+// Returns false when three rounds cannot isolate the boundary (heavily tied keys): the caller falls back.
+struct BinStack { float lo[3], scale[3]; uint32_t cb[3]; int depth; };
+__device__ __forceinline__ bool in_bins(const BinStack& s, float k) {
+    bool ok = true;
+    for (int d = 0; d < s.depth; ++d) ok = ok && lin_bin(k, s.lo[d], s.scale[d]) == s.cb[d];
+    return ok;
+}
+
+template <class ForEach, class RowOf>
+__device__ __forceinline__ bool select_boundary(ForEach for_each, RowOf row_of, uint32_t drop, float lo, float hi, bool have_hist0,
+                                                uint32_t* hist, uint32_t* sh, float* b_key, uint32_t* b_row, uint32_t* s_bufn,
+                                                float* s_K, uint32_t* s_R, Boundary& out) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    BinStack st;
+    st.depth = 0;
+    float cur_lo = lo, cur_hi = hi;
+    for (int round = 0; round < 3; ++round) {
+        const float scale = cur_hi > cur_lo ? 2048.0f / (cur_hi - cur_lo) : 0.f;
+        if (!(round == 0 && have_hist0)) {
+            __syncthreads();
+            for (int i = tid; i < 2048; i += nt) hist[i] = 0;
+            __syncthreads();
+            for_each([&](float k, uint32_t) {
+                if (in_bins(st, k)) atomicAdd(&hist[lin_bin(k, cur_lo, scale)], 1u);
+            });
+            __syncthreads();
+        }
+        find_cut_bin(hist, drop, sh);
+        const uint32_t cb = sh[0], r_in_bin = sh[1], n_in_bin = sh[2];
+        st.lo[st.depth] = cur_lo; st.scale[st.depth] = scale; st.cb[st.depth] = cb;
+        ++st.depth;
+        if (n_in_bin <= (uint32_t)kCutCap) {
+            if (tid == 0) *s_bufn = 0;
+            __syncthreads();
+            for_each([&](float k, uint32_t tok) {
+                if (in_bins(st, k)) {
+                    const uint32_t slot = atomicAdd(s_bufn, 1u);
+                    b_key[slot] = k; b_row[slot] = row_of(tok);
+                }
+            });
+            __syncthreads();
+            rank_cut_bin(b_key, b_row, *s_bufn, r_in_bin, s_K, s_R);
+            out.K = *s_K; out.R = *s_R;
+            return true;
+        }
+        drop = r_in_bin;                                   // rank inside the cut bin
+        const float w = (cur_hi - cur_lo) * (1.0f / 2048.0f);
+        cur_lo = cur_lo + w * (float)cb;
+        cur_hi = cur_lo + w;
+        if (!(cur_hi > cur_lo)) return false;
+    }
+    return false;
+}
+
 // warp-aggregated append position in a block-wide compact list (count kept in shared memory)
 __device__ __forceinline__ uint32_t compact_slot(bool take, uint32_t* s_count) {
     const uint32_t m = __ballot_sync(0xffffffffu, take);
@@ -645,54 +703,26 @@ __global__ void __launch_bounds__(kListThreads, 1) k_filter_cascade_lists(const 
         Boundary b1;
         b1.K = -INFINITY; b1.R = 0;
         bool failed = false;
-        if ((int64_t)n1 > cap1) {
-            const uint32_t drop = n1 - (uint32_t)cap1;
-            const float lo = __ldg(p.tq + (int64_t)1 * p.Q + q), hi = __ldg(p.nq + (int64_t)1 * p.Q + q);
-            const float scale = hi > lo ? 2048.0f / (hi - lo) : 0.f;
-            for (int i = tid; i < 2048; i += nt) hist[i] = 0;
-            __syncthreads();
-            // one batch of kU independent loads per thread and segment (segments hold a few thousand entries)
-            for (int item = warp; item < 2 * p.n_segs; item += nw) {       // a warp owns half a segment at a time
+        // every candidate of the query: a warp owns half a segment at a time, kU independent loads per lane
+        auto each_l1 = [&](auto visit) {
+            for (int item = warp; item < 2 * p.n_segs; item += nw) {
                 const uint32_t cnt = (uint32_t)s_cnt[item >> 1], mid = min(cnt, ((cnt >> 1) + 31u) & ~31u);
                 const uint32_t lo_e = (item & 1) ? mid : 0u, n = (item & 1) ? cnt : mid;
                 const uint32_t off = (uint32_t)(item >> 1) * (uint32_t)p.seg_cap;
-                for (uint32_t e0 = lo_e + lane; e0 - lane < n; e0 += kU * 32) {      // warp-uniform trip count
-
+                for (uint32_t e0 = lo_e + lane; e0 - lane < n; e0 += kU * 32) {
                     float k[kU];
 #pragma unroll
                     for (int u = 0; u < kU; ++u) k[u] = e0 + u * 32 < n ? __ldg(L_k1 + off + e0 + u * 32) : -1.0f;
 #pragma unroll
                     for (int u = 0; u < kU; ++u)
-                        if (e0 + u * 32 < n) atomicAdd(&hist[lin_bin(k[u], lo, scale)], 1u);
+                        if (e0 + u * 32 < n) visit(k[u], off + e0 + u * 32);
                 }
             }
-            __syncthreads();
-            find_cut_bin(hist, drop, sh);
-            const uint32_t cb = sh[0], r_in_bin = sh[1], n_in_bin = sh[2];
-            if (n_in_bin > (uint32_t)kCutCap) failed = true;
-            else {
-                for (int item = warp; item < 2 * p.n_segs; item += nw) {       // a warp owns half a segment at a time
-                    const uint32_t cnt = (uint32_t)s_cnt[item >> 1], mid = min(cnt, ((cnt >> 1) + 31u) & ~31u);
-                    const uint32_t lo_e = (item & 1) ? mid : 0u, n = (item & 1) ? cnt : mid;
-                    const uint32_t off = (uint32_t)(item >> 1) * (uint32_t)p.seg_cap;
-                    for (uint32_t e0 = lo_e + lane; e0 - lane < n; e0 += kU * 32) {      // warp-uniform trip count
-
-                        float k[kU];
-#pragma unroll
-                        for (int u = 0; u < kU; ++u) k[u] = e0 + u * 32 < n ? __ldg(L_k1 + off + e0 + u * 32) : -1.0f;
-#pragma unroll
-                        for (int u = 0; u < kU; ++u) {
-                            if (e0 + u * 32 < n && lin_bin(k[u], lo, scale) == cb) {
-                                const uint32_t slot = atomicAdd(&s_bufn, 1u);
-                                b_key[slot] = k[u]; b_row[slot] = __ldg(L_rows + off + e0 + u * 32) & 0x7fffffffu;
-                            }
-                        }
-                    }
-                }
-                __syncthreads();
-                rank_cut_bin(b_key, b_row, s_bufn, r_in_bin, &s_K, &s_R);
-                b1.K = s_K; b1.R = s_R;
-            }
+        };
+        if ((int64_t)n1 > cap1) {
+            const float lo = __ldg(p.tq + (int64_t)1 * p.Q + q), hi = __ldg(p.nq + (int64_t)1 * p.Q + q);
+            failed = !select_boundary(each_l1, [&](uint32_t tok) { return __ldg(L_rows + tok) & 0x7fffffffu; }, n1 - (uint32_t)cap1, lo, hi,
+                                      false, hist, sh, b_key, b_row, &s_bufn, &s_K, &s_R, b1);
         }
         if (failed) {
             if (tid == 0) p.fallback[q] = 1;
@@ -779,27 +809,19 @@ __global__ void __launch_bounds__(kListThreads, 1) k_filter_cascade_lists(const 
         Boundary b2;
         b2.K = -INFINITY; b2.R = 0;
         if ((int64_t)n2 > cap2) {
-            const uint32_t drop = n2 - (uint32_t)cap2;
-            find_cut_bin(hist, drop, sh);
-            const uint32_t cb = sh[0], r_in_bin = sh[1], n_in_bin = sh[2];
-            if (n_in_bin > (uint32_t)kCutCap) failed = true;
-            else {
+            auto each_l2 = [&](auto visit) {
                 for (uint32_t e0 = tid; e0 < n2; e0 += kU * nt) {
                     float k[kU];
 #pragma unroll
                     for (int u = 0; u < kU; ++u) k[u] = e0 + u * nt < n2 ? __ldcg(c_k2 + e0 + u * nt) : -1.0f;
 #pragma unroll
-                    for (int u = 0; u < kU; ++u) {
-                        if (e0 + u * nt < n2 && lin_bin(k[u], lo2, scale2) == cb) {
-                            const uint32_t slot = atomicAdd(&s_bufn, 1u);
-                            b_key[slot] = k[u]; b_row[slot] = __ldcg(c_row + e0 + u * nt);
-                        }
-                    }
+                    for (int u = 0; u < kU; ++u)
+                        if (e0 + u * nt < n2) visit(k[u], e0 + u * nt);
                 }
-                __syncthreads();
-                rank_cut_bin(b_key, b_row, s_bufn, r_in_bin, &s_K, &s_R);
-                b2.K = s_K; b2.R = s_R;
-            }
+            };
+            // round 0 reuses the histogram accumulated while compacting
+            failed = !select_boundary(each_l2, [&](uint32_t tok) { return __ldcg(c_row + tok); }, n2 - (uint32_t)cap2, lo2, hi2, true, hist,
+                                      sh, b_key, b_row, &s_bufn, &s_K, &s_R, b2);
         }
         if (failed) {
             if (tid == 0) p.fallback[q] = 1;

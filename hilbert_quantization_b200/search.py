@@ -331,7 +331,8 @@ def prepare_queries(db: EmbeddingDatabase, queries) -> Tuple[torch.Tensor, torch
 
 def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: bool = True,
                  work_bytes: int = 4 << 30, return_mask: bool = False, trace: Optional[FilterTrace] = None,
-                 rerank: str = "auto", filter_impl: str = "auto", filter_scope: str = "shard", group=None):
+                 rerank: str = "auto", filter_impl: str = "auto", filter_scope: str = "shard", group=None,
+                 filter_scratch_bytes: int = 24 << 30):
     """Progressive top-k of a batch of query embeddings against one shard.
 
     Returns (ids int64 [Q, k] (-1 = fewer than k survivors), scores float32 [Q, k]).  Scores are
@@ -374,6 +375,12 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
     if fast or not use_filter:
         work_bytes = max(work_bytes, 4 * N * Q) if rerank == "bf16" else work_bytes
     qc = int(max(1, min(Q, work_bytes // (4 * N)))) if not (rerank == "bf16" and (fast or not use_filter)) else Q
+    if fast and use_filter:
+        # the fast filter keeps bit planes and candidate lists for the whole query chunk in scratch: bound it
+        # (C5: 12.5 M rows x 4096 queries would ask for > 100 GB) by searching the batch in 128-query multiples
+        budget = max(int(filter_scratch_bytes), 1 << 28)
+        while qc > 128 and int(lib.hq_filter_fast_scratch_bytes(N, qc, C.byref(db.layout))) > budget:
+            qc = max(128, (qc // 2 + 127) // 128 * 128)
     need_scores = not (rerank == "bf16" and (fast or not use_filter))
     scores = torch.empty((qc, N), dtype=torch.float32, device=d) if need_scores else None
     mask = torch.zeros((qc, words), dtype=torch.int32, device=d)

@@ -53,5 +53,31 @@ def main(path):
             print(f"    stall {k:72s} {v:16.3f}")
 
 
+def traffic(paths):
+    """--traffic rep...: {kernel base name: DRAM read+write bytes of its LAST profiled launch} as JSON."""
+    import json
+    import re
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    out = {}
+    for path in paths:
+        txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(txt.splitlines()))
+        start = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+        hdr, units = rows[start], rows[start + 1]
+        for r in rows[start + 2:]:
+            d = dict(zip(hdr, r))
+            m = re.search(r"(k_[a-z0-9_]+)", d["Kernel Name"])
+            if not m:
+                continue
+            tot = 0.0
+            for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(d[k]) * scale[units[hdr.index(k)]]
+            out[m.group(1)] = int(tot)
+    print(json.dumps(out, indent=1, sort_keys=True))
+
+
 if __name__ == "__main__":
-    main(sys.argv[1])
+    if sys.argv[1] == "--traffic":
+        traffic(sys.argv[2:])
+    else:
+        main(sys.argv[1])
