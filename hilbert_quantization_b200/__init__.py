@@ -11,6 +11,7 @@ from .quantize import FrameQuantizer, dequantize_u8_batch, quantize_u8_batch  # 
 from .search import (EmbeddingDatabase, ProgressiveSimilaritySearchEngine, RAGSearchEngineImpl,   # noqa: F401
                      SearchResult, comprehensive_scores, search_batch)
 from .rag import DocumentSearchResult, ProgressiveSearchEngine, RAGSystem    # noqa: F401
+from .precomputed import PrecomputedHilbertIndexer, PrecomputedIndex, PrecomputedLevel   # noqa: F401
 from .distributed import ShardedSearch, allgather_merge, shard_bounds        # noqa: F401
 
 __version__ = "0.1.0"

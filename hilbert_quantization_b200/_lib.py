@@ -55,6 +55,7 @@ SIGNATURES = {
     "hq_rerank_topk_bf16": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _p, _i64, _p, _i32, _p, _i64, _i32, _i64,
                                    _p, _p, _p, _i64, _p]),
     "hq_comprehensive_scores": (_i32, [_p, _i64, _i32, _i32, _i64, _p, _i32, _i64, _p, _p, _i64, _p, _p]),
+    "hq_offset_square_means": (_i32, [_p, _i64, _i32, _i64, _p, _i64, _p]),
     "hq_topk_merge": (_i32, [_p, _p, _i32, _i32, _i32, _p, _p, _p]),
     "hq_core_level_sims": (_i32, [_p, _i64, _i32, _i64, _p, _p, _p, _p, _i32, _p, _p]),
 }

@@ -151,3 +151,40 @@ extern "C" int hq_comprehensive_scores(const float* frames, int64_t N, int n, in
     HQ_LAUNCH_OK("k_blend");
     return HQ_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// f1: half-offset squares of PrecomputedHilbertIndexer (core/precomputed_hilbert_index.py:185-203).
+// A square of side s at (s/2 + r*s, s/2 + c*s) is exactly four aligned (s/2)-blocks, so its mean is the
+// mean of four entries of the next finer level of aligned means (or of four cells when s == 2):
+//   out[item, r*(G/2-1) + c] = 0.25 * ((h[2r+1][2c+1] + h[2r+1][2c+2]) + (h[2r+2][2c+1] + h[2r+2][2c+2]))
+// with h = the finer level as a row-major [G, G] image.
+// ---------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) k_offset_squares(const float* __restrict__ half, int64_t N, int G, int64_t half_stride,
+                                                        float* __restrict__ out, int64_t out_stride) {
+    const int g1 = G / 2 - 1;
+    const int64_t per = (int64_t)g1 * g1, total = N * per;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t item = t / per;
+        const int e = (int)(t - item * per);
+        const int r = e / g1, c = e - r * g1;
+        const float* h = half + item * half_stride + (int64_t)(2 * r + 1) * G + (2 * c + 1);
+        const float a = __ldg(h), b = __ldg(h + 1), cc = __ldg(h + G), d = __ldg(h + G + 1);
+        out[item * out_stride + e] = ((a + b) + (cc + d)) * 0.25f;
+    }
+}
+}  // namespace
+
+extern "C" int hq_offset_square_means(const float* half, int64_t N, int G, int64_t half_stride, float* out, int64_t out_stride,
+                                      void* stream) {
+    HQ_REQUIRE(G >= 2 && G % 2 == 0 && N >= 0, "finer level must be an even-sided square");
+    const int64_t per = (int64_t)(G / 2 - 1) * (G / 2 - 1);
+    if (N == 0 || per == 0) return HQ_OK;
+    HQ_REQUIRE(half && out && half_stride >= (int64_t)G * G && out_stride >= per, "null pointer or stride too small");
+    int64_t blocks = (N * per + 255) / 256;
+    const int64_t cap = (int64_t)hq_cached_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    k_offset_squares<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(half, N, G, half_stride, out, out_stride);
+    HQ_LAUNCH_OK("k_offset_squares");
+    return HQ_OK;
+}

@@ -242,6 +242,14 @@ int hq_comprehensive_scores(const float* frames, int64_t N, int n, int L, int64_
                             const float* q_frames, int Q, int64_t q_stride, const float* weights_host,
                             const int64_t* cand_ids, int64_t M, float* out, void* stream);
 
+/* ---- f1: PrecomputedHilbertIndexer half-offset squares ------------------------
+ * core/precomputed_hilbert_index.py:185-203.  The aligned square means of every level come out of
+ * hq_map_index_fused (they are run means of the Hilbert stream); a square offset by half its side is
+ * the mean of four entries of the next finer level `half` (row-major [G, G] per item):
+ * out [N, (G/2 - 1)^2], row-major over (row, col) like the reference's loop. */
+int hq_offset_square_means(const float* half, int64_t N, int G, int64_t half_stride,
+                           float* out, int64_t out_stride, void* stream);
+
 /* ---- a15 multi-GPU: merge of per-shard top-k ---------------------------
  * in_ids/in_scores [P, Q, k] (all-gathered) -> out [Q, k]; ties -> lower id;
  * entries with id < 0 are empty. */

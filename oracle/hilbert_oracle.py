@@ -743,6 +743,46 @@ def comprehensive_similarity(q_frame: np.ndarray, c_frames: np.ndarray, original
 
 
 # ----------------------------------------------------------------------------
+# f1  PrecomputedHilbertIndexer               core/precomputed_hilbert_index.py:122-212
+# ----------------------------------------------------------------------------
+
+def precomputed_granularity_levels(image_size: int, max_levels: int = 6, min_square_size: int = 2) -> List[Tuple[int, int]]:
+    """(grid_size, square_size) per level.  core/precomputed_hilbert_index.py:122-150."""
+    levels = []
+    square = min_square_size
+    while square <= image_size // 2 and len(levels) < max_levels:
+        grid = image_size // square
+        if grid >= 2:
+            levels.append((grid, square))
+        square *= 2
+    if len(levels) == 0 or levels[-1][1] < image_size:
+        levels.append((1, image_size))
+    return levels
+
+
+def precomputed_level_averages(image: np.ndarray, grid_size: int, square_size: int) -> np.ndarray:
+    """Aligned square means (row-major) followed by the squares offset by half a side (row-major), float32.
+    core/precomputed_hilbert_index.py:152-212."""
+    h, w = image.shape
+    out = []
+    for r in range(grid_size):
+        for c in range(grid_size):
+            y, x = r * square_size, c * square_size
+            reg = image[y:min(y + square_size, h), x:min(x + square_size, w)]
+            if reg.size:
+                out.append(float(np.mean(reg)))
+    off = square_size // 2
+    if off > 0:
+        for r in range(grid_size - 1):
+            for c in range(grid_size - 1):
+                y, x = r * square_size + off, c * square_size + off
+                reg = image[y:min(y + square_size, h), x:min(x + square_size, w)]
+                if reg.size:
+                    out.append(float(np.mean(reg)))
+    return np.array(out, dtype=np.float32)
+
+
+# ----------------------------------------------------------------------------
 # a11  core progressive search               core/search_engine.py:42-388
 # ----------------------------------------------------------------------------
 

@@ -463,3 +463,34 @@ def test_comprehensive_blend_batch_and_shortlist(hq):
     for j in range(Q):
         for m in range(7):
             assert short[j, m] == (-1.0 if ids[j, m] < 0 else full[j, ids[j, m]])
+
+
+# ---------------------------------------------------------------------------------------
+# f1 PrecomputedHilbertIndexer (core/precomputed_hilbert_index.py:65-212)
+# ---------------------------------------------------------------------------------------
+def test_precomputed_indexer_golden(hq):
+    g = load_golden("precomputed.npz")
+    for n in (8, 16, 64, 128):
+        img = g[f"n{n}_image"]
+        ix = hq.PrecomputedHilbertIndexer()
+        idx = ix.create_precomputed_index(img, f"m{n}")
+        assert ix.get_index(f"m{n}") is idx and idx.original_shape == (n, n)
+        want_levels = [tuple(r) for r in g[f"n{n}_levels"]]
+        assert [(l.grid_size, l.square_size, l.num_squares) for l in idx.levels] == want_levels
+        for i, l in enumerate(idx.levels):
+            assert l.averages.dtype == np.float32
+            assert np.abs(l.averages - g[f"n{n}_avg{i}"]).max() < 3e-7          # 4-ary tree vs NumPy's pairwise float32 mean
+            assert np.array_equal(np.array(l.square_coordinates).reshape(-1, 2), g[f"n{n}_xy{i}"])
+    with pytest.raises(ValueError, match="must be square"):
+        hq.PrecomputedHilbertIndexer().create_precomputed_index(np.zeros((4, 8), np.float32), "x")
+
+
+def test_precomputed_indexer_batch_vs_oracle(hq):
+    rng = np.random.default_rng(3)
+    grids = rng.standard_normal((5, 32, 32)).astype(np.float32)
+    ix = hq.PrecomputedHilbertIndexer()
+    per_level = ix.level_averages_batch(torch.from_numpy(grids).cuda())
+    for (gs, ss), t in zip(O.precomputed_granularity_levels(32), per_level):
+        got = t.cpu().numpy()
+        for i in range(5):
+            assert np.abs(got[i] - O.precomputed_level_averages(grids[i], gs, ss)).max() < 3e-7

@@ -148,3 +148,15 @@ def test_oracle_comprehensive_blend_matches_reference_golden():
         assert np.abs(O.spatial_locality_similarity(qf[:H], cfs[:, :H]) - g[f"{tag}_spatial"]).max() < 2e-7
         order = np.argsort(-got, kind="stable")
         assert list(order[:5]) == list(g[f"{tag}_ranked_ids"][:5])
+
+
+def test_oracle_precomputed_indexer_matches_reference_golden():
+    """f1: oracle restatement of core/precomputed_hilbert_index.py:122-212 against the reference's output."""
+    g = load_golden("precomputed.npz")
+    for n in (8, 16, 64, 128):
+        img = g[f"n{n}_image"]
+        levels = O.precomputed_granularity_levels(n)
+        assert [tuple(r[:2]) for r in g[f"n{n}_levels"]] == levels
+        for i, (gs, ss) in enumerate(levels):
+            got = O.precomputed_level_averages(img, gs, ss)
+            assert got.shape == g[f"n{n}_avg{i}"].shape and np.array_equal(got, g[f"n{n}_avg{i}"])
