@@ -520,6 +520,199 @@ int launch_bulk(const TileParams& p, cudaStream_t st) {
     return p.log2t == 5 ? launch_bulk_t<MODE, 5>(p, st) : launch_bulk_t<MODE, 6>(p, st);
 }
 
+// ---------------------------------------------------------------------------------------
+// Big grids (n > 64), map direction: the same bulk-copy pipeline per 64x64 TILE.  A chunk is an aligned
+// 4096-run of one item's stream = one tile whose inner order is the n = 64 order composed with the
+// (swap, flip) pair of tile_frame.  Source: one 16 KB bulk load (clipped at D).  Tile out: ONE 2-D tensor
+// store (box 64 x 64 floats, rows 256 B apart by n * 4 B in global memory).  The pyramid of the tile
+// (levels 1..6) is published to the per-item scratch for k_pyramid_top, like k_tile_pass does.
+// k_tile_pass (no prefetch, five barriers per tile) ran the 494 M-parameter stream of config C4 at
+// 2.8 TB/s.
+// ---------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kBlock, 3) k_tile_pass_bulk(const __grid_constant__ CUtensorMap map_grid, const TileParams p,
+                                                              const int kRing, const int stages) {
+    using P = typename PT<MODE>::type;
+    using G = Geo<6>;
+    constexpr uint32_t kImg = 4096;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* const s_img0 = reinterpret_cast<float*>(smem_raw);                     // kRing dense tile images
+    float* const s_stage0 = s_img0 + kRing * kImg;                                // `stages` source staging buffers
+    P* const s_pyr0 = reinterpret_cast<P*>(s_stage0 + (size_t)stages * kImg);     // two pyramids
+    __shared__ __align__(8) uint64_t s_full[kMaxStages];
+    __shared__ __align__(8) uint64_t s_free[2];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool idx_warp = warp == kThreads / 32;
+    const bool want_pyr = p.plan_len > 0 && p.min_level <= 32;
+    const int upper_bits = p.log2n - 6;
+    const int64_t tiles_per_item = (int64_t)1 << (2 * upper_bits);
+    const int64_t n_cells = (int64_t)1 << (2 * p.log2n);
+
+    // tile-image offsets of the quad's four cells, unswapped (y * 64 + x) and swapped (x * 64 + y)
+    uint32_t slotA01[kQPT], slotA23[kQPT], slotB01[kQPT], slotB23[kQPT];
+#pragma unroll
+    for (int r = 0; r < kQPT; ++r) {
+        const uint32_t q = tid + r * kThreads;
+        uint32_t a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint32_t x, y;
+            hq_d2xy(6, 4ull * q + i, x, y);
+            a[i] = y * 64 + x;
+            b[i] = x * 64 + y;
+        }
+        slotA01[r] = a[0] | (a[1] << 16); slotA23[r] = a[2] | (a[3] << 16);
+        slotB01[r] = b[0] | (b[1] << 16); slotB23[r] = b[2] | (b[3] << 16);
+    }
+    for (uint32_t i = tid; i < 2 * G::pyr_vals; i += kBlock) s_pyr0[i] = (P)0;
+
+    // floats of the chunk that exist in the source (the rest of the tile is zero padding)
+    auto chunk_valid = [&](int64_t chunk) -> uint32_t {
+        const int64_t item = chunk / tiles_per_item, tile = chunk - item * tiles_per_item;
+        const int64_t left = p.D - tile * 4096;
+        return left <= 0 ? 0u : (left >= 4096 ? 4096u : (uint32_t)left);
+    };
+    auto issue_load = [&](int64_t chunk, int st) {
+        const int64_t item = chunk / tiles_per_item, tile = chunk - item * tiles_per_item;
+        const uint32_t bytes = chunk_valid(chunk) * 4u;
+        const uint32_t bar = hq_tc::smem_u32(&s_full[st]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        if (bytes)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             hq_tc::smem_u32(s_stage0 + (size_t)st * kImg)),
+                         "l"(p.src + item * p.src_stride + tile * 4096), "r"(bytes), "r"(bar)
+                         : "memory");
+    };
+
+    if (tid == 0) {
+        hq_tc::mbar_init(&s_free[0], 1);
+        hq_tc::mbar_init(&s_free[1], 1);
+        for (int i = 0; i < stages; ++i) hq_tc::mbar_init(&s_full[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int64_t c = blockIdx.x;
+        for (int i = 0; i < stages && c < p.num_chunks; ++i, c += gridDim.x) issue_load(c, i);
+    }
+
+    int64_t sc_item = 0;                                           // scratch values per item (levels min_level .. log2n)
+    for (int k = p.min_level; k <= p.log2n; ++k) sc_item += n_cells >> (2 * k);
+
+    uint32_t ring = 0, iter = 0, st = 0, st_phase = 0;
+    for (int64_t chunk = blockIdx.x; chunk < p.num_chunks; chunk += gridDim.x, ring = (ring + 1 == (uint32_t)kRing ? 0 : ring + 1), ++iter) {
+        const int64_t item = chunk / tiles_per_item;
+        const uint64_t tile = (uint64_t)(chunk - item * tiles_per_item);
+        uint32_t X, Y, swp, flp;
+        tile_frame(upper_bits, tile, X, Y, swp, flp);
+        const uint32_t valid = chunk_valid(chunk);
+        float* img = s_img0 + ring * kImg;
+        P* pyrb = s_pyr0 + (iter & 1u) * G::pyr_vals;
+
+        if (!idx_warp) {
+            hq_tc::mbar_wait(&s_full[st], st_phase);
+            const float* stg = s_stage0 + (size_t)st * kImg;
+            float4 v[kQPT];
+#pragma unroll
+            for (int r = 0; r < kQPT; ++r) {
+                const uint32_t q = tid + r * kThreads;
+                v[r] = 4 * q < valid ? *reinterpret_cast<const float4*>(stg + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (p.plan_len > 0 && iter >= 2) hq_tc::mbar_wait(&s_free[iter & 1u], ((iter >> 1) - 1u) & 1u);
+            // every cell of the tile is written (zeros beyond D): the images are reused by tiles with other fills
+            const uint32_t fl = flp ? 4095u : 0u;
+#pragma unroll
+            for (int r = 0; r < kQPT; ++r) {
+                const uint32_t s01 = swp ? slotB01[r] : slotA01[r], s23 = swp ? slotB23[r] : slotA23[r];
+                const uint32_t o0 = s01 & 0xffffu, o1 = s01 >> 16, o2 = s23 & 0xffffu, o3 = s23 >> 16;
+                img[flp ? fl - o0 : o0] = v[r].x;
+                img[flp ? fl - o1 : o1] = v[r].y;
+                img[flp ? fl - o2 : o2] = v[r].z;
+                img[flp ? fl - o3 : o3] = v[r].w;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (tid == 0) {
+                if (kRing == 2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            }
+            asm volatile("bar.sync 2, %0;" ::"n"(kThreads) : "memory");
+            if (tid == 0) {
+                if (p.grid_out) {
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                     reinterpret_cast<uint64_t>(&map_grid)),
+                                 "r"(hq_tc::smem_u32(img)), "r"((int32_t)(X * 64)), "r"((int32_t)(item * ((int64_t)1 << p.log2n) + Y * 64))
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                const int64_t nx = chunk + (int64_t)stages * gridDim.x;
+                if (nx < p.num_chunks) issue_load(nx, (int)st);
+            }
+            if (want_pyr) pyramid_levels_123<MODE, 6>(v, 0xfu, 0xfu, pyrb, tid, lane);
+            if (p.plan_len > 0) {
+                if (iter & 1u) asm volatile("bar.arrive 3, %0;" ::"n"(kBlock) : "memory");
+                else asm volatile("bar.arrive 1, %0;" ::"n"(kBlock) : "memory");
+            }
+        } else if (p.plan_len > 0) {
+            if (iter & 1u) asm volatile("bar.sync 3, %0;" ::"n"(kBlock) : "memory");
+            else asm volatile("bar.sync 1, %0;" ::"n"(kBlock) : "memory");
+            if (want_pyr) {
+                pyramid_levels_top<MODE, 6>(pyrb, G::qpi, lane);
+                // publish the tile's levels [min_level .. 6] to the per-item scratch pyramid
+                P* dst = reinterpret_cast<P*>(p.scratch) + item * sc_item;
+                int64_t lvl_base_g = 0;
+                uint32_t lvl_base_s = 0;
+                for (int k = 1; k <= 6; ++k) {
+                    const uint32_t cnt = 4096u >> (2 * k);
+                    if (k >= p.min_level) {
+                        for (uint32_t t = lane; t < cnt; t += 32) dst[lvl_base_g + (int64_t)tile * cnt + t] = pyrb[lvl_base_s + t];
+                        lvl_base_g += n_cells >> (2 * k);
+                    }
+                    lvl_base_s += cnt;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) hq_tc::mbar_arrive(&s_free[iter & 1u]);
+        }
+        if (++st == (uint32_t)stages) { st = 0; st_phase ^= 1u; }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// big grids: dense 16-byte aligned grid output (or none), whole 16-byte units in the source
+inline bool tile_bulk_eligible(const TileParams& p) {
+    return p.direction == 0 && p.log2n > 6 && p.log2n <= 15 && p.vec_src && (p.D % 4 == 0) && (p.src_stride % 4 == 0) &&
+           (!p.grid_out || (p.vec_grid && p.grid_stride == ((int64_t)1 << (2 * p.log2n)) && hq_tc::encode_tiled_fn() != nullptr &&
+                            p.N * ((int64_t)1 << p.log2n) < ((int64_t)1 << 31)));
+}
+
+template <int MODE>
+int launch_tile_bulk(const TileParams& p, cudaStream_t st) {
+    using G = Geo<6>;
+    static const int ring = env_int("HQ_TILE_RING", 2), stages = env_int("HQ_TILE_STAGES", 2);
+    const size_t smem = (size_t)(ring + stages) * 4096 * 4 + (size_t)2 * G::pyr_vals * (MODE ? 8 : 4) + 64;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        HQ_CUDA_OK(cudaFuncSetAttribute(k_tile_pass_bulk<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    int per_sm = 0;
+    HQ_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_pass_bulk<MODE>, kBlock, smem));
+    if (per_sm < 1) per_sm = 1;
+    CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    if (p.grid_out) {
+        const int64_t n = (int64_t)1 << p.log2n;
+        const int rc = hq_tc::make_map_2d_plain(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.grid_out, p.N * n, n, n, 64, 64);
+        if (rc != HQ_OK) return rc;
+    }
+    int64_t blocks = (int64_t)hq_cached_sm_count() * per_sm;
+    if (blocks > p.num_chunks) blocks = p.num_chunks;
+    k_tile_pass_bulk<MODE><<<(unsigned)blocks, kBlock, smem, st>>>(map, p, ring, stages);
+    HQ_LAUNCH_OK("k_tile_pass_bulk");
+    return HQ_OK;
+}
+
 template <int LOG2T>
 inline size_t smem_bytes(int mode) {
     using G = Geo<LOG2T>;

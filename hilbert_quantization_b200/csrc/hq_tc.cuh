@@ -128,4 +128,25 @@ inline int make_map_2d(CUtensorMap* map, CUtensorMapDataType dtype, int elem_byt
     return HQ_OK;
 }
 
+// row-major [rows, cols] matrix, unswizzled boxes (shared-memory image = dense box_rows x box_cols)
+inline int make_map_2d_plain(CUtensorMap* map, CUtensorMapDataType dtype, int elem_bytes, const void* base, int64_t rows, int64_t cols,
+                             int64_t pitch_elems, int box_cols, int box_rows) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) {
+        hq_set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return HQ_ECUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * elem_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, dtype, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        hq_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return HQ_ECUDA;
+    }
+    return HQ_OK;
+}
+
 }  // namespace hq_tc

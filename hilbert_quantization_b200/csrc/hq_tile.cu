@@ -13,6 +13,7 @@
 // shuffles straight from the loaded quads; levels >= 4 are finished from shared memory.
 #include "hq_tc.cuh"
 #include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -523,6 +524,8 @@ static int fused_impl(const float* src, int direction, int64_t N, int64_t D, int
         if (direction == 0 && item_pass::bulk_eligible(p)) rc = pyr_mode ? item_pass::launch_bulk<1>(p, st) : item_pass::launch_bulk<0>(p, st);
         else if (direction == 0) rc = pyr_mode ? item_pass::launch<0, 1>(p, st) : item_pass::launch<0, 0>(p, st);
         else rc = pyr_mode ? item_pass::launch<1, 1>(p, st) : item_pass::launch<1, 0>(p, st);
+    } else if (direction == 0 && item_pass::tile_bulk_eligible(p)) {
+        rc = pyr_mode ? item_pass::launch_tile_bulk<1>(p, st) : item_pass::launch_tile_bulk<0>(p, st);
     } else if (direction == 0) rc = pyr_mode ? launch_tile<0, 1>(p, st) : launch_tile<0, 0>(p, st);
     else rc = pyr_mode ? launch_tile<1, 1>(p, st) : launch_tile<1, 0>(p, st);
     if (rc != HQ_OK) return rc;
