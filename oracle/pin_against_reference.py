@@ -210,6 +210,43 @@ def main():
         check(f"core progressive S={S}", want_ids == list(ids) and
               np.abs(np.array([x.similarity_score for x in res]) - sc).max() < 1e-12, f"top={want_ids[:3]}")
 
+    # --- a14 comprehensive blend (rag/search/engine.py:516-575), index rows / original rows read explicitly ---
+    from unittest.mock import patch
+    eng = ref.RAGSearchEngineImpl(ref.RAGConfig())
+    gen = ref.HierarchicalIndexGenerator()
+    for n, D in ((64, 1536), (32, 768), (16, 200), (64, 4096)):
+        r = np.random.default_rng(n + D)
+
+        def frame(v):
+            return gen.generate_multi_level_indices(rmapper.map_to_2d(v.astype(np.float32), (n, n))).astype(np.float32)
+        qv = r.standard_normal(D)
+        cfs = [frame(r.standard_normal(D)) for _ in range(5)] + [frame(qv + 0.1 * r.standard_normal(D))]
+        qf = frame(qv)
+        with patch.object(eng, "_extract_hierarchical_indices", side_effect=lambda fr: gen.extract_indices_from_image(fr, original_height=n)[1]), \
+                patch.object(eng, "_extract_original_embedding", side_effect=lambda fr: fr[:n, :] if fr.ndim == 2 else fr):
+            qi = eng._extract_hierarchical_indices(qf)
+            want = np.array([eng._calculate_comprehensive_similarity(qf, qi, c, 0) for c in cfs])
+            want_sp = np.array([eng._calculate_spatial_locality_similarity(qf, c) for c in cfs])
+        got = O.comprehensive_similarity(qf, np.stack(cfs), n)
+        check(f"comprehensive blend n={n} D={D}", np.abs(want - got).max() < 2e-7, f"{np.abs(want - got).max():.1e}")
+        got_sp = O.spatial_locality_similarity(qf[:n], np.stack(cfs)[:, :n])
+        check(f"spatial locality n={n} D={D}", np.abs(want_sp - got_sp).max() < 2e-7, f"{np.abs(want_sp - got_sp).max():.1e}")
+    for L in (1, 2, 3, 6):
+        check(f"granularity weights L={L}", np.allclose(O.granularity_weights(L), eng._calculate_granularity_weights(L), rtol=0, atol=0))
+
+    # --- f1 PrecomputedHilbertIndexer (core/precomputed_hilbert_index.py:122-212) ---
+    import contextlib
+    import io
+    from hilbert_quantization.core.precomputed_hilbert_index import PrecomputedHilbertIndexer
+    for n in (8, 32, 64):
+        img = rng.standard_normal((n, n)).astype(np.float32)
+        with contextlib.redirect_stdout(io.StringIO()):
+            pidx = PrecomputedHilbertIndexer().create_precomputed_index(img, f"pin{n}")
+        lv = O.precomputed_granularity_levels(n)
+        check(f"precomputed levels n={n}", lv == [(l.grid_size, l.square_size) for l in pidx.levels])
+        ok = all(np.array_equal(O.precomputed_level_averages(img, g, s), l.averages) for (g, s), l in zip(lv, pidx.levels))
+        check(f"precomputed averages n={n}", ok)
+
     print(f"\n{len(FAILS)} failure(s)")
     return 1 if FAILS else 0
 
