@@ -251,20 +251,38 @@ __global__ void __launch_bounds__(128) k_rerank_tc_merge(const TcParams p, const
     }
     if (tid < KP) { top_val[tid] = -FLT_MAX; top_idx[tid] = -1; }
     __syncthreads();
-    for (int e = tid; e < M; e += blockDim.x) {
-        const int32_t id = c_idx[e];
-        if (id < 0) continue;
-        const float v = c_val[e];
-        int rank = 0;
-        for (int j = 0; j < M; ++j) {
-            const int32_t idj = c_idx[j];
-            if (idj < 0) continue;
-            const float vj = c_val[j];
-            rank += (vj > v || (vj == v && idj < id)) ? 1 : 0;
+    // KP rounds of block-wide arg-best (value desc, id asc).  The first version ranked every candidate
+    // against every other one (O(M^2)): 0.6 ms of a 1.0 ms single-query search when one query owns ~100 units.
+    __shared__ float r_val[4];
+    __shared__ int32_t r_idx[4], r_pos[4];
+    for (int round = 0; round < KP; ++round) {
+        float bv = -FLT_MAX;
+        int32_t bi = 0x7fffffff, bp = -1;
+        for (int e = tid; e < M; e += blockDim.x) {
+            const int32_t id = c_idx[e];
+            if (id < 0) continue;
+            const float v = c_val[e];
+            if (v > bv || (v == bv && id < bi)) { bv = v; bi = id; bp = e; }
         }
-        if (rank < KP) { top_val[rank] = v; top_idx[rank] = id; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int32_t oi = __shfl_xor_sync(0xffffffffu, bi, o), op = __shfl_xor_sync(0xffffffffu, bp, o);
+            if (op >= 0 && (bp < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; bp = op; }
+        }
+        if (lane == 0) { r_val[warp] = bv; r_idx[warp] = bi; r_pos[warp] = bp; }
+        __syncthreads();
+        if (tid == 0) {
+            int w = -1;
+            for (int i = 0; i < 4; ++i)
+                if (r_pos[i] >= 0 && (w < 0 || r_val[i] > r_val[w] || (r_val[i] == r_val[w] && r_idx[i] < r_idx[w]))) w = i;
+            if (w >= 0) {
+                top_val[round] = r_val[w]; top_idx[round] = r_idx[w];
+                c_idx[r_pos[w]] = -1;                      // taken
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
     // exact fp32 cosine of the shortlisted rows (one warp per candidate)
     const float nq = q_norm[q];
     const float* qv = q_f32 + (int64_t)q * q_stride;

@@ -368,10 +368,16 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
     if filter_scope == "global":
         filter_impl = "exact"                      # the global cut works on the per-level score matrix
     fast = False
+    dense_queries = None
     if use_filter and filter_impl != "exact":
-        fast = db.fast_filter_ok and bool((q_lens == db._keff).all().item())
+        fast = db.fast_filter_ok
         if filter_impl in ("fast", "fast_fp32") and not fast:
             raise ValueError("the fast filter needs dense index rows (all stored lengths structural) and L <= 3")
+        if fast:
+            # The fast path also needs dense QUERY index rows.  The test runs on the device and is read back only
+            # after everything has been launched (a read-back here would drain the stream on every call); a batch
+            # with a sparse query is searched again through the exact path.
+            dense_queries = (q_lens == db._keff).all()
     if fast or not use_filter:
         work_bytes = max(work_bytes, 4 * N * Q) if rerank == "bf16" else work_bytes
     qc = int(max(1, min(Q, work_bytes // (4 * N)))) if not (rerank == "bf16" and (fast or not use_filter)) else Q
@@ -421,6 +427,14 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
             check(lib.hq_topk_from_scores(dev.ptr(scores), scores.stride(0), N, nq, k, db.id_base,
                                           dev.ptr(ids[s:e]), dev.ptr(out_scores[s:e]), dev.stream_ptr()))
             _end(tok)
+    if dense_queries is not None and not bool(dense_queries.item()):
+        if filter_impl in ("fast", "fast_fp32"):
+            raise ValueError("the fast filter needs dense index rows (all stored lengths structural) and L <= 3")
+        if trace is not None:
+            trace.n_alive.clear(); trace.n_pass.clear(); trace.n_out.clear()
+        return search_batch(db, queries, k, use_filter=use_filter, work_bytes=work_bytes, return_mask=return_mask, trace=trace,
+                            rerank=rerank, filter_impl="exact", filter_scope=filter_scope, group=group,
+                            filter_scratch_bytes=filter_scratch_bytes)
     if return_mask:
         return ids, out_scores, (torch.cat(masks) if masks else None)
     return ids, out_scores

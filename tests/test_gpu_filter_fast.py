@@ -82,3 +82,19 @@ def test_global_scope_equals_exact_filter_on_one_shard(hq, N, D, Q, positive):
     assert torch.equal(i_g, i_e) and torch.equal(s_g, s_e)
     for l in range(len(te.n_out)):
         assert torch.equal(tg.n_out[l].to(torch.int64), te.n_out[l].to(torch.int64))
+
+
+def test_sparse_query_is_searched_through_the_exact_path(hq):
+    """A query whose index rows are shorter than the structural length cannot use the fast filter: the batch
+    is redone through the exact path (the check is read back after the speculative launches)."""
+    rng = np.random.default_rng(5)
+    db = rng.standard_normal((2000, 768)).astype(np.float32)
+    qs = rng.standard_normal((4, 768)).astype(np.float32)
+    qs[2, 600:] = 0.0
+    d = hq.EmbeddingDatabase(db)
+    assert d.fast_filter_ok
+    i_a, s_a = hq.search_batch(d, qs, 7)
+    i_e, s_e = hq.search_batch(d, qs, 7, filter_impl="exact")
+    assert torch.equal(i_a, i_e) and torch.equal(s_a, s_e)
+    with pytest.raises(ValueError, match="fast filter"):
+        hq.search_batch(d, qs, 7, filter_impl="fast")
