@@ -188,3 +188,62 @@ extern "C" int hq_offset_square_means(const float* half, int64_t N, int G, int64
     HQ_LAUNCH_OK("k_offset_squares");
     return HQ_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// f4: video-path hierarchical similarity (core/video_storage.py:763-781): (pearson + 1) / 2 of two index
+// vectors on their common prefix, clamped to [0, 1]; when a vector has zero variance: 1.0 if the two are
+// np.allclose (|a - b| <= 1e-8 + 1e-5 |b|), else 0.0.  All pairs of A [M, S] x B [N, S] in float64 (np.corrcoef
+// works in float64), one warp per pair, two passes (means, then centred products) like np.cov.
+// ---------------------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_pearson01(const double* __restrict__ A, int64_t M, int64_t a_stride, const double* __restrict__ B,
+                                                   int64_t N, int64_t b_stride, int S, double* __restrict__ out, int64_t out_stride) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t pair = (((int64_t)blockIdx.x * blockDim.x) + threadIdx.x) >> 5; pair < M * N; pair += warps) {
+        const int64_t m = pair / N, n = pair - m * N;
+        const double* a = A + m * a_stride;
+        const double* b = B + n * b_stride;
+        double sa = 0.0, sb = 0.0;
+        for (int i = lane; i < S; i += 32) { sa += a[i]; sb += b[i]; }
+        const double ma = warp_sum_d(sa) / S, mb = warp_sum_d(sb) / S;
+        double sab = 0.0, saa = 0.0, sbb = 0.0;
+        int close = 1;
+        for (int i = lane; i < S; i += 32) {
+            const double x = a[i], y = b[i], da = x - ma, db = y - mb;
+            sab += da * db; saa += da * da; sbb += db * db;
+            if (!(fabs(x - y) <= 1e-8 + 1e-5 * fabs(y))) close = 0;
+        }
+        sab = warp_sum_d(sab); saa = warp_sum_d(saa); sbb = warp_sum_d(sbb);
+        close = __all_sync(0xffffffffu, close);
+        double r;
+        if (saa == 0.0 || sbb == 0.0) r = close ? 1.0 : 0.0;
+        else {
+            double c = sab / sqrt(saa) / sqrt(sbb);
+            c = c > 1.0 ? 1.0 : (c < -1.0 ? -1.0 : c);           // np.corrcoef clips to [-1, 1]
+            r = (c + 1.0) / 2.0;
+            r = r < 0.0 ? 0.0 : (r > 1.0 ? 1.0 : r);
+        }
+        if (lane == 0) out[m * out_stride + n] = r;
+    }
+}
+}  // namespace
+
+extern "C" int hq_pearson01_matrix(const double* a, int64_t M, int64_t a_stride, const double* b, int64_t N, int64_t b_stride, int S,
+                                   double* out, int64_t out_stride, void* stream) {
+    HQ_REQUIRE(M >= 0 && N >= 0 && S >= 1, "bad shape");
+    if (M == 0 || N == 0) return HQ_OK;
+    HQ_REQUIRE(a && b && out && a_stride >= S && b_stride >= S && out_stride >= N, "null pointer or stride too small");
+    int64_t blocks = (M * N + 7) / 8;
+    const int64_t cap = (int64_t)hq_cached_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    k_pearson01<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, M, a_stride, b, N, b_stride, S, out, out_stride);
+    HQ_LAUNCH_OK("k_pearson01");
+    return HQ_OK;
+}

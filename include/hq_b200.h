@@ -250,6 +250,14 @@ int hq_comprehensive_scores(const float* frames, int64_t N, int n, int L, int64_
 int hq_offset_square_means(const float* half, int64_t N, int G, int64_t half_stride,
                            float* out, int64_t out_stride, void* stream);
 
+/* ---- f4: video-path hierarchical similarity ------------------------------------
+ * core/video_storage.py:763-781 (_calculate_hierarchical_similarity), used by _traditional_search (:741-761),
+ * _sort_frames_by_hierarchical_indices (:1203-1277) and _find_optimal_insertion_position (:1751-1803):
+ * out[m, n] = clamp((pearson(a_m[:S], b_n[:S]) + 1) / 2, 0, 1) in float64; zero-variance vectors score 1.0 when
+ * np.allclose, else 0.0. */
+int hq_pearson01_matrix(const double* a, int64_t M, int64_t a_stride, const double* b, int64_t N, int64_t b_stride,
+                        int S, double* out, int64_t out_stride, void* stream);
+
 /* ---- a15 multi-GPU: merge of per-shard top-k ---------------------------
  * in_ids/in_scores [P, Q, k] (all-gathered) -> out [Q, k]; ties -> lower id;
  * entries with id < 0 are empty. */

@@ -783,6 +783,63 @@ def precomputed_level_averages(image: np.ndarray, grid_size: int, square_size: i
 
 
 # ----------------------------------------------------------------------------
+# f4  video-path hierarchical similarity / frame ordering     core/video_storage.py:741-781, :1203-1277, :1751-1803
+# ----------------------------------------------------------------------------
+
+def video_hierarchical_similarity(q: np.ndarray, c: np.ndarray) -> float:
+    """(pearson + 1) / 2 on the common prefix, clamped; zero-variance special case.  core/video_storage.py:763-781."""
+    if len(q) == 0 or len(c) == 0:
+        return 0.0
+    m = min(len(q), len(c))
+    a, b = q[:m], c[:m]
+    if np.std(a) == 0 or np.std(b) == 0:
+        return 1.0 if np.allclose(a, b) else 0.0
+    corr = np.corrcoef(a, b)[0, 1]
+    return max(0.0, min(1.0, (corr + 1.0) / 2.0))
+
+
+def video_sort_frames(frame_indices: Sequence[np.ndarray]) -> List[int]:
+    """Greedy nearest-neighbour order starting at the frame closest to the centroid.  core/video_storage.py:1203-1277."""
+    F = len(frame_indices)
+    if F <= 1:
+        return list(range(F))
+    centroid = np.mean([f for f in frame_indices if len(f) > 0], axis=0)
+    best, best_d = None, float("inf")
+    for i, f in enumerate(frame_indices):
+        d = np.linalg.norm(f - centroid)
+        if d < best_d:
+            best, best_d = i, d
+    order = [best]
+    remaining = [i for i in range(F) if i != best]
+    while remaining:
+        bj, bs = None, -1.0
+        for j in remaining:
+            s = video_hierarchical_similarity(frame_indices[order[-1]], frame_indices[j])
+            if s > bs:
+                bj, bs = j, s
+        order.append(bj)
+        remaining.remove(bj)
+    return order
+
+
+def video_insertion_position(new_indices: np.ndarray, existing: Sequence[np.ndarray]) -> int:
+    """core/video_storage.py:1751-1803."""
+    if not len(existing):
+        return 0
+    sims = [video_hierarchical_similarity(new_indices, e) for e in existing]
+    pos, best = 0, -1.0
+    if sims[0] > best:
+        best, pos = sims[0], 0
+    for i in range(len(sims) - 1):
+        sc = (sims[i] + sims[i + 1]) / 2.0
+        if sc > best:
+            best, pos = sc, i + 1
+    if sims[-1] > best:
+        best, pos = sims[-1], len(sims)
+    return pos
+
+
+# ----------------------------------------------------------------------------
 # a11  core progressive search               core/search_engine.py:42-388
 # ----------------------------------------------------------------------------
 

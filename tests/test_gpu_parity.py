@@ -494,3 +494,24 @@ def test_precomputed_indexer_batch_vs_oracle(hq):
         got = t.cpu().numpy()
         for i in range(5):
             assert np.abs(got[i] - O.precomputed_level_averages(grids[i], gs, ss)).max() < 3e-7
+
+
+# ---------------------------------------------------------------------------------------
+# f4 video-path hierarchical similarity / frame ordering (core/video_storage.py)
+# ---------------------------------------------------------------------------------------
+def test_video_path_similarity_and_ordering_golden(hq):
+    g = load_golden("video_order.npz")
+    for tag in ("S64_float32", "S1024_float32", "S32_float64"):
+        frames, q = list(g[f"{tag}_frames"]), g[f"{tag}_query"]
+        sims = hq.video.hierarchical_similarity_matrix(q, np.stack(frames)).cpu().numpy()[0]
+        assert np.abs(sims - g[f"{tag}_sims"]).max() < 1e-12
+        pair = hq.video.hierarchical_similarity_matrix(np.stack(frames[:12]), np.stack(frames[:12])).cpu().numpy()
+        assert np.abs(pair - g[f"{tag}_pair_sims"]).max() < 1e-12
+        assert pair[11, 11] == 1.0 and pair[11, 0] == 0.0 and pair[3, 7] == 1.0       # zero variance / duplicate rows
+        assert hq.video.sort_frames_by_hierarchical_indices(frames) == list(g[f"{tag}_order"])
+        assert [hq.video.find_optimal_insertion_position(q, frames[:15]),
+                hq.video.find_optimal_insertion_position(frames[20], frames[:15])] == list(g[f"{tag}_insert_pos"])
+        top = hq.video.traditional_search(q, frames, 5)
+        want = np.argsort(-g[f"{tag}_sims"], kind="stable")[:5]
+        assert [t[0] for t in top] == list(want)
+        assert abs(hq.video.calculate_hierarchical_similarity(q, frames[0]) - g[f"{tag}_sims"][0]) < 1e-12

@@ -160,3 +160,14 @@ def test_oracle_precomputed_indexer_matches_reference_golden():
         for i, (gs, ss) in enumerate(levels):
             got = O.precomputed_level_averages(img, gs, ss)
             assert got.shape == g[f"n{n}_avg{i}"].shape and np.array_equal(got, g[f"n{n}_avg{i}"])
+
+
+def test_oracle_video_path_matches_reference_golden():
+    """f4: oracle restatement of core/video_storage.py:763-781, :1203-1277, :1751-1803 vs the reference's outputs."""
+    g = load_golden("video_order.npz")
+    for tag in ("S64_float32", "S1024_float32", "S32_float64"):
+        frames, q = list(g[f"{tag}_frames"]), g[f"{tag}_query"]
+        sims = np.array([O.video_hierarchical_similarity(q, f) for f in frames])
+        assert np.array_equal(sims, g[f"{tag}_sims"])
+        assert list(O.video_sort_frames(frames)) == list(g[f"{tag}_order"])
+        assert [O.video_insertion_position(q, frames[:15]), O.video_insertion_position(frames[20], frames[:15])] == list(g[f"{tag}_insert_pos"])
