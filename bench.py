@@ -327,7 +327,11 @@ def main():
     S.PHASE_TIMER = None
     per_step = [a.elapsed_time(b) for a, b in step_ms]
     tt = torch.tensor([total_ms], device=device)
+    per_rank_ms = [total_ms / args.steps]
     if world > 1:
+        allt = torch.empty(world, device=device)
+        dist.all_gather_into_tensor(allt, tt.clone())
+        per_rank_ms = [float(x) / args.steps for x in allt.cpu()]
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     total_ms = tt.item()
     ms_per_step = total_ms / args.steps
@@ -384,6 +388,7 @@ def main():
             "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": int(q_pinned.numel() * 4),
                     "d2h_bytes_per_step": int(out_ids.numel() * 8 + out_sc.numel() * 4)},
             "gpu_launches": launches,
+            "per_rank_ms_per_step": per_rank_ms,
             "phases_ms_per_step": {k: v / args.steps for k, v in phases.items()},
             "roofline": {"kernel": "k_rerank_tc<16> + k_rerank_tc_merge<16> (Q x N x D cosine contraction, bf16 tcgen05)", "bound": "tensor",
                          "achieved": achieved_tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",

@@ -156,6 +156,16 @@ __global__ void __launch_bounds__(256) k_level_norms(const float* __restrict__ i
     }
 }
 
+__global__ void __launch_bounds__(256) k_query_norms(const float* __restrict__ q_idx, int Q, hq_index_layout lay, float* __restrict__ nq) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= Q * lay.L) return;
+    const int l = t / Q, q = t - l * Q;
+    const float* r = q_idx + (int64_t)q * lay.Lsum + lay.lvl_off[l];
+    float c = 0.f;
+    for (int j = 0; j < lay.lvl_keff[l]; ++j) { const float v = __ldg(r + j); c = fmaf(v, v, c); }
+    nq[(int64_t)l * Q + q] = sqrtf(c);
+}
+
 // ---------------------------------------------------------------------------------------
 // block-wide exact selection on a compact key list (k-th SMALLEST), warp-aggregated histograms
 // ---------------------------------------------------------------------------------------
@@ -242,6 +252,7 @@ struct CascadeParams {
     uint32_t* scratch_keys;      // [gridDim][N]
     uint32_t* scratch_rows;      // [gridDim][N]
     const int32_t* only;         // optional [Q]: process only queries with a non-zero flag
+    const uint16_t* lens;        // optional [N, L] stored row lengths (rows shorter than lvl_keff exist)
 };
 
 __device__ __forceinline__ uint32_t block_sum(uint32_t v, uint32_t* s_warp) {
@@ -257,7 +268,14 @@ __device__ __forceinline__ uint32_t block_sum(uint32_t v, uint32_t* s_warp) {
 }
 
 // exact fp32 score of one (query level row, database row) pair -- same arithmetic as hq_search.cu
-__device__ __forceinline__ uint32_t level_key(const float* __restrict__ rp, const float* __restrict__ s_q, int keff, float nq) {
+// `m` < keff: the row's stored length (trailing zeros stripped) is shorter than the structural one -- the
+// reference then takes the query norm over that prefix only (rag/search/engine.py:216-227)
+__device__ __forceinline__ uint32_t level_key(const float* __restrict__ rp, const float* __restrict__ s_q, int keff, float nq, int m = 1 << 30) {
+    if (m < keff) {
+        float c = 0.f;
+        for (int j = 0; j < m; ++j) c = fmaf(s_q[j], s_q[j], c);
+        nq = sqrtf(c);
+    }
     float dot = 0.f, cn2 = 0.f;
     for (int j = 0; j < keff; j += 4) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(rp + j));
@@ -381,7 +399,7 @@ __global__ void __launch_bounds__(1024, 1) k_filter_cascade(const CascadeParams 
                     if (i < n_list) {
                         const int64_t row = __ldcg(rows + i);
                         const float* rp = lvl_base ? lvl_base + row * lvl_pitch : p.idx + row * p.lay.Lsum + p.lay.lvl_off[l];
-                        k4[u] = level_key(rp, s_q, keff, nq);
+                        k4[u] = level_key(rp, s_q, keff, nq, p.lens ? (int)p.lens[row * L + l] : (1 << 30));
                     }
                 }
 #pragma unroll
@@ -852,6 +870,76 @@ __global__ void __launch_bounds__(kListThreads, 1) k_filter_cascade_lists(const 
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Exceptional rows.  The fast path assumes every index row has its structural length; a block mean that
+// happens to be exactly 0.0f at the end of a row shortens the row's stored length (one row in ~10 M at
+// 768-D), and the reference then normalises the QUERY over that shorter prefix.  Such rows are masked out of
+// the dense passes (validity words / overwritten plane bits) and scored here pair by pair with the exact
+// path's arithmetic (k_filter_level); rows that pass levels 0 and 1 are appended to one extra list segment
+// per query with score-equivalent keys ((2 s - 1) |q_l|), so the cascade ranks them with everybody else.
+// ---------------------------------------------------------------------------------------
+struct ExcParams {
+    const float* idx;
+    const uint16_t* lens;
+    hq_index_layout lay;
+    const float* q_idx;
+    int Q;
+    const int32_t* exc_rows;
+    int n_exc;
+    double thr[3];
+    uint32_t* bits;
+    int64_t bits_pitch;
+    const float* nq;             // [3][Q] full query level norms
+    uint32_t* l_rows;            // lists (optional)
+    float* l_k1;
+    float* l_k2;
+    int32_t* seg_n;
+    int64_t seg_cap;
+    int n_segs, extra_seg;
+};
+
+__global__ void __launch_bounds__(128) k_filter_exceptions(const ExcParams p) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)p.Q * p.n_exc) return;
+    const int q = (int)(t / p.n_exc), e = (int)(t - (int64_t)q * p.n_exc);
+    const int64_t row = p.exc_rows[e];
+    const int L = p.lay.L;
+    bool pass[3] = {false, false, false};
+    float keq[3] = {0.f, 0.f, 0.f};
+    for (int l = 0; l < L && l < 3; ++l) {
+        const int keff = p.lay.lvl_keff[l];
+        int m = (int)p.lens[row * L + l];
+        m = m < keff ? m : keff;                                   // the query is dense: common prefix = row length
+        const float* c = p.idx + row * p.lay.Lsum + p.lay.lvl_off[l];
+        const float* qv = p.q_idx + (int64_t)q * p.lay.Lsum + p.lay.lvl_off[l];
+        float dot = 0.f, nc2 = 0.f, nq2 = 0.f;
+        for (int j = 0; j < keff; ++j) {
+            const float cj = __ldg(c + j), qj = __ldg(qv + j);
+            dot = fmaf(cj, qj, dot);
+            nc2 = fmaf(cj, cj, nc2);
+            if (j < m) nq2 = fmaf(qj, qj, nq2);
+        }
+        const float nq = sqrtf(nq2), nc = sqrtf(nc2);
+        float sc = 0.f;
+        if (nq != 0.f && nc != 0.f) sc = __fmul_rn(__fadd_rn(__fdiv_rn(dot, __fmul_rn(nq, nc)), 1.0f), 0.5f);
+        pass[l] = (double)sc >= p.thr[l];
+        keq[l] = (2.0f * sc - 1.0f) * __ldg(p.nq + (int64_t)l * p.Q + q);
+        uint32_t* w = p.bits + ((int64_t)l * p.Q + q) * p.bits_pitch + (row >> 5);
+        const uint32_t bit = 1u << (row & 31);
+        atomicAnd(w, ~bit);
+        if (pass[l]) atomicOr(w, bit);
+    }
+    if (p.l_rows && L >= 2 && pass[0] && pass[1]) {
+        const int pos = atomicAdd(p.seg_n + (int64_t)q * p.n_segs + p.extra_seg, 1);
+        if (pos < p.seg_cap) {
+            const int64_t a = ((int64_t)q * p.n_segs + p.extra_seg) * p.seg_cap + pos;
+            p.l_rows[a] = (uint32_t)row | ((L > 2 && pass[2]) ? 0x80000000u : 0u);
+            p.l_k1[a] = keq[1];
+            if (L > 2) p.l_k2[a] = keq[2];
+        }
+    }
+}
+
 template <int K0, int K1, int K2>
 int launch_bits(const BitsParams& p, cudaStream_t st) {
     constexpr int KT = K0 + K1 + K2;
@@ -902,12 +990,12 @@ struct ListGeom { int n_segs; int64_t seg_cap; bool on; };
 
 // candidate-list geometry of the tensor-core pass for (N, Q): two segments per row range, each sized
 // for a third of its rows (random data passes ~13-20 % of the rows through levels 0 and 1)
-static ListGeom list_geom(int64_t N, int Q, const hq_index_layout* layout) {
+static ListGeom list_geom(int64_t N, int Q, const hq_index_layout* layout, bool extra_segment) {
     ListGeom g{0, 0, false};
     if (!layout || layout->L < 2 || !hq_filter_tc_supported(layout) || N <= 0 || Q <= 0) return g;
     int n_ranges = 0, tiles_per = 0;
     if (hq_filter_tc_plan(N, Q, &n_ranges, &tiles_per) != HQ_OK) return g;
-    g.n_segs = 2 * n_ranges;
+    g.n_segs = 2 * n_ranges + (extra_segment ? 1 : 0);          // + one segment for exceptional rows
     if (g.n_segs > kMaxSegs) return g;
     g.seg_cap = (((int64_t)tiles_per * 32 + 2) / 3 + 31) & ~(int64_t)31;
     g.on = true;
@@ -922,20 +1010,21 @@ extern "C" int64_t hq_filter_fast_scratch_bytes(int64_t N, int Q, const hq_index
     // candidate lists of the tensor-core pass
     int64_t b = (int64_t)layout->L * Q * plane_pitch(N) * 4 + up16((int64_t)grid * N * 8) + (int64_t)Q * 128 * 4 +
                 3 * up16((int64_t)3 * Q * 4);
-    const ListGeom g = list_geom(N, Q, layout);
+    const ListGeom g = list_geom(N, Q, layout, true);           // sized for the worst case
     if (g.on) b += 256 + up128((int64_t)Q * g.n_segs * 4) + (int64_t)(layout->L > 2 ? 3 : 2) * Q * g.n_segs * g.seg_cap * 4;
     return b;
 }
 
 extern "C" int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, const hq_index_layout* layout, const float* q_idx, int Q,
                               const float* xstar, const double* ratio, const float* const* lvl_rows, const int32_t* lvl_pitch,
-                              const float* db_packed, const uint32_t* valid, int64_t valid_pitch, uint32_t* mask,
-                              int64_t mask_stride, int32_t* n_out, int32_t* counts, void* scratch, int64_t scratch_bytes,
-                              void* stream) {
+                              const float* db_packed, const uint32_t* valid, int64_t valid_pitch, const uint16_t* lens,
+                              const int32_t* exc_rows, int n_exc, const double* thr, uint32_t* mask, int64_t mask_stride,
+                              int32_t* n_out, int32_t* counts, void* scratch, int64_t scratch_bytes, void* stream) {
     HQ_REQUIRE(hq_filter_fast_supported(layout), "index layout not supported by the fast filter");
     HQ_REQUIRE(N >= 0 && Q >= 0, "negative size");
     if (N == 0 || Q == 0) return HQ_OK;
     HQ_REQUIRE(idx && rnorm && q_idx && xstar && ratio && mask && n_out, "null pointer");
+    HQ_REQUIRE(n_exc >= 0 && (n_exc == 0 || (exc_rows && lens && thr)), "exceptional rows need exc_rows, lens and thr");
     HQ_REQUIRE(N < ((int64_t)1 << 31), "N too large for one shard");
     HQ_REQUIRE(mask_stride * 32 >= N, "mask stride too small");
     const int64_t need = hq_filter_fast_scratch_bytes(N, Q, layout);
@@ -952,7 +1041,9 @@ extern "C" int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, c
     float* const tq = q_packed + (int64_t)Q * 128;
     float* const nq = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(tq) + up16((int64_t)3 * Q * 4));
     int32_t* const fallback = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(nq) + up16((int64_t)3 * Q * 4));
-    const ListGeom lg = db_packed ? list_geom(N, Q, layout) : ListGeom{0, 0, false};
+    ListGeom lg = db_packed ? list_geom(N, Q, layout, n_exc > 0) : ListGeom{0, 0, false};
+    if (lg.on && n_exc > lg.seg_cap) lg.on = false;            // the extra segment could overflow: generic cascade
+    if (lg.on && (int64_t)lg.n_segs * lg.seg_cap > (int64_t)grid * N) lg.on = false;   // tiny shards: no room to compact into
     HqFilterLists lists{};
     if (lg.on) {
         lists.n_segs = lg.n_segs; lists.seg_cap = lg.seg_cap;
@@ -986,6 +1077,26 @@ extern "C" int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, c
     }
     if (rc != HQ_OK) return rc;
 
+    if (n_exc > 0) {
+        ExcParams ep{};
+        ep.idx = idx; ep.lens = lens; ep.lay = *layout; ep.q_idx = q_idx; ep.Q = Q; ep.exc_rows = exc_rows; ep.n_exc = n_exc;
+        for (int l = 0; l < 3; ++l) ep.thr[l] = l < L ? thr[l] : 2.0;
+        ep.bits = planes; ep.bits_pitch = pitch; ep.nq = nq;
+        if (!db_packed) {
+            // the CUDA-core threshold pass does not compute the query norms: do it here
+            k_query_norms<<<(Q * L + 255) / 256, 256, 0, st>>>(q_idx, Q, *layout, nq);
+            HQ_LAUNCH_OK("k_query_norms");
+        }
+        if (lg.on) {
+            ep.l_rows = lists.rows; ep.l_k1 = lists.k1; ep.l_k2 = lists.k2; ep.seg_n = lists.seg_n; ep.seg_cap = lists.seg_cap;
+            ep.n_segs = lists.n_segs; ep.extra_seg = lists.n_segs - 1;
+            HQ_CUDA_OK(cudaMemset2DAsync(lists.seg_n + ep.extra_seg, (size_t)lists.n_segs * 4, 0, 4, (size_t)Q, st));
+        }
+        const int64_t pairs = (int64_t)Q * n_exc;
+        k_filter_exceptions<<<(unsigned)((pairs + 127) / 128), 128, 0, st>>>(ep);
+        HQ_LAUNCH_OK("k_filter_exceptions");
+    }
+
     CascadeParams cp{};
     cp.bits = bp.bits; cp.words = words; cp.bits_pitch = pitch; cp.idx = idx; cp.N = N; cp.lay = *layout; cp.q_idx = q_idx; cp.Q = Q;
     for (int l = 0; l < 8; ++l) {
@@ -1014,6 +1125,7 @@ extern "C" int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, c
     cp.scratch_keys = sc_keys;
     cp.scratch_rows = sc_rows;
     cp.only = nullptr;
+    cp.lens = n_exc > 0 ? lens : nullptr;
     if (lg.on) {
         // streaming cascade over the candidate lists; the generic cascade then runs only for the queries it flags
         HQ_CUDA_OK(cudaMemsetAsync(fallback, 0, (size_t)Q * 4, st));

@@ -506,7 +506,7 @@ int hq_filter_bits_tc_launch(const float* db_packed, const uint32_t* valid, int6
     p.tq = tq; p.valid = valid; p.valid_pitch = valid_pitch; p.bits = bits; p.words = words; p.bits_pitch = bits_pitch;
     plan_units(N, Q, hq_cached_sm_count(), p);
     if (lists && lists->rows) {
-        HQ_REQUIRE(lists->n_segs == 2 * p.n_ranges && lists->seg_cap > 0 && lists->k1 && lists->seg_n && (s.L < 3 || lists->k2),
+        HQ_REQUIRE(lists->n_segs >= 2 * p.n_ranges && lists->n_segs <= 2 * p.n_ranges + 1 && lists->seg_cap > 0 && lists->k1 && lists->seg_n && (s.L < 3 || lists->k2),
                    "candidate list geometry does not match hq_filter_tc_plan");
         p.l_rows = lists->rows; p.l_k1 = lists->k1; p.l_k2 = lists->k2; p.seg_n = lists->seg_n; p.seg_cap = lists->seg_cap;
         p.n_segs = lists->n_segs;

@@ -122,6 +122,8 @@ class EmbeddingDatabase:
     and their stripped lengths.  Built by ONE fused map+index pass over the embeddings
     (the 2-D grids are produced only if `keep_grids`)."""
 
+    MAX_EXCEPTION_ROWS = 4096
+
     def __init__(self, embeddings, n: Optional[int] = None, device=None, keep_grids: bool = False, id_base: int = 0,
                  bf16: bool = True, tc_filter: bool = True):
         d = dev.require_cuda(device if device is not None else (embeddings.device if isinstance(embeddings, torch.Tensor)
@@ -145,11 +147,18 @@ class EmbeddingDatabase:
         with torch.cuda.device(d):
             check(lib.hq_filter_level_norms(dev.ptr(self.idx), dev.ptr(self.lens), self.N, C.byref(self.layout),
                                             dev.ptr(self.level_norms), dev.ptr(flag), dev.stream_ptr()))
-        self.fast_filter_ok = bool(lib.hq_filter_fast_supported(C.byref(self.layout))) and (self.N == 0 or int(flag.item()) == 0)
         self._keff = torch.tensor([int(self.layout.lvl_keff[l]) for l in range(int(self.layout.L))], dtype=torch.int16, device=d)
+        # Rows whose stored length differs from the structural one (a block mean that is exactly 0.0 at the end of
+        # an index row: about one row in 10 M at 768-D) are "exceptions": masked out of the dense filter passes and
+        # scored pair by pair.  Truly sparse data (many such rows) uses the exact path.
+        self.exc_rows = torch.empty(0, dtype=torch.int32, device=d)
+        if self.N > 0 and int(flag.item()) != 0:
+            self.exc_rows = (self.lens != self._keff).any(dim=1).nonzero().flatten().to(torch.int32)
+        self.fast_filter_ok = bool(lib.hq_filter_fast_supported(C.byref(self.layout))) and self.exc_rows.numel() <= self.MAX_EXCEPTION_ROWS
         self._xstar = torch.tensor([float(xstar_for(rag_threshold(l))) for l in range(int(self.layout.L))], dtype=torch.float32, device=d)
         self._ratio = torch.tensor([rag_ratio(l) for l in range(int(self.layout.L))], dtype=torch.float64, device=d)
         self._ratio_host = (C.c_double * 8)(*([rag_ratio(l) for l in range(int(self.layout.L))] + [1.0] * (8 - int(self.layout.L))))
+        self._thr_host = (C.c_double * 3)(*([rag_threshold(l) for l in range(min(3, int(self.layout.L)))] + [2.0] * (3 - min(3, int(self.layout.L)))))
         self._xstar_host = (C.c_float * 3)(*([float(xstar_for(rag_threshold(l))) for l in range(min(3, int(self.layout.L)))] + [0.0] * (3 - min(3, int(self.layout.L)))))
         self._filter_scratch = None
         # per-level copies of the index rows (pitch rounded to 4 floats): 48 MB for 1M x 1536, L2 resident
@@ -173,6 +182,11 @@ class EmbeddingDatabase:
                                             dev.ptr(self.tc_packed), dev.stream_ptr()))
                 check(lib.hq_filter_tc_valid(dev.ptr(self.level_norms), self.N, C.byref(self.layout), dev.ptr(self.tc_valid),
                                              self.tc_valid_pitch, dev.stream_ptr()))
+            if self.exc_rows.numel():                       # exceptional rows never pass in the tensor-core pass
+                r = self.exc_rows.to(torch.int64)
+                keep = ~torch.bitwise_left_shift(torch.ones_like(r), r & 31).to(torch.int32)
+                for w, m in zip((r >> 5).tolist(), keep.tolist()):     # a handful of rows: per-word read-modify-write
+                    self.tc_valid[:, w] &= m
 
     @property
     def num_levels(self) -> int:
@@ -308,6 +322,8 @@ def progressive_filter_fast(db: EmbeddingDatabase, q_idx: torch.Tensor, mask: to
                                  C.cast(db._lvl_ptrs, C.c_void_p), C.cast(db._lvl_pitch, C.c_void_p),
                                  dev.ptr(db.tc_packed) if use_tc else None, dev.ptr(db.tc_valid) if use_tc else None,
                                  db.tc_valid_pitch if use_tc else 0,
+                                 dev.ptr(db.lens), dev.ptr(db.exc_rows) if db.exc_rows.numel() else None, int(db.exc_rows.numel()),
+                                 C.cast(db._thr_host, C.c_void_p),
                                  dev.ptr(mask), mask.stride(0), dev.ptr(n_out), dev.ptr(counts),
                                  dev.ptr(db._filter_scratch), db._filter_scratch.numel(), dev.stream_ptr()))
     if trace is not None:

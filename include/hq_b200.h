@@ -168,8 +168,14 @@ int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, const hq_ind
                    const float* q_idx, int Q, const float* xstar, const double* ratio,
                    const float* const* lvl_rows, const int32_t* lvl_pitch,
                    const float* db_packed, const uint32_t* valid, int64_t valid_pitch,
+                   const uint16_t* lens, const int32_t* exc_rows, int n_exc, const double* thr,
                    uint32_t* mask, int64_t mask_stride, int32_t* n_out, int32_t* counts,
                    void* scratch, int64_t scratch_bytes, void* stream);
+/* exc_rows [n_exc] (device int32): rows whose stored length differs from lvl_keff at some level (a block mean
+ * that is exactly 0 at the end of an index row: ~1 row in 10 M at 768-D).  The reference normalises the query
+ * over the shorter common prefix for them (rag/search/engine.py:216-227); they are excluded from the dense
+ * passes (clear their bits in `valid`) and scored pair by pair with the exact path's arithmetic, using
+ * `lens` [N, L] and the HOST thresholds `thr` [L]; the cascade ranks them together with all other rows. */
 
 /* Tensor-core form of the threshold pass of hq_filter_fast (db_packed != NULL): the per-level
  * dot products run as ONE tcgen05 tf32 contraction per 128-query x 64-row tile with every

@@ -55,10 +55,40 @@ def test_fast_filter_equals_exact_filter(hq, N, D, Q, positive, impl):
         assert int(tf.n_out[0][0]) == max(1, int(N * 0.3))
 
 
-def test_fast_filter_falls_back_on_sparse_rows(hq):
+@pytest.mark.parametrize("impl", ["fast", "fast_fp32"])
+@pytest.mark.parametrize("N,D,positive", [(3000, 768, False), (5000, 1536, False), (3000, 768, True)])
+def test_fast_filter_handles_rows_with_short_index_rows(hq, N, D, positive, impl):
+    """Rows whose index row ends in an exact zero (stored length < structural length) make the reference take the
+    query norm over the shorter prefix: the fast filter scores them as exceptions and must still equal the exact path."""
+    from hilbert_quantization_b200.search import FilterTrace, unpack_mask
+    rng = np.random.default_rng(N + D)
+    db, qs = _data(rng, N, D, 24, positive)
+    tail = D - D // 12 if D == 768 else D - 64          # zero the cells of the last live finest-level block
+    for r in (17, 18, N // 2, N - 1):
+        db[r, tail:] = 0.0
+    db[40, D // 2:] = 0.0                               # a row that loses several trailing blocks (and coarser levels)
+    qs[3] = db[17] + 0.01 * rng.standard_normal(D).astype(np.float32)
+    qs[3, tail:] = db[17, tail:] + 0.05                 # dense query next to an exceptional row
+    d = hq.EmbeddingDatabase(db)
+    assert d.fast_filter_ok and d.exc_rows.numel() >= 5
+    tf, te = FilterTrace([], [], []), FilterTrace([], [], [])
+    i_f, s_f, m_f = hq.search_batch(d, qs, 10, return_mask=True, filter_impl=impl, trace=tf)
+    i_e, s_e, m_e = hq.search_batch(d, qs, 10, return_mask=True, filter_impl="exact", trace=te)
+    a_f, a_e = unpack_mask(m_f, N), unpack_mask(m_e, N)
+    same = (a_f == a_e).all(axis=1)
+    assert same.sum() >= len(qs) - 1, f"{(~same).sum()} queries differ"
+    exc = d.exc_rows.cpu().numpy()
+    assert np.array_equal(a_f[:, exc], a_e[:, exc])     # the exceptional rows themselves are decided identically
+    ok = torch.from_numpy(same).cuda()
+    assert torch.equal(i_f[ok], i_e[ok]) and torch.equal(s_f[ok], s_e[ok])
+    for l in range(len(tf.n_out)):
+        assert torch.equal(tf.n_out[l][ok], te.n_out[l][ok])
+
+
+def test_fast_filter_falls_back_on_sparse_data(hq):
     rng = np.random.default_rng(0)
-    db = rng.standard_normal((500, 768)).astype(np.float32)
-    db[17, 700:] = 0.0                       # a trailing zero run shortens this row's finest index row
+    db = rng.standard_normal((6000, 768)).astype(np.float32)
+    db[: 4500, 700:] = 0.0                   # most rows end in a zero run: more exceptions than the fast path takes
     d = hq.EmbeddingDatabase(db)
     assert not d.fast_filter_ok
     with pytest.raises(ValueError, match="fast filter"):
