@@ -604,10 +604,14 @@ __device__ __forceinline__ void rank_cut_bin(const float* b_key, const uint32_t*
 // of that bin into 2048 sub-bins (large shards put thousands of candidates into one bin).  `for_each(visit)`
 // must call visit(key, token) for every candidate of the calling thread, `row_of(token)` returns its row id.
 // Returns false when three rounds cannot isolate the boundary (heavily tied keys): the caller falls back.
-struct BinStack { float lo[3], scale[3]; uint32_t cb[3]; int depth; };
+// (scalars, not arrays: indexing arrays by the round number put the struct into local memory and an LDL into
+// the per-candidate loops)
+struct BinStack { float lo0, lo1, lo2, sc0, sc1, sc2; uint32_t cb0, cb1, cb2; int depth; };
 __device__ __forceinline__ bool in_bins(const BinStack& s, float k) {
     bool ok = true;
-    for (int d = 0; d < s.depth; ++d) ok = ok && lin_bin(k, s.lo[d], s.scale[d]) == s.cb[d];
+    if (s.depth > 0) ok = lin_bin(k, s.lo0, s.sc0) == s.cb0;
+    if (s.depth > 1) ok = ok && lin_bin(k, s.lo1, s.sc1) == s.cb1;
+    if (s.depth > 2) ok = ok && lin_bin(k, s.lo2, s.sc2) == s.cb2;
     return ok;
 }
 
@@ -616,8 +620,7 @@ __device__ __forceinline__ bool select_boundary(ForEach for_each, RowOf row_of, 
                                                 uint32_t* hist, uint32_t* sh, float* b_key, uint32_t* b_row, uint32_t* s_bufn,
                                                 float* s_K, uint32_t* s_R, Boundary& out) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    BinStack st;
-    st.depth = 0;
+    BinStack st{};
     float cur_lo = lo, cur_hi = hi;
     for (int round = 0; round < 3; ++round) {
         const float scale = cur_hi > cur_lo ? 2048.0f / (cur_hi - cur_lo) : 0.f;
@@ -632,8 +635,10 @@ __device__ __forceinline__ bool select_boundary(ForEach for_each, RowOf row_of, 
         }
         find_cut_bin(hist, drop, sh);
         const uint32_t cb = sh[0], r_in_bin = sh[1], n_in_bin = sh[2];
-        st.lo[st.depth] = cur_lo; st.scale[st.depth] = scale; st.cb[st.depth] = cb;
-        ++st.depth;
+        if (round == 0) { st.lo0 = cur_lo; st.sc0 = scale; st.cb0 = cb; }
+        else if (round == 1) { st.lo1 = cur_lo; st.sc1 = scale; st.cb1 = cb; }
+        else { st.lo2 = cur_lo; st.sc2 = scale; st.cb2 = cb; }
+        st.depth = round + 1;
         if (n_in_bin <= (uint32_t)kCutCap) {
             if (tid == 0) *s_bufn = 0;
             __syncthreads();
@@ -806,17 +811,27 @@ __global__ void __launch_bounds__(kListThreads, 1) k_filter_cascade_lists(const 
                     k1[u] = ok ? __ldcs(L_k1 + off + e0 + u * 32) : 0.f;
                     k2[u] = ok ? __ldcs(L_k2 + off + e0 + u * 32) : 0.f;
                 }
+                // one shared-memory reservation per batch of kU x 32 candidates (not one per 32)
+                uint32_t bal[kU], total = 0;
+                bool take[kU];
 #pragma unroll
                 for (int u = 0; u < kU; ++u) {
-                    if ((e0 - lane) + u * 32 >= n) break;                             // whole warp beyond its range
-                    const uint32_t row = rw[u] & 0x7fffffffu;
-                    const bool take = (rw[u] >> 31) && kept_by(b1, k1[u], row);
-                    const uint32_t slot = compact_slot(take, &s_n2);
-                    if (take) {
+                    take[u] = (rw[u] >> 31) && kept_by(b1, k1[u], rw[u] & 0x7fffffffu);
+                    bal[u] = __ballot_sync(0xffffffffu, take[u]);
+                    total += (uint32_t)__popc(bal[u]);
+                }
+                uint32_t base = 0;
+                if (lane == 0 && total) base = atomicAdd(&s_n2, total);
+                base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    if (take[u]) {
+                        const uint32_t slot = base + (uint32_t)__popc(bal[u] & ((1u << lane) - 1u));
                         c_k2[slot] = k2[u];
-                        c_row[slot] = row;
+                        c_row[slot] = rw[u] & 0x7fffffffu;
                         atomicAdd(&hist[lin_bin(k2[u], lo2, scale2)], 1u);
                     }
+                    base += (uint32_t)__popc(bal[u]);
                 }
             }
         }
