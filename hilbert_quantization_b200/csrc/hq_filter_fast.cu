@@ -543,7 +543,9 @@ struct ListParams {
 constexpr int kMaxSegs = 320;
 constexpr int kCutCap = 2048;
 constexpr int kListThreads = 1024;    // one query per SM at a time (two 512-thread CTAs per SM measured 7 % slower)
-constexpr int kU = 4;                 // independent list loads in flight per thread
+constexpr int kU = 4;                 // independent list loads in flight per thread (128-bit each in the list passes)
+constexpr int kU2 = 2;                // same for the compaction pass, which reads three arrays
+constexpr uint32_t kChunk = kU * 128, kChunk2 = kU2 * 128;      // entries a warp takes at a time
 
 struct Boundary { float K; uint32_t R; };      // kept <=> k > K || (k == K && row < R)
 __device__ __forceinline__ bool kept_by(const Boundary& b, float k, uint32_t row) { return k > b.K || (k == b.K && row < b.R); }
@@ -716,6 +718,8 @@ __global__ void __launch_bounds__(kListThreads, 1) k_filter_cascade_lists(const 
             continue;
         }
         const int64_t qbase = (int64_t)q * p.n_segs * p.seg_cap;
+        const uint32_t cps = ((uint32_t)p.seg_cap + kChunk - 1) / kChunk, n_items = (uint32_t)p.n_segs * cps;
+        const uint32_t cps2 = ((uint32_t)p.seg_cap + kChunk2 - 1) / kChunk2, n_items2 = (uint32_t)p.n_segs * cps2;
         const uint32_t* const L_rows = p.l_rows + qbase;
         const float* const L_k1 = p.l_k1 + qbase;
         const float* const L_k2 = p.l_k2 ? p.l_k2 + qbase : nullptr;
@@ -726,19 +730,27 @@ __global__ void __launch_bounds__(kListThreads, 1) k_filter_cascade_lists(const 
         Boundary b1;
         b1.K = -INFINITY; b1.R = 0;
         bool failed = false;
-        // every candidate of the query: a warp owns half a segment at a time, kU independent loads per lane
+        // every candidate of the query: a warp owns one chunk of a segment at a time (kU x 128 entries), each lane
+        // issues kU independent 128-bit loads (4-byte loads kept only 16 KB in flight per SM: latency bound)
         auto each_l1 = [&](auto visit) {
-            for (int item = warp; item < 2 * p.n_segs; item += nw) {
-                const uint32_t cnt = (uint32_t)s_cnt[item >> 1], mid = min(cnt, ((cnt >> 1) + 31u) & ~31u);
-                const uint32_t lo_e = (item & 1) ? mid : 0u, n = (item & 1) ? cnt : mid;
-                const uint32_t off = (uint32_t)(item >> 1) * (uint32_t)p.seg_cap;
-                for (uint32_t e0 = lo_e + lane; e0 - lane < n; e0 += kU * 32) {
-                    float k[kU];
+            for (uint32_t item = warp; item < n_items; item += nw) {
+                const uint32_t seg = item / cps, e_base = (item - seg * cps) * kChunk;
+                const uint32_t cnt = (uint32_t)s_cnt[seg];
+                if (e_base >= cnt) continue;
+                const uint32_t off = seg * (uint32_t)p.seg_cap;
+                float4 k[kU];
 #pragma unroll
-                    for (int u = 0; u < kU; ++u) k[u] = e0 + u * 32 < n ? __ldg(L_k1 + off + e0 + u * 32) : -1.0f;
+                for (int u = 0; u < kU; ++u) {
+                    const uint32_t e = e_base + u * 128 + lane * 4;
+                    k[u] = e < cnt ? __ldg(reinterpret_cast<const float4*>(L_k1 + off + e)) : make_float4(-1.f, -1.f, -1.f, -1.f);
+                }
 #pragma unroll
-                    for (int u = 0; u < kU; ++u)
-                        if (e0 + u * 32 < n) visit(k[u], off + e0 + u * 32);
+                for (int u = 0; u < kU; ++u) {
+                    const uint32_t e = e_base + u * 128 + lane * 4;
+                    if (e < cnt) visit(k[u].x, off + e);
+                    if (e + 1 < cnt) visit(k[u].y, off + e + 1);
+                    if (e + 2 < cnt) visit(k[u].z, off + e + 2);
+                    if (e + 3 < cnt) visit(k[u].w, off + e + 3);
                 }
             }
         };
@@ -763,24 +775,29 @@ __global__ void __launch_bounds__(kListThreads, 1) k_filter_cascade_lists(const 
         }
         uint32_t* M = p.mask + (int64_t)q * p.mask_stride;
         if (p.L == 2) {
-            for (int item = warp; item < 2 * p.n_segs; item += nw) {       // a warp owns half a segment at a time
-                const uint32_t cnt = (uint32_t)s_cnt[item >> 1], mid = min(cnt, ((cnt >> 1) + 31u) & ~31u);
-                const uint32_t lo_e = (item & 1) ? mid : 0u, n = (item & 1) ? cnt : mid;
-                const uint32_t off = (uint32_t)(item >> 1) * (uint32_t)p.seg_cap;
-                for (uint32_t e0 = lo_e + lane; e0 - lane < n; e0 += kU * 32) {      // warp-uniform trip count
-
-                    float k[kU];
-                    uint32_t rw[kU];
+            for (uint32_t item = warp; item < n_items; item += nw) {
+                const uint32_t seg = item / cps, e_base = (item - seg * cps) * kChunk;
+                const uint32_t cnt = (uint32_t)s_cnt[seg];
+                if (e_base >= cnt) continue;
+                const uint32_t off = seg * (uint32_t)p.seg_cap;
+                float4 k[kU];
+                uint4 rw[kU];
 #pragma unroll
-                    for (int u = 0; u < kU; ++u) {
-                        const bool ok = e0 + u * 32 < n;
-                        k[u] = ok ? __ldcs(L_k1 + off + e0 + u * 32) : -INFINITY;
-                        rw[u] = ok ? __ldcs(L_rows + off + e0 + u * 32) : 0u;
-                    }
+                for (int u = 0; u < kU; ++u) {
+                    const uint32_t e = e_base + u * 128 + lane * 4;
+                    const bool ok = e < cnt;
+                    k[u] = ok ? __ldcs(reinterpret_cast<const float4*>(L_k1 + off + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    rw[u] = ok ? __ldcs(reinterpret_cast<const uint4*>(L_rows + off + e)) : make_uint4(0u, 0u, 0u, 0u);
+                }
 #pragma unroll
-                    for (int u = 0; u < kU; ++u) {
-                        const uint32_t row = rw[u] & 0x7fffffffu;
-                        if (e0 + u * 32 < n && kept_by(b1, k[u], row)) atomicOr(&M[row >> 5], 1u << (row & 31));
+                for (int u = 0; u < kU; ++u) {
+                    const uint32_t e = e_base + u * 128 + lane * 4;
+                    const float kk[4] = {k[u].x, k[u].y, k[u].z, k[u].w};
+                    const uint32_t rr[4] = {rw[u].x, rw[u].y, rw[u].z, rw[u].w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t row = rr[i] & 0x7fffffffu;
+                        if (e + i < cnt && kept_by(b1, kk[i], row)) atomicOr(&M[row >> 5], 1u << (row & 31));
                     }
                 }
             }
@@ -796,43 +813,55 @@ __global__ void __launch_bounds__(kListThreads, 1) k_filter_cascade_lists(const 
         for (int i = tid; i < 2048; i += nt) hist[i] = 0;
         if (tid == 0) s_bufn = 0;
         __syncthreads();
-        for (int item = warp; item < 2 * p.n_segs; item += nw) {       // a warp owns half a segment at a time
-            const uint32_t cnt = (uint32_t)s_cnt[item >> 1], mid = min(cnt, ((cnt >> 1) + 31u) & ~31u);
-            const uint32_t lo_e = (item & 1) ? mid : 0u, n = (item & 1) ? cnt : mid;
-            const uint32_t off = (uint32_t)(item >> 1) * (uint32_t)p.seg_cap;
-            for (uint32_t e0 = lo_e + lane; e0 - lane < n; e0 += kU * 32) {      // warp-uniform trip count
-
-                float k1[kU], k2[kU];
-                uint32_t rw[kU];
+        for (uint32_t item = warp; item < n_items2; item += nw) {       // chunks of kU2 x 128 entries (three arrays are read)
+            const uint32_t seg = item / cps2, e_base = (item - seg * cps2) * kChunk2;
+            const uint32_t cnt = (uint32_t)s_cnt[seg];
+            if (e_base >= cnt) continue;
+            const uint32_t off = seg * (uint32_t)p.seg_cap;
+            float4 k1[kU2], k2[kU2];
+            uint4 rw[kU2];
 #pragma unroll
-                for (int u = 0; u < kU; ++u) {
-                    const bool ok = e0 + u * 32 < n;
-                    rw[u] = ok ? __ldcs(L_rows + off + e0 + u * 32) : 0u;            // bit 31 clear -> not a candidate
-                    k1[u] = ok ? __ldcs(L_k1 + off + e0 + u * 32) : 0.f;
-                    k2[u] = ok ? __ldcs(L_k2 + off + e0 + u * 32) : 0.f;
-                }
-                // one shared-memory reservation per batch of kU x 32 candidates (not one per 32)
-                uint32_t bal[kU], total = 0;
-                bool take[kU];
+            for (int u = 0; u < kU2; ++u) {
+                const uint32_t e = e_base + u * 128 + lane * 4;
+                const bool ok = e < cnt;
+                rw[u] = ok ? __ldcs(reinterpret_cast<const uint4*>(L_rows + off + e)) : make_uint4(0u, 0u, 0u, 0u);
+                k1[u] = ok ? __ldcs(reinterpret_cast<const float4*>(L_k1 + off + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                k2[u] = ok ? __ldcs(reinterpret_cast<const float4*>(L_k2 + off + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            // one shared-memory reservation per batch of kU2 x 128 candidates
+            uint32_t bal[kU2 * 4], total = 0;
+            bool take[kU2 * 4];
+            float kk2[kU2 * 4];
+            uint32_t rr[kU2 * 4];
 #pragma unroll
-                for (int u = 0; u < kU; ++u) {
-                    take[u] = (rw[u] >> 31) && kept_by(b1, k1[u], rw[u] & 0x7fffffffu);
-                    bal[u] = __ballot_sync(0xffffffffu, take[u]);
-                    total += (uint32_t)__popc(bal[u]);
-                }
-                uint32_t base = 0;
-                if (lane == 0 && total) base = atomicAdd(&s_n2, total);
-                base = __shfl_sync(0xffffffffu, base, 0);
+            for (int u = 0; u < kU2; ++u) {
+                const uint32_t e = e_base + u * 128 + lane * 4;
+                const float a1[4] = {k1[u].x, k1[u].y, k1[u].z, k1[u].w};
+                const float a2[4] = {k2[u].x, k2[u].y, k2[u].z, k2[u].w};
+                const uint32_t ar[4] = {rw[u].x, rw[u].y, rw[u].z, rw[u].w};
 #pragma unroll
-                for (int u = 0; u < kU; ++u) {
-                    if (take[u]) {
-                        const uint32_t slot = base + (uint32_t)__popc(bal[u] & ((1u << lane) - 1u));
-                        c_k2[slot] = k2[u];
-                        c_row[slot] = rw[u] & 0x7fffffffu;
-                        atomicAdd(&hist[lin_bin(k2[u], lo2, scale2)], 1u);
-                    }
-                    base += (uint32_t)__popc(bal[u]);
+                for (int i = 0; i < 4; ++i) {
+                    const int s = u * 4 + i;
+                    kk2[s] = a2[i];
+                    rr[s] = ar[i] & 0x7fffffffu;
+                    // bit 31 clear -> fails the level-2 threshold; entries past the end of the segment are stale data
+                    take[s] = e + i < cnt && (ar[i] >> 31) && kept_by(b1, a1[i], rr[s]);
+                    bal[s] = __ballot_sync(0xffffffffu, take[s]);
+                    total += (uint32_t)__popc(bal[s]);
                 }
+            }
+            uint32_t base = 0;
+            if (lane == 0 && total) base = atomicAdd(&s_n2, total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+            for (int s = 0; s < kU2 * 4; ++s) {
+                if (take[s]) {
+                    const uint32_t slot = base + (uint32_t)__popc(bal[s] & ((1u << lane) - 1u));
+                    c_k2[slot] = kk2[s];
+                    c_row[slot] = rr[s];
+                    atomicAdd(&hist[lin_bin(kk2[s], lo2, scale2)], 1u);
+                }
+                base += (uint32_t)__popc(bal[s]);
             }
         }
         __syncthreads();

@@ -40,7 +40,7 @@ constexpr uint32_t ACC_COLS = 3 * FR;          // one accumulator set: 3 levels 
 constexpr uint32_t F_TMEM_COLS = 512;
 constexpr uint32_t kIdescTf32 = make_idesc(2 /*tf32*/, FM, FR);
 constexpr int TILE_GROUP = 4;                  // tiles per flush: 8 words = one 32-byte sector per query and level
-constexpr int STAGE_PITCH = 2 * TILE_GROUP + 1;
+constexpr int STAGE_WORDS = 3 * 2 * FM * 4;      // pass words of one flush group: [level][chunk of 4 words][query][4]
 constexpr int LBUF = 16;                       // per-thread staging slots of the candidate lists (flushed 8 at a time)
 
 struct Segs {
@@ -77,6 +77,7 @@ struct FtcParams {
     int64_t valid_pitch;
     uint32_t* bits;             // [L][Q][bits_pitch]
     int64_t words, bits_pitch;
+    int bits_vec;               // planes are 32-byte aligned with a pitch of whole sectors: 256-bit stores
     // optional candidate lists (L >= 2): rows passing levels 0 and 1, one private segment per
     // (query, row range, tile half) so that no atomics are needed and rows stay ascending
     uint32_t* l_rows;           // [Q][n_segs][seg_cap]  row | (passes level 2) << 31
@@ -115,8 +116,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* smem_a = smem;                                        // query tile, resident for a unit
     uint8_t* smem_b = smem + A_BYTES;                              // F_STAGES database tiles
-    uint32_t* s_stage = reinterpret_cast<uint32_t*>(smem_b + F_STAGES * B_STAGE_BYTES);   // [3][128][STAGE_PITCH]
-    uint32_t* s_lists = s_stage + ((3 * FM * STAGE_PITCH + 3) & ~3);                      // [3][LBUF][EPI_THREADS]
+    uint32_t* s_stage = reinterpret_cast<uint32_t*>(smem_b + F_STAGES * B_STAGE_BYTES);   // [3][2][128][4]
+    uint32_t* s_lists = s_stage + STAGE_WORDS;                                            // [3][LBUF][EPI_THREADS]
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_lists + 3 * LBUF * EPI_THREADS);
     uint64_t* full_bar = bars;                      // [F_STAGES]
     uint64_t* empty_bar = bars + F_STAGES;          // [F_STAGES]
@@ -155,11 +156,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
                 const int m_tile = u % p.m_tiles, range = u / p.m_tiles;
                 const int t0 = range * p.tiles_per_range;
                 const int t1 = min(p.n_tiles, t0 + p.tiles_per_range);
-                mbar_wait(qempty_bar, (uq & 1u) ^ 1u);                  // MMAs of the previous unit have retired
+                mbar_wait_relaxed(qempty_bar, (uq & 1u) ^ 1u);                  // MMAs of the previous unit have retired
                 mbar_expect_tx(qfull_bar, (uint32_t)p.n_slabs * A_SLAB_BYTES);
                 for (int s = 0; s < p.n_slabs; ++s) tma_load_2d(&map_q, qfull_bar, smem_a + s * A_SLAB_BYTES, s * 32, m_tile * FM);
                 for (int t = t0; t < t1; ++t) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], (uint32_t)p.n_slabs * B_SLAB_BYTES);
                     for (int s = 0; s < p.n_slabs; ++s)
                         tma_load_2d(&map_db, &full_bar[stage], smem_b + stage * B_STAGE_BYTES + s * B_SLAB_BYTES, s * 32, t * FR);
@@ -174,12 +175,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
             const int range = u / p.m_tiles;
             const int t0 = range * p.tiles_per_range;
             const int t1 = min(p.n_tiles, t0 + p.tiles_per_range);
-            mbar_wait(qfull_bar, uq & 1u);
+            mbar_wait_relaxed(qfull_bar, uq & 1u);
             tc_fence_after();
             for (int t = t0; t < t1; ++t, ++it) {
                 const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-                mbar_wait(&full_bar[stage], phase);
+                mbar_wait_relaxed(&tempty_bar[acc], acc_phase ^ 1);
+                mbar_wait_relaxed(&full_bar[stage], phase);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t a0 = smem_u32(smem_a), b0 = smem_u32(smem_b + stage * B_STAGE_BYTES);
@@ -242,16 +243,16 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
                 mbar_arrive(&tempty_bar[acc]);           // the values are in registers: the accumulators are free
                 uint32_t w0 = pass_word(r0, tq[0]) & vw[0], w1 = 0, w2 = 0;
                 if (!(tq[0] == tq[0])) w0 = 0;
-                s_stage[(0 * FM + q_in) * STAGE_PITCH + tl * 2 + half] = w0;
+                s_stage[((0 * 2 + (tl >> 1)) * FM + q_in) * 4 + (tl & 1) * 2 + half] = w0;
                 if (p.L > 1) {
                     w1 = pass_word(r1, tq[1]) & vw[1];
                     if (!(tq[1] == tq[1])) w1 = 0;
-                    s_stage[(1 * FM + q_in) * STAGE_PITCH + tl * 2 + half] = w1;
+                    s_stage[((1 * 2 + (tl >> 1)) * FM + q_in) * 4 + (tl & 1) * 2 + half] = w1;
                 }
                 if (p.L > 2) {
                     w2 = pass_word(r2, tq[2]) & vw[2];
                     if (!(tq[2] == tq[2])) w2 = 0;
-                    s_stage[(2 * FM + q_in) * STAGE_PITCH + tl * 2 + half] = w2;
+                    s_stage[((2 * 2 + (tl >> 1)) * FM + q_in) * 4 + (tl & 1) * 2 + half] = w2;
                 }
                 if (lists) {
                     // Rows that pass the level-0 and level-1 thresholds.  Entries are staged in per-thread
@@ -261,28 +262,30 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
                     const uint32_t t1w = w0 & w1;
                     if (t1w) {
                         const uint32_t row0 = (uint32_t)t * FR + (uint32_t)half * 32u;
-                        const uint32_t pos0 = (uint32_t)seg_pos;
+                        uint32_t run = (uint32_t)seg_pos << 10;        // entry counter in units of one ring slot (1024 B)
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
-                            // Branch-free appends: the slot of bit j follows from a prefix popcount, so the 32
-                            // blocks are independent (the first version chained them through seg_pos and a
-                            // branch per bit: 1235 instructions per thread and tile at 1.7 IPC).
+                            // Branch-free appends: every bit position is visited with predicated stores; the ring slot
+                            // comes from a running predicated counter (a prefix popcount per bit cost 4 more
+                            // instructions; a branch per bit ran at 1.7 IPC).
 #pragma unroll
                             for (int jj = 0; jj < 8; ++jj) {
                                 const int j = g * 8 + jj;
                                 const uint32_t bit = t1w & (1u << j);
-                                const uint32_t sl = (pos0 + (uint32_t)__popc(t1w & ((1u << j) - 1u))) & (LBUF - 1);
-                                const uint32_t addr = sl_addr + sl * (EPI_THREADS * 4);
+                                const uint32_t addr = sl_addr + (run & ((LBUF - 1) << 10));
                                 const uint32_t roww = (row0 + j) | ((w2 << (31 - j)) & 0x80000000u);
                                 asm volatile(
-                                    "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t"
-                                    "@p st.shared.u32 [%1], %2;\n\t"
-                                    "@p st.shared.u32 [%1+%5], %3;\n\t"
-                                    "@p st.shared.u32 [%1+%6], %4;\n\t}" ::"r"(bit),
-                                    "r"(addr), "r"(roww), "r"(r1[j]), "r"(r2[j]), "n"(LBUF * EPI_THREADS * 4), "n"(2 * LBUF * EPI_THREADS * 4)
+                                    "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t"
+                                    "@p st.shared.u32 [%2], %3;\n\t"
+                                    "@p st.shared.u32 [%2+%6], %4;\n\t"
+                                    "@p st.shared.u32 [%2+%7], %5;\n\t"
+                                    "@p add.u32 %0, %0, 1024;\n\t}"
+                                    : "+r"(run)
+                                    : "r"(bit), "r"(addr), "r"(roww), "r"(r1[j]), "r"(r2[j]), "n"(LBUF * EPI_THREADS * 4),
+                                      "n"(2 * LBUF * EPI_THREADS * 4)
                                     : "memory");
                             }
-                            seg_pos = (int)(pos0 + (uint32_t)__popc(g == 3 ? t1w : (t1w & ((1u << (8 * (g + 1))) - 1u))));
+                            seg_pos = (int)(run >> 10);
                             if (seg_pos - seg_flushed >= 8) {
                                 if (seg_flushed + 8 <= p.seg_cap) {
                                     const int f = seg_flushed & (LBUF - 1);
@@ -307,13 +310,24 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
                     asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
                     const int64_t wb = 2 * (int64_t)(t - tl);
                     const int n_w = 2 * (tl + 1);
-                    for (int e = et; e < 3 * FM * 2 * TILE_GROUP; e += EPI_THREADS) {
-                        const int l = e / (FM * 2 * TILE_GROUP);
-                        const int qq = (e / (2 * TILE_GROUP)) % FM;
-                        const int wi = e % (2 * TILE_GROUP);
+                    // one (level, query) row of the group per thread: two 128-bit reads, one 32-byte sector out
+                    // (word-by-word copies were 10 % of the kernel's instructions)
+                    for (int e = et; e < 3 * FM; e += EPI_THREADS) {
+                        const int l = e / FM, qq = e % FM;
                         const int gq = m_tile * FM + qq;
-                        if (l < p.L && gq < p.Q && wi < n_w && wb + wi < p.words)
-                            p.bits[((int64_t)l * p.Q + gq) * p.bits_pitch + wb + wi] = s_stage[(l * FM + qq) * STAGE_PITCH + wi];
+                        if (l < p.L && gq < p.Q) {
+                            const uint4 a = *reinterpret_cast<const uint4*>(s_stage + ((l * 2 + 0) * FM + qq) * 4);
+                            const uint4 b = *reinterpret_cast<const uint4*>(s_stage + ((l * 2 + 1) * FM + qq) * 4);
+                            const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                            uint32_t* dst = p.bits + ((int64_t)l * p.Q + gq) * p.bits_pitch + wb;
+                            if (p.bits_vec && n_w == 8 && wb + 8 <= p.words) {
+                                st_global_256(dst, v);
+                            } else {
+#pragma unroll
+                                for (int wi = 0; wi < 8; ++wi)
+                                    if (wi < n_w && wb + wi < p.words) dst[wi] = v[wi];
+                            }
+                        }
                     }
                     asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
                 }
@@ -504,6 +518,7 @@ int hq_filter_bits_tc_launch(const float* db_packed, const uint32_t* valid, int6
     p.N = N; p.Q = Q; p.L = s.L; p.n_slabs = s.n_slabs;
     for (int l = 0; l < 3; ++l) { p.seg_off[l] = s.off[l]; p.ksteps[l] = 3 * s.kp[l] / 8; }
     p.tq = tq; p.valid = valid; p.valid_pitch = valid_pitch; p.bits = bits; p.words = words; p.bits_pitch = bits_pitch;
+    p.bits_vec = ((reinterpret_cast<uintptr_t>(bits) & 31) == 0 && bits_pitch % 8 == 0) ? 1 : 0;
     plan_units(N, Q, hq_cached_sm_count(), p);
     if (lists && lists->rows) {
         HQ_REQUIRE(lists->n_segs >= 2 * p.n_ranges && lists->n_segs <= 2 * p.n_ranges + 1 && lists->seg_cap > 0 && lists->k1 && lists->seg_n && (s.L < 3 || lists->k2),
@@ -516,7 +531,7 @@ int hq_filter_bits_tc_launch(const float* db_packed, const uint32_t* valid, int6
     if (rc != HQ_OK) return rc;
     rc = make_map_2d(&mdb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, db_packed, N, KS, KS, 32, FR);
     if (rc != HQ_OK) return rc;
-    const size_t smem = 1024 + A_BYTES + F_STAGES * B_STAGE_BYTES + (3 * FM * STAGE_PITCH + 4 + 3 * LBUF * EPI_THREADS) * sizeof(uint32_t) +
+    const size_t smem = 1024 + A_BYTES + F_STAGES * B_STAGE_BYTES + (STAGE_WORDS + 3 * LBUF * EPI_THREADS) * sizeof(uint32_t) +
                         (2 * F_STAGES + 6) * sizeof(uint64_t) + 16;
     static bool attr = false;
     if (!attr) {
