@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
     uint8_t* smem_a = smem;                                        // query tile, resident for a unit
     uint8_t* smem_b = smem + A_BYTES;                              // F_STAGES database tiles
     uint32_t* s_stage = reinterpret_cast<uint32_t*>(smem_b + F_STAGES * B_STAGE_BYTES);   // [3][2][128][4]
-    uint32_t* s_lists = s_stage + STAGE_WORDS;                                            // [3][LBUF][EPI_THREADS]
+    uint32_t* s_lists = s_stage + STAGE_WORDS;                                            // [3][EPI_THREADS][LBUF], 16-byte chunks swizzled
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_lists + 3 * LBUF * EPI_THREADS);
     uint64_t* full_bar = bars;                      // [F_STAGES]
     uint64_t* empty_bar = bars + F_STAGES;          // [F_STAGES]
@@ -223,8 +223,14 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
             const bool lists = p.l_rows != nullptr && p.L >= 2 && q_ok;
             const int64_t seg_base = ((int64_t)q * p.n_segs + (range * 2 + half)) * p.seg_cap;
             int seg_pos = 0, seg_flushed = 0;
-            uint32_t* const sl_base = s_lists + et;
-            const uint32_t sl_addr = smem_u32(sl_base);
+            // Per-thread ring of LBUF entries per array, 64 bytes per thread, so that a flush reads its eight
+            // entries with two 128-bit loads per array (8 scalar loads per array made the flush 22 % of the
+            // kernel's instructions).  The 16-byte chunk index is XORed with (lane >> 1) & 3: the eight lanes of
+            // a quarter warp then hit eight different bank groups.
+            constexpr uint32_t RING_A_BYTES = EPI_THREADS * LBUF * 4;
+            const uint32_t swz16 = (uint32_t)((lane >> 1) & 3) << 4;
+            const uint32_t sl_addr = smem_u32(s_lists + et * LBUF);             // 64-byte aligned
+            const uint32_t sl_addr_x = sl_addr ^ swz16;
             for (int t = t0; t < t1; ++t, ++it) {
                 const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
                 const int tl = (t - t0) & (TILE_GROUP - 1);
@@ -262,7 +268,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
                     const uint32_t t1w = w0 & w1;
                     if (t1w) {
                         const uint32_t row0 = (uint32_t)t * FR + (uint32_t)half * 32u;
-                        uint32_t run = (uint32_t)seg_pos << 10;        // entry counter in units of one ring slot (1024 B)
+                        uint32_t run = (uint32_t)seg_pos << 2;         // entry counter in bytes of one ring array
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
                             // Branch-free appends: every bit position is visited with predicated stores; the ring slot
@@ -272,29 +278,29 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
                             for (int jj = 0; jj < 8; ++jj) {
                                 const int j = g * 8 + jj;
                                 const uint32_t bit = t1w & (1u << j);
-                                const uint32_t addr = sl_addr + (run & ((LBUF - 1) << 10));
+                                const uint32_t addr = sl_addr_x ^ (run & (LBUF * 4 - 1));
                                 const uint32_t roww = (row0 + j) | ((w2 << (31 - j)) & 0x80000000u);
                                 asm volatile(
                                     "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t"
                                     "@p st.shared.u32 [%2], %3;\n\t"
                                     "@p st.shared.u32 [%2+%6], %4;\n\t"
                                     "@p st.shared.u32 [%2+%7], %5;\n\t"
-                                    "@p add.u32 %0, %0, 1024;\n\t}"
+                                    "@p add.u32 %0, %0, 4;\n\t}"
                                     : "+r"(run)
-                                    : "r"(bit), "r"(addr), "r"(roww), "r"(r1[j]), "r"(r2[j]), "n"(LBUF * EPI_THREADS * 4),
-                                      "n"(2 * LBUF * EPI_THREADS * 4)
+                                    : "r"(bit), "r"(addr), "r"(roww), "r"(r1[j]), "r"(r2[j]), "n"(RING_A_BYTES), "n"(2 * RING_A_BYTES)
                                     : "memory");
                             }
-                            seg_pos = (int)(run >> 10);
+                            seg_pos = (int)(run >> 2);
                             if (seg_pos - seg_flushed >= 8) {
                                 if (seg_flushed + 8 <= p.seg_cap) {
-                                    const int f = seg_flushed & (LBUF - 1);
+                                    const uint32_t f0 = sl_addr_x ^ (((uint32_t)seg_flushed * 4u) & (LBUF * 4 - 1));   // chunk of entries f..f+3
+                                    const uint32_t f1 = f0 ^ 16u;                                                      // f+4..f+7 (f is a multiple of 8)
 #pragma unroll
                                     for (int a = 0; a < 3; ++a) {
                                         if (a == 2 && p.L < 3) break;
                                         uint32_t v[8];
-#pragma unroll
-                                        for (int i = 0; i < 8; ++i) v[i] = sl_base[(a * LBUF + f + i) * EPI_THREADS];
+                                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(f0 + a * RING_A_BYTES));
+                                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(f1 + a * RING_A_BYTES));
                                         uint32_t* dst = (a == 0 ? p.l_rows : (a == 1 ? reinterpret_cast<uint32_t*>(p.l_k1)
                                                                                      : reinterpret_cast<uint32_t*>(p.l_k2))) +
                                                         seg_base + seg_flushed;
@@ -335,10 +341,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
             if (lists) {
                 // tail of the segment (< 8 entries)
                 for (int e = seg_flushed; e < seg_pos && e < p.seg_cap; ++e) {
-                    const int sl = e & (LBUF - 1);
-                    p.l_rows[seg_base + e] = sl_base[(0 * LBUF + sl) * EPI_THREADS];
-                    p.l_k1[seg_base + e] = __uint_as_float(sl_base[(1 * LBUF + sl) * EPI_THREADS]);
-                    if (p.L > 2) p.l_k2[seg_base + e] = __uint_as_float(sl_base[(2 * LBUF + sl) * EPI_THREADS]);
+                    const uint32_t* sl = s_lists + et * LBUF + (((((uint32_t)e * 4u) & (LBUF * 4 - 1)) ^ swz16) >> 2);
+                    p.l_rows[seg_base + e] = sl[0];
+                    p.l_k1[seg_base + e] = __uint_as_float(sl[RING_A_BYTES / 4]);
+                    if (p.L > 2) p.l_k2[seg_base + e] = __uint_as_float(sl[2 * RING_A_BYTES / 4]);
                 }
                 p.seg_n[(int64_t)q * p.n_segs + range * 2 + half] = seg_pos;
             }
