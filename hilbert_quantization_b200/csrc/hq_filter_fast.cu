@@ -844,8 +844,9 @@ __global__ void __launch_bounds__(kListThreads, 1) k_filter_cascade_lists(const 
                     const int s = u * 4 + i;
                     kk2[s] = a2[i];
                     rr[s] = ar[i] & 0x7fffffffu;
-                    // bit 31 clear -> fails the level-2 threshold; entries past the end of the segment are stale data
-                    take[s] = e + i < cnt && (ar[i] >> 31) && kept_by(b1, a1[i], rr[s]);
+                    // k2 < tq fails the level-2 threshold (the same fp32 comparison as the threshold pass; false for a
+                    // NaN threshold); entries past the end of the segment are stale data
+                    take[s] = e + i < cnt && a2[i] >= lo2 && kept_by(b1, a1[i], rr[s]);
                     bal[s] = __ballot_sync(0xffffffffu, take[s]);
                     total += (uint32_t)__popc(bal[s]);
                 }
@@ -934,6 +935,7 @@ struct ExcParams {
     uint32_t* bits;
     int64_t bits_pitch;
     const float* nq;             // [3][Q] full query level norms
+    const float* tq;             // [3][Q] thresholds in dot-product units (needed with lists)
     uint32_t* l_rows;            // lists (optional)
     float* l_k1;
     float* l_k2;
@@ -977,9 +979,13 @@ __global__ void __launch_bounds__(128) k_filter_exceptions(const ExcParams p) {
         const int pos = atomicAdd(p.seg_n + (int64_t)q * p.n_segs + p.extra_seg, 1);
         if (pos < p.seg_cap) {
             const int64_t a = ((int64_t)q * p.n_segs + p.extra_seg) * p.seg_cap + pos;
-            p.l_rows[a] = (uint32_t)row | ((L > 2 && pass[2]) ? 0x80000000u : 0u);
+            p.l_rows[a] = (uint32_t)row;
             p.l_k1[a] = keq[1];
-            if (L > 2) p.l_k2[a] = keq[2];
+            if (L > 2) {
+                // the cascade repeats the level-2 test as k2 >= tq[2]: make the key say what the exact score said
+                const float t2 = __ldg(p.tq + (int64_t)2 * p.Q + q);
+                p.l_k2[a] = pass[2] ? fmaxf(keq[2], t2) : -INFINITY;
+            }
         }
     }
 }
@@ -1133,7 +1139,7 @@ extern "C" int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, c
         }
         if (lg.on) {
             ep.l_rows = lists.rows; ep.l_k1 = lists.k1; ep.l_k2 = lists.k2; ep.seg_n = lists.seg_n; ep.seg_cap = lists.seg_cap;
-            ep.n_segs = lists.n_segs; ep.extra_seg = lists.n_segs - 1;
+            ep.n_segs = lists.n_segs; ep.extra_seg = lists.n_segs - 1; ep.tq = tq;
             HQ_CUDA_OK(cudaMemset2DAsync(lists.seg_n + ep.extra_seg, (size_t)lists.n_segs * 4, 0, 4, (size_t)Q, st));
         }
         const int64_t pairs = (int64_t)Q * n_exc;

@@ -80,7 +80,7 @@ struct FtcParams {
     int bits_vec;               // planes are 32-byte aligned with a pitch of whole sectors: 256-bit stores
     // optional candidate lists (L >= 2): rows passing levels 0 and 1, one private segment per
     // (query, row range, tile half) so that no atomics are needed and rows stay ascending
-    uint32_t* l_rows;           // [Q][n_segs][seg_cap]  row | (passes level 2) << 31
+    uint32_t* l_rows;           // [Q][n_segs][seg_cap]  row (the level-2 test is k2 >= tq[2], repeated by the cascade)
     float* l_k1;                // [Q][n_segs][seg_cap]  level-1 dot product (order == score order within a query)
     float* l_k2;                // [Q][n_segs][seg_cap]  level-2 dot product (L == 3)
     int32_t* seg_n;             // [Q][n_segs] entries produced (may exceed seg_cap: overflow, list invalid)
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
                                 const int j = g * 8 + jj;
                                 const uint32_t bit = t1w & (1u << j);
                                 const uint32_t addr = sl_addr_x ^ (run & (LBUF * 4 - 1));
-                                const uint32_t roww = (row0 + j) | ((w2 << (31 - j)) & 0x80000000u);
+                                const uint32_t roww = row0 + j;
                                 asm volatile(
                                     "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t"
                                     "@p st.shared.u32 [%2], %3;\n\t"
