@@ -231,12 +231,19 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
             const uint32_t swz16 = (uint32_t)((lane >> 1) & 3) << 4;
             const uint32_t sl_addr = smem_u32(s_lists + et * LBUF);             // 64-byte aligned
             const uint32_t sl_addr_x = sl_addr ^ swz16;
+            uint32_t vw_next[3];
+#pragma unroll
+            for (int l = 0; l < 3; ++l) vw_next[l] = (l < p.L && t0 < t1) ? __ldg(p.valid + (int64_t)l * p.valid_pitch + 2 * t0 + half) : 0u;
             for (int t = t0; t < t1; ++t, ++it) {
                 const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
                 const int tl = (t - t0) & (TILE_GROUP - 1);
                 uint32_t vw[3];
 #pragma unroll
-                for (int l = 0; l < 3; ++l) vw[l] = l < p.L ? __ldg(p.valid + (int64_t)l * p.valid_pitch + 2 * t + half) : 0u;
+                for (int l = 0; l < 3; ++l) vw[l] = vw_next[l];
+                if (t + 1 < t1) {                        // the next tile's validity words travel during this tile
+#pragma unroll
+                    for (int l = 0; l < 3; ++l) vw_next[l] = l < p.L ? __ldg(p.valid + (int64_t)l * p.valid_pitch + 2 * (t + 1) + half) : 0u;
+                }
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
                 uint32_t r0[32], r1[32], r2[32];
@@ -295,17 +302,18 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
                                 if (seg_flushed + 8 <= p.seg_cap) {
                                     const uint32_t f0 = sl_addr_x ^ (((uint32_t)seg_flushed * 4u) & (LBUF * 4 - 1));   // chunk of entries f..f+3
                                     const uint32_t f1 = f0 ^ 16u;                                                      // f+4..f+7 (f is a multiple of 8)
+                                    // all six loads first, into separate registers: re-using the eight registers of one
+                                    // array for the next made every load wait for the previous 256-bit store to read them
+                                    uint32_t v[3][8];
 #pragma unroll
                                     for (int a = 0; a < 3; ++a) {
                                         if (a == 2 && p.L < 3) break;
-                                        uint32_t v[8];
-                                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(f0 + a * RING_A_BYTES));
-                                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(f1 + a * RING_A_BYTES));
-                                        uint32_t* dst = (a == 0 ? p.l_rows : (a == 1 ? reinterpret_cast<uint32_t*>(p.l_k1)
-                                                                                     : reinterpret_cast<uint32_t*>(p.l_k2))) +
-                                                        seg_base + seg_flushed;
-                                        st_global_256(dst, v);
+                                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[a][0]), "=r"(v[a][1]), "=r"(v[a][2]), "=r"(v[a][3]) : "r"(f0 + a * RING_A_BYTES));
+                                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[a][4]), "=r"(v[a][5]), "=r"(v[a][6]), "=r"(v[a][7]) : "r"(f1 + a * RING_A_BYTES));
                                     }
+                                    st_global_256(p.l_rows + seg_base + seg_flushed, v[0]);
+                                    st_global_256(reinterpret_cast<uint32_t*>(p.l_k1) + seg_base + seg_flushed, v[1]);
+                                    if (p.L > 2) st_global_256(reinterpret_cast<uint32_t*>(p.l_k2) + seg_base + seg_flushed, v[2]);
                                 }
                                 seg_flushed += 8;
                             }
@@ -313,13 +321,15 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
                     }
                 }
                 if (tl == TILE_GROUP - 1 || t == t1 - 1) {
-                    asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+                    // the two warps that share a TMEM lane quarter (row halves 0 and 1 of the same 32 queries) write
+                    // those queries' words out between themselves: a 64-thread named barrier instead of all 256
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + ew) : "memory");
                     const int64_t wb = 2 * (int64_t)(t - tl);
                     const int n_w = 2 * (tl + 1);
                     // one (level, query) row of the group per thread: two 128-bit reads, one 32-byte sector out
                     // (word-by-word copies were 10 % of the kernel's instructions)
-                    for (int e = et; e < 3 * FM; e += EPI_THREADS) {
-                        const int l = e / FM, qq = e % FM;
+                    for (int e = half * 32 + lane; e < 3 * 32; e += 64) {
+                        const int l = e >> 5, qq = ew * 32 + (e & 31);
                         const int gq = m_tile * FM + qq;
                         if (l < p.L && gq < p.Q) {
                             const uint4 a = *reinterpret_cast<const uint4*>(s_stage + ((l * 2 + 0) * FM + qq) * 4);
@@ -335,7 +345,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
                             }
                         }
                     }
-                    asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + ew) : "memory");
                 }
             }
             if (lists) {
