@@ -548,6 +548,7 @@ constexpr int kU2 = 2;                // same for the compaction pass, which rea
 constexpr uint32_t kChunk = kU * 128, kChunk2 = kU2 * 128;      // entries a warp takes at a time
 
 struct Boundary { float K; uint32_t R; };      // kept <=> k > K || (k == K && row < R)
+struct CutBin { float lo, scale; uint32_t cb, r_in_bin; bool on; };   // cut bin of a 2048-bin histogram, ranked later
 __device__ __forceinline__ bool kept_by(const Boundary& b, float k, uint32_t row) { return k > b.K || (k == b.K && row < b.R); }
 
 __device__ __forceinline__ uint32_t lin_bin(float k, float lo, float scale) {
@@ -681,6 +682,7 @@ __global__ void __launch_bounds__(kListThreads, 1) k_filter_cascade_lists(const 
     __shared__ int32_t s_cnt[kMaxSegs];
     __shared__ float b_key[kCutCap];
     __shared__ uint32_t b_row[kCutCap];
+    __shared__ float b_k2[kCutCap];
     __shared__ uint32_t s_bufn, s_flag, s_R, s_n2;
     __shared__ float s_K;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
@@ -754,17 +756,33 @@ __global__ void __launch_bounds__(kListThreads, 1) k_filter_cascade_lists(const 
                 }
             }
         };
-        if ((int64_t)n1 > cap1) {
+        // Ratio cut 1.  One histogram pass finds the cut bin; when that bin is small enough to be ranked in shared
+        // memory (the normal case) its members are collected by the NEXT pass over the list, which classifies every
+        // candidate as above / inside / below the cut bin -- no separate gather pass over the list.
+        const bool cut1 = (int64_t)n1 > cap1;
+        CutBin cb1{0.f, 0.f, 0u, 0u, false};
+        if (cut1) {
             const float lo = __ldg(p.tq + (int64_t)1 * p.Q + q), hi = __ldg(p.nq + (int64_t)1 * p.Q + q);
-            failed = !select_boundary(each_l1, [&](uint32_t tok) { return __ldg(L_rows + tok) & 0x7fffffffu; }, n1 - (uint32_t)cap1, lo, hi,
-                                      false, hist, sh, b_key, b_row, &s_bufn, &s_K, &s_R, b1);
+            const float scale = hi > lo ? 2048.0f / (hi - lo) : 0.f;
+            __syncthreads();
+            for (int i = tid; i < 2048; i += nt) hist[i] = 0;
+            __syncthreads();
+            each_l1([&](float k, uint32_t) { atomicAdd(&hist[lin_bin(k, lo, scale)], 1u); });
+            __syncthreads();
+            find_cut_bin(hist, n1 - (uint32_t)cap1, sh);
+            if (sh[2] <= (uint32_t)kCutCap) {
+                cb1.lo = lo; cb1.scale = scale; cb1.cb = sh[0]; cb1.r_in_bin = sh[1]; cb1.on = true;
+            } else {
+                failed = !select_boundary(each_l1, [&](uint32_t tok) { return __ldg(L_rows + tok) & 0x7fffffffu; }, n1 - (uint32_t)cap1, lo,
+                                          hi, true, hist, sh, b_key, b_row, &s_bufn, &s_K, &s_R, b1);
+            }
         }
         if (failed) {
             if (tid == 0) p.fallback[q] = 1;
             __syncthreads();
             continue;
         }
-        const int64_t out1 = (int64_t)n1 > cap1 ? cap1 : (int64_t)n1;
+        const int64_t out1 = cut1 ? cap1 : (int64_t)n1;
         if (p.counts && tid == 0) {
             p.counts[((int64_t)0 * 3 + 0) * p.Q + q] = (int32_t)p.N;
             p.counts[((int64_t)0 * 3 + 1) * p.Q + q] = (int32_t)c0;
@@ -774,6 +792,18 @@ __global__ void __launch_bounds__(kListThreads, 1) k_filter_cascade_lists(const 
             p.counts[((int64_t)1 * 3 + 2) * p.Q + q] = (int32_t)out1;
         }
         uint32_t* M = p.mask + (int64_t)q * p.mask_stride;
+        __syncthreads();
+        if (tid == 0) s_bufn = 0;
+        __syncthreads();
+        // 2 = survives cut 1, 1 = member of the cut bin (decided after the pass), 0 = dropped
+        auto class1 = [&](float k, uint32_t row) -> int {
+            if (!cut1) return 2;
+            if (cb1.on) {
+                const uint32_t b = lin_bin(k, cb1.lo, cb1.scale);
+                return b > cb1.cb ? 2 : (b == cb1.cb ? 1 : 0);
+            }
+            return kept_by(b1, k, row) ? 2 : 0;
+        };
         if (p.L == 2) {
             for (uint32_t item = warp; item < n_items; item += nw) {
                 const uint32_t seg = item / cps, e_base = (item - seg * cps) * kChunk;
@@ -797,9 +827,22 @@ __global__ void __launch_bounds__(kListThreads, 1) k_filter_cascade_lists(const 
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const uint32_t row = rr[i] & 0x7fffffffu;
-                        if (e + i < cnt && kept_by(b1, kk[i], row)) atomicOr(&M[row >> 5], 1u << (row & 31));
+                        const int cls = e + i < cnt ? class1(kk[i], row) : 0;
+                        if (cls == 2) atomicOr(&M[row >> 5], 1u << (row & 31));
+                        if (cls == 1) {
+                            const uint32_t slot = atomicAdd(&s_bufn, 1u);
+                            b_key[slot] = kk[i]; b_row[slot] = row;
+                        }
                     }
                 }
+            }
+            __syncthreads();
+            if (cb1.on) {
+                const uint32_t nb = s_bufn;
+                rank_cut_bin(b_key, b_row, nb, cb1.r_in_bin, &s_K, &s_R);
+                const Boundary bb{s_K, s_R};
+                for (uint32_t e = tid; e < nb; e += nt)
+                    if (kept_by(bb, b_key[e], b_row[e])) atomicOr(&M[b_row[e] >> 5], 1u << (b_row[e] & 31));
             }
             if (tid == 0) p.n_out[q] = (int32_t)out1;
             __syncthreads();
@@ -809,9 +852,7 @@ __global__ void __launch_bounds__(kListThreads, 1) k_filter_cascade_lists(const 
         // ---- level 2: survivors of cut 1 that pass the level-2 threshold are compacted; histogram of k2 on the fly ----
         const float lo2 = __ldg(p.tq + (int64_t)2 * p.Q + q), hi2 = __ldg(p.nq + (int64_t)2 * p.Q + q);
         const float scale2 = hi2 > lo2 ? 2048.0f / (hi2 - lo2) : 0.f;
-        __syncthreads();
         for (int i = tid; i < 2048; i += nt) hist[i] = 0;
-        if (tid == 0) s_bufn = 0;
         __syncthreads();
         for (uint32_t item = warp; item < n_items2; item += nw) {       // chunks of kU2 x 128 entries (three arrays are read)
             const uint32_t seg = item / cps2, e_base = (item - seg * cps2) * kChunk2;
@@ -846,7 +887,12 @@ __global__ void __launch_bounds__(kListThreads, 1) k_filter_cascade_lists(const 
                     rr[s] = ar[i] & 0x7fffffffu;
                     // k2 < tq fails the level-2 threshold (the same fp32 comparison as the threshold pass; false for a
                     // NaN threshold); entries past the end of the segment are stale data
-                    take[s] = e + i < cnt && a2[i] >= lo2 && kept_by(b1, a1[i], rr[s]);
+                    const int cls = e + i < cnt ? class1(a1[i], rr[s]) : 0;
+                    if (cls == 1) {              // every member of the cut bin: cut 1 ranks them before level 2 looks at them
+                        const uint32_t slot = atomicAdd(&s_bufn, 1u);
+                        b_key[slot] = a1[i]; b_row[slot] = rr[s]; b_k2[slot] = a2[i];
+                    }
+                    take[s] = cls == 2 && a2[i] >= lo2;
                     bal[s] = __ballot_sync(0xffffffffu, take[s]);
                     total += (uint32_t)__popc(bal[s]);
                 }
@@ -866,37 +912,61 @@ __global__ void __launch_bounds__(kListThreads, 1) k_filter_cascade_lists(const 
             }
         }
         __syncthreads();
+        if (cb1.on) {
+            // cut 1 inside its cut bin (exact ranking of all members), then the level-2 threshold for the kept ones
+            const uint32_t nb = s_bufn;
+            rank_cut_bin(b_key, b_row, nb, cb1.r_in_bin, &s_K, &s_R);
+            const Boundary bb{s_K, s_R};
+            for (uint32_t e = tid; e < nb; e += nt) {
+                if (kept_by(bb, b_key[e], b_row[e]) && b_k2[e] >= lo2) {
+                    const uint32_t slot = atomicAdd(&s_n2, 1u);
+                    c_k2[slot] = b_k2[e];
+                    c_row[slot] = b_row[e];
+                    atomicAdd(&hist[lin_bin(b_k2[e], lo2, scale2)], 1u);
+                }
+            }
+            __syncthreads();
+        }
         const uint32_t n2 = s_n2;
         int64_t cap2 = (int64_t)((double)out1 * p.ratio[2]);
         if (cap2 < 1) cap2 = 1;
+        const bool cut2 = (int64_t)n2 > cap2;
         Boundary b2;
         b2.K = -INFINITY; b2.R = 0;
-        if ((int64_t)n2 > cap2) {
-            auto each_l2 = [&](auto visit) {
-                for (uint32_t e0 = tid; e0 < n2; e0 += kU * nt) {
-                    float k[kU];
+        CutBin cb2{0.f, 0.f, 0u, 0u, false};
+        if (cut2) {
+            find_cut_bin(hist, n2 - (uint32_t)cap2, sh);          // the histogram accumulated while compacting
+            if (sh[2] <= (uint32_t)kCutCap) {
+                cb2.lo = lo2; cb2.scale = scale2; cb2.cb = sh[0]; cb2.r_in_bin = sh[1]; cb2.on = true;
+            } else {
+                auto each_l2 = [&](auto visit) {
+                    for (uint32_t e0 = tid; e0 < n2; e0 += kU * nt) {
+                        float k[kU];
 #pragma unroll
-                    for (int u = 0; u < kU; ++u) k[u] = e0 + u * nt < n2 ? __ldcg(c_k2 + e0 + u * nt) : -1.0f;
+                        for (int u = 0; u < kU; ++u) k[u] = e0 + u * nt < n2 ? __ldcg(c_k2 + e0 + u * nt) : -1.0f;
 #pragma unroll
-                    for (int u = 0; u < kU; ++u)
-                        if (e0 + u * nt < n2) visit(k[u], e0 + u * nt);
-                }
-            };
-            // round 0 reuses the histogram accumulated while compacting
-            failed = !select_boundary(each_l2, [&](uint32_t tok) { return __ldcg(c_row + tok); }, n2 - (uint32_t)cap2, lo2, hi2, true, hist,
-                                      sh, b_key, b_row, &s_bufn, &s_K, &s_R, b2);
+                        for (int u = 0; u < kU; ++u)
+                            if (e0 + u * nt < n2) visit(k[u], e0 + u * nt);
+                    }
+                };
+                failed = !select_boundary(each_l2, [&](uint32_t tok) { return __ldcg(c_row + tok); }, n2 - (uint32_t)cap2, lo2, hi2, true,
+                                          hist, sh, b_key, b_row, &s_bufn, &s_K, &s_R, b2);
+            }
         }
         if (failed) {
             if (tid == 0) p.fallback[q] = 1;
             __syncthreads();
             continue;
         }
-        const int64_t out2 = (int64_t)n2 > cap2 ? cap2 : (int64_t)n2;
+        const int64_t out2 = cut2 ? cap2 : (int64_t)n2;
         if (p.counts && tid == 0) {
             p.counts[((int64_t)2 * 3 + 0) * p.Q + q] = (int32_t)out1;
             p.counts[((int64_t)2 * 3 + 1) * p.Q + q] = (int32_t)n2;
             p.counts[((int64_t)2 * 3 + 2) * p.Q + q] = (int32_t)out2;
         }
+        __syncthreads();
+        if (tid == 0) s_bufn = 0;
+        __syncthreads();
         for (uint32_t e0 = tid; e0 < n2; e0 += kU * nt) {
             float k[kU];
             uint32_t row[kU];
@@ -907,8 +977,31 @@ __global__ void __launch_bounds__(kListThreads, 1) k_filter_cascade_lists(const 
                 row[u] = ok ? __ldcg(c_row + e0 + u * nt) : 0u;
             }
 #pragma unroll
-            for (int u = 0; u < kU; ++u)
-                if (e0 + u * nt < n2 && kept_by(b2, k[u], row[u])) atomicOr(&M[row[u] >> 5], 1u << (row[u] & 31));
+            for (int u = 0; u < kU; ++u) {
+                if (e0 + u * nt >= n2) continue;
+                int cls = 2;
+                if (cut2) {
+                    if (cb2.on) {
+                        const uint32_t b = lin_bin(k[u], cb2.lo, cb2.scale);
+                        cls = b > cb2.cb ? 2 : (b == cb2.cb ? 1 : 0);
+                    } else {
+                        cls = kept_by(b2, k[u], row[u]) ? 2 : 0;
+                    }
+                }
+                if (cls == 2) atomicOr(&M[row[u] >> 5], 1u << (row[u] & 31));
+                if (cls == 1) {
+                    const uint32_t slot = atomicAdd(&s_bufn, 1u);
+                    b_key[slot] = k[u]; b_row[slot] = row[u];
+                }
+            }
+        }
+        __syncthreads();
+        if (cb2.on) {
+            const uint32_t nb = s_bufn;
+            rank_cut_bin(b_key, b_row, nb, cb2.r_in_bin, &s_K, &s_R);
+            const Boundary bb{s_K, s_R};
+            for (uint32_t e = tid; e < nb; e += nt)
+                if (kept_by(bb, b_key[e], b_row[e])) atomicOr(&M[b_row[e] >> 5], 1u << (b_row[e] & 31));
         }
         if (tid == 0) p.n_out[q] = (int32_t)out2;
         __syncthreads();
