@@ -4,8 +4,10 @@
 //
 //   warp 0      : TMA producer   (cp.async.bulk.tensor, 128B-swizzled K-major tiles, 4 stages)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (M=128 queries, N=256 rows, K=16)
-//   warps 2..5  : epilogue, one thread per query row: tcgen05.ld 32 columns at a time, apply
-//                 mask / 1/|c|, keep the best KP (value, row) pairs in registers
+//   warps 2..   : epilogue, EH threads per query row (EH = 1: four warps, 256 columns each; EH = 2: eight warps,
+//                 128 columns each, for short rows whose MMAs finish before a four-warp epilogue does):
+//                 tcgen05.ld 32 / EH columns at a time, apply mask / 1/|c|, keep the best KP (value, row) pairs
+//                 in registers
 // Work unit = (query tile of 128, contiguous range of 256-row tiles); units are laid out so
 // that neighbouring CTAs stream the same database rows at the same time (L2 reuse), the
 // query tile comes from L2.  Two TMEM accumulators (2 x 256 columns) overlap the epilogue of
@@ -13,6 +15,7 @@
 #include "hq_tc.cuh"
 #include <cuda_bf16.h>
 #include <float.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -21,7 +24,6 @@ constexpr int UMMA_K = 16;
 constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;      // 16 KB
 constexpr uint32_t B_STAGE_BYTES = BN * BK * 2;      // 32 KB
 constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int TC_THREADS = 192;
 constexpr uint32_t TMEM_COLS = 512;
 
 using namespace hq_tc;
@@ -35,12 +37,13 @@ struct TcParams {
     const float* db_norm;
     const uint32_t* mask;
     int64_t mask_stride;
-    float* part_val;      // [num_units][128][KP]
+    int eh;               // epilogue threads per query row (1 or 2): partial lists per unit
+    float* part_val;      // [num_units][eh][128][KP]
     int32_t* part_idx;
 };
 
-template <int KP>
-__global__ void __launch_bounds__(TC_THREADS, 1) k_rerank_tc(const __grid_constant__ CUtensorMap map_q,
+template <int KP, int EH>
+__global__ void __launch_bounds__(64 + 128 * EH, 1) k_rerank_tc(const __grid_constant__ CUtensorMap map_q,
                                                             const __grid_constant__ CUtensorMap map_db, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 128B-swizzled tiles need 1024-byte alignment in the shared window
@@ -48,8 +51,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rerank_tc(const __grid_consta
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
     float* s_inv = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);          // [2][BN]
-    float* s_vals = s_inv + 2 * BN;                                                // [32][128] spill column per epilogue thread
-    uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_vals + 32 * 128);             // [8][128]
+    float* s_vals = s_inv + 2 * BN;                                                // [32 / EH][128 * EH] spill column per epilogue thread
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_vals + 32 * 128);             // [8 / EH][128 * EH]
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_mask + 8 * 128);
     uint64_t* full_bar = bars;                  // [STAGES]
     uint64_t* empty_bar = bars + STAGES;        // [STAGES]
@@ -65,7 +68,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rerank_tc(const __grid_consta
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_db)) : "memory");
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128 * EH); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -132,9 +135,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rerank_tc(const __grid_consta
         // loop is rolled, each 32-column chunk computes a hit mask against the thread's current
         // k'-th best, and only chunks with hits spill their values to a private shared-memory
         // column and walk the set bits through ONE insertion site.
+        constexpr int EPI = 128 * EH;                    // epilogue threads
+        constexpr int CW = 32 / EH;                      // columns per chunk (the spill area holds CW x EPI values)
+        constexpr int COLS = BN / EH;                    // columns per thread and tile
+        constexpr int MW = COLS / 32;                    // mask words per thread and tile
         const int ew = warp & 3;                         // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;                // which COLS columns of the tile (0 when EH == 1)
+        const int col0 = half * COLS;
         const int row_in_tile = ew * 32 + lane;
-        const int et = (warp - 2) * 32 + lane;           // 0..127 index among the epilogue threads
+        const int et = (warp - 2) * 32 + lane;           // index among the epilogue threads
         uint32_t it = 0;
         for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
             const int m_tile = u % p.m_tiles, range = u / p.m_tiles;
@@ -147,41 +156,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rerank_tc(const __grid_consta
 #pragma unroll
             for (int j = 0; j < KP; ++j) { bv[j] = -FLT_MAX; bi[j] = -1; }
             float thr = -FLT_MAX;
-            for (int t = t0; t < t1; ++t, ++it) {
-                const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-                // 1/|c| of this tile's rows (0 marks a zero-norm or out-of-range row)
-                float* inv = s_inv + acc * BN;
+            // The mask words (thread-private) and row norms of a tile are fetched one tile ahead: issued right after
+            // the barrier, they travel while this tile's columns are processed (loading them at the top of the tile
+            // put a global-load latency plus a barrier in front of every epilogue: 768-D ran at 60 % of the tensor peak).
+            static_assert(BN % EPI == 0 && BN / EPI <= 2, "row norms: at most two per thread");
+            uint32_t m_next[MW];
+            float n_next[BN / EPI];
+            auto fetch = [&](int t) {
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int64_t r = (int64_t)t * BN + et + 128 * h;
-                    float v = 0.f;
-                    if (r < p.N) { const float nc = __ldg(p.db_norm + r); v = nc > 0.f ? 1.0f / nc : 0.f; }
-                    inv[et + 128 * h] = v;
+                for (int h = 0; h < BN / EPI; ++h) {
+                    const int64_t r = (int64_t)t * BN + et + EPI * h;
+                    n_next[h] = r < p.N ? __ldg(p.db_norm + r) : 0.f;
                 }
 #pragma unroll
-                for (int w = 0; w < 8; ++w) {
+                for (int w = 0; w < MW; ++w) {
                     uint32_t m = 0xffffffffu;
-                    const int64_t r0 = (int64_t)t * BN + 32 * w;
+                    const int64_t r0 = (int64_t)t * BN + col0 + 32 * w;
                     if (!q_ok || r0 >= p.N) m = 0;
                     else {
                         if (p.mask) m = __ldg(p.mask + (int64_t)q * p.mask_stride + (r0 >> 5));
                         if (r0 + 32 > p.N) m &= (1u << (uint32_t)(p.N - r0)) - 1u;
                     }
-                    s_mask[w * 128 + et] = m;            // thread-private slot, read back below
+                    m_next[w] = m;
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+            };
+            if (t0 < t1) fetch(t0);
+            for (int t = t0; t < t1; ++t, ++it) {
+                const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+                // 1/|c| of this tile's rows (0 marks a zero-norm or out-of-range row)
+                float* inv = s_inv + acc * BN;
+#pragma unroll
+                for (int h = 0; h < BN / EPI; ++h) inv[et + EPI * h] = n_next[h] > 0.f ? 1.0f / n_next[h] : 0.f;
+#pragma unroll
+                for (int w = 0; w < MW; ++w) s_mask[w * EPI + et] = m_next[w];       // thread-private slots, read back per chunk
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");
+                if (t + 1 < t1) fetch(t + 1);
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
 #pragma unroll 1
-                for (int w = 0; w < 8; ++w) {
-                    uint32_t r[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + 32 * w, r);
+                for (int c = 0; c < COLS / CW; ++c) {
+                    uint32_t r[CW];
+                    tmem_ld(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + col0 + CW * c, r);
                     tmem_ld_wait();
-                    const uint32_t m = s_mask[w * 128 + et];
+                    uint32_t m = s_mask[((CW * c) >> 5) * EPI + et];
+                    if constexpr (CW < 32) m = (m >> ((CW * c) & 31)) & ((1u << CW) - 1u);
                     uint32_t hits = 0;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float iv = inv[32 * w + j];
+                    for (int j = 0; j < CW; ++j) {
+                        const float iv = inv[col0 + CW * c + j];
                         const float v = iv > 0.f ? __uint_as_float(r[j]) * iv : -FLT_MAX * 0.5f;
                         r[j] = __float_as_uint(v);
                         hits |= (v > thr ? 1u : 0u) << j;
@@ -189,14 +211,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rerank_tc(const __grid_consta
                     hits &= m;
                     if (hits) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) s_vals[j * 128 + et] = __uint_as_float(r[j]);
+                        for (int j = 0; j < CW; ++j) s_vals[j * EPI + et] = __uint_as_float(r[j]);
                         while (hits) {
                             const int j = __ffs(hits) - 1;
                             hits &= hits - 1;
-                            const float v = s_vals[j * 128 + et];
+                            const float v = s_vals[j * EPI + et];
                             if (v > bv[KP - 1]) {
                                 bv[KP - 1] = v;
-                                bi[KP - 1] = t * BN + 32 * w + j;
+                                bi[KP - 1] = t * BN + col0 + CW * c + j;
 #pragma unroll
                                 for (int s = KP - 1; s > 0; --s) {
                                     if (bv[s] > bv[s - 1]) {
@@ -213,8 +235,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rerank_tc(const __grid_consta
                 mbar_arrive(&tempty_bar[acc]);
             }
             if (q_ok) {
-                float* pv = p.part_val + ((int64_t)u * BM + row_in_tile) * KP;
-                int32_t* pi = p.part_idx + ((int64_t)u * BM + row_in_tile) * KP;
+                float* pv = p.part_val + (((int64_t)u * EH + half) * BM + row_in_tile) * KP;
+                int32_t* pi = p.part_idx + (((int64_t)u * EH + half) * BM + row_in_tile) * KP;
 #pragma unroll
                 for (int j = 0; j < KP; ++j) { pv[j] = bv[j]; pi[j] = bi[j]; }
             }
@@ -235,7 +257,7 @@ __global__ void __launch_bounds__(128) k_rerank_tc_merge(const TcParams p, const
                                                          const float* __restrict__ q_norm, int k, int64_t id_base,
                                                          int64_t* __restrict__ ids, float* __restrict__ scores) {
     extern __shared__ unsigned char sm[];
-    const int M = p.n_ranges * KP;
+    const int M = p.n_ranges * p.eh * KP;
     float* c_val = reinterpret_cast<float*>(sm);
     int32_t* c_idx = reinterpret_cast<int32_t*>(c_val + M);
     __shared__ float top_val[KP];
@@ -244,10 +266,11 @@ __global__ void __launch_bounds__(128) k_rerank_tc_merge(const TcParams p, const
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m_tile = q / BM, row = q % BM;
     for (int e = tid; e < M; e += blockDim.x) {
-        const int r = e / KP, j = e - r * KP;
-        const int64_t u = (int64_t)r * p.m_tiles + m_tile;
-        c_val[e] = p.part_val[(u * BM + row) * KP + j];
-        c_idx[e] = p.part_idx[(u * BM + row) * KP + j];
+        const int r = e / KP, j = e - r * KP;                   // r = range * eh + half
+        const int64_t u = (int64_t)(r / p.eh) * p.m_tiles + m_tile;
+        const int64_t a = (((u * p.eh + r % p.eh) * BM + row) * KP) + j;
+        c_val[e] = p.part_val[a];
+        c_idx[e] = p.part_idx[a];
     }
     if (tid < KP) { top_val[tid] = -FLT_MAX; top_idx[tid] = -1; }
     __syncthreads();
@@ -370,21 +393,21 @@ void plan_units(int64_t N, int Q, int sms, TcParams& p) {
 
 int pick_kp(int k) { return k <= 10 ? 16 : (k <= 20 ? 32 : 0); }
 
-template <int KP>
+template <int KP, int EH>
 int launch_tc(const CUtensorMap& mq, const CUtensorMap& mdb, const TcParams& p, const float* db_f32, int64_t db_stride,
               const float* q_f32, int64_t q_stride, const float* q_norm, int k, int64_t id_base, int64_t* ids, float* scores,
               cudaStream_t st) {
     const size_t smem = STAGES * STAGE_BYTES + (2 * BN + 32 * 128 + 8 * 128) * sizeof(float) + (2 * STAGES + 4) * sizeof(uint64_t) + 16 + 1024;
     static bool attr = false;
     if (!attr) {
-        HQ_CUDA_OK(cudaFuncSetAttribute(k_rerank_tc<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HQ_CUDA_OK(cudaFuncSetAttribute((k_rerank_tc<KP, EH>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
     int grid = hq_cached_sm_count();
     if (grid > p.num_units) grid = p.num_units;
-    k_rerank_tc<KP><<<grid, TC_THREADS, smem, st>>>(mq, mdb, p);
+    k_rerank_tc<KP, EH><<<grid, 64 + 128 * EH, smem, st>>>(mq, mdb, p);
     HQ_LAUNCH_OK("k_rerank_tc");
-    const size_t msm = (size_t)p.n_ranges * KP * 8;
+    const size_t msm = (size_t)p.n_ranges * EH * KP * 8;
     if (msm > 48 * 1024) HQ_CUDA_OK(cudaFuncSetAttribute(k_rerank_tc_merge<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
     k_rerank_tc_merge<KP><<<p.Q, 128, msm, st>>>(p, db_f32, db_stride, q_f32, q_stride, q_norm, k, id_base, ids, scores);
     HQ_LAUNCH_OK("k_rerank_tc_merge");
@@ -410,7 +433,7 @@ extern "C" int64_t hq_rerank_bf16_scratch_bytes(int64_t N, int Q, int k) {
     if (kp == 0 || N <= 0 || Q <= 0) return 0;
     TcParams p{};
     plan_units(N, Q, hq_cached_sm_count(), p);
-    return (int64_t)p.num_units * BM * kp * 8;
+    return (int64_t)p.num_units * 2 * BM * kp * 8;            // sized for two partial lists per unit
 }
 
 extern "C" int hq_rerank_topk_bf16(const void* db_bf16, int64_t db_pitch, const float* db_f32, int64_t db_stride, const float* db_norm,
@@ -431,16 +454,22 @@ extern "C" int hq_rerank_topk_bf16(const void* db_bf16, int64_t db_pitch, const 
     TcParams p{};
     p.N = N; p.Q = Q; p.D = (int)D; p.db_norm = db_norm; p.mask = mask; p.mask_stride = mask_stride;
     plan_units(N, Q, hq_cached_sm_count(), p);
-    const int64_t need = (int64_t)p.num_units * BM * kp * 8;
+    // Rows of up to 1024 values: the MMAs of a tile take less time than a four-warp epilogue (768-D ran at 60 % of
+    // the tensor peak), so the tile's columns are split over eight epilogue warps.
+    p.eh = D <= 1024 ? 2 : 1;
+    if (const char* e = getenv("HQ_RERANK_EH")) { if (e[0] == '1') p.eh = 1; else if (e[0] == '2') p.eh = 2; }
+    const int64_t need = (int64_t)p.num_units * p.eh * BM * kp * 8;
     HQ_REQUIRE(scratch && scratch_bytes >= need, "scratch too small: need %lld bytes", (long long)need);
     p.part_val = reinterpret_cast<float*>(scratch);
-    p.part_idx = reinterpret_cast<int32_t*>(p.part_val + (int64_t)p.num_units * BM * kp);
+    p.part_idx = reinterpret_cast<int32_t*>(p.part_val + (int64_t)p.num_units * p.eh * BM * kp);
     CUtensorMap mq, mdb;
     int rc = make_map(&mq, q_bf16, Q, D, q_pitch, BM);
     if (rc != HQ_OK) return rc;
     rc = make_map(&mdb, db_bf16, N, D, db_pitch, BN);
     if (rc != HQ_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (kp == 16) return launch_tc<16>(mq, mdb, p, db_f32, db_stride, q_f32, q_stride, q_norm, k, id_base, ids, scores, st);
-    return launch_tc<32>(mq, mdb, p, db_f32, db_stride, q_f32, q_stride, q_norm, k, id_base, ids, scores, st);
+    if (kp == 16 && p.eh == 2) return launch_tc<16, 2>(mq, mdb, p, db_f32, db_stride, q_f32, q_stride, q_norm, k, id_base, ids, scores, st);
+    if (kp == 16) return launch_tc<16, 1>(mq, mdb, p, db_f32, db_stride, q_f32, q_stride, q_norm, k, id_base, ids, scores, st);
+    if (p.eh == 2) return launch_tc<32, 2>(mq, mdb, p, db_f32, db_stride, q_f32, q_stride, q_norm, k, id_base, ids, scores, st);
+    return launch_tc<32, 1>(mq, mdb, p, db_f32, db_stride, q_f32, q_stride, q_norm, k, id_base, ids, scores, st);
 }
