@@ -55,6 +55,9 @@ SIGNATURES = {
     "hq_rerank_bf16_scratch_bytes": (_i64, [_i64, _i32, _i32]),
     "hq_rerank_topk_bf16": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _p, _i64, _p, _i32, _p, _i64, _i32, _i64,
                                    _p, _p, _p, _i64, _p]),
+    "hq_to_bf16_unit": (_i32, [_p, _i64, _i64, _i64, _p, _p, _i64, _p]),
+    "hq_rerank_topk_unit_bf16": (_i32, [_p, _i64, _p, _i64, _p, _p, _i32, _i64, _i64, _p, _i64, _p, _i64, _p, _i32, _p, _i64, _i32, _i64,
+                                        _p, _p, _p, _i64, _p]),
     "hq_comprehensive_scores": (_i32, [_p, _i64, _i32, _i32, _i64, _p, _i32, _i64, _p, _p, _i64, _p, _p]),
     "hq_offset_square_means": (_i32, [_p, _i64, _i32, _i64, _p, _i64, _p]),
     "hq_pearson01_matrix": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _i32, _p, _i64, _p]),

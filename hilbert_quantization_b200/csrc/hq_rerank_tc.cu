@@ -38,11 +38,16 @@ struct TcParams {
     const uint32_t* mask;
     int64_t mask_stride;
     int eh;               // epilogue threads per query row (1 or 2): partial lists per unit
+    const int32_t* zero_rows;   // unit-row operand: ids of the zero-norm rows (ascending), appended by the merge when fewer
+    int n_zero;                 // than k other survivors exist (they score exactly 0.0, the lowest possible score)
     float* part_val;      // [num_units][eh][128][KP]
     int32_t* part_idx;
 };
 
-template <int KP, int EH>
+// PS: the database operand holds unit rows (c / |c| rounded to bf16, hq_to_bf16_unit).  The accumulator then orders a
+// query's rows like the cosine and the epilogue needs no 1/|c| per column (a shared-memory read, a select and a
+// multiply: half of its instructions); zero-norm rows are cleared from the mask instead.
+template <int KP, int EH, bool PS>
 __global__ void __launch_bounds__(64 + 128 * EH, 1) k_rerank_tc(const __grid_constant__ CUtensorMap map_q,
                                                             const __grid_constant__ CUtensorMap map_db, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -170,13 +175,12 @@ __global__ void __launch_bounds__(64 + 128 * EH, 1) k_rerank_tc(const __grid_con
                 }
 #pragma unroll
                 for (int w = 0; w < MW; ++w) {
-                    uint32_t m = 0xffffffffu;
+                    // the loaded word is not touched here (the tail of the last word is cut where it is consumed):
+                    // any use would wait for the load right away
                     const int64_t r0 = (int64_t)t * BN + col0 + 32 * w;
-                    if (!q_ok || r0 >= p.N) m = 0;
-                    else {
-                        if (p.mask) m = __ldg(p.mask + (int64_t)q * p.mask_stride + (r0 >> 5));
-                        if (r0 + 32 > p.N) m &= (1u << (uint32_t)(p.N - r0)) - 1u;
-                    }
+                    const bool in = q_ok && r0 < p.N;
+                    uint32_t m = in ? 0xffffffffu : 0u;
+                    if (in && p.mask) m = __ldg(p.mask + (int64_t)q * p.mask_stride + (r0 >> 5));
                     m_next[w] = m;
                 }
             };
@@ -185,10 +189,23 @@ __global__ void __launch_bounds__(64 + 128 * EH, 1) k_rerank_tc(const __grid_con
                 const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
                 // 1/|c| of this tile's rows (0 marks a zero-norm or out-of-range row)
                 float* inv = s_inv + acc * BN;
+                uint32_t* nzw = reinterpret_cast<uint32_t*>(inv);       // PS: bit r = row r of the tile has a non-zero norm
 #pragma unroll
-                for (int h = 0; h < BN / EPI; ++h) inv[et + EPI * h] = n_next[h] > 0.f ? 1.0f / n_next[h] : 0.f;
+                for (int h = 0; h < BN / EPI; ++h) {
+                    if constexpr (PS) {
+                        const uint32_t b = __ballot_sync(0xffffffffu, n_next[h] > 0.f);
+                        if (lane == 0) nzw[((et + EPI * h) >> 5)] = b;
+                    } else {
+                        inv[et + EPI * h] = n_next[h] > 0.f ? 1.0f / n_next[h] : 0.f;
+                    }
+                }
 #pragma unroll
-                for (int w = 0; w < MW; ++w) s_mask[w * EPI + et] = m_next[w];       // thread-private slots, read back per chunk
+                for (int w = 0; w < MW; ++w) {                                       // thread-private slots, read back per chunk
+                    const int64_t r0 = (int64_t)t * BN + col0 + 32 * w;
+                    uint32_t m = m_next[w];
+                    if (r0 + 32 > p.N) m = r0 < p.N ? (m & ((1u << (uint32_t)(p.N - r0)) - 1u)) : 0u;
+                    s_mask[w * EPI + et] = m;
+                }
                 asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");
                 if (t + 1 < t1) fetch(t + 1);
                 mbar_wait(&tfull_bar[acc], acc_phase);
@@ -201,12 +218,20 @@ __global__ void __launch_bounds__(64 + 128 * EH, 1) k_rerank_tc(const __grid_con
                     uint32_t m = s_mask[((CW * c) >> 5) * EPI + et];
                     if constexpr (CW < 32) m = (m >> ((CW * c) & 31)) & ((1u << CW) - 1u);
                     uint32_t hits = 0;
+                    if constexpr (PS) {
+                        uint32_t nz = nzw[(col0 + CW * c) >> 5];
+                        if constexpr (CW < 32) nz = (nz >> ((CW * c) & 31)) & ((1u << CW) - 1u);
+                        m &= nz;
 #pragma unroll
-                    for (int j = 0; j < CW; ++j) {
-                        const float iv = inv[col0 + CW * c + j];
-                        const float v = iv > 0.f ? __uint_as_float(r[j]) * iv : -FLT_MAX * 0.5f;
-                        r[j] = __float_as_uint(v);
-                        hits |= (v > thr ? 1u : 0u) << j;
+                        for (int j = 0; j < CW; ++j) hits |= (__uint_as_float(r[j]) > thr ? 1u : 0u) << j;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < CW; ++j) {
+                            const float iv = inv[col0 + CW * c + j];
+                            const float v = iv > 0.f ? __uint_as_float(r[j]) * iv : -FLT_MAX * 0.5f;
+                            r[j] = __float_as_uint(v);
+                            hits |= (v > thr ? 1u : 0u) << j;
+                        }
                     }
                     hits &= m;
                     if (hits) {
@@ -352,6 +377,14 @@ __global__ void __launch_bounds__(128) k_rerank_tc_merge(const TcParams p, const
     if (tid == 0) {
         int cnt = 0;
         for (int j = 0; j < KP; ++j) cnt += top_idx[j] >= 0 ? 1 : 0;
+        // unit-row operand: zero-norm rows never reach the shortlists; they score 0.0 and follow everybody else
+        for (int z = 0; z < p.n_zero && cnt < k; ++z) {
+            const int32_t id = p.zero_rows[z];
+            if (p.mask && !((p.mask[(int64_t)q * p.mask_stride + (id >> 5)] >> (id & 31)) & 1u)) continue;
+            ids[(int64_t)q * k + cnt] = (int64_t)id + id_base;
+            scores[(int64_t)q * k + cnt] = 0.f;
+            ++cnt;
+        }
         for (int j = cnt; j < k; ++j) { ids[(int64_t)q * k + j] = -1; scores[(int64_t)q * k + j] = -1.0f; }
     }
 }
@@ -362,6 +395,16 @@ __global__ void __launch_bounds__(256) k_to_bf16(const float* __restrict__ src, 
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / dst_pitch, c = i - r * dst_pitch;
         dst[i] = __float2bfloat16_rn(c < D ? __ldg(src + r * src_stride + c) : 0.f);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_to_bf16_unit(const float* __restrict__ src, int64_t N, int64_t D, int64_t src_stride,
+                                                      const float* __restrict__ norms, __nv_bfloat16* __restrict__ dst, int64_t dst_pitch) {
+    const int64_t total = N * dst_pitch;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / dst_pitch, c = i - r * dst_pitch;
+        const float n = __ldg(norms + r);
+        dst[i] = __float2bfloat16_rn((c < D && n > 0.f) ? __fdiv_rn(__ldg(src + r * src_stride + c), n) : 0.f);
     }
 }
 
@@ -393,19 +436,19 @@ void plan_units(int64_t N, int Q, int sms, TcParams& p) {
 
 int pick_kp(int k) { return k <= 10 ? 16 : (k <= 20 ? 32 : 0); }
 
-template <int KP, int EH>
+template <int KP, int EH, bool PS>
 int launch_tc(const CUtensorMap& mq, const CUtensorMap& mdb, const TcParams& p, const float* db_f32, int64_t db_stride,
               const float* q_f32, int64_t q_stride, const float* q_norm, int k, int64_t id_base, int64_t* ids, float* scores,
               cudaStream_t st) {
     const size_t smem = STAGES * STAGE_BYTES + (2 * BN + 32 * 128 + 8 * 128) * sizeof(float) + (2 * STAGES + 4) * sizeof(uint64_t) + 16 + 1024;
     static bool attr = false;
     if (!attr) {
-        HQ_CUDA_OK(cudaFuncSetAttribute((k_rerank_tc<KP, EH>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HQ_CUDA_OK(cudaFuncSetAttribute((k_rerank_tc<KP, EH, PS>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
     int grid = hq_cached_sm_count();
     if (grid > p.num_units) grid = p.num_units;
-    k_rerank_tc<KP, EH><<<grid, 64 + 128 * EH, smem, st>>>(mq, mdb, p);
+    k_rerank_tc<KP, EH, PS><<<grid, 64 + 128 * EH, smem, st>>>(mq, mdb, p);
     HQ_LAUNCH_OK("k_rerank_tc");
     const size_t msm = (size_t)p.n_ranges * EH * KP * 8;
     if (msm > 48 * 1024) HQ_CUDA_OK(cudaFuncSetAttribute(k_rerank_tc_merge<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
@@ -436,10 +479,11 @@ extern "C" int64_t hq_rerank_bf16_scratch_bytes(int64_t N, int Q, int k) {
     return (int64_t)p.num_units * 2 * BM * kp * 8;            // sized for two partial lists per unit
 }
 
-extern "C" int hq_rerank_topk_bf16(const void* db_bf16, int64_t db_pitch, const float* db_f32, int64_t db_stride, const float* db_norm,
-                                   int64_t N, int64_t D, const void* q_bf16, int64_t q_pitch, const float* q_f32, int64_t q_stride,
-                                   const float* q_norm, int Q, const uint32_t* mask, int64_t mask_stride, int k, int64_t id_base,
-                                   int64_t* ids, float* scores, void* scratch, int64_t scratch_bytes, void* stream) {
+static int rerank_topk_bf16(bool unit_rows, const int32_t* zero_rows, int n_zero, const void* db_bf16, int64_t db_pitch,
+                            const float* db_f32, int64_t db_stride, const float* db_norm,
+                            int64_t N, int64_t D, const void* q_bf16, int64_t q_pitch, const float* q_f32, int64_t q_stride,
+                            const float* q_norm, int Q, const uint32_t* mask, int64_t mask_stride, int k, int64_t id_base,
+                            int64_t* ids, float* scores, void* scratch, int64_t scratch_bytes, void* stream) {
     HQ_REQUIRE(N >= 0 && Q >= 0 && D > 0, "bad shape");
     const int kp = pick_kp(k);
     HQ_REQUIRE(k >= 1 && kp != 0, "k must be in [1, 20] for the tensor-core rerank (got %d)", k);
@@ -453,11 +497,13 @@ extern "C" int hq_rerank_topk_bf16(const void* db_bf16, int64_t db_pitch, const 
     HQ_REQUIRE(!mask || mask_stride * 32 >= N, "mask stride too small");
     TcParams p{};
     p.N = N; p.Q = Q; p.D = (int)D; p.db_norm = db_norm; p.mask = mask; p.mask_stride = mask_stride;
+    p.zero_rows = zero_rows; p.n_zero = n_zero;
     plan_units(N, Q, hq_cached_sm_count(), p);
     // Rows of up to 1024 values: the MMAs of a tile take less time than a four-warp epilogue (768-D ran at 60 % of
     // the tensor peak), so the tile's columns are split over eight epilogue warps.
-    p.eh = D <= 1024 ? 2 : 1;
-    if (const char* e = getenv("HQ_RERANK_EH")) { if (e[0] == '1') p.eh = 1; else if (e[0] == '2') p.eh = 2; }
+    // (measured faster at 1536-D too: 2.40 -> 2.25 ms per 1024 x 1 M batch)
+    p.eh = 2;
+    if (const char* e = getenv("HQ_RERANK_EH")) { if (e[0] == '1' && !unit_rows) p.eh = 1; }
     const int64_t need = (int64_t)p.num_units * p.eh * BM * kp * 8;
     HQ_REQUIRE(scratch && scratch_bytes >= need, "scratch too small: need %lld bytes", (long long)need);
     p.part_val = reinterpret_cast<float*>(scratch);
@@ -468,8 +514,46 @@ extern "C" int hq_rerank_topk_bf16(const void* db_bf16, int64_t db_pitch, const 
     rc = make_map(&mdb, db_bf16, N, D, db_pitch, BN);
     if (rc != HQ_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (kp == 16 && p.eh == 2) return launch_tc<16, 2>(mq, mdb, p, db_f32, db_stride, q_f32, q_stride, q_norm, k, id_base, ids, scores, st);
-    if (kp == 16) return launch_tc<16, 1>(mq, mdb, p, db_f32, db_stride, q_f32, q_stride, q_norm, k, id_base, ids, scores, st);
-    if (p.eh == 2) return launch_tc<32, 2>(mq, mdb, p, db_f32, db_stride, q_f32, q_stride, q_norm, k, id_base, ids, scores, st);
-    return launch_tc<32, 1>(mq, mdb, p, db_f32, db_stride, q_f32, q_stride, q_norm, k, id_base, ids, scores, st);
+#define HQ_TC_LAUNCH(KP_, EH_, PS_) \
+    return launch_tc<KP_, EH_, PS_>(mq, mdb, p, db_f32, db_stride, q_f32, q_stride, q_norm, k, id_base, ids, scores, st)
+    if (unit_rows) {
+        if (kp == 16) HQ_TC_LAUNCH(16, 2, true);
+        HQ_TC_LAUNCH(32, 2, true);
+    }
+    if (kp == 16 && p.eh == 2) HQ_TC_LAUNCH(16, 2, false);
+    if (kp == 16) HQ_TC_LAUNCH(16, 1, false);
+    if (p.eh == 2) HQ_TC_LAUNCH(32, 2, false);
+    HQ_TC_LAUNCH(32, 1, false);
+#undef HQ_TC_LAUNCH
+}
+
+extern "C" int hq_rerank_topk_bf16(const void* db_bf16, int64_t db_pitch, const float* db_f32, int64_t db_stride, const float* db_norm,
+                                   int64_t N, int64_t D, const void* q_bf16, int64_t q_pitch, const float* q_f32, int64_t q_stride,
+                                   const float* q_norm, int Q, const uint32_t* mask, int64_t mask_stride, int k, int64_t id_base,
+                                   int64_t* ids, float* scores, void* scratch, int64_t scratch_bytes, void* stream) {
+    return rerank_topk_bf16(false, nullptr, 0, db_bf16, db_pitch, db_f32, db_stride, db_norm, N, D, q_bf16, q_pitch, q_f32, q_stride, q_norm,
+                            Q, mask, mask_stride, k, id_base, ids, scores, scratch, scratch_bytes, stream);
+}
+
+extern "C" int hq_rerank_topk_unit_bf16(const void* db_unit_bf16, int64_t db_pitch, const float* db_f32, int64_t db_stride,
+                                        const float* db_norm, const int32_t* zero_rows, int n_zero, int64_t N, int64_t D,
+                                        const void* q_bf16, int64_t q_pitch, const float* q_f32, int64_t q_stride, const float* q_norm,
+                                        int Q, const uint32_t* mask, int64_t mask_stride, int k, int64_t id_base, int64_t* ids,
+                                        float* scores, void* scratch, int64_t scratch_bytes, void* stream) {
+    HQ_REQUIRE(n_zero >= 0 && (n_zero == 0 || zero_rows), "zero_rows missing");
+    return rerank_topk_bf16(true, zero_rows, n_zero, db_unit_bf16, db_pitch, db_f32, db_stride, db_norm, N, D, q_bf16, q_pitch, q_f32,
+                            q_stride, q_norm, Q, mask, mask_stride, k, id_base, ids, scores, scratch, scratch_bytes, stream);
+}
+
+extern "C" int hq_to_bf16_unit(const float* src, int64_t N, int64_t D, int64_t src_stride, const float* norms, void* dst,
+                               int64_t dst_pitch, void* stream) {
+    HQ_REQUIRE(N >= 0 && D > 0 && src_stride >= D && dst_pitch >= D, "bad shape");
+    if (N == 0) return HQ_OK;
+    HQ_REQUIRE(src && dst && norms, "null pointer");
+    int64_t blocks = (N * dst_pitch + 255) / 256;
+    const int64_t cap = (int64_t)hq_cached_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    k_to_bf16_unit<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, N, D, src_stride, norms, (__nv_bfloat16*)dst, dst_pitch);
+    HQ_LAUNCH_OK("k_to_bf16_unit");
+    return HQ_OK;
 }

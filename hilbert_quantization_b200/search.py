@@ -140,7 +140,10 @@ class EmbeddingDatabase:
         self.grids = grids if keep_grids else None
         self.lens = row_lengths(self.idx, self.layout)
         self.norms = row_norms(self.emb)
-        self.emb_bf16 = to_bf16(self.emb) if bf16 else None       # operand of the tensor-core rerank
+        # operand of the tensor-core rerank: unit rows (the epilogue then needs no 1 / |c|); zero-norm rows score 0.0 and
+        # are listed separately
+        self.emb_bf16 = to_bf16(self.emb, self.norms) if bf16 else None
+        self.zero_rows = (self.norms == 0).nonzero().flatten().to(torch.int32) if bf16 else None
         # fast filter: per-level row norms + "every stored length is the structural one" check
         self.level_norms = torch.empty((self.N, int(self.layout.L)), dtype=torch.float32, device=d)
         flag = torch.zeros(1, dtype=torch.int32, device=d)
@@ -193,13 +196,17 @@ class EmbeddingDatabase:
         return int(self.layout.L)
 
 
-def to_bf16(x: torch.Tensor) -> torch.Tensor:
-    """float32 [N, D] -> bf16 [N, pitch] (round to nearest even, pitch = D rounded up to 8, zero padded)."""
+def to_bf16(x: torch.Tensor, norms: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """float32 [N, D] -> bf16 [N, pitch] (round to nearest even, pitch = D rounded up to 8, zero padded); with `norms`
+    the rows are divided by their norm first (unit rows, zero rows stay zero)."""
     N, D = x.shape
     pitch = (D + 7) // 8 * 8
     out = torch.empty((N, pitch), dtype=torch.bfloat16, device=x.device)
     with torch.cuda.device(x.device):
-        check(lib.hq_to_bf16(dev.ptr(x), N, D, x.stride(0) if N else D, dev.ptr(out), pitch, dev.stream_ptr()))
+        if norms is None:
+            check(lib.hq_to_bf16(dev.ptr(x), N, D, x.stride(0) if N else D, dev.ptr(out), pitch, dev.stream_ptr()))
+        else:
+            check(lib.hq_to_bf16_unit(dev.ptr(x), N, D, x.stride(0) if N else D, dev.ptr(norms), dev.ptr(out), pitch, dev.stream_ptr()))
     return out
 
 
@@ -427,8 +434,9 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
                 tok = _phase("rerank_gemm")
                 sb = int(lib.hq_rerank_bf16_scratch_bytes(N, nq, k))
                 scratch = torch.empty(sb, dtype=torch.uint8, device=d)
-                check(lib.hq_rerank_topk_bf16(dev.ptr(db.emb_bf16), db.emb_bf16.stride(0), dev.ptr(db.emb), db.emb.stride(0),
-                                              dev.ptr(db.norms), N, db.D, dev.ptr(q_bf16[s:e]), q_bf16.stride(0),
+                check(lib.hq_rerank_topk_unit_bf16(dev.ptr(db.emb_bf16), db.emb_bf16.stride(0), dev.ptr(db.emb), db.emb.stride(0),
+                                              dev.ptr(db.norms), dev.ptr(db.zero_rows), int(db.zero_rows.numel()), N, db.D,
+                                              dev.ptr(q_bf16[s:e]), q_bf16.stride(0),
                                               dev.ptr(q[s:e]), q.stride(0), dev.ptr(q_norms[s:e]), nq,
                                               dev.ptr(m), mask.stride(0), k, db.id_base,
                                               dev.ptr(ids[s:e]), dev.ptr(out_scores[s:e]), dev.ptr(scratch), sb, dev.stream_ptr()))

@@ -235,6 +235,18 @@ int hq_rerank_topk_bf16(const void* db_bf16, int64_t db_pitch, const float* db_f
                         const float* q_norm, int Q, const uint32_t* mask, int64_t mask_stride,
                         int k, int64_t id_base, int64_t* ids, float* scores,
                         void* scratch, int64_t scratch_bytes, void* stream);
+/* Same search with a database operand of UNIT rows (c / |c| rounded to bf16, hq_to_bf16_unit): the epilogue then
+ * needs no 1/|c| per column (half of its instructions; 768-D rows: 94 -> 5x ms per 4096 x 12.5 M batch).  Zero-norm
+ * rows score exactly 0.0 (rag/search/engine.py:640-643) and cannot be told apart in this operand: the caller passes
+ * their ids (ascending) and they are appended after every other survivor, as the reference's stable sort orders them. */
+int hq_to_bf16_unit(const float* src, int64_t N, int64_t D, int64_t src_stride, const float* norms, void* dst,
+                    int64_t dst_pitch, void* stream);
+int hq_rerank_topk_unit_bf16(const void* db_unit_bf16, int64_t db_pitch, const float* db_f32, int64_t db_stride,
+                             const float* db_norm, const int32_t* zero_rows, int n_zero, int64_t N, int64_t D,
+                             const void* q_bf16, int64_t q_pitch, const float* q_f32, int64_t q_stride,
+                             const float* q_norm, int Q, const uint32_t* mask, int64_t mask_stride,
+                             int k, int64_t id_base, int64_t* ids, float* scores,
+                             void* scratch, int64_t scratch_bytes, void* stream);
 
 /* ---- a14: comprehensive similarity blend -----------------------------------
  * rag/search/engine.py:516-575 (_calculate_comprehensive_similarity):

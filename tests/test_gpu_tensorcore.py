@@ -53,3 +53,23 @@ def test_tc_rerank_sharded_id_base(hq):
     mi, ms = merge_topk_host(np.stack([ia.cpu().numpy(), ib.cpu().numpy()]), np.stack([sa.cpu().numpy(), sb.cpu().numpy()]), 10)
     fi, fs = hq.search_batch(full, qs, 10, use_filter=False)
     assert np.array_equal(mi, fi.cpu().numpy())
+
+
+def test_tc_rerank_lists_zero_norm_rows_last(hq):
+    """The tensor-core operand holds unit rows, zero-norm rows are appended from their id list: they score exactly 0.0
+    (rag/search/engine.py:640-643) and follow every other survivor in id order."""
+    rng = np.random.default_rng(11)
+    db = rng.standard_normal((40, 768)).astype(np.float32)
+    zero = [2, 5, 17, 30, 31, 39]
+    db[zero] = 0.0
+    qs = rng.standard_normal((3, 768)).astype(np.float32)
+    for n_rows, k in ((8, 10), (40, 10), (40, 20), (20, 16)):
+        d = hq.EmbeddingDatabase(db[:n_rows])
+        i32, s32 = hq.search_batch(d, qs, k, use_filter=False, rerank="f32")
+        itc, stc = hq.search_batch(d, qs, k, use_filter=False, rerank="bf16")
+        assert torch.equal(itc, i32), (n_rows, k)
+        assert torch.equal(stc == 0, s32 == 0)
+        for j in range(3):
+            iw, sw = O.topk_stable(np.arange(n_rows), O.cosine01(qs[j], db[:n_rows]), k)
+            got = itc[j].cpu().numpy()
+            assert list(got[: len(iw)]) == list(iw)
