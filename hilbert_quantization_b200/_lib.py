@@ -62,6 +62,7 @@ SIGNATURES = {
     "hq_offset_square_means": (_i32, [_p, _i64, _i32, _i64, _p, _i64, _p]),
     "hq_pearson01_matrix": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _i32, _p, _i64, _p]),
     "hq_topk_merge": (_i32, [_p, _p, _i32, _i32, _i32, _p, _p, _p]),
+    "hq_topk_merge_strided": (_i32, [_p, _p, _i32, _i32, _i32, _i64, _i64, _p, _p, _p]),
     "hq_core_level_sims": (_i32, [_p, _i64, _i32, _i64, _p, _p, _p, _p, _i32, _p, _p]),
 }
 

@@ -456,7 +456,8 @@ __global__ void __launch_bounds__(1024) k_topk_scores(const float* __restrict__ 
 
 // merge of P per-shard lists per query; ties -> lower id; id < 0 = empty slot
 __global__ void __launch_bounds__(256) k_topk_merge(const int64_t* __restrict__ in_ids, const float* __restrict__ in_scores, int P,
-                                                    int Q, int k, int64_t* __restrict__ out_ids, float* __restrict__ out_scores) {
+                                                    int Q, int k, int64_t ids_shard_stride, int64_t scores_shard_stride,
+                                                    int64_t* __restrict__ out_ids, float* __restrict__ out_scores) {
     extern __shared__ unsigned char smraw[];
     const int M = P * k;
     int64_t* s_id = reinterpret_cast<int64_t*>(smraw);
@@ -464,8 +465,8 @@ __global__ void __launch_bounds__(256) k_topk_merge(const int64_t* __restrict__ 
     const int q = blockIdx.x;
     for (int e = threadIdx.x; e < M; e += blockDim.x) {
         const int p = e / k, j = e - p * k;
-        s_id[e] = in_ids[((int64_t)p * Q + q) * k + j];
-        s_val[e] = in_scores[((int64_t)p * Q + q) * k + j];
+        s_id[e] = in_ids[p * ids_shard_stride + (int64_t)q * k + j];
+        s_val[e] = in_scores[p * scores_shard_stride + (int64_t)q * k + j];
     }
     for (int j = threadIdx.x; j < k; j += blockDim.x) { out_ids[(int64_t)q * k + j] = -1; out_scores[(int64_t)q * k + j] = -1.0f; }
     __syncthreads();
@@ -652,16 +653,23 @@ extern "C" int hq_rerank_topk_f32(const float* db, const float* db_norm, int64_t
     return hq_topk_from_scores((const float*)scratch, N, N, Q, k, id_base, ids, scores, stream);
 }
 
-extern "C" int hq_topk_merge(const int64_t* in_ids, const float* in_scores, int P, int Q, int k, int64_t* out_ids, float* out_scores,
-                             void* stream) {
+extern "C" int hq_topk_merge_strided(const int64_t* in_ids, const float* in_scores, int P, int Q, int k, int64_t ids_shard_stride,
+                                     int64_t scores_shard_stride, int64_t* out_ids, float* out_scores, void* stream) {
     HQ_REQUIRE(P >= 1 && Q >= 0 && k >= 1, "bad shape");
     if (Q == 0) return HQ_OK;
     HQ_REQUIRE(in_ids && in_scores && out_ids && out_scores, "null pointer");
+    HQ_REQUIRE(ids_shard_stride >= (int64_t)Q * k && scores_shard_stride >= (int64_t)Q * k, "shard stride smaller than Q * k");
     const size_t smem = (size_t)P * k * 12;
     HQ_REQUIRE(smem <= 48 * 1024, "P*k too large for the merge kernel");
-    k_topk_merge<<<Q, 256, smem, (cudaStream_t)stream>>>(in_ids, in_scores, P, Q, k, out_ids, out_scores);
+    k_topk_merge<<<Q, 256, smem, (cudaStream_t)stream>>>(in_ids, in_scores, P, Q, k, ids_shard_stride, scores_shard_stride, out_ids,
+                                                         out_scores);
     HQ_LAUNCH_OK("k_topk_merge");
     return HQ_OK;
+}
+
+extern "C" int hq_topk_merge(const int64_t* in_ids, const float* in_scores, int P, int Q, int k, int64_t* out_ids, float* out_scores,
+                             void* stream) {
+    return hq_topk_merge_strided(in_ids, in_scores, P, Q, k, (int64_t)Q * k, (int64_t)Q * k, out_ids, out_scores, stream);
 }
 
 extern "C" int hq_core_level_sims(const double* cand, int64_t N, int S, int64_t cand_stride, const double* q, const int32_t* q_start,

@@ -46,19 +46,48 @@ def merge_topk_host(ids: np.ndarray, scores: np.ndarray, k: int) -> Tuple[np.nda
 
 def allgather_merge(local_ids: torch.Tensor, local_scores: torch.Tensor, k: int, group=None,
                     merge_on_host: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
-    """All-gather the per-shard [Q, k] results and merge them on every rank."""
+    """All-gather the per-shard [Q, k] results and merge them on every rank.  Results that come from
+    `search.packed_result_buffers` (what `search_batch` returns) travel in ONE all-gather."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return local_ids, local_scores
     Q = local_ids.shape[0]
-    g_ids = torch.empty((world * Q, k), dtype=local_ids.dtype, device=local_ids.device)
-    g_sc = torch.empty((world * Q, k), dtype=local_scores.dtype, device=local_scores.device)
-    dist.all_gather_into_tensor(g_ids, local_ids.contiguous(), group=group)
-    dist.all_gather_into_tensor(g_sc, local_scores.contiguous(), group=group)
-    g_ids, g_sc = g_ids.view(world, Q, k), g_sc.view(world, Q, k)
-    if merge_on_host or not local_ids.is_cuda:
-        i, s = merge_topk_host(g_ids.cpu().numpy(), g_sc.cpu().numpy(), k)
-        return torch.from_numpy(i).to(local_ids.device), torch.from_numpy(s).to(local_scores.device)
+    n = Q * k
+    packed = (local_ids.dtype == torch.int64 and local_scores.dtype == torch.float32 and local_ids.is_contiguous()
+              and local_scores.is_contiguous() and local_ids.untyped_storage().data_ptr() == local_scores.untyped_storage().data_ptr()
+              and local_scores.data_ptr() == local_ids.data_ptr() + 8 * n)
+    if packed:
+        # search_batch returns ids and scores as two views of one buffer: ONE all-gather ships both
+        block = torch.empty(0, dtype=torch.int32, device=local_ids.device).set_(
+            local_ids.untyped_storage(), local_ids.storage_offset() * 2, (3 * n,))
+        g = torch.empty(world * 3 * n, dtype=torch.int32, device=local_ids.device)
+        dist.all_gather_into_tensor(g, block, group=group)
+        g2 = g.view(world, 3 * n)
+        g_ids = g2[:, : 2 * n]                       # int32 pairs = int64 ids, shard stride 3n int32 = 1.5n int64
+        g_sc = g2[:, 2 * n:].view(torch.float32)
+        if merge_on_host or not local_ids.is_cuda:
+            gi = g_ids.contiguous().view(torch.int64).view(world, Q, k)
+            i, s = merge_topk_host(gi.cpu().numpy(), g_sc.contiguous().view(world, Q, k).cpu().numpy(), k)
+            return torch.from_numpy(i).to(local_ids.device), torch.from_numpy(s).to(local_scores.device)
+        if (3 * n) % 2 == 0:                         # shard blocks stay 8-byte aligned
+            from ._lib import check, lib
+            from .search import packed_result_buffers
+            out_i, out_s = packed_result_buffers(Q, k, local_ids.device)
+            with torch.cuda.device(local_ids.device):
+                check(lib.hq_topk_merge_strided(g.data_ptr(), g.data_ptr() + 8 * n, world, Q, k, (3 * n) // 2, 3 * n,
+                                                dev.ptr(out_i), dev.ptr(out_s), dev.stream_ptr()))
+            return out_i, out_s
+        g_ids = g_ids.contiguous().view(torch.int64).view(world, Q, k)
+        g_sc = g_sc.contiguous().view(world, Q, k)
+    else:
+        g_ids = torch.empty((world * Q, k), dtype=local_ids.dtype, device=local_ids.device)
+        g_sc = torch.empty((world * Q, k), dtype=local_scores.dtype, device=local_scores.device)
+        dist.all_gather_into_tensor(g_ids, local_ids.contiguous(), group=group)
+        dist.all_gather_into_tensor(g_sc, local_scores.contiguous(), group=group)
+        g_ids, g_sc = g_ids.view(world, Q, k), g_sc.view(world, Q, k)
+        if merge_on_host or not local_ids.is_cuda:
+            i, s = merge_topk_host(g_ids.cpu().numpy(), g_sc.cpu().numpy(), k)
+            return torch.from_numpy(i).to(local_ids.device), torch.from_numpy(s).to(local_scores.device)
     from ._lib import check, lib
     out_i = torch.empty((Q, k), dtype=torch.int64, device=local_ids.device)
     out_s = torch.empty((Q, k), dtype=torch.float32, device=local_ids.device)

@@ -352,6 +352,15 @@ def prepare_queries(db: EmbeddingDatabase, queries) -> Tuple[torch.Tensor, torch
     return q, q_idx, row_lengths(q_idx, db.layout), row_norms(q)
 
 
+def packed_result_buffers(Q: int, k: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """ids int64 [Q, k] and scores float32 [Q, k] carved out of ONE allocation (ids first), so that a row-sharded
+    search can ship both with a single all-gather (`distributed.allgather_merge`)."""
+    buf = torch.empty(3 * Q * k, dtype=torch.int32, device=device)
+    ids = buf[: 2 * Q * k].view(torch.int64).view(Q, k)
+    scores = buf[2 * Q * k:].view(torch.float32).view(Q, k)
+    return ids, scores
+
+
 def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: bool = True,
                  work_bytes: int = 4 << 30, return_mask: bool = False, trace: Optional[FilterTrace] = None,
                  rerank: str = "auto", filter_impl: str = "auto", filter_scope: str = "shard", group=None,
@@ -366,8 +375,7 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
     q, q_idx, q_lens, q_norms = prepare_queries(db, queries)
     _end(tok)
     Q, N, d = q.shape[0], db.N, db.device
-    ids = torch.empty((Q, k), dtype=torch.int64, device=d)
-    out_scores = torch.empty((Q, k), dtype=torch.float32, device=d)
+    ids, out_scores = packed_result_buffers(Q, k, d)
     if N == 0 or Q == 0:
         ids.fill_(-1)
         out_scores.fill_(-1.0)
@@ -397,9 +405,11 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
         if filter_impl in ("fast", "fast_fp32") and not fast:
             raise ValueError("the fast filter needs dense index rows (all stored lengths structural) and L <= 3")
         if fast:
-            # The fast path also needs dense QUERY index rows.  The test runs on the device and is read back only
-            # after everything has been launched (a read-back here would drain the stream on every call); a batch
-            # with a sparse query is searched again through the exact path.
+            # The fast path also needs dense QUERY index rows.  The test runs on the device; its read-back sits
+            # right before the filter launch (below), after every other query-side kernel has been queued, so the
+            # host prepares batch i+1 while batch i is still running and the stream only drains the tiny
+            # query-side kernels.  (Reading it back after the rerank launch cost ~0.3 ms of idle GPU per batch:
+            # the host could not start on the next batch before this one had finished.)
             dense_queries = (q_lens == db._keff).all()
     if fast or not use_filter:
         work_bytes = max(work_bytes, 4 * N * Q) if rerank == "bf16" else work_bytes
@@ -414,6 +424,14 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
     scores = torch.empty((qc, N), dtype=torch.float32, device=d) if need_scores else None
     mask = torch.zeros((qc, words), dtype=torch.int32, device=d)
     masks = [] if return_mask else None
+    if dense_queries is not None and not bool(dense_queries.item()):
+        # a batch with a sparse query (an exactly-zero block mean at the end of an index row) goes through the exact path
+        if filter_impl in ("fast", "fast_fp32"):
+            raise ValueError("the fast filter needs dense index rows (all stored lengths structural) and L <= 3")
+        del mask, scores
+        return search_batch(db, queries, k, use_filter=use_filter, work_bytes=work_bytes, return_mask=return_mask, trace=trace,
+                            rerank=rerank, filter_impl="exact", filter_scope=filter_scope, group=group,
+                            filter_scratch_bytes=filter_scratch_bytes)
     with torch.cuda.device(d):
         for s in range(0, Q, qc):
             e = min(Q, s + qc)
@@ -451,14 +469,6 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
             check(lib.hq_topk_from_scores(dev.ptr(scores), scores.stride(0), N, nq, k, db.id_base,
                                           dev.ptr(ids[s:e]), dev.ptr(out_scores[s:e]), dev.stream_ptr()))
             _end(tok)
-    if dense_queries is not None and not bool(dense_queries.item()):
-        if filter_impl in ("fast", "fast_fp32"):
-            raise ValueError("the fast filter needs dense index rows (all stored lengths structural) and L <= 3")
-        if trace is not None:
-            trace.n_alive.clear(); trace.n_pass.clear(); trace.n_out.clear()
-        return search_batch(db, queries, k, use_filter=use_filter, work_bytes=work_bytes, return_mask=return_mask, trace=trace,
-                            rerank=rerank, filter_impl="exact", filter_scope=filter_scope, group=group,
-                            filter_scratch_bytes=filter_scratch_bytes)
     if return_mask:
         return ids, out_scores, (torch.cat(masks) if masks else None)
     return ids, out_scores

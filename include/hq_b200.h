@@ -281,6 +281,11 @@ int hq_pearson01_matrix(const double* a, int64_t M, int64_t a_stride, const doub
  * entries with id < 0 are empty. */
 int hq_topk_merge(const int64_t* in_ids, const float* in_scores, int P, int Q, int k,
                   int64_t* out_ids, float* out_scores, void* stream);
+/* Same merge for results gathered as ONE packed block per shard ([Q, k] int64 ids followed by [Q, k] float32
+ * scores, a single all-gather): shard p's lists start at in_ids + p * ids_shard_stride (int64 elements) and
+ * in_scores + p * scores_shard_stride (float elements). */
+int hq_topk_merge_strided(const int64_t* in_ids, const float* in_scores, int P, int Q, int k, int64_t ids_shard_stride,
+                          int64_t scores_shard_stride, int64_t* out_ids, float* out_scores, void* stream);
 
 /* ---- a11: core progressive search, per-level similarity ------------------
  * core/search_engine.py:111-189 (compare_indices_at_level): sims [N, n_levels]

@@ -152,6 +152,17 @@ for j in range(Q):
     i, s = O.topk_stable(np.arange(N), O.cosine01(qs[j], db).astype(np.float32), k)
     assert list(gi[j].numpy()) == list(i), (rank, j, gi[j], i)
 assert list(gi[0][:2].numpy()) == [10, 300]
+# packed results (what search_batch returns): ids and scores are views of one buffer -> ONE all-gather
+from hilbert_quantization_b200.search import packed_result_buffers
+pi, ps = packed_result_buffers(Q, k, "cpu")
+pi.copy_(torch.from_numpy(ids)); ps.copy_(torch.from_numpy(sc))
+calls = []
+real = dist.all_gather_into_tensor
+dist.all_gather_into_tensor = lambda *a, **kw: (calls.append(1), real(*a, **kw))[1]
+gi2, gs2 = allgather_merge(pi, ps, k, merge_on_host=True)
+dist.all_gather_into_tensor = real
+assert len(calls) == 1, calls
+assert torch.equal(gi2, gi) and torch.equal(gs2, gs)
 dist.destroy_process_group()
 print("rank", rank, "ok")
 '''

@@ -413,6 +413,16 @@ def test_topk_merge_kernel(hq):
     check(lib.hq_topk_merge(dv.ptr(ti), dv.ptr(ts), P, Q, k, dv.ptr(oi), dv.ptr(os_), dv.stream_ptr()))
     wi, ws = merge_topk_host(ids, sc, k)
     assert np.array_equal(oi.cpu().numpy(), wi) and np.array_equal(os_.cpu().numpy(), ws)
+    # packed layout of the single all-gather: per shard [Q*k int64 ids | Q*k float32 scores]
+    n = Q * k
+    blocks = np.zeros((P, 3 * n), dtype=np.int32)
+    blocks[:, : 2 * n] = ids.reshape(P, n).view(np.int32)
+    blocks[:, 2 * n:] = sc.reshape(P, n).view(np.int32)
+    tb = dev_t(blocks)
+    oi.fill_(0); os_.fill_(0)
+    check(lib.hq_topk_merge_strided(tb.data_ptr(), tb.data_ptr() + 8 * n, P, Q, k, 3 * n // 2, 3 * n, dv.ptr(oi), dv.ptr(os_),
+                                    dv.stream_ptr()))
+    assert np.array_equal(oi.cpu().numpy(), wi) and np.array_equal(os_.cpu().numpy(), ws)
 
 
 def test_readme_surface(hq):
