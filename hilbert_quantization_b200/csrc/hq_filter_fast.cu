@@ -20,6 +20,7 @@
 #include "hq_common.cuh"
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace {
@@ -542,7 +543,8 @@ struct ListParams {
 
 constexpr int kMaxSegs = 320;
 constexpr int kCutCap = 2048;
-constexpr int kListThreads = 1024;    // one query per SM at a time (two 512-thread CTAs per SM measured 7 % slower)
+constexpr int kListThreads = 1024;    // one query per SM at a time (two 512-thread CTAs per SM measured 7 % slower at 1 M rows)
+constexpr int64_t kListSmallShardRows = 400000;   // shards up to this many rows run two 512-thread CTAs per SM instead
 constexpr int kU = 4;                 // independent list loads in flight per thread (128-bit each in the list passes)
 constexpr int kU2 = 2;                // same for the compaction pass, which reads three arrays
 constexpr uint32_t kChunk = kU * 128, kChunk2 = kU2 * 128;      // entries a warp takes at a time
@@ -1281,13 +1283,19 @@ extern "C" int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, c
         lp.n_out = n_out; lp.fallback = fallback;
         // compaction scratch: shared with the generic cascade, which runs afterwards ([grid][N] keys + rows)
         lp.tmp_stride = (int64_t)lists.n_segs * lists.seg_cap;
-        int lgrid = hq_cached_sm_count();
+        // Large shards: one 1024-thread CTA per SM (two 512-thread CTAs measured 7 % slower at 1 M rows).  Small
+        // shards (a GPU's share of a row-sharded database): the per-query fixed work (segment table, plane popcount,
+        // histogram clears / scans, cut-bin ranking: ~15 block-wide barriers) dominates the list streaming, so two
+        // 512-thread CTAs per SM overlap one query's barriers with the other's loads.
+        static const int forced_threads = [] { const char* e = getenv("HQ_LIST_CTA_THREADS"); return e ? atoi(e) : 0; }();
+        int lthreads = forced_threads == 256 || forced_threads == 512 || forced_threads == 1024 ? forced_threads : (N <= kListSmallShardRows ? 512 : kListThreads);
+        int lgrid = hq_cached_sm_count() * (kListThreads / lthreads);
         if (lgrid > Q) lgrid = Q;
         while (lgrid > 1 && (int64_t)lgrid * lp.tmp_stride > (int64_t)grid * N) --lgrid;
         HQ_REQUIRE(lp.tmp_stride <= (int64_t)grid * N, "internal: candidate lists larger than the cascade scratch");
         lp.tmp_keys = reinterpret_cast<float*>(sc_keys);
         lp.tmp_rows = sc_keys + (int64_t)lgrid * lp.tmp_stride;
-        k_filter_cascade_lists<<<lgrid, kListThreads, 0, st>>>(lp);
+        k_filter_cascade_lists<<<lgrid, lthreads, 0, st>>>(lp);
         HQ_LAUNCH_OK("k_filter_cascade_lists");
         cp.only = fallback;
     }

@@ -299,38 +299,72 @@ __global__ void __launch_bounds__(128) k_rerank_tc_merge(const TcParams p, const
     }
     if (tid < KP) { top_val[tid] = -FLT_MAX; top_idx[tid] = -1; }
     __syncthreads();
-    // KP rounds of block-wide arg-best (value desc, id asc).  The first version ranked every candidate
-    // against every other one (O(M^2)): 0.6 ms of a 1.0 ms single-query search when one query owns ~100 units.
-    __shared__ float r_val[4];
-    __shared__ int32_t r_idx[4], r_pos[4];
-    for (int round = 0; round < KP; ++round) {
-        float bv = -FLT_MAX;
-        int32_t bi = 0x7fffffff, bp = -1;
-        for (int e = tid; e < M; e += blockDim.x) {
-            const int32_t id = c_idx[e];
-            if (id < 0) continue;
-            const float v = c_val[e];
-            if (v > bv || (v == bv && id < bi)) { bv = v; bi = id; bp = e; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int32_t oi = __shfl_xor_sync(0xffffffffu, bi, o), op = __shfl_xor_sync(0xffffffffu, bp, o);
-            if (op >= 0 && (bp < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; bp = op; }
-        }
-        if (lane == 0) { r_val[warp] = bv; r_idx[warp] = bi; r_pos[warp] = bp; }
-        __syncthreads();
-        if (tid == 0) {
-            int w = -1;
-            for (int i = 0; i < 4; ++i)
-                if (r_pos[i] >= 0 && (w < 0 || r_val[i] > r_val[w] || (r_val[i] == r_val[w] && r_idx[i] < r_idx[w]))) w = i;
-            if (w >= 0) {
-                top_val[round] = r_val[w]; top_idx[round] = r_idx[w];
-                c_idx[r_pos[w]] = -1;                      // taken
+    // Shortlist = best KP of the M candidates (value desc, id asc), in two levels so that no round needs a block-wide
+    // barrier: every warp extracts the best KP of its own quarter of the candidates (KP rounds of a warp arg-best over
+    // shared memory, __syncwarp only), then warp 0 merges the 4 x KP winners held two per lane in registers.  (The
+    // first version ranked every candidate against every other one, O(M^2): 0.6 ms of a 1.0 ms single-query search;
+    // the second ran KP block-wide rounds with two __syncthreads and a serial pick each: 60 us per 1024-query batch.)
+    __shared__ float w_val[4 * KP];
+    __shared__ int32_t w_idx[4 * KP];
+    {
+        const int per = (M + 3) / 4, e0 = warp * per, e1 = min(M, e0 + per);
+        for (int round = 0; round < KP; ++round) {
+            float bv = -FLT_MAX;
+            int32_t bi = 0x7fffffff, bp = -1;
+            for (int e = e0 + lane; e < e1; e += 32) {
+                const int32_t id = c_idx[e];
+                if (id < 0) continue;
+                const float v = c_val[e];
+                if (bp < 0 || v > bv || (v == bv && id < bi)) { bv = v; bi = id; bp = e; }
             }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int32_t oi = __shfl_xor_sync(0xffffffffu, bi, o), op = __shfl_xor_sync(0xffffffffu, bp, o);
+                if (op >= 0 && (bp < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; bp = op; }
+            }
+            if (lane == 0) {
+                w_val[warp * KP + round] = bp >= 0 ? bv : -FLT_MAX;
+                w_idx[warp * KP + round] = bp >= 0 ? bi : -1;
+                if (bp >= 0) c_idx[bp] = -1;                   // taken
+            }
+            __syncwarp();
         }
-        __syncthreads();
     }
+    __syncthreads();
+    if (warp == 0) {
+        constexpr int PER = (4 * KP + 31) / 32;
+        float mv[PER];
+        int32_t mi[PER];
+#pragma unroll
+        for (int s = 0; s < PER; ++s) {
+            const int e = lane + 32 * s;
+            mv[s] = e < 4 * KP ? w_val[e] : -FLT_MAX;
+            mi[s] = e < 4 * KP ? w_idx[e] : -1;
+        }
+        for (int round = 0; round < KP; ++round) {
+            float bv = -FLT_MAX;
+            int32_t bi = -1, bs = -1;
+#pragma unroll
+            for (int s = 0; s < PER; ++s)
+                if (mi[s] >= 0 && (bi < 0 || mv[s] > bv || (mv[s] == bv && mi[s] < bi))) { bv = mv[s]; bi = mi[s]; bs = s; }
+            int bl = lane;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+                if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && (oi < bi || (oi == bi && ol < bl))))) { bv = ov; bi = oi; bl = ol; }
+            }
+            if (bi >= 0 && bl == lane) {
+#pragma unroll
+                for (int s = 0; s < PER; ++s)
+                    if (s == bs) mi[s] = -1;
+            }
+            if (lane == 0) { top_val[round] = bi >= 0 ? bv : -FLT_MAX; top_idx[round] = bi; }
+        }
+    }
+    __syncthreads();
     // exact fp32 cosine of the shortlisted rows (one warp per candidate)
     const float nq = q_norm[q];
     const float* qv = q_f32 + (int64_t)q * q_stride;

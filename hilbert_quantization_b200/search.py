@@ -352,6 +352,40 @@ def prepare_queries(db: EmbeddingDatabase, queries) -> Tuple[torch.Tensor, torch
     return q, q_idx, row_lengths(q_idx, db.layout), row_norms(q)
 
 
+_SIDE_STREAMS: dict = {}
+_FLAG_POOL: list = []          # pinned one-byte buffers (allocating pinned memory per call would synchronise the device)
+
+
+class _DenseCheck:
+    """`(q_lens == keff).all()` evaluated on the main stream, read back through a side stream so that the host can
+    wait for it without waiting for kernels launched afterwards on the main stream."""
+
+    def __init__(self, q_lens: torch.Tensor, db: "EmbeddingDatabase"):
+        d = q_lens.device
+        flag = (q_lens == db._keff).all()
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(d))
+        side = _SIDE_STREAMS.get(d)
+        if side is None:
+            side = _SIDE_STREAMS[d] = torch.cuda.Stream(device=d, priority=-1)
+        try:
+            self.host = _FLAG_POOL.pop()
+        except IndexError:
+            self.host = torch.empty(1, dtype=torch.bool).pin_memory()
+        self.done = torch.cuda.Event()
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            self.host.copy_(flag.reshape(1), non_blocking=True)
+            self.done.record(side)
+        flag.record_stream(side)
+
+    def result(self) -> bool:
+        self.done.synchronize()
+        ok = bool(self.host[0])
+        _FLAG_POOL.append(self.host)
+        return ok
+
+
 def packed_result_buffers(Q: int, k: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
     """ids int64 [Q, k] and scores float32 [Q, k] carved out of ONE allocation (ids first), so that a row-sharded
     search can ship both with a single all-gather (`distributed.allgather_merge`)."""
@@ -405,12 +439,13 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
         if filter_impl in ("fast", "fast_fp32") and not fast:
             raise ValueError("the fast filter needs dense index rows (all stored lengths structural) and L <= 3")
         if fast:
-            # The fast path also needs dense QUERY index rows.  The test runs on the device; its read-back sits
-            # right before the filter launch (below), after every other query-side kernel has been queued, so the
-            # host prepares batch i+1 while batch i is still running and the stream only drains the tiny
-            # query-side kernels.  (Reading it back after the rerank launch cost ~0.3 ms of idle GPU per batch:
-            # the host could not start on the next batch before this one had finished.)
-            dense_queries = (q_lens == db._keff).all()
+            # The fast path also needs dense QUERY index rows.  The test runs on the device and its result travels to
+            # the host on a SIDE stream that only waits for the query-side kernels; the filter and the rerank are
+            # launched speculatively on the main stream and the host looks at the flag after the launches.  The host
+            # therefore never waits for the big kernels of this batch (a read-back on the main stream did: ~0.3 ms of
+            # idle GPU per batch while the host prepared the next one); a batch with a sparse query is searched
+            # again through the exact path.
+            dense_queries = _DenseCheck(q_lens, db)
     if fast or not use_filter:
         work_bytes = max(work_bytes, 4 * N * Q) if rerank == "bf16" else work_bytes
     qc = int(max(1, min(Q, work_bytes // (4 * N)))) if not (rerank == "bf16" and (fast or not use_filter)) else Q
@@ -424,14 +459,6 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
     scores = torch.empty((qc, N), dtype=torch.float32, device=d) if need_scores else None
     mask = torch.zeros((qc, words), dtype=torch.int32, device=d)
     masks = [] if return_mask else None
-    if dense_queries is not None and not bool(dense_queries.item()):
-        # a batch with a sparse query (an exactly-zero block mean at the end of an index row) goes through the exact path
-        if filter_impl in ("fast", "fast_fp32"):
-            raise ValueError("the fast filter needs dense index rows (all stored lengths structural) and L <= 3")
-        del mask, scores
-        return search_batch(db, queries, k, use_filter=use_filter, work_bytes=work_bytes, return_mask=return_mask, trace=trace,
-                            rerank=rerank, filter_impl="exact", filter_scope=filter_scope, group=group,
-                            filter_scratch_bytes=filter_scratch_bytes)
     with torch.cuda.device(d):
         for s in range(0, Q, qc):
             e = min(Q, s + qc)
@@ -469,6 +496,16 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
             check(lib.hq_topk_from_scores(dev.ptr(scores), scores.stride(0), N, nq, k, db.id_base,
                                           dev.ptr(ids[s:e]), dev.ptr(out_scores[s:e]), dev.stream_ptr()))
             _end(tok)
+    if dense_queries is not None and not dense_queries.result():
+        # a batch with a sparse query (an exactly-zero block mean at the end of an index row): exact path
+        if filter_impl in ("fast", "fast_fp32"):
+            raise ValueError("the fast filter needs dense index rows (all stored lengths structural) and L <= 3")
+        if trace is not None:
+            trace.n_alive.clear(); trace.n_pass.clear(); trace.n_out.clear()
+        del mask, scores, ids, out_scores
+        return search_batch(db, queries, k, use_filter=use_filter, work_bytes=work_bytes, return_mask=return_mask, trace=trace,
+                            rerank=rerank, filter_impl="exact", filter_scope=filter_scope, group=group,
+                            filter_scratch_bytes=filter_scratch_bytes)
     if return_mask:
         return ids, out_scores, (torch.cat(masks) if masks else None)
     return ids, out_scores

@@ -1,9 +1,14 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest50.log 2>&1; tail -6 gpurun_out/pytest50.log
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke50.log 2>&1; tail -2 gpurun_out/smoke50.log
-python bench.py > gpurun_out/bench50.json 2>gpurun_out/bench50.err; tail -c 600 gpurun_out/bench50.err
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest54.log 2>&1; tail -3 gpurun_out/pytest54.log
+for rows in 125000 250000; do
+ for th in 512 256; do
+  HQ_LIST_CTA_THREADS=$th python bench.py --rows $rows --steps 50 --no-cpu-baseline > gpurun_out/b54_${rows}_${th}.json 2>gpurun_out/b54.err
+  python -c "
+import json,sys
+d=json.loads(open('gpurun_out/b54_${rows}_${th}.json').read().strip().splitlines()[-1]); print('rows', $rows, 'threads', $th, 'qps %.0f ms %.3f' % (d['value'], d['ms_per_step']), d['phases_ms_per_step'])"
+ done
+done
+python bench.py --steps 50 --no-cpu-baseline > gpurun_out/b54_1m.json 2>gpurun_out/b54.err
 python -c "
-import json
-d=json.loads(open('gpurun_out/bench50.json').read().strip().splitlines()[-1]); print('C2', d['value'], d['e2e'], d['phases_ms_per_step'], d['roofline']['frac'], d['map_index']['value'], d['cpu_baseline'])"
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench50_ref.json 2>gpurun_out/bench50_ref.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches50.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu50.log 2>&1
-tail -3 gpurun_out/launches50.csv
+import json,sys
+d=json.loads(open('gpurun_out/b54_1m.json').read().strip().splitlines()[-1]); print('1M qps %.0f ms %.3f' % (d['value'], d['ms_per_step']), d['phases_ms_per_step'])"
+python bench_extra.py --only c1 2>&1 | tail -1 | cut -c1-400
