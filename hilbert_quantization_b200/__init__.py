@@ -6,7 +6,7 @@ from .exceptions import HilbertQuantizationError                              # 
 from .dimension import PowerOf4DimensionCalculator, rag_optimal_dimensions    # noqa: F401
 from .mapper import HilbertCurveMapper, HilbertCurveMapperImpl               # noqa: F401
 from .index import (HierarchicalIndexGenerator, HierarchicalIndexGeneratorImpl,   # noqa: F401
-                    StreamingHilbertIndexGenerator, index_from_grids, map_and_index)
+                    StreamingHilbertIndexGenerator, index_from_grids, map_and_index, map_parameter_stream)
 from .quantize import FrameQuantizer, dequantize_u8_batch, quantize_u8_batch  # noqa: F401
 from .search import (EmbeddingDatabase, ProgressiveSimilaritySearchEngine, RAGSearchEngineImpl,   # noqa: F401
                      SearchResult, comprehensive_scores, search_batch)

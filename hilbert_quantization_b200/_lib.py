@@ -30,6 +30,7 @@ SIGNATURES = {
     "hq_fused_scratch_bytes_min_level": (_i64, [_i64, _i32, _i32, _i32]),
     "hq_map_index_fused": (_i32, [_p, _i32, _i64, _i64, _i64, _i32, _p, _i64, _p, _i64, _p, _i32, _i32, _p, _i64, _p, _i64, _p]),
     "hq_map_index_fused_ml": (_i32, [_p, _i32, _i64, _i64, _i64, _i32, _p, _i64, _p, _i64, _p, _i32, _i32, _i32, _p, _i64, _p, _i64, _p]),
+    "hq_map_index_stream": (_i32, [_p, _i64, _i32, _p, _p, _i32, _i32, _i32, _p, _i64, _p, _i64, _p]),
     "hq_block_means": (_i32, [_p, _i64, _i32, _i32, _i64, _i32, _i32, _p, _p, _i32, _p, _i64, _p]),
     "hq_quantize_u8": (_i32, [_p, _i64, _i64, _i64, _p, _i64, _p, _p]),
     "hq_dequantize_u8": (_i32, [_p, _i64, _i64, _i64, _p, _p, _i64, _p]),

@@ -570,7 +570,7 @@ __global__ void __launch_bounds__(kBlock, 3) k_tile_pass_bulk(const __grid_const
     // floats of the chunk that exist in the source (the rest of the tile is zero padding)
     auto chunk_valid = [&](int64_t chunk) -> uint32_t {
         const int64_t item = chunk / tiles_per_item, tile = chunk - item * tiles_per_item;
-        const int64_t left = p.D - tile * 4096;
+        const int64_t left = (item == p.N - 1 ? p.D_last : p.D) - tile * 4096;
         return left <= 0 ? 0u : (left >= 4096 ? 4096u : (uint32_t)left);
     };
     auto issue_load = [&](int64_t chunk, int st) {

@@ -25,6 +25,7 @@ struct TileParams {
     const float* src;
     int direction;          // 0 stream->grid, 1 grid->stream
     int64_t N, D, src_stride;
+    int64_t D_last;         // values of the LAST item (parameter streams: the tail grid is partially filled); == D otherwise
     int log2n;              // whole-grid side
     int log2t;              // tile side (min(n, 64))
     float* grid_out; int64_t grid_stride;
@@ -477,7 +478,7 @@ extern "C" int64_t hq_fused_scratch_bytes_min_level(int64_t N, int n, int pyr_mo
 static int fused_impl(const float* src, int direction, int64_t N, int64_t D, int64_t src_stride, int n, float* grid_out,
                       int64_t grid_stride, float* stream_out, int64_t stream_stride, const int32_t* plan, int plan_len,
                       int pyr_mode, int min_level, void* idx_out, int64_t idx_stride, void* scratch, int64_t scratch_bytes,
-                      cudaStream_t st) {
+                      cudaStream_t st, int64_t D_last = -1) {
     HQ_REQUIRE(hq_is_pow2(n) && n >= 4 && n <= (1 << 15), "fused path needs a power-of-2 grid side in [4, 32768], got %d", n);
     HQ_REQUIRE(direction == 0 || direction == 1, "direction must be 0 or 1");
     HQ_REQUIRE(pyr_mode == 0 || pyr_mode == 1, "pyr_mode must be 0 or 1");
@@ -495,6 +496,7 @@ static int fused_impl(const float* src, int direction, int64_t N, int64_t D, int
 
     TileParams p{};
     p.src = src; p.direction = direction; p.N = N; p.D = D; p.src_stride = src_stride;
+    p.D_last = D_last < 0 ? D : D_last;
     p.log2n = hq_log2(n); p.log2t = p.log2n > 6 ? 6 : p.log2n;
     p.grid_out = grid_out; p.grid_stride = grid_stride;
     p.stream_out = stream_out; p.stream_stride = stream_stride;
@@ -524,8 +526,10 @@ static int fused_impl(const float* src, int direction, int64_t N, int64_t D, int
         if (direction == 0 && item_pass::bulk_eligible(p)) rc = pyr_mode ? item_pass::launch_bulk<1>(p, st) : item_pass::launch_bulk<0>(p, st);
         else if (direction == 0) rc = pyr_mode ? item_pass::launch<0, 1>(p, st) : item_pass::launch<0, 0>(p, st);
         else rc = pyr_mode ? item_pass::launch<1, 1>(p, st) : item_pass::launch<1, 0>(p, st);
-    } else if (direction == 0 && item_pass::tile_bulk_eligible(p)) {
+    } else if (direction == 0 && item_pass::tile_bulk_eligible(p) && p.D_last % 4 == 0) {
         rc = pyr_mode ? item_pass::launch_tile_bulk<1>(p, st) : item_pass::launch_tile_bulk<0>(p, st);
+    } else if (p.D_last != p.D) {
+        HQ_REQUIRE(false, "a ragged parameter stream needs the bulk tile path (grid side > 64, 16-byte aligned buffers, length %% 4 == 0)");
     } else if (direction == 0) rc = pyr_mode ? launch_tile<0, 1>(p, st) : launch_tile<0, 0>(p, st);
     else rc = pyr_mode ? launch_tile<1, 1>(p, st) : launch_tile<1, 0>(p, st);
     if (rc != HQ_OK) return rc;
@@ -551,6 +555,23 @@ extern "C" int hq_map_index_fused_ml(const float* src, int direction, int64_t N,
                                      int64_t idx_stride, void* scratch, int64_t scratch_bytes, void* stream) {
     return fused_impl(src, direction, N, D, src_stride, n, grid_out, grid_stride, stream_out, stream_stride, plan, plan_len,
                       pyr_mode, min_level, idx_out, idx_stride, scratch, scratch_bytes, (cudaStream_t)stream);
+}
+
+// Parameter stream (BASELINE config 4): `total` consecutive float32 values cut into ceil(total / n^2) grids of n x n,
+// the last one zero padded -- the chunking of core/streaming_processor.py:539-582 + _pad_parameters
+// (core/pipeline.py:325-349) + map_to_2d + index, as ONE launch over all grids (the partially filled tail grid used to
+// be a second pair of launches).
+extern "C" int hq_map_index_stream(const float* src, int64_t total, int n, float* grid_out, const int32_t* plan, int plan_len,
+                                   int pyr_mode, int min_level, void* idx_out, int64_t idx_stride, void* scratch,
+                                   int64_t scratch_bytes, void* stream) {
+    HQ_REQUIRE(total >= 0, "negative stream length");
+    HQ_REQUIRE(hq_is_pow2(n) && n > 64, "the stream entry point needs a power-of-2 grid side > 64, got %d", n);
+    if (total == 0) return HQ_OK;
+    const int64_t cells = (int64_t)n * n;
+    const int64_t N = (total + cells - 1) / cells;
+    const int64_t D_last = total - (N - 1) * cells;
+    return fused_impl(src, 0, N, cells, cells, n, grid_out, cells, nullptr, 0, plan, plan_len, pyr_mode, min_level, idx_out, idx_stride,
+                      scratch, scratch_bytes, (cudaStream_t)stream, D_last);
 }
 
 // 32-bit words, no arithmetic: the dtype-preserving 4-byte map / unmap.

@@ -116,6 +116,61 @@ def map_and_index(embeddings: torch.Tensor, n: Optional[int] = None, *, variant:
     raise ValueError(f"unknown index variant {variant!r}")
 
 
+def map_parameter_stream(stream: torch.Tensor, n: int = 4096, *, variant: str = "C", index_space: Optional[int] = None,
+                         want_grid: bool = True, grid_out: Optional[torch.Tensor] = None,
+                         idx_out: Optional[torch.Tensor] = None):
+    """A flat float32 parameter stream (BASELINE config 4: a model's `named_parameters()` concatenated,
+    core/streaming_processor.py:414-432,539-582) -> ceil(len / n^2) Hilbert grids of n x n with their hierarchical
+    indices, the last grid zero padded (core/pipeline.py:325-349).  One launch over all grids when the stream is
+    16-byte aligned and its length a multiple of 4 (hq_map_index_stream); otherwise the full grids and the tail grid go
+    through two fused passes.  Returns (grids [N, n, n] or None, indices [N, S])."""
+    d = dev.require_cuda(stream.device)
+    if stream.dtype != torch.float32 or stream.dim() != 1:
+        raise TypeError("parameter stream must be a 1-D float32 tensor")
+    stream = stream.contiguous()
+    total, cells = int(stream.numel()), n * n
+    N = -(-total // cells)
+    pyr_mode = 0
+    if variant == "C":
+        plan, _, ml = plans.c_plan(n, "compact")
+        key = ("C", n, "compact")
+    elif variant == "A":
+        S = int(index_space if index_space is not None else n)
+        plan, ml = plans.a_plan(n, S)
+        key = ("A", n, S)
+    elif variant == "B":
+        S = int(index_space if index_space is not None else n)
+        plan, ml = plans.b_plan(n, S)
+        key, pyr_mode = ("B", n, S), 1
+    else:
+        raise ValueError(f"unknown index variant {variant!r}")
+    grid = grid_out
+    if grid is None and want_grid:
+        grid = torch.empty((N, n, n), dtype=torch.float32, device=d)
+    idx = idx_out if idx_out is not None else torch.empty((N, len(plan)), dtype=torch.float64 if pyr_mode else torch.float32, device=d)
+    if N == 0:
+        return grid, idx
+    one_launch = n > 64 and total % 4 == 0 and stream.data_ptr() % 16 == 0 and (grid is None or grid.data_ptr() % 16 == 0) \
+        and N * n < (1 << 31)
+    if one_launch:
+        plan_t = _plan_tensor(key, plan, d)
+        sb = int(lib.hq_fused_scratch_bytes_min_level(N, n, pyr_mode, min(ml, 6)))
+        scratch = torch.empty(max(sb, 8), dtype=torch.uint8, device=d)
+        with torch.cuda.device(d):
+            check(lib.hq_map_index_stream(dev.ptr(stream), total, n, dev.ptr(grid), dev.ptr(plan_t), int(plan_t.numel()), pyr_mode, ml,
+                                          dev.ptr(idx), idx.stride(0), dev.ptr(scratch), sb, dev.stream_ptr()))
+        return grid, idx
+    full = total // cells
+    if full:
+        fused_pass(stream[: full * cells].view(full, cells), 0, n, cells, plan=plan, plan_key=key, min_level=ml, pyr_mode=pyr_mode,
+                   grid_out=grid[:full].view(full, -1) if grid is not None else None, idx_out=idx[:full])
+    if N > full:
+        tail = total - full * cells
+        fused_pass(stream[full * cells:].view(1, tail), 0, n, tail, plan=plan, plan_key=key, min_level=ml, pyr_mode=pyr_mode,
+                   grid_out=grid[full:].view(1, -1) if grid is not None else None, idx_out=idx[full:])
+    return grid, idx
+
+
 def index_from_grids(grids: torch.Tensor, *, variant: str = "C", index_space: Optional[int] = None, layout: str = "compact"):
     """Hierarchical indices of already-mapped float32 grids [N, n, n] (direction 1 pass)."""
     N, n, _ = grids.shape

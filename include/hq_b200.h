@@ -83,6 +83,13 @@ int hq_map_index_fused_ml(const float* src, int direction, int64_t N, int64_t D,
                           const int32_t* plan, int plan_len, int pyr_mode, int min_level,
                           void* idx_out, int64_t idx_stride,
                           void* scratch, int64_t scratch_bytes, void* stream);
+/* Parameter stream (BASELINE config 4; core/streaming_processor.py:539-582 chunking, core/pipeline.py:325-349
+ * zero padding, then map_to_2d + index per chunk): `total` consecutive float32 values -> ceil(total / n^2) grids of
+ * n x n (n > 64, src and grid_out 16-byte aligned, total % 4 == 0), the last grid zero padded, ONE launch.
+ * grid_out [N, n, n] dense (or NULL); idx_out / plan / scratch as for hq_map_index_fused_ml with N = ceil(total / n^2). */
+int hq_map_index_stream(const float* src, int64_t total, int n, float* grid_out, const int32_t* plan, int plan_len,
+                        int pyr_mode, int min_level, void* idx_out, int64_t idx_stride, void* scratch,
+                        int64_t scratch_bytes, void* stream);
 int hq_map_index_fused(const float* src, int direction, int64_t N, int64_t D, int64_t src_stride, int n,
                        float* grid_out, int64_t grid_stride,
                        float* stream_out, int64_t stream_stride,

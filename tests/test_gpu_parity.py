@@ -197,6 +197,33 @@ def test_fused_map_index_batch(hq, n, D, N):
     assert torch.equal(idx2, idx)
 
 
+@pytest.mark.parametrize("n,total", [(128, 3 * 128 * 128 + 5000), (256, 65536 * 2), (128, 128 * 128 - 4), (256, 70000),
+                                     (128, 2 * 128 * 128 + 4098)])
+def test_parameter_stream_ragged_tail(hq, n, total):
+    """BASELINE config 4 shape: a flat parameter stream cut into n x n grids, the last one zero padded, ONE launch
+    (hq_map_index_stream); total = 2 * 128 * 128 + 4098 is not a multiple of 4 -> two-pass fallback, same results."""
+    rng = np.random.default_rng(total)
+    stream = (0.02 * rng.standard_normal(total)).astype(np.float32)
+    cells = n * n
+    N = -(-total // cells)
+    padded = np.zeros(N * cells, dtype=np.float32)
+    padded[:total] = stream
+    grids_want = O.map_to_2d_batch(padded.reshape(N, cells), n)
+    t = dev_t(stream)
+    grids, idx = hq.map_parameter_stream(t, n, variant="C")
+    assert np.array_equal(grids.cpu().numpy(), grids_want)
+    want = O.index_c_batch_compact(grids_want)
+    assert idx.shape == want.shape and np.abs(idx.cpu().numpy() - want).max() <= 1e-8        # values ~ 0.02: 3e-7 relative
+    # same numbers as the per-grid API on the padded stream
+    g2, i2 = hq.map_and_index(dev_t(padded.reshape(N, cells)), n, variant="C")
+    assert torch.equal(g2, grids) and torch.equal(i2, idx)
+    _, b = hq.map_parameter_stream(t, n, variant="B", index_space=n, want_grid=False)
+    bw = np.stack([O.index_b(gw, n) for gw in grids_want])
+    assert np.array_equal(b.cpu().numpy(), bw)
+    back = hq.HilbertCurveMapper().map_from_2d_batch(grids).cpu().numpy().reshape(-1)
+    assert np.array_equal(back[:total], stream) and not back[total:].any()
+
+
 def test_index_c_general_shapes(hq):
     rng = np.random.default_rng(11)
     c_gen = hq.HierarchicalIndexGenerator()
