@@ -49,6 +49,7 @@ SIGNATURES = {
     "hq_filter_tc_valid": (_i32, [_p, _i64, C.POINTER(IndexLayout), _p, _i64, _p]),
     "hq_row_norms": (_i32, [_p, _i64, _i64, _i64, _p, _p]),
     "hq_rerank_scores_f32": (_i32, [_p, _p, _i64, _i64, _i64, _p, _p, _i32, _i64, _p, _i64, _p, _i64, _p]),
+    "hq_rerank_scores_sparse_f32": (_i32, [_p, _p, _i64, _i64, _i64, _p, _p, _i32, _i64, _p, _i64, _p, _i64, _p]),
     "hq_topk_from_scores": (_i32, [_p, _i64, _i64, _i32, _i32, _i64, _p, _p, _p]),
     "hq_rerank_scratch_bytes": (_i64, [_i64, _i32]),
     "hq_rerank_topk_f32": (_i32, [_p, _p, _i64, _i64, _i64, _p, _p, _i32, _i64, _p, _i64, _i32, _i64, _p, _p, _p, _i64, _p]),

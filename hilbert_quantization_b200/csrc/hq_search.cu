@@ -383,6 +383,55 @@ __global__ void __launch_bounds__(256) k_rerank_scores(const float* __restrict__
 }
 
 // ------------------------------------------------------------------------------------
+// a13 for a handful of queries: exact fp32 cosine of the SURVIVING rows only.  One warp per (query, 32-row mask word):
+// dead rows get -1, a surviving row is scored by the whole warp with the arithmetic of the tensor-core path's exact
+// re-score (k_rerank_tc_merge: lane-strided fmaf chain, xor tree), so both paths return identical scores.  A single
+// query against 1 M x 1536 reads ~45 K surviving rows (0.3 GB) instead of the 3 GB bf16 database.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_rerank_sparse(const float* __restrict__ db, const float* __restrict__ db_norm, int64_t N,
+                                                       int64_t D, int64_t db_stride, const float* __restrict__ qm,
+                                                       const float* __restrict__ q_norm, int Q, int64_t q_stride,
+                                                       const uint32_t* __restrict__ mask, int64_t mask_stride,
+                                                       float* __restrict__ scores, int64_t scores_stride, int vec) {
+    const int lane = threadIdx.x & 31;
+    const int64_t words = (N + 31) / 32;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < (int64_t)Q * words; t += warps) {
+        const int q = (int)(t / words);
+        const int64_t w = t - (int64_t)q * words;
+        uint32_t m = mask ? __ldg(mask + (int64_t)q * mask_stride + w) : 0xffffffffu;
+        if (w * 32 + 32 > N) m &= (1u << (uint32_t)(N - w * 32)) - 1u;
+        const float nq = __ldg(q_norm + q);
+        const float* qv = qm + (int64_t)q * q_stride;
+        float out = -1.0f;
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            const int64_t row = w * 32 + b;
+            const float* rv = db + row * db_stride;
+            float acc = 0.f;
+            if (vec) {
+                for (int64_t i = lane; i < D / 4; i += 32) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(qv) + i);
+                    const float4 c = __ldg(reinterpret_cast<const float4*>(rv) + i);
+                    acc = fmaf(a.x, c.x, acc); acc = fmaf(a.y, c.y, acc); acc = fmaf(a.z, c.z, acc); acc = fmaf(a.w, c.w, acc);
+                }
+            } else {
+                for (int64_t i = lane; i < D; i += 32) acc = fmaf(__ldg(qv + i), __ldg(rv + i), acc);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            const float nc = __ldg(db_norm + row);
+            float sc = 0.f;
+            if (nq != 0.f && nc != 0.f) sc = __fmul_rn(__fadd_rn(__fdiv_rn(acc, __fmul_rn(nq, nc)), 1.0f), 0.5f);
+            if (lane == b) out = sc;
+        }
+        const int64_t row = w * 32 + lane;
+        if (row < N) scores[(int64_t)q * scores_stride + row] = out;
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // per-query top-k of a score row (exact; ties -> lower row id).  One CTA per query.
 // ------------------------------------------------------------------------------------
 constexpr int kMaxK = 1024;
@@ -627,6 +676,23 @@ extern "C" int hq_rerank_scores_f32(const float* db, const float* db_norm, int64
     k_rerank_scores<<<g, 256, 0, (cudaStream_t)stream>>>(db, db_norm, N, D, db_stride, q, q_norm, Q, q_stride, mask, mask_stride,
                                                          scores, scores_stride, vec);
     HQ_LAUNCH_OK("k_rerank_scores");
+    return HQ_OK;
+}
+
+extern "C" int hq_rerank_scores_sparse_f32(const float* db, const float* db_norm, int64_t N, int64_t D, int64_t db_stride, const float* q,
+                                           const float* q_norm, int Q, int64_t q_stride, const uint32_t* mask, int64_t mask_stride,
+                                           float* scores, int64_t scores_stride, void* stream) {
+    HQ_REQUIRE(N >= 0 && Q >= 0 && D > 0, "bad shape");
+    if (N == 0 || Q == 0) return HQ_OK;
+    HQ_REQUIRE(db && db_norm && q && q_norm && scores, "null pointer");
+    HQ_REQUIRE(db_stride >= D && q_stride >= D && scores_stride >= N, "stride too small");
+    HQ_REQUIRE(!mask || mask_stride * 32 >= N, "mask stride too small");
+    const int vec = (D % 4 == 0) && (db_stride % 4 == 0) && (q_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(db) & 15) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(q) & 15) == 0);
+    const int64_t tasks = (int64_t)Q * ((N + 31) / 32);
+    k_rerank_sparse<<<grid_cap((tasks + 7) / 8, 16), 256, 0, (cudaStream_t)stream>>>(db, db_norm, N, D, db_stride, q, q_norm, Q, q_stride,
+                                                                                   mask, mask_stride, scores, scores_stride, vec);
+    HQ_LAUNCH_OK("k_rerank_sparse");
     return HQ_OK;
 }
 

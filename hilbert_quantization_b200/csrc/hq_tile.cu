@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(256) k_pyramid_top(const TileParams p) {
                     val = (P)p.src[item * p.src_stride + off];
                 } else {
                     const int64_t d = (int64_t)hq_xy2d(log2n, x, y);
-                    val = d < p.D ? (P)p.src[item * p.src_stride + d] : (P)0;
+                    val = d < (item == p.N - 1 ? p.D_last : p.D) ? (P)p.src[item * p.src_stride + d] : (P)0;
                 }
             } else {
                 val = sc[(int64_t)off - n_cells - skip];

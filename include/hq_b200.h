@@ -221,6 +221,12 @@ int hq_rerank_scores_f32(const float* db, const float* db_norm, int64_t N, int64
                          const float* q, const float* q_norm, int Q, int64_t q_stride,
                          const uint32_t* mask, int64_t mask_stride,
                          float* scores, int64_t scores_stride, void* stream);
+/* same scores, but only the rows alive in `mask` are read (one warp per surviving row): the latency path for a
+ * handful of queries, where the survivors (a few per cent of the rows) are far less data than the whole database */
+int hq_rerank_scores_sparse_f32(const float* db, const float* db_norm, int64_t N, int64_t D, int64_t db_stride,
+                                const float* q, const float* q_norm, int Q, int64_t q_stride,
+                                const uint32_t* mask, int64_t mask_stride,
+                                float* scores, int64_t scores_stride, void* stream);
 int hq_topk_from_scores(const float* scores, int64_t scores_stride, int64_t N, int Q, int k, int64_t id_base,
                         int64_t* ids, float* out_scores, void* stream);
 int64_t hq_rerank_scratch_bytes(int64_t N, int Q);

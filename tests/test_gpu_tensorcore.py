@@ -40,6 +40,29 @@ def test_tc_rerank_matches_exact_path(hq, N, D, Q, k):
         assert np.abs(su[j].cpu().numpy() - sw).max() < 5e-7
 
 
+@pytest.mark.parametrize("N,D,Q", [(5000, 1536, 1), (20000, 768, 4), (3001, 250, 3), (70000, 1024, 2)])
+def test_sparse_rerank_equals_tensor_core_path(hq, N, D, Q):
+    """Latency path (Q <= 4, what rerank="auto" picks): only the filter's survivors are scored, in exact fp32.
+    Ids and scores must be IDENTICAL to the tensor-core path (which re-scores its shortlist with the same arithmetic)."""
+    rng = np.random.default_rng(N + Q)
+    db = rng.standard_normal((N, D)).astype(np.float32)
+    db[N // 2] = db[3]
+    db[7] = 0.0
+    qs = rng.standard_normal((Q, D)).astype(np.float32)
+    qs[0] = db[3] + 0.001 * rng.standard_normal(D).astype(np.float32)
+    d = hq.EmbeddingDatabase(db)
+    i_auto, s_auto = hq.search_batch(d, qs, 10)                       # auto -> sparse
+    i_sp, s_sp = hq.search_batch(d, qs, 10, rerank="sparse")
+    i_tc, s_tc = hq.search_batch(d, qs, 10, rerank="bf16")
+    assert torch.equal(i_auto, i_sp) and torch.equal(s_auto, s_sp)
+    assert torch.equal(i_sp, i_tc), (i_sp, i_tc)
+    assert torch.equal(s_sp, s_tc)
+    assert set(i_sp[0, :2].tolist()) == {3, N // 2}
+    for j in range(Q):
+        iw, sw = O.progressive_search(qs[j], db, d.n, 10)
+        assert list(i_sp[j, : len(iw)].cpu().numpy()) == list(iw)
+
+
 def test_tc_rerank_sharded_id_base(hq):
     rng = np.random.default_rng(3)
     db = rng.standard_normal((2048, 512)).astype(np.float32)
