@@ -51,6 +51,8 @@ SIGNATURES = {
     "hq_rerank_scores_f32": (_i32, [_p, _p, _i64, _i64, _i64, _p, _p, _i32, _i64, _p, _i64, _p, _i64, _p]),
     "hq_rerank_scores_sparse_f32": (_i32, [_p, _p, _i64, _i64, _i64, _p, _p, _i32, _i64, _p, _i64, _p, _i64, _p]),
     "hq_topk_from_scores": (_i32, [_p, _i64, _i64, _i32, _i32, _i64, _p, _p, _p]),
+    "hq_topk_chunked_scratch_bytes": (_i64, [_i64, _i32, _i32]),
+    "hq_topk_from_scores_chunked": (_i32, [_p, _i64, _i64, _i32, _i32, _i64, _p, _p, _p, _i64, _p]),
     "hq_rerank_scratch_bytes": (_i64, [_i64, _i32]),
     "hq_rerank_topk_f32": (_i32, [_p, _p, _i64, _i64, _i64, _p, _p, _i32, _i64, _p, _i64, _i32, _i64, _p, _p, _p, _i64, _p]),
     "hq_to_bf16": (_i32, [_p, _i64, _i64, _i64, _p, _i64, _p]),

@@ -217,6 +217,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
             const int t1 = min(p.n_tiles, t0 + p.tiles_per_range);
             const int q = m_tile * FM + q_in;
             const bool q_ok = q < p.Q;
+            // A batch of a few queries fills one lane quarter of the last (or only) query tile: the warps of the other
+            // quarters skip the epilogue (single query against 1 M rows: 141 -> ~90 us, the pass becomes HBM bound).
+            const bool warp_has_q = m_tile * FM + ew * 32 < p.Q;
             float tq[3];
 #pragma unroll
             for (int l = 0; l < 3; ++l) tq[l] = (q_ok && l < p.L) ? __ldg(p.tq + (int64_t)l * p.Q + q) : __int_as_float(0x7fc00000);
@@ -245,6 +248,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
                     for (int l = 0; l < 3; ++l) vw_next[l] = l < p.L ? __ldg(p.valid + (int64_t)l * p.valid_pitch + 2 * (t + 1) + half) : 0u;
                 }
                 mbar_wait(&tfull_bar[acc], acc_phase);
+                if (!warp_has_q) {                       // no query in this warp's 32 rows of the tile: release the accumulator, nothing to test
+                    mbar_arrive(&tempty_bar[acc]);
+                    continue;
+                }
                 tc_fence_after();
                 uint32_t r0[32], r1[32], r2[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * ACC_COLS + half * 32;

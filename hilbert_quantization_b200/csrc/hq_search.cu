@@ -436,8 +436,12 @@ __global__ void __launch_bounds__(256) k_rerank_sparse(const float* __restrict__
 // ------------------------------------------------------------------------------------
 constexpr int kMaxK = 1024;
 
+// `parts` > 1: every query's row is cut into `parts` chunks of N scores (the last one clipped at n_total) and CTA
+// (query * parts + part) returns the top-k of its chunk with row ids counted from the start of the row; k_topk_merge
+// then merges the chunk lists.  One CTA walking a whole 1 M-score row took 0.65 ms of a 1.25 ms single-query search.
 __global__ void __launch_bounds__(1024) k_topk_scores(const float* __restrict__ scores, int64_t scores_stride, int64_t N, int k,
-                                                      int64_t id_base, int64_t* __restrict__ ids, float* __restrict__ out_scores) {
+                                                      int64_t id_base, int64_t* __restrict__ ids, float* __restrict__ out_scores,
+                                                      int parts, int64_t n_total) {
     __shared__ uint32_t hist[2048];
     __shared__ uint32_t sh[4];
     __shared__ uint32_t s_warp[32];
@@ -445,7 +449,10 @@ __global__ void __launch_bounds__(1024) k_topk_scores(const float* __restrict__ 
     __shared__ int64_t s_id[kMaxK];
     __shared__ uint32_t s_cnt;
     const int q = blockIdx.x, tid = threadIdx.x;
-    const float* s = scores + (int64_t)q * scores_stride;
+    const int part = q % parts;
+    const float* s = scores + (int64_t)(q / parts) * scores_stride + (int64_t)part * N;
+    id_base += (int64_t)part * N;
+    if (n_total - (int64_t)part * N < N) N = n_total - (int64_t)part * N > 0 ? n_total - (int64_t)part * N : 0;
 
     // how many live entries are there?  (needed when fewer than k survive)
     uint32_t live = 0;
@@ -504,9 +511,9 @@ __global__ void __launch_bounds__(1024) k_topk_scores(const float* __restrict__ 
 }
 
 // merge of P per-shard lists per query; ties -> lower id; id < 0 = empty slot
-__global__ void __launch_bounds__(256) k_topk_merge(const int64_t* __restrict__ in_ids, const float* __restrict__ in_scores, int P,
+__global__ void __launch_bounds__(1024) k_topk_merge(const int64_t* __restrict__ in_ids, const float* __restrict__ in_scores, int P,
                                                     int Q, int k, int64_t ids_shard_stride, int64_t scores_shard_stride,
-                                                    int64_t* __restrict__ out_ids, float* __restrict__ out_scores) {
+                                                    int64_t q_stride, int64_t* __restrict__ out_ids, float* __restrict__ out_scores) {
     extern __shared__ unsigned char smraw[];
     const int M = P * k;
     int64_t* s_id = reinterpret_cast<int64_t*>(smraw);
@@ -514,8 +521,8 @@ __global__ void __launch_bounds__(256) k_topk_merge(const int64_t* __restrict__ 
     const int q = blockIdx.x;
     for (int e = threadIdx.x; e < M; e += blockDim.x) {
         const int p = e / k, j = e - p * k;
-        s_id[e] = in_ids[p * ids_shard_stride + (int64_t)q * k + j];
-        s_val[e] = in_scores[p * scores_shard_stride + (int64_t)q * k + j];
+        s_id[e] = in_ids[p * ids_shard_stride + (int64_t)q * q_stride + j];
+        s_val[e] = in_scores[p * scores_shard_stride + (int64_t)q * q_stride + j];
     }
     for (int j = threadIdx.x; j < k; j += blockDim.x) { out_ids[(int64_t)q * k + j] = -1; out_scores[(int64_t)q * k + j] = -1.0f; }
     __syncthreads();
@@ -703,8 +710,46 @@ extern "C" int hq_topk_from_scores(const float* scores, int64_t scores_stride, i
     if (Q == 0) return HQ_OK;
     HQ_REQUIRE(ids && out_scores && (scores || N == 0), "null pointer");
     HQ_REQUIRE(N < ((int64_t)1 << 31), "N too large for one shard");
-    k_topk_scores<<<Q, 1024, 0, (cudaStream_t)stream>>>(scores, scores_stride, N, k, id_base, ids, out_scores);
+    k_topk_scores<<<Q, 1024, 0, (cudaStream_t)stream>>>(scores, scores_stride, N, k, id_base, ids, out_scores, 1, N);
     HQ_LAUNCH_OK("k_topk_scores");
+    return HQ_OK;
+}
+
+// chunks per query of the two-level top-k (1 = single level): enough CTAs to fill the GPU, chunks of >= 4096 scores
+static int topk_parts(int64_t N, int Q, int k) {
+    int64_t parts = (2 * (int64_t)hq_cached_sm_count() + Q - 1) / Q;
+    if (parts > 256) parts = 256;
+    if (parts > N / 4096) parts = N / 4096;
+    // the merge ranks its parts * k candidates against each other (O(M^2) on one CTA: 244 x 10 candidates took 1.8 ms)
+    if (parts * (int64_t)k > 512) parts = 512 / k;
+    return parts < 2 ? 1 : (int)parts;
+}
+
+extern "C" int64_t hq_topk_chunked_scratch_bytes(int64_t N, int Q, int k) {
+    if (N <= 0 || Q <= 0 || k <= 0) return 0;
+    return (int64_t)Q * topk_parts(N, Q, k) * k * 12;
+}
+
+// Same result as hq_topk_from_scores for FEW queries over LONG rows: two levels (chunk top-k, then merge).
+extern "C" int hq_topk_from_scores_chunked(const float* scores, int64_t scores_stride, int64_t N, int Q, int k, int64_t id_base,
+                                           int64_t* ids, float* out_scores, void* scratch, int64_t scratch_bytes, void* stream) {
+    HQ_REQUIRE(k >= 1 && k <= kMaxK, "k must be in [1, %d]", kMaxK);
+    HQ_REQUIRE(N >= 0 && Q >= 0, "negative size");
+    if (Q == 0) return HQ_OK;
+    HQ_REQUIRE(ids && out_scores && (scores || N == 0), "null pointer");
+    HQ_REQUIRE(N < ((int64_t)1 << 31), "N too large for one shard");
+    const int parts = topk_parts(N, Q, k);
+    if (parts == 1) return hq_topk_from_scores(scores, scores_stride, N, Q, k, id_base, ids, out_scores, stream);
+    HQ_REQUIRE(scratch && scratch_bytes >= hq_topk_chunked_scratch_bytes(N, Q, k), "scratch too small");
+    const int64_t chunk = ((N + parts - 1) / parts + 31) & ~(int64_t)31;        // trailing chunks may be empty
+    int64_t* p_ids = reinterpret_cast<int64_t*>(scratch);                       // [Q][parts][k]
+    float* p_sc = reinterpret_cast<float*>(p_ids + (int64_t)Q * parts * k);
+    k_topk_scores<<<Q * parts, 1024, 0, (cudaStream_t)stream>>>(scores, scores_stride, chunk, k, id_base, p_ids, p_sc, parts, N);
+    HQ_LAUNCH_OK("k_topk_scores");
+    // "shard" p of query q starts at p * k + q * parts * k
+    k_topk_merge<<<Q, parts * k > 256 ? 1024 : 256, (size_t)parts * k * 12, (cudaStream_t)stream>>>(p_ids, p_sc, parts, Q, k, (int64_t)k, (int64_t)k,
+                                                                          (int64_t)parts * k, ids, out_scores);
+    HQ_LAUNCH_OK("k_topk_merge");
     return HQ_OK;
 }
 
@@ -727,8 +772,8 @@ extern "C" int hq_topk_merge_strided(const int64_t* in_ids, const float* in_scor
     HQ_REQUIRE(ids_shard_stride >= (int64_t)Q * k && scores_shard_stride >= (int64_t)Q * k, "shard stride smaller than Q * k");
     const size_t smem = (size_t)P * k * 12;
     HQ_REQUIRE(smem <= 48 * 1024, "P*k too large for the merge kernel");
-    k_topk_merge<<<Q, 256, smem, (cudaStream_t)stream>>>(in_ids, in_scores, P, Q, k, ids_shard_stride, scores_shard_stride, out_ids,
-                                                         out_scores);
+    k_topk_merge<<<Q, P * k > 256 ? 1024 : 256, smem, (cudaStream_t)stream>>>(in_ids, in_scores, P, Q, k, ids_shard_stride, scores_shard_stride, (int64_t)k,
+                                                         out_ids, out_scores);
     HQ_LAUNCH_OK("k_topk_merge");
     return HQ_OK;
 }

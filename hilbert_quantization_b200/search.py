@@ -500,8 +500,10 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
                                            dev.ptr(m), mask.stride(0), dev.ptr(scores), scores.stride(0), dev.stream_ptr()))
             _end(tok)
             tok = _phase("topk")
-            check(lib.hq_topk_from_scores(dev.ptr(scores), scores.stride(0), N, nq, k, db.id_base,
-                                          dev.ptr(ids[s:e]), dev.ptr(out_scores[s:e]), dev.stream_ptr()))
+            tb = int(lib.hq_topk_chunked_scratch_bytes(N, nq, k))
+            tscratch = torch.empty(max(tb, 8), dtype=torch.uint8, device=d)
+            check(lib.hq_topk_from_scores_chunked(dev.ptr(scores), scores.stride(0), N, nq, k, db.id_base,
+                                                  dev.ptr(ids[s:e]), dev.ptr(out_scores[s:e]), dev.ptr(tscratch), tb, dev.stream_ptr()))
             _end(tok)
     if dense_queries is not None and not dense_queries.result():
         # a batch with a sparse query (an exactly-zero block mean at the end of an index row): exact path

@@ -229,6 +229,11 @@ int hq_rerank_scores_sparse_f32(const float* db, const float* db_norm, int64_t N
                                 float* scores, int64_t scores_stride, void* stream);
 int hq_topk_from_scores(const float* scores, int64_t scores_stride, int64_t N, int Q, int k, int64_t id_base,
                         int64_t* ids, float* out_scores, void* stream);
+/* hq_topk_from_scores for FEW queries over LONG rows: the row is cut into chunks (one CTA each), the chunk lists are
+ * merged; identical results (ties -> lower row id).  scratch: hq_topk_chunked_scratch_bytes(N, Q, k). */
+int64_t hq_topk_chunked_scratch_bytes(int64_t N, int Q, int k);
+int hq_topk_from_scores_chunked(const float* scores, int64_t scores_stride, int64_t N, int Q, int k, int64_t id_base,
+                                int64_t* ids, float* out_scores, void* scratch, int64_t scratch_bytes, void* stream);
 int64_t hq_rerank_scratch_bytes(int64_t N, int Q);
 int hq_rerank_topk_f32(const float* db, const float* db_norm, int64_t N, int64_t D, int64_t db_stride,
                        const float* q, const float* q_norm, int Q, int64_t q_stride,

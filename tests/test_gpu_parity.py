@@ -452,6 +452,32 @@ def test_topk_merge_kernel(hq):
     assert np.array_equal(oi.cpu().numpy(), wi) and np.array_equal(os_.cpu().numpy(), ws)
 
 
+@pytest.mark.parametrize("N,Q,k", [(100003, 3, 10), (50000, 1, 100), (9000, 2, 10), (300000, 4, 7)])
+def test_topk_chunked_equals_single_level(hq, N, Q, k):
+    """Two-level top-k (chunk lists + merge) for few queries over long rows == the one-CTA-per-row kernel, ties included."""
+    from hilbert_quantization_b200._lib import lib, check
+    from hilbert_quantization_b200 import _device as dv
+    rng = np.random.default_rng(N + k)
+    sc = np.round(rng.random((Q, N)), 3).astype(np.float32)             # ~1000 distinct values: many exact ties
+    sc[rng.random((Q, N)) < 0.7] = -1.0                                  # dead rows
+    sc[1 % Q, :] = -1.0
+    sc[1 % Q, N - 3:] = 0.5                                              # fewer than k live entries, all in the last chunk
+    t = dev_t(sc)
+    i1 = torch.empty((Q, k), dtype=torch.int64, device="cuda"); s1 = torch.empty((Q, k), dtype=torch.float32, device="cuda")
+    i2 = torch.empty_like(i1); s2 = torch.empty_like(s1)
+    check(lib.hq_topk_from_scores(dv.ptr(t), t.stride(0), N, Q, k, 1000, dv.ptr(i1), dv.ptr(s1), dv.stream_ptr()))
+    nb = int(lib.hq_topk_chunked_scratch_bytes(N, Q, k))
+    scratch = torch.empty(max(nb, 8), dtype=torch.uint8, device="cuda")
+    check(lib.hq_topk_from_scores_chunked(dv.ptr(t), t.stride(0), N, Q, k, 1000, dv.ptr(i2), dv.ptr(s2), dv.ptr(scratch), nb,
+                                          dv.stream_ptr()))
+    assert torch.equal(i1, i2) and torch.equal(s1, s2)
+    for q in range(Q):
+        live = np.nonzero(sc[q] >= 0)[0]
+        order = live[np.lexsort((live, -sc[q, live]))][:k]
+        assert list(i1[q, : len(order)].cpu().numpy() - 1000) == list(order)
+        assert (i1[q, len(order):] == -1).all()
+
+
 def test_readme_surface(hq):
     rng = np.random.default_rng(1)
     eng = hq.ProgressiveSearchEngine(use_frame_caching=True)
