@@ -1,1 +1,2 @@
-timeout 500 python tools/stress.py 0 40 > gpurun_out/stress68.log 2>&1; tail -45 gpurun_out/stress68.log | cut -c1-220
+timeout 600 python tools/stress.py 0 40 > gpurun_out/stress69a.log 2>&1; grep -c "^ok" gpurun_out/stress69a.log; grep -v "^ok" gpurun_out/stress69a.log | cut -c1-260
+timeout 600 python tools/stress.py 7 60 > gpurun_out/stress69b.log 2>&1; grep -c "^ok" gpurun_out/stress69b.log; grep -v "^ok" gpurun_out/stress69b.log | cut -c1-260
