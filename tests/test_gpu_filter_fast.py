@@ -85,6 +85,40 @@ def test_fast_filter_handles_rows_with_short_index_rows(hq, N, D, positive, impl
         assert torch.equal(tf.n_out[l][ok], te.n_out[l][ok])
 
 
+@pytest.mark.parametrize("N,D,Q,offset", [(60000, 1536, 24, 0.03), (60000, 1536, 24, 0.04), (200000, 1536, 8, 0.03)])
+def test_list_cascade_when_the_later_ratio_cuts_bind(hq, N, D, Q, offset):
+    """N(offset, 1) data: the fine level still decides by its threshold (so the streaming list cascade runs, not the
+    per-query fallback) while the coarse levels see similar block means for every row, so MORE rows pass their thresholds
+    than the ratio caps allow and the exact selection at the level-1 / level-2 cuts decides.  Fast == exact filter."""
+    from hilbert_quantization_b200.search import FilterTrace, unpack_mask
+    rng = np.random.default_rng(N + D + Q)
+    db = (rng.standard_normal((N, D)) + offset).astype(np.float32)
+    qs = (rng.standard_normal((Q, D)) + offset).astype(np.float32)
+    db[N // 3] = db[5]
+    qs[0] = db[5]
+    d = hq.EmbeddingDatabase(db)
+    assert d.fast_filter_ok and d.tc_packed is not None
+    tf, te = FilterTrace([], [], []), FilterTrace([], [], [])
+    i_f, s_f, m_f = hq.search_batch(d, qs, 10, return_mask=True, filter_impl="fast", trace=tf, rerank="bf16")
+    i_e, s_e, m_e = hq.search_batch(d, qs, 10, return_mask=True, filter_impl="exact", trace=te, rerank="bf16")
+    L = len(te.n_out)
+    n_pass = [te.n_pass[l].cpu().numpy() for l in range(L)]
+    n_out = [te.n_out[l].cpu().numpy() for l in range(L)]
+    # the scenario this test is about: level 0 decided by the threshold for a good share of the queries (those run the
+    # list cascade; the others take the per-query fallback), the last level's cap binds for most queries
+    assert (n_out[0] == n_pass[0]).mean() > 0.3, (n_out[0], n_pass[0])
+    assert (n_out[L - 1] < n_pass[L - 1]).mean() > 0.5, (n_out[L - 1], n_pass[L - 1])
+    a_f, a_e = unpack_mask(m_f, N), unpack_mask(m_e, N)
+    same = (a_f == a_e).all(axis=1)
+    assert same.sum() >= Q - 2, f"{(~same).sum()} queries differ"
+    for j in np.nonzero(~same)[0]:
+        assert (a_f[j] != a_e[j]).sum() <= 2
+    ok = torch.from_numpy(same).cuda()
+    assert torch.equal(i_f[ok], i_e[ok]) and torch.equal(s_f[ok], s_e[ok])
+    for l in range(L):
+        assert torch.equal(tf.n_out[l][ok].to(torch.int64), te.n_out[l][ok].to(torch.int64))
+
+
 def test_fast_filter_falls_back_on_sparse_data(hq):
     rng = np.random.default_rng(0)
     db = rng.standard_normal((6000, 768)).astype(np.float32)
