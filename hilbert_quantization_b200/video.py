@@ -1,5 +1,9 @@
 """Video-path hierarchical similarity and frame ordering on the device.
 
+core/video_search.py:215-262 (`_hierarchical_search`) with :1316-1328 scores every stored frame against the query
+with the core engine's finest-level comparison: `hierarchical_search` below does that as ONE launch of
+hq_core_level_sims over the whole frame pool.
+
 core/video_storage.py:741-781 (`_traditional_search`, `_calculate_hierarchical_similarity`), :1203-1277
 (`_sort_frames_by_hierarchical_indices`) and :1751-1803 (`_find_optimal_insertion_position`) call a NumPy
 `corrcoef` per frame pair; here every similarity of a call is one launch of hq_pearson01_matrix (float64, like
@@ -106,3 +110,24 @@ def find_optimal_insertion_position(new_indices: np.ndarray, existing_indices: S
     if sims[-1] > best_score:
         best_score, best_position = sims[-1], len(sims)
     return int(best_position)
+
+
+def hierarchical_search(query_indices: np.ndarray, frame_indices: Sequence, max_results: int,
+                        similarity_threshold: float = 0.1, device=None) -> List[Tuple[int, float]]:
+    """core/video_search.py:215-262 (`VideoEnhancedSearchEngine._hierarchical_search`): every frame that has index
+    vectors is scored with `compare_indices_at_level(query, frame, 0)` (:1316-1328 -> core/search_engine.py:111-189),
+    kept when the score is strictly above the threshold, stable descending sort, first `max_results`
+    (frame position, similarity).  `None` entries are frames without index vectors (skipped, :237)."""
+    from .search import ProgressiveSimilaritySearchEngine
+    have = [i for i, f in enumerate(frame_indices) if f is not None]
+    if not have:
+        return []
+    if len(query_indices) == 0:
+        sims = np.zeros(len(have))                      # :1321-1322
+    else:
+        eng = ProgressiveSimilaritySearchEngine(similarity_threshold, device=device)
+        all_levels = eng._level_sims(query_indices, [frame_indices[i] for i in have])
+        sims = all_levels[:, 0] if all_levels.shape[1] else np.zeros(len(have))
+    keep = np.nonzero(sims > similarity_threshold)[0]
+    order = keep[np.argsort(-sims[keep], kind="stable")][:max_results]
+    return [(have[int(j)], float(sims[j])) for j in order]

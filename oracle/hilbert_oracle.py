@@ -839,6 +839,29 @@ def video_insertion_position(new_indices: np.ndarray, existing: Sequence[np.ndar
     return pos
 
 
+def video_hierarchical_search(q: np.ndarray, frames: Sequence, max_results: int, similarity_threshold: float = 0.1):
+    """core/video_search.py:215-262 with :1316-1328: finest-level comparison of the core engine per frame, strict
+    threshold, stable descending sort.  Returns [(frame position, similarity)]."""
+    cands = []
+    for i, f in enumerate(frames):
+        if f is None:
+            continue
+        if len(q) == 0 or len(f) == 0:
+            s = 0.0
+        else:
+            ql, cl = core_parse_levels(len(q), len(q)), core_parse_levels(len(f), len(f))
+            if not ql or not cl:
+                s = 0.0
+            else:
+                a, b = q[ql[0][1]:ql[0][2]], np.asarray(f)[cl[0][1]:cl[0][2]]
+                m = min(len(a), len(b))
+                s = float(core_level_similarity(np.asarray(a[:m], dtype=np.float64), np.asarray(b[:m], dtype=np.float64)[None, :])[0]) if m else 0.0
+        if s > similarity_threshold:
+            cands.append((i, s))
+    cands.sort(key=lambda t: t[1], reverse=True)
+    return cands[:max_results]
+
+
 # ----------------------------------------------------------------------------
 # a11  core progressive search               core/search_engine.py:42-388
 # ----------------------------------------------------------------------------

@@ -578,3 +578,16 @@ def test_video_path_similarity_and_ordering_golden(hq):
         want = np.argsort(-g[f"{tag}_sims"], kind="stable")[:5]
         assert [t[0] for t in top] == list(want)
         assert abs(hq.video.calculate_hierarchical_similarity(q, frames[0]) - g[f"{tag}_sims"][0]) < 1e-12
+
+
+def test_video_hierarchical_search_golden(hq):
+    """core/video_search.py:215-262: every frame scored by the core engine's finest-level comparison in one launch;
+    ids (ties and skipped frames included) identical to the reference's, scores <= 1e-12."""
+    g = load_golden("video_search.npz")
+    for tag in ("S64", "S340", "S21"):
+        frames = [None if i in set(g[f"{tag}_missing"].tolist()) else f for i, f in enumerate(g[f"{tag}_frames"])]
+        res = hq.video.hierarchical_search(g[f"{tag}_query"], frames, 12, float(g[f"{tag}_threshold"]))
+        assert [r[0] for r in res] == list(g[f"{tag}_ids"])
+        assert np.abs(np.array([r[1] for r in res]) - g[f"{tag}_scores"]).max() < 1e-12
+    assert hq.video.hierarchical_search(g["S64_query"], [None, None], 5) == []
+    assert hq.video.hierarchical_search(np.zeros(0), list(g["S64_frames"][:4]), 5) == []

@@ -171,3 +171,13 @@ def test_oracle_video_path_matches_reference_golden():
         assert np.array_equal(sims, g[f"{tag}_sims"])
         assert list(O.video_sort_frames(frames)) == list(g[f"{tag}_order"])
         assert [O.video_insertion_position(q, frames[:15]), O.video_insertion_position(frames[20], frames[:15])] == list(g[f"{tag}_insert_pos"])
+
+
+def test_oracle_video_hierarchical_search_matches_reference_golden():
+    """f4: oracle restatement of core/video_search.py:215-262 (+ :1316-1328) vs VideoEnhancedSearchEngine._hierarchical_search."""
+    g = load_golden("video_search.npz")
+    for tag in ("S64", "S340", "S21"):
+        frames = [None if i in set(g[f"{tag}_missing"].tolist()) else f for i, f in enumerate(g[f"{tag}_frames"])]
+        res = O.video_hierarchical_search(g[f"{tag}_query"], frames, 12, float(g[f"{tag}_threshold"]))
+        assert [r[0] for r in res] == list(g[f"{tag}_ids"])
+        assert np.abs(np.array([r[1] for r in res]) - g[f"{tag}_scores"]).max() < 1e-12
