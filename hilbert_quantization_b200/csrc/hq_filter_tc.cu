@@ -226,6 +226,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
             const bool lists = p.l_rows != nullptr && p.L >= 2 && q_ok;
             const int64_t seg_base = ((int64_t)q * p.n_segs + (range * 2 + half)) * p.seg_cap;
             int seg_pos = 0, seg_flushed = 0;
+            // Byte offset of the next sector of this thread's segment, kept in a register pair and advanced by 32 per flush
+            // (opaque to the compiler: it used to rebuild (q * n_segs + seg) * seg_cap + flushed from the constant bank with
+            // 64-bit multiplies in every flush), and the capacity as a 32-bit value (one compare instead of a 64-bit pair).
+            uint64_t goff = (uint64_t)seg_base * 4u;
+            asm volatile("" : "+l"(goff));
+            const int seg_cap32 = (int)min(p.seg_cap, (int64_t)0x7ffffff0);
             // Per-thread ring of LBUF entries per array, 64 bytes per thread, so that a flush reads its eight
             // entries with two 128-bit loads per array (8 scalar loads per array made the flush 22 % of the
             // kernel's instructions).  The 16-byte chunk index is XORed with (lane >> 1) & 3: the eight lanes of
@@ -292,21 +298,23 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
                             for (int jj = 0; jj < 8; ++jj) {
                                 const int j = g * 8 + jj;
                                 const uint32_t bit = t1w & (1u << j);
-                                const uint32_t addr = sl_addr_x ^ (run & (LBUF * 4 - 1));
                                 const uint32_t roww = row0 + j;
+                                // ring slot = base ^ (run & mask) as ONE lop3 (the compiler split it into an AND and an XOR)
                                 asm volatile(
-                                    "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t"
-                                    "@p st.shared.u32 [%2], %3;\n\t"
-                                    "@p st.shared.u32 [%2+%6], %4;\n\t"
-                                    "@p st.shared.u32 [%2+%7], %5;\n\t"
+                                    "{\n\t.reg .pred p;\n\t.reg .b32 a;\n\tsetp.ne.u32 p, %1, 0;\n\t"
+                                    "lop3.b32 a, %0, %8, %2, 0x6a;\n\t"
+                                    "@p st.shared.u32 [a], %3;\n\t"
+                                    "@p st.shared.u32 [a+%6], %4;\n\t"
+                                    "@p st.shared.u32 [a+%7], %5;\n\t"
                                     "@p add.u32 %0, %0, 4;\n\t}"
                                     : "+r"(run)
-                                    : "r"(bit), "r"(addr), "r"(roww), "r"(r1[j]), "r"(r2[j]), "n"(RING_A_BYTES), "n"(2 * RING_A_BYTES)
+                                    : "r"(bit), "r"(sl_addr_x), "r"(roww), "r"(r1[j]), "r"(r2[j]), "n"(RING_A_BYTES), "n"(2 * RING_A_BYTES),
+                                      "n"(LBUF * 4 - 1)
                                     : "memory");
                             }
                             seg_pos = (int)(run >> 2);
                             if (seg_pos - seg_flushed >= 8) {
-                                if (seg_flushed + 8 <= p.seg_cap) {
+                                if (seg_flushed + 8 <= seg_cap32) {
                                     const uint32_t f0 = sl_addr_x ^ (((uint32_t)seg_flushed * 4u) & (LBUF * 4 - 1));   // chunk of entries f..f+3
                                     const uint32_t f1 = f0 ^ 16u;                                                      // f+4..f+7 (f is a multiple of 8)
                                     // all six loads first, into separate registers: re-using the eight registers of one
@@ -318,11 +326,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
                                         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[a][0]), "=r"(v[a][1]), "=r"(v[a][2]), "=r"(v[a][3]) : "r"(f0 + a * RING_A_BYTES));
                                         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[a][4]), "=r"(v[a][5]), "=r"(v[a][6]), "=r"(v[a][7]) : "r"(f1 + a * RING_A_BYTES));
                                     }
-                                    st_global_256(p.l_rows + seg_base + seg_flushed, v[0]);
-                                    st_global_256(reinterpret_cast<uint32_t*>(p.l_k1) + seg_base + seg_flushed, v[1]);
-                                    if (p.L > 2) st_global_256(reinterpret_cast<uint32_t*>(p.l_k2) + seg_base + seg_flushed, v[2]);
+                                    st_global_256(reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(p.l_rows) + goff), v[0]);
+                                    st_global_256(reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(p.l_k1) + goff), v[1]);
+                                    if (p.L > 2) st_global_256(reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(p.l_k2) + goff), v[2]);
                                 }
                                 seg_flushed += 8;
+                                goff += 32u;
                             }
                         }
                     }

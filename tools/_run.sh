@@ -1,1 +1,7 @@
-timeout 500 python -m pytest tests/test_gpu_zz_full_size.py tests/test_gpu_parity.py -m gpu -q -k "full_size or c2_ or c3_ or c4_ or c5_ or video" --durations=8 > gpurun_out/pytest73.log 2>&1; tail -40 gpurun_out/pytest73.log | cut -c1-300
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest75.log 2>&1; tail -3 gpurun_out/pytest75.log | cut -c1-300
+for i in 1 2; do python bench.py --steps 100 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('1M', d['value'], d['ms_per_step'], d['phases_ms_per_step'], d['clocks'])"; done
+python bench.py --rows 125000 --steps 100 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('125k', d['value'], d['ms_per_step'], d['phases_ms_per_step'])"
