@@ -60,6 +60,8 @@ SIGNATURES = {
     "hq_rerank_topk_bf16": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _p, _i64, _p, _i32, _p, _i64, _i32, _i64,
                                    _p, _p, _p, _i64, _p]),
     "hq_to_bf16_unit": (_i32, [_p, _i64, _i64, _i64, _p, _p, _i64, _p]),
+    "hq_shard_ingest_supported": (_i32, [_i64]),
+    "hq_shard_ingest": (_i32, [_p, _i64, _i64, _i64, _p, _i32, _p, _i64, _p, _p, _i64, _p]),
     "hq_rerank_topk_unit_bf16": (_i32, [_p, _i64, _p, _i64, _p, _p, _i32, _i64, _i64, _p, _i64, _p, _i64, _p, _i32, _p, _i64, _i32, _i64,
                                         _p, _p, _p, _i64, _p]),
     "hq_comprehensive_scores": (_i32, [_p, _i64, _i32, _i32, _i64, _p, _i32, _i64, _p, _p, _i64, _p, _p]),

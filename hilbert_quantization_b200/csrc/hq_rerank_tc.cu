@@ -442,6 +442,34 @@ __global__ void __launch_bounds__(256) k_to_bf16_unit(const float* __restrict__ 
     }
 }
 
+// Database build: eight elements per thread (two 128-bit loads, one 128-bit store), one 64-bit division per chunk instead of
+// one per element (the scalar kernel above ran at 1.7 TB/s: 5.5 ms per 1 M x 1536 rows).  Same arithmetic: IEEE division by the
+// row norm, round to nearest even.  Needs 16-byte aligned rows on both sides.
+__global__ void __launch_bounds__(256) k_to_bf16_unit_vec(const float* __restrict__ src, int64_t N, int64_t D, int64_t src_stride,
+                                                          const float* __restrict__ norms, __nv_bfloat16* __restrict__ dst, int64_t dst_pitch) {
+    const int64_t cpr = dst_pitch >> 3, total = N * cpr;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cpr, c = (i - r * cpr) << 3;
+        const float n = __ldg(norms + r);
+        const float* s = src + r * src_stride + c;
+        float v[8];
+        if (c + 8 <= D) {
+            const float4 a = __ldcs(reinterpret_cast<const float4*>(s)), b = __ldcs(reinterpret_cast<const float4*>(s) + 1);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = c + j < D ? __ldg(s + j) : 0.f;
+        }
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float lo = n > 0.f ? __fdiv_rn(v[2 * j], n) : 0.f, hi = n > 0.f ? __fdiv_rn(v[2 * j + 1], n) : 0.f;
+            w[j] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(lo)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(hi)) << 16);
+        }
+        *reinterpret_cast<uint4*>(dst + r * dst_pitch + c) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t pitch_elems, int box_rows) {
     return make_map_2d(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, cols, pitch_elems, BK, box_rows);
 }
@@ -584,8 +612,15 @@ extern "C" int hq_to_bf16_unit(const float* src, int64_t N, int64_t D, int64_t s
     HQ_REQUIRE(N >= 0 && D > 0 && src_stride >= D && dst_pitch >= D, "bad shape");
     if (N == 0) return HQ_OK;
     HQ_REQUIRE(src && dst && norms, "null pointer");
-    int64_t blocks = (N * dst_pitch + 255) / 256;
     const int64_t cap = (int64_t)hq_cached_sm_count() * 16;
+    if (dst_pitch % 8 == 0 && src_stride % 4 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0) {
+        int64_t blocks = (N * (dst_pitch / 8) + 255) / 256;
+        if (blocks > cap) blocks = cap;
+        k_to_bf16_unit_vec<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, N, D, src_stride, norms, (__nv_bfloat16*)dst, dst_pitch);
+        HQ_LAUNCH_OK("k_to_bf16_unit_vec");
+        return HQ_OK;
+    }
+    int64_t blocks = (N * dst_pitch + 255) / 256;
     if (blocks > cap) blocks = cap;
     k_to_bf16_unit<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, N, D, src_stride, norms, (__nv_bfloat16*)dst, dst_pitch);
     HQ_LAUNCH_OK("k_to_bf16_unit");

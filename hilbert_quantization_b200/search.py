@@ -136,13 +136,18 @@ class EmbeddingDatabase:
         self.n = int(n) if n is not None else rag_optimal_dimensions(self.D)[0]
         self.id_base = int(id_base)
         self.layout, self.levels = make_layout(self.n, self.D)
-        grids, self.idx = map_and_index(self.emb, self.n, variant="C", layout="compact", want_grid=keep_grids)
-        self.grids = grids if keep_grids else None
-        self.lens = row_lengths(self.idx, self.layout)
-        self.norms = row_norms(self.emb)
         # operand of the tensor-core rerank: unit rows (the epilogue then needs no 1 / |c|); zero-norm rows score 0.0 and
         # are listed separately
-        self.emb_bf16 = to_bf16(self.emb, self.norms) if bf16 else None
+        fused = None if keep_grids else shard_ingest(self.emb, self.n, want_bf16=bf16)
+        if fused is not None:                       # one pass over the fp32 rows: index rows + norms + bf16 unit rows
+            self.grids = None
+            self.idx, self.norms, self.emb_bf16 = fused
+        else:
+            grids, self.idx = map_and_index(self.emb, self.n, variant="C", layout="compact", want_grid=keep_grids)
+            self.grids = grids if keep_grids else None
+            self.norms = row_norms(self.emb)
+            self.emb_bf16 = to_bf16(self.emb, self.norms) if bf16 else None
+        self.lens = row_lengths(self.idx, self.layout)
         self.zero_rows = (self.norms == 0).nonzero().flatten().to(torch.int32) if bf16 else None
         # fast filter: per-level row norms + "every stored length is the structural one" check
         self.level_norms = torch.empty((self.N, int(self.layout.L)), dtype=torch.float32, device=d)
@@ -208,6 +213,54 @@ def to_bf16(x: torch.Tensor, norms: Optional[torch.Tensor] = None) -> torch.Tens
         else:
             check(lib.hq_to_bf16_unit(dev.ptr(x), N, D, x.stride(0) if N else D, dev.ptr(norms), dev.ptr(out), pitch, dev.stream_ptr()))
     return out
+
+
+_INGEST_PLANS: dict = {}
+
+
+def ingest_plan_codes(n: int) -> Optional[np.ndarray]:
+    """The variant-C compact plan of an n x n grid as (pyramid level << 24) | position-in-curve-order per index slot, or
+    None when a slot reads raw cells or a level below 3 / above 6 (hq_shard_ingest reduces levels 3..6 only)."""
+    plan, _, _ = plans.c_plan(n, "compact")
+    cells = n * n
+    codes = np.empty(len(plan), dtype=np.int32)
+    for s, e in enumerate(plan.tolist()):
+        if e < cells:
+            return None
+        off, k = e - cells, 1
+        while off >= cells >> (2 * k):
+            off -= cells >> (2 * k)
+            k += 1
+        if k < 3 or k > 6:
+            return None
+        codes[s] = (k << 24) | off
+    return codes
+
+
+def shard_ingest(emb: torch.Tensor, n: int, want_bf16: bool = True):
+    """Index rows (variant C, compact), row norms and bf16 unit rows of a block of embeddings in ONE pass
+    (hq_shard_ingest); None when the shape is not covered (the caller then runs the three separate passes, whose
+    results are bit identical)."""
+    N, D = emb.shape
+    d = emb.device
+    if N == 0 or emb.stride(1) != 1 or emb.stride(0) % 4 or emb.data_ptr() % 16 or D > n * n \
+            or not lib.hq_shard_ingest_supported(D):
+        return None
+    key = (n, d)
+    if key not in _INGEST_PLANS:
+        codes = ingest_plan_codes(n)
+        _INGEST_PLANS[key] = None if codes is None else torch.from_numpy(codes).to(d)
+    codes = _INGEST_PLANS[key]
+    if codes is None:
+        return None
+    Lsum = int(codes.numel())
+    idx = torch.empty((N, Lsum), dtype=torch.float32, device=d)
+    norms = torch.empty(N, dtype=torch.float32, device=d)
+    unit = torch.empty((N, D), dtype=torch.bfloat16, device=d) if want_bf16 else None
+    with torch.cuda.device(d):
+        check(lib.hq_shard_ingest(dev.ptr(emb), N, D, emb.stride(0), dev.ptr(codes), Lsum, dev.ptr(idx), idx.stride(0),
+                                  dev.ptr(norms), dev.ptr(unit) if unit is not None else None, D, dev.stream_ptr()))
+    return idx, norms, unit
 
 
 def row_lengths(idx: torch.Tensor, layout: IndexLayout) -> torch.Tensor:

@@ -259,6 +259,16 @@ int hq_rerank_topk_bf16(const void* db_bf16, int64_t db_pitch, const float* db_f
  * their ids (ascending) and they are appended after every other survivor, as the reference's stable sort orders them. */
 int hq_to_bf16_unit(const float* src, int64_t N, int64_t D, int64_t src_stride, const float* norms, void* dst,
                     int64_t dst_pitch, void* stream);
+/* Shard ingest: ONE pass over a block of embeddings [N, D] writes what the search path keeps per row -- the compact
+ * hierarchical index row (rag/embedding_generation/hierarchical_index_generator.py:23-342 per document; identical bits to
+ * hq_map_index with no grid output), the row norm (hq_row_norms) and the unit-row bf16 operand (hq_to_bf16_unit; may be
+ * NULL).  Without a grid to write, block means over the Hilbert grid are run means of the input row, so the pass is
+ * bound by HBM (read 4 D, write 2 D + 4 Lsum + 4 bytes per row).  `plan_codes[s]` = (pyramid level k << 24) | position in
+ * curve order for index slot s (levels 3..6: runs of 64 .. 4096 values).  D / 128 must be in {2,4,6,8,12,16,24,32}
+ * (hq_shard_ingest_supported), rows 16-byte aligned. */
+int hq_shard_ingest_supported(int64_t D);
+int hq_shard_ingest(const float* emb, int64_t N, int64_t D, int64_t stride, const int32_t* plan_codes, int Lsum,
+                    float* idx, int64_t idx_pitch, float* norms, void* unit_bf16, int64_t unit_pitch, void* stream);
 int hq_rerank_topk_unit_bf16(const void* db_unit_bf16, int64_t db_pitch, const float* db_f32, int64_t db_stride,
                              const float* db_norm, const int32_t* zero_rows, int n_zero, int64_t N, int64_t D,
                              const void* q_bf16, int64_t q_pitch, const float* q_f32, int64_t q_stride,

@@ -591,3 +591,46 @@ def test_video_hierarchical_search_golden(hq):
         assert np.abs(np.array([r[1] for r in res]) - g[f"{tag}_scores"]).max() < 1e-12
     assert hq.video.hierarchical_search(g["S64_query"], [None, None], 5) == []
     assert hq.video.hierarchical_search(np.zeros(0), list(g["S64_frames"][:4]), 5) == []
+
+
+# ---------------------------------------------------------------------------------------
+# shard ingest: index rows + norms + bf16 unit rows in one pass (hq_shard_ingest)
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,D", [(1000, 1536), (777, 768), (513, 1024), (100, 512), (64, 2048), (33, 3072), (9, 4096), (1, 1536)])
+def test_shard_ingest_is_bit_identical_to_the_separate_passes(hq, N, D):
+    """run means of the input row == block means over the Hilbert grid: the fused pass must reproduce hq_map_index (no grid),
+    hq_row_norms and hq_to_bf16_unit bit for bit, and the oracle's index rows within the fp32 bound of test_fused_map_index_batch"""
+    from hilbert_quantization_b200.index import map_and_index
+    from hilbert_quantization_b200.search import row_norms, shard_ingest, to_bf16
+    from hilbert_quantization_b200.dimension import rag_optimal_dimensions
+    g = torch.Generator(device="cuda").manual_seed(N + D)
+    x = torch.randn((N, D), device="cuda", generator=g)
+    if N > 4:
+        x[3] = 0.0
+        x[4, D // 2:] = 0.0
+    n = rag_optimal_dimensions(D)[0]
+    fused = shard_ingest(x, n)
+    assert fused is not None
+    idx, norms, unit = fused
+    _, want_idx = map_and_index(x, n, variant="C", layout="compact", want_grid=False)
+    want_norms = row_norms(x)
+    assert torch.equal(idx.view(torch.int32), want_idx.view(torch.int32))
+    assert torch.equal(norms.view(torch.int32), want_norms.view(torch.int32))
+    assert torch.equal(unit.view(torch.int16), to_bf16(x, want_norms).view(torch.int16))
+    m = min(N, 50)
+    ref = O.index_c_batch_compact(O.map_to_2d_batch(x[:m].cpu().numpy(), n))
+    assert np.abs(idx[:m].cpu().numpy().astype(np.float64) - ref).max() < 3e-7
+    # a row-pitched view of a wider matrix, no bf16 rows
+    wide = torch.randn((N, D + 128), device="cuda", generator=g)
+    i2, n2, u2 = shard_ingest(wide[:, :D], n, want_bf16=False)
+    _, w2 = map_and_index(wide[:, :D].contiguous(), n, variant="C", layout="compact", want_grid=False)
+    assert u2 is None and torch.equal(i2, w2) and torch.equal(n2, row_norms(wide[:, :D]))
+
+
+def test_shard_ingest_declines_shapes_it_does_not_cover(hq):
+    from hilbert_quantization_b200.dimension import rag_optimal_dimensions
+    from hilbert_quantization_b200.search import shard_ingest
+    for D in (250, 256, 640, 1537):                                            # odd widths, 16 x 16 grids (levels below 3)
+        assert shard_ingest(torch.randn((10, D), device="cuda"), rag_optimal_dimensions(D)[0]) is None
+    d = hq.EmbeddingDatabase(torch.randn((300, 250), device="cuda"))          # falls back to the separate passes
+    assert d.idx.shape[0] == 300 and d.emb_bf16 is not None

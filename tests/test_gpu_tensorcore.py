@@ -96,3 +96,26 @@ def test_tc_rerank_lists_zero_norm_rows_last(hq):
             iw, sw = O.topk_stable(np.arange(n_rows), O.cosine01(qs[j], db[:n_rows]), k)
             got = itc[j].cpu().numpy()
             assert list(got[: len(iw)]) == list(iw)
+
+
+@pytest.mark.parametrize("N,D", [(1000, 1536), (333, 250), (64, 1537), (5, 8), (2049, 771)])
+def test_unit_row_bf16_operand_is_exact(hq, N, D):
+    """the rerank GEMM's database operand: c / |c| in fp32 (IEEE division), rounded to nearest-even bf16, zero rows and the
+    padding columns zero -- bit for bit against torch, for row lengths that do and do not fill the 8-element chunks"""
+    from hilbert_quantization_b200.search import row_norms, to_bf16
+    g = torch.Generator(device="cuda").manual_seed(N * 7 + D)
+    x = torch.randn((N, D), device="cuda", generator=g)
+    x[N // 2] = 0.0
+    norms = row_norms(x)
+    got = to_bf16(x, norms)
+    pitch = (D + 7) // 8 * 8
+    assert got.shape == (N, pitch) and got.dtype == torch.bfloat16
+    want = torch.zeros((N, pitch), dtype=torch.bfloat16, device="cuda")
+    want[:, :D] = torch.where(norms[:, None] > 0, x / norms[:, None], torch.zeros_like(x)).to(torch.bfloat16)
+    assert torch.equal(got.view(torch.int16), want.view(torch.int16))
+    sub = x[:, : D - D % 4 - 4] if D > 8 else x                      # a row-pitched view: stride > width
+    if sub.shape[1] > 0 and not sub.is_contiguous():
+        n2 = row_norms(sub)
+        got2 = to_bf16(sub, n2)
+        w2 = torch.where(n2[:, None] > 0, sub / n2[:, None], torch.zeros_like(sub)).to(torch.bfloat16)
+        assert torch.equal(got2[:, : sub.shape[1]].view(torch.int16), w2.view(torch.int16)) and not got2[:, sub.shape[1]:].any()
