@@ -119,3 +119,32 @@ def test_unit_row_bf16_operand_is_exact(hq, N, D):
         got2 = to_bf16(sub, n2)
         w2 = torch.where(n2[:, None] > 0, sub / n2[:, None], torch.zeros_like(sub)).to(torch.bfloat16)
         assert torch.equal(got2[:, : sub.shape[1]].view(torch.int16), w2.view(torch.int16)) and not got2[:, sub.shape[1]:].any()
+
+
+@pytest.mark.parametrize("N,D,Q", [(50000, 1536, 1), (20000, 768, 3), (30000, 1024, 64), (4097, 250, 2)])
+def test_search_graph_replays_the_same_search(hq, N, D, Q):
+    """SearchGraph = search_batch captured once as a CUDA graph: identical ids and scores on every replay, for the sparse
+    (few queries) and the tensor-core rerank, with the fast and (odd D) the exact filter; a batch with a sparse query index row
+    is answered through the exact path like search_batch does."""
+    g = torch.Generator(device="cuda").manual_seed(N + Q)
+    db = torch.randn((N, D), device="cuda", generator=g)
+    d = hq.EmbeddingDatabase(db)
+    sg = hq.SearchGraph(d, Q, 10)
+    for rep in range(3):
+        qs = torch.randn((Q, D), device="cuda", generator=g)
+        qs[0] = db[rep * 7 + 1]
+        ids, sc = sg.search(qs)
+        ids, sc = ids.clone(), sc.clone()
+        want_i, want_s = hq.search_batch(d, qs, 10)
+        assert torch.equal(ids, want_i) and torch.equal(sc, want_s)
+        assert ids[0, 0].item() == rep * 7 + 1
+    ids, sc = sg.search(qs.cpu().numpy())                              # host queries
+    assert torch.equal(ids, want_i) and torch.equal(sc, want_s)
+    if D % 64 == 0:
+        sparse_q = qs.clone()
+        sparse_q[0, D - 64:] = 0.0                                     # last level-0 block mean exactly 0: a shortened index row
+        ids, sc = sg.search(sparse_q)
+        want_i, want_s = hq.search_batch(d, sparse_q, 10)
+        assert torch.equal(ids, want_i) and torch.equal(sc, want_s)
+    with pytest.raises(ValueError):
+        sg.search(torch.randn((Q + 1, D), device="cuda"))

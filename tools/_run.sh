@@ -1,5 +1,4 @@
-python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "shard_ingest" > gpurun_out/pytest78.log 2>&1; tail -25 gpurun_out/pytest78.log | cut -c1-250
-python tools/db_build_time.py 1000000 1536
-python tools/db_build_time.py 12500000 768
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches78.csv python tools/db_build_time.py 1000000 1536 > /dev/null 2>&1
-grep -i "ingest" gpurun_out/launches78.csv | tail -2 | cut -c1-50,250-400
+timeout 300 python -m pytest tests/test_gpu_tensorcore.py -m gpu -x -q -k "search_graph" > gpurun_out/pytest80.log 2>&1; tail -30 gpurun_out/pytest80.log | cut -c1-250
+python bench.py --steps 30 --no-cpu-baseline 2>gpurun_out/b80.err | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('1M', d['value'], d['single_query_latency_ms'])"; tail -c 600 gpurun_out/b80.err
