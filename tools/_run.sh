@@ -1,1 +1,3 @@
-python bench_extra.py > gpurun_out/extra81.jsonl 2>gpurun_out/extra81.err; tail -c 400 gpurun_out/extra81.err; cut -c1-420 gpurun_out/extra81.jsonl
+python tools/latency_variants.py 1000000 1
+python tools/latency_variants.py 1000000 4
+python tools/latency_variants.py 25000 1
