@@ -401,6 +401,10 @@ def prepare_queries(db: EmbeddingDatabase, queries) -> Tuple[torch.Tensor, torch
         q = q.reshape(1, -1)
     if q.shape[1] != db.D:
         raise ValueError(f"query dimension {q.shape[1]} does not match database dimension {db.D}")
+    fused = shard_ingest(q, db.n, want_bf16=False)          # index rows + norms in one launch (bit identical to the two below)
+    if fused is not None:
+        q_idx, q_norms, _ = fused
+        return q, q_idx, row_lengths(q_idx, db.layout), q_norms
     _, q_idx = map_and_index(q, db.n, variant="C", layout="compact", want_grid=False)
     return q, q_idx, row_lengths(q_idx, db.layout), row_norms(q)
 
