@@ -247,6 +247,29 @@ def main():
         ok = all(np.array_equal(O.precomputed_level_averages(img, g, s), l.averages) for (g, s), l in zip(lv, pidx.levels))
         check(f"precomputed averages n={n}", ok)
 
+    # --- f4 video path (core/video_storage.py:763-781,1203-1277,1751-1803; core/video_search.py:215-262,1316-1328) ---
+    from types import SimpleNamespace
+    from hilbert_quantization.core.video_search import VideoEnhancedSearchEngine as VE
+    from hilbert_quantization.core.video_storage import VideoModelStorage as VS
+    for S, F, thr in ((64, 30, 0.1), (340, 20, 0.55)):
+        base = rng.standard_normal(S)
+        frames = [base * rng.uniform(-0.5, 1.0) + rng.standard_normal(S) * rng.uniform(0.05, 1.5) for _ in range(F)]
+        frames[7] = frames[3].copy()
+        frames[11] = np.full(S, 0.5)
+        q = base + 0.3 * rng.standard_normal(S)
+        want = np.array([VS._calculate_hierarchical_similarity(None, q, f) for f in frames])
+        got = np.array([O.video_hierarchical_similarity(q, f) for f in frames])
+        check(f"video pearson similarity S={S}", np.array_equal(want, got))
+        metas = [SimpleNamespace(hierarchical_indices=None if i == 4 else f, frame_index=i) for i, f in enumerate(frames)]
+        eng_c = ref.ProgressiveSimilaritySearchEngine(thr, 100)
+        me = SimpleNamespace(video_storage=SimpleNamespace(_video_index={"v": SimpleNamespace(frame_metadata=metas)}),
+                             similarity_threshold=thr, traditional_engine=eng_c)
+        me._calculate_hierarchical_similarity = lambda a, b, _s=me: VE._calculate_hierarchical_similarity(_s, a, b)
+        res = VE._hierarchical_search(me, SimpleNamespace(hierarchical_indices=q), 8)
+        mine = O.video_hierarchical_search(q, [m.hierarchical_indices for m in metas], 8, thr)
+        check(f"video hierarchical search S={S}", [r.frame_metadata.frame_index for r in res] == [m[0] for m in mine]
+              and np.abs(np.array([r.similarity_score for r in res]) - np.array([m[1] for m in mine])).max() < 1e-12)
+
     print(f"\n{len(FAILS)} failure(s)")
     return 1 if FAILS else 0
 

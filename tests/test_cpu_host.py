@@ -218,3 +218,22 @@ def test_two_rank_global_ratio_cut_over_gloo(tmp_path):
                               stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+
+
+def test_ingest_plan_codes_describe_run_means_of_the_input_row():
+    """host logic of the one-pass shard ingest (search.ingest_plan_codes): every slot of the variant-C compact index row is
+    the mean of an aligned run of 4^k consecutive stream values, in exactly the order the oracle's block means over the
+    Hilbert grid produce (rag/embedding_generation/hierarchical_index_generator.py:138-178)."""
+    from hilbert_quantization_b200.search import ingest_plan_codes
+    from oracle import hilbert_oracle as O
+    assert ingest_plan_codes(8) is None and ingest_plan_codes(16) is None          # levels below 3: the fused item kernel's job
+    rng = np.random.default_rng(5)
+    for n, D in ((32, 768), (64, 1536), (64, 4096)):
+        codes = ingest_plan_codes(n)
+        x = rng.standard_normal((4, D)).astype(np.float32)
+        want = O.index_c_batch_compact(O.map_to_2d_batch(x, n))
+        assert codes is not None and len(codes) == want.shape[1]
+        pad = np.zeros((4, n * n))
+        pad[:, :D] = x
+        got = np.stack([pad[:, (c & 0xFFFFFF) * 4 ** (c >> 24):((c & 0xFFFFFF) + 1) * 4 ** (c >> 24)].mean(axis=1) for c in codes.tolist()], axis=1)
+        assert np.abs(got - want).max() < 3e-7
