@@ -613,6 +613,9 @@ class SearchGraph:
             self.ids, self.scores = search_batch(db, self.q, self.k, _dense_flag=flag, **self.kw)
             self.dense = flag[0].to(torch.int32) if flag else None
         self._dense_host = torch.empty(1, dtype=torch.int32).pin_memory() if self.dense is not None else None
+        # the captured kernels point into the shard's filter scratch: keep THAT allocation alive even if a later, larger
+        # eager batch makes the shard replace it
+        self._keep = (db._filter_scratch,)
 
     def search(self, queries, sync: bool = True):
         """queries [batch, D] (host or device).  Returns (ids, scores): the graph's output buffers, overwritten by the
