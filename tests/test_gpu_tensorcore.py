@@ -148,3 +148,11 @@ def test_search_graph_replays_the_same_search(hq, N, D, Q):
         assert torch.equal(ids, want_i) and torch.equal(sc, want_s)
     with pytest.raises(ValueError):
         sg.search(torch.randn((Q + 1, D), device="cuda"))
+    # a larger eager batch makes the shard replace its filter scratch; the graph keeps the allocation it captured
+    big = torch.randn((4 * Q + 200, D), device="cuda", generator=g)
+    hq.search_batch(d, big, 10)
+    junk = [torch.full((1 << 22,), 7.0, device="cuda") for _ in range(8)]          # would land in a freed scratch
+    qs = torch.randn((Q, D), device="cuda", generator=g)
+    ids, sc = sg.search(qs)
+    want_i, want_s = hq.search_batch(d, qs, 10)
+    assert torch.equal(ids, want_i) and torch.equal(sc, want_s) and all(bool((j == 7.0).all()) for j in junk)
