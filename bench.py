@@ -342,21 +342,24 @@ def main():
     out_ids = torch.empty((args.queries, args.k), dtype=torch.int64).pin_memory()
     out_sc = torch.empty((args.queries, args.k), dtype=torch.float32).pin_memory()
 
-    def e2e_step():
-        qd = q_pinned.to(device, non_blocking=True)
-        ids, sc = step(qd)
-        out_ids.copy_(ids, non_blocking=True)
-        out_sc.copy_(sc, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return float(out_sc[0, 0])
-    for _ in range(args.warmup):
-        e2e_step()
+    # hq.search_stream: the public call for host-resident query batches.  Every step copies its 1024 queries from pinned
+    # host memory and reads its ids / scores back on the host; the copy of step i + 1 runs on a copy stream under the search
+    # of step i (two slots), the host consumes step i's results while step i + 1 runs.
+    post = (lambda i_, s_: allgather_merge(i_, s_, args.k)) if world > 1 else None
+
+    def e2e_run(n_steps):
+        acc = 0.0
+        for ids_h, sc_h in hq.search_stream(db, (q_pinned for _ in range(n_steps)), args.k, post=post):
+            out_ids.copy_(ids_h)
+            out_sc.copy_(sc_h)
+            acc += float(out_sc[0, 0])
+        return acc
+    e2e_run(args.warmup)
     barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_run(args.steps)
     e1.record()
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), 0.0)

@@ -9,7 +9,7 @@ from .index import (HierarchicalIndexGenerator, HierarchicalIndexGeneratorImpl, 
                     StreamingHilbertIndexGenerator, index_from_grids, map_and_index, map_parameter_stream)
 from .quantize import FrameQuantizer, dequantize_u8_batch, quantize_u8_batch  # noqa: F401
 from .search import (EmbeddingDatabase, ProgressiveSimilaritySearchEngine, RAGSearchEngineImpl,   # noqa: F401
-                     SearchGraph, SearchResult, comprehensive_scores, search_batch)
+                     SearchGraph, SearchResult, comprehensive_scores, search_batch, search_stream)
 from .rag import DocumentSearchResult, ProgressiveSearchEngine, RAGSystem    # noqa: F401
 from .precomputed import PrecomputedHilbertIndexer, PrecomputedIndex, PrecomputedLevel   # noqa: F401
 from . import video                                                       # noqa: F401

@@ -580,6 +580,55 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
     return ids, out_scores
 
 
+def search_stream(db: EmbeddingDatabase, host_batches, k: int = 10, *, depth: int = 2, post=None, **kw):
+    """Throughput path for queries that live in HOST memory: a generator over `host_batches` (CPU tensors [Q, D], pinned for
+    asynchronous copies; every batch the same shape) that yields `(ids, scores)` as pinned host tensors, in order.  The copy
+    of batch i + 1 runs on a copy stream while batch i is searched and the results of batch i - 1 travel back, so the
+    host never sits between a synchronisation and the next launch (a copy -> search -> read-back -> synchronise loop leaves the
+    GPU idle for the copy and for the host's launch preparation: 20 % of a 1 ms batch on a 125 K-row shard).  `post(ids,
+    scores)` runs on the device results before they are read back (the all-gather merge of a row-sharded search).  The
+    yielded tensors belong to one of `depth` slots and are overwritten `depth` batches later."""
+    from collections import deque
+    d = db.device
+    main = torch.cuda.current_stream(d)
+    copy_stream = torch.cuda.Stream(device=d)
+    slots: list = []
+    pending: deque = deque()
+
+    def finish(slot):
+        slot["done"].synchronize()
+        return slot["ids"], slot["scores"]
+
+    for i, qh in enumerate(host_batches):
+        qh = qh if isinstance(qh, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(qh, dtype=np.float32))
+        if qh.dim() == 1:
+            qh = qh.reshape(1, -1)
+        if len(slots) < depth:
+            slots.append({"q": torch.empty(tuple(qh.shape), dtype=torch.float32, device=d), "ids": None, "scores": None,
+                          "copied": torch.cuda.Event(), "done": torch.cuda.Event()})
+        slot = slots[i % depth]
+        if len(pending) == depth:                    # the slot's previous batch: finished before its buffers are reused
+            yield finish(pending.popleft())
+        if tuple(qh.shape) != tuple(slots[0]["q"].shape):
+            raise ValueError(f"search_stream needs batches of one shape, got {tuple(qh.shape)} after {tuple(slots[0]['q'].shape)}")
+        with torch.cuda.stream(copy_stream):
+            slot["q"].copy_(qh, non_blocking=True)
+            slot["copied"].record(copy_stream)
+        main.wait_event(slot["copied"])
+        ids, sc = search_batch(db, slot["q"], k, **kw)
+        if post is not None:
+            ids, sc = post(ids, sc)
+        if slot["ids"] is None:
+            slot["ids"] = torch.empty(tuple(ids.shape), dtype=ids.dtype).pin_memory()
+            slot["scores"] = torch.empty(tuple(sc.shape), dtype=sc.dtype).pin_memory()
+        slot["ids"].copy_(ids, non_blocking=True)
+        slot["scores"].copy_(sc, non_blocking=True)
+        slot["done"].record(main)
+        pending.append(slot)
+    while pending:
+        yield finish(pending.popleft())
+
+
 class SearchGraph:
     """`search_batch` for a fixed (shard, batch size, k) captured ONCE as a CUDA graph and replayed per batch.
 

@@ -156,3 +156,26 @@ def test_search_graph_replays_the_same_search(hq, N, D, Q):
     ids, sc = sg.search(qs)
     want_i, want_s = hq.search_batch(d, qs, 10)
     assert torch.equal(ids, want_i) and torch.equal(sc, want_s) and all(bool((j == 7.0).all()) for j in junk)
+
+
+@pytest.mark.parametrize("depth", [1, 2, 3])
+def test_search_stream_pipelines_host_batches(hq, depth):
+    """search_stream = search_batch per host batch with the copies overlapped: same ids / scores, in order, for more batches
+    than slots; results are pinned host tensors"""
+    g = torch.Generator(device="cuda").manual_seed(depth)
+    db = torch.randn((40000, 1024), device="cuda", generator=g)
+    d = hq.EmbeddingDatabase(db)
+    batches = [torch.randn((96, 1024), generator=torch.Generator().manual_seed(100 + i)).pin_memory() for i in range(7)]
+    for b in batches:
+        b[0] = db[11].cpu()
+    got = [(i.clone(), s.clone()) for i, s in hq.search_stream(d, batches, 10, depth=depth)]
+    assert len(got) == len(batches)
+    for b, (ids, sc) in zip(batches, got):
+        want_i, want_s = hq.search_batch(d, b.cuda(), 10)
+        assert not ids.is_cuda and torch.equal(ids, want_i.cpu()) and torch.equal(sc, want_s.cpu())
+        assert ids[0, 0].item() == 11
+    # a post hook (what the sharded search uses for its all-gather merge) and numpy batches
+    got2 = list(hq.search_stream(d, [b.numpy() for b in batches[:2]], 10, depth=depth, post=lambda i, s: (i + 5, s)))
+    assert torch.equal(got2[-1][0], got[1][0] + 5)
+    with pytest.raises(ValueError):
+        list(hq.search_stream(d, [batches[0], batches[1][:5]], 10, depth=depth))

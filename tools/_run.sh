@@ -1,1 +1,1 @@
-timeout 300 python -m pytest tests/test_gpu_tensorcore.py -m gpu -x -q -k "search_graph" > gpurun_out/pytest86.log 2>&1; tail -15 gpurun_out/pytest86.log | cut -c1-250
+timeout 300 python -m pytest tests/test_gpu_tensorcore.py -m gpu -x -q > gpurun_out/pytest88.log 2>&1; tail -5 gpurun_out/pytest88.log | cut -c1-250
