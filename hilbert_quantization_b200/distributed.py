@@ -183,3 +183,11 @@ class ShardedSearch:
         from .search import search_batch
         ids, scores = search_batch(self.db, queries, k, filter_scope=filter_scope, group=self.group, **kw)
         return allgather_merge(ids, scores, k, self.group)
+
+    def search_stream(self, host_batches, k: int = 10, *, depth: int = 2, **kw):
+        """`search.search_stream` over this rank's shard with the all-gather merge as its post step: every rank feeds the same
+        host batches and gets the merged global top-k of each batch back in pinned host memory, copies overlapped with the
+        search (the bench's e2e figure at N > 1 is exactly this composition)."""
+        from .search import search_stream
+        return search_stream(self.db, host_batches, k, depth=depth,
+                             post=lambda ids, scores: allgather_merge(ids, scores, k, self.group), **kw)
