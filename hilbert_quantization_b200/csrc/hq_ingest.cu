@@ -27,7 +27,7 @@ constexpr int kWarps = 8;
 constexpr int kStage = 64 + 16 + 4 + 1 + 3;          // levels 3..6 of a 64 x 64 grid, padded
 
 template <int J>
-__global__ void __launch_bounds__(kWarps * 32) k_shard_ingest(const float* __restrict__ emb, int64_t N, int64_t stride,
+__global__ void __launch_bounds__(kWarps * 32, (J <= 12 ? 3 : 1)) k_shard_ingest(const float* __restrict__ emb, int64_t N, int64_t stride,
                                                              const int32_t* __restrict__ plan, int Lsum, float* __restrict__ idx,
                                                              int64_t idx_pitch, float* __restrict__ norms,
                                                              __nv_bfloat16* __restrict__ unit, int64_t unit_pitch) {

@@ -1,6 +1,4 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest90.log 2>&1; tail -3 gpurun_out/pytest90.log | cut -c1-300
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | cut -c1-200
-python bench.py > gpurun_out/b90.json 2>gpurun_out/b90.err; tail -c 300 gpurun_out/b90.err
-python -c "
-import json
-d=json.loads(open('gpurun_out/b90.json').read().strip().splitlines()[-1]); print(d['value'], d['e2e']['value'], d['phases_ms_per_step'], d['single_query_latency_ms']['cuda_graph'], d['roofline']['frac'], d['map_index']['value'], d['gpu_launches'], d['cpu_baseline']['value'])"
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "shard_ingest" 2>&1 | tail -2
+python tools/db_build_time.py 1000000 1536
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches92.csv python tools/db_build_time.py 1000000 1536 > /dev/null 2>&1
+grep -i "ingest" gpurun_out/launches92.csv | tail -1 | rev | cut -d, -f1 | rev
