@@ -1,5 +1,3 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest93.log 2>&1; tail -3 gpurun_out/pytest93.log | cut -c1-300
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | cut -c1-200
-python bench.py --steps 50 --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('1M', d['value'], d['e2e']['value'], d['phases_ms_per_step'])"
+ncu --set full --clock-control none --import-source on -k regex:"k_filter_bits_tc|k_filter_cascade_lists|k_rerank_tc" -s 12 -c 4 -o /tmp/prof_head python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu95.log 2>&1
+python tools/ncu_summary.py /tmp/prof_head.ncu-rep > gpurun_out/ncu95_summary.txt 2>gpurun_out/ncu95_summary.err
+grep -E "^\[|gpu__time_duration|issue_active|dram_throughput|tensor_cycles_active|inst_executed" gpurun_out/ncu95_summary.txt | cut -c1-130
