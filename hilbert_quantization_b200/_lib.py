@@ -49,6 +49,7 @@ SIGNATURES = {
     "hq_filter_tc_valid": (_i32, [_p, _i64, C.POINTER(IndexLayout), _p, _i64, _p]),
     "hq_row_norms": (_i32, [_p, _i64, _i64, _i64, _p, _p]),
     "hq_rerank_scores_f32": (_i32, [_p, _p, _i64, _i64, _i64, _p, _p, _i32, _i64, _p, _i64, _p, _i64, _p]),
+    "hq_paired_cosine01": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _p, _p]),
     "hq_rerank_scores_sparse_f32": (_i32, [_p, _p, _i64, _i64, _i64, _p, _p, _i32, _i64, _p, _i64, _p, _i64, _p]),
     "hq_topk_from_scores": (_i32, [_p, _i64, _i64, _i32, _i32, _i64, _p, _p, _p]),
     "hq_topk_chunked_scratch_bytes": (_i64, [_i64, _i32, _i32]),
@@ -89,6 +90,9 @@ def _load():
                 raise HQLibraryError(
                     f"libhq_b200.so is not built ({path}) and could not be compiled here: {e}. "
                     "There is no CPU fallback; run `python -m hilbert_quantization_b200.build`.") from e
+            import warnings
+            warnings.warn(f"libhq_b200.so is older than its sources and the rebuild failed ({e}); loading the STALE library "
+                          f"{path}", RuntimeWarning)
     try:
         lib = C.CDLL(path)
     except OSError as e:

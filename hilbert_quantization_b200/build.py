@@ -33,31 +33,56 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every csrc/*.cu and link lib/libhq_b200.so.  Safe under torchrun: one process builds (exclusive flock on
+    lib/.build.lock), the others wait and find the library up to date; objects and the library are written under
+    temporary names and moved into place, so no process can load a half-written file."""
     if not force and not needs_build():
         return LIB_PATH
+    import fcntl
+    os.makedirs(LIB_DIR, exist_ok=True)
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():        # another rank built it while this one waited
+                return LIB_PATH
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found; libhq_b200.so cannot be built")
-    os.makedirs(LIB_DIR, exist_ok=True)
+    tag = f".tmp{os.getpid()}"
     objs = []
     procs = []
     for src in sources():
         obj = os.path.join(LIB_DIR, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj + tag]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    for src, p in procs:
+        procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = None
+    for src, obj, p in procs:
         out, _ = p.communicate()
         if verbose and out:
             print(out)
-        if p.returncode != 0:
-            raise RuntimeError(f"nvcc failed on {src}:\n{out}")
-    cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-lcudart"]
+        if p.returncode != 0 and failed is None:
+            failed = f"nvcc failed on {src}:\n{out}"
+    if failed is not None:
+        for _, obj, _ in procs:
+            if os.path.exists(obj + tag):
+                os.remove(obj + tag)
+        raise RuntimeError(failed)
+    for _, obj, _ in procs:
+        os.replace(obj + tag, obj)
+    cmd = [nvcc, "-shared", "-o", LIB_PATH + tag, *objs, "-lcudart"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
+    os.replace(LIB_PATH + tag, LIB_PATH)
     return LIB_PATH
 
 

@@ -713,6 +713,36 @@ extern "C" int hq_rerank_scores_f32(const float* db, const float* db_norm, int64
     return HQ_OK;
 }
 
+// paired rows: out[i] = (cos(a_i, b_i) + 1) / 2 with the score arithmetic of k_rerank_scores (0 when a norm is 0).  One warp
+// per pair; the windows of _calculate_spatial_locality_similarity (rag/search/engine.py:662-714) are one launch.
+__global__ void __launch_bounds__(256) k_paired_cosine01(const float* __restrict__ a, const float* __restrict__ na,
+                                                         const float* __restrict__ b, const float* __restrict__ nb, int64_t n,
+                                                         int64_t D, int64_t stride, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n) return;
+    const float* pa = a + i * stride;
+    const float* pb = b + i * stride;
+    float acc = 0.f;
+    for (int64_t k = lane; k < D; k += 32) acc = fmaf(__ldg(pa + k), __ldg(pb + k), acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+        const float x = __ldg(na + i), y = __ldg(nb + i);
+        out[i] = (x != 0.f && y != 0.f) ? __fmul_rn(__fadd_rn(__fdiv_rn(acc, __fmul_rn(x, y)), 1.0f), 0.5f) : 0.f;
+    }
+}
+
+extern "C" int hq_paired_cosine01(const float* a, const float* a_norm, const float* b, const float* b_norm, int64_t n, int64_t D,
+                                  int64_t stride, float* out, void* stream) {
+    HQ_REQUIRE(n >= 0 && D > 0 && stride >= D, "bad shape");
+    if (n == 0) return HQ_OK;
+    HQ_REQUIRE(a && a_norm && b && b_norm && out, "null pointer");
+    k_paired_cosine01<<<(unsigned)((n * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, a_norm, b, b_norm, n, D, stride, out);
+    HQ_LAUNCH_OK("k_paired_cosine01");
+    return HQ_OK;
+}
+
 extern "C" int hq_rerank_scores_sparse_f32(const float* db, const float* db_norm, int64_t N, int64_t D, int64_t db_stride, const float* q,
                                            const float* q_norm, int Q, int64_t q_stride, const uint32_t* mask, int64_t mask_stride,
                                            float* scores, int64_t scores_stride, void* stream) {

@@ -23,6 +23,8 @@ class PaddingConfig:
 
 
 class PowerOf4DimensionCalculator:
+    _padding_config_cls = None      # dropin.install() points this at the reference's models.PaddingConfig
+
     def __init__(self, min_efficiency_ratio: float = MIN_EFFICIENCY_RATIO):
         self.min_efficiency_ratio = min_efficiency_ratio
 
@@ -40,7 +42,7 @@ class PowerOf4DimensionCalculator:
         eff = param_count / total
         if eff < self.min_efficiency_ratio:
             raise ValueError(f"Efficiency ratio {eff:.3f} is below minimum {self.min_efficiency_ratio}")
-        return PaddingConfig(target_dims, DEFAULT_PADDING_VALUE, self._padding_positions(param_count, target_dims), eff)
+        return (self._padding_config_cls or PaddingConfig)(target_dims, DEFAULT_PADDING_VALUE, self._padding_positions(param_count, target_dims), eff)
 
     @staticmethod
     def _find_nearest_power_of_4(value: int) -> int:

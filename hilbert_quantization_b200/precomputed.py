@@ -59,6 +59,8 @@ class PrecomputedHilbertIndexer:
     the reference's (`np.mean` of a float32 region), computed in a 4-ary tree instead of NumPy's pairwise
     order (|delta| <= 3e-7 on N(0,1) data, tests)."""
 
+    _level_cls = _index_cls = None   # dropin.install() points these at the reference's dataclasses (pickle compatibility)
+
     def __init__(self, max_levels: int = 6, min_square_size: int = 2, device=None):
         self.max_levels = max_levels
         self.min_square_size = min_square_size
@@ -146,9 +148,9 @@ class PrecomputedHilbertIndexer:
         for (g, s), t in zip(self._calculate_granularity_levels(width), per_level):
             avg = t[0].cpu().numpy().astype(np.float32)
             coords = self._coordinates(g, s)
-            levels.append(PrecomputedLevel(grid_size=g, square_size=s, num_squares=len(avg), averages=avg, square_coordinates=coords))
+            levels.append((self._level_cls or PrecomputedLevel)(grid_size=g, square_size=s, num_squares=len(avg), averages=avg, square_coordinates=coords))
             total += avg.nbytes + len(coords) * 16
-        index = PrecomputedIndex(model_id=model_id, original_shape=(height, width), levels=levels,
+        index = (self._index_cls or PrecomputedIndex)(model_id=model_id, original_shape=(height, width), levels=levels,
                                  creation_time=time.time() - start, total_storage_bytes=total)
         if cache:
             self._index_cache[model_id] = index
@@ -162,8 +164,24 @@ class PrecomputedHilbertIndexer:
             pickle.dump(index, f)
 
     def load_index_from_disk(self, filepath: str) -> PrecomputedIndex:
+        """Reads files written by this class AND by the reference's indexer (same pickle layout, class path
+        hilbert_quantization.core.precomputed_hilbert_index).  A restricted unpickler: only the two index dataclasses
+        and NumPy's array reconstruction are resolvable, anything else in the stream raises."""
+        level_cls, index_cls = self._level_cls or PrecomputedLevel, self._index_cls or PrecomputedIndex
+
+        class _Restricted(pickle.Unpickler):
+            def find_class(self, module, name):
+                if module in (__name__, "hilbert_quantization.core.precomputed_hilbert_index"):
+                    if name == "PrecomputedIndex":
+                        return index_cls
+                    if name == "PrecomputedLevel":
+                        return level_cls
+                if module.split(".")[0] == "numpy" and name in ("_reconstruct", "ndarray", "dtype", "scalar", "_frombuffer"):
+                    return super().find_class(module, name)
+                raise pickle.UnpicklingError(f"{module}.{name} is not allowed in a precomputed index file")
+
         with open(filepath, "rb") as f:
-            index = pickle.load(f)
+            index = _Restricted(f).load()
         self._index_cache[index.model_id] = index
         return index
 

@@ -59,6 +59,7 @@ class ProgressiveSearchEngine:
         self._vectors: List[np.ndarray] = []
         self._docs: list = []
         self._db: Optional[EmbeddingDatabase] = None
+        self._bulk: Optional[torch.Tensor] = None
 
     def _vector_of(self, doc) -> np.ndarray:
         if isinstance(doc, str):
@@ -82,6 +83,7 @@ class ProgressiveSearchEngine:
         if isinstance(embeddings, torch.Tensor) and embeddings.is_cuda and not self._vectors:
             self._db = EmbeddingDatabase(embeddings, device=embeddings.device)
             self._docs = list(range(self._db.N))
+            self._bulk = embeddings                     # device rows of the bulk load: a later add_document rebuilds from them
             self._vectors = [None] * self._db.N
             return
         arr = embeddings.detach().cpu().numpy() if isinstance(embeddings, torch.Tensor) else np.asarray(embeddings)
@@ -92,7 +94,15 @@ class ProgressiveSearchEngine:
         if self._db is None:
             if not self._vectors:
                 raise ValueError("no documents")
-            self._db = EmbeddingDatabase(np.stack(self._vectors), device=self._device)
+            n_bulk = 0 if self._bulk is None else int(self._bulk.shape[0])
+            tail = self._vectors[n_bulk:]
+            if n_bulk:                                  # bulk-loaded device rows first, documents added since then after them
+                rows = self._bulk.to(torch.float32)
+                if tail:
+                    rows = torch.cat([rows, torch.from_numpy(np.stack(tail).astype(np.float32)).to(rows.device)])
+                self._db = EmbeddingDatabase(rows, device=rows.device)
+            else:
+                self._db = EmbeddingDatabase(np.stack(tail), device=self._device)
         return self._db
 
     def search_vectors(self, queries, max_results: int = 10):

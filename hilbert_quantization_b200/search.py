@@ -763,13 +763,23 @@ class RAGSearchEngineImpl:
 
     `progressive_hierarchical_search(query_frame)` filters the frames returned by
     `_get_all_candidate_embeddings()` (the hook the reference's own tests patch,
-    tests/test_progressive_filtering.py:167-169).  Index rows are read at
-    `original_height = frame_height - default_level_count` (the explicit mode of
-    SURVEY 8c); the reference's >=50 %-zeros height guess (:134-162) is not reproduced."""
+    tests/test_progressive_filtering.py:167-169).
 
-    def __init__(self, config=None, dual_storage=None, device=None):
+    Two ways of locating the index rows of a frame:
+      * default (`strict=False`): explicitly, `original_height = frame_height - default_level_count`,
+        all levels of all candidates in one launch per level (`hq_filter_level` / `hq_filter_select`);
+      * `strict=True` (what `dropin.install()` uses): the reference's own >= 50 %-zeros height
+        heuristic (:134-162), trailing-zero stripping and dropping of all-zero rows (:97-132), per
+        frame, with the reference's list bookkeeping (stable sort, so ties keep the previous level's
+        order, :236) on the host and every level's scores of all current candidates from one device
+        launch per distinct prefix length."""
+
+    strict = False
+
+    def __init__(self, config=None, dual_storage=None, device=None, strict: bool = False):
         self.config = config
         self._device = device
+        self.strict = bool(strict)
 
     def _get_all_candidate_embeddings(self) -> List[np.ndarray]:
         return []
@@ -780,9 +790,29 @@ class RAGSearchEngineImpl:
         L = len(plans.c_levels(width))
         return max(0, height - L), L
 
+    def _detect_original_embedding_height(self, enhanced_embedding: np.ndarray) -> int:
+        """rag/search/engine.py:134-162: the first row from the bottom with fewer than 50 % zeros ends the
+        embedding (host scalar logic over one frame)."""
+        height, width = enhanced_embedding.shape
+        if width == 0:
+            return height
+        dense = (np.count_nonzero(enhanced_embedding == 0, axis=1) / width) < 0.5
+        hit = np.nonzero(dense)[0]
+        return int(hit[-1]) + 1 if len(hit) else height
+
     def _extract_hierarchical_indices(self, embedding_with_indices: np.ndarray) -> List[np.ndarray]:
         if embedding_with_indices.ndim != 2:
             return []
+        if self.strict:                                   # rag/search/engine.py:97-132
+            height = embedding_with_indices.shape[0]
+            H = self._detect_original_embedding_height(embedding_with_indices)
+            rows = []
+            for r in range(H, height):
+                row = embedding_with_indices[r, :]
+                nz = np.nonzero(row)[0]
+                if len(nz) > 0:                           # all-zero rows are dropped: later rows move up a level
+                    rows.append(row[: nz[-1] + 1])
+            return rows
         H, _ = self._split(embedding_with_indices)
         rows = []
         for r in range(H, embedding_with_indices.shape[0]):
@@ -794,10 +824,80 @@ class RAGSearchEngineImpl:
     def _extract_original_embedding(self, enhanced_embedding: np.ndarray) -> np.ndarray:
         if enhanced_embedding.ndim == 1:
             return enhanced_embedding
+        if self.strict:                                   # rag/search/engine.py:604-620
+            return enhanced_embedding[: self._detect_original_embedding_height(enhanced_embedding), :]
         return enhanced_embedding[: self._split(enhanced_embedding)[0], :]
 
+    # ---- strict mode: the reference's list flow, scores from the device --------------------------------
+    def _prefix_scores(self, query_row: np.ndarray, cand_rows: Sequence[Optional[np.ndarray]]) -> np.ndarray:
+        """(cos + 1) / 2 of `query_row` against every candidate row on the common prefix (0.0 for a missing or empty
+        row, rag/search/engine.py:208-231): one launch per distinct prefix length."""
+        out = np.zeros(len(cand_rows), dtype=np.float64)
+        by_len: Dict[int, List[int]] = {}
+        for i, r in enumerate(cand_rows):
+            m = 0 if r is None else min(len(r), len(query_row))
+            if m > 0:
+                by_len.setdefault(m, []).append(i)
+        if not by_len:
+            return out
+        d = dev.require_cuda(self._device)
+        for m, members in by_len.items():
+            rows = dev.f32_device(np.stack([np.asarray(cand_rows[i][:m], dtype=np.float32) for i in members]), d)
+            q = dev.f32_device(np.asarray(query_row[:m], dtype=np.float32).reshape(1, m), d)
+            sc = torch.empty((1, len(members)), dtype=torch.float32, device=d)
+            nr, nq = row_norms(rows), row_norms(q)
+            with torch.cuda.device(d):
+                check(lib.hq_rerank_scores_f32(dev.ptr(rows), dev.ptr(nr), len(members), m, m, dev.ptr(q), dev.ptr(nq),
+                                               1, m, None, 0, dev.ptr(sc), len(members), dev.stream_ptr()))
+            out[np.asarray(members)] = sc[0].cpu().numpy()
+        return out
+
+    def _apply_progressive_threshold(self, candidate_scores: List[Tuple[int, float]], level: int) -> List[int]:
+        """rag/search/engine.py:243-287 (host list logic)."""
+        if not candidate_scores:
+            return []
+        threshold = rag_threshold(level)
+        max_candidates = max(1, int(len(candidate_scores) * rag_ratio(level)))
+        kept: List[int] = []
+        for candidate_idx, score in candidate_scores:
+            if score >= threshold and len(kept) < max_candidates:
+                kept.append(candidate_idx)
+        return kept
+
+    def _filter_candidates_at_level(self, query_level_indices: np.ndarray, candidate_embeddings: List[np.ndarray],
+                                    current_candidates: List[int], level: int) -> List[int]:
+        """rag/search/engine.py:178-241 with the per-candidate cosine loop replaced by one batched device call."""
+        if not current_candidates or len(query_level_indices) == 0:
+            return current_candidates
+        members, rows = [], []
+        for candidate_idx in current_candidates:
+            if candidate_idx >= len(candidate_embeddings):
+                continue
+            cand = self._extract_hierarchical_indices(candidate_embeddings[candidate_idx])
+            members.append(candidate_idx)
+            rows.append(cand[level] if level < len(cand) else None)
+        scores = self._prefix_scores(np.asarray(query_level_indices), rows)
+        candidate_scores = [(i, float(s)) for i, s in zip(members, scores)]
+        candidate_scores.sort(key=lambda x: x[1], reverse=True)            # stable: ties keep the incoming order (:236)
+        return self._apply_progressive_threshold(candidate_scores, level)
+
     def progressive_hierarchical_search(self, query_embedding: np.ndarray) -> List[int]:
-        if query_embedding.size == 0 or query_embedding.ndim != 2:
+        if query_embedding.size == 0:
+            return []
+        if self.strict:                                   # rag/search/engine.py:51-95
+            query_indices = self._extract_hierarchical_indices(query_embedding)
+            if len(query_indices) == 0:
+                return []
+            cands = self._get_all_candidate_embeddings()
+            if not cands:
+                return []
+            candidates = list(range(len(cands)))
+            for level in range(len(query_indices)):
+                if not candidates:
+                    break
+                candidates = self._filter_candidates_at_level(query_indices[level], cands, candidates, level)
+            return candidates
+        if query_embedding.ndim != 2:
             return []
         cands = self._get_all_candidate_embeddings()
         if not cands:
@@ -850,9 +950,61 @@ class RAGSearchEngineImpl:
         """rag/search/engine.py:716-727"""
         return {"hierarchical": 0.5, "embedding": 0.3, "spatial": 0.2}
 
+    def _pad_indices_to_length(self, indices: List[np.ndarray], target_length: int) -> np.ndarray:
+        """rag/search/engine.py:577-602 (host copy)."""
+        if not indices:
+            return np.zeros((target_length, 1))
+        padded = np.zeros((target_length, max(len(i) for i in indices)))
+        for i, row in enumerate(indices):
+            if i < target_length:
+                padded[i, : len(row)] = row
+        return padded
+
+    def _calculate_spatial_locality_similarity(self, embedding1: np.ndarray, embedding2: np.ndarray) -> float:
+        """rag/search/engine.py:662-714: mean (cos + 1) / 2 over w x w windows at stride w / 2 of the two original grids.
+        All windows of the pair are scored by ONE device launch (window rows as a [windows, w * w] operand)."""
+        if embedding1.shape != embedding2.shape or embedding1.ndim != 2:
+            return 0.0
+        o1, o2 = self._extract_original_embedding(embedding1), self._extract_original_embedding(embedding2)
+        if o1.shape != o2.shape:
+            return 0.0
+        height, width = o1.shape
+        w = min(4, height // 4, width // 4)
+        if w < 2:
+            return self._calculate_embedding_cosine_similarity(o1, o2)
+        ii = np.arange(0, height - w + 1, w // 2)
+        jj = np.arange(0, width - w + 1, w // 2)
+        if len(ii) == 0 or len(jj) == 0:
+            return 0.0
+
+        def windows(o):
+            v = np.lib.stride_tricks.sliding_window_view(np.asarray(o, dtype=np.float32), (w, w))
+            return np.ascontiguousarray(v[ii][:, jj].reshape(len(ii) * len(jj), w * w))
+        d = dev.require_cuda(self._device)
+        a, b = dev.f32_device(windows(o1), d), dev.f32_device(windows(o2), d)
+        nw = a.shape[0]
+        sc = torch.empty(nw, dtype=torch.float32, device=d)
+        na, nb = row_norms(a), row_norms(b)
+        with torch.cuda.device(d):
+            check(lib.hq_paired_cosine01(dev.ptr(a), dev.ptr(na), dev.ptr(b), dev.ptr(nb), nw, w * w, w * w, dev.ptr(sc),
+                                         dev.stream_ptr()))
+        return float(sc.to(torch.float64).mean().item())
+
     def _calculate_comprehensive_similarity(self, query_embedding: np.ndarray, query_indices, candidate_frame: np.ndarray,
                                             frame_number: int = 0) -> float:
-        """rag/search/engine.py:516-575 for one pair (index rows read explicitly, see the class docstring)."""
+        """rag/search/engine.py:516-575 for one pair."""
+        if self.strict:                  # the reference's composition over this class's (device) leaf methods
+            candidate_indices = self._extract_hierarchical_indices(candidate_frame)
+            hier = 0.0
+            if query_indices and candidate_indices:
+                levels = max(len(query_indices), len(candidate_indices))
+                hier = self.compare_hierarchical_indices(self._pad_indices_to_length(query_indices, levels),
+                                                         self._pad_indices_to_length(candidate_indices, levels))
+            emb = self._calculate_embedding_cosine_similarity(self._extract_original_embedding(query_embedding),
+                                                              self._extract_original_embedding(candidate_frame))
+            spatial = self._calculate_spatial_locality_similarity(query_embedding, candidate_frame)
+            w = self._get_similarity_weights()
+            return w["hierarchical"] * hier + w["embedding"] * emb + w["spatial"] * spatial
         return float(comprehensive_scores(np.asarray(candidate_frame, dtype=np.float32)[None], np.asarray(query_embedding, dtype=np.float32),
                                           self._split(query_embedding)[0], device=self._device)[0, 0].item())
 
@@ -861,6 +1013,11 @@ class RAGSearchEngineImpl:
         (stable: ties keep the dictionary order)."""
         if query_embedding.size == 0 or not cached_frames:
             return []
+        if self.strict:
+            query_indices = self._extract_hierarchical_indices(query_embedding)
+            sims = [(k, self._calculate_comprehensive_similarity(query_embedding, query_indices, f, k)) for k, f in cached_frames.items()]
+            sims.sort(key=lambda x: x[1], reverse=True)
+            return sims
         keys = list(cached_frames.keys())
         frames = np.stack([np.asarray(cached_frames[k], dtype=np.float32) for k in keys])
         sc = comprehensive_scores(frames, np.asarray(query_embedding, dtype=np.float32), self._split(query_embedding)[0],
@@ -922,10 +1079,15 @@ class ProgressiveSimilaritySearchEngine:
     """core/search_engine.py:23: per-level similarities run on the device for the whole
     candidate pool at once; the (tiny) filter / sort bookkeeping stays on the host."""
 
+    _result_cls = None             # dropin.install() points this at the reference's models.SearchResult
+
     def __init__(self, similarity_threshold: float = 0.1, max_candidates_per_level: int = 100, device=None):
         self.similarity_threshold = similarity_threshold
         self.max_candidates_per_level = max_candidates_per_level
         self._device = device
+
+    def _result(self, *fields):
+        return (self._result_cls or SearchResult)(*fields)
 
     def _parse_index_structure(self, indices: np.ndarray, total_space: int):
         return plans.core_levels(len(indices), total_space)
@@ -983,7 +1145,7 @@ class ProgressiveSimilaritySearchEngine:
         else:
             overall = self._overall(sims)
         order = np.argsort(-overall, kind="stable")[:max_results]
-        return [SearchResult(candidate_pool[i], float(overall[i]), {l: float(sims[i, l]) for l in range(sims.shape[1])}, 0.0)
+        return [self._result(candidate_pool[i], float(overall[i]), {l: float(sims[i, l]) for l in range(sims.shape[1])}, 0.0)
                 for i in order]
 
     def progressive_search(self, query_indices: np.ndarray, candidate_pool: List, max_results: int) -> List[SearchResult]:
@@ -1012,5 +1174,5 @@ class ProgressiveSimilaritySearchEngine:
         for j in order:
             i = int(cur[j])
             s = float(overall[j])
-            res.append(SearchResult(candidate_pool[i], s, {l: float(sims[i, l]) for l in range(L)}, max(0.0, 1.0 - s)))
+            res.append(self._result(candidate_pool[i], s, {l: float(sims[i, l]) for l in range(L)}, max(0.0, 1.0 - s)))
         return res

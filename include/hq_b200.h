@@ -221,6 +221,10 @@ int hq_rerank_scores_f32(const float* db, const float* db_norm, int64_t N, int64
                          const float* q, const float* q_norm, int Q, int64_t q_stride,
                          const uint32_t* mask, int64_t mask_stride,
                          float* scores, int64_t scores_stride, void* stream);
+/* out[i] = (cos(a_i, b_i) + 1) / 2 of n PAIRED rows (0 when a norm is 0): all windows of
+ * _calculate_spatial_locality_similarity (rag/search/engine.py:662-714) in one launch.     */
+int hq_paired_cosine01(const float* a, const float* a_norm, const float* b, const float* b_norm, int64_t n, int64_t D,
+                       int64_t stride, float* out, void* stream);
 /* same scores, but only the rows alive in `mask` are read (one warp per surviving row): the latency path for a
  * handful of queries, where the survivors (a few per cent of the rows) are far less data than the whole database */
 int hq_rerank_scores_sparse_f32(const float* db, const float* db_norm, int64_t N, int64_t D, int64_t db_stride,

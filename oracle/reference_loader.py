@@ -1,8 +1,9 @@
 """TEST INFRASTRUCTURE ONLY -- import the real reference package when it is reachable.
 
-The GPU box never has ``/root/reference``; anything that runs there must not
-depend on this module succeeding.  It is used in the authoring container by
-``oracle/pin_against_reference.py`` and ``tests/golden/make_golden.py``.
+The GPU box never has ``/root/reference``; there the reference is only reachable as the
+``baseline/_ref`` install (``baseline/install_reference.sh``), which the CPU-baseline leg of
+``bench.py`` times.  Used in the authoring container by ``oracle/pin_against_reference.py``
+and ``tests/golden/make_golden*.py``.
 """
 from __future__ import annotations
 
@@ -14,8 +15,13 @@ from types import SimpleNamespace
 from unittest.mock import patch
 
 
+_BASELINE_REF = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
 def reference_path():
-    for p in (os.environ.get("HQ_REFERENCE_PATH"), "/root/reference"):
+    """$HQ_REFERENCE_PATH -> /root/reference -> baseline/_ref (the install that travels to the GPU box,
+    baseline/install_reference.sh)."""
+    for p in (os.environ.get("HQ_REFERENCE_PATH"), "/root/reference", _BASELINE_REF):
         if p and os.path.isdir(os.path.join(p, "hilbert_quantization")):
             return p
     return None
