@@ -450,6 +450,34 @@ def main():
                                   "traffic": ncu_traffic("k_item_pass_bulk") if chunk == 262144 else None,
                                   "peak_source": pk["source"]}}
         del grids_buf, idx_buf
+        # the same rows through the fused map + index + uint8 quantise kernel (north star (2)): uint8 enhanced frames out
+        rows_c = len(plans.c_plan(n, "rows")[0]) // n
+        q_bytes_per_row = 4 * args.dim + n * n + rows_c * n + 8
+
+        def quant_pass():
+            for s in range(0, mi_rows, chunk):
+                hq.map_index_quantize(mi_src[s:min(mi_rows, s + chunk)], n, variant="C")
+        for _ in range(max(3, args.warmup)):
+            quant_pass()
+        torch.cuda.synchronize()
+        mq_ms = []
+        for _ in range(max(3, args.steps)):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            quant_pass()
+            e1.record()
+            torch.cuda.synchronize()
+            mq_ms.append(e0.elapsed_time(e1))
+        mq = float(np.mean(mq_ms))
+        map_index["quantized"] = {"value": mi_rows * q_bytes_per_row / (mq * 1e-3) / 1e9, "unit": "GB/s", "ms_per_pass": mq,
+                                  "rows_per_s": mi_rows / (mq * 1e-3), "bytes_per_embedding": q_bytes_per_row,
+                                  "kernel": "k_item_pass_bulk<0,6,quant> (map_to_2d + variant-C index + embed + uint8 min/max normalise, "
+                                            "one launch; replaces the map+index pass AND the separate quantise pass over the frames)",
+                                  "roofline": {"bound": "hbm", "achieved": mi_rows * q_bytes_per_row / (mq * 1e-3) / 1e9,
+                                               "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                               "frac": mi_rows * q_bytes_per_row / (mq * 1e-3) / 1e9 / pk["hbm_gbs"],
+                                               "note": "issue bound, not HBM bound: the pass moves 2.2x fewer bytes than the grid-writing "
+                                                       "pass in a similar time (see DESIGN.md section 5)"}}
     del mi_src
 
     # ---- database build (untimed) ----
@@ -514,12 +542,16 @@ def main():
     # of step i (two slots), the host consumes step i's results while step i + 1 runs.
     post = (lambda i_, s_: allgather_merge(i_, s_, args.k)) if world > 1 else None
 
+    e2e_stamps = []
+
     def e2e_run(n_steps):
         acc = 0.0
+        e2e_stamps.clear()
         for ids_h, sc_h in hq.search_stream(db, (q_pinned for _ in range(n_steps)), args.k, post=post):
             out_ids.copy_(ids_h)
             out_sc.copy_(sc_h)
             acc += float(out_sc[0, 0])
+            e2e_stamps.append(time.perf_counter())
         return acc
     e2e_run(args.warmup)
     barrier()
@@ -527,6 +559,7 @@ def main():
     e2e_run(args.steps)                               # (returns after the last batch's results are on the host)
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
+    gaps = np.diff([t0] + e2e_stamps) * 1e3              # host time between consecutive result batches
     barrier()
     te = torch.tensor([e2e_ms], device=device)
     if world > 1:
@@ -614,7 +647,9 @@ def main():
             "single_query_latency_ms": latency,
             "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": int(q_pinned.numel() * 4),
                     "d2h_bytes_per_step": int(out_ids.numel() * 8 + out_sc.numel() * 4),
-                    "clock": "time.perf_counter around the loop (barrier + synchronize on both sides), max over ranks"},
+                    "clock": "time.perf_counter around the loop (barrier + synchronize on both sides), max over ranks",
+                    "result_gaps_ms": {"first": float(gaps[0]), "median": float(np.median(gaps[1:])) if len(gaps) > 1 else None,
+                                       "max": float(gaps[1:].max()) if len(gaps) > 1 else None}},
             "gpu_launches": launches,
             "per_rank_ms_per_step": per_rank_ms,
             "phases_ms_per_step": {k: v / args.steps for k, v in phases.items()},

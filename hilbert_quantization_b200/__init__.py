@@ -7,7 +7,7 @@ from .dimension import PowerOf4DimensionCalculator, rag_optimal_dimensions    # 
 from .mapper import HilbertCurveMapper, HilbertCurveMapperImpl               # noqa: F401
 from .index import (HierarchicalIndexGenerator, HierarchicalIndexGeneratorImpl,   # noqa: F401
                     StreamingHilbertIndexGenerator, index_from_grids, map_and_index, map_parameter_stream)
-from .quantize import FrameQuantizer, dequantize_u8_batch, quantize_u8_batch  # noqa: F401
+from .quantize import FrameQuantizer, dequantize_u8_batch, map_index_quantize, quantize_u8_batch  # noqa: F401
 from .search import (EmbeddingDatabase, ProgressiveSimilaritySearchEngine, RAGSearchEngineImpl,   # noqa: F401
                      SearchGraph, SearchResult, comprehensive_scores, search_batch, search_stream)
 from .rag import DocumentSearchResult, ProgressiveSearchEngine, RAGSystem    # noqa: F401

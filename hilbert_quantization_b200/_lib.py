@@ -32,6 +32,7 @@ SIGNATURES = {
     "hq_map_index_fused_ml": (_i32, [_p, _i32, _i64, _i64, _i64, _i32, _p, _i64, _p, _i64, _p, _i32, _i32, _i32, _p, _i64, _p, _i64, _p]),
     "hq_map_index_stream": (_i32, [_p, _i64, _i32, _p, _p, _i32, _i32, _i32, _p, _i64, _p, _i64, _p]),
     "hq_block_means": (_i32, [_p, _i64, _i32, _i32, _i64, _i32, _i32, _p, _p, _i32, _p, _i64, _p]),
+    "hq_map_index_quant": (_i32, [_p, _i64, _i64, _i64, _i32, _p, _i32, _i32, _i32, _i32, _p, _i64, _p, _p, _i64, _p]),
     "hq_quantize_u8": (_i32, [_p, _i64, _i64, _i64, _p, _i64, _p, _p]),
     "hq_dequantize_u8": (_i32, [_p, _i64, _i64, _i64, _p, _p, _i64, _p]),
     "hq_index_row_lengths": (_i32, [_p, _i64, C.POINTER(IndexLayout), _p, _p]),
@@ -58,13 +59,12 @@ SIGNATURES = {
     "hq_rerank_topk_f32": (_i32, [_p, _p, _i64, _i64, _i64, _p, _p, _i32, _i64, _p, _i64, _i32, _i64, _p, _p, _p, _i64, _p]),
     "hq_to_bf16": (_i32, [_p, _i64, _i64, _i64, _p, _i64, _p]),
     "hq_rerank_bf16_scratch_bytes": (_i64, [_i64, _i32, _i32]),
-    "hq_rerank_topk_bf16": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _p, _i64, _p, _i32, _p, _i64, _i32, _i64,
-                                   _p, _p, _p, _i64, _p]),
     "hq_to_bf16_unit": (_i32, [_p, _i64, _i64, _i64, _p, _p, _i64, _p]),
     "hq_shard_ingest_supported": (_i32, [_i64]),
     "hq_shard_ingest": (_i32, [_p, _i64, _i64, _i64, _p, _i32, _p, _i64, _p, _p, _i64, _p]),
     "hq_rerank_topk_unit_bf16": (_i32, [_p, _i64, _p, _i64, _p, _p, _i32, _i64, _i64, _p, _i64, _p, _i64, _p, _i32, _p, _i64, _i32, _i64,
-                                        _p, _p, _p, _i64, _p]),
+                                        C.c_float, _p, _p, _p, _p, _i64, _p]),
+    "hq_bf16_unit_error_max": (_i32, [_p, _i64, _i64, _i64, _p, _p, _i64, _p, _p]),
     "hq_comprehensive_scores": (_i32, [_p, _i64, _i32, _i32, _i64, _p, _i32, _i64, _p, _p, _i64, _p, _p]),
     "hq_offset_square_means": (_i32, [_p, _i64, _i32, _i64, _p, _i64, _p]),
     "hq_pearson01_matrix": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _i32, _p, _i64, _p]),

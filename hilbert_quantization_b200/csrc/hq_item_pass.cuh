@@ -299,12 +299,26 @@ __global__ void __launch_bounds__(kBlock, 3) k_item_pass(const TileParams p) {
 // ---------------------------------------------------------------------------------------
 constexpr int kMaxStages = 8;
 
-template <int MODE, int LOG2T>
+// QUANT (north star (2): "quantization and encoding of those indices fused into the same kernel"): the uint8 min/max
+// quantisation of the ENHANCED frame (grid + index rows, core/compressor.py:256-280 applied to the output of
+// embed_indices_in_image, core/pipeline.py:140-146) leaves the same pass.  The frame's min / max are those of the grid
+// cells (plus 0 when the frame holds structural zeros: padding cells, padded index slots): every index value is either a
+// cell or a mean of cells, and rounding is monotonic, so fl(mean) stays inside [min, max] of its cells.  The data warps
+// reduce min / max from the quads they hold anyway, quantise the dense tile image (16 cells per thread, one 128-bit store)
+// and the index warp quantises the index rows it gathers: 4 D bytes in, n^2 + plan_len + 8 bytes out per item, no second pass.
+__device__ __forceinline__ uint32_t quant_u8(float v, float mn, float range, bool constant) {
+    if (constant) return 128u;
+    return (uint32_t)(uint8_t)(int)__fmul_rn(__fdiv_rn(__fsub_rn(v, mn), range), 255.0f);   // truncation, like astype(uint8)
+}
+
+template <int MODE, int LOG2T, bool QUANT>
 __global__ void __launch_bounds__(kBlock, 3) k_item_pass_bulk(const TileParams p, const int kRing, const int stages, const uint32_t stage_floats,
                                                               const int plan_cap) {
     using P = typename PT<MODE>::type;
     using G = Geo<LOG2T>;
     constexpr uint32_t kImg = 4096;                                 // floats per chunk image (ipc items of T x T)
+    constexpr int IPC = (int)G::ipc;                                // items per chunk (1 for 64 x 64, 4 for 32 x 32)
+    __shared__ float s_mm[QUANT ? 2 : 1][QUANT ? IPC : 1][QUANT ? kThreads / 32 : 1][2];   // per-warp (min, max) partials, two chunks
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* const s_img0 = reinterpret_cast<float*>(smem_raw);                                    // kRing dense tile images
     float* const s_stage0 = s_img0 + kRing * kImg;                                               // `stages` source staging buffers
@@ -407,6 +421,30 @@ __global__ void __launch_bounds__(kBlock, 3) k_item_pass_bulk(const TileParams p
             // the index warp reads pyramid (iter & 1): it must be done with chunk iter-2 (the image of
             // chunk iter-3 was released even earlier)
             if (p.plan_len > 0 && iter >= 2) hq_tc::mbar_wait(&s_free[iter & 1u], ((iter >> 1) - 1u) & 1u);
+            if constexpr (QUANT) {
+                // (min, max) of the live quads per item; quad slot r belongs to item (r * kThreads) >> log2qpi
+                float mn[IPC], mx[IPC];
+#pragma unroll
+                for (int i = 0; i < IPC; ++i) { mn[i] = FLT_MAX; mx[i] = -FLT_MAX; }
+#pragma unroll
+                for (int r = 0; r < kQPT; ++r) {
+                    constexpr int dummy = 0; (void)dummy;
+                    const int il = (r * kThreads) >> G::log2qpi;
+                    if ((live_bits >> r) & 1u) {
+                        mn[il] = fminf(mn[il], fminf(fminf(v[r].x, v[r].y), fminf(v[r].z, v[r].w)));
+                        mx[il] = fmaxf(mx[il], fmaxf(fmaxf(v[r].x, v[r].y), fmaxf(v[r].z, v[r].w)));
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < IPC; ++i) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        mn[i] = fminf(mn[i], __shfl_xor_sync(0xffffffffu, mn[i], o));
+                        mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], o));
+                    }
+                    if (lane == 0) { s_mm[iter & 1u][i][warp][0] = mn[i]; s_mm[iter & 1u][i][warp][1] = mx[i]; }
+                }
+            }
 #pragma unroll
             for (int r = 0; r < kQPT; ++r) {
                 if ((live_bits >> r) & 1u) {
@@ -438,6 +476,28 @@ __global__ void __launch_bounds__(kBlock, 3) k_item_pass_bulk(const TileParams p
                 const int64_t nx = chunk + (int64_t)stages * gridDim.x;
                 if (nx < p.num_chunks) issue_loads(nx, (int)st);
             }
+            if constexpr (QUANT) {
+                // 16 consecutive cells of the dense image per thread -> 16 bytes, one 128-bit store
+                const uint32_t c0 = (uint32_t)tid * 16u, il = c0 >> (2 * LOG2T), cell = c0 & (G::cells - 1);
+                if (full || (int64_t)il < left) {
+                    float mn = FLT_MAX, mx = -FLT_MAX;
+#pragma unroll
+                    for (int w = 0; w < kThreads / 32; ++w) { mn = fminf(mn, s_mm[iter & 1u][il][w][0]); mx = fmaxf(mx, s_mm[iter & 1u][il][w][1]); }
+                    if (p.frame_zero) { mn = fminf(mn, 0.f); mx = fmaxf(mx, 0.f); }
+                    const bool constant = mn == mx;
+                    const float range = __fsub_rn(mx, mn);
+                    uint32_t w4[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 c = *reinterpret_cast<const float4*>(img + c0 + 4 * j);
+                        w4[j] = quant_u8(c.x, mn, range, constant) | (quant_u8(c.y, mn, range, constant) << 8) |
+                                (quant_u8(c.z, mn, range, constant) << 16) | (quant_u8(c.w, mn, range, constant) << 24);
+                    }
+                    uint8_t* frame = p.u8_out + (item0 + il) * p.u8_stride;
+                    __stcs(reinterpret_cast<uint4*>(frame + cell), make_uint4(w4[0], w4[1], w4[2], w4[3]));
+                    if (cell == 0) { p.mm_out[2 * (item0 + il)] = mn; p.mm_out[2 * (item0 + il) + 1] = mx; }
+                }
+            }
             if (want_pyr) pyramid_levels_123<MODE, LOG2T>(v, live_bits, warp_live, pyrb, tid, lane);
             if (p.plan_len > 0) {
                 if (iter & 1u) asm volatile("bar.arrive 3, %0;" ::"n"(kBlock) : "memory");
@@ -449,6 +509,18 @@ __global__ void __launch_bounds__(kBlock, 3) k_item_pass_bulk(const TileParams p
             if (want_pyr) pyramid_levels_top<MODE, LOG2T>(pyrb, (uint32_t)((p.D + 3) >> 2), lane);
             P* out = reinterpret_cast<P*>(p.idx_out) + item0 * p.idx_stride;
             const uint32_t n_items = full ? G::ipc : (uint32_t)left;
+            float q_mn[IPC], q_rg[IPC];
+            bool q_const[IPC];
+            if constexpr (QUANT) {
+#pragma unroll
+                for (int i = 0; i < IPC; ++i) {
+                    float mn = FLT_MAX, mx = -FLT_MAX;
+#pragma unroll
+                    for (int w = 0; w < kThreads / 32; ++w) { mn = fminf(mn, s_mm[iter & 1u][i][w][0]); mx = fmaxf(mx, s_mm[iter & 1u][i][w][1]); }
+                    if (p.frame_zero) { mn = fminf(mn, 0.f); mx = fmaxf(mx, 0.f); }
+                    q_mn[i] = mn; q_rg[i] = __fsub_rn(mx, mn); q_const[i] = mn == mx;
+                }
+            }
             for (uint32_t e = lane; e < n_items * (uint32_t)p.plan_len; e += 32) {
                 const uint32_t il = e / (uint32_t)p.plan_len, i = e - il * (uint32_t)p.plan_len;
                 const int32_t off = plan_in_smem ? s_plan[i] : __ldg(p.plan + i);
@@ -457,7 +529,16 @@ __global__ void __launch_bounds__(kBlock, 3) k_item_pass_bulk(const TileParams p
                     if ((uint32_t)off < G::cells) val = (P)img[il * G::cells + off];
                     else val = pyrb[il * G::pyr_items + (uint32_t)off - G::cells];
                 }
-                __stcs(out + il * p.idx_stride + i, val);
+                if (!QUANT || p.idx_out) __stcs(out + il * p.idx_stride + i, val);
+                if constexpr (QUANT) {
+                    // the index row is embedded in the image's dtype (float32) before the frame is normalised
+                    float mn = q_mn[0], rg = q_rg[0];
+                    bool cst = q_const[0];
+#pragma unroll
+                    for (int j = 1; j < IPC; ++j)
+                        if ((int)il == j) { mn = q_mn[j]; rg = q_rg[j]; cst = q_const[j]; }
+                    p.u8_out[(item0 + il) * p.u8_stride + G::cells + i] = (uint8_t)quant_u8((float)val, mn, rg, cst);
+                }
             }
             __syncwarp();
             if (lane == 0) hq_tc::mbar_arrive(&s_free[iter & 1u]);
@@ -480,7 +561,7 @@ inline int env_int(const char* name, int dflt) {
     return e && *e ? atoi(e) : dflt;
 }
 
-template <int MODE, int LOG2T>
+template <int MODE, int LOG2T, bool QUANT = false>
 int launch_bulk_t(const TileParams& p, cudaStream_t st) {
     using G = Geo<LOG2T>;
     // images: kRing chunk images when a grid is written (the stores read them asynchronously), two otherwise
@@ -502,23 +583,28 @@ int launch_bulk_t(const TileParams& p, cudaStream_t st) {
     const size_t smem = fixed + (size_t)stages * stage_floats * 4;
     static size_t smem_set = 0;
     if (smem > smem_set) {
-        HQ_CUDA_OK(cudaFuncSetAttribute(k_item_pass_bulk<MODE, LOG2T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HQ_CUDA_OK(cudaFuncSetAttribute((k_item_pass_bulk<MODE, LOG2T, QUANT>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
     int per_sm = 0;
-    HQ_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_item_pass_bulk<MODE, LOG2T>, kBlock, smem));
+    HQ_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (k_item_pass_bulk<MODE, LOG2T, QUANT>), kBlock, smem));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > ctas_cap) per_sm = ctas_cap;
     int64_t blocks = (int64_t)hq_cached_sm_count() * per_sm;
     if (blocks > p.num_chunks) blocks = p.num_chunks;
-    k_item_pass_bulk<MODE, LOG2T><<<(unsigned)blocks, kBlock, smem, st>>>(p, ring, stages, stage_floats, plan_cap);
-    HQ_LAUNCH_OK("k_item_pass_bulk");
+    k_item_pass_bulk<MODE, LOG2T, QUANT><<<(unsigned)blocks, kBlock, smem, st>>>(p, ring, stages, stage_floats, plan_cap);
+    HQ_LAUNCH_OK(QUANT ? "k_item_pass_bulk<quant>" : "k_item_pass_bulk");
     return HQ_OK;
 }
 
 template <int MODE>
 int launch_bulk(const TileParams& p, cudaStream_t st) {
     return p.log2t == 5 ? launch_bulk_t<MODE, 5>(p, st) : launch_bulk_t<MODE, 6>(p, st);
+}
+
+template <int MODE>
+int launch_bulk_quant(const TileParams& p, cudaStream_t st) {
+    return p.log2t == 5 ? launch_bulk_t<MODE, 5, true>(p, st) : launch_bulk_t<MODE, 6, true>(p, st);
 }
 
 // ---------------------------------------------------------------------------------------

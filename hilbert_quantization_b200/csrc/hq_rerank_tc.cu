@@ -1,6 +1,8 @@
 // K6: tensor-core rerank.  scores = Q x N x D cosine contraction on tcgen05 (bf16 in, fp32
 // accumulate in TMEM) with the survivor mask and a streaming per-query top-k' fused into the
-// epilogue, followed by an exact fp32 re-score of the k' shortlisted rows.
+// epilogue, followed by an exact fp32 re-score of a shortlist (k_rerank_tc_merge) whose sufficiency is
+// PROVEN per query with a rounding-error bound; queries that cannot be proven are re-scored exactly over
+// all their surviving rows (k_guard_rescore / k_guard_merge), so the returned top-k is the exact path's.
 //
 //   warp 0      : TMA producer   (cp.async.bulk.tensor, 128B-swizzled K-major tiles, 4 stages)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (M=128 queries, N=256 rows, K=16)
@@ -275,152 +277,389 @@ __global__ void __launch_bounds__(64 + 128 * EH, 1) k_rerank_tc(const __grid_con
     }
 }
 
-// merge the per-unit shortlists of one query, re-score the best KP exactly in fp32, emit top-k
-template <int KP>
+constexpr int R_MAX = 64;        // rows re-scored exactly per query at most (in chunks of R_CHUNK, until the guard passes)
+constexpr int R_CHUNK = 16;
+constexpr int FB_SLICES = 128;   // exact fallback: slices of a flagged query's mask row, one CTA each
+constexpr int FB_K = 20;         // the tensor-core rerank supports k <= 20
+
+__device__ __forceinline__ uint32_t ord_of(float v) {            // order-preserving float -> uint32 (> 0 for finite values)
+    const uint32_t b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float float_of_ord(uint32_t o) {
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+// dot(q, row) by one warp: lane-strided fmaf chain + xor tree, every lane returns the sum.  fp32 rows: the arithmetic of
+// k_rerank_sparse (identical scores on both paths).  bf16 rows (a bf16-only database): the stored values, exactly.
+template <bool B16>
+__device__ __forceinline__ float warp_row_dot(const float* __restrict__ qv, const void* __restrict__ row, int D, bool vec, int lane) {
+    float acc = 0.f;
+    if constexpr (!B16) {
+        const float* rv = reinterpret_cast<const float*>(row);
+        if (vec) {
+            for (int i = lane; i < D / 4; i += 32) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(qv) + i);
+                const float4 b = __ldg(reinterpret_cast<const float4*>(rv) + i);
+                acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+            }
+        } else {
+            for (int i = lane; i < D; i += 32) acc = fmaf(__ldg(qv + i), __ldg(rv + i), acc);
+        }
+    } else {
+        const __nv_bfloat16* rv = reinterpret_cast<const __nv_bfloat16*>(row);
+        if (vec) {
+            for (int i = lane; i < D / 8; i += 32) {
+                const uint4 w = __ldg(reinterpret_cast<const uint4*>(rv) + i);
+                const float4 a0 = __ldg(reinterpret_cast<const float4*>(qv) + 2 * i);
+                const float4 a1 = __ldg(reinterpret_cast<const float4*>(qv) + 2 * i + 1);
+                acc = fmaf(a0.x, __uint_as_float(w.x << 16), acc); acc = fmaf(a0.y, __uint_as_float(w.x & 0xffff0000u), acc);
+                acc = fmaf(a0.z, __uint_as_float(w.y << 16), acc); acc = fmaf(a0.w, __uint_as_float(w.y & 0xffff0000u), acc);
+                acc = fmaf(a1.x, __uint_as_float(w.z << 16), acc); acc = fmaf(a1.y, __uint_as_float(w.z & 0xffff0000u), acc);
+                acc = fmaf(a1.z, __uint_as_float(w.w << 16), acc); acc = fmaf(a1.w, __uint_as_float(w.w & 0xffff0000u), acc);
+            }
+        } else {
+            for (int i = lane; i < D; i += 32) acc = fmaf(__ldg(qv + i), __bfloat162float(rv[i]), acc);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    return acc;
+}
+
+__device__ __forceinline__ float score_of(float acc, float nq, float nc) {
+    return (nq != 0.f && nc != 0.f) ? __fmul_rn(__fadd_rn(__fdiv_rn(acc, __fmul_rn(nq, nc)), 1.0f), 0.5f) : 0.f;
+}
+
+// fewer than k results: zero-norm rows (they never reach the shortlists, score exactly 0.0 and follow everybody else), then -1
+__device__ void fill_tail(const TcParams& p, int q, int cnt, int k, int64_t id_base, int64_t* ids, float* scores) {
+    for (int z = 0; z < p.n_zero && cnt < k; ++z) {
+        const int32_t id = p.zero_rows[z];
+        if (p.mask && !((p.mask[(int64_t)q * p.mask_stride + (id >> 5)] >> (id & 31)) & 1u)) continue;
+        ids[(int64_t)q * k + cnt] = (int64_t)id + id_base;
+        scores[(int64_t)q * k + cnt] = 0.f;
+        ++cnt;
+    }
+    for (int j = cnt; j < k; ++j) { ids[(int64_t)q * k + j] = -1; scores[(int64_t)q * k + j] = -1.0f; }
+}
+
+// Merge the per-unit shortlists of one query, re-score the best rows exactly, PROVE that no other row can belong to the
+// top-k, emit.
+//
+// Pool: n_sub = n_ranges * eh sublists of KP (value, row) pairs, each the best KP accumulator values of one epilogue thread's
+// rows, sorted.  The merge walks the pool in (value desc, row asc) order with a tournament over the sublist heads and
+// re-scores the rows it takes in chunks of R_CHUNK (one warp per row, exact).  After every chunk the guard is evaluated:
+//   every row NOT re-scored has accumulator value a <= bound = max(last value of every FULL sublist, value of the next head)
+//   and true value t = q . c / |c| <= a + E, so if the k-th best exact t of the re-scored rows exceeds bound + E, the exact
+//   top-k lies inside the re-scored set.  E bounds |a - t| rigorously:
+//     a - t = (q16 - q) . c16  +  q . (c16 - c / |c|)  +  accumulation error of the tensor pipe
+//     |a - t| <= |q16 - q| * |c16|  +  |q| * dc_max  +  D * 2^-22 * |q| * |c16|          (Cauchy-Schwarz; |c16| <= 1 + 2^-8)
+//   with |q16 - q| computed here from the query, dc_max = max over the rows of |c16 - c / |c|| computed when the database was
+//   built (0 for a bf16-only database, whose rows ARE c16), plus 1e-5 |q| for the fp32 rounding of the exact values themselves.
+// A query whose guard still fails after R_MAX rows (near-duplicate clusters around the k-th score) is appended to the flag
+// list; k_guard_rescore / k_guard_merge then re-score ALL its surviving rows exactly and overwrite its results.
+template <int KP, bool B16>
 __global__ void __launch_bounds__(128) k_rerank_tc_merge(const TcParams p, const float* __restrict__ db_f32, int64_t db_stride,
+                                                         const __nv_bfloat16* __restrict__ db_b16, int64_t db_pitch,
                                                          const float* __restrict__ q_f32, int64_t q_stride,
-                                                         const float* __restrict__ q_norm, int k, int64_t id_base,
-                                                         int64_t* __restrict__ ids, float* __restrict__ scores) {
-    extern __shared__ unsigned char sm[];
-    const int M = p.n_ranges * p.eh * KP;
-    float* c_val = reinterpret_cast<float*>(sm);
-    int32_t* c_idx = reinterpret_cast<int32_t*>(c_val + M);
-    __shared__ float top_val[KP];
-    __shared__ int32_t top_idx[KP];
-    __shared__ float ex_val[KP];
+                                                         const float* __restrict__ q_norm, int k, int64_t id_base, float dc_max,
+                                                         int32_t* __restrict__ guard, int64_t* __restrict__ ids,
+                                                         float* __restrict__ scores) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    const int n_sub = p.n_ranges * p.eh, M = n_sub * KP;
+    uint64_t* c_key = reinterpret_cast<uint64_t*>(sm);           // [M]  (ord(value) << 32) | ~row, 0 = empty slot
+    uint8_t* head = reinterpret_cast<uint8_t*>(c_key + M);       // [n_sub] next untaken entry of every sublist
+    __shared__ uint64_t w_key[4];
+    __shared__ int w_sub[4];
+    __shared__ int32_t sel_id[R_MAX];
+    __shared__ float ex_s[R_MAX], ex_t[R_MAX];
+    __shared__ uint32_t s_B;
+    __shared__ float s_red[4];
+    __shared__ float s_tk;
+    __shared__ int s_state;
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m_tile = q / BM, row = q % BM;
+    if (tid == 0) { s_B = 0; s_state = 0; }
+    for (int s = tid; s < n_sub; s += blockDim.x) head[s] = 0;
+    __syncthreads();
     for (int e = tid; e < M; e += blockDim.x) {
         const int r = e / KP, j = e - r * KP;                   // r = range * eh + half
         const int64_t u = (int64_t)(r / p.eh) * p.m_tiles + m_tile;
         const int64_t a = (((u * p.eh + r % p.eh) * BM + row) * KP) + j;
-        c_val[e] = p.part_val[a];
-        c_idx[e] = p.part_idx[a];
+        const int32_t id = p.part_idx[a];
+        const uint32_t o = ord_of(p.part_val[a]);
+        c_key[e] = id >= 0 ? (((uint64_t)o << 32) | (uint32_t)(0xffffffffu - (uint32_t)id)) : 0ull;
+        if (j == KP - 1 && id >= 0) atomicMax(&s_B, o);         // a full sublist may have dropped rows up to its last value
     }
-    if (tid < KP) { top_val[tid] = -FLT_MAX; top_idx[tid] = -1; }
+    // |bf16(q) - q|
+    const float nq = q_norm[q];
+    const float* qv = q_f32 + (int64_t)q * q_stride;
+    float qe = 0.f;
+    for (int i = tid; i < p.D; i += blockDim.x) {
+        const float x = __ldg(qv + i);
+        const float d = __bfloat162float(__float2bfloat16_rn(x)) - x;
+        qe = fmaf(d, d, qe);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) qe += __shfl_xor_sync(0xffffffffu, qe, o);
+    if (lane == 0) s_red[warp] = qe;
     __syncthreads();
-    // Shortlist = best KP of the M candidates (value desc, id asc), in two levels so that no round needs a block-wide
-    // barrier: every warp extracts the best KP of its own quarter of the candidates (KP rounds of a warp arg-best over
-    // shared memory, __syncwarp only), then warp 0 merges the 4 x KP winners held two per lane in registers.  (The
-    // first version ranked every candidate against every other one, O(M^2): 0.6 ms of a 1.0 ms single-query search;
-    // the second ran KP block-wide rounds with two __syncthreads and a serial pick each: 60 us per 1024-query batch.)
-    __shared__ float w_val[4 * KP];
-    __shared__ int32_t w_idx[4 * KP];
-    {
-        const int per = (M + 3) / 4, e0 = warp * per, e1 = min(M, e0 + per);
-        for (int round = 0; round < KP; ++round) {
-            float bv = -FLT_MAX;
-            int32_t bi = 0x7fffffff, bp = -1;
-            for (int e = e0 + lane; e < e1; e += 32) {
-                const int32_t id = c_idx[e];
+    const float q_err = sqrtf(s_red[0] + s_red[1] + s_red[2] + s_red[3]) * 1.0001f;
+    const float E = q_err * 1.00391f + nq * (dc_max + 1.0e-5f + (float)p.D * 2.4e-7f);
+
+    const bool vec = B16 ? ((p.D % 8 == 0) && (db_pitch % 8 == 0) && (q_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(db_b16) & 15) == 0) &&
+                            ((reinterpret_cast<uintptr_t>(q_f32) & 15) == 0))
+                         : ((p.D % 4 == 0) && (db_stride % 4 == 0) && (q_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(db_f32) & 15) == 0) &&
+                            ((reinterpret_cast<uintptr_t>(q_f32) & 15) == 0));
+    int cnt = 0, done = 0;
+    while (true) {
+        // ---- tournament round: the best head over all sublists ----
+        uint64_t bk = 0;
+        int bs = -1;
+        for (int s = tid; s < n_sub; s += blockDim.x) {
+            const int h = head[s];
+            if (h < KP) {
+                const uint64_t key = c_key[s * KP + h];
+                if (key > bk) { bk = key; bs = s; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const uint64_t ok = __shfl_xor_sync(0xffffffffu, bk, o);
+            const int os = __shfl_xor_sync(0xffffffffu, bs, o);
+            if (ok > bk) { bk = ok; bs = os; }
+        }
+        if (lane == 0) { w_key[warp] = bk; w_sub[warp] = bs; }
+        __syncthreads();
+        uint64_t next_key = w_key[0];
+        int next_sub = w_sub[0];
+#pragma unroll
+        for (int w = 1; w < 4; ++w)
+            if (w_key[w] > next_key) { next_key = w_key[w]; next_sub = w_sub[w]; }
+        const bool exhausted = next_key == 0ull;
+        if (exhausted || cnt == R_MAX || (cnt > done && cnt % R_CHUNK == 0)) {
+            // ---- exact values of the rows taken since the last check (one warp per row) ----
+            for (int c = done + warp; c < cnt; c += 4) {
+                const int32_t id = sel_id[c];
+                const void* rv = B16 ? reinterpret_cast<const void*>(db_b16 + (int64_t)id * db_pitch)
+                                     : reinterpret_cast<const void*>(db_f32 + (int64_t)id * db_stride);
+                const float acc = warp_row_dot<B16>(qv, rv, p.D, vec, lane);
+                const float nc = __ldg(p.db_norm + id);
+                if (lane == 0) { ex_s[c] = score_of(acc, nq, nc); ex_t[c] = nc != 0.f ? __fdiv_rn(acc, nc) : 0.f; }
+            }
+            done = cnt;
+            __syncthreads();
+            // ---- guard ----
+            if (warp == 0) {
+                const uint32_t next_o = exhausted ? 0u : (uint32_t)(next_key >> 32);
+                const uint32_t bound_o = s_B > next_o ? s_B : next_o;
+                int state;
+                if (bound_o == 0u) {
+                    state = 1;                                      // nothing was left out: every surviving row has been re-scored
+                } else if (cnt >= k) {
+                    // k-th largest exact value among the re-scored rows (rank by counting, cnt <= 64)
+                    for (int i = lane; i < cnt; i += 32) {
+                        const float ti = ex_t[i];
+                        int rank = 0;
+                        for (int j = 0; j < cnt; ++j) rank += (ex_t[j] > ti || (ex_t[j] == ti && j < i)) ? 1 : 0;
+                        if (rank == k - 1) s_tk = ti;
+                    }
+                    __syncwarp();
+                    state = (s_tk > float_of_ord(bound_o) + E) ? 1 : ((exhausted || cnt >= R_MAX) ? 2 : 0);
+                } else {
+                    state = (exhausted || cnt >= R_MAX) ? 2 : 0;
+                }
+                if (lane == 0) s_state = state;
+            }
+            __syncthreads();
+            if (s_state != 0) break;
+        }
+        // ---- take the head ----
+        if (tid == 0) {
+            sel_id[cnt] = (int32_t)(0xffffffffu - (uint32_t)(next_key & 0xffffffffull));
+            head[next_sub] = (uint8_t)(head[next_sub] + 1);
+        }
+        ++cnt;
+        __syncthreads();
+    }
+    // ---- emit: rank the re-scored rows by (exact score desc, row asc) ----
+    if (tid < cnt) {
+        const int32_t id = sel_id[tid];
+        const float v = ex_s[tid];
+        int rank = 0;
+        for (int j = 0; j < cnt; ++j) rank += (ex_s[j] > v || (ex_s[j] == v && sel_id[j] < id)) ? 1 : 0;
+        if (rank < k) { ids[(int64_t)q * k + rank] = (int64_t)id + id_base; scores[(int64_t)q * k + rank] = v; }
+    }
+    if (tid == 0) {
+        fill_tail(p, q, cnt < k ? cnt : k, k, id_base, ids, scores);
+        if (guard) {
+            atomicAdd(&guard[1], cnt);
+            if (s_state == 2) guard[4 + atomicAdd(&guard[0], 1)] = q;
+        }
+    }
+}
+
+// ---- exact fallback of the flagged queries -----------------------------------------------------------------------
+// Persistent over (flagged query, mask slice) items read from the device-side flag list; no flagged query = immediate exit.
+// One warp per surviving row, exact score; per-warp top-k lists in shared memory, merged per CTA into fb[q][slice][FB_K].
+template <bool B16>
+__global__ void __launch_bounds__(256) k_guard_rescore(const TcParams p, const float* __restrict__ db_f32, int64_t db_stride,
+                                                       const __nv_bfloat16* __restrict__ db_b16, int64_t db_pitch,
+                                                       const float* __restrict__ q_f32, int64_t q_stride,
+                                                       const float* __restrict__ q_norm, int k, const int32_t* __restrict__ guard,
+                                                       float* __restrict__ fb_val, int32_t* __restrict__ fb_idx) {
+    __shared__ float l_val[8][FB_K];
+    __shared__ int32_t l_idx[8][FB_K];
+    const int n_f = guard[0];
+    if (n_f <= 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t words = (p.N + 31) / 32, wps = (words + FB_SLICES - 1) / FB_SLICES;
+    const bool vec = B16 ? ((p.D % 8 == 0) && (db_pitch % 8 == 0) && (q_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(db_b16) & 15) == 0) &&
+                            ((reinterpret_cast<uintptr_t>(q_f32) & 15) == 0))
+                         : ((p.D % 4 == 0) && (db_stride % 4 == 0) && (q_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(db_f32) & 15) == 0) &&
+                            ((reinterpret_cast<uintptr_t>(q_f32) & 15) == 0));
+    for (int64_t item = blockIdx.x; item < (int64_t)n_f * FB_SLICES; item += gridDim.x) {
+        const int f = (int)(item / FB_SLICES), sl = (int)(item - (int64_t)f * FB_SLICES);
+        const int q = guard[4 + f];
+        const float nq = q_norm[q];
+        const float* qv = q_f32 + (int64_t)q * q_stride;
+        if (lane < FB_K) { l_val[warp][lane] = -1.f; l_idx[warp][lane] = -1; }
+        __syncwarp();
+        const int64_t w0 = sl * wps, w1 = min(words, w0 + wps);
+        for (int64_t w = w0 + warp; w < w1; w += 8) {
+            uint32_t bits = p.mask ? __ldg(p.mask + (int64_t)q * p.mask_stride + w) : 0xffffffffu;
+            if (w * 32 + 32 > p.N) bits &= (1u << (uint32_t)(p.N - w * 32)) - 1u;
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const int32_t id = (int32_t)(w * 32 + b);
+                const float nc = __ldg(p.db_norm + id);
+                if (nc == 0.f) continue;                          // zero-norm rows: appended by the merge's tail rule
+                const void* rv = B16 ? reinterpret_cast<const void*>(db_b16 + (int64_t)id * db_pitch)
+                                     : reinterpret_cast<const void*>(db_f32 + (int64_t)id * db_stride);
+                const float s = score_of(warp_row_dot<B16>(qv, rv, p.D, vec, lane), nq, nc);
+                const float wv = l_val[warp][k - 1];
+                const int32_t wi = l_idx[warp][k - 1];
+                if (wi < 0 || s > wv || (s == wv && id < wi)) {
+                    if (lane == 0) {
+                        int pos = k - 1;
+                        while (pos > 0) {
+                            const float pv = l_val[warp][pos - 1];
+                            const int32_t pi = l_idx[warp][pos - 1];
+                            if (pi >= 0 && (pv > s || (pv == s && pi < id))) break;
+                            l_val[warp][pos] = pv; l_idx[warp][pos] = pi;
+                            --pos;
+                        }
+                        l_val[warp][pos] = s; l_idx[warp][pos] = id;
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        __syncthreads();
+        // CTA top-k of the 8 warp lists: rank by counting (<= 8 * FB_K entries)
+        float* ov = fb_val + ((int64_t)q * FB_SLICES + sl) * FB_K;
+        int32_t* oi = fb_idx + ((int64_t)q * FB_SLICES + sl) * FB_K;
+        if (tid < FB_K) { ov[tid] = -1.f; oi[tid] = -1; }
+        __syncthreads();
+        if (tid < 8 * k) {
+            const int wl = tid / k, j = tid - wl * k;
+            const float v = l_val[wl][j];
+            const int32_t id = l_idx[wl][j];
+            if (id >= 0) {
+                int rank = 0;
+                for (int a = 0; a < 8; ++a)
+                    for (int c = 0; c < k; ++c) {
+                        const int32_t ic = l_idx[a][c];
+                        if (ic < 0) continue;
+                        const float vc = l_val[a][c];
+                        rank += (vc > v || (vc == v && ic < id)) ? 1 : 0;
+                    }
+                if (rank < k) { ov[rank] = v; oi[rank] = id; }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) k_guard_merge(const TcParams p, int k, int64_t id_base, const int32_t* __restrict__ guard,
+                                                     float* __restrict__ fb_val, int32_t* __restrict__ fb_idx,
+                                                     int64_t* __restrict__ ids, float* __restrict__ scores) {
+    __shared__ float w_val[8];
+    __shared__ int32_t w_idx[8];
+    __shared__ int w_pos[8];
+    const int n_f = guard[0];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int f = blockIdx.x; f < n_f; f += gridDim.x) {
+        const int q = guard[4 + f];
+        float* cv = fb_val + (int64_t)q * FB_SLICES * FB_K;
+        int32_t* ci = fb_idx + (int64_t)q * FB_SLICES * FB_K;
+        int cnt = 0;
+        for (int round = 0; round < k; ++round) {
+            float bv = -2.f;
+            int32_t bi = -1;
+            int bp = -1;
+            for (int e = tid; e < FB_SLICES * FB_K; e += blockDim.x) {
+                const int32_t id = ci[e];
                 if (id < 0) continue;
-                const float v = c_val[e];
+                const float v = cv[e];
                 if (bp < 0 || v > bv || (v == bv && id < bi)) { bv = v; bi = id; bp = e; }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int32_t oi = __shfl_xor_sync(0xffffffffu, bi, o), op = __shfl_xor_sync(0xffffffffu, bp, o);
+                const int32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                const int op = __shfl_xor_sync(0xffffffffu, bp, o);
                 if (op >= 0 && (bp < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; bp = op; }
             }
-            if (lane == 0) {
-                w_val[warp * KP + round] = bp >= 0 ? bv : -FLT_MAX;
-                w_idx[warp * KP + round] = bp >= 0 ? bi : -1;
-                if (bp >= 0) c_idx[bp] = -1;                   // taken
-            }
-            __syncwarp();
-        }
-    }
-    __syncthreads();
-    if (warp == 0) {
-        constexpr int PER = (4 * KP + 31) / 32;
-        float mv[PER];
-        int32_t mi[PER];
-#pragma unroll
-        for (int s = 0; s < PER; ++s) {
-            const int e = lane + 32 * s;
-            mv[s] = e < 4 * KP ? w_val[e] : -FLT_MAX;
-            mi[s] = e < 4 * KP ? w_idx[e] : -1;
-        }
-        for (int round = 0; round < KP; ++round) {
-            float bv = -FLT_MAX;
-            int32_t bi = -1, bs = -1;
-#pragma unroll
-            for (int s = 0; s < PER; ++s)
-                if (mi[s] >= 0 && (bi < 0 || mv[s] > bv || (mv[s] == bv && mi[s] < bi))) { bv = mv[s]; bi = mi[s]; bs = s; }
-            int bl = lane;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
-                if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && (oi < bi || (oi == bi && ol < bl))))) { bv = ov; bi = oi; bl = ol; }
-            }
-            if (bi >= 0 && bl == lane) {
-#pragma unroll
-                for (int s = 0; s < PER; ++s)
-                    if (s == bs) mi[s] = -1;
-            }
-            if (lane == 0) { top_val[round] = bi >= 0 ? bv : -FLT_MAX; top_idx[round] = bi; }
-        }
-    }
-    __syncthreads();
-    // exact fp32 cosine of the shortlisted rows (one warp per candidate)
-    const float nq = q_norm[q];
-    const float* qv = q_f32 + (int64_t)q * q_stride;
-    const bool vec = (p.D % 4 == 0) && (db_stride % 4 == 0) && (q_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(db_f32) & 15) == 0) &&
-                     ((reinterpret_cast<uintptr_t>(q_f32) & 15) == 0);
-    for (int c = warp; c < KP; c += 4) {
-        const int32_t id = top_idx[c];
-        float s = -1.0f;
-        if (id >= 0) {
-            const float* rv = db_f32 + (int64_t)id * db_stride;
-            float acc = 0.f;
-            if (vec) {
-                for (int i = lane; i < p.D / 4; i += 32) {
-                    const float4 a = __ldg(reinterpret_cast<const float4*>(qv) + i);
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(rv) + i);
-                    acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+            if (lane == 0) { w_val[warp] = bv; w_idx[warp] = bi; w_pos[warp] = bp; }
+            __syncthreads();
+            if (tid == 0) {
+                int best = -1;
+                for (int w = 0; w < 8; ++w) {
+                    if (w_pos[w] < 0) continue;
+                    if (best < 0 || w_val[w] > w_val[best] || (w_val[w] == w_val[best] && w_idx[w] < w_idx[best])) best = w;
                 }
-            } else {
-                for (int i = lane; i < p.D; i += 32) acc = fmaf(__ldg(qv + i), __ldg(rv + i), acc);
+                if (best >= 0) {
+                    ids[(int64_t)q * k + round] = (int64_t)w_idx[best] + id_base;
+                    scores[(int64_t)q * k + round] = w_val[best];
+                    ci[w_pos[best]] = -1;                          // taken
+                    w_pos[0] = 1;
+                } else {
+                    w_pos[0] = -1;
+                }
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            const float nc = __ldg(p.db_norm + id);
-            s = 0.f;
-            if (nq != 0.f && nc != 0.f) s = __fmul_rn(__fadd_rn(__fdiv_rn(acc, __fmul_rn(nq, nc)), 1.0f), 0.5f);
-        }
-        if (lane == 0) ex_val[c] = s;
-    }
-    __syncthreads();
-    if (tid < KP) {
-        const int32_t id = top_idx[tid];
-        const float v = ex_val[tid];
-        if (id >= 0) {
-            int rank = 0;
-            for (int j = 0; j < KP; ++j) {
-                const int32_t idj = top_idx[j];
-                if (idj < 0) continue;
-                rank += (ex_val[j] > v || (ex_val[j] == v && idj < id)) ? 1 : 0;
-            }
-            if (rank < k) { ids[(int64_t)q * k + rank] = (int64_t)id + id_base; scores[(int64_t)q * k + rank] = v; }
-        }
-    }
-    // fewer than k survivors: fill the tail
-    if (tid == 0) {
-        int cnt = 0;
-        for (int j = 0; j < KP; ++j) cnt += top_idx[j] >= 0 ? 1 : 0;
-        // unit-row operand: zero-norm rows never reach the shortlists; they score 0.0 and follow everybody else
-        for (int z = 0; z < p.n_zero && cnt < k; ++z) {
-            const int32_t id = p.zero_rows[z];
-            if (p.mask && !((p.mask[(int64_t)q * p.mask_stride + (id >> 5)] >> (id & 31)) & 1u)) continue;
-            ids[(int64_t)q * k + cnt] = (int64_t)id + id_base;
-            scores[(int64_t)q * k + cnt] = 0.f;
+            __syncthreads();
+            const bool got = w_pos[0] >= 0;
+            __syncthreads();
+            if (!got) break;
             ++cnt;
         }
-        for (int j = cnt; j < k; ++j) { ids[(int64_t)q * k + j] = -1; scores[(int64_t)q * k + j] = -1.0f; }
+        if (tid == 0) fill_tail(p, q, cnt, k, id_base, ids, scores);
+        __syncthreads();
     }
+}
+
+// max over the rows of | bf16 unit row - c / |c| |_2  (the database-side term of the guard's error bound)
+__global__ void __launch_bounds__(256) k_bf16_unit_error_max(const float* __restrict__ src, int64_t N, int64_t D, int64_t src_stride,
+                                                             const float* __restrict__ norms, const __nv_bfloat16* __restrict__ unit,
+                                                             int64_t pitch, float* __restrict__ out_max) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float worst = 0.f;
+    for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < N; r += warps) {
+        const float n = __ldg(norms + r);
+        float e = 0.f;
+        for (int64_t c = lane; c < D; c += 32) {
+            const float x = n > 0.f ? __fdiv_rn(__ldg(src + r * src_stride + c), n) : 0.f;
+            const float d = __bfloat162float(unit[r * pitch + c]) - x;
+            e = fmaf(d, d, e);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+        worst = fmaxf(worst, e);
+    }
+    if (lane == 0 && worst > 0.f) atomicMax(reinterpret_cast<int*>(out_max), __float_as_int(sqrtf(worst) * 1.0001f + 1e-7f));
 }
 
 __global__ void __launch_bounds__(256) k_to_bf16(const float* __restrict__ src, int64_t N, int64_t D, int64_t src_stride,
@@ -498,26 +737,48 @@ void plan_units(int64_t N, int Q, int sms, TcParams& p) {
 
 int pick_kp(int k) { return k <= 10 ? 16 : (k <= 20 ? 32 : 0); }
 
-template <int KP, int EH, bool PS>
+struct GuardArgs {
+    float dc_max;
+    int32_t* guard;        // [4 + Q] int32: [0] flagged queries, [1] rows re-scored exactly, [4..] the flagged queries
+    float* fb_val;         // [Q][FB_SLICES][FB_K] fallback partial lists
+    int32_t* fb_idx;
+};
+
+template <int KP, int EH, bool B16>
 int launch_tc(const CUtensorMap& mq, const CUtensorMap& mdb, const TcParams& p, const float* db_f32, int64_t db_stride,
-              const float* q_f32, int64_t q_stride, const float* q_norm, int k, int64_t id_base, int64_t* ids, float* scores,
-              cudaStream_t st) {
+              const __nv_bfloat16* db_b16, int64_t db_pitch, const float* q_f32, int64_t q_stride, const float* q_norm, int k,
+              int64_t id_base, const GuardArgs& g, int64_t* ids, float* scores, cudaStream_t st) {
     const size_t smem = STAGES * STAGE_BYTES + (2 * BN + 32 * 128 + 8 * 128) * sizeof(float) + (2 * STAGES + 4) * sizeof(uint64_t) + 16 + 1024;
     static bool attr = false;
     if (!attr) {
-        HQ_CUDA_OK(cudaFuncSetAttribute((k_rerank_tc<KP, EH, PS>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HQ_CUDA_OK(cudaFuncSetAttribute((k_rerank_tc<KP, EH, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
     int grid = hq_cached_sm_count();
     if (grid > p.num_units) grid = p.num_units;
-    k_rerank_tc<KP, EH, PS><<<grid, 64 + 128 * EH, smem, st>>>(mq, mdb, p);
+    HQ_CUDA_OK(cudaMemsetAsync(g.guard, 0, 4 * sizeof(int32_t), st));
+    k_rerank_tc<KP, EH, true><<<grid, 64 + 128 * EH, smem, st>>>(mq, mdb, p);
     HQ_LAUNCH_OK("k_rerank_tc");
-    const size_t msm = (size_t)p.n_ranges * EH * KP * 8;
-    if (msm > 48 * 1024) HQ_CUDA_OK(cudaFuncSetAttribute(k_rerank_tc_merge<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
-    k_rerank_tc_merge<KP><<<p.Q, 128, msm, st>>>(p, db_f32, db_stride, q_f32, q_stride, q_norm, k, id_base, ids, scores);
+    const size_t msm = (size_t)p.n_ranges * EH * KP * 8 + (size_t)p.n_ranges * EH + 16;
+    static size_t msm_set = 48 * 1024;
+    if (msm > msm_set) {
+        HQ_REQUIRE(msm <= 220 * 1024, "too many partial shortlists per query (%zu bytes of shared memory)", msm);
+        HQ_CUDA_OK(cudaFuncSetAttribute((k_rerank_tc_merge<KP, B16>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
+        msm_set = msm;
+    }
+    k_rerank_tc_merge<KP, B16><<<p.Q, 128, msm, st>>>(p, db_f32, db_stride, db_b16, db_pitch, q_f32, q_stride, q_norm, k, id_base,
+                                                       g.dc_max, g.guard, ids, scores);
     HQ_LAUNCH_OK("k_rerank_tc_merge");
+    // exact fallback of the flagged queries (both kernels return at once when the flag list is empty)
+    k_guard_rescore<B16><<<hq_cached_sm_count() * 2, 256, 0, st>>>(p, db_f32, db_stride, db_b16, db_pitch, q_f32, q_stride, q_norm, k,
+                                                                   g.guard, g.fb_val, g.fb_idx);
+    HQ_LAUNCH_OK("k_guard_rescore");
+    k_guard_merge<<<64, 256, 0, st>>>(p, k, id_base, g.guard, g.fb_val, g.fb_idx, ids, scores);
+    HQ_LAUNCH_OK("k_guard_merge");
     return HQ_OK;
 }
+
+int64_t parts_bytes(const TcParams& p, int kp) { return (int64_t)p.num_units * 2 * BM * kp * 8; }
 
 }  // namespace
 
@@ -538,73 +799,76 @@ extern "C" int64_t hq_rerank_bf16_scratch_bytes(int64_t N, int Q, int k) {
     if (kp == 0 || N <= 0 || Q <= 0) return 0;
     TcParams p{};
     plan_units(N, Q, hq_cached_sm_count(), p);
-    return (int64_t)p.num_units * 2 * BM * kp * 8;            // sized for two partial lists per unit
+    return parts_bytes(p, kp) + (int64_t)Q * FB_SLICES * FB_K * 8;     // partial shortlists + fallback partial lists
 }
 
-static int rerank_topk_bf16(bool unit_rows, const int32_t* zero_rows, int n_zero, const void* db_bf16, int64_t db_pitch,
-                            const float* db_f32, int64_t db_stride, const float* db_norm,
-                            int64_t N, int64_t D, const void* q_bf16, int64_t q_pitch, const float* q_f32, int64_t q_stride,
-                            const float* q_norm, int Q, const uint32_t* mask, int64_t mask_stride, int k, int64_t id_base,
-                            int64_t* ids, float* scores, void* scratch, int64_t scratch_bytes, void* stream) {
+extern "C" int hq_rerank_topk_unit_bf16(const void* db_unit_bf16, int64_t db_pitch, const float* db_f32, int64_t db_stride,
+                                        const float* db_norm, const int32_t* zero_rows, int n_zero, int64_t N, int64_t D,
+                                        const void* q_bf16, int64_t q_pitch, const float* q_f32, int64_t q_stride, const float* q_norm,
+                                        int Q, const uint32_t* mask, int64_t mask_stride, int k, int64_t id_base, float dc_max,
+                                        int64_t* ids, float* scores, int32_t* guard, void* scratch, int64_t scratch_bytes,
+                                        void* stream) {
+    HQ_REQUIRE(n_zero >= 0 && (n_zero == 0 || zero_rows), "zero_rows missing");
     HQ_REQUIRE(N >= 0 && Q >= 0 && D > 0, "bad shape");
     const int kp = pick_kp(k);
     HQ_REQUIRE(k >= 1 && kp != 0, "k must be in [1, 20] for the tensor-core rerank (got %d)", k);
     if (Q == 0) return HQ_OK;
     HQ_REQUIRE(ids && scores, "null output");
     if (N == 0) return hq_topk_from_scores(nullptr, 0, 0, Q, k, id_base, ids, scores, stream);
-    HQ_REQUIRE(db_bf16 && db_f32 && db_norm && q_bf16 && q_f32 && q_norm, "null pointer");
+    HQ_REQUIRE(db_unit_bf16 && db_norm && q_bf16 && q_f32 && q_norm && guard, "null pointer");
+    HQ_REQUIRE(dc_max >= 0.f && dc_max < 1.f, "dc_max out of range");
     HQ_REQUIRE(db_pitch % 8 == 0 && q_pitch % 8 == 0 && db_pitch >= D && q_pitch >= D, "bf16 row pitch must be a multiple of 8 and >= D");
-    HQ_REQUIRE((reinterpret_cast<uintptr_t>(db_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(q_bf16) & 15) == 0, "bf16 operands must be 16-byte aligned");
+    HQ_REQUIRE((reinterpret_cast<uintptr_t>(db_unit_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(q_bf16) & 15) == 0, "bf16 operands must be 16-byte aligned");
     HQ_REQUIRE(N < ((int64_t)1 << 31), "N too large for one shard");
     HQ_REQUIRE(!mask || mask_stride * 32 >= N, "mask stride too small");
     TcParams p{};
     p.N = N; p.Q = Q; p.D = (int)D; p.db_norm = db_norm; p.mask = mask; p.mask_stride = mask_stride;
     p.zero_rows = zero_rows; p.n_zero = n_zero;
     plan_units(N, Q, hq_cached_sm_count(), p);
-    // Rows of up to 1024 values: the MMAs of a tile take less time than a four-warp epilogue (768-D ran at 60 % of
-    // the tensor peak), so the tile's columns are split over eight epilogue warps.
-    // (measured faster at 1536-D too: 2.40 -> 2.25 ms per 1024 x 1 M batch)
+    // Eight epilogue warps (two threads per query row): the MMAs of a 768-D tile take less time than a four-warp epilogue
+    // (60 % of the tensor peak), and it measured faster at 1536-D too (2.40 -> 2.25 ms per 1024 x 1 M batch).
     p.eh = 2;
-    if (const char* e = getenv("HQ_RERANK_EH")) { if (e[0] == '1' && !unit_rows) p.eh = 1; }
-    const int64_t need = (int64_t)p.num_units * p.eh * BM * kp * 8;
+    const int64_t parts = (int64_t)p.num_units * p.eh * BM * kp * 8;
+    const int64_t need = parts + (int64_t)Q * FB_SLICES * FB_K * 8;
     HQ_REQUIRE(scratch && scratch_bytes >= need, "scratch too small: need %lld bytes", (long long)need);
     p.part_val = reinterpret_cast<float*>(scratch);
     p.part_idx = reinterpret_cast<int32_t*>(p.part_val + (int64_t)p.num_units * p.eh * BM * kp);
+    GuardArgs g{};
+    g.dc_max = dc_max;
+    g.guard = guard;
+    g.fb_val = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + parts);
+    g.fb_idx = reinterpret_cast<int32_t*>(g.fb_val + (int64_t)Q * FB_SLICES * FB_K);
     CUtensorMap mq, mdb;
     int rc = make_map(&mq, q_bf16, Q, D, q_pitch, BM);
     if (rc != HQ_OK) return rc;
-    rc = make_map(&mdb, db_bf16, N, D, db_pitch, BN);
+    rc = make_map(&mdb, db_unit_bf16, N, D, db_pitch, BN);
     if (rc != HQ_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-#define HQ_TC_LAUNCH(KP_, EH_, PS_) \
-    return launch_tc<KP_, EH_, PS_>(mq, mdb, p, db_f32, db_stride, q_f32, q_stride, q_norm, k, id_base, ids, scores, st)
-    if (unit_rows) {
-        if (kp == 16) HQ_TC_LAUNCH(16, 2, true);
-        HQ_TC_LAUNCH(32, 2, true);
+    const __nv_bfloat16* b16 = reinterpret_cast<const __nv_bfloat16*>(db_unit_bf16);
+#define HQ_TC_LAUNCH(KP_, B16_) \
+    return launch_tc<KP_, 2, B16_>(mq, mdb, p, db_f32, db_stride, b16, db_pitch, q_f32, q_stride, q_norm, k, id_base, g, ids, scores, st)
+    if (db_f32) {
+        HQ_REQUIRE(db_stride >= D, "fp32 row stride too small");
+        if (kp == 16) HQ_TC_LAUNCH(16, false);
+        HQ_TC_LAUNCH(32, false);
     }
-    if (kp == 16 && p.eh == 2) HQ_TC_LAUNCH(16, 2, false);
-    if (kp == 16) HQ_TC_LAUNCH(16, 1, false);
-    if (p.eh == 2) HQ_TC_LAUNCH(32, 2, false);
-    HQ_TC_LAUNCH(32, 1, false);
+    if (kp == 16) HQ_TC_LAUNCH(16, true);
+    HQ_TC_LAUNCH(32, true);
 #undef HQ_TC_LAUNCH
 }
 
-extern "C" int hq_rerank_topk_bf16(const void* db_bf16, int64_t db_pitch, const float* db_f32, int64_t db_stride, const float* db_norm,
-                                   int64_t N, int64_t D, const void* q_bf16, int64_t q_pitch, const float* q_f32, int64_t q_stride,
-                                   const float* q_norm, int Q, const uint32_t* mask, int64_t mask_stride, int k, int64_t id_base,
-                                   int64_t* ids, float* scores, void* scratch, int64_t scratch_bytes, void* stream) {
-    return rerank_topk_bf16(false, nullptr, 0, db_bf16, db_pitch, db_f32, db_stride, db_norm, N, D, q_bf16, q_pitch, q_f32, q_stride, q_norm,
-                            Q, mask, mask_stride, k, id_base, ids, scores, scratch, scratch_bytes, stream);
-}
-
-extern "C" int hq_rerank_topk_unit_bf16(const void* db_unit_bf16, int64_t db_pitch, const float* db_f32, int64_t db_stride,
-                                        const float* db_norm, const int32_t* zero_rows, int n_zero, int64_t N, int64_t D,
-                                        const void* q_bf16, int64_t q_pitch, const float* q_f32, int64_t q_stride, const float* q_norm,
-                                        int Q, const uint32_t* mask, int64_t mask_stride, int k, int64_t id_base, int64_t* ids,
-                                        float* scores, void* scratch, int64_t scratch_bytes, void* stream) {
-    HQ_REQUIRE(n_zero >= 0 && (n_zero == 0 || zero_rows), "zero_rows missing");
-    return rerank_topk_bf16(true, zero_rows, n_zero, db_unit_bf16, db_pitch, db_f32, db_stride, db_norm, N, D, q_bf16, q_pitch, q_f32,
-                            q_stride, q_norm, Q, mask, mask_stride, k, id_base, ids, scores, scratch, scratch_bytes, stream);
+extern "C" int hq_bf16_unit_error_max(const float* src, int64_t N, int64_t D, int64_t src_stride, const float* norms,
+                                      const void* unit_bf16, int64_t pitch, float* out_max, void* stream) {
+    HQ_REQUIRE(N >= 0 && D > 0 && src_stride >= D && pitch >= D, "bad shape");
+    if (N == 0) return HQ_OK;
+    HQ_REQUIRE(src && norms && unit_bf16 && out_max, "null pointer");
+    int64_t blocks = (N * 32 + 255) / 256;
+    const int64_t cap = (int64_t)hq_cached_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    k_bf16_unit_error_max<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, N, D, src_stride, norms,
+                                                                             (const __nv_bfloat16*)unit_bf16, pitch, out_max);
+    HQ_LAUNCH_OK("k_bf16_unit_error_max");
+    return HQ_OK;
 }
 
 extern "C" int hq_to_bf16_unit(const float* src, int64_t N, int64_t D, int64_t src_stride, const float* norms, void* dst,

@@ -12,6 +12,7 @@
 // segments.  The run-mean pyramid (levels 1..3) is reduced in registers with warp
 // shuffles straight from the loaded quads; levels >= 4 are finished from shared memory.
 #include "hq_tc.cuh"
+#include <float.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -36,6 +37,10 @@ struct TileParams {
     int min_level;          // lowest pyramid level the plan references (>= 1), 99 = none
     int64_t num_chunks;
     int vec_src, vec_grid, vec_stream;   // 128-bit access legal?
+    // fused uint8 quantisation of the enhanced frame (k_item_pass_bulk<.., QUANT>): frame = n^2 grid bytes + plan_len index bytes
+    uint8_t* u8_out; int64_t u8_stride;  // bytes per item frame (multiple of 16)
+    float* mm_out;                       // [N, 2] (min, max) of every frame
+    int frame_zero;                      // the frame holds structural zeros (padding cells / padded index slots)
 };
 
 __device__ __forceinline__ uint32_t quad_entry(int log2t, uint32_t q) {
@@ -555,6 +560,38 @@ extern "C" int hq_map_index_fused_ml(const float* src, int direction, int64_t N,
                                      int64_t idx_stride, void* scratch, int64_t scratch_bytes, void* stream) {
     return fused_impl(src, direction, N, D, src_stride, n, grid_out, grid_stride, stream_out, stream_stride, plan, plan_len,
                       pyr_mode, min_level, idx_out, idx_stride, scratch, scratch_bytes, (cudaStream_t)stream);
+}
+
+// map_to_2d + hierarchical index + uint8 quantisation of the enhanced frame in ONE launch (grids of 32 x 32 and 64 x 64,
+// 16-byte aligned rows with D % 4 == 0); HQ_EUNSUPPORTED otherwise (callers run hq_map_index_fused + hq_quantize_u8).
+extern "C" int hq_map_index_quant(const float* src, int64_t N, int64_t D, int64_t src_stride, int n, const int32_t* plan, int plan_len,
+                                  int pyr_mode, int min_level, int frame_zero, uint8_t* u8_out, int64_t u8_stride, float* minmax,
+                                  void* idx_out, int64_t idx_stride, void* stream) {
+    HQ_REQUIRE(hq_is_pow2(n) && n >= 4 && n <= (1 << 15), "fused path needs a power-of-2 grid side in [4, 32768], got %d", n);
+    HQ_REQUIRE(pyr_mode == 0 || pyr_mode == 1, "pyr_mode must be 0 or 1");
+    const int64_t cells = (int64_t)n * n;
+    HQ_REQUIRE(D >= 0 && D <= cells, "Too many parameters (%lld) for dimensions %dx%d", (long long)D, n, n);
+    HQ_REQUIRE(N >= 0 && plan_len >= 0, "negative size");
+    if (N == 0) return HQ_OK;
+    HQ_REQUIRE(src && u8_out && minmax && (plan_len == 0 || plan), "null pointer");
+    HQ_REQUIRE(src_stride >= D && u8_stride >= cells + plan_len, "stride smaller than row / frame");
+    TileParams p{};
+    p.src = src; p.direction = 0; p.N = N; p.D = D; p.src_stride = src_stride; p.D_last = D;
+    p.log2n = hq_log2(n); p.log2t = p.log2n;
+    p.plan = plan; p.plan_len = plan_len; p.idx_out = idx_out; p.idx_stride = idx_stride;
+    p.min_level = plan_len > 0 ? (min_level < 1 ? 1 : min_level) : 99;
+    p.u8_out = u8_out; p.u8_stride = u8_stride; p.mm_out = minmax; p.frame_zero = (frame_zero || D < cells) ? 1 : 0;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    p.vec_src = al16(src) && (src_stride % 4 == 0);
+    const bool ok = (n == 32 || n == 64) && p.vec_src && D % 4 == 0 && D >= 4 && al16(u8_out) && u8_stride % 16 == 0 &&
+                    (int64_t)256 * src_stride < ((int64_t)1 << 31);
+    if (!ok) {
+        hq_set_error("hq_map_index_quant: shape not covered by the fused kernel (n = %d, D = %lld)", n, (long long)D);
+        return HQ_EUNSUPPORTED;
+    }
+    const uint32_t qpi = (1u << (2 * p.log2t)) / 4;
+    p.num_chunks = (N + (kChunkQuads / qpi) - 1) / (kChunkQuads / qpi);
+    return pyr_mode ? item_pass::launch_bulk_quant<1>(p, (cudaStream_t)stream) : item_pass::launch_bulk_quant<0>(p, (cudaStream_t)stream);
 }
 
 // Parameter stream (BASELINE config 4): `total` consecutive float32 values cut into ceil(total / n^2) grids of n x n,

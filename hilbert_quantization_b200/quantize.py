@@ -5,7 +5,7 @@ stores min/max on the instance, `_denormalize_from_compression` uses the last st
 pair); the batched functions carry min/max explicitly per frame."""
 from __future__ import annotations
 
-from typing import Tuple
+from typing import Optional, Tuple
 
 import numpy as np
 import torch
@@ -27,6 +27,70 @@ def quantize_u8_batch(frames: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]
     with torch.cuda.device(d):
         check(lib.hq_quantize_u8(dev.ptr(frames), N, elems, elems, dev.ptr(out), elems, dev.ptr(mm), dev.stream_ptr()))
     return out, mm
+
+
+def map_index_quantize(embeddings: torch.Tensor, n: Optional[int] = None, *, variant: str = "B", index_space: Optional[int] = None,
+                       want_indices: bool = False):
+    """map_to_2d + hierarchical index + embed + uint8 normalise of a batch in ONE kernel (hq_map_index_quant): what
+    QuantizationPipeline.quantize_model hands to the image codec (core/pipeline.py:129-146, core/compressor.py:256-280).
+
+    embeddings float32 [N, D] on the device.  Returns (frames uint8 [N, n + rows, n], minmax float32 [N, 2], indices or None):
+    rows = 1 (variants A / B, index_space = n values, the pipeline's layout) or L (variant C).  Shapes the fused kernel does
+    not cover (grids other than 32 x 32 / 64 x 64, unaligned rows) run the two-launch path (fused map + index into an
+    enhanced float32 frame, then hq_quantize_u8) with identical results."""
+    from . import plans
+    from .index import _plan_tensor, fused_pass
+    d = dev.require_cuda(embeddings.device)
+    if embeddings.dtype != torch.float32 or embeddings.dim() != 2:
+        raise TypeError("map_index_quantize expects float32 [N, D]")
+    emb = embeddings.contiguous()
+    N, D = emb.shape
+    if n is None:
+        from .dimension import rag_optimal_dimensions
+        n = rag_optimal_dimensions(D)[0]
+    pyr_mode = 0
+    if variant == "C":
+        plan, widths, ml = plans.c_plan(n, "rows")
+        key = ("C", n, "rows")
+    else:
+        S = int(index_space if index_space is not None else n)
+        if S != n:
+            raise ValueError("the embedded index row holds exactly n values (core/pipeline.py:112, core/index_generator.py:241-245)")
+        plan, ml = plans.a_plan(n, S) if variant == "A" else plans.b_plan(n, S)
+        key, pyr_mode = ((variant, n, S), 0 if variant == "A" else 1)
+    rows = len(plan) // n
+    frames = torch.empty((N, n + rows, n), dtype=torch.uint8, device=d)
+    mm = torch.empty((N, 2), dtype=torch.float32, device=d)
+    idx = None
+    if want_indices:
+        idx = torch.empty((N, len(plan)), dtype=torch.float64 if pyr_mode else torch.float32, device=d)
+    if N == 0:
+        return frames, mm, idx
+    plan_t = _plan_tensor(key, plan, d)
+    frame_zero = int(bool((plan < 0).any()))
+    from ._lib import HQ_EUNSUPPORTED
+    with torch.cuda.device(d):
+        rc = lib.hq_map_index_quant(dev.ptr(emb), N, D, emb.stride(0), n, dev.ptr(plan_t), len(plan), pyr_mode, ml, frame_zero,
+                                    dev.ptr(frames), (n + rows) * n, dev.ptr(mm), dev.ptr(idx), len(plan), dev.stream_ptr())
+    if rc == HQ_EUNSUPPORTED:
+        # two launches: enhanced float32 frame (grid + index rows in the image dtype), then the frame quantiser
+        enhanced = torch.empty((N, n + rows, n), dtype=torch.float32, device=d)
+        flat = enhanced.view(N, -1)
+        if pyr_mode:
+            _, _, i64 = fused_pass(emb, 0, n, D, plan=plan, plan_key=key, min_level=ml, pyr_mode=1, grid_out=flat,
+                                   grid_stride=(n + rows) * n)
+            flat[:, n * n:] = i64.to(torch.float32)
+            if idx is not None:
+                idx.copy_(i64)
+        else:
+            fused_pass(emb, 0, n, D, plan=plan, plan_key=key, min_level=ml, grid_out=flat, grid_stride=(n + rows) * n,
+                       idx_out=flat[:, n * n:], idx_stride=(n + rows) * n)
+            if idx is not None:
+                idx.copy_(flat[:, n * n:])
+        q, mm = quantize_u8_batch(enhanced)
+        return q, mm, idx
+    check(rc)
+    return frames, mm, idx
 
 
 def dequantize_u8_batch(q: torch.Tensor, minmax: torch.Tensor) -> torch.Tensor:

@@ -120,7 +120,8 @@ class EmbeddingDatabase:
 
     Holds, per row: the float32 embedding, its L2 norm, the compact variant-C index rows
     and their stripped lengths.  Built by ONE fused map+index pass over the embeddings
-    (the 2-D grids are produced only if `keep_grids`)."""
+    (the 2-D grids are produced only if `keep_grids`).  `EmbeddingDatabase.from_chunks` builds a bf16-only shard
+    (no float32 rows) from a stream of row blocks."""
 
     MAX_EXCEPTION_ROWS = 4096
 
@@ -147,6 +148,74 @@ class EmbeddingDatabase:
             self.grids = grids if keep_grids else None
             self.norms = row_norms(self.emb)
             self.emb_bf16 = to_bf16(self.emb, self.norms) if bf16 else None
+        # database-side term of the rerank guard's error bound: max_r |bf16 unit row - c_r / |c_r||_2  (hq_rerank_topk_unit_bf16)
+        self.dc_max = 0.0
+        if self.emb_bf16 is not None and self.N > 0:
+            worst = torch.zeros(1, dtype=torch.float32, device=d)
+            with torch.cuda.device(d):
+                check(lib.hq_bf16_unit_error_max(dev.ptr(self.emb), self.N, self.D, self.emb.stride(0), dev.ptr(self.norms),
+                                                 dev.ptr(self.emb_bf16), self.emb_bf16.stride(0), dev.ptr(worst), dev.stream_ptr()))
+            self.dc_max = float(worst.item())
+        self._finish_build(bf16, tc_filter)
+
+    @classmethod
+    def from_chunks(cls, chunks, N: int, D: int, n: Optional[int] = None, device=None, id_base: int = 0,
+                    tc_filter: bool = True) -> "EmbeddingDatabase":
+        """bf16-ONLY shard built from a stream of float32 row blocks (device tensors [m, D], in row order, N rows in
+        total): every block goes through hq_shard_ingest once and is dropped; the shard keeps the bf16 unit rows, the
+        index rows and the filter operands -- 2 D + ~600 bytes per row instead of 6 D (a 100 M x 768 database over two or
+        more GPUs, BASELINE config 5).  The stored rows ARE the bf16 unit rows: scores are (cos(q, stored row) + 1) / 2,
+        exact fp32 for the stored values (include/hq_b200.h, hq_rerank_topk_unit_bf16); the filter runs on the fp32 index
+        rows of the original embeddings, exactly like the full database."""
+        d = dev.require_cuda(device)
+        self = cls.__new__(cls)
+        self.device, self.N, self.D = d, int(N), int(D)
+        self.n = int(n) if n is not None else rag_optimal_dimensions(self.D)[0]
+        self.id_base = int(id_base)
+        self.layout, self.levels = make_layout(self.n, self.D)
+        self.emb = self.grids = None
+        Lsum = int(self.layout.Lsum)
+        pitch = (self.D + 7) // 8 * 8
+        self.idx = torch.empty((self.N, Lsum), dtype=torch.float32, device=d)
+        self.emb_bf16 = torch.empty((self.N, pitch), dtype=torch.bfloat16, device=d)
+        if pitch != self.D:
+            self.emb_bf16.zero_()
+        at = 0
+        for block in chunks:
+            block = dev.f32_device(block, d)
+            m = int(block.shape[0])
+            if block.dim() != 2 or block.shape[1] != self.D or at + m > self.N:
+                raise ValueError("chunks must be [m, D] row blocks adding up to N rows")
+            fused = shard_ingest(block, self.n, want_bf16=True)
+            if fused is not None:
+                idx, _, unit = fused
+            else:
+                _, idx = map_and_index(block, self.n, variant="C", layout="compact", want_grid=False)
+                unit = to_bf16(block, row_norms(block))
+            self.idx[at:at + m] = idx
+            self.emb_bf16[at:at + m, : unit.shape[1]] = unit
+            at += m
+            del block, fused, idx, unit
+        if at != self.N:
+            raise ValueError(f"chunks held {at} rows, expected {self.N}")
+        # norms of the STORED rows (1 up to the bf16 rounding; 0 for zero rows) and the guard term that covers them
+        self.norms = torch.empty(self.N, dtype=torch.float32, device=d)
+        step = 1 << 20
+        worst = 0.0
+        for s0 in range(0, self.N, step):
+            blk = self.emb_bf16[s0:s0 + step, : self.D].to(torch.float32)
+            nb = row_norms(blk)
+            self.norms[s0:s0 + step] = nb
+            nz = nb[nb > 0]
+            if nz.numel():
+                worst = max(worst, float((nz - 1.0).abs().max().item()))
+            del blk, nb, nz
+        self.dc_max = worst * 1.01 + 1e-6
+        self._finish_build(True, tc_filter)
+        return self
+
+    def _finish_build(self, bf16: bool, tc_filter: bool):
+        d = self.device
         self.lens = row_lengths(self.idx, self.layout)
         self.zero_rows = (self.norms == 0).nonzero().flatten().to(torch.int32) if bf16 else None
         # fast filter: per-level row norms + "every stored length is the structural one" check
@@ -456,13 +525,15 @@ def packed_result_buffers(Q: int, k: int, device) -> Tuple[torch.Tensor, torch.T
 def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: bool = True,
                  work_bytes: int = 4 << 30, return_mask: bool = False, trace: Optional[FilterTrace] = None,
                  rerank: str = "auto", filter_impl: str = "auto", filter_scope: str = "shard", group=None,
-                 filter_scratch_bytes: int = 24 << 30, _dense_flag: Optional[list] = None):
+                 filter_scratch_bytes: int = 24 << 30, _dense_flag: Optional[list] = None, guard_stats: Optional[list] = None):
     """Progressive top-k of a batch of query embeddings against one shard.
 
     Returns (ids int64 [Q, k] (-1 = fewer than k survivors), scores float32 [Q, k]).  Scores are
     (cos + 1) / 2 of the full embeddings; ties resolve to the lower row id.
     `filter_scope="global"` (row-sharded databases): the ratio cut of every filter level ranks the
-    candidates of ALL shards of `group` together, like the reference's single list."""
+    candidates of ALL shards of `group` together, like the reference's single list.
+    `guard_stats`: a list that receives one int32 device tensor per tensor-core rerank launch ([0] = queries whose
+    bf16 shortlist could not be proven sufficient and were re-scored exactly over all survivors, [1] = rows re-scored)."""
     tok = _phase("query_index")
     q, q_idx, q_lens, q_norms = prepare_queries(db, queries)
     _end(tok)
@@ -477,12 +548,14 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
         # A handful of queries: the filter's ratio cuts keep at most 0.3 * 0.5 * 0.7 = 10.5 % of the rows, so scoring only
         # the survivors in fp32 (<= Q * 0.105 * N rows of 4 D bytes) reads less than the dense pass over the bf16 copy
         # (N rows of 2 D bytes) up to Q = 4.  Same scores: the tensor-core path re-scores its shortlist with this arithmetic.
-        if use_filter and Q <= SPARSE_RERANK_MAX_QUERIES:
+        if use_filter and Q <= SPARSE_RERANK_MAX_QUERIES and db.emb is not None:
             rerank = "sparse"
     if rerank not in ("bf16", "f32", "sparse"):
         raise ValueError("rerank must be 'auto', 'bf16', 'f32' or 'sparse'")
     if rerank == "bf16" and (db.emb_bf16 is None or k > 20):
         raise ValueError("the tensor-core rerank needs a bf16 database copy and k <= 20")
+    if rerank != "bf16" and db.emb is None:
+        raise ValueError("a bf16-only database (EmbeddingDatabase.from_chunks) is searched by the tensor-core rerank only (k <= 20)")
     q_bf16 = None
     if rerank == "bf16":
         tok = _phase("query_index")
@@ -545,12 +618,17 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
                 tok = _phase("rerank_gemm")
                 sb = int(lib.hq_rerank_bf16_scratch_bytes(N, nq, k))
                 scratch = torch.empty(sb, dtype=torch.uint8, device=d)
-                check(lib.hq_rerank_topk_unit_bf16(dev.ptr(db.emb_bf16), db.emb_bf16.stride(0), dev.ptr(db.emb), db.emb.stride(0),
+                guard = torch.empty(4 + nq, dtype=torch.int32, device=d)   # [0] queries sent to the exact fallback, [1] rows re-scored
+                check(lib.hq_rerank_topk_unit_bf16(dev.ptr(db.emb_bf16), db.emb_bf16.stride(0), dev.ptr(db.emb),
+                                              db.emb.stride(0) if db.emb is not None else 0,
                                               dev.ptr(db.norms), dev.ptr(db.zero_rows), int(db.zero_rows.numel()), N, db.D,
                                               dev.ptr(q_bf16[s:e]), q_bf16.stride(0),
                                               dev.ptr(q[s:e]), q.stride(0), dev.ptr(q_norms[s:e]), nq,
-                                              dev.ptr(m), mask.stride(0), k, db.id_base,
-                                              dev.ptr(ids[s:e]), dev.ptr(out_scores[s:e]), dev.ptr(scratch), sb, dev.stream_ptr()))
+                                              dev.ptr(m), mask.stride(0), k, db.id_base, float(db.dc_max),
+                                              dev.ptr(ids[s:e]), dev.ptr(out_scores[s:e]), dev.ptr(guard), dev.ptr(scratch), sb,
+                                              dev.stream_ptr()))
+                if guard_stats is not None:
+                    guard_stats.append(guard)
                 _end(tok)
                 continue
             tok = _phase("rerank_gemm")
@@ -574,7 +652,7 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
         del mask, scores, ids, out_scores
         return search_batch(db, queries, k, use_filter=use_filter, work_bytes=work_bytes, return_mask=return_mask, trace=trace,
                             rerank=rerank, filter_impl="exact", filter_scope=filter_scope, group=group,
-                            filter_scratch_bytes=filter_scratch_bytes)
+                            filter_scratch_bytes=filter_scratch_bytes, guard_stats=guard_stats)
     if return_mask:
         return ids, out_scores, (torch.cat(masks) if masks else None)
     return ids, out_scores
@@ -646,7 +724,8 @@ class SearchGraph:
         d = db.device
         self.q = torch.empty((self.Q, db.D), dtype=torch.float32, device=d)
         if db.N > 0:
-            self.q.copy_(db.emb[torch.arange(self.Q, device=d) % db.N])       # warm-up input with dense index rows
+            rows = torch.arange(self.Q, device=d) % db.N                  # warm-up input with dense index rows
+            self.q.copy_(db.emb[rows] if db.emb is not None else db.emb_bf16[rows, : db.D].to(torch.float32))
         else:
             self.q.fill_(1.0)
         side = torch.cuda.Stream(device=d)
@@ -707,7 +786,9 @@ def cosine01(a, b, device=None) -> float:
     with torch.cuda.device(d):
         check(lib.hq_rerank_scores_f32(dev.ptr(tb), dev.ptr(nb), 1, m, m, dev.ptr(ta), dev.ptr(na),
                                        1, m, None, 0, dev.ptr(out), 1, dev.stream_ptr()))
-    return float(out.item())
+    # |cos| <= 1: a score above 1.0 is rounding noise of dot / (|a| |b|) (identical vectors give 1 + 1 ulp for some inputs;
+    # the reference's tests compare such a pair with == 1.0, tests/test_similarity_calculation.py:150-158)
+    return min(1.0, float(out.item()))
 
 
 def granularity_weights(num_levels: int) -> np.ndarray:

@@ -105,6 +105,19 @@ int hq_block_means(const float* img, int64_t N, int H, int W, int64_t img_stride
                    const int32_t* rows, const int32_t* cols, int count,
                    float* out, int64_t out_stride, void* stream);
 
+/* ---- a3 + a6/a7/a8 + a9 + a10 fused: map_to_2d, hierarchical index, embed, uint8 normalise in ONE launch ----
+ * core/pipeline.py:129-146 (map_to_2d -> generate_optimized_indices -> embed_indices_in_image) followed by
+ * core/compressor.py:256-280 (_normalize_for_compression of the enhanced frame).  Per item: 4 D bytes in;
+ * n^2 + plan_len uint8 frame bytes (grid rows, then the index slots of `plan` in order: one row of S = n values for
+ * variants A / B, L rows of n for variant C), the (min, max) pair and optionally the float index values out.
+ * The frame's min / max are reduced from the grid cells (every index value is a cell or a mean of cells, and rounding
+ * is monotonic) plus 0 when `frame_zero` (padded index slots) or D < n^2 (padding cells): bit-identical to quantising
+ * the materialised frame with hq_quantize_u8.  Grids of 32 x 32 and 64 x 64, rows of D % 4 == 0 values, 16-byte aligned;
+ * other shapes return HQ_EUNSUPPORTED (run hq_map_index_fused + hq_quantize_u8).  u8_stride: bytes per frame, % 16 == 0. */
+int hq_map_index_quant(const float* src, int64_t N, int64_t D, int64_t src_stride, int n, const int32_t* plan, int plan_len,
+                       int pyr_mode, int min_level, int frame_zero, uint8_t* u8_out, int64_t u8_stride, float* minmax,
+                       void* idx_out, int64_t idx_stride, void* stream);
+
 /* ---- a10: uint8 quantise / dequantise ---------------------------------
  * core/compressor.py:256-280 (_normalize_for_compression: truncating cast,
  * constant image -> 128) and :282-303 (_denormalize_from_compression).
@@ -245,20 +258,13 @@ int hq_rerank_topk_f32(const float* db, const float* db_norm, int64_t N, int64_t
                        int64_t* ids, float* scores, void* scratch, int64_t scratch_bytes, void* stream);
 
 /* Tensor-core rerank (the one true dense GEMM of the path): bf16 tcgen05 contraction with
- * the survivor mask and a streaming top-k' (k' = 16 for k <= 10, 32 for k <= 20) fused
- * into the epilogue, then an exact fp32 re-score of the k' shortlisted rows from db_f32,
- * so the returned scores are the same fp32 (cos+1)/2 values as the exact path.
- * db_bf16 / q_bf16: row-major bf16 copies (hq_to_bf16), row pitch a multiple of 8. */
+ * the survivor mask and a streaming top-k' (k' = 16 for k <= 10, 32 for k <= 20) per epilogue thread fused
+ * into the epilogue, then an exact re-score of a shortlist and a per-query PROOF that the shortlist contains
+ * the exact top-k (see hq_rerank_topk_unit_bf16).  q_bf16: row-major bf16 copy of the queries
+ * (hq_to_bf16), row pitch a multiple of 8. */
 int hq_to_bf16(const float* src, int64_t N, int64_t D, int64_t src_stride, void* dst, int64_t dst_pitch, void* stream);
 int64_t hq_rerank_bf16_scratch_bytes(int64_t N, int Q, int k);
-int hq_rerank_topk_bf16(const void* db_bf16, int64_t db_pitch, const float* db_f32, int64_t db_stride,
-                        const float* db_norm, int64_t N, int64_t D,
-                        const void* q_bf16, int64_t q_pitch, const float* q_f32, int64_t q_stride,
-                        const float* q_norm, int Q, const uint32_t* mask, int64_t mask_stride,
-                        int k, int64_t id_base, int64_t* ids, float* scores,
-                        void* scratch, int64_t scratch_bytes, void* stream);
-/* Same search with a database operand of UNIT rows (c / |c| rounded to bf16, hq_to_bf16_unit): the epilogue then
- * needs no 1/|c| per column (half of its instructions; 768-D rows: 94 -> 5x ms per 4096 x 12.5 M batch).  Zero-norm
+/* Database operand of UNIT rows (c / |c| rounded to bf16): the epilogue needs no 1/|c| per column.  Zero-norm
  * rows score exactly 0.0 (rag/search/engine.py:640-643) and cannot be told apart in this operand: the caller passes
  * their ids (ascending) and they are appended after every other survivor, as the reference's stable sort orders them. */
 int hq_to_bf16_unit(const float* src, int64_t N, int64_t D, int64_t src_stride, const float* norms, void* dst,
@@ -273,12 +279,28 @@ int hq_to_bf16_unit(const float* src, int64_t N, int64_t D, int64_t src_stride, 
 int hq_shard_ingest_supported(int64_t D);
 int hq_shard_ingest(const float* emb, int64_t N, int64_t D, int64_t stride, const int32_t* plan_codes, int Lsum,
                     float* idx, int64_t idx_pitch, float* norms, void* unit_bf16, int64_t unit_pitch, void* stream);
+/* rag/search/engine.py:622-660 + :512 for a whole query batch.  The database operand holds UNIT rows (c / |c| rounded to
+ * bf16), so the accumulator a of a (query, row) pair orders the rows like the cosine.  Per query the rows are taken in
+ * accumulator order and re-scored exactly (fp32 FMA over db_f32, the arithmetic of hq_rerank_scores_sparse_f32) in chunks of
+ * 16 until the GUARD holds:   (k-th best exact q.c/|c| so far)  >  (largest accumulator of any row not re-scored) + E,
+ *   E = |bf16(q) - q| (1 + 2^-8) + |q| (dc_max + D 2^-22 + 1e-5)   >=   |a - q.c/|c||   for every row,
+ * which proves that the exact top-k lies among the re-scored rows.  dc_max = max over the rows of |unit_bf16 - c / |c||_2
+ * (hq_bf16_unit_error_max).  Queries still unproven after 64 rows (near-duplicate clusters around the k-th score) are listed in
+ * `guard` and re-scored exactly over ALL their surviving rows by a second pair of kernels in the same call, so the result
+ * equals the exact path's for every query.
+ *   db_f32 == NULL : bf16-only database.  The stored rows ARE the bf16 unit rows: scores are (cos(q, stored row) + 1) / 2,
+ *                    exact for the stored values (they differ from the fp32 rows' scores by the bf16 rounding of the rows,
+ *                    <= 2^-8 relative per component); db_norm = norms of the stored rows, dc_max = 0.
+ *   guard [4 + Q] int32 (device): [0] queries sent to the exact fallback, [1] rows re-scored exactly, [4..] the flagged queries. */
 int hq_rerank_topk_unit_bf16(const void* db_unit_bf16, int64_t db_pitch, const float* db_f32, int64_t db_stride,
                              const float* db_norm, const int32_t* zero_rows, int n_zero, int64_t N, int64_t D,
                              const void* q_bf16, int64_t q_pitch, const float* q_f32, int64_t q_stride,
                              const float* q_norm, int Q, const uint32_t* mask, int64_t mask_stride,
-                             int k, int64_t id_base, int64_t* ids, float* scores,
+                             int k, int64_t id_base, float dc_max, int64_t* ids, float* scores, int32_t* guard,
                              void* scratch, int64_t scratch_bytes, void* stream);
+/* out_max (device float, initialised by the caller, e.g. 0) = max(out_max, max_r |unit_bf16[r] - src[r] / norms[r]|_2) */
+int hq_bf16_unit_error_max(const float* src, int64_t N, int64_t D, int64_t src_stride, const float* norms,
+                           const void* unit_bf16, int64_t pitch, float* out_max, void* stream);
 
 /* ---- a14: comprehensive similarity blend -----------------------------------
  * rag/search/engine.py:516-575 (_calculate_comprehensive_similarity):

@@ -272,6 +272,65 @@ def test_quantize_batch_and_large(hq):
         assert np.array_equal(q[i].cpu().numpy(), want) and float(mm[i, 0]) == mn and float(mm[i, 1]) == mx
 
 
+def test_fused_map_index_quantize_matches_the_reference_pipeline(hq):
+    """North star (2): map_to_2d + index + embed + uint8 normalise in ONE kernel.  The golden `u8_*` frames are the
+    REFERENCE's _normalize_for_compression(embed_indices_in_image(map_to_2d(p), B-indices)) (core/pipeline.py:129-146,
+    core/compressor.py:256-280): bit-exact, including the (min, max) pair.  32 x 32 and 64 x 64 run the fused kernel, the
+    other sizes the two-launch path."""
+    g = load_golden("index.npz")
+    for key in [k[3:] for k in g.files if k.startswith("in_n")]:
+        n = int(key[1:].split("_")[0])
+        p = g[f"in_{key}"]
+        frames, mm, idx = hq.map_index_quantize(dev_t(p[None, :]), n, variant="B", want_indices=True)
+        want = g[f"u8_{key}"]
+        assert frames.dtype == torch.uint8 and tuple(frames.shape) == (1, n + 1, n), key
+        assert np.array_equal(frames[0].cpu().numpy(), want), (key, int((frames[0].cpu().numpy() != want).sum()))
+        enh = g[f"enhB_{key}"]
+        assert float(mm[0, 0]) == float(enh.min()) and float(mm[0, 1]) == float(enh.max()), key
+        assert np.array_equal(idx[0].cpu().numpy(), g[f"B_{key}"]), key
+
+
+@pytest.mark.parametrize("n,D,variant", [(64, 1536, "C"), (64, 4096, "B"), (64, 1536, "A"), (32, 768, "C"), (32, 1024, "A"),
+                                         (32, 768, "B"), (64, 1000, "B"), (32, 12, "C")])
+def test_fused_map_index_quantize_batches(hq, n, D, variant):
+    """Batches (partial last chunk, constant rows, all-positive rows whose padding pulls the minimum to 0) against the oracle:
+    frame = grid + index rows in float32, then O.normalize_u8; and against the two-launch device path."""
+    rng = np.random.default_rng(n * D)
+    N = 1037
+    x = (rng.standard_normal((N, D)) * 2).astype(np.float32)
+    x[3] = 1.5                                            # constant vector (a constant FRAME only when D == n * n and the index is constant)
+    x[4] = np.abs(x[4]) + 0.25                            # all positive: min comes from the zero padding, if any
+    x[5] = -np.abs(x[5]) - 0.25                           # all negative: max comes from the zero padding, if any
+    x[6] = 0.0
+    frames, mm, idx = hq.map_index_quantize(dev_t(x), n, variant=variant, want_indices=True)
+    fr, mmn = frames.cpu().numpy(), mm.cpu().numpy()
+    for i in (0, 3, 4, 5, 6, 511, 1024, N - 1):
+        img = O.map_to_2d(x[i], (n, n))
+        if variant == "C":
+            enh = O.index_c(img)
+        else:
+            row = O.index_a(img, n) if variant == "A" else O.index_b(img, n)
+            enh = O.embed_index_row(img, row)
+        if variant == "B":
+            want, mn, mx = O.normalize_u8(enh.astype(np.float32))
+            assert np.array_equal(fr[i], want), (i, int((fr[i] != want).sum()))
+            assert mmn[i, 0] == mn and mmn[i, 1] == mx, i
+        else:       # fp32 block means: tree vs pairwise order (<= 3e-7 on the index values): a byte may differ where a value sits on a bin edge
+            want, mn, mx = O.normalize_u8(enh.astype(np.float32))
+            assert np.array_equal(fr[i, :n], want[:n]), i                       # the grid part is exact
+            assert mmn[i, 0] == mn and mmn[i, 1] == mx, i
+            assert np.abs(fr[i, n:].astype(int) - want[n:].astype(int)).max() <= 1, i
+    # the same frames from the two-launch device path (fused map + index, then hq_quantize_u8): bit-identical
+    if variant == "C":
+        enh_dev, _ = hq.map_and_index(dev_t(x), n, variant="C", enhanced=True)
+    else:
+        grid, ix = hq.map_and_index(dev_t(x), n, variant=variant, index_space=n)
+        enh_dev = torch.cat([grid, ix.to(torch.float32).unsqueeze(1)], dim=1)
+        assert torch.equal(ix, idx)
+    q2, mm2 = hq.quantize_u8_batch(enh_dev)
+    assert torch.equal(q2, frames) and torch.equal(mm2, mm)
+
+
 # ------------------------------------------------------------------ a12/a13/a15 search
 def _oracle_rows(db, n):
     levels = O.c_granularity_levels(n)

@@ -179,3 +179,132 @@ def test_search_stream_pipelines_host_batches(hq, depth):
     assert torch.equal(got2[-1][0], got[1][0] + 5)
     with pytest.raises(ValueError):
         list(hq.search_stream(d, [batches[0], batches[1][:5]], 10, depth=depth))
+
+
+# ------------------------------------------------------------------------------------------------
+# shortlist-sufficiency guard (hq_rerank_topk_unit_bf16): the bf16 accumulator only PROPOSES rows; the
+# returned top-k is proven per query, and queries that cannot be proven are re-scored exactly
+# ------------------------------------------------------------------------------------------------
+def _check_topk_modulo_near_ties(ids, sc, qs, db, alive, k, tol=5e-7):
+    """ids / scores are a correct top-k of the eligible rows: the score list equals the fp64 oracle's sorted top-k scores within
+    `tol`, every returned row is eligible and its own fp64 score is the returned one (rows whose scores differ by less than the
+    fp32 resolution may legitimately swap places)."""
+    for j in range(len(qs)):
+        rows = np.nonzero(alive[j])[0]
+        s64 = O.cosine01(qs[j], db[rows])
+        want = np.sort(s64)[::-1][:k]
+        m = len(want)
+        assert (ids[j, :m] >= 0).all() and (ids[j, m:] == -1).all(), j
+        if m == 0:
+            continue
+        assert np.abs(sc[j, :m] - want).max() <= tol, (j, np.abs(sc[j, :m] - want).max())
+        pos = {int(r): i for i, r in enumerate(rows)}
+        own = np.array([s64[pos[int(i)]] for i in ids[j, :m]])           # KeyError = a row that is not eligible
+        assert np.abs(own - sc[j, :m]).max() <= tol, j
+        assert len(set(ids[j, :m].tolist())) == m
+
+
+def _stats(guard_list):
+    g = torch.stack([t[:2] for t in guard_list]).sum(0).tolist()
+    return int(g[0]), int(g[1])
+
+
+def test_guard_passes_on_random_data_and_counts_rescored_rows(hq):
+    rng = np.random.default_rng(11)
+    N, D, Q, k = 60000, 1536, 64, 10
+    db = rng.standard_normal((N, D)).astype(np.float32)
+    qs = rng.standard_normal((Q, D)).astype(np.float32)
+    d = hq.EmbeddingDatabase(db)
+    assert 0.0 < d.dc_max < 2.0 ** -8                       # |bf16(c/|c|) - c/|c|| <= 2^-8 |c/|c||
+    stats = []
+    itc, stc = hq.search_batch(d, qs, k, use_filter=False, rerank="bf16", guard_stats=stats)
+    i32, s32 = hq.search_batch(d, qs, k, use_filter=False, rerank="f32")
+    assert torch.equal(itc, i32) and (stc - s32).abs().max().item() <= 1e-6
+    flagged, rescored = _stats(stats)
+    assert flagged == 0, flagged                            # no query needed the exact fallback
+    assert Q * 16 <= rescored <= Q * 64, rescored           # 16 .. 64 rows per query were re-scored exactly
+
+
+@pytest.mark.parametrize("use_filter", [False, True])
+def test_guard_catches_near_duplicate_clusters(hq, use_filter):
+    """ADVERSARIAL: 50 000 rows within ~1e-4 cosine of each other.  Hundreds of rows lie inside the bf16 error band of the
+    10th score, so a fixed shortlist of 16 drops true top-10 rows; the guard must flag those queries and the exact fallback
+    must return the exact path's ids and scores (rag/search/engine.py:622-660, :512)."""
+    rng = np.random.default_rng(5)
+    N, D, Q, k = 50000, 768, 24, 10
+    base = rng.standard_normal(D).astype(np.float32)
+    base /= np.linalg.norm(base)
+    db = base[None, :] + (1.0e-2 / np.sqrt(D)) * rng.standard_normal((N, D)).astype(np.float32)   # cos(row, row') ~ 1 - 1e-4
+    db[100:110] = 0.5 * base[None, :] + 0.5 * rng.standard_normal((10, D)).astype(np.float32) / np.sqrt(D)   # a few ordinary rows
+    qs = base[None, :] + (1.0e-2 / np.sqrt(D)) * rng.standard_normal((Q, D)).astype(np.float32)
+    qs[Q // 2:] = rng.standard_normal((Q - Q // 2, D)).astype(np.float32)       # half the queries see the cluster from far away
+    d = hq.EmbeddingDatabase(db)
+    stats = []
+    itc, stc, mask = hq.search_batch(d, qs, k, use_filter=use_filter, rerank="bf16", guard_stats=stats, return_mask=True)
+    from hilbert_quantization_b200.search import unpack_mask
+    alive = unpack_mask(mask, N) if use_filter else np.ones((Q, N), dtype=bool)
+    _check_topk_modulo_near_ties(itc.cpu().numpy(), stc.cpu().numpy(), qs, db, alive, k)
+    if use_filter:          # the sparse fp32 rerank scores every survivor with the arithmetic of the re-score: identical results
+        isp, ssp = hq.search_batch(d, qs, k, rerank="sparse")
+        assert torch.equal(itc, isp), (itc != isp).sum().item()
+        assert torch.equal(stc, ssp)
+    flagged, _ = _stats(stats)
+    assert flagged >= 1, "the adversarial cluster should defeat the 64-row shortlist for at least one query"
+    # and the unguarded shortlist really would have been wrong: the exact top-10 is not inside the bf16 top-16
+    q16 = torch.from_numpy(qs[:1]).cuda().bfloat16().float()
+    acc = (q16 @ d.emb_bf16[:, :D].float().T)[0]
+    top16 = set(acc.topk(16).indices.tolist())
+    exact_top = set(np.argsort(-O.cosine01(qs[0], db), kind="stable")[:k].tolist())
+    assert not exact_top <= top16
+
+
+def test_guard_zero_query_and_all_ties(hq):
+    rng = np.random.default_rng(2)
+    N, D = 3000, 256
+    db = rng.standard_normal((N, D)).astype(np.float32)
+    db[50:2050] = db[50]                                    # 2000 identical rows: every one of them ties
+    qs = np.stack([np.zeros(D, np.float32), db[50], rng.standard_normal(D).astype(np.float32)])
+    d = hq.EmbeddingDatabase(db)
+    itc, stc = hq.search_batch(d, qs, 10, use_filter=False, rerank="bf16")
+    i32, s32 = hq.search_batch(d, qs, 10, use_filter=False, rerank="f32")
+    assert torch.equal(itc, i32) and (stc - s32).abs().max().item() <= 1e-6
+    assert itc[0].tolist() == list(range(10))               # zero query: every score is 0.0, lowest ids win
+    assert itc[1].tolist() == list(range(50, 60))
+
+
+@pytest.mark.parametrize("N,D,Q,k", [(30000, 768, 40, 10), (9000, 1536, 130, 20), (2000, 250, 3, 5)])
+def test_bf16_only_database_scores_the_stored_rows_exactly(hq, N, D, Q, k):
+    """EmbeddingDatabase.from_chunks keeps no fp32 rows: the stored rows are the bf16 unit rows, the returned scores are the
+    exact (cos + 1) / 2 of the query with the STORED row (<= 5e-7), ids equal the oracle's top-k over the stored rows, and
+    the scores stay within the stated bf16 tolerance (2e-3) of the fp32 database's."""
+    rng = np.random.default_rng(N + D)
+    db = rng.standard_normal((N, D)).astype(np.float32)
+    db[5] = 0.0
+    db[N // 3] = db[9]
+    qs = rng.standard_normal((Q, D)).astype(np.float32)
+    qs[0] = db[9]
+    chunks = [torch.from_numpy(db[s:s + 7000]).cuda() for s in range(0, N, 7000)]
+    lean = hq.EmbeddingDatabase.from_chunks(iter(chunks), N, D)
+    full = hq.EmbeddingDatabase(db)
+    assert lean.emb is None and torch.equal(lean.idx, full.idx)
+    if D % 8 == 0:
+        assert torch.equal(lean.emb_bf16, full.emb_bf16)
+    stored = lean.emb_bf16[:, :D].float().cpu().numpy()
+    for use_filter in (False, True):
+        ids, sc = hq.search_batch(lean, qs, k, use_filter=use_filter)
+        idf, scf = hq.search_batch(full, qs, k, use_filter=use_filter, return_mask=False)
+        ids, sc = ids.cpu().numpy(), sc.cpu().numpy()
+        if use_filter:
+            _, _, mask = hq.search_batch(lean, qs, k, return_mask=True)
+            from hilbert_quantization_b200.search import unpack_mask
+            alive = unpack_mask(mask, N)
+        for j in range(min(Q, 12)):
+            rows = np.nonzero(alive[j])[0] if use_filter else np.arange(N)
+            iw, sw = O.topk_stable(rows, O.cosine01(qs[j], stored[rows]), k)
+            m = len(iw)
+            assert list(ids[j, :m]) == list(iw), (use_filter, j)
+            assert np.abs(sc[j, :m] - sw).max() < 5e-7
+        valid = (ids >= 0) & (idf.cpu().numpy() == ids)
+        assert np.abs(sc[valid] - scf.cpu().numpy()[valid]).max() < 2e-3
+    with pytest.raises(ValueError, match="bf16-only"):
+        hq.search_batch(lean, qs, k, rerank="f32")
