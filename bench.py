@@ -555,10 +555,22 @@ def main():
         return acc
     e2e_run(args.warmup)
     barrier()
+    import gc
+    gc_ms = [0.0, 0]
+    gc_t = [0.0]
+
+    def gc_probe(phase, info):                        # diagnostic: Python garbage collections inside the timed region
+        if phase == "start":
+            gc_t[0] = time.perf_counter()
+        else:
+            gc_ms[0] += (time.perf_counter() - gc_t[0]) * 1e3
+            gc_ms[1] += 1
+    gc.callbacks.append(gc_probe)
     t0 = time.perf_counter()                          # host wall clock: the e2e figure includes everything the caller waits for
     e2e_run(args.steps)                               # (returns after the last batch's results are on the host)
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
+    gc.callbacks.remove(gc_probe)
     gaps = np.diff([t0] + e2e_stamps) * 1e3              # host time between consecutive result batches
     barrier()
     te = torch.tensor([e2e_ms], device=device)
@@ -649,7 +661,9 @@ def main():
                     "d2h_bytes_per_step": int(out_ids.numel() * 8 + out_sc.numel() * 4),
                     "clock": "time.perf_counter around the loop (barrier + synchronize on both sides), max over ranks",
                     "result_gaps_ms": {"first": float(gaps[0]), "median": float(np.median(gaps[1:])) if len(gaps) > 1 else None,
-                                       "max": float(gaps[1:].max()) if len(gaps) > 1 else None}},
+                                       "max": float(gaps[1:].max()) if len(gaps) > 1 else None,
+                                       "argmax": int(1 + np.argmax(gaps[1:])) if len(gaps) > 1 else None,
+                                       "gc_ms": gc_ms[0], "gc_collections": gc_ms[1]}},
             "gpu_launches": launches,
             "per_rank_ms_per_step": per_rank_ms,
             "phases_ms_per_step": {k: v / args.steps for k, v in phases.items()},

@@ -306,9 +306,26 @@ constexpr int kMaxStages = 8;
 // cell or a mean of cells, and rounding is monotonic, so fl(mean) stays inside [min, max] of its cells.  The data warps
 // reduce min / max from the quads they hold anyway, quantise the dense tile image (16 cells per thread, one 128-bit store)
 // and the index warp quantises the index rows it gathers: 4 D bytes in, n^2 + plan_len + 8 bytes out per item, no second pass.
-__device__ __forceinline__ uint32_t quant_u8(float v, float mn, float range, bool constant) {
+// The reference evaluates ((v - min) / (max - min) * 255).astype(uint8) as three float32 operations and a truncation
+// (core/compressor.py:274).  An IEEE division per cell (~10 instructions) made the fused pass issue bound at twice the
+// instruction count of the index pass, so the correctly rounded quotient comes from the item's correctly rounded reciprocal
+// y = RN(1 / range), computed once, and one Newton correction with an exact FMA residual (Markstein: q0 = RN(d y) is faithful,
+// rem = d - range q0 is exact, RN(q0 + rem y) = RN(d / range) when nothing under- or overflows).  `y == 0` selects the plain
+// division (ranges below 1e-30 or above 1e30, where y or the residual could leave the normal range).
+__device__ __forceinline__ float quant_recip(float range) {
+    return (range > 1.0e-30f && range < 1.0e30f) ? __frcp_rn(range) : 0.f;
+}
+__device__ __forceinline__ uint32_t quant_u8(float v, float mn, float range, float y, bool constant) {
     if (constant) return 128u;
-    return (uint32_t)(uint8_t)(int)__fmul_rn(__fdiv_rn(__fsub_rn(v, mn), range), 255.0f);   // truncation, like astype(uint8)
+    const float d = __fsub_rn(v, mn);
+    float a;
+    if (y != 0.f) {
+        const float q0 = __fmul_rn(d, y);
+        a = __fmaf_rn(__fmaf_rn(-range, q0, d), y, q0);
+    } else {
+        a = __fdiv_rn(d, range);
+    }
+    return (uint32_t)(uint8_t)(int)__fmul_rn(a, 255.0f);                                     // truncation, like astype(uint8)
 }
 
 template <int MODE, int LOG2T, bool QUANT>
@@ -485,13 +502,13 @@ __global__ void __launch_bounds__(kBlock, 3) k_item_pass_bulk(const TileParams p
                     for (int w = 0; w < kThreads / 32; ++w) { mn = fminf(mn, s_mm[iter & 1u][il][w][0]); mx = fmaxf(mx, s_mm[iter & 1u][il][w][1]); }
                     if (p.frame_zero) { mn = fminf(mn, 0.f); mx = fmaxf(mx, 0.f); }
                     const bool constant = mn == mx;
-                    const float range = __fsub_rn(mx, mn);
+                    const float range = __fsub_rn(mx, mn), y = quant_recip(range);
                     uint32_t w4[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const float4 c = *reinterpret_cast<const float4*>(img + c0 + 4 * j);
-                        w4[j] = quant_u8(c.x, mn, range, constant) | (quant_u8(c.y, mn, range, constant) << 8) |
-                                (quant_u8(c.z, mn, range, constant) << 16) | (quant_u8(c.w, mn, range, constant) << 24);
+                        w4[j] = quant_u8(c.x, mn, range, y, constant) | (quant_u8(c.y, mn, range, y, constant) << 8) |
+                                (quant_u8(c.z, mn, range, y, constant) << 16) | (quant_u8(c.w, mn, range, y, constant) << 24);
                     }
                     uint8_t* frame = p.u8_out + (item0 + il) * p.u8_stride;
                     __stcs(reinterpret_cast<uint4*>(frame + cell), make_uint4(w4[0], w4[1], w4[2], w4[3]));
@@ -537,7 +554,7 @@ __global__ void __launch_bounds__(kBlock, 3) k_item_pass_bulk(const TileParams p
 #pragma unroll
                     for (int j = 1; j < IPC; ++j)
                         if ((int)il == j) { mn = q_mn[j]; rg = q_rg[j]; cst = q_const[j]; }
-                    p.u8_out[(item0 + il) * p.u8_stride + G::cells + i] = (uint8_t)quant_u8((float)val, mn, rg, cst);
+                    p.u8_out[(item0 + il) * p.u8_stride + G::cells + i] = (uint8_t)quant_u8((float)val, mn, rg, quant_recip(rg), cst);
                 }
             }
             __syncwarp();

@@ -45,7 +45,7 @@ def fused_pass(src: torch.Tensor, direction: int, n: int, D: int, *, plan: Optio
     src = src.contiguous()
     N = src.shape[0]
     cells = n * n
-    src_stride = src.stride(0) if N > 0 else (D if direction == 0 else cells)
+    src_stride = src.stride(0) if N > 1 else (D if direction == 0 else cells)      # (a size-1 axis may report any stride)
     grid = stream = idx = None
     if direction == 0 and (want_grid or grid_out is not None):
         grid = grid_out if grid_out is not None else torch.empty((N, n, n), dtype=torch.float32, device=d)

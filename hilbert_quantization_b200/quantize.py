@@ -70,7 +70,8 @@ def map_index_quantize(embeddings: torch.Tensor, n: Optional[int] = None, *, var
     frame_zero = int(bool((plan < 0).any()))
     from ._lib import HQ_EUNSUPPORTED
     with torch.cuda.device(d):
-        rc = lib.hq_map_index_quant(dev.ptr(emb), N, D, emb.stride(0), n, dev.ptr(plan_t), len(plan), pyr_mode, ml, frame_zero,
+        src_stride = emb.stride(0) if N > 1 else D        # (a size-1 axis may report any stride)
+        rc = lib.hq_map_index_quant(dev.ptr(emb), N, D, src_stride, n, dev.ptr(plan_t), len(plan), pyr_mode, ml, frame_zero,
                                     dev.ptr(frames), (n + rows) * n, dev.ptr(mm), dev.ptr(idx), len(plan), dev.stream_ptr())
     if rc == HQ_EUNSUPPORTED:
         # two launches: enhanced float32 frame (grid + index rows in the image dtype), then the frame quantiser

@@ -418,14 +418,19 @@ def progressive_filter_global(db: EmbeddingDatabase, q_idx: torch.Tensor, q_lens
         for level in range(db.num_levels):
             n_alive = torch.zeros(Qc, dtype=torch.int32, device=d)
             n_pass = torch.zeros(Qc, dtype=torch.int32, device=d)
-            check(lib.hq_filter_level(dev.ptr(db.idx), dev.ptr(db.lens), N, C.byref(db.layout), level,
-                                      dev.ptr(q_idx), dev.ptr(q_lens), Qc,
-                                      dev.ptr(mask) if level > 0 else None, mask.stride(0),
-                                      rag_threshold(level), dev.ptr(scores), scores.stride(0), dev.ptr(mask),
-                                      dev.ptr(n_alive), dev.ptr(n_pass), st))
-            passed = _unpack_bits(mask[:Qc, :words], N)
-            keep, n_out = global_ratio_cut(scores[:Qc, :N], passed, n_alive, rag_ratio(level), db.id_base, group)
-            mask[:Qc, :words] = _pack_bits(keep, words)
+            if N == 0:                              # an empty shard contributes nothing but takes part in every collective
+                none = torch.zeros((Qc, 0), dtype=torch.bool, device=d)
+                _, n_out = global_ratio_cut(torch.zeros((Qc, 0), dtype=torch.float32, device=d), none, n_alive, rag_ratio(level),
+                                            db.id_base, group)
+            else:
+                check(lib.hq_filter_level(dev.ptr(db.idx), dev.ptr(db.lens), N, C.byref(db.layout), level,
+                                          dev.ptr(q_idx), dev.ptr(q_lens), Qc,
+                                          dev.ptr(mask) if level > 0 else None, mask.stride(0),
+                                          rag_threshold(level), dev.ptr(scores), scores.stride(0), dev.ptr(mask),
+                                          dev.ptr(n_alive), dev.ptr(n_pass), st))
+                passed = _unpack_bits(mask[:Qc, :words], N)
+                keep, n_out = global_ratio_cut(scores[:Qc, :N], passed, n_alive, rag_ratio(level), db.id_base, group)
+                mask[:Qc, :words] = _pack_bits(keep, words)
             if trace is not None:
                 trace.n_alive.append(n_alive)
                 trace.n_pass.append(n_pass)
@@ -539,7 +544,10 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
     _end(tok)
     Q, N, d = q.shape[0], db.N, db.device
     ids, out_scores = packed_result_buffers(Q, k, d)
-    if N == 0 or Q == 0:
+    if filter_scope not in ("shard", "global"):
+        raise ValueError("filter_scope must be 'shard' or 'global'")
+    collective = filter_scope == "global" and use_filter          # every rank must take part in the per-level collectives,
+    if Q == 0 or (N == 0 and not collective):                     # an empty shard included
         ids.fill_(-1)
         out_scores.fill_(-1.0)
         return (ids, out_scores, None) if return_mask else (ids, out_scores)
@@ -564,10 +572,17 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
     words = _mask_words(N)
     if filter_impl not in ("auto", "fast", "fast_fp32", "exact"):
         raise ValueError("filter_impl must be 'auto', 'fast', 'fast_fp32' or 'exact'")
-    if filter_scope not in ("shard", "global"):
-        raise ValueError("filter_scope must be 'shard' or 'global'")
+    n_chunk_rows = N
     if filter_scope == "global":
         filter_impl = "exact"                      # the global cut works on the per-level score matrix
+        if collective:
+            # the number of query chunks (= collectives per level) must be the same on every rank: size the chunks by the
+            # LARGEST shard (shard_bounds gives base or base + 1 rows, and a shard may be empty)
+            import torch.distributed as dist
+            if dist.is_initialized() and dist.get_world_size(group) > 1:
+                nmax = torch.tensor([N], dtype=torch.int64, device=d)
+                dist.all_reduce(nmax, op=dist.ReduceOp.MAX, group=group)
+                n_chunk_rows = int(nmax.item())
     fast = False
     dense_queries = None
     if use_filter and filter_impl != "exact":
@@ -587,7 +602,7 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
                 dense_queries = _DenseCheck(q_lens, db)
     if fast or not use_filter:
         work_bytes = max(work_bytes, 4 * N * Q) if rerank == "bf16" else work_bytes
-    qc = int(max(1, min(Q, work_bytes // (4 * N)))) if not (rerank == "bf16" and (fast or not use_filter)) else Q
+    qc = int(max(1, min(Q, work_bytes // (4 * max(1, n_chunk_rows))))) if not (rerank == "bf16" and (fast or not use_filter)) else Q
     if fast and use_filter:
         # the fast filter keeps bit planes and candidate lists for the whole query chunk in scratch: bound it
         # (C5: 12.5 M rows x 4096 queries would ask for > 100 GB) by searching the batch in 128-query multiples
@@ -603,6 +618,11 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
             e = min(Q, s + qc)
             nq = e - s
             m = None
+            if N == 0:                              # empty shard in a global-scope search: collectives only, no results
+                progressive_filter_global(db, q_idx[s:e], q_lens[s:e], scores[:nq], mask[:nq], group, trace)
+                ids[s:e].fill_(-1)
+                out_scores[s:e].fill_(-1.0)
+                continue
             if use_filter:
                 tok = _phase("filter")
                 if fast:

@@ -195,6 +195,8 @@ thr, ratio = 0.35, 0.3
 passed = alive & (scores >= thr)
 passed[7] = False; passed[7, 5] = True                                                           # fewer passes than the cap
 lo, hi = shard_bounds(N, 2, rank)
+if len(sys.argv) > 4 and sys.argv[4] == "empty":                       # rank 1 owns no rows: it must still take part in every collective
+    lo, hi = (0, N) if rank == 0 else (N, N)
 keep, n_out = global_ratio_cut(torch.from_numpy(scores[:, lo:hi].copy()), torch.from_numpy(passed[:, lo:hi].copy()),
                                torch.from_numpy(alive[:, lo:hi].sum(1)), ratio, lo)
 for q in range(Q):
@@ -207,6 +209,16 @@ for q in range(Q):
 dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
+
+
+def test_two_rank_global_ratio_cut_with_an_empty_shard_over_gloo(tmp_path):
+    script = tmp_path / "worker_cut_empty.py"
+    script.write_text(_WORKER_GLOBAL_CUT)
+    port = str(33500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r), "empty"], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)
 
 
 def test_two_rank_global_ratio_cut_over_gloo(tmp_path):

@@ -331,6 +331,22 @@ def test_fused_map_index_quantize_batches(hq, n, D, variant):
     assert torch.equal(q2, frames) and torch.equal(mm2, mm)
 
 
+def test_fused_quantize_reciprocal_division_is_exact_over_many_scales(hq):
+    """The fused kernel replaces the per-cell IEEE division by the item's reciprocal + one exact-residual correction
+    (hq_item_pass.cuh, quant_u8).  80 M cells at scales from 1e-25 to 1e25 (and beyond, where it falls back to the division):
+    every byte must equal hq_quantize_u8's, which divides."""
+    g = torch.Generator(device="cuda").manual_seed(99)
+    N, D, n = 20000, 4096, 64
+    x = torch.randn((N, D), generator=g, device="cuda")
+    scale = torch.pow(10.0, torch.rand((N, 1), generator=g, device="cuda") * 70.0 - 35.0)
+    x = (x * scale + torch.randn((N, 1), generator=g, device="cuda") * scale * 3).contiguous()
+    frames, mm, _ = hq.map_index_quantize(x, n, variant="C")
+    enh, _ = hq.map_and_index(x, n, variant="C", enhanced=True)
+    q2, mm2 = hq.quantize_u8_batch(enh)
+    assert torch.equal(mm, mm2)
+    assert torch.equal(frames, q2), int((frames != q2).sum())
+
+
 # ------------------------------------------------------------------ a12/a13/a15 search
 def _oracle_rows(db, n):
     levels = O.c_granularity_levels(n)
