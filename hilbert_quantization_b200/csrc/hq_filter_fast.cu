@@ -706,7 +706,7 @@ __global__ void __launch_bounds__(kListThreads, 1) k_filter_cascade_lists(const 
     __shared__ float b_key[kCutCap];
     __shared__ uint32_t b_row[kCutCap];
     __shared__ float b_k2[kCutCap];
-    __shared__ uint32_t s_bufn, s_flag, s_R, s_n2;
+    __shared__ uint32_t s_bufn, s_flag, s_R, s_n2, s_nd, s_d2;
     __shared__ float s_K;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
     // level-2 candidates of the query this CTA works on, compacted by the level-1 pass
@@ -726,15 +726,35 @@ __global__ void __launch_bounds__(kListThreads, 1) k_filter_cascade_lists(const 
         }
         const uint32_t n1 = block_sum(part, s_warp);
         // ---- level 0: survivors of the threshold; its ratio cut must not bind ----
+        // (the same pass counts the rows that pass EVERY level's threshold: when no ratio cut binds, or cut 1 drops only a
+        // few rows, the survivor mask is the AND of the planes and the lists are not streamed at all -- see "lazy path")
         const uint32_t* P0 = p.bits + (int64_t)q * p.bits_pitch;
-        uint32_t c = 0;
-        for (int64_t w = tid; w < p.words; w += nt) {
-            uint32_t v = __ldg(P0 + w);
-            const int64_t r0 = w * 32;
-            if (r0 + 32 > p.N) v &= (1u << (uint32_t)(p.N - r0)) - 1u;
-            c += __popc(v);
+        const uint32_t* P1 = p.L > 1 ? p.bits + ((int64_t)1 * p.Q + q) * p.bits_pitch : nullptr;
+        const uint32_t* P2 = p.L > 2 ? p.bits + ((int64_t)2 * p.Q + q) * p.bits_pitch : nullptr;
+        const int64_t groups = (p.words + 3) >> 2;                    // plane rows are 32-byte aligned and padded to 8 words
+        auto and_group = [&](int64_t g, uint32_t (&v0)[4], uint32_t (&va)[4]) {
+            const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(P0) + g);
+            uint4 a1 = make_uint4(~0u, ~0u, ~0u, ~0u), a2 = a1;
+            if (P1) a1 = __ldg(reinterpret_cast<const uint4*>(P1) + g);
+            if (P2) a2 = __ldg(reinterpret_cast<const uint4*>(P2) + g);
+            const uint32_t x0[4] = {a0.x, a0.y, a0.z, a0.w}, x1[4] = {a1.x, a1.y, a1.z, a1.w}, x2[4] = {a2.x, a2.y, a2.z, a2.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int64_t r0 = (g * 4 + i) * 32;
+                const uint32_t tm = r0 + 32 <= p.N ? 0xffffffffu : (r0 < p.N ? ((1u << (uint32_t)(p.N - r0)) - 1u) : 0u);
+                v0[i] = x0[i] & tm;
+                va[i] = v0[i] & x1[i] & x2[i];
+            }
+        };
+        uint32_t c = 0, ca = 0;
+        for (int64_t g = tid; g < groups; g += nt) {
+            uint32_t v0[4], va[4];
+            and_group(g, v0, va);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { c += __popc(v0[i]); ca += __popc(va[i]); }
         }
         const uint32_t c0 = block_sum(c, s_warp);
+        const uint32_t c_all = block_sum(ca, s_warp);                 // rows passing the thresholds of all levels
         int64_t cap0 = (int64_t)((double)p.N * p.ratio[0]);
         if (cap0 < 1) cap0 = 1;
         if (s_flag || (int64_t)c0 > cap0 || p.L < 2) {
@@ -827,6 +847,94 @@ __global__ void __launch_bounds__(kListThreads, 1) k_filter_cascade_lists(const 
             }
             return kept_by(b1, k, row) ? 2 : 0;
         };
+        // ---- lazy path ----
+        // Without a binding ratio cut the survivors are exactly the rows that pass every threshold: M = P0 & P1 & P2, no list
+        // is read (random-like data: level 2 never binds, level 1 binds for about half of the queries).  When cut 1 binds
+        // but drops only a small part of the list, the dropped entries (below the cut bin, or the low ranks inside it) are
+        // found by ONE more pass over k1 alone; their rows are cleared from the AND of the planes, and level 2 cannot bind
+        // as long as (rows passing all thresholds) - (dropped rows that pass level 2) <= cap2.  Everything else (a deep cut
+        // 1, a binding cut 2) takes the streaming path below.  It replaces, for these queries, a pass over all three list
+        // arrays, the compaction of the level-2 candidates and one atomicOr per survivor (~45 K per query at 1 M rows).
+        {
+            const uint32_t drop1 = cut1 ? n1 - (uint32_t)cap1 : 0u;
+            const float lo2l = p.L > 2 ? __ldg(p.tq + (int64_t)2 * p.Q + q) : 0.f;
+            bool lazy = !cut1 || drop1 <= n1 / 8u;
+            if (lazy && cut1) {
+                if (tid == 0) { s_nd = 0; s_d2 = 0; }
+                __syncthreads();
+                auto dropped = [&](uint32_t row, float k2) {
+                    c_row[atomicAdd(&s_nd, 1u)] = row;
+                    if (p.L > 2 && k2 >= lo2l) atomicAdd(&s_d2, 1u);
+                };
+                each_l1([&](float k, uint32_t tok) {
+                    int cls;
+                    if (cb1.on) {
+                        const uint32_t b = lin_bin(k, cb1.lo, cb1.scale);
+                        cls = b > cb1.cb ? 2 : (b == cb1.cb ? 1 : 0);
+                    } else {
+                        cls = k > b1.K ? 2 : (k < b1.K ? 0 : 3);          // 3: ties with the boundary key, decided by the row id
+                    }
+                    if (cls == 2) return;
+                    const uint32_t row = __ldg(L_rows + tok) & 0x7fffffffu;
+                    const float k2 = L_k2 ? __ldg(L_k2 + tok) : 0.f;
+                    if (cls == 3) cls = row < b1.R ? 2 : 0;
+                    if (cls == 2) return;
+                    if (cls == 1) {
+                        const uint32_t slot = atomicAdd(&s_bufn, 1u);
+                        b_key[slot] = k; b_row[slot] = row; b_k2[slot] = k2;
+                    } else {
+                        dropped(row, k2);
+                    }
+                });
+                __syncthreads();
+                if (cb1.on) {
+                    const uint32_t nb = s_bufn;
+                    rank_cut_bin(b_key, b_row, nb, cb1.r_in_bin, &s_K, &s_R);
+                    const Boundary bb{s_K, s_R};
+                    for (uint32_t e = tid; e < nb; e += nt)
+                        if (!kept_by(bb, b_key[e], b_row[e])) dropped(b_row[e], b_k2[e]);
+                    __syncthreads();
+                }
+                lazy = s_nd == drop1;                                      // (always; a mismatch would mean an inconsistent list)
+            }
+            int64_t n2l = 0, cap2l = 0;
+            if (lazy && p.L > 2) {
+                n2l = (int64_t)c_all - (cut1 ? (int64_t)s_d2 : 0);
+                cap2l = (int64_t)((double)out1 * p.ratio[2]);
+                if (cap2l < 1) cap2l = 1;
+                lazy = n2l <= cap2l;
+            }
+            if (lazy) {
+                for (int64_t g = tid; g < groups; g += nt) {
+                    uint32_t v0[4], va[4];
+                    and_group(g, v0, va);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (g * 4 + i < p.words) M[g * 4 + i] = va[i];
+                }
+                __syncthreads();
+                if (cut1) {
+                    const uint32_t nd = s_nd;
+                    for (uint32_t e = tid; e < nd; e += nt) {
+                        const uint32_t row = __ldcg(c_row + e);
+                        atomicAnd(&M[row >> 5], ~(1u << (row & 31)));
+                    }
+                }
+                if (tid == 0) {
+                    if (p.counts && p.L > 2) {
+                        p.counts[((int64_t)2 * 3 + 0) * p.Q + q] = (int32_t)out1;
+                        p.counts[((int64_t)2 * 3 + 1) * p.Q + q] = (int32_t)n2l;
+                        p.counts[((int64_t)2 * 3 + 2) * p.Q + q] = (int32_t)n2l;
+                    }
+                    p.n_out[q] = (int32_t)(p.L > 2 ? n2l : out1);
+                }
+                __syncthreads();
+                continue;
+            }
+            __syncthreads();
+            if (tid == 0) s_bufn = 0;
+            __syncthreads();
+        }
         if (p.L == 2) {
             for (uint32_t item = warp; item < n_items; item += nw) {
                 const uint32_t seg = item / cps, e_base = (item - seg * cps) * kChunk;
