@@ -52,6 +52,19 @@ int hq_filter_bits_tc_launch(const float* db_packed, const uint32_t* valid, int6
                              const hq_index_layout* layout, const float* q_idx, int Q, const float* xstar, float* q_packed,
                              float* tq, float* nq, uint32_t* bits, int64_t bits_pitch, const HqFilterLists* lists, cudaStream_t st);
 extern "C" int hq_filter_tc_plan(int64_t N, int Q, int* n_ranges, int* tiles_per_range);
+int hq_filter_tc_plan_strided(int64_t N, int Q, int tile_stride, int* n_ranges, int* tiles_per_range);
+struct HqFtcOpts {              // variants of the threshold pass (see FtcParams in hq_filter_tc.cu)
+    int tile_stride;            // > 1: sample pass over every tile_stride-th 64-row tile (lists + level-0 counts, no planes)
+    const int32_t* unit_only;   // optional [ceil(Q / 128)]: only query tiles with a non-zero flag are processed
+    int32_t* c0_cnt;            // optional [Q]: += rows passing the level-0 threshold
+    const float* win;           // window mode: [4][Q] lo1, hi1, lo2, hi2
+    int32_t* wcnt;              // window mode: [4][Q] counters
+};
+int hq_filter_tc_prepare(const hq_index_layout* layout, const float* q_idx, int Q, const float* xstar, float* q_packed, float* tq,
+                         float* nq, cudaStream_t st);
+int hq_filter_tc_pass(const float* db_packed, const uint32_t* valid, int64_t valid_pitch, int64_t N, const hq_index_layout* layout, int Q,
+                      const float* q_packed, const float* tq, uint32_t* bits, int64_t bits_pitch, const HqFilterLists* lists,
+                      const HqFtcOpts* o, cudaStream_t st);
 
 // ---- Hilbert curve, the reference's variant (core/hilbert_mapper.py:42-113) ----
 // d -> (x, y), low bit-pairs first.

@@ -644,7 +644,7 @@ __device__ __forceinline__ bool in_bins(const BinStack& s, float k) {
 template <class ForEach, class RowOf>
 __device__ __forceinline__ bool select_boundary(ForEach for_each, RowOf row_of, uint32_t drop, float lo, float hi, bool have_hist0,
                                                 uint32_t* hist, uint32_t* sh, float* b_key, uint32_t* b_row, uint32_t* s_bufn,
-                                                float* s_K, uint32_t* s_R, Boundary& out) {
+                                                float* s_K, uint32_t* s_R, Boundary& out, uint32_t cut_cap = (uint32_t)kCutCap) {
     const int tid = threadIdx.x, nt = blockDim.x;
     BinStack st{};
     float cur_lo = lo, cur_hi = hi;
@@ -665,7 +665,7 @@ __device__ __forceinline__ bool select_boundary(ForEach for_each, RowOf row_of, 
         else if (round == 1) { st.lo1 = cur_lo; st.sc1 = scale; st.cb1 = cb; }
         else { st.lo2 = cur_lo; st.sc2 = scale; st.cb2 = cb; }
         st.depth = round + 1;
-        if (n_in_bin <= (uint32_t)kCutCap) {
+        if (n_in_bin <= cut_cap) {
             if (tid == 0) *s_bufn = 0;
             __syncthreads();
             for_each([&](float k, uint32_t tok) {
@@ -1140,6 +1140,483 @@ __global__ void __launch_bounds__(kListThreads, 1) k_filter_cascade_lists(const 
 }
 
 // ---------------------------------------------------------------------------------------
+// Window mode.  On most data the ratio cuts bind far above the thresholds (the level-1 and level-2 index rows are block
+// means of the level-0 row, so a row that passes level 0 almost always passes the other thresholds too: cut 1 keeps the
+// best 50 % of the level-0 survivors, cut 2 the best 70 % of those), and 13 % of all (query, row) pairs went through the
+// candidate lists only for the cascade to find two cut keys per query.  Instead:
+//   1. a SAMPLE pass (the same tensor-core kernel over every s-th 64-row tile) writes the lists of a sample of the rows;
+//   2. k_filter_predict simulates the cascade on the sample and brackets each cut key by a window [lo, hi) that contains
+//      the true cut with ~5 sigma of the sampling error (distribution free: the error is binomial in rank space);
+//   3. the WINDOW pass (k_filter_bits_tc<true>) classifies every pair against the windows with bit-mask arithmetic, writes
+//      the plane of the rows that survive both cuts for sure, four counters per query, and lists only the window rows;
+//   4. k_filter_cascade_win ranks the window rows exactly (same selection code as the streaming cascade) and checks the
+//      prediction against the exact counters.  A query whose cut lies outside its window (or whose lists overflow, or
+//      whose level-0 cut binds) is flagged and redone by the fallback: full-threshold planes for its query tile +
+//      the generic gather cascade.
+// ---------------------------------------------------------------------------------------
+struct PredictParams {
+    int Q, L;
+    double ratio[3];
+    float z;                     // window half width in standard deviations of the sample rank
+    const float* tq;             // [3][Q]
+    const float* nq;             // [3][Q]
+    const float* l_k1;           // sample lists
+    const float* l_k2;
+    const int32_t* seg_n;
+    int64_t seg_cap;
+    int n_segs;
+    const int32_t* c0_s;         // [Q] rows of the sample passing level 0
+    float* win;                  // [4][Q] out
+    int32_t* pflag;              // [Q] out: 1 = no prediction (sample lists overflowed)
+};
+
+// suffix[b] = sum of hist[b..2047] (256 threads, eight bins each)
+__device__ __forceinline__ void suffix_sums_256(const uint32_t* hist, uint32_t* suffix, uint32_t* s_scan) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t v[8], sum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i] = hist[2047 - (tid * 8 + i)]; sum += v[i]; }      // reversed: thread 0 owns the top bins
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_scan[warp] = incl;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int w = 0; w < warp; ++w) base += s_scan[w];
+    uint32_t run = base + incl - sum;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { run += v[i]; suffix[2047 - (tid * 8 + i)] = run; }
+    __syncthreads();
+}
+
+// Window around the rank `r` (from the top) of a key distribution given as suffix sums over 2048 linear bins of
+// [lo, hi): out_hi = lower edge of the lowest bin b with suffix[b] <= r - m (+inf if none), out_lo = lower edge of the
+// highest bin b with suffix[b] >= r + m (lo if none).  sh_f[0] / sh_f[1] receive them.
+__device__ __forceinline__ void window_from_suffix(const uint32_t* suffix, float r, float m, float lo, float hi, float* sh_f) {
+    const int tid = threadIdx.x;
+    const float w = (hi - lo) * (1.0f / 2048.0f);
+    if (tid == 0) { sh_f[0] = INFINITY; sh_f[1] = lo; }
+    __syncthreads();
+    const float r_hi = r - m, r_lo = r + m;
+    for (int b = tid; b < 2048; b += blockDim.x) {
+        const float sb = (float)suffix[b];
+        if (sb <= r_hi && (b == 0 || (float)suffix[b - 1] > r_hi)) sh_f[0] = lo + w * (float)b;
+        if (sb >= r_lo && (b == 2047 || (float)suffix[b + 1] < r_lo)) sh_f[1] = lo + w * (float)b;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) k_filter_predict(const PredictParams p) {
+    __shared__ uint32_t hist[2048];
+    __shared__ uint32_t suffix[2048];
+    __shared__ uint32_t s_scan[8];
+    __shared__ uint32_t s_warp[32];
+    __shared__ float sh_f[2];
+    __shared__ uint32_t s_cross;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int q = blockIdx.x;
+    const float qnan = __int_as_float(0x7fc00000);
+    uint32_t part = 0, over = 0;
+    for (int i = tid; i < p.n_segs; i += nt) {
+        const int32_t n = p.seg_n[(int64_t)q * p.n_segs + i];
+        if (n > p.seg_cap) over = 1;
+        part += (uint32_t)(n > p.seg_cap ? (int32_t)p.seg_cap : n);
+    }
+    const uint32_t n1 = block_sum(part, s_warp);
+    const uint32_t any_over = block_sum(over, s_warp);
+    const bool three = p.L > 2;
+    const float t1 = __ldg(p.tq + (int64_t)1 * p.Q + q), t2 = three ? __ldg(p.tq + (int64_t)2 * p.Q + q) : -INFINITY;
+    const float u1 = __ldg(p.nq + (int64_t)1 * p.Q + q), u2 = three ? __ldg(p.nq + (int64_t)2 * p.Q + q) : 0.f;
+    const float t0 = __ldg(p.tq + q);
+    if (any_over || !(t0 == t0) || !(t1 == t1) || !(t2 == t2)) {
+        // NaN thresholds (a zero query level: nothing passes) give NaN windows = an empty result without a fallback
+        if (tid < 4) p.win[(int64_t)tid * p.Q + q] = qnan;
+        if (tid == 0) p.pflag[q] = any_over ? 1 : 0;
+        return;
+    }
+    const float c0s = (float)p.c0_s[q];
+    const int64_t qbase = (int64_t)q * p.n_segs * p.seg_cap;
+    // a warp owns one segment at a time and keeps four 128-bit loads per array in flight (segments are 128-byte aligned)
+    const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    auto each = [&](auto visit) {
+        for (int sgi = warp; sgi < p.n_segs; sgi += nw) {
+            int32_t cnt = p.seg_n[(int64_t)q * p.n_segs + sgi];
+            if (cnt > p.seg_cap) cnt = (int32_t)p.seg_cap;
+            const int64_t off = qbase + (int64_t)sgi * p.seg_cap;
+            for (int e0 = lane * 4; e0 < cnt; e0 += 512) {
+                float4 a[4], b[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int e = e0 + u * 128;
+                    a[u] = e < cnt ? __ldg(reinterpret_cast<const float4*>(p.l_k1 + off + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    b[u] = (three && e < cnt) ? __ldg(reinterpret_cast<const float4*>(p.l_k2 + off + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int e = e0 + u * 128;
+                    if (e < cnt) visit(a[u].x, b[u].x);
+                    if (e + 1 < cnt) visit(a[u].y, b[u].y);
+                    if (e + 2 < cnt) visit(a[u].z, b[u].z);
+                    if (e + 3 < cnt) visit(a[u].w, b[u].w);
+                }
+            }
+        }
+    };
+    // ---- level 1 ----
+    const float r1 = (float)p.ratio[1], r12 = (float)(p.ratio[1] * p.ratio[2]);
+    const float cap1 = r1 * c0s;
+    const float m1 = p.z * sqrtf(fmaxf(r1 * (1.0f - r1), 0.01f) * fmaxf(c0s, 1.0f)) + 4.0f;
+    const float sc1 = u1 > t1 ? 2048.0f / (u1 - t1) : 0.f;
+    for (int i = tid; i < 2048; i += nt) hist[i] = 0;
+    __syncthreads();
+    each([&](float k1, float) { atomicAdd(&hist[lin_bin(k1, t1, sc1)], 1u); });
+    __syncthreads();
+    suffix_sums_256(hist, suffix, s_scan);
+    float lo1 = t1, hi1 = t1;
+    const bool bind1 = (float)n1 + m1 > cap1;
+    uint32_t cross_bin = 0;                            // entries in bins >= cross_bin play the survivors of cut 1 below
+    if (bind1) {
+        window_from_suffix(suffix, cap1, m1, t1, u1, sh_f);
+        hi1 = sh_f[0]; lo1 = sh_f[1];
+        if (tid == 0) s_cross = 0;
+        __syncthreads();
+        for (int b = tid; b < 2048; b += nt)
+            if ((float)suffix[b] >= cap1 && (b == 2047 || (float)suffix[b + 1] < cap1)) s_cross = (uint32_t)b;
+        __syncthreads();
+        cross_bin = s_cross;
+    }
+    const float pop_cross = bind1 ? (float)hist[cross_bin] : 0.f;
+    __syncthreads();
+    if (!three) {                                      // two levels: no cut 2 (the window cascade treats level 2 as "everything passes")
+        if (tid == 0) {
+            p.win[(int64_t)0 * p.Q + q] = lo1; p.win[(int64_t)1 * p.Q + q] = hi1;
+            p.win[(int64_t)2 * p.Q + q] = -INFINITY; p.win[(int64_t)3 * p.Q + q] = -INFINITY;
+            p.pflag[q] = 0;
+        }
+        return;
+    }
+    // ---- level 2 on the sample's survivors of cut 1 ----
+    const float out1 = fminf((float)n1, cap1);
+    const float cap2 = (float)p.ratio[2] * out1;
+    const float m2 = p.z * sqrtf(fmaxf(r12 * (1.0f - r12), 0.01f) * fmaxf(c0s, 1.0f)) + pop_cross + 4.0f;
+    const float sc2 = u2 > t2 ? 2048.0f / (u2 - t2) : 0.f;
+    for (int i = tid; i < 2048; i += nt) hist[i] = 0;
+    __syncthreads();
+    uint32_t c2 = 0;
+    each([&](float k1, float k2) {
+        if (lin_bin(k1, t1, sc1) >= cross_bin && k2 >= t2) { atomicAdd(&hist[lin_bin(k2, t2, sc2)], 1u); ++c2; }
+    });
+    const uint32_t n2 = block_sum(c2, s_warp);
+    suffix_sums_256(hist, suffix, s_scan);
+    float lo2 = t2, hi2 = t2;
+    if ((float)n2 + m2 > cap2) {
+        window_from_suffix(suffix, cap2, m2, t2, u2, sh_f);
+        hi2 = sh_f[0]; lo2 = sh_f[1];
+    }
+    if (tid == 0) {
+        p.win[(int64_t)0 * p.Q + q] = lo1; p.win[(int64_t)1 * p.Q + q] = hi1;
+        p.win[(int64_t)2 * p.Q + q] = lo2; p.win[(int64_t)3 * p.Q + q] = hi2;
+        p.pflag[q] = 0;
+    }
+}
+
+struct WinParams {
+    const uint32_t* alive;       // [Q][pitch] rows that survive both cuts for sure (window pass)
+    int64_t words, pitch;
+    int64_t N;
+    int Q, L;
+    double ratio[3];
+    const float* tq;             // [3][Q]
+    const float* nq;             // [3][Q]
+    const float* win;            // [4][Q]
+    const int32_t* wcnt;         // [4][Q]
+    const int32_t* pflag;        // [Q]
+    const uint32_t* l_rows;
+    const float* l_k1;
+    const float* l_k2;
+    const int32_t* seg_n;
+    int64_t seg_cap;
+    int n_segs;
+    uint32_t* mask;
+    int64_t mask_stride;
+    int32_t* n_out;
+    int32_t* fallback;           // [Q] out
+    int32_t* tile_flag;          // [ceil(Q / 128)] out: a query of the tile fell back
+    float* tmp_keys;             // [gridDim][tmp_stride]
+    uint32_t* tmp_rows;
+    int64_t tmp_stride;
+};
+
+constexpr int kWinThreads = 256;
+constexpr int kWinCutCap = 1024;      // cut-bin members ranked in shared memory (window histograms are fine grained)
+constexpr int kWinCtasPerSm = 4;      // 64 registers per thread (7 CTAs per SM = one wave of 1024 queries would leave 32: spills)
+
+__global__ void __launch_bounds__(kWinThreads, kWinCtasPerSm) k_filter_cascade_win(const WinParams p) {
+    __shared__ uint32_t hist[2048];
+    __shared__ uint32_t sh[4];
+    __shared__ uint32_t s_warp[32];
+    __shared__ int32_t s_cnt[kMaxSegs];
+    __shared__ float b_key[kWinCutCap];
+    __shared__ uint32_t b_row[kWinCutCap];
+    __shared__ float b_k2[kWinCutCap];
+    __shared__ uint32_t s_bufn, s_flag, s_R, s_n2, s_x1, s_x2;
+    __shared__ float s_K;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    float* const c_k2 = p.tmp_keys + (int64_t)blockIdx.x * p.tmp_stride;
+    uint32_t* const c_row = p.tmp_rows + (int64_t)blockIdx.x * p.tmp_stride;
+
+    for (int q = blockIdx.x; q < p.Q; q += gridDim.x) {
+        if (tid == 0) { s_flag = 0; s_n2 = 0; s_bufn = 0; s_x1 = 0; s_x2 = 0; }
+        __syncthreads();
+        for (int i = tid; i < p.n_segs; i += nt) {
+            const int32_t n = p.seg_n[(int64_t)q * p.n_segs + i];
+            if (n > p.seg_cap) s_flag = 1;
+            s_cnt[i] = n;
+        }
+        if (q + 1 < p.Q)                                 // padding words of the mask row (the last row ends at `words`)
+            for (int64_t w = p.words + tid; w < p.mask_stride; w += nt) p.mask[(int64_t)q * p.mask_stride + w] = 0u;
+        const int64_t c0 = __ldg(p.wcnt + q), nA1 = __ldg(p.wcnt + (int64_t)1 * p.Q + q);
+        const int64_t nA1A2 = __ldg(p.wcnt + (int64_t)2 * p.Q + q), nAl = __ldg(p.wcnt + (int64_t)3 * p.Q + q);
+        int64_t cap0 = (int64_t)((double)p.N * p.ratio[0]);
+        if (cap0 < 1) cap0 = 1;
+        __syncthreads();
+        bool failed = s_flag || __ldg(p.pflag + q) || c0 > cap0;
+        auto fail = [&]() {
+            if (tid == 0) { p.fallback[q] = 1; p.tile_flag[q >> 7] = 1; }
+            __syncthreads();
+        };
+        if (failed) { fail(); continue; }
+        const bool three = p.L > 2;
+        const float lo1 = __ldg(p.win + q), hi1 = __ldg(p.win + (int64_t)1 * p.Q + q);
+        const float lo2 = __ldg(p.win + (int64_t)2 * p.Q + q), hi2 = __ldg(p.win + (int64_t)3 * p.Q + q);
+        const float t1 = __ldg(p.tq + (int64_t)1 * p.Q + q), t2 = three ? __ldg(p.tq + (int64_t)2 * p.Q + q) : -INFINITY;
+        uint32_t* M = p.mask + (int64_t)q * p.mask_stride;
+        const uint32_t* AL = p.alive + (int64_t)q * p.pitch;
+        if (AL != M) {   // M = alive plane (plane rows are 32-byte aligned and padded to 8 words; four 128-bit loads in flight per thread)
+            const int64_t groups = (p.words + 3) >> 2;
+            for (int64_t g0 = tid; g0 < groups; g0 += 4 * (int64_t)nt) {
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int64_t g = g0 + (int64_t)u * nt;
+                    v[u] = g < groups ? __ldg(reinterpret_cast<const uint4*>(AL) + g) : make_uint4(0u, 0u, 0u, 0u);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int64_t w = (g0 + (int64_t)u * nt) * 4;
+                    if (w < p.words) M[w] = v[u].x;
+                    if (w + 1 < p.words) M[w + 1] = v[u].y;
+                    if (w + 2 < p.words) M[w + 2] = v[u].z;
+                    if (w + 3 < p.words) M[w + 3] = v[u].w;
+                }
+            }
+        }
+        if (!(lo1 == lo1)) {                            // NaN windows: a zero query level, nothing survives
+            if (tid == 0) p.n_out[q] = 0;
+            __syncthreads();
+            continue;
+        }
+        const int64_t qbase = (int64_t)q * p.n_segs * p.seg_cap;
+        const uint32_t* const L_rows = p.l_rows + qbase;
+        const float* const L_k1 = p.l_k1 + qbase;
+        const float* const L_k2 = three ? p.l_k2 + qbase : nullptr;
+        // every listed entry of the query: visit(k1, token).  A warp owns one segment at a time and keeps four loads per
+        // lane in flight (a block-wide loop over one short segment after the other was a chain of ~40 DRAM round trips
+        // per pass).
+        const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+        auto each_all = [&](auto visit) {
+            for (int sgi = warp; sgi < p.n_segs; sgi += nw) {
+                const uint32_t cnt = (uint32_t)s_cnt[sgi];
+                const uint32_t off = (uint32_t)sgi * (uint32_t)p.seg_cap;
+                for (uint32_t e0 = lane * 4; e0 < cnt; e0 += 512) {         // four 128-bit loads in flight per lane
+                    float4 k[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t e = e0 + u * 128;
+                        k[u] = e < cnt ? __ldg(reinterpret_cast<const float4*>(L_k1 + off + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t e = e0 + u * 128;
+                        if (e < cnt) visit(k[u].x, off + e);
+                        if (e + 1 < cnt) visit(k[u].y, off + e + 1);
+                        if (e + 2 < cnt) visit(k[u].z, off + e + 2);
+                        if (e + 3 < cnt) visit(k[u].w, off + e + 3);
+                    }
+                }
+            }
+        };
+        // the same with the rows and the level-2 keys loaded up front (the classification pass needs them for most entries)
+        auto each_all3 = [&](auto visit) {
+            for (int sgi = warp; sgi < p.n_segs; sgi += nw) {
+                const uint32_t cnt = (uint32_t)s_cnt[sgi];
+                const uint32_t off = (uint32_t)sgi * (uint32_t)p.seg_cap;
+                for (uint32_t e0 = lane * 4; e0 < cnt; e0 += 256) {
+                    float4 k[2], k2[2];
+                    uint4 rw[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const uint32_t e = e0 + u * 128;
+                        const bool ok = e < cnt;
+                        k[u] = ok ? __ldg(reinterpret_cast<const float4*>(L_k1 + off + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        rw[u] = ok ? __ldg(reinterpret_cast<const uint4*>(L_rows + off + e)) : make_uint4(0u, 0u, 0u, 0u);
+                        k2[u] = (ok && three) ? __ldg(reinterpret_cast<const float4*>(L_k2 + off + e)) : make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const uint32_t e = e0 + u * 128;
+                        if (e < cnt) visit(k[u].x, rw[u].x & 0x7fffffffu, k2[u].x);
+                        if (e + 1 < cnt) visit(k[u].y, rw[u].y & 0x7fffffffu, k2[u].y);
+                        if (e + 2 < cnt) visit(k[u].z, rw[u].z & 0x7fffffffu, k2[u].z);
+                        if (e + 3 < cnt) visit(k[u].w, rw[u].w & 0x7fffffffu, k2[u].w);
+                    }
+                }
+            }
+        };
+        auto each_w1 = [&](auto visit) {
+            each_all([&](float k, uint32_t tok) { if (k < hi1) visit(k, tok); });
+        };
+        // ---- level 1: rows inside window 1, ranked below the nA1 rows above it ----
+        const float top1 = hi1 < INFINITY ? hi1 : __ldg(p.nq + (int64_t)1 * p.Q + q);
+        const float scale1 = top1 > lo1 ? 2048.0f / (top1 - lo1) : 0.f;
+        for (int i = tid; i < 2048; i += nt) hist[i] = 0;
+        __syncthreads();
+        uint32_t cw = 0;
+        each_w1([&](float k, uint32_t) { atomicAdd(&hist[lin_bin(k, lo1, scale1)], 1u); ++cw; });
+        const int64_t n_w1 = block_sum(cw, s_warp);
+        int64_t cap1 = (int64_t)((double)c0 * p.ratio[1]);
+        if (cap1 < 1) cap1 = 1;
+        const bool exact1 = lo1 == t1;                  // the window reaches down to the threshold: n1 is exact
+        const int64_t n1 = nA1 + n_w1;
+        if ((!exact1 && n1 < cap1) || (n1 > cap1 && nA1 > cap1)) { fail(); continue; }
+        const bool cut1 = n1 > cap1;
+        Boundary b1;
+        b1.K = -INFINITY; b1.R = 0;
+        CutBin cb1{0.f, 0.f, 0u, 0u, false};
+        if (cut1) {
+            find_cut_bin(hist, (uint32_t)(n1 - cap1), sh);
+            if (sh[2] <= (uint32_t)kWinCutCap) {
+                cb1.lo = lo1; cb1.scale = scale1; cb1.cb = sh[0]; cb1.r_in_bin = sh[1]; cb1.on = true;
+            } else {
+                failed = !select_boundary(each_w1, [&](uint32_t tok) { return __ldg(L_rows + tok) & 0x7fffffffu; }, (uint32_t)(n1 - cap1),
+                                          lo1, top1, true, hist, sh, b_key, b_row, &s_bufn, &s_K, &s_R, b1, (uint32_t)kWinCutCap);
+            }
+        }
+        if (failed) { fail(); continue; }
+        const int64_t out1 = cut1 ? cap1 : n1;
+        int64_t cap2 = three ? (int64_t)((double)out1 * p.ratio[2]) : out1;
+        if (cap2 < 1) cap2 = 1;
+        __syncthreads();
+        if (tid == 0) s_bufn = 0;
+        const float top2 = hi2 < INFINITY ? hi2 : (three ? __ldg(p.nq + (int64_t)2 * p.Q + q) : 0.f);
+        const float scale2 = top2 > lo2 ? 2048.0f / (top2 - lo2) : 0.f;
+        for (int i = tid; i < 2048; i += nt) hist[i] = 0;
+        __syncthreads();
+        // a survivor of cut 1: dead below window 2, alive above it (window-1 rows are not in the plane yet), else a member
+        auto level2 = [&](uint32_t row, float k2, bool w1) {
+            if (!(k2 >= lo2)) return;
+            if (w1) atomicAdd(&s_x1, 1u);
+            if (k2 >= hi2) {
+                if (w1) { atomicOr(&M[row >> 5], 1u << (row & 31)); atomicAdd(&s_x2, 1u); }
+                return;
+            }
+            const uint32_t slot = atomicAdd(&s_n2, 1u);
+            c_k2[slot] = k2; c_row[slot] = row;
+            atomicAdd(&hist[lin_bin(k2, lo2, scale2)], 1u);
+        };
+        each_all3([&](float k1, uint32_t row, float k2) {          // (two levels: k2 = +inf, every survivor of cut 1 survives)
+            const bool w1 = k1 < hi1;
+            int cls = 2;
+            if (w1 && cut1) {
+                if (cb1.on) {
+                    const uint32_t b = lin_bin(k1, cb1.lo, cb1.scale);
+                    cls = b > cb1.cb ? 2 : (b == cb1.cb ? 1 : 0);
+                } else {
+                    cls = kept_by(b1, k1, row) ? 2 : 0;
+                }
+            }
+            if (cls == 0) return;
+            if (cls == 1) {
+                const uint32_t slot = atomicAdd(&s_bufn, 1u);
+                b_key[slot] = k1; b_row[slot] = row; b_k2[slot] = k2;
+                return;
+            }
+            level2(row, k2, w1);
+        });
+        __syncthreads();
+        if (cb1.on) {
+            const uint32_t nb = s_bufn;
+            rank_cut_bin(b_key, b_row, nb, cb1.r_in_bin, &s_K, &s_R);
+            const Boundary bb{s_K, s_R};
+            for (uint32_t e = tid; e < nb; e += nt)
+                if (kept_by(bb, b_key[e], b_row[e])) level2(b_row[e], b_k2[e], true);
+            __syncthreads();
+        }
+        const int64_t n_w2 = s_n2;
+        const int64_t n2 = nA1A2 + (int64_t)s_x1, nAbove2 = nAl + (int64_t)s_x2;
+        const bool exact2 = lo2 == t2;
+        if (n2 - nAbove2 != n_w2 || (!exact2 && n2 < cap2) || (n2 > cap2 && nAbove2 > cap2)) { fail(); continue; }
+        const bool cut2 = n2 > cap2;
+        Boundary b2;
+        b2.K = -INFINITY; b2.R = 0;
+        CutBin cb2{0.f, 0.f, 0u, 0u, false};
+        auto each_l2 = [&](auto visit) {
+            for (uint32_t e0 = tid; e0 < (uint32_t)n_w2; e0 += 4 * nt) {
+                float k[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) k[u] = e0 + u * nt < (uint32_t)n_w2 ? __ldcg(c_k2 + e0 + u * nt) : -1.0f;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (e0 + u * nt < (uint32_t)n_w2) visit(k[u], e0 + u * nt);
+            }
+        };
+        if (cut2) {
+            find_cut_bin(hist, (uint32_t)(n2 - cap2), sh);
+            if (sh[2] <= (uint32_t)kWinCutCap) {
+                cb2.lo = lo2; cb2.scale = scale2; cb2.cb = sh[0]; cb2.r_in_bin = sh[1]; cb2.on = true;
+            } else {
+                failed = !select_boundary(each_l2, [&](uint32_t tok) { return __ldcg(c_row + tok); }, (uint32_t)(n2 - cap2), lo2, top2, true,
+                                          hist, sh, b_key, b_row, &s_bufn, &s_K, &s_R, b2, (uint32_t)kWinCutCap);
+            }
+        }
+        if (failed) { fail(); continue; }
+        __syncthreads();
+        if (tid == 0) s_bufn = 0;
+        __syncthreads();
+        each_l2([&](float k, uint32_t tok) {
+            const uint32_t row = __ldcg(c_row + tok);
+            int cls = 2;
+            if (cut2) {
+                if (cb2.on) {
+                    const uint32_t b = lin_bin(k, cb2.lo, cb2.scale);
+                    cls = b > cb2.cb ? 2 : (b == cb2.cb ? 1 : 0);
+                } else {
+                    cls = kept_by(b2, k, row) ? 2 : 0;
+                }
+            }
+            if (cls == 2) atomicOr(&M[row >> 5], 1u << (row & 31));
+            if (cls == 1) {
+                const uint32_t slot = atomicAdd(&s_bufn, 1u);
+                b_key[slot] = k; b_row[slot] = row;
+            }
+        });
+        __syncthreads();
+        if (cb2.on) {
+            const uint32_t nb = s_bufn;
+            rank_cut_bin(b_key, b_row, nb, cb2.r_in_bin, &s_K, &s_R);
+            const Boundary bb{s_K, s_R};
+            for (uint32_t e = tid; e < nb; e += nt)
+                if (kept_by(bb, b_key[e], b_row[e])) atomicOr(&M[b_row[e] >> 5], 1u << (b_row[e] & 31));
+        }
+        if (tid == 0) p.n_out[q] = (int32_t)(cut2 ? cap2 : n2);
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Exceptional rows.  The fast path assumes every index row has its structural length; a block mean that
 // happens to be exactly 0.0f at the end of a row shortens the row's stored length (one row in ~10 M at
 // 768-D), and the reference then normalises the QUERY over that shorter prefix.  Such rows are masked out of
@@ -1214,6 +1691,69 @@ __global__ void __launch_bounds__(128) k_filter_exceptions(const ExcParams p) {
     }
 }
 
+// The same rows in window mode: classified against the query's windows like the window pass does (counters, alive
+// plane, extra list segment).  Runs between the window pass and k_filter_cascade_win.
+struct ExcWinParams {
+    ExcParams e;
+    const float* win;            // [4][Q]
+    int32_t* wcnt;               // [4][Q]
+    uint32_t* alive;             // [Q][alive_pitch]
+    int64_t alive_pitch;
+};
+
+__global__ void __launch_bounds__(128) k_filter_exceptions_win(const ExcWinParams pw) {
+    const ExcParams& p = pw.e;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)p.Q * p.n_exc) return;
+    const int q = (int)(t / p.n_exc), e = (int)(t - (int64_t)q * p.n_exc);
+    const int64_t row = p.exc_rows[e];
+    const int L = p.lay.L;
+    bool pass[3] = {false, false, false};
+    float keq[3] = {0.f, 0.f, 0.f};
+    for (int l = 0; l < L && l < 3; ++l) {
+        const int keff = p.lay.lvl_keff[l];
+        int m = (int)p.lens[row * L + l];
+        m = m < keff ? m : keff;
+        const float* c = p.idx + row * p.lay.Lsum + p.lay.lvl_off[l];
+        const float* qv = p.q_idx + (int64_t)q * p.lay.Lsum + p.lay.lvl_off[l];
+        float dot = 0.f, nc2 = 0.f, nq2 = 0.f;
+        for (int j = 0; j < keff; ++j) {
+            const float cj = __ldg(c + j), qj = __ldg(qv + j);
+            dot = fmaf(cj, qj, dot);
+            nc2 = fmaf(cj, cj, nc2);
+            if (j < m) nq2 = fmaf(qj, qj, nq2);
+        }
+        const float nq = sqrtf(nq2), nc = sqrtf(nc2);
+        float sc = 0.f;
+        if (nq != 0.f && nc != 0.f) sc = __fmul_rn(__fadd_rn(__fdiv_rn(dot, __fmul_rn(nq, nc)), 1.0f), 0.5f);
+        pass[l] = (double)sc >= p.thr[l];
+        keq[l] = (2.0f * sc - 1.0f) * __ldg(p.nq + (int64_t)l * p.Q + q);
+    }
+    const float lo1 = __ldg(pw.win + q), hi1 = __ldg(pw.win + (int64_t)1 * p.Q + q);
+    const float lo2 = __ldg(pw.win + (int64_t)2 * p.Q + q), hi2 = __ldg(pw.win + (int64_t)3 * p.Q + q);
+    if (!(lo1 == lo1) || !pass[0]) return;
+    const float t1 = __ldg(p.tq + (int64_t)1 * p.Q + q), t2 = L > 2 ? __ldg(p.tq + (int64_t)2 * p.Q + q) : 0.f;
+    // keys that say what the exact scores said: a row that passes a threshold never sorts below it
+    const float k1 = pass[1] ? fmaxf(keq[1], t1) : -INFINITY, k2 = pass[2] ? fmaxf(keq[2], t2) : -INFINITY;
+    const bool A1 = k1 >= lo1, B1 = A1 && k1 >= hi1, A2 = L < 3 || k2 >= lo2, B2 = L < 3 || (A2 && k2 >= hi2);
+    atomicAdd(pw.wcnt + q, 1);
+    if (B1) atomicAdd(pw.wcnt + (int64_t)1 * p.Q + q, 1);
+    if (B1 && A2) atomicAdd(pw.wcnt + (int64_t)2 * p.Q + q, 1);
+    if (B1 && B2) {
+        atomicAdd(pw.wcnt + (int64_t)3 * p.Q + q, 1);
+        atomicOr(pw.alive + (int64_t)q * pw.alive_pitch + (row >> 5), 1u << (row & 31));
+    }
+    if (A1 && (!B1 || (A2 && !B2))) {
+        const int pos = atomicAdd(p.seg_n + (int64_t)q * p.n_segs + p.extra_seg, 1);
+        if (pos < p.seg_cap) {
+            const int64_t a = ((int64_t)q * p.n_segs + p.extra_seg) * p.seg_cap + pos;
+            p.l_rows[a] = (uint32_t)row;
+            p.l_k1[a] = k1;
+            if (L > 2) p.l_k2[a] = k2;
+        }
+    }
+}
+
 template <int K0, int K1, int K2>
 int launch_bits(const BitsParams& p, cudaStream_t st) {
     constexpr int KT = K0 + K1 + K2;
@@ -1276,17 +1816,121 @@ static ListGeom list_geom(int64_t N, int Q, const hq_index_layout* layout, bool 
     return g;
 }
 
+// Window mode (see k_filter_predict): sample stride, list geometry of the sample pass and of the window pass.
+constexpr int64_t kWinMinRows = 131072;           // below this the sample would be a large part of the pass itself
+constexpr int kWinMinQueries = 16;                // a few queries are latency bound: fewer launches win (full lists)
+constexpr int kWinSampleTiles = 512;              // 64-row tiles the sample pass aims for
+struct WinGeom { bool on; int stride; int n_segs_s; int64_t seg_cap_s; int n_segs_w; int64_t seg_cap_w; };
+
+static bool win_enabled() {
+    static const int v = [] { const char* e = getenv("HQ_FILTER_WINDOW"); return e ? atoi(e) : 1; }();
+    return v != 0;
+}
+
+static WinGeom win_geom(int64_t N, int Q, const hq_index_layout* layout) {
+    WinGeom g{false, 1, 0, 0, 0, 0};
+    if (!win_enabled() || !layout || layout->L < 2 || layout->L > 3 || !hq_filter_tc_supported(layout) || N < kWinMinRows || Q < kWinMinQueries)
+        return g;
+    const int64_t tiles = (N + 63) / 64;
+    int64_t stride = tiles / kWinSampleTiles;
+    stride = stride < 2 ? 2 : (stride > 64 ? 64 : stride);
+    int nr = 0, tp = 0;
+    if (hq_filter_tc_plan_strided(N, Q, (int)stride, &nr, &tp) != HQ_OK) return g;
+    g.stride = (int)stride;
+    g.n_segs_s = 2 * nr;
+    g.seg_cap_s = (((int64_t)tp * 32 + 2) / 3 + 31) & ~(int64_t)31;        // like the full lists: a third of the segment's rows
+    if (hq_filter_tc_plan(N, Q, &nr, &tp) != HQ_OK) return g;
+    g.n_segs_w = 2 * nr + 1;                                                // + the segment of the exceptional rows
+    g.seg_cap_w = (((int64_t)tp * 32 + 7) / 8 + 31) & ~(int64_t)31;        // window rows: an eighth of the segment's rows
+    if (g.seg_cap_w < 64) g.seg_cap_w = 64;
+    if (g.n_segs_s > kMaxSegs || g.n_segs_w > kMaxSegs) return g;
+    g.on = true;
+    return g;
+}
+
+static inline int64_t win_list_entries(const WinGeom& g) {
+    const int64_t a = (int64_t)g.n_segs_s * g.seg_cap_s, b = (int64_t)g.n_segs_w * g.seg_cap_w;
+    return a > b ? a : b;
+}
+static inline int win_seg_slots(const WinGeom& g) { return g.n_segs_s > g.n_segs_w ? g.n_segs_s : g.n_segs_w; }
+
+// window-mode scratch after the common part: alive plane | windows | counters | c0 of the sample, prediction flags,
+// fallback tile flags | segment counts | rows, k1, k2
+static int64_t win_extra_bytes(int64_t N, int Q, const WinGeom& g) {
+    return 256 + up128((int64_t)Q * plane_pitch(N) * 4) + 2 * up128((int64_t)4 * Q * 4) + 3 * up128((int64_t)Q * 4) +
+           up128((int64_t)Q * win_seg_slots(g) * 4) + 3 * up128((int64_t)Q * win_list_entries(g) * 4);
+}
+
+static void fill_cascade_keys(CascadeParams& cp, int L, const float* xstar, const double* ratio) {
+    for (int l = 0; l < 8; ++l) {
+        cp.ratio[l] = l < L ? ratio[l] : 1.0;
+        // survivors of level l score >= (x*_l + 1) / 2 (up to rounding): offset keys from a little below it
+        float lo = l < L && l < 3 ? (xstar[l] + 1.0f) * 0.5f : 0.f;
+        if (!(lo > 0.f)) lo = 0.f;
+        uint32_t klo;
+        memcpy(&klo, &lo, 4);
+        klo = klo > 64 ? klo - 64 : 0;
+        const float one = 1.0f;
+        uint32_t khi;
+        memcpy(&khi, &one, 4);
+        khi += 64;
+        uint32_t range = khi > klo ? khi - klo : 1, sh_a = 0;
+        while ((range >> sh_a) > 2047u) ++sh_a;
+        cp.key_lo[l] = klo;
+        cp.shift_a[l] = sh_a;
+    }
+}
+
 extern "C" int64_t hq_filter_fast_scratch_bytes(int64_t N, int Q, const hq_index_layout* layout) {
     if (!layout || N <= 0 || Q <= 0) return 0;
     int grid = hq_cached_sm_count();
     if (grid > Q) grid = Q;
     // bit planes | generic cascade key / row lists | packed query operand, thresholds, norms, fallback flags |
-    // candidate lists of the tensor-core pass
+    // candidate lists of the tensor-core pass (full lists, or the window-mode block when that is larger)
     int64_t b = (int64_t)layout->L * Q * plane_pitch(N) * 4 + up16((int64_t)grid * N * 8) + (int64_t)Q * 128 * 4 +
                 3 * up16((int64_t)3 * Q * 4);
     const ListGeom g = list_geom(N, Q, layout, true);           // sized for the worst case
-    if (g.on) b += 256 + up128((int64_t)Q * g.n_segs * 4) + (int64_t)(layout->L > 2 ? 3 : 2) * Q * g.n_segs * g.seg_cap * 4;
-    return b;
+    int64_t lists = 0;
+    if (g.on) lists = 256 + up128((int64_t)Q * g.n_segs * 4) + (int64_t)(layout->L > 2 ? 3 : 2) * Q * g.n_segs * g.seg_cap * 4;
+    const WinGeom wg = win_geom(N, Q, layout);
+    if (wg.on) { const int64_t w = win_extra_bytes(N, Q, wg); if (w > lists) lists = w; }
+    return b + lists;
+}
+
+extern "C" int hq_filter_fast_mode(int64_t N, int Q, const hq_index_layout* layout) {
+    if (!layout || N <= 0 || Q <= 0) return 0;
+    if (win_geom(N, Q, layout).on) return 2;
+    int grid = hq_cached_sm_count();
+    if (grid > Q) grid = Q;
+    const ListGeom lg = list_geom(N, Q, layout, false);
+    return (lg.on && (int64_t)lg.n_segs * lg.seg_cap <= (int64_t)grid * N) ? 1 : 0;
+}
+
+extern "C" int64_t hq_filter_fast_fallback_offset(int64_t N, int Q, const hq_index_layout* layout) {
+    if (!layout || N <= 0 || Q <= 0) return -1;
+    int grid = hq_cached_sm_count();
+    if (grid > Q) grid = Q;
+    return (int64_t)layout->L * Q * plane_pitch(N) * 4 + up16((int64_t)grid * N * 8) + (int64_t)Q * 128 * 4 + 2 * up16((int64_t)3 * Q * 4);
+}
+
+extern "C" int hq_filter_fast_window_layout(int64_t N, int Q, const hq_index_layout* layout, int64_t* out) {
+    HQ_REQUIRE(layout && out && N > 0 && Q > 0, "bad arguments");
+    const WinGeom wg = win_geom(N, Q, layout);
+    HQ_REQUIRE(wg.on, "window mode is not used for this shape");
+    const int64_t fb = hq_filter_fast_fallback_offset(N, Q, layout);
+    int64_t cur = fb + up16((int64_t)3 * Q * 4);
+    // the block is 128-byte aligned relative to the scratch base (torch allocations are 512-byte aligned)
+    cur = (cur + 127) & ~(int64_t)127;
+    auto take = [&](int64_t bytes) { const int64_t r = cur; cur += up128(bytes); return r; };
+    out[0] = take((int64_t)Q * plane_pitch(N) * 4);       // alive plane
+    out[1] = take((int64_t)4 * Q * 4);                    // windows
+    out[2] = take((int64_t)4 * Q * 4);                    // counters
+    out[3] = take((int64_t)Q * 4);                        // c0 of the sample
+    out[4] = take((int64_t)Q * 4);                        // prediction flags
+    out[5] = take((int64_t)Q * 4);                        // tile flags
+    out[6] = take((int64_t)Q * win_seg_slots(wg) * 4);    // segment counts (window geometry after the search)
+    out[7] = wg.n_segs_w; out[8] = wg.seg_cap_w; out[9] = wg.stride;
+    return HQ_OK;
 }
 
 extern "C" int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, const hq_index_layout* layout, const float* q_idx, int Q,
@@ -1325,6 +1969,113 @@ extern "C" int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, c
         lists.rows = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(lists.seg_n) + up128((int64_t)Q * lg.n_segs * 4));
         lists.k1 = reinterpret_cast<float*>(lists.rows + (int64_t)Q * lg.n_segs * lg.seg_cap);
         lists.k2 = L > 2 ? lists.k1 + (int64_t)Q * lg.n_segs * lg.seg_cap : nullptr;
+    }
+
+    const WinGeom wg = (db_packed && valid && !counts) ? win_geom(N, Q, layout) : WinGeom{false, 1, 0, 0, 0, 0};
+    if (wg.on) {
+        // ================= window mode =================
+        unsigned char* cur = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(fallback) + up16((int64_t)3 * Q * 4) + 127) & ~(uintptr_t)127);
+        auto take = [&](int64_t bytes) { unsigned char* r = cur; cur += up128(bytes); return r; };
+        uint32_t* const alive_scratch = reinterpret_cast<uint32_t*>(take((int64_t)Q * pitch * 4));
+        // mask rows padded like the planes (whole 32-byte sectors): the window pass writes the alive plane straight into the mask
+        const bool in_place = mask_stride == pitch && (reinterpret_cast<uintptr_t>(mask) & 31) == 0;
+        uint32_t* const alive = in_place ? mask : alive_scratch;
+        float* const win = reinterpret_cast<float*>(take((int64_t)4 * Q * 4));
+        int32_t* const wcnt = reinterpret_cast<int32_t*>(take((int64_t)4 * Q * 4));
+        int32_t* const c0_s = reinterpret_cast<int32_t*>(take((int64_t)Q * 4));
+        int32_t* const pflag = reinterpret_cast<int32_t*>(take((int64_t)Q * 4));
+        int32_t* const tile_flag = reinterpret_cast<int32_t*>(take((int64_t)Q * 4));
+        int32_t* const seg_n = reinterpret_cast<int32_t*>(take((int64_t)Q * win_seg_slots(wg) * 4));
+        const int64_t ents = win_list_entries(wg);
+        uint32_t* const l_rows = reinterpret_cast<uint32_t*>(take((int64_t)Q * ents * 4));
+        float* const l_k1 = reinterpret_cast<float*>(take((int64_t)Q * ents * 4));
+        float* const l_k2 = reinterpret_cast<float*>(take((int64_t)Q * ents * 4));
+        HQ_REQUIRE(cur <= reinterpret_cast<unsigned char*>(scratch) + scratch_bytes, "internal: window-mode scratch layout exceeds the buffer");
+
+        int rc = hq_filter_tc_prepare(layout, q_idx, Q, xstar, q_packed, tq, nq, st);
+        if (rc != HQ_OK) return rc;
+        // wcnt | c0_s | pflag | tile_flag are contiguous
+        HQ_CUDA_OK(cudaMemsetAsync(wcnt, 0, (size_t)(reinterpret_cast<unsigned char*>(seg_n) - reinterpret_cast<unsigned char*>(wcnt)), st));
+        HQ_CUDA_OK(cudaMemsetAsync(fallback, 0, (size_t)Q * 4, st));
+        // 1. sample pass
+        HqFilterLists ls{};
+        ls.rows = l_rows; ls.k1 = l_k1; ls.k2 = L > 2 ? l_k2 : nullptr; ls.seg_n = seg_n; ls.seg_cap = wg.seg_cap_s; ls.n_segs = wg.n_segs_s;
+        HqFtcOpts os{};
+        os.tile_stride = wg.stride; os.c0_cnt = c0_s;
+        rc = hq_filter_tc_pass(db_packed, valid, valid_pitch, N, layout, Q, q_packed, tq, nullptr, 0, &ls, &os, st);
+        if (rc != HQ_OK) return rc;
+        // 2. windows
+        PredictParams pp{};
+        pp.Q = Q; pp.L = L;
+        for (int l = 0; l < 3; ++l) pp.ratio[l] = l < L ? ratio[l] : 1.0;
+        static const float zwin = [] { const char* e = getenv("HQ_FILTER_WINDOW_Z"); return e ? (float)atof(e) : 5.0f; }();
+        pp.z = zwin;
+        pp.tq = tq; pp.nq = nq; pp.l_k1 = l_k1; pp.l_k2 = l_k2; pp.seg_n = seg_n; pp.seg_cap = wg.seg_cap_s; pp.n_segs = wg.n_segs_s;
+        pp.c0_s = c0_s; pp.win = win; pp.pflag = pflag;
+        k_filter_predict<<<Q, 256, 0, st>>>(pp);
+        HQ_LAUNCH_OK("k_filter_predict");
+        // 3. window pass
+        HQ_CUDA_OK(cudaMemsetAsync(seg_n, 0, (size_t)Q * wg.n_segs_w * 4, st));
+        HqFilterLists lw{};
+        lw.rows = l_rows; lw.k1 = l_k1; lw.k2 = L > 2 ? l_k2 : nullptr; lw.seg_n = seg_n; lw.seg_cap = wg.seg_cap_w; lw.n_segs = wg.n_segs_w;
+        HqFtcOpts ow{};
+        ow.tile_stride = 1; ow.win = win; ow.wcnt = wcnt;
+        rc = hq_filter_tc_pass(db_packed, valid, valid_pitch, N, layout, Q, q_packed, tq, alive, pitch, &lw, &ow, st);
+        if (rc != HQ_OK) return rc;
+        ExcParams ep{};
+        if (n_exc > 0) {
+            ep.idx = idx; ep.lens = lens; ep.lay = *layout; ep.q_idx = q_idx; ep.Q = Q; ep.exc_rows = exc_rows; ep.n_exc = n_exc;
+            for (int l = 0; l < 3; ++l) ep.thr[l] = l < L ? thr[l] : 2.0;
+            ep.bits = planes; ep.bits_pitch = pitch; ep.nq = nq; ep.tq = tq;
+            ep.l_rows = l_rows; ep.l_k1 = l_k1; ep.l_k2 = l_k2; ep.seg_n = seg_n; ep.seg_cap = wg.seg_cap_w; ep.n_segs = wg.n_segs_w;
+            ep.extra_seg = wg.n_segs_w - 1;
+            ExcWinParams ew{};
+            ew.e = ep; ew.win = win; ew.wcnt = wcnt; ew.alive = alive; ew.alive_pitch = pitch;
+            const int64_t pairs = (int64_t)Q * n_exc;
+            k_filter_exceptions_win<<<(unsigned)((pairs + 127) / 128), 128, 0, st>>>(ew);
+            HQ_LAUNCH_OK("k_filter_exceptions_win");
+        }
+        // 4. exact ranking of the window rows
+        WinParams wp{};
+        wp.alive = alive; wp.words = words; wp.pitch = pitch; wp.N = N; wp.Q = Q; wp.L = L;
+        for (int l = 0; l < 3; ++l) wp.ratio[l] = l < L ? ratio[l] : 1.0;
+        wp.tq = tq; wp.nq = nq; wp.win = win; wp.wcnt = wcnt; wp.pflag = pflag;
+        wp.l_rows = l_rows; wp.l_k1 = l_k1; wp.l_k2 = l_k2; wp.seg_n = seg_n; wp.seg_cap = wg.seg_cap_w; wp.n_segs = wg.n_segs_w;
+        wp.mask = mask; wp.mask_stride = mask_stride; wp.n_out = n_out; wp.fallback = fallback; wp.tile_flag = tile_flag;
+        wp.tmp_stride = (int64_t)wg.n_segs_w * wg.seg_cap_w;
+        int wgrid = hq_cached_sm_count() * kWinCtasPerSm;
+        if (wgrid > Q) wgrid = Q;
+        while (wgrid > 1 && (int64_t)wgrid * wp.tmp_stride > (int64_t)grid * N) --wgrid;
+        HQ_REQUIRE((int64_t)wgrid * wp.tmp_stride <= (int64_t)grid * N, "internal: window lists larger than the cascade scratch");
+        wp.tmp_keys = reinterpret_cast<float*>(sc_keys);
+        wp.tmp_rows = sc_keys + (int64_t)wgrid * wp.tmp_stride;
+        k_filter_cascade_win<<<wgrid, kWinThreads, 0, st>>>(wp);
+        HQ_LAUNCH_OK("k_filter_cascade_win");
+        // 5. fallback for the flagged queries: full-threshold planes of their query tiles, generic gather cascade
+        HqFtcOpts of{};
+        of.tile_stride = 1; of.unit_only = tile_flag;
+        rc = hq_filter_tc_pass(db_packed, valid, valid_pitch, N, layout, Q, q_packed, tq, planes, pitch, nullptr, &of, st);
+        if (rc != HQ_OK) return rc;
+        if (n_exc > 0) {
+            ep.l_rows = nullptr; ep.l_k1 = nullptr; ep.l_k2 = nullptr; ep.seg_n = nullptr;
+            const int64_t pairs = (int64_t)Q * n_exc;
+            k_filter_exceptions<<<(unsigned)((pairs + 127) / 128), 128, 0, st>>>(ep);
+            HQ_LAUNCH_OK("k_filter_exceptions");
+        }
+        CascadeParams cp{};
+        cp.bits = planes; cp.words = words; cp.bits_pitch = pitch; cp.idx = idx; cp.N = N; cp.lay = *layout; cp.q_idx = q_idx; cp.Q = Q;
+        fill_cascade_keys(cp, L, xstar, ratio);
+        for (int l = 0; l < 3; ++l) {
+            cp.lvl[l] = (lvl_rows && lvl_pitch && l < L) ? lvl_rows[l] : nullptr;
+            cp.lvl_pitch[l] = (lvl_rows && lvl_pitch && l < L) ? lvl_pitch[l] : 0;
+            HQ_REQUIRE(!cp.lvl[l] || (cp.lvl_pitch[l] % 4 == 0 && cp.lvl_pitch[l] >= ((layout->lvl_keff[l] + 3) & ~3)), "bad level pitch");
+        }
+        cp.mask = mask; cp.mask_stride = mask_stride; cp.counts = nullptr; cp.n_out = n_out;
+        cp.scratch_keys = sc_keys; cp.scratch_rows = sc_rows; cp.only = fallback;
+        cp.lens = n_exc > 0 ? lens : nullptr;
+        k_filter_cascade<<<grid, 1024, 0, st>>>(cp);
+        HQ_LAUNCH_OK("k_filter_cascade");
+        return HQ_OK;
     }
 
     BitsParams bp{};
@@ -1373,23 +2124,7 @@ extern "C" int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, c
 
     CascadeParams cp{};
     cp.bits = bp.bits; cp.words = words; cp.bits_pitch = pitch; cp.idx = idx; cp.N = N; cp.lay = *layout; cp.q_idx = q_idx; cp.Q = Q;
-    for (int l = 0; l < 8; ++l) {
-        cp.ratio[l] = l < L ? ratio[l] : 1.0;
-        // survivors of level l score >= (x*_l + 1) / 2 (up to rounding): offset keys from a little below it
-        float lo = l < L && l < 3 ? (xstar[l] + 1.0f) * 0.5f : 0.f;
-        if (!(lo > 0.f)) lo = 0.f;
-        uint32_t klo;
-        memcpy(&klo, &lo, 4);
-        klo = klo > 64 ? klo - 64 : 0;
-        const float one = 1.0f;
-        uint32_t khi;
-        memcpy(&khi, &one, 4);
-        khi += 64;
-        uint32_t range = khi > klo ? khi - klo : 1, sh_a = 0;
-        while ((range >> sh_a) > 2047u) ++sh_a;
-        cp.key_lo[l] = klo;
-        cp.shift_a[l] = sh_a;
-    }
+    fill_cascade_keys(cp, L, xstar, ratio);
     for (int l = 0; l < 3; ++l) {
         cp.lvl[l] = (lvl_rows && lvl_pitch && l < L) ? lvl_rows[l] : nullptr;
         cp.lvl_pitch[l] = (lvl_rows && lvl_pitch && l < L) ? lvl_pitch[l] : 0;

@@ -86,7 +86,16 @@ struct FtcParams {
     int32_t* seg_n;             // [Q][n_segs] entries produced (may exceed seg_cap: overflow, list invalid)
     int64_t seg_cap;
     int n_segs;
+    int tile_stride;            // sample pass: only every tile_stride-th 64-row tile is visited (no planes are written)
+    const int32_t* unit_only;   // optional [m_tiles]: query tiles with a zero flag are skipped (fallback pass)
+    int32_t* c0_cnt;            // optional [Q]: += rows passing the level-0 threshold (sample pass)
+    // window mode (k_filter_bits_tc<true>): per-query key windows around the predicted ratio cuts
+    const float* win;           // [4][Q] lo1, hi1, lo2, hi2 (dot-product units; window = lo <= k < hi)
+    int32_t* wcnt;              // [4][Q] += c0 | rows above window 1 | of those, k2 >= lo2 | of those, k2 >= hi2 (= alive plane)
 };
+
+constexpr int LBUF_W = 8;                       // window mode: ring of eight entries per array, flushed when full
+constexpr int KSTAGE_BYTES = 8 * EPI_THREADS * 16;   // window mode: k1 / k2 of 16 rows per epilogue thread, 16-byte chunks
 
 __device__ __forceinline__ uint32_t pass_word(const uint32_t (&r)[32], float tq) {
     // bit j = (r[j] >= tq): the sign of (r[j] - tq) is shifted in element by element; four independent
@@ -110,15 +119,175 @@ __device__ __forceinline__ void st_global_256(uint32_t* dst, const uint32_t (&v)
                  : "memory");
 }
 
+
+// One unit (128-query tile x row range) of the epilogue in WINDOW mode.  The ratio cuts of levels 1 and 2 keep a fixed
+// fraction of the rows that pass level 0, so on most data they bind far above the thresholds and ~13 % of all (query, row)
+// pairs used to be appended to the candidate lists only for the cascade to find two cut keys among them.  Here every query
+// carries two key windows [lo1, hi1) and [lo2, hi2) that a sample pass predicted around its cuts (k_filter_predict):
+//   k1 >= hi1 : survives cut 1 for sure           k2 >= hi2 : survives cut 2 for sure
+//   k1 <  lo1 : dropped by cut 1 for sure         k2 <  lo2 : dropped by cut 2 (or fails the threshold) for sure
+// so the pass writes ONE plane (rows alive for sure), four counters per query and appends only the rows inside a window
+// (~1.5 % of the pairs instead of 13 %); the cascade ranks those exactly and checks the prediction against the counters
+// (a query whose cut falls outside its window is redone by the fallback pass).  The five sign tests are bit-mask
+// arithmetic; the rare appends walk the set bits and fetch k1 / k2 from a per-thread staging area in shared memory
+// (register arrays cannot be indexed by a run-time bit position).
+__device__ __forceinline__ void win_unit(const FtcParams& p, int m_tile, int range, int t0, int t1, int q, bool q_ok, bool warp_has_q,
+                                         float tq0, int ew, int half, int q_in, int et, int lane, uint32_t& it, uint32_t tmem_base,
+                                         uint32_t (&vw_next)[3], uint32_t* s_stage, uint32_t* s_lists, uint8_t* s_kstage,
+                                         uint64_t* tfull_bar, uint64_t* tempty_bar) {
+    const float qnan = __int_as_float(0x7fc00000);
+    const float lo1 = q_ok ? __ldg(p.win + (int64_t)0 * p.Q + q) : qnan, hi1 = q_ok ? __ldg(p.win + (int64_t)1 * p.Q + q) : qnan;
+    const float lo2 = q_ok ? __ldg(p.win + (int64_t)2 * p.Q + q) : qnan, hi2 = q_ok ? __ldg(p.win + (int64_t)3 * p.Q + q) : qnan;
+    const bool three = p.L > 2;                                            // two-level layouts (32 x 32 grids) have no cut 2
+    const bool okw = (tq0 == tq0) && (lo1 == lo1) && (hi1 == hi1) && (!three || ((lo2 == lo2) && (hi2 == hi2)));
+    const bool lists = p.l_rows != nullptr && q_ok;
+    const int64_t seg_base = ((int64_t)q * p.n_segs + (range * 2 + half)) * p.seg_cap;
+    const int seg_cap32 = (int)min(p.seg_cap, (int64_t)0x7ffffff0);
+    uint32_t run = 0, flushed = 0;
+    uint32_t c_c0 = 0, c_a1 = 0, c_a1a2 = 0, c_al = 0;
+    uint32_t* const ring = s_lists + et * LBUF_W;                          // [3][EPI_THREADS][LBUF_W]
+    constexpr int RING_W = EPI_THREADS * LBUF_W;
+    float* const kst = reinterpret_cast<float*>(s_kstage + et * 16);       // chunk c at kst + c * EPI_THREADS * 4 floats
+    constexpr int KCH = EPI_THREADS * 4;
+    for (int t = t0; t < t1; ++t, ++it) {
+        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        const int tl = (t - t0) & (TILE_GROUP - 1);
+        uint32_t vw[3];
+#pragma unroll
+        for (int l = 0; l < 3; ++l) vw[l] = vw_next[l];
+        if (t + 1 < t1) {
+#pragma unroll
+            for (int l = 0; l < 3; ++l) vw_next[l] = __ldg(p.valid + (int64_t)l * p.valid_pitch + 2 * (int64_t)(t + 1) * p.tile_stride + half);
+        }
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        if (!warp_has_q) {
+            mbar_arrive(&tempty_bar[acc]);
+            continue;
+        }
+        tc_fence_after();
+        uint32_t r0[32], r1[32], r2[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * ACC_COLS + half * 32;
+        tmem_ld32(taddr, r0);
+        tmem_ld32(taddr + FR, r1);
+        if (three) tmem_ld32(taddr + 2 * FR, r2);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[acc]);
+        // Five sign-test words; classes, counters and the alive word are bit-mask arithmetic, only the window rows (~2 % of
+        // the pairs) are walked bit by bit.  (Tried: two sign tests and a walk over the ~9 % of the pairs that pass level 0
+        // and the lower edge of window 1, classifying them from the staging area: 2.05 ms instead of 1.39 ms per 1024 x 1 M
+        // batch -- a divergent loop runs as long as the lane with the most bits, with a shared-memory load in every turn.)
+        uint32_t alive = 0, E = 0;
+        if (okw) {
+            const uint32_t W0 = pass_word(r0, tq0) & vw[0];
+            const uint32_t A1 = pass_word(r1, lo1) & vw[1], B1 = pass_word(r1, hi1) & A1;
+            uint32_t A2 = 0xffffffffu, B2 = 0xffffffffu;
+            if (three) { A2 = pass_word(r2, lo2) & vw[2]; B2 = pass_word(r2, hi2) & A2; }
+            const uint32_t S1 = W0 & B1;
+            alive = S1 & B2;
+            E = W0 & A1 & (~B1 | (A2 & ~B2));
+            c_c0 += (uint32_t)__popc(W0);
+            c_a1 += (uint32_t)__popc(S1);
+            c_a1a2 += (uint32_t)__popc(S1 & A2);
+            c_al += (uint32_t)__popc(alive);
+        }
+        if (lists && E) {
+            const uint32_t row0 = (uint32_t)t * (uint32_t)p.tile_stride * FR + (uint32_t)half * 32u;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t m = (E >> (16 * h)) & 0xffffu;
+                if (m) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        *reinterpret_cast<uint4*>(kst + c * KCH) = make_uint4(r1[16 * h + 4 * c], r1[16 * h + 4 * c + 1], r1[16 * h + 4 * c + 2], r1[16 * h + 4 * c + 3]);
+                        if (three) *reinterpret_cast<uint4*>(kst + (4 + c) * KCH) = make_uint4(r2[16 * h + 4 * c], r2[16 * h + 4 * c + 1], r2[16 * h + 4 * c + 2], r2[16 * h + 4 * c + 3]);
+                    }
+                    // (two bits per turn with both rows' keys fetched before the first append: 1.46 ms instead of 1.39 ms)
+                    while (m) {
+                        const int j = __ffs((int)m) - 1;
+                        m &= m - 1;
+                        const float* src = kst + (j >> 2) * KCH + (j & 3);
+                        const uint32_t k1b = __float_as_uint(src[0]), k2b = __float_as_uint(src[4 * KCH]);
+                        const uint32_t roww = row0 + 16u * h + (uint32_t)j;
+                        const uint32_t slot = run & (LBUF_W - 1);
+                        ring[slot] = roww;
+                        ring[RING_W + slot] = k1b;
+                        ring[2 * RING_W + slot] = k2b;
+                        ++run;
+                        if ((run & (LBUF_W - 1)) == 0) {                    // ring full: one 32-byte sector per array
+                            if ((int)flushed + 8 <= seg_cap32) {
+                                uint32_t v[3][8];
+#pragma unroll
+                                for (int a = 0; a < 3; ++a) {
+                                    const uint4 x = *reinterpret_cast<const uint4*>(ring + a * RING_W);
+                                    const uint4 y = *reinterpret_cast<const uint4*>(ring + a * RING_W + 4);
+                                    v[a][0] = x.x; v[a][1] = x.y; v[a][2] = x.z; v[a][3] = x.w;
+                                    v[a][4] = y.x; v[a][5] = y.y; v[a][6] = y.z; v[a][7] = y.w;
+                                }
+                                st_global_256(p.l_rows + seg_base + flushed, v[0]);
+                                st_global_256(reinterpret_cast<uint32_t*>(p.l_k1 + seg_base + flushed), v[1]);
+                                if (three) st_global_256(reinterpret_cast<uint32_t*>(p.l_k2 + seg_base + flushed), v[2]);
+                            }
+                            flushed += 8;
+                        }
+                    }
+                }
+            }
+        }
+        s_stage[((tl >> 1) * FM + q_in) * 4 + (tl & 1) * 2 + half] = alive;
+        if (tl == TILE_GROUP - 1 || t == t1 - 1) {
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + ew) : "memory");
+            const int64_t wb = 2 * ((int64_t)(t - tl) * p.tile_stride);
+            const int n_w = 2 * (tl + 1);
+            if (half == 0) {
+                const int qq = ew * 32 + lane;
+                const int gq = m_tile * FM + qq;
+                if (gq < p.Q) {
+                    const uint4 a = *reinterpret_cast<const uint4*>(s_stage + (0 * FM + qq) * 4);
+                    const uint4 b = *reinterpret_cast<const uint4*>(s_stage + (1 * FM + qq) * 4);
+                    const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                    uint32_t* dst = p.bits + (int64_t)gq * p.bits_pitch + wb;
+                    if (p.bits_vec && n_w == 8 && wb + 8 <= p.words) {
+                        st_global_256(dst, v);
+                    } else {
+#pragma unroll
+                        for (int wi = 0; wi < 8; ++wi)
+                            if (wi < n_w && wb + wi < p.words) dst[wi] = v[wi];
+                    }
+                }
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + ew) : "memory");
+        }
+    }
+    if (lists) {
+        for (uint32_t e = flushed; e < run && (int64_t)e < p.seg_cap; ++e) {
+            const uint32_t slot = e & (LBUF_W - 1);
+            p.l_rows[seg_base + e] = ring[slot];
+            p.l_k1[seg_base + e] = __uint_as_float(ring[RING_W + slot]);
+            if (three) p.l_k2[seg_base + e] = __uint_as_float(ring[2 * RING_W + slot]);
+        }
+        p.seg_n[(int64_t)q * p.n_segs + range * 2 + half] = (int)run;
+    }
+    if (q_ok && p.wcnt) {
+        if (c_c0) atomicAdd(p.wcnt + (int64_t)0 * p.Q + q, (int)c_c0);
+        if (c_a1) atomicAdd(p.wcnt + (int64_t)1 * p.Q + q, (int)c_a1);
+        if (c_a1a2) atomicAdd(p.wcnt + (int64_t)2 * p.Q + q, (int)c_a1a2);
+        if (c_al) atomicAdd(p.wcnt + (int64_t)3 * p.Q + q, (int)c_al);
+    }
+}
+
+template <bool WIN>
 __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_constant__ CUtensorMap map_q,
                                                                  const __grid_constant__ CUtensorMap map_db, const FtcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* smem_a = smem;                                        // query tile, resident for a unit
     uint8_t* smem_b = smem + A_BYTES;                              // F_STAGES database tiles
-    uint32_t* s_stage = reinterpret_cast<uint32_t*>(smem_b + F_STAGES * B_STAGE_BYTES);   // [3][2][128][4]
-    uint32_t* s_lists = s_stage + STAGE_WORDS;                                            // [3][EPI_THREADS][LBUF], 16-byte chunks swizzled
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_lists + 3 * LBUF * EPI_THREADS);
+    uint32_t* s_stage = reinterpret_cast<uint32_t*>(smem_b + F_STAGES * B_STAGE_BYTES);   // [3][2][128][4] ([1][2][128][4] in window mode)
+    uint32_t* s_lists = s_stage + (WIN ? STAGE_WORDS / 3 : STAGE_WORDS);                  // [3][EPI_THREADS][LBUF], 16-byte chunks swizzled
+    // window mode: [3][EPI_THREADS][LBUF_W] rings, then the k1 / k2 staging area [8][EPI_THREADS][4]
+    uint8_t* s_kstage = reinterpret_cast<uint8_t*>(s_lists + 3 * LBUF_W * EPI_THREADS);
+    uint64_t* bars = WIN ? reinterpret_cast<uint64_t*>(s_kstage + KSTAGE_BYTES) : reinterpret_cast<uint64_t*>(s_lists + 3 * LBUF * EPI_THREADS);
     uint64_t* full_bar = bars;                      // [F_STAGES]
     uint64_t* empty_bar = bars + F_STAGES;          // [F_STAGES]
     uint64_t* tfull_bar = bars + 2 * F_STAGES;      // [2]
@@ -152,18 +321,20 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
         // ================= TMA producer =================
         if (elect_one()) {
             uint32_t stage = 0, phase = 0, uq = 0;
-            for (int u = blockIdx.x; u < p.num_units; u += gridDim.x, ++uq) {
+            for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
                 const int m_tile = u % p.m_tiles, range = u / p.m_tiles;
+                if (p.unit_only && !__ldg(p.unit_only + m_tile)) continue;
                 const int t0 = range * p.tiles_per_range;
                 const int t1 = min(p.n_tiles, t0 + p.tiles_per_range);
                 mbar_wait_relaxed(qempty_bar, (uq & 1u) ^ 1u);                  // MMAs of the previous unit have retired
+                ++uq;
                 mbar_expect_tx(qfull_bar, (uint32_t)p.n_slabs * A_SLAB_BYTES);
                 for (int s = 0; s < p.n_slabs; ++s) tma_load_2d(&map_q, qfull_bar, smem_a + s * A_SLAB_BYTES, s * 32, m_tile * FM);
                 for (int t = t0; t < t1; ++t) {
                     mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], (uint32_t)p.n_slabs * B_SLAB_BYTES);
                     for (int s = 0; s < p.n_slabs; ++s)
-                        tma_load_2d(&map_db, &full_bar[stage], smem_b + stage * B_STAGE_BYTES + s * B_SLAB_BYTES, s * 32, t * FR);
+                        tma_load_2d(&map_db, &full_bar[stage], smem_b + stage * B_STAGE_BYTES + s * B_SLAB_BYTES, s * 32, t * p.tile_stride * FR);
                     if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -171,11 +342,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
     } else if (warp == 1) {
         // ================= MMA issuer =================
         uint32_t stage = 0, phase = 0, it = 0, uq = 0;
-        for (int u = blockIdx.x; u < p.num_units; u += gridDim.x, ++uq) {
+        for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
             const int range = u / p.m_tiles;
+            if (p.unit_only && !__ldg(p.unit_only + u % p.m_tiles)) continue;
             const int t0 = range * p.tiles_per_range;
             const int t1 = min(p.n_tiles, t0 + p.tiles_per_range);
             mbar_wait_relaxed(qfull_bar, uq & 1u);
+            ++uq;
             tc_fence_after();
             for (int t = t0; t < t1; ++t, ++it) {
                 const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
@@ -213,6 +386,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
         uint32_t it = 0;
         for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
             const int m_tile = u % p.m_tiles, range = u / p.m_tiles;
+            if (p.unit_only && !__ldg(p.unit_only + m_tile)) continue;
             const int t0 = range * p.tiles_per_range;
             const int t1 = min(p.n_tiles, t0 + p.tiles_per_range);
             const int q = m_tile * FM + q_in;
@@ -242,7 +416,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
             const uint32_t sl_addr_x = sl_addr ^ swz16;
             uint32_t vw_next[3];
 #pragma unroll
-            for (int l = 0; l < 3; ++l) vw_next[l] = (l < p.L && t0 < t1) ? __ldg(p.valid + (int64_t)l * p.valid_pitch + 2 * t0 + half) : 0u;
+            for (int l = 0; l < 3; ++l) vw_next[l] = (l < p.L && t0 < t1) ? __ldg(p.valid + (int64_t)l * p.valid_pitch + 2 * (int64_t)t0 * p.tile_stride + half) : 0u;
+            if constexpr (WIN) {
+                win_unit(p, m_tile, range, t0, t1, q, q_ok, warp_has_q, tq[0], ew, half, q_in, et, lane, it, tmem_base, vw_next, s_stage, s_lists, s_kstage,
+                         tfull_bar, tempty_bar);
+                continue;
+            }
+            uint32_t c0_acc = 0;
             for (int t = t0; t < t1; ++t, ++it) {
                 const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
                 const int tl = (t - t0) & (TILE_GROUP - 1);
@@ -251,7 +431,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
                 for (int l = 0; l < 3; ++l) vw[l] = vw_next[l];
                 if (t + 1 < t1) {                        // the next tile's validity words travel during this tile
 #pragma unroll
-                    for (int l = 0; l < 3; ++l) vw_next[l] = l < p.L ? __ldg(p.valid + (int64_t)l * p.valid_pitch + 2 * (t + 1) + half) : 0u;
+                    for (int l = 0; l < 3; ++l) vw_next[l] = l < p.L ? __ldg(p.valid + (int64_t)l * p.valid_pitch + 2 * (int64_t)(t + 1) * p.tile_stride + half) : 0u;
                 }
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 if (!warp_has_q) {                       // no query in this warp's 32 rows of the tile: release the accumulator, nothing to test
@@ -269,6 +449,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
                 mbar_arrive(&tempty_bar[acc]);           // the values are in registers: the accumulators are free
                 uint32_t w0 = pass_word(r0, tq[0]) & vw[0], w1 = 0, w2 = 0;
                 if (!(tq[0] == tq[0])) w0 = 0;
+                c0_acc += (uint32_t)__popc(w0);
                 s_stage[((0 * 2 + (tl >> 1)) * FM + q_in) * 4 + (tl & 1) * 2 + half] = w0;
                 if (p.L > 1) {
                     w1 = pass_word(r1, tq[1]) & vw[1];
@@ -287,7 +468,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
                     // (partial-sector writes are read-modify-write in the ECC-protected L2).
                     const uint32_t t1w = w0 & w1;
                     if (t1w) {
-                        const uint32_t row0 = (uint32_t)t * FR + (uint32_t)half * 32u;
+                        const uint32_t row0 = (uint32_t)t * (uint32_t)p.tile_stride * FR + (uint32_t)half * 32u;
                         uint32_t run = (uint32_t)seg_pos << 2;         // entry counter in bytes of one ring array
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
@@ -336,7 +517,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
                         }
                     }
                 }
-                if (tl == TILE_GROUP - 1 || t == t1 - 1) {
+                if (p.bits && (tl == TILE_GROUP - 1 || t == t1 - 1)) {
                     // the two warps that share a TMEM lane quarter (row halves 0 and 1 of the same 32 queries) write
                     // those queries' words out between themselves: a 64-thread named barrier instead of all 256
                     asm volatile("bar.sync %0, 64;" ::"r"(1 + ew) : "memory");
@@ -374,6 +555,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
                 }
                 p.seg_n[(int64_t)q * p.n_segs + range * 2 + half] = seg_pos;
             }
+            if (p.c0_cnt && q_ok && c0_acc) atomicAdd(p.c0_cnt + q, (int)c0_acc);
         }
     }
     tc_fence_before();
@@ -453,9 +635,9 @@ __global__ void __launch_bounds__(256) k_valid_bits(const float* __restrict__ rn
     }
 }
 
-void plan_units(int64_t N, int Q, int sms, FtcParams& p) {
+void plan_units(int64_t n_tiles, int Q, int sms, FtcParams& p) {
     p.m_tiles = (Q + FM - 1) / FM;
-    p.n_tiles = (int)((N + FR - 1) / FR);
+    p.n_tiles = (int)n_tiles;
     int best_tp = p.n_tiles;
     double best_eff = -1.0;
     for (int waves = 1; waves <= 4; ++waves) {
@@ -521,9 +703,92 @@ extern "C" int hq_filter_tc_valid(const float* rnorm, int64_t N, const hq_index_
 extern "C" int hq_filter_tc_plan(int64_t N, int Q, int* n_ranges, int* tiles_per_range) {
     HQ_REQUIRE(N > 0 && Q > 0 && n_ranges && tiles_per_range, "bad arguments");
     FtcParams p{};
-    plan_units(N, Q, hq_cached_sm_count(), p);
+    plan_units((N + FR - 1) / FR, Q, hq_cached_sm_count(), p);
     *n_ranges = p.n_ranges;
     *tiles_per_range = p.tiles_per_range;
+    return HQ_OK;
+}
+
+// the same for a pass that visits every tile_stride-th 64-row tile (sample pass)
+int hq_filter_tc_plan_strided(int64_t N, int Q, int tile_stride, int* n_ranges, int* tiles_per_range) {
+    HQ_REQUIRE(N > 0 && Q > 0 && tile_stride >= 1 && n_ranges && tiles_per_range, "bad arguments");
+    FtcParams p{};
+    const int64_t tiles = (N + FR - 1) / FR;
+    plan_units((tiles + tile_stride - 1) / tile_stride, Q, hq_cached_sm_count(), p);
+    *n_ranges = p.n_ranges;
+    *tiles_per_range = p.tiles_per_range;
+    return HQ_OK;
+}
+
+// Query-side preparation of a batch: packed operand [Q, 128], thresholds tq [3, Q] and level norms nq [3, Q].
+int hq_filter_tc_prepare(const hq_index_layout* layout, const float* q_idx, int Q, const float* xstar, float* q_packed, float* tq,
+                         float* nq, cudaStream_t st) {
+    Segs s;
+    HQ_REQUIRE(make_segs(layout, s), "index layout not supported by the tensor-core filter");
+    HQ_REQUIRE(q_idx && q_packed && tq && nq && xstar, "null pointer");
+    int rc = hq_filter_tc_pack(q_idx, nullptr, Q, layout, 1, q_packed, st);
+    if (rc != HQ_OK) return rc;
+    k_query_tq<<<(Q * layout->L + 255) / 256, 256, 0, st>>>(q_idx, Q, *layout, xstar[0], layout->L > 1 ? xstar[1] : 0.f,
+                                                            layout->L > 2 ? xstar[2] : 0.f, tq, nq);
+    HQ_LAUNCH_OK("k_query_tq");
+    return HQ_OK;
+}
+
+// The threshold pass over a prepared batch.  bits may be null (sample pass: lists and the level-0 count only); `o`
+// selects the sample stride, the query-tile subset and the window mode (see FtcParams).
+int hq_filter_tc_pass(const float* db_packed, const uint32_t* valid, int64_t valid_pitch, int64_t N, const hq_index_layout* layout, int Q,
+                      const float* q_packed, const float* tq, uint32_t* bits, int64_t bits_pitch, const HqFilterLists* lists,
+                      const HqFtcOpts* o, cudaStream_t st) {
+    Segs s;
+    HQ_REQUIRE(make_segs(layout, s), "index layout not supported by the tensor-core filter");
+    HQ_REQUIRE(db_packed && valid && q_packed && tq, "null pointer");
+    HQ_REQUIRE((reinterpret_cast<uintptr_t>(db_packed) & 15) == 0 && (reinterpret_cast<uintptr_t>(q_packed) & 15) == 0,
+               "packed operands must be 16-byte aligned");
+    HQ_REQUIRE(valid_pitch >= hq_filter_tc_valid_pitch(N), "valid pitch too small");
+    const int64_t words = (N + 31) / 32;
+    HQ_REQUIRE(!bits || bits_pitch >= words, "bit plane pitch too small");
+    const int stride = o && o->tile_stride > 1 ? o->tile_stride : 1;
+    const bool win = o && o->win;
+    HQ_REQUIRE(!(stride > 1 && bits), "the sample pass does not write planes");
+    HQ_REQUIRE(!win || (s.L >= 2 && stride == 1 && bits && o->wcnt && lists && lists->rows && (s.L < 3 || lists->k2)),
+               "window mode needs two or three levels, a plane, counters and lists");
+
+    FtcParams p{};
+    p.N = N; p.Q = Q; p.L = s.L; p.n_slabs = s.n_slabs;
+    for (int l = 0; l < 3; ++l) { p.seg_off[l] = s.off[l]; p.ksteps[l] = 3 * s.kp[l] / 8; }
+    p.tq = tq; p.valid = valid; p.valid_pitch = valid_pitch; p.bits = bits; p.words = words; p.bits_pitch = bits_pitch;
+    p.bits_vec = (bits && (reinterpret_cast<uintptr_t>(bits) & 31) == 0 && bits_pitch % 8 == 0) ? 1 : 0;
+    p.tile_stride = stride;
+    if (o) { p.unit_only = o->unit_only; p.c0_cnt = o->c0_cnt; p.win = o->win; p.wcnt = o->wcnt; }
+    const int64_t tiles = (N + FR - 1) / FR;
+    plan_units((tiles + stride - 1) / stride, Q, hq_cached_sm_count(), p);
+    if (lists && lists->rows) {
+        HQ_REQUIRE(lists->n_segs >= 2 * p.n_ranges && lists->n_segs <= 2 * p.n_ranges + 1 && lists->seg_cap > 0 && lists->seg_cap % 8 == 0 &&
+                       lists->k1 && lists->seg_n && (s.L < 3 || lists->k2),
+                   "candidate list geometry does not match hq_filter_tc_plan");
+        p.l_rows = lists->rows; p.l_k1 = lists->k1; p.l_k2 = lists->k2; p.seg_n = lists->seg_n; p.seg_cap = lists->seg_cap;
+        p.n_segs = lists->n_segs;
+    }
+    CUtensorMap mq, mdb;
+    int rc = make_map_2d(&mq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, q_packed, Q, KS, KS, 32, FM);
+    if (rc != HQ_OK) return rc;
+    rc = make_map_2d(&mdb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, db_packed, N, KS, KS, 32, FR);
+    if (rc != HQ_OK) return rc;
+    const size_t smem_full = 1024 + A_BYTES + F_STAGES * B_STAGE_BYTES + (STAGE_WORDS + 3 * LBUF * EPI_THREADS) * sizeof(uint32_t) +
+                             (2 * F_STAGES + 6) * sizeof(uint64_t) + 16;
+    const size_t smem_win = 1024 + A_BYTES + F_STAGES * B_STAGE_BYTES + (STAGE_WORDS / 3 + 3 * LBUF_W * EPI_THREADS) * sizeof(uint32_t) +
+                            KSTAGE_BYTES + (2 * F_STAGES + 6) * sizeof(uint64_t) + 16;
+    static bool attr = false;
+    if (!attr) {
+        HQ_CUDA_OK(cudaFuncSetAttribute(k_filter_bits_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_full));
+        HQ_CUDA_OK(cudaFuncSetAttribute(k_filter_bits_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_win));
+        attr = true;
+    }
+    int grid = hq_cached_sm_count();
+    if (grid > p.num_units) grid = p.num_units;
+    if (win) k_filter_bits_tc<true><<<grid, F_THREADS, smem_win, st>>>(mq, mdb, p);
+    else k_filter_bits_tc<false><<<grid, F_THREADS, smem_full, st>>>(mq, mdb, p);
+    HQ_LAUNCH_OK("k_filter_bits_tc");
     return HQ_OK;
 }
 
@@ -532,47 +797,8 @@ extern "C" int hq_filter_tc_plan(int64_t N, int Q, int* n_ranges, int* tiles_per
 int hq_filter_bits_tc_launch(const float* db_packed, const uint32_t* valid, int64_t valid_pitch, int64_t N,
                              const hq_index_layout* layout, const float* q_idx, int Q, const float* xstar, float* q_packed,
                              float* tq, float* nq, uint32_t* bits, int64_t bits_pitch, const HqFilterLists* lists, cudaStream_t st) {
-    Segs s;
-    HQ_REQUIRE(make_segs(layout, s), "index layout not supported by the tensor-core filter");
-    HQ_REQUIRE(db_packed && valid && q_idx && q_packed && tq && nq && bits, "null pointer");
-    HQ_REQUIRE((reinterpret_cast<uintptr_t>(db_packed) & 15) == 0 && (reinterpret_cast<uintptr_t>(q_packed) & 15) == 0,
-               "packed operands must be 16-byte aligned");
-    HQ_REQUIRE(valid_pitch >= hq_filter_tc_valid_pitch(N), "valid pitch too small");
-    const int64_t words = (N + 31) / 32;
-    HQ_REQUIRE(bits_pitch >= words, "bit plane pitch too small");
-    int rc = hq_filter_tc_pack(q_idx, nullptr, Q, layout, 1, q_packed, st);
+    HQ_REQUIRE(bits, "null pointer");
+    int rc = hq_filter_tc_prepare(layout, q_idx, Q, xstar, q_packed, tq, nq, st);
     if (rc != HQ_OK) return rc;
-    k_query_tq<<<(Q * layout->L + 255) / 256, 256, 0, st>>>(q_idx, Q, *layout, xstar[0], layout->L > 1 ? xstar[1] : 0.f,
-                                                            layout->L > 2 ? xstar[2] : 0.f, tq, nq);
-    HQ_LAUNCH_OK("k_query_tq");
-
-    FtcParams p{};
-    p.N = N; p.Q = Q; p.L = s.L; p.n_slabs = s.n_slabs;
-    for (int l = 0; l < 3; ++l) { p.seg_off[l] = s.off[l]; p.ksteps[l] = 3 * s.kp[l] / 8; }
-    p.tq = tq; p.valid = valid; p.valid_pitch = valid_pitch; p.bits = bits; p.words = words; p.bits_pitch = bits_pitch;
-    p.bits_vec = ((reinterpret_cast<uintptr_t>(bits) & 31) == 0 && bits_pitch % 8 == 0) ? 1 : 0;
-    plan_units(N, Q, hq_cached_sm_count(), p);
-    if (lists && lists->rows) {
-        HQ_REQUIRE(lists->n_segs >= 2 * p.n_ranges && lists->n_segs <= 2 * p.n_ranges + 1 && lists->seg_cap > 0 && lists->k1 && lists->seg_n && (s.L < 3 || lists->k2),
-                   "candidate list geometry does not match hq_filter_tc_plan");
-        p.l_rows = lists->rows; p.l_k1 = lists->k1; p.l_k2 = lists->k2; p.seg_n = lists->seg_n; p.seg_cap = lists->seg_cap;
-        p.n_segs = lists->n_segs;
-    }
-    CUtensorMap mq, mdb;
-    rc = make_map_2d(&mq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, q_packed, Q, KS, KS, 32, FM);
-    if (rc != HQ_OK) return rc;
-    rc = make_map_2d(&mdb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, db_packed, N, KS, KS, 32, FR);
-    if (rc != HQ_OK) return rc;
-    const size_t smem = 1024 + A_BYTES + F_STAGES * B_STAGE_BYTES + (STAGE_WORDS + 3 * LBUF * EPI_THREADS) * sizeof(uint32_t) +
-                        (2 * F_STAGES + 6) * sizeof(uint64_t) + 16;
-    static bool attr = false;
-    if (!attr) {
-        HQ_CUDA_OK(cudaFuncSetAttribute(k_filter_bits_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
-    int grid = hq_cached_sm_count();
-    if (grid > p.num_units) grid = p.num_units;
-    k_filter_bits_tc<<<grid, F_THREADS, smem, st>>>(mq, mdb, p);
-    HQ_LAUNCH_OK("k_filter_bits_tc");
-    return HQ_OK;
+    return hq_filter_tc_pass(db_packed, valid, valid_pitch, N, layout, Q, q_packed, tq, bits, bits_pitch, lists, nullptr, st);
 }

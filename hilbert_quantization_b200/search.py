@@ -611,7 +611,8 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
             qc = max(128, (qc // 2 + 127) // 128 * 128)
     need_scores = not (rerank == "bf16" and (fast or not use_filter))
     scores = torch.empty((qc, N), dtype=torch.float32, device=d) if need_scores else None
-    mask = torch.zeros((qc, words), dtype=torch.int32, device=d)
+    # rows padded to whole 32-byte sectors: the window pass of the fast filter then writes its plane straight into the mask
+    mask = torch.zeros((qc, (words + 7) // 8 * 8), dtype=torch.int32, device=d)[:, :words]
     masks = [] if return_mask else None
     with torch.cuda.device(d):
         for s in range(0, Q, qc):

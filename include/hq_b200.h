@@ -181,6 +181,15 @@ int hq_filter_fast_supported(const hq_index_layout* layout);
 int hq_filter_level_norms(const float* idx, const uint16_t* lens, int64_t N, const hq_index_layout* layout,
                           float* rnorm, int32_t* nonuniform, void* stream);
 int64_t hq_filter_fast_scratch_bytes(int64_t N, int Q, const hq_index_layout* layout);
+/* Diagnostics: which variant hq_filter_fast runs for (N, Q) with a packed tensor-core operand and no `counts`
+ * (2 = window mode: sample pass + predicted cut windows, 1 = full candidate lists, 0 = planes + generic cascade), and the
+ * byte offset inside `scratch` of the int32 [Q] flags of the queries that were redone by the per-query fallback. */
+int hq_filter_fast_mode(int64_t N, int Q, const hq_index_layout* layout);
+int64_t hq_filter_fast_fallback_offset(int64_t N, int Q, const hq_index_layout* layout);
+/* Window mode only: byte offsets inside `scratch` (a 128-byte aligned buffer) of out[0] the alive plane, out[1] the
+ * windows float [4][Q], out[2] the counters int32 [4][Q], out[3] the sample's level-0 counts, out[4] prediction flags,
+ * out[5] fallback tile flags, out[6] the segment counts int32 [Q][out[7]]; out[8] = segment capacity, out[9] = sample stride. */
+int hq_filter_fast_window_layout(int64_t N, int Q, const hq_index_layout* layout, int64_t* out);
 /* lvl_rows / lvl_pitch: optional HOST arrays [L] of device pointers / pitches of per-level
  * copies [N, pitch] of the index rows (pitch % 4 == 0); they are small enough to stay in the
  * 126 MB L2 while every query re-ranks its candidates. */

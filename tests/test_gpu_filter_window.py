@@ -1,0 +1,120 @@
+"""GPU: window mode of the fast filter (sample pass -> predicted cut windows -> window pass -> exact ranking of the window
+rows, csrc/hq_filter_fast.cu "Window mode") against the exact per-level path (rag/search/engine.py:178-287)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hq():
+    import hilbert_quantization_b200 as m
+    return m
+
+
+def _fallbacks(hq, d, Q):
+    from hilbert_quantization_b200._lib import lib
+    off = int(lib.hq_filter_fast_fallback_offset(d.N, Q, C.byref(d.layout)))
+    return d._filter_scratch[off: off + 4 * Q].view(torch.int32).clone()
+
+
+def _mode(hq, d, Q):
+    from hilbert_quantization_b200._lib import lib
+    return int(lib.hq_filter_fast_mode(d.N, Q, C.byref(d.layout)))
+
+
+def _compare(hq, db, qs, max_fallbacks=None, borderline=2):
+    from hilbert_quantization_b200.search import unpack_mask
+    N, Q = db.shape[0], qs.shape[0]
+    d = hq.EmbeddingDatabase(db)
+    assert d.fast_filter_ok and d.tc_packed is not None
+    assert _mode(hq, d, Q) == 2, "window mode expected for this shape"
+    i_f, s_f, m_f = hq.search_batch(d, qs, 10, return_mask=True, filter_impl="fast")
+    fb = _fallbacks(hq, d, Q).cpu().numpy()
+    i_e, s_e, m_e = hq.search_batch(d, qs, 10, return_mask=True, filter_impl="exact")
+    a_f, a_e = unpack_mask(m_f, N), unpack_mask(m_e, N)
+    same = (a_f == a_e).all(axis=1)
+    # the tensor-core pass and the exact path round the threshold / cut scores differently: a few borderline queries
+    # may differ by single rows (same rule as tests/test_gpu_filter_fast.py)
+    assert same.sum() >= Q - borderline, f"{(~same).sum()} of {Q} queries differ; fallbacks {fb.sum()}"
+    for j in np.nonzero(~same)[0]:
+        assert (a_f[j] != a_e[j]).sum() <= 2, (j, int((a_f[j] != a_e[j]).sum()), int(a_f[j].sum()), int(a_e[j].sum()))
+    ok = torch.from_numpy(same).cuda()
+    assert torch.equal(i_f[ok], i_e[ok]) and torch.equal(s_f[ok], s_e[ok])
+    if max_fallbacks is not None:
+        assert fb.sum() <= max_fallbacks, f"{fb.sum()} of {Q} queries fell back to the generic cascade"
+    return fb
+
+
+@pytest.mark.parametrize("N,D,Q", [(150000, 1536, 40), (200000, 768, 33), (140000, 1024, 130), (260000, 1536, 17)])
+def test_window_mode_equals_exact_filter_on_random_rows(hq, N, D, Q):
+    rng = np.random.default_rng(N + D + Q)
+    db = rng.standard_normal((N, D)).astype(np.float32)
+    qs = rng.standard_normal((Q, D)).astype(np.float32)
+    qs[: Q // 2] = db[: Q // 2] + 0.1 * rng.standard_normal((Q // 2, D)).astype(np.float32)
+    db[N // 3] = db[5]
+    db[N - 2] = db[5]
+    qs[0] = db[5]
+    _compare(hq, db, qs, max_fallbacks=1)          # the windows hold for (almost) every query: no silent slow path
+
+
+def test_window_mode_with_exceptional_rows(hq):
+    N, D, Q = 150000, 768, 24
+    rng = np.random.default_rng(77)
+    db = rng.standard_normal((N, D)).astype(np.float32)
+    qs = rng.standard_normal((Q, D)).astype(np.float32)
+    tail = D - D // 12
+    for r in (17, 18, N // 2, N - 1, 99999):
+        db[r, tail:] = 0.0
+    db[40, D // 2:] = 0.0
+    qs[3] = db[17] + 0.01 * rng.standard_normal(D).astype(np.float32)
+    qs[3, tail:] = db[17, tail:] + 0.05
+    _compare(hq, db, qs, max_fallbacks=1)
+
+
+@pytest.mark.parametrize("offset", [0.03, 0.04])
+def test_window_mode_when_the_cuts_bind_deep(hq, offset):
+    """N(offset, 1) rows: nearly every row passes the coarse thresholds, both ratio cuts bind in the middle of the lists."""
+    N, D, Q = 180000, 1536, 24
+    rng = np.random.default_rng(int(offset * 1000))
+    db = (rng.standard_normal((N, D)) + offset).astype(np.float32)
+    qs = (rng.standard_normal((Q, D)) + offset).astype(np.float32)
+    db[N // 3] = db[5]
+    qs[0] = db[5]
+    _compare(hq, db, qs)          # queries whose level-0 cut binds take the fallback by design
+
+
+def test_window_mode_positive_rows_take_the_fallback(hq):
+    """All-positive rows: the level-0 ratio cut binds for every query (exact selection over the whole shard): every query
+    is flagged by the window cascade and redone by the fallback pass; results still equal the exact path."""
+    N, D, Q = 140000, 768, 19
+    rng = np.random.default_rng(3)
+    db = (rng.random((N, D)) + 0.25).astype(np.float32)
+    qs = (rng.random((Q, D)) + 0.25).astype(np.float32)
+    fb = _compare(hq, db, qs)
+    assert fb.sum() == Q
+
+
+def test_window_mode_on_clustered_rows_in_cluster_order(hq):
+    """Rows stored cluster by cluster: the tile sample is as unrepresentative as it gets, windows may miss -> fallback,
+    never a wrong survivor set."""
+    N, D, Q = 160000, 1536, 32
+    rng = np.random.default_rng(11)
+    centers = rng.standard_normal((160, D)).astype(np.float32)
+    db = (np.repeat(centers, N // 160, axis=0) + 0.7 * rng.standard_normal((N, D))).astype(np.float32)
+    qs = (centers[rng.integers(0, 160, Q)] + 0.7 * rng.standard_normal((Q, D))).astype(np.float32)
+    _compare(hq, db, qs, borderline=3)
+
+
+def test_window_mode_many_duplicates(hq):
+    """Blocks of identical rows: keys tie exactly inside the windows, the cut falls inside a tie group (ties -> lower id)."""
+    N, D, Q = 140000, 768, 20
+    rng = np.random.default_rng(5)
+    base = rng.standard_normal((N // 20, D)).astype(np.float32)
+    db = np.tile(base, (20, 1))
+    qs = rng.standard_normal((Q, D)).astype(np.float32)
+    qs[0] = base[3]
+    _compare(hq, db, qs)
