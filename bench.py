@@ -487,10 +487,17 @@ def main():
         db = hq.EmbeddingDatabase(emb, n=n, device=device, id_base=lo)
     torch.cuda.synchronize()
 
-    def step(queries):
+    # N > 1: the all-gather + merge of batch i runs on a communication stream under the search of batch i + 1
+    # (hq.distributed.MergePipeline); `wait` makes the main stream wait for it (latency measurements, the last batch)
+    from hilbert_quantization_b200.distributed import MergePipeline
+    pipe = MergePipeline(device) if world > 1 else None
+
+    def step(queries, wait=True):
         ids, sc = hq.search_batch(db, queries, args.k)
         if world > 1:
-            ids, sc = allgather_merge(ids, sc, args.k)
+            ids, sc, _ = pipe.submit(ids, sc, args.k)
+            if wait:
+                pipe.drain()
         return ids, sc
 
     def barrier():
@@ -512,9 +519,11 @@ def main():
         for _ in range(args.steps):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            step(q_dev)
+            step(q_dev, wait=False)
             e1.record()
             step_ms.append((e0, e1))
+        if pipe is not None:
+            pipe.drain()                              # the timed region ends when the last batch's merged result exists
         t_all1.record()
         barrier()
     total_ms = t_all0.elapsed_time(t_all1)
@@ -541,13 +550,14 @@ def main():
     # host memory and reads its ids / scores back on the host; the copy of step i + 1 runs on a copy stream under the search
     # of step i (two slots), the host consumes step i's results while step i + 1 runs.
     post = (lambda i_, s_: allgather_merge(i_, s_, args.k)) if world > 1 else None
+    post_stream = pipe.stream if pipe is not None else None
 
     e2e_stamps = []
 
     def e2e_run(n_steps):
         acc = 0.0
         e2e_stamps.clear()
-        for ids_h, sc_h in hq.search_stream(db, (q_pinned for _ in range(n_steps)), args.k, post=post):
+        for ids_h, sc_h in hq.search_stream(db, (q_pinned for _ in range(n_steps)), args.k, post=post, post_stream=post_stream):
             out_ids.copy_(ids_h)
             out_sc.copy_(sc_h)
             acc += float(out_sc[0, 0])

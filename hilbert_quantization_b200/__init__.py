@@ -13,6 +13,6 @@ from .search import (EmbeddingDatabase, ProgressiveSimilaritySearchEngine, RAGSe
 from .rag import DocumentSearchResult, ProgressiveSearchEngine, RAGSystem    # noqa: F401
 from .precomputed import PrecomputedHilbertIndexer, PrecomputedIndex, PrecomputedLevel   # noqa: F401
 from . import video                                                       # noqa: F401
-from .distributed import ShardedSearch, allgather_merge, shard_bounds        # noqa: F401
+from .distributed import MergePipeline, ShardedSearch, allgather_merge, shard_bounds        # noqa: F401
 
 __version__ = "0.1.0"

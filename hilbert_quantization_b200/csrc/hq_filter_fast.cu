@@ -568,10 +568,10 @@ __device__ __forceinline__ void find_cut_bin(const uint32_t* hist, uint32_t drop
     // ~4 us per call with every other warp parked at the barrier, 10 % of the kernel on a 125 K-row shard.
     __shared__ uint32_t s_scan[32];
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
-    const int per = 2048 / nt;
-    uint32_t v[8], sum = 0;
+    const int per = 2048 / nt;                         // <= 16: blockDim.x >= 128
+    uint32_t v[16], sum = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 16; ++i) {
         v[i] = i < per ? hist[tid * per + i] : 0u;
         sum += v[i];
     }
@@ -598,7 +598,7 @@ __device__ __forceinline__ void find_cut_bin(const uint32_t* hist, uint32_t drop
     if (excl < drop && drop <= excl + sum) {
         uint32_t below = excl;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 16; ++i) {
             if (i < per && below < drop) {
                 if (below + v[i] >= drop) { sh[0] = (uint32_t)(tid * per + i); sh[1] = drop - below; sh[2] = v[i]; }
                 below += v[i];
@@ -1209,7 +1209,7 @@ __device__ __forceinline__ void window_from_suffix(const uint32_t* suffix, float
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) k_filter_predict(const PredictParams p) {
+__global__ void __launch_bounds__(256, 4) k_filter_predict(const PredictParams p) {
     __shared__ uint32_t hist[2048];
     __shared__ uint32_t suffix[2048];
     __shared__ uint32_t s_scan[8];
@@ -1350,9 +1350,9 @@ struct WinParams {
     int64_t tmp_stride;
 };
 
-constexpr int kWinThreads = 256;
+constexpr int kWinThreads = 128;      // eight CTAs per SM: 1184 queries in flight, a 1024-query batch is ONE wave
 constexpr int kWinCutCap = 1024;      // cut-bin members ranked in shared memory (window histograms are fine grained)
-constexpr int kWinCtasPerSm = 4;      // 64 registers per thread (7 CTAs per SM = one wave of 1024 queries would leave 32: spills)
+constexpr int kWinCtasPerSm = 8;      // 64 registers per thread (256-thread CTAs: 4 per SM = 592 queries in flight, two waves)
 
 __global__ void __launch_bounds__(kWinThreads, kWinCtasPerSm) k_filter_cascade_win(const WinParams p) {
     __shared__ uint32_t hist[2048];
@@ -1364,6 +1364,7 @@ __global__ void __launch_bounds__(kWinThreads, kWinCtasPerSm) k_filter_cascade_w
     __shared__ float b_k2[kWinCutCap];
     __shared__ uint32_t s_bufn, s_flag, s_R, s_n2, s_x1, s_x2;
     __shared__ float s_K;
+    __shared__ int32_t s_goff[kMaxSegs + 1];          // exclusive prefix of the segments' 4-entry groups
     const int tid = threadIdx.x, nt = blockDim.x;
     float* const c_k2 = p.tmp_keys + (int64_t)blockIdx.x * p.tmp_stride;
     uint32_t* const c_row = p.tmp_rows + (int64_t)blockIdx.x * p.tmp_stride;
@@ -1423,56 +1424,88 @@ __global__ void __launch_bounds__(kWinThreads, kWinCtasPerSm) k_filter_cascade_w
         const uint32_t* const L_rows = p.l_rows + qbase;
         const float* const L_k1 = p.l_k1 + qbase;
         const float* const L_k2 = three ? p.l_k2 + qbase : nullptr;
-        // every listed entry of the query: visit(k1, token).  A warp owns one segment at a time and keeps four loads per
-        // lane in flight (a block-wide loop over one short segment after the other was a chain of ~40 DRAM round trips
-        // per pass).
-        const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+        // every listed entry of the query: visit(k1, token).  The entries are walked as 4-entry groups (segments are
+        // 128-byte aligned) numbered across ALL segments, so that a thread's loads are independent and in flight together:
+        // a loop over one short segment after the other (per block, then per warp) was a chain of 20-40 DRAM round trips
+        // per pass -- the whole kernel at small shards.
+        const int lane = tid & 31;
+        if (tid < 32) {
+            const int per = (p.n_segs + 31) / 32;
+            int sum = 0;
+            for (int i = 0; i < per; ++i) { const int sg = lane * per + i; if (sg < p.n_segs) sum += (s_cnt[sg] + 3) >> 2; }
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            int run = incl - sum;
+            for (int i = 0; i < per; ++i) {
+                const int sg = lane * per + i;
+                if (sg < p.n_segs) { s_goff[sg] = run; run += (s_cnt[sg] + 3) >> 2; }
+            }
+            if (lane == 31) s_goff[p.n_segs] = incl;
+        }
+        __syncthreads();
+        const int n_groups = s_goff[p.n_segs];
+        // group g -> (offset of its first entry inside the query's arrays, entries in it)
+        auto locate = [&](int g, uint32_t& off, uint32_t& n) {
+            int lo = 0, hi = p.n_segs;                               // last segment whose first group is <= g
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_goff[mid] <= g) lo = mid; else hi = mid;
+            }
+            const uint32_t e = (uint32_t)(g - s_goff[lo]) * 4u;
+            off = (uint32_t)lo * (uint32_t)p.seg_cap + e;
+            n = min(4u, (uint32_t)s_cnt[lo] - e);
+        };
         auto each_all = [&](auto visit) {
-            for (int sgi = warp; sgi < p.n_segs; sgi += nw) {
-                const uint32_t cnt = (uint32_t)s_cnt[sgi];
-                const uint32_t off = (uint32_t)sgi * (uint32_t)p.seg_cap;
-                for (uint32_t e0 = lane * 4; e0 < cnt; e0 += 512) {         // four 128-bit loads in flight per lane
-                    float4 k[4];
+            for (int g0 = tid; g0 < n_groups; g0 += 2 * nt) {
+                float4 k[2];
+                uint32_t off[2], n[2];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const uint32_t e = e0 + u * 128;
-                        k[u] = e < cnt ? __ldg(reinterpret_cast<const float4*>(L_k1 + off + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int u = 0; u < 2; ++u) {
+                    const int g = g0 + u * nt;
+                    n[u] = 0; off[u] = 0;
+                    if (g < n_groups) {
+                        locate(g, off[u], n[u]);
+                        k[u] = __ldg(reinterpret_cast<const float4*>(L_k1 + off[u]));
                     }
+                }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const uint32_t e = e0 + u * 128;
-                        if (e < cnt) visit(k[u].x, off + e);
-                        if (e + 1 < cnt) visit(k[u].y, off + e + 1);
-                        if (e + 2 < cnt) visit(k[u].z, off + e + 2);
-                        if (e + 3 < cnt) visit(k[u].w, off + e + 3);
-                    }
+                for (int u = 0; u < 2; ++u) {
+                    if (n[u] > 0) visit(k[u].x, off[u]);
+                    if (n[u] > 1) visit(k[u].y, off[u] + 1);
+                    if (n[u] > 2) visit(k[u].z, off[u] + 2);
+                    if (n[u] > 3) visit(k[u].w, off[u] + 3);
                 }
             }
         };
         // the same with the rows and the level-2 keys loaded up front (the classification pass needs them for most entries)
         auto each_all3 = [&](auto visit) {
-            for (int sgi = warp; sgi < p.n_segs; sgi += nw) {
-                const uint32_t cnt = (uint32_t)s_cnt[sgi];
-                const uint32_t off = (uint32_t)sgi * (uint32_t)p.seg_cap;
-                for (uint32_t e0 = lane * 4; e0 < cnt; e0 += 256) {
-                    float4 k[2], k2[2];
-                    uint4 rw[2];
+            for (int g0 = tid; g0 < n_groups; g0 += 2 * nt) {
+                float4 k[2], k2[2];
+                uint4 rw[2];
+                uint32_t n[2];
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const uint32_t e = e0 + u * 128;
-                        const bool ok = e < cnt;
-                        k[u] = ok ? __ldg(reinterpret_cast<const float4*>(L_k1 + off + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        rw[u] = ok ? __ldg(reinterpret_cast<const uint4*>(L_rows + off + e)) : make_uint4(0u, 0u, 0u, 0u);
-                        k2[u] = (ok && three) ? __ldg(reinterpret_cast<const float4*>(L_k2 + off + e)) : make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+                for (int u = 0; u < 2; ++u) {
+                    const int g = g0 + u * nt;
+                    n[u] = 0;
+                    k2[u] = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+                    if (g < n_groups) {
+                        uint32_t off;
+                        locate(g, off, n[u]);
+                        k[u] = __ldg(reinterpret_cast<const float4*>(L_k1 + off));
+                        rw[u] = __ldg(reinterpret_cast<const uint4*>(L_rows + off));
+                        if (three) k2[u] = __ldg(reinterpret_cast<const float4*>(L_k2 + off));
                     }
+                }
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const uint32_t e = e0 + u * 128;
-                        if (e < cnt) visit(k[u].x, rw[u].x & 0x7fffffffu, k2[u].x);
-                        if (e + 1 < cnt) visit(k[u].y, rw[u].y & 0x7fffffffu, k2[u].y);
-                        if (e + 2 < cnt) visit(k[u].z, rw[u].z & 0x7fffffffu, k2[u].z);
-                        if (e + 3 < cnt) visit(k[u].w, rw[u].w & 0x7fffffffu, k2[u].w);
-                    }
+                for (int u = 0; u < 2; ++u) {
+                    if (n[u] > 0) visit(k[u].x, rw[u].x & 0x7fffffffu, k2[u].x);
+                    if (n[u] > 1) visit(k[u].y, rw[u].y & 0x7fffffffu, k2[u].y);
+                    if (n[u] > 2) visit(k[u].z, rw[u].z & 0x7fffffffu, k2[u].z);
+                    if (n[u] > 3) visit(k[u].w, rw[u].w & 0x7fffffffu, k2[u].w);
                 }
             }
         };
@@ -1817,9 +1850,9 @@ static ListGeom list_geom(int64_t N, int Q, const hq_index_layout* layout, bool 
 }
 
 // Window mode (see k_filter_predict): sample stride, list geometry of the sample pass and of the window pass.
-constexpr int64_t kWinMinRows = 131072;           // below this the sample would be a large part of the pass itself
+constexpr int64_t kWinMinRows = 65536;            // below this the sample would be a large part of the pass itself
 constexpr int kWinMinQueries = 16;                // a few queries are latency bound: fewer launches win (full lists)
-constexpr int kWinSampleTiles = 512;              // 64-row tiles the sample pass aims for
+constexpr int kWinSampleTiles = 512;              // 64-row tiles the sample pass aims for (256 on shards below ~500 K rows)
 struct WinGeom { bool on; int stride; int n_segs_s; int64_t seg_cap_s; int n_segs_w; int64_t seg_cap_w; };
 
 static bool win_enabled() {
@@ -1832,7 +1865,11 @@ static WinGeom win_geom(int64_t N, int Q, const hq_index_layout* layout) {
     if (!win_enabled() || !layout || layout->L < 2 || layout->L > 3 || !hq_filter_tc_supported(layout) || N < kWinMinRows || Q < kWinMinQueries)
         return g;
     const int64_t tiles = (N + 63) / 64;
-    int64_t stride = tiles / kWinSampleTiles;
+    static const int forced_tiles = [] { const char* e = getenv("HQ_FILTER_WINDOW_SAMPLE_TILES"); return e ? atoi(e) : 0; }();
+    int64_t want = tiles / 16;                                              // ~6 % of the shard, within [256, 512] tiles
+    want = want < 256 ? 256 : (want > kWinSampleTiles ? kWinSampleTiles : want);
+    if (forced_tiles > 0) want = forced_tiles;
+    int64_t stride = tiles / want;
     stride = stride < 2 ? 2 : (stride > 64 ? 64 : stride);
     int nr = 0, tp = 0;
     if (hq_filter_tc_plan_strided(N, Q, (int)stride, &nr, &tp) != HQ_OK) return g;

@@ -327,6 +327,52 @@ __device__ __forceinline__ float warp_row_dot(const float* __restrict__ qv, cons
     return acc;
 }
 
+// the same dot products for up to four rows at once (loads of the four rows in flight together; every row's own
+// accumulation order is that of warp_row_dot, so the values are bit identical)
+template <bool B16>
+__device__ __forceinline__ void warp_rows_dot4(const float* __restrict__ qv, const void* const (&row)[4], int n_rows, int D, bool vec, int lane,
+                                               float (&out)[4]) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (!vec) {
+        for (int r = 0; r < n_rows; ++r) out[r] = warp_row_dot<B16>(qv, row[r], D, false, lane);
+        return;
+    }
+    if constexpr (!B16) {
+        for (int i = lane; i < D / 4; i += 32) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(qv) + i);
+            float4 b[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) b[r] = r < n_rows ? __ldg(reinterpret_cast<const float4*>(row[r]) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                acc[r] = fmaf(a.x, b[r].x, acc[r]); acc[r] = fmaf(a.y, b[r].y, acc[r]);
+                acc[r] = fmaf(a.z, b[r].z, acc[r]); acc[r] = fmaf(a.w, b[r].w, acc[r]);
+            }
+        }
+    } else {
+        for (int i = lane; i < D / 8; i += 32) {
+            const float4 a0 = __ldg(reinterpret_cast<const float4*>(qv) + 2 * i);
+            const float4 a1 = __ldg(reinterpret_cast<const float4*>(qv) + 2 * i + 1);
+            uint4 w[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) w[r] = r < n_rows ? __ldg(reinterpret_cast<const uint4*>(row[r]) + i) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                acc[r] = fmaf(a0.x, __uint_as_float(w[r].x << 16), acc[r]); acc[r] = fmaf(a0.y, __uint_as_float(w[r].x & 0xffff0000u), acc[r]);
+                acc[r] = fmaf(a0.z, __uint_as_float(w[r].y << 16), acc[r]); acc[r] = fmaf(a0.w, __uint_as_float(w[r].y & 0xffff0000u), acc[r]);
+                acc[r] = fmaf(a1.x, __uint_as_float(w[r].z << 16), acc[r]); acc[r] = fmaf(a1.y, __uint_as_float(w[r].z & 0xffff0000u), acc[r]);
+                acc[r] = fmaf(a1.z, __uint_as_float(w[r].w << 16), acc[r]); acc[r] = fmaf(a1.w, __uint_as_float(w[r].w & 0xffff0000u), acc[r]);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+        out[r] = acc[r];
+    }
+}
+
 __device__ __forceinline__ float score_of(float acc, float nq, float nc) {
     return (nq != 0.f && nc != 0.f) ? __fmul_rn(__fadd_rn(__fdiv_rn(acc, __fmul_rn(nq, nc)), 1.0f), 0.5f) : 0.f;
 }
@@ -368,9 +414,6 @@ __global__ void __launch_bounds__(128) k_rerank_tc_merge(const TcParams p, const
     extern __shared__ __align__(16) unsigned char sm[];
     const int n_sub = p.n_ranges * p.eh, M = n_sub * KP;
     uint64_t* c_key = reinterpret_cast<uint64_t*>(sm);           // [M]  (ord(value) << 32) | ~row, 0 = empty slot
-    uint8_t* head = reinterpret_cast<uint8_t*>(c_key + M);       // [n_sub] next untaken entry of every sublist
-    __shared__ uint64_t w_key[4];
-    __shared__ int w_sub[4];
     __shared__ int32_t sel_id[R_MAX];
     __shared__ float ex_s[R_MAX], ex_t[R_MAX];
     __shared__ uint32_t s_B;
@@ -380,7 +423,6 @@ __global__ void __launch_bounds__(128) k_rerank_tc_merge(const TcParams p, const
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m_tile = q / BM, row = q % BM;
     if (tid == 0) { s_B = 0; s_state = 0; }
-    for (int s = tid; s < n_sub; s += blockDim.x) head[s] = 0;
     __syncthreads();
     for (int e = tid; e < M; e += blockDim.x) {
         const int r = e / KP, j = e - r * KP;                   // r = range * eh + half
@@ -411,76 +453,102 @@ __global__ void __launch_bounds__(128) k_rerank_tc_merge(const TcParams p, const
                             ((reinterpret_cast<uintptr_t>(q_f32) & 15) == 0))
                          : ((p.D % 4 == 0) && (db_stride % 4 == 0) && (q_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(db_f32) & 15) == 0) &&
                             ((reinterpret_cast<uintptr_t>(q_f32) & 15) == 0));
+    // ---- merge: ONE warp walks the pool in (value desc, row asc) order, a chunk of R_CHUNK rows at a time, with a
+    // tournament over the sublist heads that needs no block-wide barrier (the first version took one element per round
+    // of the whole block with two barriers each: ~95 us per query whatever the shard size; ranking every pool entry by
+    // binary searches over all sublists was worse: the pool holds up to ~2000 entries in ~120 sublists).
+    uint8_t* head = reinterpret_cast<uint8_t*>(c_key + M);       // [n_sub] next untaken entry of every sublist
+    __shared__ int s_cnt;
+    __shared__ unsigned long long s_next;
+    for (int sb = tid; sb < n_sub; sb += blockDim.x) head[sb] = 0;
+    __syncthreads();
     int cnt = 0, done = 0;
     while (true) {
-        // ---- tournament round: the best head over all sublists ----
-        uint64_t bk = 0;
-        int bs = -1;
-        for (int s = tid; s < n_sub; s += blockDim.x) {
-            const int h = head[s];
-            if (h < KP) {
-                const uint64_t key = c_key[s * KP + h];
-                if (key > bk) { bk = key; bs = s; }
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const uint64_t ok = __shfl_xor_sync(0xffffffffu, bk, o);
-            const int os = __shfl_xor_sync(0xffffffffu, bs, o);
-            if (ok > bk) { bk = ok; bs = os; }
-        }
-        if (lane == 0) { w_key[warp] = bk; w_sub[warp] = bs; }
-        __syncthreads();
-        uint64_t next_key = w_key[0];
-        int next_sub = w_sub[0];
-#pragma unroll
-        for (int w = 1; w < 4; ++w)
-            if (w_key[w] > next_key) { next_key = w_key[w]; next_sub = w_sub[w]; }
-        const bool exhausted = next_key == 0ull;
-        if (exhausted || cnt == R_MAX || (cnt > done && cnt % R_CHUNK == 0)) {
-            // ---- exact values of the rows taken since the last check (one warp per row) ----
-            for (int c = done + warp; c < cnt; c += 4) {
-                const int32_t id = sel_id[c];
-                const void* rv = B16 ? reinterpret_cast<const void*>(db_b16 + (int64_t)id * db_pitch)
-                                     : reinterpret_cast<const void*>(db_f32 + (int64_t)id * db_stride);
-                const float acc = warp_row_dot<B16>(qv, rv, p.D, vec, lane);
-                const float nc = __ldg(p.db_norm + id);
-                if (lane == 0) { ex_s[c] = score_of(acc, nq, nc); ex_t[c] = nc != 0.f ? __fdiv_rn(acc, nc) : 0.f; }
-            }
-            done = cnt;
-            __syncthreads();
-            // ---- guard ----
-            if (warp == 0) {
-                const uint32_t next_o = exhausted ? 0u : (uint32_t)(next_key >> 32);
-                const uint32_t bound_o = s_B > next_o ? s_B : next_o;
-                int state;
-                if (bound_o == 0u) {
-                    state = 1;                                      // nothing was left out: every surviving row has been re-scored
-                } else if (cnt >= k) {
-                    // k-th largest exact value among the re-scored rows (rank by counting, cnt <= 64)
-                    for (int i = lane; i < cnt; i += 32) {
-                        const float ti = ex_t[i];
-                        int rank = 0;
-                        for (int j = 0; j < cnt; ++j) rank += (ex_t[j] > ti || (ex_t[j] == ti && j < i)) ? 1 : 0;
-                        if (rank == k - 1) s_tk = ti;
+        if (warp == 0) {
+            int c = cnt;
+            const int target = min(done + R_CHUNK, R_MAX);
+            uint64_t nk;
+            while (true) {
+                uint64_t bk = 0;
+                int bs = -1;
+                for (int sb = lane; sb < n_sub; sb += 32) {
+                    const int h = head[sb];
+                    if (h < KP) {
+                        const uint64_t key = c_key[sb * KP + h];
+                        if (key > bk) { bk = key; bs = sb; }
                     }
-                    __syncwarp();
-                    state = (s_tk > float_of_ord(bound_o) + E) ? 1 : ((exhausted || cnt >= R_MAX) ? 2 : 0);
-                } else {
-                    state = (exhausted || cnt >= R_MAX) ? 2 : 0;
                 }
-                if (lane == 0) s_state = state;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const uint64_t ok = __shfl_xor_sync(0xffffffffu, bk, o);
+                    const int os = __shfl_xor_sync(0xffffffffu, bs, o);
+                    if (ok > bk) { bk = ok; bs = os; }
+                }
+                nk = bk;
+                if (nk == 0ull || c == target) break;
+                if (lane == 0) {
+                    sel_id[c] = (int32_t)(0xffffffffu - (uint32_t)(nk & 0xffffffffull));
+                    head[bs] = (uint8_t)(head[bs] + 1);
+                }
+                ++c;
+                __syncwarp();
             }
-            __syncthreads();
-            if (s_state != 0) break;
+            if (lane == 0) { s_cnt = c; s_next = nk; }
         }
-        // ---- take the head ----
-        if (tid == 0) {
-            sel_id[cnt] = (int32_t)(0xffffffffu - (uint32_t)(next_key & 0xffffffffull));
-            head[next_sub] = (uint8_t)(head[next_sub] + 1);
-        }
-        ++cnt;
         __syncthreads();
+        cnt = s_cnt;
+        const uint64_t next_key = s_next;
+        const bool exhausted = next_key == 0ull;
+        // ---- exact values of the chunk: a warp takes four rows at once ----
+        for (int c0 = done + 4 * warp; c0 < cnt; c0 += 16) {
+            const int nr = min(4, cnt - c0);
+            const void* rows[4];
+            int32_t idr[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                idr[r] = sel_id[c0 + (r < nr ? r : 0)];
+                rows[r] = B16 ? reinterpret_cast<const void*>(db_b16 + (int64_t)idr[r] * db_pitch)
+                              : reinterpret_cast<const void*>(db_f32 + (int64_t)idr[r] * db_stride);
+            }
+            float acc[4];
+            warp_rows_dot4<B16>(qv, rows, nr, p.D, vec, lane, acc);
+            if (lane < nr) {
+                float a = acc[0];
+                int32_t id = idr[0];
+#pragma unroll
+                for (int r = 1; r < 4; ++r)
+                    if (lane == r) { a = acc[r]; id = idr[r]; }
+                const float nc = __ldg(p.db_norm + id);
+                ex_s[c0 + lane] = score_of(a, nq, nc);
+                ex_t[c0 + lane] = nc != 0.f ? __fdiv_rn(a, nc) : 0.f;
+            }
+        }
+        done = cnt;
+        __syncthreads();
+        // ---- guard ----
+        if (warp == 0) {
+            const uint32_t next_o = exhausted ? 0u : (uint32_t)(next_key >> 32);
+            const uint32_t bound_o = s_B > next_o ? s_B : next_o;
+            int state;
+            if (bound_o == 0u) {
+                state = 1;                                      // nothing was left out: every surviving row has been re-scored
+            } else if (cnt >= k) {
+                // k-th largest exact value among the re-scored rows (rank by counting, cnt <= 64)
+                for (int i = lane; i < cnt; i += 32) {
+                    const float ti = ex_t[i];
+                    int rank = 0;
+                    for (int j = 0; j < cnt; ++j) rank += (ex_t[j] > ti || (ex_t[j] == ti && j < i)) ? 1 : 0;
+                    if (rank == k - 1) s_tk = ti;
+                }
+                __syncwarp();
+                state = (s_tk > float_of_ord(bound_o) + E) ? 1 : ((exhausted || cnt >= R_MAX) ? 2 : 0);
+            } else {
+                state = (exhausted || cnt >= R_MAX) ? 2 : 0;
+            }
+            if (lane == 0) s_state = state;
+        }
+        __syncthreads();
+        if (s_state != 0) break;
     }
     // ---- emit: rank the re-scored rows by (exact score desc, row asc) ----
     if (tid < cnt) {

@@ -96,6 +96,44 @@ def allgather_merge(local_ids: torch.Tensor, local_scores: torch.Tensor, k: int,
     return out_i, out_s
 
 
+class MergePipeline:
+    """The all-gather + merge of batch i on a communication stream while the main stream already searches batch i + 1.
+
+    A step of the row-sharded search ends with ~0.1 ms of NCCL latency and a small merge kernel; with shards of 125 K
+    rows (1 M rows over 8 GPUs) the search itself takes 0.9 ms, so a serial step spends a tenth of its time waiting for
+    120 KB of results.  `submit` orders the collective after the search (event on the main stream), runs it on the
+    pipeline's stream and returns the merged (ids, scores) device tensors, valid once `done` (the returned event) has
+    completed or after `drain()`.  Every rank must submit the same sequence of batches."""
+
+    def __init__(self, device, group=None, depth: int = 2):
+        self.device, self.group, self.depth = torch.device(device), group, max(1, int(depth))
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._inflight: list = []
+
+    def submit(self, local_ids: torch.Tensor, local_scores: torch.Tensor, k: int):
+        main = torch.cuda.current_stream(self.device)
+        if len(self._inflight) >= self.depth:        # bound the work queued on the communication stream
+            main.wait_event(self._inflight.pop(0))
+        ready = torch.cuda.Event()
+        ready.record(main)
+        self.stream.wait_event(ready)
+        with torch.cuda.stream(self.stream):
+            out_i, out_s = allgather_merge(local_ids, local_scores, k, self.group)
+            for t in (local_ids, local_scores, out_i, out_s):
+                t.record_stream(self.stream)         # the caching allocator must not hand these to the main stream early
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        self._inflight.append(done)
+        return out_i, out_s, done
+
+    def drain(self):
+        """The main stream waits for every submitted merge."""
+        main = torch.cuda.current_stream(self.device)
+        for ev in self._inflight:
+            main.wait_event(ev)
+        self._inflight.clear()
+
+
 def _all_reduce(t: torch.Tensor, op, group) -> torch.Tensor:
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, op=op, group=group)
@@ -184,10 +222,23 @@ class ShardedSearch:
         ids, scores = search_batch(self.db, queries, k, filter_scope=filter_scope, group=self.group, **kw)
         return allgather_merge(ids, scores, k, self.group)
 
+    def search_pipelined(self, query_batches, k: int = 10, **kw):
+        """Throughput path for device-resident query batches: yields (ids, scores, done_event) per batch, the merge of
+        batch i running on a communication stream under the search of batch i + 1 (see `MergePipeline`).  The caller waits
+        for `done_event` (or synchronises the device) before reading a batch's result."""
+        from .search import search_batch
+        pipe = MergePipeline(self.db.device, self.group)
+        for q in query_batches:
+            ids, scores = search_batch(self.db, q, k, group=self.group, **kw)
+            yield pipe.submit(ids, scores, k)
+        pipe.drain()
+
     def search_stream(self, host_batches, k: int = 10, *, depth: int = 2, **kw):
         """`search.search_stream` over this rank's shard with the all-gather merge as its post step: every rank feeds the same
         host batches and gets the merged global top-k of each batch back in pinned host memory, copies overlapped with the
         search (the bench's e2e figure at N > 1 is exactly this composition)."""
         from .search import search_stream
-        return search_stream(self.db, host_batches, k, depth=depth,
+        if getattr(self, "_post_stream", None) is None:
+            self._post_stream = torch.cuda.Stream(device=self.db.device)
+        return search_stream(self.db, host_batches, k, depth=depth, post_stream=self._post_stream,
                              post=lambda ids, scores: allgather_merge(ids, scores, k, self.group), **kw)

@@ -679,7 +679,7 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
     return ids, out_scores
 
 
-def search_stream(db: EmbeddingDatabase, host_batches, k: int = 10, *, depth: int = 2, post=None, **kw):
+def search_stream(db: EmbeddingDatabase, host_batches, k: int = 10, *, depth: int = 2, post=None, post_stream=None, **kw):
     """Throughput path for queries that live in HOST memory: a generator over `host_batches` (CPU tensors [Q, D], pinned for
     asynchronous copies; every batch the same shape) that yields `(ids, scores)` as pinned host tensors, in order.  The copy
     of batch i + 1 runs on a copy stream while batch i is searched and the results of batch i - 1 travel back, so the
@@ -723,14 +723,28 @@ def search_stream(db: EmbeddingDatabase, host_batches, k: int = 10, *, depth: in
             slot["copied"].record(copy_stream)
         main.wait_event(slot["copied"])
         ids, sc = search_batch(db, slot["q"], k, **kw)
-        if post is not None:
-            ids, sc = post(ids, sc)
         if slot["ids"] is None or tuple(slot["ids"].shape) != tuple(ids.shape):
             slot["ids"] = torch.empty(tuple(ids.shape), dtype=ids.dtype).pin_memory()
             slot["scores"] = torch.empty(tuple(sc.shape), dtype=sc.dtype).pin_memory()
-        slot["ids"].copy_(ids, non_blocking=True)
-        slot["scores"].copy_(sc, non_blocking=True)
-        slot["done"].record(main)
+        if post is not None and post_stream is not None:
+            # the post step (the all-gather merge of a row-sharded search) and the read-back run on `post_stream`, ordered
+            # after this batch's search; the main stream goes straight on to the next batch
+            searched = torch.cuda.Event()
+            searched.record(main)
+            post_stream.wait_event(searched)
+            with torch.cuda.stream(post_stream):
+                out_i, out_s = post(ids, sc)
+                for t in (ids, sc, out_i, out_s):
+                    t.record_stream(post_stream)
+                slot["ids"].copy_(out_i, non_blocking=True)
+                slot["scores"].copy_(out_s, non_blocking=True)
+                slot["done"].record(post_stream)
+        else:
+            if post is not None:
+                ids, sc = post(ids, sc)
+            slot["ids"].copy_(ids, non_blocking=True)
+            slot["scores"].copy_(sc, non_blocking=True)
+            slot["done"].record(main)
         pending.append(slot)
     while pending:
         yield finish(pending.popleft())
