@@ -1239,29 +1239,63 @@ __global__ void __launch_bounds__(256, 4) k_filter_predict(const PredictParams p
     }
     const float c0s = (float)p.c0_s[q];
     const int64_t qbase = (int64_t)q * p.n_segs * p.seg_cap;
-    // a warp owns one segment at a time and keeps four 128-bit loads per array in flight (segments are 128-byte aligned)
-    const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    // the sample entries as 4-entry groups numbered across all segments (independent loads, in flight together: a warp per
+    // segment was a chain of 30 DRAM round trips per pass for a single query's 262 segments)
+    __shared__ int32_t s_pcnt[kMaxSegs];
+    __shared__ int32_t s_pgoff[kMaxSegs + 1];
+    const int lane = tid & 31;
+    for (int i = tid; i < p.n_segs; i += nt) {
+        const int32_t n = p.seg_n[(int64_t)q * p.n_segs + i];
+        s_pcnt[i] = n > p.seg_cap ? (int32_t)p.seg_cap : n;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        const int per = (p.n_segs + 31) / 32;
+        int sum = 0;
+        for (int i = 0; i < per; ++i) { const int sg = lane * per + i; if (sg < p.n_segs) sum += (s_pcnt[sg] + 3) >> 2; }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        int run = incl - sum;
+        for (int i = 0; i < per; ++i) {
+            const int sg = lane * per + i;
+            if (sg < p.n_segs) { s_pgoff[sg] = run; run += (s_pcnt[sg] + 3) >> 2; }
+        }
+        if (lane == 31) s_pgoff[p.n_segs] = incl;
+    }
+    __syncthreads();
+    const int n_groups = s_pgoff[p.n_segs];
     auto each = [&](auto visit) {
-        for (int sgi = warp; sgi < p.n_segs; sgi += nw) {
-            int32_t cnt = p.seg_n[(int64_t)q * p.n_segs + sgi];
-            if (cnt > p.seg_cap) cnt = (int32_t)p.seg_cap;
-            const int64_t off = qbase + (int64_t)sgi * p.seg_cap;
-            for (int e0 = lane * 4; e0 < cnt; e0 += 512) {
-                float4 a[4], b[4];
+        for (int g0 = tid; g0 < n_groups; g0 += 2 * nt) {
+            float4 a[2], b[2];
+            int n[2];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int e = e0 + u * 128;
-                    a[u] = e < cnt ? __ldg(reinterpret_cast<const float4*>(p.l_k1 + off + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    b[u] = (three && e < cnt) ? __ldg(reinterpret_cast<const float4*>(p.l_k2 + off + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int u = 0; u < 2; ++u) {
+                const int g = g0 + u * nt;
+                n[u] = 0;
+                b[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g < n_groups) {
+                    int lo = 0, hi = p.n_segs;
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (s_pgoff[mid] <= g) lo = mid; else hi = mid;
+                    }
+                    const int e = (g - s_pgoff[lo]) * 4;
+                    const int64_t off = qbase + (int64_t)lo * p.seg_cap + e;
+                    n[u] = min(4, s_pcnt[lo] - e);
+                    a[u] = __ldg(reinterpret_cast<const float4*>(p.l_k1 + off));
+                    if (three) b[u] = __ldg(reinterpret_cast<const float4*>(p.l_k2 + off));
                 }
+            }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int e = e0 + u * 128;
-                    if (e < cnt) visit(a[u].x, b[u].x);
-                    if (e + 1 < cnt) visit(a[u].y, b[u].y);
-                    if (e + 2 < cnt) visit(a[u].z, b[u].z);
-                    if (e + 3 < cnt) visit(a[u].w, b[u].w);
-                }
+            for (int u = 0; u < 2; ++u) {
+                if (n[u] > 0) visit(a[u].x, b[u].x);
+                if (n[u] > 1) visit(a[u].y, b[u].y);
+                if (n[u] > 2) visit(a[u].z, b[u].z);
+                if (n[u] > 3) visit(a[u].w, b[u].w);
             }
         }
     };
@@ -1354,7 +1388,8 @@ constexpr int kWinThreads = 128;      // eight CTAs per SM: 1184 queries in flig
 constexpr int kWinCutCap = 1024;      // cut-bin members ranked in shared memory (window histograms are fine grained)
 constexpr int kWinCtasPerSm = 8;      // 64 registers per thread (256-thread CTAs: 4 per SM = 592 queries in flight, two waves)
 
-__global__ void __launch_bounds__(kWinThreads, kWinCtasPerSm) k_filter_cascade_win(const WinParams p) {
+template <int THREADS, int CTAS, int U>          // U: 4-entry groups a thread keeps in flight in the list passes
+__global__ void __launch_bounds__(THREADS, CTAS) k_filter_cascade_win(const WinParams p) {
     __shared__ uint32_t hist[2048];
     __shared__ uint32_t sh[4];
     __shared__ uint32_t s_warp[32];
@@ -1448,32 +1483,43 @@ __global__ void __launch_bounds__(kWinThreads, kWinCtasPerSm) k_filter_cascade_w
         }
         __syncthreads();
         const int n_groups = s_goff[p.n_segs];
-        // group g -> (offset of its first entry inside the query's arrays, entries in it)
-        auto locate = [&](int g, uint32_t& off, uint32_t& n) {
-            int lo = 0, hi = p.n_segs;                               // last segment whose first group is <= g
+        // A warp owns a contiguous range of groups, its lanes take consecutive groups (coalesced 512-byte reads); a lane's
+        // groups ascend, so the segment of a group is found by walking forward from the lane's previous segment (a binary
+        // search per group made the passes instruction bound on long lists).
+        const int warp = tid >> 5, nw = nt >> 5;
+        const int g_per_warp = (n_groups + nw - 1) / nw;
+        const int g_begin = warp * g_per_warp, g_end = min(n_groups, g_begin + g_per_warp);
+        int seg0 = 0;
+        {
+            int lo = 0, hi = p.n_segs;                               // last segment whose first group is <= g_begin
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
-                if (s_goff[mid] <= g) lo = mid; else hi = mid;
+                if (s_goff[mid] <= g_begin) lo = mid; else hi = mid;
             }
-            const uint32_t e = (uint32_t)(g - s_goff[lo]) * 4u;
-            off = (uint32_t)lo * (uint32_t)p.seg_cap + e;
-            n = min(4u, (uint32_t)s_cnt[lo] - e);
+            seg0 = lo;
+        }
+        auto locate = [&](int g, int& seg, uint32_t& off, uint32_t& n) {
+            while (s_goff[seg + 1] <= g) ++seg;
+            const uint32_t e = (uint32_t)(g - s_goff[seg]) * 4u;
+            off = (uint32_t)seg * (uint32_t)p.seg_cap + e;
+            n = min(4u, (uint32_t)s_cnt[seg] - e);
         };
         auto each_all = [&](auto visit) {
-            for (int g0 = tid; g0 < n_groups; g0 += 2 * nt) {
-                float4 k[2];
-                uint32_t off[2], n[2];
+            int seg = seg0;
+            for (int g0 = g_begin + lane; g0 < g_end; g0 += U * 32) {
+                float4 k[U];
+                uint32_t off[U], n[U];
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int g = g0 + u * nt;
+                for (int u = 0; u < U; ++u) {
+                    const int g = g0 + u * 32;
                     n[u] = 0; off[u] = 0;
-                    if (g < n_groups) {
-                        locate(g, off[u], n[u]);
+                    if (g < g_end) {
+                        locate(g, seg, off[u], n[u]);
                         k[u] = __ldg(reinterpret_cast<const float4*>(L_k1 + off[u]));
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
+                for (int u = 0; u < U; ++u) {
                     if (n[u] > 0) visit(k[u].x, off[u]);
                     if (n[u] > 1) visit(k[u].y, off[u] + 1);
                     if (n[u] > 2) visit(k[u].z, off[u] + 2);
@@ -1483,18 +1529,19 @@ __global__ void __launch_bounds__(kWinThreads, kWinCtasPerSm) k_filter_cascade_w
         };
         // the same with the rows and the level-2 keys loaded up front (the classification pass needs them for most entries)
         auto each_all3 = [&](auto visit) {
-            for (int g0 = tid; g0 < n_groups; g0 += 2 * nt) {
+            int seg = seg0;
+            for (int g0 = g_begin + lane; g0 < g_end; g0 += 2 * 32) {
                 float4 k[2], k2[2];
                 uint4 rw[2];
                 uint32_t n[2];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    const int g = g0 + u * nt;
+                    const int g = g0 + u * 32;
                     n[u] = 0;
                     k2[u] = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
-                    if (g < n_groups) {
+                    if (g < g_end) {
                         uint32_t off;
-                        locate(g, off, n[u]);
+                        locate(g, seg, off, n[u]);
                         k[u] = __ldg(reinterpret_cast<const float4*>(L_k1 + off));
                         rw[u] = __ldg(reinterpret_cast<const uint4*>(L_rows + off));
                         if (three) k2[u] = __ldg(reinterpret_cast<const float4*>(L_k2 + off));
@@ -1851,7 +1898,7 @@ static ListGeom list_geom(int64_t N, int Q, const hq_index_layout* layout, bool 
 
 // Window mode (see k_filter_predict): sample stride, list geometry of the sample pass and of the window pass.
 constexpr int64_t kWinMinRows = 65536;            // below this the sample would be a large part of the pass itself
-constexpr int kWinMinQueries = 16;                // a few queries are latency bound: fewer launches win (full lists)
+constexpr int kWinMinQueries = 1;                 // (a single query against 1 M rows: 0.46 -> 0.39 ms through SearchGraph)
 constexpr int kWinSampleTiles = 512;              // 64-row tiles the sample pass aims for (256 on shards below ~500 K rows)
 struct WinGeom { bool on; int stride; int n_segs_s; int64_t seg_cap_s; int n_segs_w; int64_t seg_cap_w; };
 
@@ -1862,7 +1909,8 @@ static bool win_enabled() {
 
 static WinGeom win_geom(int64_t N, int Q, const hq_index_layout* layout) {
     WinGeom g{false, 1, 0, 0, 0, 0};
-    if (!win_enabled() || !layout || layout->L < 2 || layout->L > 3 || !hq_filter_tc_supported(layout) || N < kWinMinRows || Q < kWinMinQueries)
+    static const int min_q = [] { const char* e = getenv("HQ_FILTER_WINDOW_MIN_Q"); return e ? atoi(e) : kWinMinQueries; }();
+    if (!win_enabled() || !layout || layout->L < 2 || layout->L > 3 || !hq_filter_tc_supported(layout) || N < kWinMinRows || Q < min_q)
         return g;
     const int64_t tiles = (N + 63) / 64;
     static const int forced_tiles = [] { const char* e = getenv("HQ_FILTER_WINDOW_SAMPLE_TILES"); return e ? atoi(e) : 0; }();
@@ -2086,7 +2134,12 @@ extern "C" int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, c
         HQ_REQUIRE((int64_t)wgrid * wp.tmp_stride <= (int64_t)grid * N, "internal: window lists larger than the cascade scratch");
         wp.tmp_keys = reinterpret_cast<float*>(sc_keys);
         wp.tmp_rows = sc_keys + (int64_t)wgrid * wp.tmp_stride;
-        k_filter_cascade_win<<<wgrid, kWinThreads, 0, st>>>(wp);
+        // a few queries: one large CTA per query (latency), a batch: eight small CTAs per SM (one wave)
+        static const int variant = [] { const char* e = getenv("HQ_FILTER_WINDOW_CTA"); return e ? atoi(e) : 0; }();
+        const bool big = variant == 256;       // (measured at 1 M rows: 341 us against 297 us for the small CTAs; 86 / 70 us at 125 K rows)
+        if (Q <= hq_cached_sm_count()) k_filter_cascade_win<1024, 1, 2><<<wgrid, 1024, 0, st>>>(wp);
+        else if (big) k_filter_cascade_win<256, 4, 4><<<wgrid > hq_cached_sm_count() * 4 ? hq_cached_sm_count() * 4 : wgrid, 256, 0, st>>>(wp);
+        else k_filter_cascade_win<kWinThreads, kWinCtasPerSm, 2><<<wgrid, kWinThreads, 0, st>>>(wp);
         HQ_LAUNCH_OK("k_filter_cascade_win");
         // 5. fallback for the flagged queries: full-threshold planes of their query tiles, generic gather cascade
         HqFtcOpts of{};
