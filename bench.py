@@ -130,6 +130,19 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------
 # synthetic data: randn rows, L2-normalised; half the queries are perturbed rows
 # --------------------------------------------------------------------------------------
+def make_shard(torch, rows, dim, seed, device):
+    """fp32 [rows, dim] randn rows, L2-normalised, generated on the device (bench_extra.py and the tools use it)"""
+    g = torch.Generator(device=device).manual_seed(seed)
+    out = torch.empty((rows, dim), dtype=torch.float32, device=device)
+    step = 1 << 20
+    for s in range(0, rows, step):
+        e = min(rows, s + step)
+        x = torch.randn((e - s, dim), generator=g, device=device)
+        x /= x.norm(dim=1, keepdim=True)
+        out[s:e] = x
+    return out
+
+
 def make_queries_host(np_db_rows, Q, dim, seed=4321):
     rng = np.random.default_rng(seed)
     q = rng.standard_normal((Q, dim)).astype(np.float32)
@@ -663,8 +676,9 @@ def main():
                         "database": "bf16 unit rows only (no fp32 copy)" if args.bf16_only else "fp32 rows + bf16 unit rows",
                         "rerank": "tcgen05 bf16 contraction + fused mask/top-16 epilogue, exact fp32 re-score of the shortlist "
                                   "with a shortlist-sufficiency guard (flagged queries re-scored exactly over all survivors)",
-                        "filter": "tcgen05 tf32 (hi/lo split) threshold pass emitting bit planes + candidate lists, streaming list "
-                                  "cascade with exact selection at the ratio cuts (generic gather cascade as per-query fallback)"},
+                        "filter": "window mode: tcgen05 tf32 (hi/lo split) sample pass -> predicted cut windows -> window pass (alive "
+                                  "plane + counters + lists of the window rows) -> exact ranking of the window rows; mispredicted "
+                                  "queries are redone by the fallback pass (full-threshold planes + generic gather cascade)"},
             "p50_ms": float(np.median(per_step)), "p99_ms": float(np.percentile(per_step, 99)),
             "single_query_latency_ms": latency,
             "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": int(q_pinned.numel() * 4),
@@ -684,8 +698,8 @@ def main():
                          "peak_source": pk["source"] + " (burst cuBLAS bf16)",
                          "frac_of_sustained_peak": (achieved_tf / pk["bf16_tflops"]) if achieved_tf else None,
                          "algorithmic_flops_per_launch": flops,
-                         "note": "largest single kernel of the step; the coarse filter (tcgen05 tf32 threshold pass + list "
-                                 "cascade) is issue bound, see DESIGN.md section 5 and profiles/"},
+                         "note": "largest single kernel of the step; the coarse filter (tcgen05 tf32 window pass + window "
+                                 "cascade) is issue bound, see DESIGN.md section 5 (K5w) and profiles/"},
             "clocks": clocks.summary(),
             "top1_hit_rate_perturbed": float((ids[: args.queries // 2, 0].cpu().numpy() == np.arange(args.queries // 2)).mean())
             if lo == 0 else None,

@@ -21,7 +21,7 @@ sys.path.insert(0, ROOT)
 
 import hilbert_quantization_b200 as hq                      # noqa: E402
 from hilbert_quantization_b200.index import fused_pass, plans   # noqa: E402
-from bench import make_queries_host, make_shard, peaks       # noqa: E402
+from bench import ClockSampler, make_queries_host, make_shard, peaks       # noqa: E402
 
 
 def timed(fn, warmup=3, iters=5):
@@ -157,7 +157,9 @@ def main():
     for name in args.only.split(","):
         fn = {"c1": c1, "c3": c3, "c4": c4, "c5": c5}[name]
         try:
-            res = fn(pk)
+            with ClockSampler(0) as clocks:                      # nvidia-smi clocks / throttle reasons while the workload runs
+                res = fn(pk)
+            res["clocks"] = clocks.summary()
         except Exception as e:                                   # keep the other workloads running
             res = {"workload": name, "error": repr(e)[:400]}
         res["name"] = name

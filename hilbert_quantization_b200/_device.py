@@ -46,8 +46,16 @@ def to_device(arr: np.ndarray, device: torch.device) -> torch.Tensor:
     return torch.from_numpy(np.ascontiguousarray(arr)).to(device, non_blocking=False)
 
 
+def canonical_strides(t: torch.Tensor) -> torch.Tensor:
+    """A contiguous tensor whose size-1 axes also report row-major strides (NumPy and torch keep whatever stride such an
+    axis had, e.g. `q[None, :]`; the C ABI takes `stride(0)` at face value)."""
+    if t.dim() >= 2 and t.numel() > 0 and t.is_contiguous():
+        return t.view(t.numel()).view(t.shape)
+    return t
+
+
 def f32_device(x, device: torch.device) -> torch.Tensor:
     """float32, contiguous, on `device` (accepts ndarray or tensor)."""
     if isinstance(x, torch.Tensor):
-        return x.to(device=device, dtype=torch.float32).contiguous()
-    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(device)
+        return canonical_strides(x.to(device=device, dtype=torch.float32).contiguous())
+    return canonical_strides(torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(device))

@@ -38,6 +38,7 @@ SIGNATURES = {
     "hq_index_row_lengths": (_i32, [_p, _i64, C.POINTER(IndexLayout), _p, _p]),
     "hq_filter_level": (_i32, [_p, _p, _i64, C.POINTER(IndexLayout), _i32, _p, _p, _i32, _p, _i64, _dbl, _p, _i64, _p, _p, _p, _p]),
     "hq_filter_select": (_i32, [_p, _i64, _i64, _i32, _p, _p, _dbl, _p, _i64, _p, _p]),
+    "hq_filter_select_prev": (_i32, [_p, _i64, _i64, _i32, _p, _p, _i64, _p, _p, _dbl, _p, _i64, _p, _p]),
     "hq_filter_fast_supported": (_i32, [C.POINTER(IndexLayout)]),
     "hq_filter_level_norms": (_i32, [_p, _p, _i64, C.POINTER(IndexLayout), _p, _p, _p]),
     "hq_filter_fast_scratch_bytes": (_i64, [_i64, _i32, C.POINTER(IndexLayout)]),

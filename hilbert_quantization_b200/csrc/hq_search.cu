@@ -228,6 +228,64 @@ __device__ SelectResult block_radix_select(const float* __restrict__ s, int64_t 
     return r;
 }
 
+// the same selection over keys produced by a functor: key_of(i, key) returns false for rows that do not take part
+template <class KeyFn>
+__device__ SelectResult block_radix_select_fn(KeyFn key_of, int64_t N, uint32_t k, uint32_t* hist /*2048*/, uint32_t* sh /*4*/) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    uint32_t prefix = 0, pmask = 0, remaining = k;
+    const int shifts[3] = {21, 10, 0};
+    const int bits[3] = {11, 11, 10};
+    uint32_t ties_total = 0;
+    for (int pass = 0; pass < 3; ++pass) {
+        const int shift = shifts[pass];
+        const uint32_t nb = 1u << bits[pass];
+        for (uint32_t i = tid; i < nb; i += nt) hist[i] = 0;
+        __syncthreads();
+        for (int64_t i = tid; i < N; i += nt) {
+            uint32_t key;
+            if (key_of(i, key) && (key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & (nb - 1)], 1u);
+        }
+        __syncthreads();
+        if (tid < 32) {
+            const uint32_t seg = nb / 32;
+            uint32_t sum = 0;
+            const uint32_t top = nb - tid * seg;
+            for (uint32_t b = 0; b < seg; ++b) sum += hist[top - 1 - b];
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (tid >= o) incl += t;
+            }
+            const uint32_t excl = incl - sum;
+            if (excl < remaining && remaining <= incl) {
+                uint32_t above = excl, b = top;
+                for (;;) {
+                    --b;
+                    const uint32_t h = hist[b];
+                    if (above + h >= remaining) break;
+                    above += h;
+                }
+                sh[0] = b;
+                sh[1] = remaining - above;
+                sh[2] = hist[b];
+            }
+        }
+        __syncthreads();
+        const uint32_t b = sh[0];
+        remaining = sh[1];
+        ties_total = sh[2];
+        prefix |= b << shift;
+        pmask |= (nb - 1) << shift;
+        __syncthreads();
+    }
+    SelectResult r;
+    r.key = prefix;
+    r.take_ties = remaining;
+    r.ties_total = ties_total;
+    return r;
+}
+
 // block-wide exclusive prefix of a 0/1 flag for threads in row order; returns the rank
 // and adds the block total to `running` (kept identical in every thread).
 __device__ __forceinline__ uint32_t block_flag_rank(bool flag, uint32_t& running, uint32_t* s_warp /*32*/) {
@@ -278,6 +336,90 @@ __global__ void __launch_bounds__(1024) k_filter_select(const float* __restrict_
         if (ordered) {
             const uint32_t rank = block_flag_rank(tie, running, s_warp);
             keep = keep || (tie && rank < r.take_ties);
+        } else {
+            keep = keep || tie;
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0 && i < N) m[i >> 5] = bal;
+    }
+    if (threadIdx.x == 0) n_out[q] = (int32_t)cap;
+}
+
+// K5b with the REFERENCE's tie rule.  The reference sorts each level's candidate list with a stable sort
+// (rag/search/engine.py:236), and the list arrives in the previous level's order: rows whose level score ties exactly at
+// the cut are kept in the order of the previous level's score (then the level before that, then the row id).
+// prev1 / prev0: the score matrices of levels l - 1 and l - 2 (null when absent).  Deeper ties (more than three
+// levels) fall back to the row id.
+__global__ void __launch_bounds__(1024) k_filter_select_prev(const float* __restrict__ scores, int64_t scores_stride, int64_t N,
+                                                             const float* __restrict__ prev1, const float* __restrict__ prev0,
+                                                             int64_t prev_stride, const int32_t* __restrict__ n_alive,
+                                                             const int32_t* __restrict__ n_pass, double ratio,
+                                                             uint32_t* __restrict__ mask, int64_t mask_stride,
+                                                             int32_t* __restrict__ n_out) {
+    __shared__ uint32_t hist[2048];
+    __shared__ uint32_t sh[4];
+    __shared__ uint32_t s_warp[32];
+    const int q = blockIdx.x;
+    const int64_t na = n_alive[q], np = n_pass[q];
+    int64_t cap = (int64_t)((double)na * ratio);
+    if (cap < 1) cap = 1;
+    if (np <= cap) {
+        if (threadIdx.x == 0) n_out[q] = (int32_t)np;
+        return;
+    }
+    const float* s = scores + (int64_t)q * scores_stride;
+    const float* p1 = prev1 ? prev1 + (int64_t)q * prev_stride : nullptr;
+    const float* p0 = prev0 ? prev0 + (int64_t)q * prev_stride : nullptr;
+    const SelectResult r = block_radix_select(s, N, (uint32_t)cap, hist, sh);
+    const bool ordered = r.take_ties < r.ties_total;
+    SelectResult r1{0u, 0u, 0u}, r2{0u, 0u, 0u};
+    const bool use1 = ordered && p1 != nullptr;
+    bool use2 = false;
+    if (use1) {
+        r1 = block_radix_select_fn([&](int64_t i, uint32_t& key) {
+                 const float v = __ldg(s + i);
+                 if (!(v >= 0.f) || __float_as_uint(v) != r.key) return false;
+                 key = __float_as_uint(fmaxf(__ldg(p1 + i), 0.f));
+                 return true;
+             }, N, r.take_ties, hist, sh);
+        use2 = p0 != nullptr && r1.take_ties < r1.ties_total;
+        if (use2)
+            r2 = block_radix_select_fn([&](int64_t i, uint32_t& key) {
+                     const float v = __ldg(s + i);
+                     if (!(v >= 0.f) || __float_as_uint(v) != r.key) return false;
+                     if (__float_as_uint(fmaxf(__ldg(p1 + i), 0.f)) != r1.key) return false;
+                     key = __float_as_uint(fmaxf(__ldg(p0 + i), 0.f));
+                     return true;
+                 }, N, r1.take_ties, hist, sh);
+    }
+    uint32_t* m = mask + (int64_t)q * mask_stride;
+    uint32_t running = 0;
+    const int lane = threadIdx.x & 31;
+    for (int64_t base = 0; base < N; base += blockDim.x) {
+        const int64_t i = base + threadIdx.x;
+        const float v = i < N ? __ldg(s + i) : -1.f;
+        const uint32_t key = __float_as_uint(v);
+        bool keep = v >= 0.f && key > r.key;
+        const bool tie = v >= 0.f && key == r.key;
+        if (ordered) {
+            bool id_tie = tie;                       // rows still tied after every available level: lower row id first
+            uint32_t take = r.take_ties;
+            if (use1 && tie) {
+                const uint32_t k1 = __float_as_uint(fmaxf(__ldg(p1 + i), 0.f));
+                id_tie = false;
+                if (k1 > r1.key) keep = true;
+                else if (k1 == r1.key) {
+                    if (!use2) id_tie = true;
+                    else {
+                        const uint32_t k0 = __float_as_uint(fmaxf(__ldg(p0 + i), 0.f));
+                        if (k0 > r2.key) keep = true;
+                        else if (k0 == r2.key) id_tie = true;
+                    }
+                }
+            }
+            if (use1) take = use2 ? r2.take_ties : r1.take_ties;
+            const uint32_t rank = block_flag_rank(id_tie, running, s_warp);
+            keep = keep || (id_tie && rank < take);
         } else {
             keep = keep || tie;
         }
@@ -693,6 +835,21 @@ extern "C" int hq_filter_select(const float* scores, int64_t scores_stride, int6
     HQ_REQUIRE(N < ((int64_t)1 << 31), "N too large for one shard");
     k_filter_select<<<Q, 1024, 0, (cudaStream_t)stream>>>(scores, scores_stride, N, n_alive, n_pass, ratio, mask, mask_stride, n_out);
     HQ_LAUNCH_OK("k_filter_select");
+    return HQ_OK;
+}
+
+extern "C" int hq_filter_select_prev(const float* scores, int64_t scores_stride, int64_t N, int Q, const float* prev1, const float* prev0,
+                                     int64_t prev_stride, const int32_t* n_alive, const int32_t* n_pass, double ratio, uint32_t* mask,
+                                     int64_t mask_stride, int32_t* n_out, void* stream) {
+    HQ_REQUIRE(N >= 0 && Q >= 0, "negative size");
+    if (N == 0 || Q == 0) return HQ_OK;
+    HQ_REQUIRE(scores && n_alive && n_pass && mask && n_out, "null pointer");
+    HQ_REQUIRE(N < ((int64_t)1 << 31), "N too large for one shard");
+    HQ_REQUIRE(!prev0 || prev1, "prev0 (level l - 2) needs prev1 (level l - 1)");
+    HQ_REQUIRE(!prev1 || prev_stride >= N, "prev stride too small");
+    k_filter_select_prev<<<Q, 1024, 0, (cudaStream_t)stream>>>(scores, scores_stride, N, prev1, prev0, prev_stride, n_alive, n_pass, ratio,
+                                                               mask, mask_stride, n_out);
+    HQ_LAUNCH_OK("k_filter_select_prev");
     return HQ_OK;
 }
 

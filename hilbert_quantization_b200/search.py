@@ -327,7 +327,8 @@ def shard_ingest(emb: torch.Tensor, n: int, want_bf16: bool = True):
     norms = torch.empty(N, dtype=torch.float32, device=d)
     unit = torch.empty((N, D), dtype=torch.bfloat16, device=d) if want_bf16 else None
     with torch.cuda.device(d):
-        check(lib.hq_shard_ingest(dev.ptr(emb), N, D, emb.stride(0), dev.ptr(codes), Lsum, dev.ptr(idx), idx.stride(0),
+        emb_stride = emb.stride(0) if N > 1 else D           # (a size-1 axis may report any stride)
+        check(lib.hq_shard_ingest(dev.ptr(emb), N, D, emb_stride, dev.ptr(codes), Lsum, dev.ptr(idx), idx.stride(0),
                                   dev.ptr(norms), dev.ptr(unit) if unit is not None else None, D, dev.stream_ptr()))
     return idx, norms, unit
 
@@ -361,10 +362,16 @@ def _mask_words(N: int) -> int:
 
 
 def progressive_filter(db: EmbeddingDatabase, q_idx: torch.Tensor, q_lens: torch.Tensor, scores: torch.Tensor,
-                       mask: torch.Tensor, trace: Optional[FilterTrace] = None, keep_level_scores: Optional[list] = None):
+                       mask: torch.Tensor, trace: Optional[FilterTrace] = None, keep_level_scores: Optional[list] = None,
+                       tie_rule: str = "id"):
     """Run all filter levels for the queries of one chunk.  `scores` [Qc, N] float32 and
     `mask` [Qc, words] int32 are caller-provided work buffers; on return `mask` holds the
-    survivor bits and `scores` the last level's scores (-1 for rows dead before it)."""
+    survivor bits and `scores` the last level's scores (-1 for rows dead before it).
+    tie_rule="reference": rows tied exactly at a ratio cut keep the previous levels' order (the reference's stable sort,
+    rag/search/engine.py:236) instead of the row id order; costs a copy of the score matrix per level."""
+    if tie_rule not in ("id", "reference"):
+        raise ValueError("tie_rule must be 'id' or 'reference'")
+    prev: list = []
     Qc = q_idx.shape[0]
     N = db.N
     d = db.device
@@ -378,8 +385,18 @@ def progressive_filter(db: EmbeddingDatabase, q_idx: torch.Tensor, q_lens: torch
                                       dev.ptr(mask) if level > 0 else None, mask.stride(0),
                                       rag_threshold(level), dev.ptr(scores), scores.stride(0), dev.ptr(mask),
                                       dev.ptr(n_alive), dev.ptr(n_pass), st))
-            check(lib.hq_filter_select(dev.ptr(scores), scores.stride(0), N, Qc, dev.ptr(n_alive), dev.ptr(n_pass),
-                                       rag_ratio(level), dev.ptr(mask), mask.stride(0), dev.ptr(n_out), st))
+            if tie_rule == "reference" and prev:
+                p1 = prev[-1]
+                p0 = prev[-2] if len(prev) > 1 else None
+                check(lib.hq_filter_select_prev(dev.ptr(scores), scores.stride(0), N, Qc, dev.ptr(p1), dev.ptr(p0), p1.stride(0),
+                                                dev.ptr(n_alive), dev.ptr(n_pass), rag_ratio(level), dev.ptr(mask), mask.stride(0),
+                                                dev.ptr(n_out), st))
+            else:
+                check(lib.hq_filter_select(dev.ptr(scores), scores.stride(0), N, Qc, dev.ptr(n_alive), dev.ptr(n_pass),
+                                           rag_ratio(level), dev.ptr(mask), mask.stride(0), dev.ptr(n_out), st))
+            if tie_rule == "reference" and level + 1 < db.num_levels:
+                prev.append(scores[:Qc].clone())
+                prev = prev[-2:]
             if keep_level_scores is not None:
                 keep_level_scores.append(scores.clone())
     if trace is not None:
@@ -530,8 +547,13 @@ def packed_result_buffers(Q: int, k: int, device) -> Tuple[torch.Tensor, torch.T
 def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: bool = True,
                  work_bytes: int = 4 << 30, return_mask: bool = False, trace: Optional[FilterTrace] = None,
                  rerank: str = "auto", filter_impl: str = "auto", filter_scope: str = "shard", group=None,
-                 filter_scratch_bytes: int = 24 << 30, _dense_flag: Optional[list] = None, guard_stats: Optional[list] = None):
+                 filter_scratch_bytes: int = 24 << 30, _dense_flag: Optional[list] = None, guard_stats: Optional[list] = None,
+                 tie_rule: str = "id"):
     """Progressive top-k of a batch of query embeddings against one shard.
+
+    `tie_rule`: rows whose level score ties EXACTLY at a ratio cut are kept by ascending row id ("id", every filter
+    path) or in the order of the previous levels' scores like the reference's stable sort ("reference",
+    rag/search/engine.py:236; exact filter path only -- it is selected automatically).
 
     Returns (ids int64 [Q, k] (-1 = fewer than k survivors), scores float32 [Q, k]).  Scores are
     (cos + 1) / 2 of the full embeddings; ties resolve to the lower row id.
@@ -573,6 +595,12 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
     if filter_impl not in ("auto", "fast", "fast_fp32", "exact"):
         raise ValueError("filter_impl must be 'auto', 'fast', 'fast_fp32' or 'exact'")
     n_chunk_rows = N
+    if tie_rule not in ("id", "reference"):
+        raise ValueError("tie_rule must be 'id' or 'reference'")
+    if tie_rule == "reference":
+        if filter_scope == "global" or filter_impl in ("fast", "fast_fp32"):
+            raise ValueError("tie_rule='reference' is implemented by the exact shard-local filter only")
+        filter_impl = "exact"
     if filter_scope == "global":
         filter_impl = "exact"                      # the global cut works on the per-level score matrix
         if collective:
@@ -631,7 +659,7 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
                 elif filter_scope == "global":
                     m = progressive_filter_global(db, q_idx[s:e], q_lens[s:e], scores[:nq], mask[:nq], group, trace)
                 else:
-                    m = progressive_filter(db, q_idx[s:e], q_lens[s:e], scores[:nq], mask[:nq], trace)
+                    m = progressive_filter(db, q_idx[s:e], q_lens[s:e], scores[:nq], mask[:nq], trace, tie_rule=tie_rule)
                 _end(tok)
                 if return_mask:
                     masks.append(m.clone())
@@ -673,7 +701,7 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
         del mask, scores, ids, out_scores
         return search_batch(db, queries, k, use_filter=use_filter, work_bytes=work_bytes, return_mask=return_mask, trace=trace,
                             rerank=rerank, filter_impl="exact", filter_scope=filter_scope, group=group,
-                            filter_scratch_bytes=filter_scratch_bytes, guard_stats=guard_stats)
+                            filter_scratch_bytes=filter_scratch_bytes, guard_stats=guard_stats, tie_rule=tie_rule)
     if return_mask:
         return ids, out_scores, (torch.cat(masks) if masks else None)
     return ids, out_scores

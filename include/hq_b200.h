@@ -166,6 +166,13 @@ int hq_filter_level(const float* idx, const uint16_t* lens, int64_t N, const hq_
 int hq_filter_select(const float* scores, int64_t scores_stride, int64_t N, int Q,
                      const int32_t* n_alive, const int32_t* n_pass, double ratio,
                      uint32_t* mask, int64_t mask_stride, int32_t* n_out, void* stream);
+/* The same cut with the reference's tie rule (stable sort of a list that arrives in the previous level's order,
+ * rag/search/engine.py:236): rows tied exactly at the cut score are kept in the order of the previous level's score
+ * (prev1 [Q, prev_stride], level l - 1), then of the level before (prev0, level l - 2), then by row id.  prev1 / prev0 may
+ * be null (first levels). */
+int hq_filter_select_prev(const float* scores, int64_t scores_stride, int64_t N, int Q, const float* prev1, const float* prev0,
+                          int64_t prev_stride, const int32_t* n_alive, const int32_t* n_pass, double ratio, uint32_t* mask,
+                          int64_t mask_stride, int32_t* n_out, void* stream);
 
 /* Fast path of the same filter (no score matrix): one pass computes the threshold tests of
  * all levels as bit planes, then one CTA per query walks the levels and ranks rows exactly

@@ -34,7 +34,7 @@ def run(files=None, native: bool = False, extra=(), timeout: int = 1500) -> dict
     with tempfile.TemporaryDirectory() as tmp:
         xml = os.path.join(tmp, "junit.xml")
         cmd = [sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "--rootdir", REF, f"--junitxml={xml}",
-               "-o", "junit_family=xunit1", "--tb=short", *extra]
+               "-o", "junit_family=xunit1", "--tb=short", "-p", "hq_seed_plugin", *extra]
         if not native:
             cmd += ["-p", "hq_dropin_plugin"]
         cmd += [os.path.join(REF, "ref_tests", f) for f in files]

@@ -709,3 +709,42 @@ def test_shard_ingest_declines_shapes_it_does_not_cover(hq):
         assert shard_ingest(torch.randn((10, D), device="cuda"), rag_optimal_dimensions(D)[0]) is None
     d = hq.EmbeddingDatabase(torch.randn((300, 250), device="cuda"))          # falls back to the separate passes
     assert d.idx.shape[0] == 300 and d.emb_bf16 is not None
+
+
+# ------------------------------------------------------------------ a12: the reference's tie rule at the ratio cuts
+def test_exact_ties_at_a_ratio_cut_follow_the_previous_level_like_the_reference(hq):
+    """Rows that differ only by a permutation of four level-0 blocks inside ONE level-1 block have identical level-1 and
+    level-2 index rows (integer values: every block mean is exact), so their level-1 / level-2 scores tie EXACTLY while their
+    level-0 scores differ.  The reference's stable sort (rag/search/engine.py:236) keeps such rows in the previous level's
+    order; `tie_rule="reference"` reproduces it (ids equal the oracle's), the default rule (lower row id) provably differs
+    on this input -- the deviation DESIGN.md section 8 documents."""
+    import itertools
+    D, n = 1536, 64
+    base = np.full(24, 2.0, dtype=np.float32)
+    rows = []
+    for perm in itertools.permutations([1.0, 2.0, 3.0, 5.0]):
+        b = base.copy()
+        b[:4] = perm
+        rows.append(np.repeat(b, 64))
+    db = np.stack(rows).astype(np.float32)                      # 24 rows, constant inside every level-0 block
+    order = np.random.default_rng(0).permutation(len(db))       # level-0 score is not monotone in the row id
+    db = db[order]
+    q = np.repeat(np.concatenate([[5.0, 3.0, 2.0, 1.0], np.full(20, 2.0)]).astype(np.float32), 64)
+    d = hq.EmbeddingDatabase(db, n=n)
+    want_i, want_s = O.progressive_search(q, db, n, 10)
+    ids_ref, sc_ref = hq.search_batch(d, q[None, :], 10, tie_rule="reference")
+    m = len(want_i)
+    assert m >= 2
+    assert list(ids_ref[0, :m].cpu().numpy()) == list(want_i), (ids_ref[0].cpu().numpy(), want_i)
+    assert (ids_ref[0, m:] == -1).all()
+    assert np.abs(sc_ref[0, :m].cpu().numpy() - want_s).max() < 5e-7
+    ids_id, _ = hq.search_batch(d, q[None, :], 10, filter_impl="exact")
+    assert sorted(ids_id[0, :m].cpu().numpy()) != sorted(want_i)         # the row-id rule keeps other rows of the tie group
+    # the rule costs nothing when nothing ties: random rows give identical results under both rules
+    rng = np.random.default_rng(1)
+    db2 = rng.standard_normal((3000, D)).astype(np.float32)
+    qs2 = rng.standard_normal((5, D)).astype(np.float32)
+    d2 = hq.EmbeddingDatabase(db2, n=n)
+    a_i, a_s = hq.search_batch(d2, qs2, 10, tie_rule="reference")
+    b_i, b_s = hq.search_batch(d2, qs2, 10, filter_impl="exact")
+    assert torch.equal(a_i, b_i) and torch.equal(a_s, b_s)
