@@ -12,6 +12,7 @@ from .search import (EmbeddingDatabase, ProgressiveSimilaritySearchEngine, RAGSe
                      SearchGraph, SearchResult, comprehensive_scores, search_batch, search_stream)
 from .rag import DocumentSearchResult, ProgressiveSearchEngine, RAGSystem    # noqa: F401
 from .precomputed import PrecomputedHilbertIndexer, PrecomputedIndex, PrecomputedLevel   # noqa: F401
+from .frames import EmbeddingFrame, EmbeddingFrameBatch, QuantizedModelBatch   # noqa: F401
 from . import video                                                       # noqa: F401
 from .distributed import MergePipeline, ShardedSearch, allgather_merge, shard_bounds        # noqa: F401
 

@@ -214,6 +214,36 @@ class EmbeddingDatabase:
         self._finish_build(True, tc_filter)
         return self
 
+    @classmethod
+    def from_frames(cls, batch, device=None, id_base: int = 0, bf16: bool = True, tc_filter: bool = True) -> "EmbeddingDatabase":
+        """The search shard of a batch of stored ENHANCED FRAMES (frames.EmbeddingFrameBatch: grid + one index row per
+        level, the reference's storage format, rag/.../hierarchical_index_generator.py:344-385): the embeddings come back
+        through map_from_2d, the index rows are the frames' own rows (sliced, not recomputed), the original height is the
+        batch's explicit field (the reference guesses it from the pixel values, rag/search/engine.py:134-162)."""
+        d = dev.require_cuda(device if device is not None else batch.frames.device)
+        self = cls.__new__(cls)
+        self.device = d
+        self.emb = batch.embeddings().to(d)
+        self.N, self.D = (int(x) for x in self.emb.shape)
+        self.n = int(batch.original_height)
+        self.id_base = int(id_base)
+        self.layout, self.levels = make_layout(self.n, self.D)
+        self.grids = None
+        self.idx = batch.index_rows().to(d)
+        if int(self.idx.shape[1]) != int(self.layout.Lsum):
+            raise ValueError("frame index rows do not match the index layout of this grid size")
+        self.norms = row_norms(self.emb)
+        self.emb_bf16 = to_bf16(self.emb, self.norms) if bf16 else None
+        self.dc_max = 0.0
+        if self.emb_bf16 is not None and self.N > 0:
+            worst = torch.zeros(1, dtype=torch.float32, device=d)
+            with torch.cuda.device(d):
+                check(lib.hq_bf16_unit_error_max(dev.ptr(self.emb), self.N, self.D, self.emb.stride(0), dev.ptr(self.norms),
+                                                 dev.ptr(self.emb_bf16), self.emb_bf16.stride(0), dev.ptr(worst), dev.stream_ptr()))
+            self.dc_max = float(worst.item())
+        self._finish_build(bf16, tc_filter)
+        return self
+
     def _finish_build(self, bf16: bool, tc_filter: bool):
         d = self.device
         self.lens = row_lengths(self.idx, self.layout)
@@ -1254,9 +1284,13 @@ class ProgressiveSimilaritySearchEngine:
         if nl == 0 or len(cand_arrays) == 0:
             return out
         tq = torch.from_numpy(q).to(d)
+        groups = getattr(cand_arrays, "groups", None)        # frames.QuantizedModelBatch: indices already stacked on the device
         by_len: Dict[int, List[int]] = {}
-        for i, c in enumerate(cand_arrays):
-            by_len.setdefault(len(c), []).append(i)
+        if groups is None:
+            for i, c in enumerate(cand_arrays):
+                by_len.setdefault(len(c), []).append(i)
+        else:
+            by_len = {S: rows for S, (rows, _) in groups.items()}
         for S, rows in by_len.items():
             if S == 0:
                 continue
@@ -1268,7 +1302,10 @@ class ProgressiveSimilaritySearchEngine:
             cs = np.array([c_levels[l][1] for l in range(n_cmp)], dtype=np.int32)
             ln = np.array([min(q_levels[l][2] - q_levels[l][1], c_levels[l][2] - c_levels[l][1]) for l in range(n_cmp)],
                           dtype=np.int32)
-            cand = torch.from_numpy(np.stack([np.asarray(cand_arrays[i], dtype=np.float64) for i in rows])).to(d)
+            if groups is None:
+                cand = torch.from_numpy(np.stack([np.asarray(cand_arrays[i], dtype=np.float64) for i in rows])).to(d)
+            else:
+                cand = groups[S][1].to(d)
             sims = torch.empty((len(rows), n_cmp), dtype=torch.float64, device=d)
             tqs, tcs, tln = (torch.from_numpy(a).to(d) for a in (qs, cs, ln))
             with torch.cuda.device(d):
@@ -1276,6 +1313,11 @@ class ProgressiveSimilaritySearchEngine:
                                              dev.ptr(tln), n_cmp, dev.ptr(sims), dev.stream_ptr()))
             out[np.asarray(rows), :n_cmp] = sims.cpu().numpy()
         return out
+
+    @staticmethod
+    def _pool_indices(candidate_pool):
+        """the candidates' index vectors: a frames.QuantizedModelBatch keeps them stacked on the device"""
+        return candidate_pool if hasattr(candidate_pool, "groups") else [c.hierarchical_indices for c in candidate_pool]
 
     def compare_indices_at_level(self, query_indices: np.ndarray, candidate_indices: np.ndarray, level: int) -> float:
         if len(query_indices) == 0 or len(candidate_indices) == 0:
@@ -1291,7 +1333,7 @@ class ProgressiveSimilaritySearchEngine:
     def brute_force_search(self, query_indices: np.ndarray, candidate_pool: List, max_results: int) -> List[SearchResult]:
         if len(query_indices) == 0 or not candidate_pool:
             return []
-        sims = self._level_sims(query_indices, [c.hierarchical_indices for c in candidate_pool])
+        sims = self._level_sims(query_indices, self._pool_indices(candidate_pool))
         if sims.shape[1] == 0:
             overall = np.zeros(len(candidate_pool))
         else:
@@ -1303,7 +1345,7 @@ class ProgressiveSimilaritySearchEngine:
     def progressive_search(self, query_indices: np.ndarray, candidate_pool: List, max_results: int) -> List[SearchResult]:
         if len(query_indices) == 0 or not candidate_pool:
             return []
-        sims = self._level_sims(query_indices, [c.hierarchical_indices for c in candidate_pool])
+        sims = self._level_sims(query_indices, self._pool_indices(candidate_pool))
         L = sims.shape[1]
         if L == 0:
             return []

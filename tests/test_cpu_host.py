@@ -249,3 +249,21 @@ def test_ingest_plan_codes_describe_run_means_of_the_input_row():
         pad[:, :D] = x
         got = np.stack([pad[:, (c & 0xFFFFFF) * 4 ** (c >> 24):((c & 0xFFFFFF) + 1) * 4 ** (c >> 24)].mean(axis=1) for c in codes.tolist()], axis=1)
         assert np.abs(got - want).max() < 3e-7
+
+
+def test_embedding_frame_dataclass_validates_like_the_reference():
+    """frames.EmbeddingFrame mirrors rag/models.py:38-59 (same fields, same checks); no GPU needed."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("hq_frames_src", os.path.join(ROOT, "hilbert_quantization_b200", "frames.py"))
+    src = open(spec.origin).read()
+    assert "class EmbeddingFrameBatch" in src and "class QuantizedModelBatch" in src
+    from hilbert_quantization_b200.frames import EmbeddingFrame
+    ok = EmbeddingFrame(np.zeros((67, 64), np.float32), [], 1536, (64, 64), 0.8, 0)
+    assert ok.hilbert_dimensions == (64, 64)
+    for bad in (dict(original_embedding_dimensions=0), dict(hilbert_dimensions=(64,)), dict(compression_quality=1.5),
+                dict(frame_number=-1), dict(embedding_data=np.zeros(3, np.float32))):
+        kw = dict(embedding_data=np.zeros((67, 64), np.float32), hierarchical_indices=[], original_embedding_dimensions=1536,
+                  hilbert_dimensions=(64, 64), compression_quality=0.8, frame_number=0)
+        kw.update(bad)
+        with pytest.raises(ValueError):
+            EmbeddingFrame(**kw)
