@@ -523,6 +523,7 @@ def main():
         step(q_dev)
     barrier()
     lib.hq_launch_count(1)
+    lib.hq_kernel_timing(1)                           # CUDA events around the launches of the four search kernels (roofline)
     S.PHASE_TIMER = S.PhaseTimer()
     step_ms = []
     with ClockSampler(local) as clocks:
@@ -540,6 +541,11 @@ def main():
         t_all1.record()
         barrier()
     total_ms = t_all0.elapsed_time(t_all1)
+    import ctypes as _C
+    k_ms, k_n = (_C.c_float * 4)(), (_C.c_int32 * 4)()
+    lib.hq_kernel_timing_read(k_ms, k_n, 4)
+    kernel_ms = {name: (float(k_ms[i]) / args.steps, int(k_n[i]) // max(1, args.steps))
+                 for i, name in enumerate(("k_rerank_tc", "k_filter_bits_tc", "k_filter_cascade", "k_rerank_tc_merge"))}
     launches = int(lib.hq_launch_count(1))
     phases = S.PHASE_TIMER.totals_ms()
     S.PHASE_TIMER = None
@@ -659,8 +665,9 @@ def main():
     torch.cuda.synchronize()
 
     if rank == 0:
-        gemm_ms = phases.get("rerank_gemm", 0.0) / args.steps
-        flops = 2.0 * args.queries * rows * args.dim               # per launch, this rank's shard
+        phase_ms = phases.get("rerank_gemm", 0.0) / args.steps    # GEMM + shortlist merge + guard kernels
+        gemm_ms = kernel_ms["k_rerank_tc"][0] or phase_ms          # the GEMM kernel alone (events around its launches)
+        flops = 2.0 * args.queries * rows * args.dim               # per step, this rank's shard (one launch per query chunk)
         achieved_tf = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
         # roofline denominator: the BURST cuBLAS bf16 figure (the timed region is a fraction of a second; the sustained
         # figure, which this kernel exceeded in round 1, is kept as a side field)
@@ -691,13 +698,17 @@ def main():
             "gpu_launches": launches,
             "per_rank_ms_per_step": per_rank_ms,
             "phases_ms_per_step": {k: v / args.steps for k, v in phases.items()},
-            "roofline": {"kernel": "k_rerank_tc<16> + k_rerank_tc_merge<16> (Q x N x D cosine contraction, bf16 tcgen05)", "bound": "tensor",
+            "kernels_ms_per_step": {k: {"ms": v[0], "launches": v[1]} for k, v in kernel_ms.items()},
+            "roofline": {"kernel": "k_rerank_tc<16> (Q x N x D cosine contraction, bf16 tcgen05, fused mask / top-16 epilogue)", "bound": "tensor",
                          "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": (achieved_tf / peak_tf) if achieved_tf else None,
                          "traffic": ncu_traffic("k_rerank_tc") if world == 1 and args.rows == 1_000_000 else None,
                          "peak_source": pk["source"] + " (burst cuBLAS bf16)",
                          "frac_of_sustained_peak": (achieved_tf / pk["bf16_tflops"]) if achieved_tf else None,
-                         "algorithmic_flops_per_launch": flops,
+                         "algorithmic_flops_per_launch": flops / max(1, kernel_ms["k_rerank_tc"][1]),
+                         "launches_per_step": kernel_ms["k_rerank_tc"][1], "kernel_ms_per_step": gemm_ms,
+                         "timing": "CUDA events on the launching stream around every k_rerank_tc launch of the timed region",
+                         "frac_with_merge_and_guard": (flops / (phase_ms * 1e-3) / 1e12 / peak_tf) if phase_ms > 0 else None,
                          "note": "largest single kernel of the step; the coarse filter (tcgen05 tf32 window pass + window "
                                  "cascade) is issue bound, see DESIGN.md section 5 (K5w) and profiles/"},
             "clocks": clocks.summary(),

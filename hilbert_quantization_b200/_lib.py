@@ -72,6 +72,8 @@ SIGNATURES = {
     "hq_comprehensive_scores": (_i32, [_p, _i64, _i32, _i32, _i64, _p, _i32, _i64, _p, _p, _i64, _p, _p]),
     "hq_offset_square_means": (_i32, [_p, _i64, _i32, _i64, _p, _i64, _p]),
     "hq_pearson01_matrix": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _i32, _p, _i64, _p]),
+    "hq_kernel_timing": (_i32, [_i32]),
+    "hq_kernel_timing_read": (_i32, [_p, _p, _i32]),
     "hq_topk_merge": (_i32, [_p, _p, _i32, _i32, _i32, _p, _p, _p]),
     "hq_topk_merge_strided": (_i32, [_p, _p, _i32, _i32, _i32, _i64, _i64, _p, _p, _p]),
     "hq_core_level_sims": (_i32, [_p, _i64, _i32, _i64, _p, _p, _p, _p, _i32, _p, _p]),

@@ -39,6 +39,9 @@ void hq_note_launch(int n);     // bookkeeping for hq_launch_count (bench.py rep
 static inline bool hq_is_pow2(int64_t n) { return n > 0 && (n & (n - 1)) == 0; }
 static inline int hq_log2(int64_t n) { int k = 0; while ((int64_t(1) << k) < n) ++k; return k; }
 int hq_cached_sm_count();
+// per-kernel timing hooks for bench.py (hq_lib.cu): no-ops unless hq_kernel_timing(1) armed them
+int hq_time_begin(int slot, cudaStream_t st);
+void hq_time_end(int slot, int token, cudaStream_t st);
 // tensor-core bit-plane pass of the coarse filter (hq_filter_tc.cu), used by hq_filter_fast
 struct HqFilterLists {          // candidate lists written by the pass (see FtcParams in hq_filter_tc.cu)
     uint32_t* rows;

@@ -2137,9 +2137,11 @@ extern "C" int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, c
         // a few queries: one large CTA per query (latency), a batch: eight small CTAs per SM (one wave)
         static const int variant = [] { const char* e = getenv("HQ_FILTER_WINDOW_CTA"); return e ? atoi(e) : 0; }();
         const bool big = variant == 256;       // (measured at 1 M rows: 341 us against 297 us for the small CTAs; 86 / 70 us at 125 K rows)
+        const int tkw = hq_time_begin(2, st);
         if (Q <= hq_cached_sm_count()) k_filter_cascade_win<1024, 1, 2><<<wgrid, 1024, 0, st>>>(wp);
         else if (big) k_filter_cascade_win<256, 4, 4><<<wgrid > hq_cached_sm_count() * 4 ? hq_cached_sm_count() * 4 : wgrid, 256, 0, st>>>(wp);
         else k_filter_cascade_win<kWinThreads, kWinCtasPerSm, 2><<<wgrid, kWinThreads, 0, st>>>(wp);
+        hq_time_end(2, tkw, st);
         HQ_LAUNCH_OK("k_filter_cascade_win");
         // 5. fallback for the flagged queries: full-threshold planes of their query tiles, generic gather cascade
         HqFtcOpts of{};
@@ -2249,7 +2251,9 @@ extern "C" int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, c
         HQ_REQUIRE(lp.tmp_stride <= (int64_t)grid * N, "internal: candidate lists larger than the cascade scratch");
         lp.tmp_keys = reinterpret_cast<float*>(sc_keys);
         lp.tmp_rows = sc_keys + (int64_t)lgrid * lp.tmp_stride;
+        const int tkl = hq_time_begin(2, st);
         k_filter_cascade_lists<<<lgrid, lthreads, 0, st>>>(lp);
+        hq_time_end(2, tkl, st);
         HQ_LAUNCH_OK("k_filter_cascade_lists");
         cp.only = fallback;
     }

@@ -786,8 +786,10 @@ int hq_filter_tc_pass(const float* db_packed, const uint32_t* valid, int64_t val
     }
     int grid = hq_cached_sm_count();
     if (grid > p.num_units) grid = p.num_units;
+    const int tk = (win || (stride == 1 && !p.unit_only)) ? hq_time_begin(1, st) : -1;      // the main pass, not sample / fallback
     if (win) k_filter_bits_tc<true><<<grid, F_THREADS, smem_win, st>>>(mq, mdb, p);
     else k_filter_bits_tc<false><<<grid, F_THREADS, smem_full, st>>>(mq, mdb, p);
+    hq_time_end(1, tk, st);
     HQ_LAUNCH_OK("k_filter_bits_tc");
     return HQ_OK;
 }

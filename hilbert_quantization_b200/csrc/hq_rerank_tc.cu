@@ -825,7 +825,9 @@ int launch_tc(const CUtensorMap& mq, const CUtensorMap& mdb, const TcParams& p, 
     int grid = hq_cached_sm_count();
     if (grid > p.num_units) grid = p.num_units;
     HQ_CUDA_OK(cudaMemsetAsync(g.guard, 0, 4 * sizeof(int32_t), st));
+    const int tk = hq_time_begin(0, st);
     k_rerank_tc<KP, EH, true><<<grid, 64 + 128 * EH, smem, st>>>(mq, mdb, p);
+    hq_time_end(0, tk, st);
     HQ_LAUNCH_OK("k_rerank_tc");
     const size_t msm = (size_t)p.n_ranges * EH * KP * 8 + (size_t)p.n_ranges * EH + 16;
     static size_t msm_set = 48 * 1024;
@@ -834,8 +836,10 @@ int launch_tc(const CUtensorMap& mq, const CUtensorMap& mdb, const TcParams& p, 
         HQ_CUDA_OK(cudaFuncSetAttribute((k_rerank_tc_merge<KP, B16>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
         msm_set = msm;
     }
+    const int tm = hq_time_begin(3, st);
     k_rerank_tc_merge<KP, B16><<<p.Q, 128, msm, st>>>(p, db_f32, db_stride, db_b16, db_pitch, q_f32, q_stride, q_norm, k, id_base,
                                                        g.dc_max, g.guard, ids, scores);
+    hq_time_end(3, tm, st);
     HQ_LAUNCH_OK("k_rerank_tc_merge");
     // exact fallback of the flagged queries (both kernels return at once when the flag list is empty)
     k_guard_rescore<B16><<<hq_cached_sm_count() * 2, 256, 0, st>>>(p, db_f32, db_stride, db_b16, db_pitch, q_f32, q_stride, q_norm, k,

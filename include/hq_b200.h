@@ -365,6 +365,13 @@ int hq_core_level_sims(const double* cand, int64_t N, int S, int64_t cand_stride
                        const int32_t* q_start, const int32_t* c_start, const int32_t* lvl_len, int n_levels,
                        double* sims, void* stream);
 
+/* Per-kernel timing for the benchmark's roofline (CUDA events on the launching stream around the launches of the four
+ * search kernels): hq_kernel_timing(1) arms it, hq_kernel_timing_read synchronises and returns, per slot, the summed
+ * milliseconds and the number of launches since it was armed (slot 0 k_rerank_tc, 1 k_filter_bits_tc main pass,
+ * 2 k_filter_cascade_win / _lists, 3 k_rerank_tc_merge), then disarms. */
+int hq_kernel_timing(int on);
+int hq_kernel_timing_read(float* ms_out, int32_t* n_out, int slots);
+
 #ifdef __cplusplus
 }
 #endif
