@@ -1,4 +1,5 @@
 #!/usr/bin/env bash
+# 2-GPU checks: cross-rank NCCL parity (tests/multi/nccl_check.py) + bench at 125 K and 500 K rows per GPU:  gpurun --gpus 2 -- bash tools/gpu_multi_check.sh
 set -u
 mkdir -p gpurun_out
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29655 tests/multi/nccl_check.py > gpurun_out/nccl_check_n2.txt 2>&1; echo "nccl_check rc=$?"
