@@ -2097,8 +2097,10 @@ extern "C" int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, c
         // 1 M x 1536 rows (tools/window_fallback_rate.py): z = 3 -> 34 fallbacks in 24576 queries, 3.5 -> 6, 4 -> 1, 5 -> 0
         // (the "+ 4 ranks + bin population" slack makes the windows a little wider than z sigma).  z = 4 against z = 5:
         // window pass 1.45 -> 1.36 ms, window cascade 0.32 -> 0.27 ms; a fallback costs ~0.35 ms once per ~25 batches.
-        static const float zwin = [] { const char* e = getenv("HQ_FILTER_WINDOW_Z"); return e ? (float)atof(e) : 4.0f; }();
-        pp.z = zwin;
+        // Large shards keep z = 5: a fallback ends in the generic gather cascade, whose cost grows with the shard (~12 ms for
+        // one query against 12.5 M rows: more than the 5 ms per 4096-query batch the narrower windows save there).
+        static const float zwin = [] { const char* e = getenv("HQ_FILTER_WINDOW_Z"); return e ? (float)atof(e) : 0.0f; }();
+        pp.z = zwin > 0.f ? zwin : (N > 2000000 ? 5.0f : 4.0f);
         pp.tq = tq; pp.nq = nq; pp.l_k1 = l_k1; pp.l_k2 = l_k2; pp.seg_n = seg_n; pp.seg_cap = wg.seg_cap_s; pp.n_segs = wg.n_segs_s;
         pp.c0_s = c0_s; pp.win = win; pp.pflag = pflag;
         k_filter_predict<<<Q, 256, 0, st>>>(pp);
