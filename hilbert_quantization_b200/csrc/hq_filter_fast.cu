@@ -536,6 +536,8 @@ struct ListParams {
     int32_t* counts;             // optional [L][3][Q]
     int32_t* n_out;              // [Q]
     int32_t* fallback;           // [Q] out
+    const int32_t* only;         // optional [Q]: process only queries with a non-zero flag (second stage of the window mode);
+                                 // their mask rows are zero-filled here first
     float* tmp_keys;             // [gridDim][tmp_stride] compacted level-2 candidates of the query in flight
     uint32_t* tmp_rows;          // [gridDim][tmp_stride]
     int64_t tmp_stride;          // >= n_segs * seg_cap
@@ -714,6 +716,10 @@ __global__ void __launch_bounds__(kListThreads, 1) k_filter_cascade_lists(const 
     uint32_t* const c_row = p.tmp_rows + (int64_t)blockIdx.x * p.tmp_stride;
 
     for (int q = blockIdx.x; q < p.Q; q += gridDim.x) {
+        if (p.only) {
+            if (!__ldg(p.only + q)) continue;
+            for (int64_t w = tid; w < p.words; w += nt) p.mask[(int64_t)q * p.mask_stride + w] = 0u;
+        }
         // ---- segment table, overflow check ----
         if (tid == 0) { s_flag = 0; s_n2 = 0; s_bufn = 0; }
         __syncthreads();
@@ -2012,7 +2018,8 @@ extern "C" int hq_filter_fast_window_layout(int64_t N, int Q, const hq_index_lay
     out[2] = take((int64_t)4 * Q * 4);                    // counters
     out[3] = take((int64_t)Q * 4);                        // c0 of the sample
     out[4] = take((int64_t)Q * 4);                        // prediction flags
-    out[5] = take((int64_t)Q * 4);                        // tile flags
+    (void)take((int64_t)Q * 4);
+    out[5] = fb + (int64_t)Q * 4;                         // query-tile flags (int32 [Q / 128]); second-stage failures follow at fb + 8 Q
     out[6] = take((int64_t)Q * win_seg_slots(wg) * 4);    // segment counts (window geometry after the search)
     out[7] = wg.n_segs_w; out[8] = wg.seg_cap_w; out[9] = wg.stride;
     return HQ_OK;
@@ -2069,7 +2076,11 @@ extern "C" int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, c
         int32_t* const wcnt = reinterpret_cast<int32_t*>(take((int64_t)4 * Q * 4));
         int32_t* const c0_s = reinterpret_cast<int32_t*>(take((int64_t)Q * 4));
         int32_t* const pflag = reinterpret_cast<int32_t*>(take((int64_t)Q * 4));
-        int32_t* const tile_flag = reinterpret_cast<int32_t*>(take((int64_t)Q * 4));
+        (void)take((int64_t)Q * 4);                      // (slot kept so that the documented layout offsets stay valid)
+        // flags that must survive the second stage (its full lists overwrite this window block): the fallback block has
+        // room for three int32 per query -- [0, Q) window-stage failures, [Q, 2Q) query-tile flags, [2Q, 3Q) second-stage failures
+        int32_t* const tile_flag = fallback + Q;
+        int32_t* const fallback2 = fallback + 2 * (int64_t)Q;
         int32_t* const seg_n = reinterpret_cast<int32_t*>(take((int64_t)Q * win_seg_slots(wg) * 4));
         const int64_t ents = win_list_entries(wg);
         uint32_t* const l_rows = reinterpret_cast<uint32_t*>(take((int64_t)Q * ents * 4));
@@ -2081,7 +2092,7 @@ extern "C" int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, c
         if (rc != HQ_OK) return rc;
         // wcnt | c0_s | pflag | tile_flag are contiguous
         HQ_CUDA_OK(cudaMemsetAsync(wcnt, 0, (size_t)(reinterpret_cast<unsigned char*>(seg_n) - reinterpret_cast<unsigned char*>(wcnt)), st));
-        HQ_CUDA_OK(cudaMemsetAsync(fallback, 0, (size_t)Q * 4, st));
+        HQ_CUDA_OK(cudaMemsetAsync(fallback, 0, (size_t)Q * 12, st));
         // 1. sample pass
         HqFilterLists ls{};
         ls.rows = l_rows; ls.k1 = l_k1; ls.k2 = L > 2 ? l_k2 : nullptr; ls.seg_n = seg_n; ls.seg_cap = wg.seg_cap_s; ls.n_segs = wg.n_segs_s;
@@ -2149,16 +2160,45 @@ extern "C" int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, c
         else k_filter_cascade_win<kWinThreads, kWinCtasPerSm, 2><<<wgrid, kWinThreads, 0, st>>>(wp);
         hq_time_end(2, tkw, st);
         HQ_LAUNCH_OK("k_filter_cascade_win");
-        // 5. fallback for the flagged queries: full-threshold planes of their query tiles, generic gather cascade
+        // 5. second stage for the flagged queries (a cut outside its window, a list overflow): the full-threshold pass with
+        //    FULL candidate lists for their 128-query tiles, then the streaming list cascade for exactly those queries --
+        //    the round-1 path, which needs no prediction.  Only what that cannot decide either (the level-0 cut binds, the
+        //    full lists overflow) goes on to the generic gather cascade, whose cost grows with the shard (~12 ms per query
+        //    against 12.5 M rows).  No flagged query: three launches that return at once.
         HqFtcOpts of{};
         of.tile_stride = 1; of.unit_only = tile_flag;
-        rc = hq_filter_tc_pass(db_packed, valid, valid_pitch, N, layout, Q, q_packed, tq, planes, pitch, nullptr, &of, st);
+        const bool stage2_lists = lg.on;
+        rc = hq_filter_tc_pass(db_packed, valid, valid_pitch, N, layout, Q, q_packed, tq, planes, pitch, stage2_lists ? &lists : nullptr, &of, st);
         if (rc != HQ_OK) return rc;
         if (n_exc > 0) {
-            ep.l_rows = nullptr; ep.l_k1 = nullptr; ep.l_k2 = nullptr; ep.seg_n = nullptr;
+            if (stage2_lists) {
+                ep.l_rows = lists.rows; ep.l_k1 = lists.k1; ep.l_k2 = lists.k2; ep.seg_n = lists.seg_n; ep.seg_cap = lists.seg_cap;
+                ep.n_segs = lists.n_segs; ep.extra_seg = lists.n_segs - 1;
+                HQ_CUDA_OK(cudaMemset2DAsync(lists.seg_n + ep.extra_seg, (size_t)lists.n_segs * 4, 0, 4, (size_t)Q, st));
+            } else {
+                ep.l_rows = nullptr; ep.l_k1 = nullptr; ep.l_k2 = nullptr; ep.seg_n = nullptr;
+            }
             const int64_t pairs = (int64_t)Q * n_exc;
             k_filter_exceptions<<<(unsigned)((pairs + 127) / 128), 128, 0, st>>>(ep);
             HQ_LAUNCH_OK("k_filter_exceptions");
+        }
+        const int32_t* generic_only = fallback;
+        if (stage2_lists) {
+            ListParams lp{};
+            lp.bits = planes; lp.words = words; lp.bits_pitch = pitch; lp.N = N; lp.L = L; lp.Q = Q;
+            for (int l = 0; l < 8; ++l) lp.ratio[l] = l < L ? ratio[l] : 1.0;
+            lp.tq = tq; lp.nq = nq; lp.l_rows = lists.rows; lp.l_k1 = lists.k1; lp.l_k2 = lists.k2; lp.seg_n = lists.seg_n;
+            lp.seg_cap = lists.seg_cap; lp.n_segs = lists.n_segs; lp.mask = mask; lp.mask_stride = mask_stride; lp.counts = nullptr;
+            lp.n_out = n_out; lp.fallback = fallback2; lp.only = fallback;
+            lp.tmp_stride = (int64_t)lists.n_segs * lists.seg_cap;
+            int lgrid = hq_cached_sm_count();
+            if (lgrid > Q) lgrid = Q;
+            while (lgrid > 1 && (int64_t)lgrid * lp.tmp_stride > (int64_t)grid * N) --lgrid;
+            lp.tmp_keys = reinterpret_cast<float*>(sc_keys);
+            lp.tmp_rows = sc_keys + (int64_t)lgrid * lp.tmp_stride;
+            k_filter_cascade_lists<<<lgrid, kListThreads, 0, st>>>(lp);
+            HQ_LAUNCH_OK("k_filter_cascade_lists");
+            generic_only = fallback2;
         }
         CascadeParams cp{};
         cp.bits = planes; cp.words = words; cp.bits_pitch = pitch; cp.idx = idx; cp.N = N; cp.lay = *layout; cp.q_idx = q_idx; cp.Q = Q;
@@ -2169,7 +2209,7 @@ extern "C" int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, c
             HQ_REQUIRE(!cp.lvl[l] || (cp.lvl_pitch[l] % 4 == 0 && cp.lvl_pitch[l] >= ((layout->lvl_keff[l] + 3) & ~3)), "bad level pitch");
         }
         cp.mask = mask; cp.mask_stride = mask_stride; cp.counts = nullptr; cp.n_out = n_out;
-        cp.scratch_keys = sc_keys; cp.scratch_rows = sc_rows; cp.only = fallback;
+        cp.scratch_keys = sc_keys; cp.scratch_rows = sc_rows; cp.only = generic_only;
         cp.lens = n_exc > 0 ? lens : nullptr;
         k_filter_cascade<<<grid, 1024, 0, st>>>(cp);
         HQ_LAUNCH_OK("k_filter_cascade");
