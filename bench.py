@@ -64,11 +64,14 @@ def parse():
 def ncu_traffic(kernel: str):
     """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture of this benchmark
     (profiles/r01_traffic.json, written by tools/ncu_summary.py --traffic); None when absent."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    try:
-        return json.load(open(path)).get(kernel)
-    except Exception:
-        return None
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            v = json.load(open(os.path.join(ROOT, "profiles", name))).get(kernel)
+        except Exception:
+            v = None
+        if v is not None:
+            return v
+    return None
 
 
 def peaks():
