@@ -110,10 +110,16 @@ class MergePipeline:
         self.stream = torch.cuda.Stream(device=self.device)
         self._inflight: list = []
 
+    def reserve(self):
+        """The main stream waits until fewer than `depth` merges are in flight.  Call it BEFORE producing the next batch's
+        results when those live in reused buffers (SearchGraph output buffers: two graphs alternate, depth = 2)."""
+        main = torch.cuda.current_stream(self.device)
+        while len(self._inflight) >= self.depth:
+            main.wait_event(self._inflight.pop(0))
+
     def submit(self, local_ids: torch.Tensor, local_scores: torch.Tensor, k: int):
         main = torch.cuda.current_stream(self.device)
-        if len(self._inflight) >= self.depth:        # bound the work queued on the communication stream
-            main.wait_event(self._inflight.pop(0))
+        self.reserve()                               # bound the work queued on the communication stream
         ready = torch.cuda.Event()
         ready.record(main)
         self.stream.wait_event(ready)
