@@ -72,6 +72,10 @@ SIGNATURES = {
     "hq_comprehensive_scores": (_i32, [_p, _i64, _i32, _i32, _i64, _p, _i32, _i64, _p, _p, _i64, _p, _p]),
     "hq_offset_square_means": (_i32, [_p, _i64, _i32, _i64, _p, _i64, _p]),
     "hq_pearson01_matrix": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _i32, _p, _i64, _p]),
+    "hq_gcut_hist": (_i32, [_p, _i64, _i64, _i32, _p, _i64, _p, _p, _p, _p]),
+    "hq_gcut_scan": (_i32, [_p, _i32, _p, _p, _p, _p, _p]),
+    "hq_gcut_ties": (_i32, [_p, _i64, _i64, _i32, _p, _i64, _p, _p, _p, _p]),
+    "hq_gcut_apply": (_i32, [_p, _i64, _i64, _i32, _p, _i64, _p, _p, _p, _p]),
     "hq_kernel_timing": (_i32, [_i32]),
     "hq_kernel_timing_read": (_i32, [_p, _p, _i32]),
     "hq_topk_merge": (_i32, [_p, _p, _i32, _i32, _i32, _p, _p, _p]),

@@ -430,6 +430,119 @@ __global__ void __launch_bounds__(1024) k_filter_select_prev(const float* __rest
 }
 
 // ------------------------------------------------------------------------------------
+// filter_scope = "global" (row-sharded database, the reference's SINGLE candidate list, rag/search/engine.py:272-287):
+// the exact cut score of every query is found with two all-reduced histograms over the float32 bit pattern of the level
+// scores (high 16 bits, then low 16 bits inside the winning high digit), ties at the cut score go to the lower GLOBAL row
+// id.  These kernels are the per-shard halves; the host glue (distributed.global_ratio_cut_device) does the collectives on
+// [Q, 65536] int32 histograms and [Q] vectors -- no [Q, N] boolean or int64 tensor is ever materialised (the first
+// version went through eager PyTorch on such tensors: 51 GB per level for a 4096 x 12.5 M chunk).
+// ------------------------------------------------------------------------------------
+// hist[q][digit] += 1 for every passed row of a query that needs the cut; pass 1: digit = key >> 16, pass 2: digit = key &
+// 0xffff for rows whose high digit equals d_hi[q].  grid = (chunks of rows, Q).
+__global__ void __launch_bounds__(256) k_gcut_hist(const float* __restrict__ scores, int64_t scores_stride, int64_t N,
+                                                   const uint32_t* __restrict__ mask, int64_t mask_stride,
+                                                   const int32_t* __restrict__ need, const int32_t* __restrict__ d_hi,
+                                                   int32_t* __restrict__ hist) {
+    const int q = blockIdx.y;
+    if (!need[q]) return;
+    const float* s = scores + (int64_t)q * scores_stride;
+    const uint32_t* m = mask + (int64_t)q * mask_stride;
+    int32_t* h = hist + (int64_t)q * 65536;
+    const int hi = d_hi ? d_hi[q] : -1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        if (!((__ldg(m + (i >> 5)) >> (i & 31)) & 1u)) continue;
+        const uint32_t key = __float_as_uint(fmaxf(__ldg(s + i), 0.f));
+        if (d_hi) {
+            if ((int)(key >> 16) == hi) atomicAdd(h + (key & 0xffffu), 1);
+        } else {
+            atomicAdd(h + (key >> 16), 1);
+        }
+    }
+}
+
+// largest digit d with #(digit >= d) >= want[q]; above[q] = #(digit > d).  One CTA of 1024 threads per query.
+__global__ void __launch_bounds__(1024) k_gcut_scan(const int32_t* __restrict__ hist, const int32_t* __restrict__ need,
+                                                    const int64_t* __restrict__ want, int64_t* __restrict__ d_out,
+                                                    int64_t* __restrict__ above_out) {
+    __shared__ long long s_part[1024];
+    const int q = blockIdx.x, tid = threadIdx.x;
+    if (!need[q]) return;
+    const int32_t* h = hist + (int64_t)q * 65536;
+    // thread t owns the 64 digits [65536 - 64 (t + 1), 65536 - 64 t): thread 0 the top ones
+    const int top = 65536 - 64 * tid;
+    long long sum = 0;
+    for (int b = 0; b < 64; ++b) sum += h[top - 1 - b];
+    s_part[tid] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        long long run = 0;
+        for (int t = 0; t < 1024; ++t) { const long long v = s_part[t]; s_part[t] = run; run += v; }   // exclusive, from the top
+    }
+    __syncthreads();
+    const long long w = want[q];
+    long long above = s_part[tid];
+    if (above < w && w <= above + sum) {
+        int b = top;
+        for (;;) {
+            --b;
+            const long long c = h[b];
+            if (above + c >= w) break;
+            above += c;
+        }
+        d_out[q] = b;
+        above_out[q] = above;
+    }
+}
+
+// local number of passed rows whose score equals the cut score
+__global__ void __launch_bounds__(256) k_gcut_ties(const float* __restrict__ scores, int64_t scores_stride, int64_t N,
+                                                   const uint32_t* __restrict__ mask, int64_t mask_stride,
+                                                   const int32_t* __restrict__ need, const int64_t* __restrict__ k_star,
+                                                   int64_t* __restrict__ ties) {
+    const int q = blockIdx.y;
+    if (!need[q]) return;
+    const float* s = scores + (int64_t)q * scores_stride;
+    const uint32_t* m = mask + (int64_t)q * mask_stride;
+    const uint32_t ks = (uint32_t)k_star[q];
+    unsigned long long c = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x)
+        if (((__ldg(m + (i >> 5)) >> (i & 31)) & 1u) && __float_as_uint(fmaxf(__ldg(s + i), 0.f)) == ks) ++c;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(reinterpret_cast<unsigned long long*>(ties + q), c);
+}
+
+// keep = passed && (key > k*  ||  (key == k* && rank among this shard's ties (ascending row id) < quota[q]))
+__global__ void __launch_bounds__(1024) k_gcut_apply(const float* __restrict__ scores, int64_t scores_stride, int64_t N,
+                                                     uint32_t* __restrict__ mask, int64_t mask_stride,
+                                                     const int32_t* __restrict__ need, const int64_t* __restrict__ k_star,
+                                                     const int64_t* __restrict__ quota) {
+    __shared__ uint32_t s_warp[32];
+    const int q = blockIdx.x;
+    if (!need[q]) return;
+    const float* s = scores + (int64_t)q * scores_stride;
+    uint32_t* m = mask + (int64_t)q * mask_stride;
+    const uint32_t ks = (uint32_t)k_star[q];
+    const long long qt = quota[q];
+    uint32_t running = 0;
+    const int lane = threadIdx.x & 31;
+    for (int64_t base = 0; base < N; base += blockDim.x) {
+        const int64_t i = base + threadIdx.x;
+        bool passed = false;
+        uint32_t key = 0;
+        if (i < N) {
+            passed = (m[i >> 5] >> (i & 31)) & 1u;
+            key = __float_as_uint(fmaxf(__ldg(s + i), 0.f));
+        }
+        const bool tie = passed && key == ks;
+        const uint32_t rank = block_flag_rank(tie, running, s_warp);       // barriers inside: the word is read before it is rewritten
+        const bool keep = passed && (key > ks || (tie && (long long)rank < qt));
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0 && i < N) m[i >> 5] = bal;
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // exact fp32 rerank scores: tiled FMA GEMM (64 queries x 128 rows x 16 k per step)
 // ------------------------------------------------------------------------------------
 constexpr int kBM = 64, kBN = 128, kBK = 16;
@@ -850,6 +963,49 @@ extern "C" int hq_filter_select_prev(const float* scores, int64_t scores_stride,
     k_filter_select_prev<<<Q, 1024, 0, (cudaStream_t)stream>>>(scores, scores_stride, N, prev1, prev0, prev_stride, n_alive, n_pass, ratio,
                                                                mask, mask_stride, n_out);
     HQ_LAUNCH_OK("k_filter_select_prev");
+    return HQ_OK;
+}
+
+extern "C" int hq_gcut_hist(const float* scores, int64_t scores_stride, int64_t N, int Q, const uint32_t* mask, int64_t mask_stride,
+                            const int32_t* need, const int32_t* d_hi, int32_t* hist, void* stream) {
+    HQ_REQUIRE(N >= 0 && Q >= 0, "negative size");
+    if (N == 0 || Q == 0) return HQ_OK;
+    HQ_REQUIRE(scores && mask && need && hist, "null pointer");
+    int64_t chunks = (N + 256 * 64 - 1) / (256 * 64);
+    if (chunks > 64) chunks = 64;
+    k_gcut_hist<<<dim3((unsigned)chunks, (unsigned)Q), 256, 0, (cudaStream_t)stream>>>(scores, scores_stride, N, mask, mask_stride, need, d_hi, hist);
+    HQ_LAUNCH_OK("k_gcut_hist");
+    return HQ_OK;
+}
+
+extern "C" int hq_gcut_scan(const int32_t* hist, int Q, const int32_t* need, const int64_t* want, int64_t* d_out, int64_t* above_out,
+                            void* stream) {
+    if (Q <= 0) return HQ_OK;
+    HQ_REQUIRE(hist && need && want && d_out && above_out, "null pointer");
+    k_gcut_scan<<<Q, 1024, 0, (cudaStream_t)stream>>>(hist, need, want, d_out, above_out);
+    HQ_LAUNCH_OK("k_gcut_scan");
+    return HQ_OK;
+}
+
+extern "C" int hq_gcut_ties(const float* scores, int64_t scores_stride, int64_t N, int Q, const uint32_t* mask, int64_t mask_stride,
+                            const int32_t* need, const int64_t* k_star, int64_t* ties, void* stream) {
+    HQ_REQUIRE(N >= 0 && Q >= 0, "negative size");
+    if (N == 0 || Q == 0) return HQ_OK;
+    HQ_REQUIRE(scores && mask && need && k_star && ties, "null pointer");
+    int64_t chunks = (N + 256 * 64 - 1) / (256 * 64);
+    if (chunks > 64) chunks = 64;
+    k_gcut_ties<<<dim3((unsigned)chunks, (unsigned)Q), 256, 0, (cudaStream_t)stream>>>(scores, scores_stride, N, mask, mask_stride, need, k_star, ties);
+    HQ_LAUNCH_OK("k_gcut_ties");
+    return HQ_OK;
+}
+
+extern "C" int hq_gcut_apply(const float* scores, int64_t scores_stride, int64_t N, int Q, uint32_t* mask, int64_t mask_stride,
+                             const int32_t* need, const int64_t* k_star, const int64_t* quota, void* stream) {
+    HQ_REQUIRE(N >= 0 && Q >= 0, "negative size");
+    if (N == 0 || Q == 0) return HQ_OK;
+    HQ_REQUIRE(scores && mask && need && k_star && quota, "null pointer");
+    k_gcut_apply<<<Q, 1024, 0, (cudaStream_t)stream>>>(scores, scores_stride, N, mask, mask_stride, need, k_star, quota);
+    HQ_LAUNCH_OK("k_gcut_apply");
     return HQ_OK;
 }
 

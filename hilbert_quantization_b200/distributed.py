@@ -215,6 +215,62 @@ def global_ratio_cut(scores: torch.Tensor, passed: torch.Tensor, n_alive_local: 
     return keep, n_out
 
 
+def global_ratio_cut_device(scores: torch.Tensor, mask: torch.Tensor, N: int, n_alive_local: torch.Tensor,
+                            n_pass_local: torch.Tensor, ratio: float, id_base: int, group=None) -> torch.Tensor:
+    """`global_ratio_cut` on the device without [Q, N] temporaries: `scores` [Q, >= N] float32 are the level scores of
+    hq_filter_level, `mask` [Q, words] int32 its pass bits, rewritten IN PLACE with the survivors of the global cut.
+    Per level: two all-reduced [Q, 65536] histograms (high / low 16 bits of the score's bit pattern) locate the exact cut
+    score, one all-gather of the per-shard tie counts shares out the ties by ascending global row id (row shards are
+    contiguous id ranges, so a shard's quota is what the shards with smaller ids leave).  Returns n_out [Q] int64.
+    Every rank must call it, an empty shard (N == 0) included."""
+    import ctypes as C
+    from ._lib import check, lib
+    Q = int(n_alive_local.shape[0])
+    d = n_alive_local.device
+    n_alive = _all_reduce(n_alive_local.to(torch.int64).clone(), dist.ReduceOp.SUM, group)
+    n_pass = _all_reduce(n_pass_local.to(torch.int64).clone(), dist.ReduceOp.SUM, group)
+    cap = torch.clamp((n_alive.to(torch.float64) * ratio).floor().to(torch.int64), min=1)
+    need = n_pass > cap                                           # identical on every rank
+    n_out = torch.minimum(n_pass, cap)
+    if Q == 0 or not bool(need.any()):
+        return n_out
+    need32 = need.to(torch.int32).contiguous()
+    st = dev.stream_ptr()
+    s_ptr, s_stride = (dev.ptr(scores), scores.stride(0)) if N > 0 else (None, 0)
+    m_ptr, m_stride = (dev.ptr(mask), mask.stride(0)) if N > 0 else (None, 0)
+    hist = torch.zeros((Q, 65536), dtype=torch.int32, device=d)
+    d1, above1, d2, above2 = (torch.zeros(Q, dtype=torch.int64, device=d) for _ in range(4))
+    with torch.cuda.device(d):
+        if N > 0:
+            check(lib.hq_gcut_hist(s_ptr, s_stride, N, Q, m_ptr, m_stride, dev.ptr(need32), None, dev.ptr(hist), st))
+        _all_reduce(hist, dist.ReduceOp.SUM, group)
+        check(lib.hq_gcut_scan(dev.ptr(hist), Q, dev.ptr(need32), dev.ptr(cap), dev.ptr(d1), dev.ptr(above1), st))
+        d1_32 = d1.to(torch.int32).contiguous()
+        hist.zero_()
+        if N > 0:
+            check(lib.hq_gcut_hist(s_ptr, s_stride, N, Q, m_ptr, m_stride, dev.ptr(need32), dev.ptr(d1_32), dev.ptr(hist), st))
+        _all_reduce(hist, dist.ReduceOp.SUM, group)
+        want2 = (cap - above1).contiguous()
+        check(lib.hq_gcut_scan(dev.ptr(hist), Q, dev.ptr(need32), dev.ptr(want2), dev.ptr(d2), dev.ptr(above2), st))
+        k_star = ((d1 << 16) | d2).contiguous()
+        r_ties = cap - above1 - above2                            # ties to keep over all shards (>= 1)
+        ties = torch.zeros(Q, dtype=torch.int64, device=d)
+        if N > 0:
+            check(lib.hq_gcut_ties(s_ptr, s_stride, N, Q, m_ptr, m_stride, dev.ptr(need32), dev.ptr(k_star), dev.ptr(ties), st))
+        before = torch.zeros(Q, dtype=torch.int64, device=d)
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            world = dist.get_world_size(group)
+            mine = torch.cat([torch.tensor([int(id_base)], dtype=torch.int64, device=d), ties])
+            allr = torch.empty((world, Q + 1), dtype=torch.int64, device=d)
+            dist.all_gather_into_tensor(allr.view(-1), mine.contiguous(), group=group)
+            lower = (allr[:, 0] < int(id_base)) | ((allr[:, 0] == int(id_base)) & (torch.arange(world, device=d) < dist.get_rank(group)))
+            before = (allr[:, 1:] * lower[:, None].to(torch.int64)).sum(0)
+        quota = torch.minimum(torch.clamp(r_ties - before, min=0), ties).contiguous()
+        if N > 0:
+            check(lib.hq_gcut_apply(s_ptr, s_stride, N, Q, m_ptr, m_stride, dev.ptr(need32), dev.ptr(k_star), dev.ptr(quota), st))
+    return n_out
+
+
 class ShardedSearch:
     """One instance per rank.  `local_embeddings` are this rank's rows [start, end) of the global database."""
 

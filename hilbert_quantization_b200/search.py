@@ -6,6 +6,8 @@ core/search_engine.py:23-388 for the core engine over QuantizedModel indices.
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -457,7 +459,7 @@ def progressive_filter_global(db: EmbeddingDatabase, q_idx: torch.Tensor, q_lens
                               mask: torch.Tensor, group=None, trace: Optional[FilterTrace] = None):
     """`filter_scope="global"`: level scores and threshold tests by hq_filter_level on this shard, the ratio
     cut over the GLOBAL candidate list of each query (distributed.global_ratio_cut)."""
-    from .distributed import global_ratio_cut
+    from .distributed import global_ratio_cut, global_ratio_cut_device
     Qc, N, d = q_idx.shape[0], db.N, db.device
     words = _mask_words(N)
     with torch.cuda.device(d):
@@ -465,19 +467,25 @@ def progressive_filter_global(db: EmbeddingDatabase, q_idx: torch.Tensor, q_lens
         for level in range(db.num_levels):
             n_alive = torch.zeros(Qc, dtype=torch.int32, device=d)
             n_pass = torch.zeros(Qc, dtype=torch.int32, device=d)
-            if N == 0:                              # an empty shard contributes nothing but takes part in every collective
-                none = torch.zeros((Qc, 0), dtype=torch.bool, device=d)
-                _, n_out = global_ratio_cut(torch.zeros((Qc, 0), dtype=torch.float32, device=d), none, n_alive, rag_ratio(level),
-                                            db.id_base, group)
-            else:
+            # the ratio cut over the global list on the device (distributed.global_ratio_cut_device: histograms of the score
+            # bits, no [Q, N] temporaries); an empty shard contributes nothing but takes part in every collective
+            if N > 0:
                 check(lib.hq_filter_level(dev.ptr(db.idx), dev.ptr(db.lens), N, C.byref(db.layout), level,
                                           dev.ptr(q_idx), dev.ptr(q_lens), Qc,
                                           dev.ptr(mask) if level > 0 else None, mask.stride(0),
                                           rag_threshold(level), dev.ptr(scores), scores.stride(0), dev.ptr(mask),
                                           dev.ptr(n_alive), dev.ptr(n_pass), st))
-                passed = _unpack_bits(mask[:Qc, :words], N)
-                keep, n_out = global_ratio_cut(scores[:Qc, :N], passed, n_alive, rag_ratio(level), db.id_base, group)
-                mask[:Qc, :words] = _pack_bits(keep, words)
+            if os.environ.get("HQ_GLOBAL_CUT_TORCH"):     # the first implementation (eager PyTorch on [Q, N] tensors), kept for A/B
+                if N == 0:
+                    none = torch.zeros((Qc, 0), dtype=torch.bool, device=d)
+                    _, n_out = global_ratio_cut(torch.zeros((Qc, 0), dtype=torch.float32, device=d), none, n_alive, rag_ratio(level),
+                                                db.id_base, group)
+                else:
+                    passed = _unpack_bits(mask[:Qc, :words], N)
+                    keep, n_out = global_ratio_cut(scores[:Qc, :N], passed, n_alive, rag_ratio(level), db.id_base, group)
+                    mask[:Qc, :words] = _pack_bits(keep, words)
+            else:
+                n_out = global_ratio_cut_device(scores, mask, N, n_alive, n_pass, rag_ratio(level), db.id_base, group)
             if trace is not None:
                 trace.n_alive.append(n_alive)
                 trace.n_pass.append(n_pass)

@@ -365,6 +365,22 @@ int hq_core_level_sims(const double* cand, int64_t N, int S, int64_t cand_stride
                        const int32_t* q_start, const int32_t* c_start, const int32_t* lvl_len, int n_levels,
                        double* sims, void* stream);
 
+/* filter_scope = "global" on a row-sharded database: the per-shard halves of the reference's single-list ratio cut
+ * (rag/search/engine.py:272-287).  scores [Q, scores_stride] are the level scores of hq_filter_level, mask [Q, mask_stride] its
+ * pass bits, need [Q] marks the queries whose global pass count exceeds the cap.  hq_gcut_hist adds the passed rows to
+ * hist [Q, 65536] by the high (d_hi == NULL) or the low 16 bits of the score's bit pattern (rows whose high digit is
+ * d_hi[q]); the caller all-reduces hist; hq_gcut_scan finds the digit of the want[q]-th best and the count above it;
+ * hq_gcut_ties counts this shard's rows AT the cut score k_star[q]; hq_gcut_apply rewrites the mask: rows above the cut
+ * score and the first quota[q] tied rows by ascending row id. */
+int hq_gcut_hist(const float* scores, int64_t scores_stride, int64_t N, int Q, const uint32_t* mask, int64_t mask_stride,
+                 const int32_t* need, const int32_t* d_hi, int32_t* hist, void* stream);
+int hq_gcut_scan(const int32_t* hist, int Q, const int32_t* need, const int64_t* want, int64_t* d_out, int64_t* above_out,
+                 void* stream);
+int hq_gcut_ties(const float* scores, int64_t scores_stride, int64_t N, int Q, const uint32_t* mask, int64_t mask_stride,
+                 const int32_t* need, const int64_t* k_star, int64_t* ties, void* stream);
+int hq_gcut_apply(const float* scores, int64_t scores_stride, int64_t N, int Q, uint32_t* mask, int64_t mask_stride,
+                  const int32_t* need, const int64_t* k_star, const int64_t* quota, void* stream);
+
 /* Per-kernel timing for the benchmark's roofline (CUDA events on the launching stream around the launches of the four
  * search kernels): hq_kernel_timing(1) arms it, hq_kernel_timing_read synchronises and returns, per slot, the summed
  * milliseconds and the number of launches since it was armed (slot 0 k_rerank_tc, 1 k_filter_bits_tc main pass,
