@@ -49,6 +49,7 @@ SIGNATURES = {
                               _p, _i64, _p, _p, _p, _i64, _p]),
     "hq_filter_tc_supported": (_i32, [C.POINTER(IndexLayout)]),
     "hq_filter_tc_plan": (_i32, [_i64, _i32, _p, _p]),
+    "hq_filter_tc_packed_cols": (_i32, [C.POINTER(IndexLayout)]),
     "hq_filter_tc_valid_pitch": (_i64, [_i64]),
     "hq_filter_tc_pack": (_i32, [_p, _p, _i64, C.POINTER(IndexLayout), _i32, _p, _p]),
     "hq_filter_tc_valid": (_i32, [_p, _i64, C.POINTER(IndexLayout), _p, _i64, _p]),

@@ -7,7 +7,10 @@
 // within ~2e-6 of the threshold, so a plain tf32 contraction (10-bit mantissa) is not enough.
 // Every operand value x is split exactly: hi = x with the low 13 mantissa bits cleared (a tf32
 // number), lo = (x - hi) truncated the same way; the contraction runs over the three products
-// hi*hi + hi*lo + lo*hi, laid out along K as  A = [q_hi | q_hi | q_lo],  B = [c_hi | c_lo | c_hi].
+// hi*hi + hi*lo + lo*hi.  Both operands hold  [x_hi | x_lo]  per level (2 x kp floats, kp = level width padded to 8); the
+// three products are three MMA k-step sequences over (A_hi, B_hi), (A_hi, B_lo), (A_lo, B_hi) -- the descriptors simply
+// point at the same hi block twice.  (Round 1 stored A = [q_hi | q_hi | q_lo], B = [c_hi | c_lo | c_hi]: 512 bytes per
+// database row instead of 384 for 1536-D, 256 for 768-D.)
 // The dropped terms are below 2^-21 relative per product (score error < 3e-7).  Database
 // rows are pre-scaled by 1/|c_l|, so the test is  dot >= x*_l * |q_l|  with a per-thread
 // constant; zero-norm rows are all-zero operands and are cleared through a per-level validity
@@ -28,7 +31,7 @@ namespace {
 
 constexpr int FM = 128;                        // queries per tile (MMA M)
 constexpr int FR = 64;                         // database rows per tile (MMA N)
-constexpr int KS = 128;                        // packed floats per row: 4 slabs of 32 (128 B)
+constexpr int KS = 128;                        // most packed floats per row: 4 slabs of 32 (128 B); a layout uses n_slabs of them
 constexpr int F_STAGES = 3;
 constexpr uint32_t A_SLAB_BYTES = FM * 128;    // 16 KB
 constexpr uint32_t B_SLAB_BYTES = FR * 128;    // 8 KB
@@ -59,7 +62,7 @@ bool make_segs(const hq_index_layout* lay, Segs& s) {
         if (lay->lvl_keff[l] < 1) return false;
         s.kp[l] = (lay->lvl_keff[l] + 7) & ~7;
         s.off[l] = off;
-        off += 3 * s.kp[l];
+        off += 2 * s.kp[l];                     // [hi | lo]
     }
     if (off > KS) return false;
     s.n_slabs = (off + 31) / 32;
@@ -69,7 +72,7 @@ bool make_segs(const hq_index_layout* lay, Segs& s) {
 struct FtcParams {
     int64_t N;
     int Q, L;
-    int seg_off[3], ksteps[3];
+    int seg_off[3], ksteps[3];  // first packed column of the level's hi block; k-steps of 8 floats per block (kp / 8)
     int n_slabs;
     int m_tiles, n_tiles, n_ranges, tiles_per_range, num_units;
     const float* tq;            // [3][Q]  x*_l * |q_l| (NaN when |q_l| == 0)
@@ -360,12 +363,17 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
 #pragma unroll
                     for (int l = 0; l < 3; ++l) {
                         if (l < p.L) {
-                            for (int s = 0; s < p.ksteps[l]; ++s) {
-                                const uint32_t off = (uint32_t)p.seg_off[l] + 8u * s;          // packed column of this k-step
-                                const uint32_t slab = off >> 5, byte = (off & 31u) * 4u;
-                                const uint64_t da = make_smem_desc(a0 + slab * A_SLAB_BYTES + byte);
-                                const uint64_t db = make_smem_desc(b0 + slab * B_SLAB_BYTES + byte);
-                                umma_tf32(tmem_base + acc * ACC_COLS + l * FR, da, db, kIdescTf32, s > 0 ? 1u : 0u);
+                            // hi*hi, hi*lo, lo*hi: (A block, B block) = (0, 0), (0, 1), (1, 0)
+#pragma unroll
+                            for (int pr = 0; pr < 3; ++pr) {
+                                const uint32_t a_blk = pr == 2 ? 1u : 0u, b_blk = pr == 1 ? 1u : 0u;
+                                for (int s = 0; s < p.ksteps[l]; ++s) {
+                                    const uint32_t offa = (uint32_t)p.seg_off[l] + a_blk * 8u * p.ksteps[l] + 8u * s;
+                                    const uint32_t offb = (uint32_t)p.seg_off[l] + b_blk * 8u * p.ksteps[l] + 8u * s;
+                                    const uint64_t da = make_smem_desc(a0 + (offa >> 5) * A_SLAB_BYTES + (offa & 31u) * 4u);
+                                    const uint64_t db = make_smem_desc(b0 + (offb >> 5) * B_SLAB_BYTES + (offb & 31u) * 4u);
+                                    umma_tf32(tmem_base + acc * ACC_COLS + l * FR, da, db, kIdescTf32, (pr > 0 || s > 0) ? 1u : 0u);
+                                }
                             }
                         }
                     }
@@ -576,20 +584,21 @@ struct PackParams {
     hq_index_layout lay;
     int is_query;
     int seg_off[3], kp[3];
-    float* out;             // [N, KS]
+    float* out;             // [N, pitch]
+    int pitch;              // packed floats per row (n_slabs * 32)
 };
 
 __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
 __global__ void __launch_bounds__(256) k_pack_rows(const PackParams p) {
-    const int64_t total = p.N * KS;
+    const int64_t total = p.N * p.pitch;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t row = i >> 7;
-        const int c = (int)(i & (KS - 1));
+        const int64_t row = i / p.pitch;
+        const int c = (int)(i - row * p.pitch);
         float outv = 0.f;
 #pragma unroll
         for (int l = 0; l < 3; ++l) {
-            if (l < p.lay.L && c >= p.seg_off[l] && c < p.seg_off[l] + 3 * p.kp[l]) {
+            if (l < p.lay.L && c >= p.seg_off[l] && c < p.seg_off[l] + 2 * p.kp[l]) {
                 const int rel = c - p.seg_off[l];
                 const int part = rel / p.kp[l], j = rel - part * p.kp[l];
                 float x = j < p.lay.lvl_keff[l] ? __ldg(p.idx + row * p.lay.Lsum + p.lay.lvl_off[l] + j) : 0.f;
@@ -599,8 +608,7 @@ __global__ void __launch_bounds__(256) k_pack_rows(const PackParams p) {
                 }
                 const float hi = trunc_tf32(x);
                 const float lo = trunc_tf32(__fadd_rn(x, -hi));
-                const bool want_lo = p.is_query ? (part == 2) : (part == 1);
-                outv = want_lo ? lo : hi;
+                outv = part == 1 ? lo : hi;
             }
         }
         p.out[i] = outv;
@@ -663,6 +671,11 @@ extern "C" int hq_filter_tc_supported(const hq_index_layout* layout) {
     return make_segs(layout, s) ? 1 : 0;
 }
 
+extern "C" int hq_filter_tc_packed_cols(const hq_index_layout* layout) {
+    Segs s;
+    return make_segs(layout, s) ? s.n_slabs * 32 : 0;
+}
+
 extern "C" int64_t hq_filter_tc_valid_pitch(int64_t N) {
     // words, rounded up to whole 64-row tiles
     return (N + FR - 1) / FR * 2;
@@ -677,8 +690,9 @@ extern "C" int hq_filter_tc_pack(const float* idx, const float* rnorm, int64_t N
     HQ_REQUIRE(idx && packed && (is_query || rnorm), "null pointer");
     PackParams p{};
     p.idx = idx; p.rnorm = rnorm; p.N = N; p.lay = *layout; p.is_query = is_query ? 1 : 0; p.out = packed;
+    p.pitch = s.n_slabs * 32;
     for (int l = 0; l < 3; ++l) { p.seg_off[l] = s.off[l]; p.kp[l] = s.kp[l]; }
-    int64_t blocks = (N * KS + 255) / 256;
+    int64_t blocks = (N * p.pitch + 255) / 256;
     const int64_t cap = (int64_t)hq_cached_sm_count() * 32;
     if (blocks > cap) blocks = cap;
     k_pack_rows<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
@@ -755,7 +769,7 @@ int hq_filter_tc_pass(const float* db_packed, const uint32_t* valid, int64_t val
 
     FtcParams p{};
     p.N = N; p.Q = Q; p.L = s.L; p.n_slabs = s.n_slabs;
-    for (int l = 0; l < 3; ++l) { p.seg_off[l] = s.off[l]; p.ksteps[l] = 3 * s.kp[l] / 8; }
+    for (int l = 0; l < 3; ++l) { p.seg_off[l] = s.off[l]; p.ksteps[l] = s.kp[l] / 8; }
     p.tq = tq; p.valid = valid; p.valid_pitch = valid_pitch; p.bits = bits; p.words = words; p.bits_pitch = bits_pitch;
     p.bits_vec = (bits && (reinterpret_cast<uintptr_t>(bits) & 31) == 0 && bits_pitch % 8 == 0) ? 1 : 0;
     p.tile_stride = stride;
@@ -770,9 +784,10 @@ int hq_filter_tc_pass(const float* db_packed, const uint32_t* valid, int64_t val
         p.n_segs = lists->n_segs;
     }
     CUtensorMap mq, mdb;
-    int rc = make_map_2d(&mq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, q_packed, Q, KS, KS, 32, FM);
+    const int ks = s.n_slabs * 32;                 // packed floats per row of both operands
+    int rc = make_map_2d(&mq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, q_packed, Q, ks, ks, 32, FM);
     if (rc != HQ_OK) return rc;
-    rc = make_map_2d(&mdb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, db_packed, N, KS, KS, 32, FR);
+    rc = make_map_2d(&mdb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, db_packed, N, ks, ks, 32, FR);
     if (rc != HQ_OK) return rc;
     const size_t smem_full = 1024 + A_BYTES + F_STAGES * B_STAGE_BYTES + (STAGE_WORDS + 3 * LBUF * EPI_THREADS) * sizeof(uint32_t) +
                              (2 * F_STAGES + 6) * sizeof(uint64_t) + 16;

@@ -284,7 +284,8 @@ class EmbeddingDatabase:
         self.tc_valid_pitch = 0
         if tc_filter and self.fast_filter_ok and self.N > 0 and bool(lib.hq_filter_tc_supported(C.byref(self.layout))):
             self.tc_valid_pitch = int(lib.hq_filter_tc_valid_pitch(self.N))
-            self.tc_packed = torch.empty((self.N, 128), dtype=torch.float32, device=d)
+            cols = int(lib.hq_filter_tc_packed_cols(C.byref(self.layout)))       # [hi | lo] per level, whole 128-byte slabs
+            self.tc_packed = torch.empty((self.N, cols), dtype=torch.float32, device=d)
             self.tc_valid = torch.empty((int(self.layout.L), self.tc_valid_pitch), dtype=torch.int32, device=d)
             with torch.cuda.device(d):
                 check(lib.hq_filter_tc_pack(dev.ptr(self.idx), dev.ptr(self.level_norms), self.N, C.byref(self.layout), 0,

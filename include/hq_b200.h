@@ -217,9 +217,12 @@ int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, const hq_ind
  * dot products run as ONE tcgen05 tf32 contraction per 128-query x 64-row tile with every
  * value split exactly into tf32 hi + lo parts (three products per term, score error < 3e-7),
  * rows pre-scaled by 1 / |c_l|, and the comparison + bit packing done in the TMEM epilogue.
- * Supported when 3 * sum_l pad8(lvl_keff[l]) <= 128 and L <= 3.
- *   hq_filter_tc_pack  : idx [N, Lsum] (+ rnorm) -> packed [N, 128] float32 operand rows
- *                        (is_query = 1: unscaled, [hi | hi | lo]; 0: scaled, [hi | lo | hi])
+ * Supported when 2 * sum_l pad8(lvl_keff[l]) <= 128 and L <= 3.
+ *   hq_filter_tc_packed_cols : packed floats per operand row ([x_hi | x_lo] per level, whole 128-byte slabs): 96 for
+ *                        1536-D (64 x 64 grids), 64 for 768-D (32 x 32); 0 when the layout is not supported
+ *   hq_filter_tc_pack  : idx [N, Lsum] (+ rnorm) -> packed [N, hq_filter_tc_packed_cols] float32 operand rows
+ *                        (is_query = 1: unscaled; 0: scaled by 1 / |c_l|); the three products hi*hi + hi*lo + lo*hi are
+ *                        three MMA sequences over the same blocks
  *   hq_filter_tc_valid : valid [L][valid_pitch] bit r = row r has a non-zero level norm;
  *                        valid_pitch >= hq_filter_tc_valid_pitch(N) (whole 64-row tiles)
  *   hq_filter_tc_plan  : work split of the pass for (N, Q) on the current device: n_ranges row ranges of
@@ -231,6 +234,7 @@ int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, const hq_ind
 int hq_filter_tc_supported(const hq_index_layout* layout);
 int hq_filter_tc_plan(int64_t N, int Q, int* n_ranges, int* tiles_per_range);
 int64_t hq_filter_tc_valid_pitch(int64_t N);
+int hq_filter_tc_packed_cols(const hq_index_layout* layout);
 int hq_filter_tc_pack(const float* idx, const float* rnorm, int64_t N, const hq_index_layout* layout, int is_query,
                       float* packed, void* stream);
 int hq_filter_tc_valid(const float* rnorm, int64_t N, const hq_index_layout* layout, uint32_t* valid,
