@@ -1562,16 +1562,19 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_filter_cascade_win(const WinP
                 }
             }
         };
+        // Keys are relative to the lower window edges (the window pass folds -lo into the contraction): k1 in [0, w1) inside
+        // window 1, >= w1 above it; k2 < 0 below window 2, >= w2 above it (w = hi - lo, the same float the pass tests against).
+        const float w1 = hi1 - lo1, w2 = three ? hi2 - lo2 : -INFINITY;
         auto each_w1 = [&](auto visit) {
-            each_all([&](float k, uint32_t tok) { if (k < hi1) visit(k, tok); });
+            each_all([&](float k, uint32_t tok) { if (k < w1) visit(k, tok); });
         };
         // ---- level 1: rows inside window 1, ranked below the nA1 rows above it ----
-        const float top1 = hi1 < INFINITY ? hi1 : __ldg(p.nq + (int64_t)1 * p.Q + q);
-        const float scale1 = top1 > lo1 ? 2048.0f / (top1 - lo1) : 0.f;
+        const float top1 = (hi1 < INFINITY ? hi1 : __ldg(p.nq + (int64_t)1 * p.Q + q)) - lo1;       // relative upper edge
+        const float scale1 = top1 > 0.f ? 2048.0f / top1 : 0.f;
         for (int i = tid; i < 2048; i += nt) hist[i] = 0;
         __syncthreads();
         uint32_t cw = 0;
-        each_w1([&](float k, uint32_t) { atomicAdd(&hist[lin_bin(k, lo1, scale1)], 1u); ++cw; });
+        each_w1([&](float k, uint32_t) { atomicAdd(&hist[lin_bin(k, 0.f, scale1)], 1u); ++cw; });
         const int64_t n_w1 = block_sum(cw, s_warp);
         int64_t cap1 = (int64_t)((double)c0 * p.ratio[1]);
         if (cap1 < 1) cap1 = 1;
@@ -1585,10 +1588,10 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_filter_cascade_win(const WinP
         if (cut1) {
             find_cut_bin(hist, (uint32_t)(n1 - cap1), sh);
             if (sh[2] <= (uint32_t)kWinCutCap) {
-                cb1.lo = lo1; cb1.scale = scale1; cb1.cb = sh[0]; cb1.r_in_bin = sh[1]; cb1.on = true;
+                cb1.lo = 0.f; cb1.scale = scale1; cb1.cb = sh[0]; cb1.r_in_bin = sh[1]; cb1.on = true;
             } else {
                 failed = !select_boundary(each_w1, [&](uint32_t tok) { return __ldg(L_rows + tok) & 0x7fffffffu; }, (uint32_t)(n1 - cap1),
-                                          lo1, top1, true, hist, sh, b_key, b_row, &s_bufn, &s_K, &s_R, b1, (uint32_t)kWinCutCap);
+                                          0.f, top1, true, hist, sh, b_key, b_row, &s_bufn, &s_K, &s_R, b1, (uint32_t)kWinCutCap);
             }
         }
         if (failed) { fail(); continue; }
@@ -1597,26 +1600,26 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_filter_cascade_win(const WinP
         if (cap2 < 1) cap2 = 1;
         __syncthreads();
         if (tid == 0) s_bufn = 0;
-        const float top2 = hi2 < INFINITY ? hi2 : (three ? __ldg(p.nq + (int64_t)2 * p.Q + q) : 0.f);
-        const float scale2 = top2 > lo2 ? 2048.0f / (top2 - lo2) : 0.f;
+        const float top2 = three ? (hi2 < INFINITY ? hi2 : __ldg(p.nq + (int64_t)2 * p.Q + q)) - lo2 : 0.f;
+        const float scale2 = top2 > 0.f ? 2048.0f / top2 : 0.f;
         for (int i = tid; i < 2048; i += nt) hist[i] = 0;
         __syncthreads();
         // a survivor of cut 1: dead below window 2, alive above it (window-1 rows are not in the plane yet), else a member
-        auto level2 = [&](uint32_t row, float k2, bool w1) {
-            if (!(k2 >= lo2)) return;
-            if (w1) atomicAdd(&s_x1, 1u);
-            if (k2 >= hi2) {
-                if (w1) { atomicOr(&M[row >> 5], 1u << (row & 31)); atomicAdd(&s_x2, 1u); }
+        auto level2 = [&](uint32_t row, float k2, bool inw1) {
+            if (!(k2 >= 0.f)) return;
+            if (inw1) atomicAdd(&s_x1, 1u);
+            if (k2 >= w2) {
+                if (inw1) { atomicOr(&M[row >> 5], 1u << (row & 31)); atomicAdd(&s_x2, 1u); }
                 return;
             }
             const uint32_t slot = atomicAdd(&s_n2, 1u);
             c_k2[slot] = k2; c_row[slot] = row;
-            atomicAdd(&hist[lin_bin(k2, lo2, scale2)], 1u);
+            atomicAdd(&hist[lin_bin(k2, 0.f, scale2)], 1u);
         };
         each_all3([&](float k1, uint32_t row, float k2) {          // (two levels: k2 = +inf, every survivor of cut 1 survives)
-            const bool w1 = k1 < hi1;
+            const bool inw1 = k1 < w1;
             int cls = 2;
-            if (w1 && cut1) {
+            if (inw1 && cut1) {
                 if (cb1.on) {
                     const uint32_t b = lin_bin(k1, cb1.lo, cb1.scale);
                     cls = b > cb1.cb ? 2 : (b == cb1.cb ? 1 : 0);
@@ -1630,7 +1633,7 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_filter_cascade_win(const WinP
                 b_key[slot] = k1; b_row[slot] = row; b_k2[slot] = k2;
                 return;
             }
-            level2(row, k2, w1);
+            level2(row, k2, inw1);
         });
         __syncthreads();
         if (cb1.on) {
@@ -1662,9 +1665,9 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_filter_cascade_win(const WinP
         if (cut2) {
             find_cut_bin(hist, (uint32_t)(n2 - cap2), sh);
             if (sh[2] <= (uint32_t)kWinCutCap) {
-                cb2.lo = lo2; cb2.scale = scale2; cb2.cb = sh[0]; cb2.r_in_bin = sh[1]; cb2.on = true;
+                cb2.lo = 0.f; cb2.scale = scale2; cb2.cb = sh[0]; cb2.r_in_bin = sh[1]; cb2.on = true;
             } else {
-                failed = !select_boundary(each_l2, [&](uint32_t tok) { return __ldcg(c_row + tok); }, (uint32_t)(n2 - cap2), lo2, top2, true,
+                failed = !select_boundary(each_l2, [&](uint32_t tok) { return __ldcg(c_row + tok); }, (uint32_t)(n2 - cap2), 0.f, top2, true,
                                           hist, sh, b_key, b_row, &s_bufn, &s_K, &s_R, b2, (uint32_t)kWinCutCap);
             }
         }
@@ -1821,7 +1824,13 @@ __global__ void __launch_bounds__(128) k_filter_exceptions_win(const ExcWinParam
     const float t1 = __ldg(p.tq + (int64_t)1 * p.Q + q), t2 = L > 2 ? __ldg(p.tq + (int64_t)2 * p.Q + q) : 0.f;
     // keys that say what the exact scores said: a row that passes a threshold never sorts below it
     const float k1 = pass[1] ? fmaxf(keq[1], t1) : -INFINITY, k2 = pass[2] ? fmaxf(keq[2], t2) : -INFINITY;
-    const bool A1 = k1 >= lo1, B1 = A1 && k1 >= hi1, A2 = L < 3 || k2 >= lo2, B2 = L < 3 || (A2 && k2 >= hi2);
+    const bool A1 = k1 >= lo1, A2 = L < 3 || k2 >= lo2;
+    // stored like the window pass stores them: relative to the lower window edge; the classes are then taken FROM the stored
+    // keys, exactly as the cascade will repeat them
+    const float k1s = A1 ? fmaxf(k1 - lo1, 0.f) : -INFINITY;
+    const float k2s = L < 3 ? INFINITY : (A2 ? fmaxf(k2 - lo2, 0.f) : -INFINITY);
+    const float w1 = hi1 - lo1, w2 = hi2 - lo2;
+    const bool B1 = A1 && k1s >= w1, B2 = L < 3 || (A2 && k2s >= w2);
     atomicAdd(pw.wcnt + q, 1);
     if (B1) atomicAdd(pw.wcnt + (int64_t)1 * p.Q + q, 1);
     if (B1 && A2) atomicAdd(pw.wcnt + (int64_t)2 * p.Q + q, 1);
@@ -1834,8 +1843,8 @@ __global__ void __launch_bounds__(128) k_filter_exceptions_win(const ExcWinParam
         if (pos < p.seg_cap) {
             const int64_t a = ((int64_t)q * p.n_segs + p.extra_seg) * p.seg_cap + pos;
             p.l_rows[a] = (uint32_t)row;
-            p.l_k1[a] = k1;
-            if (L > 2) p.l_k2[a] = k2;
+            p.l_k1[a] = k1s;
+            if (L > 2) p.l_k2[a] = k2s;
         }
     }
 }
@@ -2116,7 +2125,9 @@ extern "C" int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, c
         pp.c0_s = c0_s; pp.win = win; pp.pflag = pflag;
         k_filter_predict<<<Q, 256, 0, st>>>(pp);
         HQ_LAUNCH_OK("k_filter_predict");
-        // 3. window pass
+        // 3. window pass (its thresholds folded into the query operand first)
+        rc = hq_filter_tc_fold(layout, tq, win, Q, q_packed, st);
+        if (rc != HQ_OK) return rc;
         HQ_CUDA_OK(cudaMemsetAsync(seg_n, 0, (size_t)Q * wg.n_segs_w * 4, st));
         HqFilterLists lw{};
         lw.rows = l_rows; lw.k1 = l_k1; lw.k2 = L > 2 ? l_k2 : nullptr; lw.seg_n = seg_n; lw.seg_cap = wg.seg_cap_w; lw.n_segs = wg.n_segs_w;

@@ -50,7 +50,11 @@ struct Segs {
     int L;
     int off[3];        // first packed column of the level
     int kp[3];         // level width padded to 8 (one tf32 k-step)
-    int n_slabs;       // 128-byte slabs that hold data
+    int n_slabs;       // 128-byte slabs of a DATABASE row: the level blocks
+    int n_slabs_q;     // slabs of a QUERY row: the level blocks + three threshold blocks (window mode's folded thresholds)
+    int thr_off;       // first packed column after the level blocks: A holds its threshold blocks there
+    int ones_in_row;   // the B side of the folded thresholds, a block (1, 1, 0 ...): 1 = in the padding of the row's fourth slab
+                       // (columns thr_off ..), 0 = a constant slab in shared memory (the stage's unused fourth slab)
 };
 
 bool make_segs(const hq_index_layout* lay, Segs& s) {
@@ -64,8 +68,11 @@ bool make_segs(const hq_index_layout* lay, Segs& s) {
         s.off[l] = off;
         off += 2 * s.kp[l];                     // [hi | lo]
     }
-    if (off > KS) return false;
+    s.thr_off = off;
+    if (off + 8 * 3 > KS) return false;
     s.n_slabs = (off + 31) / 32;
+    s.n_slabs_q = (off + 8 * 3 + 31) / 32;
+    s.ones_in_row = s.n_slabs == 4 ? 1 : 0;     // off + 8 <= KS holds (checked above): the block fits the padding
     return true;
 }
 
@@ -73,7 +80,7 @@ struct FtcParams {
     int64_t N;
     int Q, L;
     int seg_off[3], ksteps[3];  // first packed column of the level's hi block; k-steps of 8 floats per block (kp / 8)
-    int n_slabs;
+    int n_slabs, n_slabs_q, thr_off, ones_in_row;
     int m_tiles, n_tiles, n_ranges, tiles_per_range, num_units;
     const float* tq;            // [3][Q]  x*_l * |q_l| (NaN when |q_l| == 0)
     const uint32_t* valid;      // [L][valid_pitch] bit r: row r has a non-zero level norm
@@ -116,6 +123,18 @@ __device__ __forceinline__ uint32_t pass_word(const uint32_t (&r)[32], float tq)
     return ~__brev(all);
 }
 
+__device__ __forceinline__ uint32_t sign_word(const uint32_t (&r)[32]) {
+    // bit j = (r[j] >= 0) as a float, i.e. its sign bit is clear: the funnel shifts of pass_word without the subtraction
+    uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) w[c] = __funnelshift_l(r[c * 8 + j], w[c], 1);
+    }
+    const uint32_t all = (w[0] << 24) | (w[1] << 16) | (w[2] << 8) | w[3];
+    return ~__brev(all);
+}
+
 __device__ __forceinline__ void st_global_256(uint32_t* dst, const uint32_t (&v)[8]) {       // one full 32-byte sector
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
                  "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
@@ -143,6 +162,7 @@ __device__ __forceinline__ void win_unit(const FtcParams& p, int m_tile, int ran
     const float lo2 = q_ok ? __ldg(p.win + (int64_t)2 * p.Q + q) : qnan, hi2 = q_ok ? __ldg(p.win + (int64_t)3 * p.Q + q) : qnan;
     const bool three = p.L > 2;                                            // two-level layouts (32 x 32 grids) have no cut 2
     const bool okw = (tq0 == tq0) && (lo1 == lo1) && (hi1 == hi1) && (!three || ((lo2 == lo2) && (hi2 == hi2)));
+    const float w1 = hi1 - lo1, w2 = three ? hi2 - lo2 : 0.f;            // upper window edges relative to the folded lower ones
     const bool lists = p.l_rows != nullptr && q_ok;
     const int64_t seg_base = ((int64_t)q * p.n_segs + (range * 2 + half)) * p.seg_cap;
     const int seg_cap32 = (int)min(p.seg_cap, (int64_t)0x7ffffff0);
@@ -176,16 +196,18 @@ __device__ __forceinline__ void win_unit(const FtcParams& p, int m_tile, int ran
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&tempty_bar[acc]);
-        // Five sign-test words; classes, counters and the alive word are bit-mask arithmetic, only the window rows (~2 % of
-        // the pairs) are walked bit by bit.  (Tried: two sign tests and a walk over the ~9 % of the pairs that pass level 0
-        // and the lower edge of window 1, classifying them from the staging area: 2.05 ms instead of 1.39 ms per 1024 x 1 M
-        // batch -- a divergent loop runs as long as the lane with the most bits, with a shared-memory load in every turn.)
+        // The accumulators hold dot0 - t0, dot1 - lo1, dot2 - lo2 (thresholds folded into the contraction): the level-0 test and
+        // the lower window edges are SIGN tests (one funnel shift per element), the upper edges one subtraction more
+        // (k - (hi - lo) >= 0).  Classes, counters, the alive word and the word E of the window rows are bit-mask arithmetic.
+        uint32_t W0 = 0, A1 = 0, B1 = 0, A2 = 0xffffffffu, B2 = 0xffffffffu;
+        if (okw) {
+            W0 = sign_word(r0) & vw[0];
+            A1 = sign_word(r1) & vw[1];
+            B1 = pass_word(r1, w1) & A1;
+            if (three) { A2 = sign_word(r2) & vw[2]; B2 = pass_word(r2, w2) & A2; }
+        }
         uint32_t alive = 0, E = 0;
         if (okw) {
-            const uint32_t W0 = pass_word(r0, tq0) & vw[0];
-            const uint32_t A1 = pass_word(r1, lo1) & vw[1], B1 = pass_word(r1, hi1) & A1;
-            uint32_t A2 = 0xffffffffu, B2 = 0xffffffffu;
-            if (three) { A2 = pass_word(r2, lo2) & vw[2]; B2 = pass_word(r2, hi2) & A2; }
             const uint32_t S1 = W0 & B1;
             alive = S1 & B2;
             E = W0 & A1 & (~B1 | (A2 & ~B2));
@@ -210,6 +232,8 @@ __device__ __forceinline__ void win_unit(const FtcParams& p, int m_tile, int ran
                         const int j = __ffs((int)m) - 1;
                         m &= m - 1;
                         const float* src = kst + (j >> 2) * KCH + (j & 3);
+                        // the keys are RELATIVE to the lower window edges (k1 = dot1 - lo1, k2 = dot2 - lo2); the cascade repeats
+                        // the class tests on them (k1 < hi1 - lo1: inside window 1; k2 >= hi2 - lo2: above window 2)
                         const uint32_t k1b = __float_as_uint(src[0]), k2b = __float_as_uint(src[4 * KCH]);
                         const uint32_t roww = row0 + 16u * h + (uint32_t)j;
                         const uint32_t slot = run & (LBUF_W - 1);
@@ -315,6 +339,18 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(F_TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
+    if constexpr (WIN) {
+        if (!p.ones_in_row) {
+            // constant B block of the folded thresholds: the fourth slab of every stage (never written by the loads, n_slabs <= 3)
+            // holds (1, 1, 0 ...) in the first 16-byte chunk of each row, at its 128-byte-swizzled place (chunk ^ (row & 7))
+            for (int i = threadIdx.x; i < F_STAGES * FR * 8; i += F_THREADS) {
+                const int st = i / (FR * 8), r = (i >> 3) % FR, c = i & 7;
+                const float one = c == (r & 7) ? 1.0f : 0.f;
+                *reinterpret_cast<float4*>(smem_b + st * B_STAGE_BYTES + 3 * B_SLAB_BYTES + r * 128 + c * 16) = make_float4(one, one, 0.f, 0.f);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -331,8 +367,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
                 const int t1 = min(p.n_tiles, t0 + p.tiles_per_range);
                 mbar_wait_relaxed(qempty_bar, (uq & 1u) ^ 1u);                  // MMAs of the previous unit have retired
                 ++uq;
-                mbar_expect_tx(qfull_bar, (uint32_t)p.n_slabs * A_SLAB_BYTES);
-                for (int s = 0; s < p.n_slabs; ++s) tma_load_2d(&map_q, qfull_bar, smem_a + s * A_SLAB_BYTES, s * 32, m_tile * FM);
+                mbar_expect_tx(qfull_bar, (uint32_t)p.n_slabs_q * A_SLAB_BYTES);
+                for (int s = 0; s < p.n_slabs_q; ++s) tma_load_2d(&map_q, qfull_bar, smem_a + s * A_SLAB_BYTES, s * 32, m_tile * FM);
                 for (int t = t0; t < t1; ++t) {
                     mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], (uint32_t)p.n_slabs * B_SLAB_BYTES);
@@ -374,6 +410,16 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_filter_bits_tc(const __grid_co
                                     const uint64_t db = make_smem_desc(b0 + (offb >> 5) * B_SLAB_BYTES + (offb & 31u) * 4u);
                                     umma_tf32(tmem_base + acc * ACC_COLS + l * FR, da, db, kIdescTf32, (pr > 0 || s > 0) ? 1u : 0u);
                                 }
+                            }
+                            if constexpr (WIN) {
+                                // window mode: one more k-step makes the accumulator  dot_l - threshold_l  (-t0, -lo1, -lo2 in
+                                // the query operand's threshold blocks against a (1, 1, 0 ...) block: the padding of the
+                                // rows' fourth slab, or the constant slab behind a stage's three data slabs)
+                                const uint32_t offt = (uint32_t)p.thr_off + 8u * l, offo = (uint32_t)p.thr_off;
+                                const uint64_t da = make_smem_desc(a0 + (offt >> 5) * A_SLAB_BYTES + (offt & 31u) * 4u);
+                                const uint64_t db = make_smem_desc(p.ones_in_row ? b0 + (offo >> 5) * B_SLAB_BYTES + (offo & 31u) * 4u
+                                                                                 : b0 + 3u * B_SLAB_BYTES);
+                                umma_tf32(tmem_base + acc * ACC_COLS + l * FR, da, db, kIdescTf32, 1u);
                             }
                         }
                     }
@@ -585,7 +631,9 @@ struct PackParams {
     int is_query;
     int seg_off[3], kp[3];
     float* out;             // [N, pitch]
-    int pitch;              // packed floats per row (n_slabs * 32)
+    int pitch;              // packed floats per row (whole slabs)
+    int thr_off;            // rows with padding in their fourth slab (ones_in_row): columns thr_off, thr_off + 1 hold 1.0 (the B side
+                            // of the folded thresholds); -1 otherwise and for queries
 };
 
 __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
@@ -595,7 +643,7 @@ __global__ void __launch_bounds__(256) k_pack_rows(const PackParams p) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t row = i / p.pitch;
         const int c = (int)(i - row * p.pitch);
-        float outv = 0.f;
+        float outv = (p.thr_off >= 0 && (c == p.thr_off || c == p.thr_off + 1)) ? 1.0f : 0.f;
 #pragma unroll
         for (int l = 0; l < 3; ++l) {
             if (l < p.lay.L && c >= p.seg_off[l] && c < p.seg_off[l] + 2 * p.kp[l]) {
@@ -628,6 +676,29 @@ __global__ void __launch_bounds__(256) k_query_tq(const float* __restrict__ q_id
     const float xs = l == 0 ? x0 : (l == 1 ? x1 : x2);
     tq[(int64_t)l * Q + q] = nq > 0.f ? __fmul_rn(xs, nq) : __int_as_float(0x7fc00000);
     nq_out[(int64_t)l * Q + q] = nq;
+}
+
+// Window mode folds its lower thresholds into the contraction: the query operand carries three 8-column blocks after the
+// level blocks -- [-t0], [-lo1], [-lo2], each as an exact tf32 (hi, lo) pair in its first two columns -- and every database
+// row the pair (1, 1) at the same place, so one extra k-step per level makes the accumulator  dot - threshold  and the
+// epilogue's test is the SIGN of the accumulator (one funnel shift per element instead of FADD + shift).  Runs between
+// k_filter_predict and the window pass.  (Tried: five single-buffered accumulators with the upper edges folded as well, so
+// that every test is a sign test: 1.83 ms instead of 1.39 ms -- 26 MMAs per tile from one issuing thread and no second
+// accumulator set to hide them.)
+__global__ void __launch_bounds__(256) k_fold_thresholds(const float* __restrict__ tq, const float* __restrict__ win, int Q, int L,
+                                                         int thr_off, int pitch, float* __restrict__ q_packed) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= Q * 3) return;
+    const int q = t / 3, b = t - q * 3;
+    float v;
+    if (b == 0) v = __ldg(tq + q);                                           // t0
+    else if (b == 1) v = __ldg(win + (int64_t)0 * Q + q);                    // lo1
+    else v = L > 2 ? __ldg(win + (int64_t)2 * Q + q) : 0.f;                  // lo2
+    const float hi = trunc_tf32(v);
+    const float lo = trunc_tf32(__fadd_rn(v, -hi));
+    float* dst = q_packed + (int64_t)q * pitch + thr_off + 8 * b;
+    dst[0] = -hi;
+    dst[1] = -lo;
 }
 
 __global__ void __launch_bounds__(256) k_valid_bits(const float* __restrict__ rnorm, int64_t N, int L, uint32_t* __restrict__ valid,
@@ -690,7 +761,8 @@ extern "C" int hq_filter_tc_pack(const float* idx, const float* rnorm, int64_t N
     HQ_REQUIRE(idx && packed && (is_query || rnorm), "null pointer");
     PackParams p{};
     p.idx = idx; p.rnorm = rnorm; p.N = N; p.lay = *layout; p.is_query = is_query ? 1 : 0; p.out = packed;
-    p.pitch = s.n_slabs * 32;
+    p.pitch = (is_query ? s.n_slabs_q : s.n_slabs) * 32;
+    p.thr_off = (!is_query && s.ones_in_row) ? s.thr_off : -1;
     for (int l = 0; l < 3; ++l) { p.seg_off[l] = s.off[l]; p.kp[l] = s.kp[l]; }
     int64_t blocks = (N * p.pitch + 255) / 256;
     const int64_t cap = (int64_t)hq_cached_sm_count() * 32;
@@ -748,6 +820,16 @@ int hq_filter_tc_prepare(const hq_index_layout* layout, const float* q_idx, int 
     return HQ_OK;
 }
 
+// Window mode: write the folded thresholds (-t0, -lo1, -lo2, -hi1, -hi2 as tf32 pairs) into the query operand.
+int hq_filter_tc_fold(const hq_index_layout* layout, const float* tq, const float* win, int Q, float* q_packed, cudaStream_t st) {
+    Segs s;
+    HQ_REQUIRE(make_segs(layout, s) && s.L >= 2, "index layout not supported by the window mode");
+    HQ_REQUIRE(tq && win && q_packed && Q > 0, "bad arguments");
+    k_fold_thresholds<<<(Q * 3 + 255) / 256, 256, 0, st>>>(tq, win, Q, s.L, s.thr_off, s.n_slabs_q * 32, q_packed);
+    HQ_LAUNCH_OK("k_fold_thresholds");
+    return HQ_OK;
+}
+
 // The threshold pass over a prepared batch.  bits may be null (sample pass: lists and the level-0 count only); `o`
 // selects the sample stride, the query-tile subset and the window mode (see FtcParams).
 int hq_filter_tc_pass(const float* db_packed, const uint32_t* valid, int64_t valid_pitch, int64_t N, const hq_index_layout* layout, int Q,
@@ -768,7 +850,7 @@ int hq_filter_tc_pass(const float* db_packed, const uint32_t* valid, int64_t val
                "window mode needs two or three levels, a plane, counters and lists");
 
     FtcParams p{};
-    p.N = N; p.Q = Q; p.L = s.L; p.n_slabs = s.n_slabs;
+    p.N = N; p.Q = Q; p.L = s.L; p.n_slabs = s.n_slabs; p.n_slabs_q = s.n_slabs_q; p.thr_off = s.thr_off; p.ones_in_row = s.ones_in_row;
     for (int l = 0; l < 3; ++l) { p.seg_off[l] = s.off[l]; p.ksteps[l] = s.kp[l] / 8; }
     p.tq = tq; p.valid = valid; p.valid_pitch = valid_pitch; p.bits = bits; p.words = words; p.bits_pitch = bits_pitch;
     p.bits_vec = (bits && (reinterpret_cast<uintptr_t>(bits) & 31) == 0 && bits_pitch % 8 == 0) ? 1 : 0;
@@ -784,8 +866,8 @@ int hq_filter_tc_pass(const float* db_packed, const uint32_t* valid, int64_t val
         p.n_segs = lists->n_segs;
     }
     CUtensorMap mq, mdb;
-    const int ks = s.n_slabs * 32;                 // packed floats per row of both operands
-    int rc = make_map_2d(&mq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, q_packed, Q, ks, ks, 32, FM);
+    const int ks = s.n_slabs * 32, ksq = s.n_slabs_q * 32;          // packed floats per database / query row
+    int rc = make_map_2d(&mq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, q_packed, Q, ksq, ksq, 32, FM);
     if (rc != HQ_OK) return rc;
     rc = make_map_2d(&mdb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, db_packed, N, ks, ks, 32, FR);
     if (rc != HQ_OK) return rc;

@@ -3,6 +3,7 @@
 //
 // Reference semantics: rag/search/engine.py:178-287 (filter), :622-660 (cosine), :512 (sort).
 #include "hq_common.cuh"
+#include "hq_tc.cuh"
 #include <float.h>
 
 namespace {
@@ -687,6 +688,242 @@ __global__ void __launch_bounds__(256) k_rerank_sparse(const float* __restrict__
 }
 
 // ------------------------------------------------------------------------------------
+// a13 + a15 for a handful of queries in ONE launch: exact fp32 cosine of the surviving rows (the arithmetic of k_rerank_sparse,
+// bit for bit) with the top-k taken on the way -- no [Q, N] score row, no separate top-k launches.
+//   grid (P, Q): the P CTAs of a query draw chunks of 16 mask words from a ticket counter (the survivors are a few per cent
+//     of the rows and unevenly spread);
+//   warp 0 of a CTA walks the mask and fetches every surviving row into a ring of shared-memory slots with ONE bulk copy
+//     (cp.async.bulk + full / empty mbarriers, up to 64 rows in flight per SM); the other warps take the slots in turn and
+//     score a row each, the query sits in shared memory.  (The D-strided loop of k_rerank_sparse waits for HBM once per 128
+//     values -- 12 round trips per 1536-D row: ptxas sinks the loads next to their FMAs even when the source issues them
+//     first; two buffers per warp with one copy ahead: 112 us for 57 K rows of 6 KB, slower than that loop.)
+//   every warp keeps its best 32 (score desc, id asc) one per lane, the CTA ranks its warps' lists into a list of k, and the
+//     LAST CTA of the query to finish (a done counter) merges the P lists: only the entries that reach tau = max over the
+//     full lists of their minimum can be in the result.
+// counters: [2 * Q] uint32, zero on entry (ticket, done); the last CTA leaves them zero again.
+// ------------------------------------------------------------------------------------
+constexpr int kSparseTopkThreads = 512;
+constexpr int kSparseTopkMaxK = 32;
+constexpr int kSparseTopkSlots = 64;           // most row slots of the shared-memory ring
+constexpr int kSparseTopkSel = 1024;           // candidates the final merge ranks in shared memory
+
+__device__ __forceinline__ bool cand_better(float s, int64_t id, float s2, int64_t id2) { return s > s2 || (s == s2 && id < id2); }
+
+__global__ void __launch_bounds__(kSparseTopkThreads) k_rerank_sparse_topk(
+    const float* __restrict__ db, const float* __restrict__ db_norm, int64_t N, int64_t D, int64_t db_stride,
+    const float* __restrict__ qm, const float* __restrict__ q_norm, int Q, int64_t q_stride, const uint32_t* __restrict__ mask,
+    int64_t mask_stride, int k, int64_t id_base, int64_t* __restrict__ part_ids, float* __restrict__ part_scores,
+    uint32_t* __restrict__ counters, int64_t* __restrict__ out_ids, float* __restrict__ out_scores, int S, int NP) {
+    extern __shared__ __align__(128) unsigned char sm_raw[];
+    constexpr int NWMAX = kSparseTopkThreads / 32;
+    __shared__ float s_ls[NWMAX * 32];
+    __shared__ int64_t s_lid[NWMAX * 32];
+    __shared__ uint32_t s_nvalid, s_last, s_m;
+    __shared__ float s_wmax[NWMAX];
+    __shared__ __align__(8) uint64_t s_full[kSparseTopkSlots], s_empty[kSparseTopkSlots];
+    __shared__ int s_row[kSparseTopkSlots];
+    const int q = blockIdx.y, P = gridDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nw = nthr >> 5;
+    const int NC = nw - NP, depth = S / NC;                                           // consumer warps, row slots of each (1, 2 or 4)
+    const int NCg = NC / NP;                                                          // consumers served by one producer warp
+    const uint32_t ldepth = depth == 4 ? 2u : (depth == 2 ? 1u : 0u);
+    const int64_t words = (N + 31) / 32;
+    const int n4 = (int)(D / 4);
+    const uint32_t row_bytes = (uint32_t)D * 4u;
+    const uint32_t buf_bytes = (row_bytes + 127u) & ~127u;
+    float4* qs = reinterpret_cast<float4*>(sm_raw);                                   // the query
+    unsigned char* ring = sm_raw + buf_bytes;                                         // S row slots
+    for (int i = tid; i < n4; i += nthr) qs[i] = __ldg(reinterpret_cast<const float4*>(qm + (int64_t)q * q_stride) + i);
+    if (tid == 0) { s_nvalid = 0; s_m = 0; }
+    if (tid < S) { hq_tc::mbar_init(s_full + tid, 1); hq_tc::mbar_init(s_empty + tid, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    float my_s = -2.0f;                       // lane j: the warp's j-th best so far
+    int64_t my_id = INT64_MAX;
+    if (warp < NP) {
+        // ================= producers: walk the mask, one bulk copy per surviving row =================
+        // Chunks of 16 mask words from the query's ticket counter; the ticket two chunks ahead and the words one chunk ahead
+        // are in flight while the rows of the current chunk are issued.  Lane l owns 16 bits of the chunk (word l / 2, half
+        // l % 2) and issues the copies of its own rows; the lanes of a round take consecutive sequence numbers.
+        // A producer warp serves NCg consumer warps; its sequence number i belongs to its consumer i % NCg and to that
+        // consumer's slot (i / NCg) % depth: the phases of a slot are
+        // filled and drained strictly in order by ONE warp each (with a shared ring a warp could meet a slot two phases behind
+        // -- bulk copies complete out of order -- and a parity wait cannot tell that from "ready").
+        // (One lane issuing every copy, with the slot arithmetic as integer divisions: 870 cycles per row, 183 us per query;
+        // one producer warp with 32 issuing lanes: 90 us, the consumers still waiting 40 % of the time.)
+        const int64_t n_chunks = (words + 15) / 16;
+        auto ticket = [&]() -> uint32_t { return lane == 0 ? atomicAdd(counters + 2 * q, 1u) : 0u; };
+        auto load_half = [&](uint32_t ch) -> uint32_t {
+            const int64_t w = 16 * (int64_t)ch + (lane >> 1);
+            uint32_t mw = 0;
+            if ((int64_t)ch < n_chunks && w < words) {
+                mw = __ldg(mask + (int64_t)q * mask_stride + w);
+                if (w * 32 + 32 > N) mw &= (1u << (uint32_t)(N - w * 32)) - 1u;
+            }
+            return (mw >> (16 * (lane & 1))) & 0xffffu;
+        };
+        uint32_t ch1 = __shfl_sync(0xffffffffu, ticket(), 0);
+        uint32_t h1 = load_half(ch1);
+        uint32_t t2 = ticket();
+        uint32_t c_next = 0, turn_base = 0;                    // consumer and turn of the next sequence number
+        const uint32_t dmask = (uint32_t)depth - 1u;           // depth is a power of two
+        const uint32_t lower = (1u << lane) - 1u;
+        const uint32_t cap = (uint32_t)(NCg * depth);          // slots of this producer
+        for (;;) {
+            const uint32_t ch = ch1;
+            uint32_t h = h1;
+            if ((int64_t)ch >= n_chunks) break;
+            ch1 = __shfl_sync(0xffffffffu, t2, 0);
+            h1 = load_half(ch1);
+            t2 = ticket();
+            const int64_t row_base = (16 * (int64_t)ch + (lane >> 1)) * 32 + 16 * (lane & 1);
+            for (;;) {
+                const bool act = h != 0;
+                const uint32_t bal = __ballot_sync(0xffffffffu, act);
+                if (!bal) break;
+                // at most one row per slot and round: a lane never waits for a slot that a lane of the same round fills
+                const uint32_t rank = (uint32_t)__popc(bal & lower);
+                if (act && rank < cap) {
+                    const int b = __ffs(h) - 1;
+                    h &= h - 1;
+                    uint32_t c = c_next + rank, turn = turn_base;
+                    while (c >= (uint32_t)NCg) { c -= (uint32_t)NCg; ++turn; }
+                    const uint32_t slot = (uint32_t)(warp * NCg) + c + (uint32_t)NC * (turn & dmask), use = turn >> ldepth;
+                    if (use >= 1u) hq_tc::mbar_wait(s_empty + slot, (use - 1u) & 1u);
+                    const int64_t row = row_base + b;
+                    s_row[slot] = (int)row;
+                    hq_tc::mbar_expect_tx(s_full + slot, row_bytes);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     hq_tc::smem_u32(ring + (size_t)slot * buf_bytes)),
+                                 "l"(db + row * db_stride), "r"(row_bytes), "r"(hq_tc::smem_u32(s_full + slot))
+                                 : "memory");
+                }
+                c_next += min((uint32_t)__popc(bal), cap);
+                while (c_next >= (uint32_t)NCg) { c_next -= (uint32_t)NCg; ++turn_base; }
+            }
+        }
+        if (lane < NCg) {                                       // one end marker per consumer warp of this producer
+            uint32_t c = c_next + (uint32_t)lane, turn = turn_base;
+            while (c >= (uint32_t)NCg) { c -= (uint32_t)NCg; ++turn; }
+            const uint32_t slot = (uint32_t)(warp * NCg) + c + (uint32_t)NC * (turn & dmask), use = turn >> ldepth;
+            if (use >= 1u) hq_tc::mbar_wait(s_empty + slot, (use - 1u) & 1u);
+            s_row[slot] = -1;
+            hq_tc::mbar_arrive(s_full + slot);
+        }
+        __syncwarp();
+    } else {
+        // ================= consumers: sequence numbers warp - 1, warp - 1 + NC, ... =================
+        const float nq = __ldg(q_norm + q);
+        float thr = -2.0f;                        // score of lane k - 1
+        for (uint32_t turn = 0;; ++turn) {
+            const uint32_t slot = (uint32_t)(warp - NP) + (uint32_t)NC * (turn & ((uint32_t)depth - 1u));
+            hq_tc::mbar_wait(s_full + slot, (turn >> ldepth) & 1u);     // (a suspend-time hint here cost a microsecond per row)
+            const int row = s_row[slot];
+            if (row < 0) break;
+            const float nc = __ldg(db_norm + row);
+            const float4* rv = reinterpret_cast<const float4*>(ring + (size_t)slot * buf_bytes);
+            float acc = 0.f;                                   // lane-strided fmaf chain: the order of k_rerank_sparse
+#pragma unroll 4
+            for (int i4 = lane; i4 < n4; i4 += 32) {
+                const float4 a = qs[i4];
+                const float4 c = rv[i4];
+                acc = fmaf(a.x, c.x, acc); acc = fmaf(a.y, c.y, acc); acc = fmaf(a.z, c.z, acc); acc = fmaf(a.w, c.w, acc);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) hq_tc::mbar_arrive(s_empty + slot);                 // every lane's reads precede the shuffles
+            float sc = 0.f;
+            if (nq != 0.f && nc != 0.f) sc = __fmul_rn(__fadd_rn(__fdiv_rn(acc, __fmul_rn(nq, nc)), 1.0f), 0.5f);
+            if (sc < thr) continue;                                   // warp-uniform
+            const uint32_t bt = __ballot_sync(0xffffffffu, cand_better(sc, (int64_t)row, my_s, my_id));
+            if (!bt) continue;
+            const int pos = __ffs(bt) - 1;                            // the list is sorted: better than lanes pos .. 31
+            const float up_s = __shfl_up_sync(0xffffffffu, my_s, 1);
+            const int64_t up_id = __shfl_up_sync(0xffffffffu, my_id, 1);
+            if (lane > pos) { my_s = up_s; my_id = up_id; }
+            else if (lane == pos) { my_s = sc; my_id = row; }
+            thr = __shfl_sync(0xffffffffu, my_s, k - 1);
+        }
+    }
+    // ---- the CTA's list: rank the warps' entries by counting ----
+    s_ls[tid] = lane < k ? my_s : -2.0f;
+    s_lid[tid] = lane < k ? my_id : INT64_MAX;
+    __syncthreads();
+    {
+        const float v = s_ls[tid];
+        const int64_t id = s_lid[tid];
+        if (id != INT64_MAX) {
+            int rank = 0;
+            for (int j = 0; j < nthr; ++j) rank += cand_better(s_ls[j], s_lid[j], v, id) ? 1 : 0;
+            atomicAdd(&s_nvalid, 1u);
+            if (rank < k) {
+                part_ids[((int64_t)q * P + blockIdx.x) * k + rank] = id;
+                part_scores[((int64_t)q * P + blockIdx.x) * k + rank] = v;
+            }
+        }
+    }
+    __syncthreads();
+    for (int j = (int)min(s_nvalid, (uint32_t)k) + tid; j < k; j += nthr) {
+        part_ids[((int64_t)q * P + blockIdx.x) * k + j] = -1;
+        part_scores[((int64_t)q * P + blockIdx.x) * k + j] = -1.0f;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(counters + 2 * q + 1, 1u) == (uint32_t)(P - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // ---- last CTA of the query: merge the P lists ----
+    const int64_t* pi = part_ids + (int64_t)q * P * k;
+    const float* ps = part_scores + (int64_t)q * P * k;
+    const int M = P * k;
+    float tau = -INFINITY;
+    for (int p = tid; p < P; p += nthr)
+        if (__ldcg(pi + (int64_t)p * k + k - 1) >= 0) tau = fmaxf(tau, __ldcg(ps + (int64_t)p * k + k - 1));   // sorted: last = minimum
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tau = fmaxf(tau, __shfl_xor_sync(0xffffffffu, tau, o));
+    if (lane == 0) s_wmax[warp] = tau;
+    __syncthreads();
+    tau = -INFINITY;
+    for (int w = 0; w < nw; ++w) tau = fmaxf(tau, s_wmax[w]);
+    int64_t* c_id = reinterpret_cast<int64_t*>(sm_raw);                   // the query and the row buffers are no longer needed
+    float* c_s = reinterpret_cast<float*>(c_id + kSparseTopkSel);
+    for (int e = tid; e < M; e += nthr) {
+        const int64_t id = __ldcg(pi + e);
+        const float v = __ldcg(ps + e);
+        if (id >= 0 && !(v < tau)) {
+            const uint32_t slot = atomicAdd(&s_m, 1u);
+            if (slot < (uint32_t)kSparseTopkSel) { c_id[slot] = id; c_s[slot] = v; }
+        }
+    }
+    for (int j = tid; j < k; j += nthr) { out_ids[(int64_t)q * k + j] = -1; out_scores[(int64_t)q * k + j] = -1.0f; }
+    __syncthreads();
+    const int m = (int)s_m;
+    if (m <= kSparseTopkSel) {
+        for (int t = tid; t < m; t += nthr) {
+            const int64_t id = c_id[t];
+            const float v = c_s[t];
+            int rank = 0;
+            for (int u = 0; u < m; ++u) rank += cand_better(c_s[u], c_id[u], v, id) ? 1 : 0;
+            if (rank < k) { out_ids[(int64_t)q * k + rank] = id + id_base; out_scores[(int64_t)q * k + rank] = v; }
+        }
+    } else {
+        // heavily tied scores: more candidates than the shared list holds -- rank them against the global lists
+        for (int e = tid; e < M; e += nthr) {
+            const int64_t id = __ldcg(pi + e);
+            const float v = __ldcg(ps + e);
+            if (id < 0 || v < tau) continue;
+            int rank = 0;
+            for (int u = 0; u < M && rank < k; ++u) {
+                const int64_t idu = __ldcg(pi + u);
+                rank += (idu >= 0 && cand_better(__ldcg(ps + u), idu, v, id)) ? 1 : 0;
+            }
+            if (rank < k) { out_ids[(int64_t)q * k + rank] = id + id_base; out_scores[(int64_t)q * k + rank] = v; }
+        }
+    }
+    if (tid == 0) { counters[2 * q] = 0; counters[2 * q + 1] = 0; }
+}
+
+// ------------------------------------------------------------------------------------
 // per-query top-k of a score row (exact; ties -> lower row id).  One CTA per query.
 // ------------------------------------------------------------------------------------
 constexpr int kMaxK = 1024;
@@ -1070,6 +1307,62 @@ extern "C" int hq_rerank_scores_sparse_f32(const float* db, const float* db_norm
     k_rerank_sparse<<<grid_cap((tasks + 7) / 8, 16), 256, 0, (cudaStream_t)stream>>>(db, db_norm, N, D, db_stride, q, q_norm, Q, q_stride,
                                                                                    mask, mask_stride, scores, scores_stride, vec);
     HQ_LAUNCH_OK("k_rerank_sparse");
+    return HQ_OK;
+}
+
+extern "C" int hq_rerank_sparse_topk_supported(int64_t D, int64_t db_stride, int64_t q_stride, int k) {
+    return (D % 4 == 0 && db_stride % 4 == 0 && q_stride % 4 == 0 && D <= 8192 && k >= 1 && k <= kSparseTopkMaxK) ? 1 : 0;
+}
+
+static int sparse_topk_ctas(int Q) {
+    const int sms = hq_cached_sm_count();          // one wave of 512-thread CTAs (one per SM), shared by the queries
+    return Q <= 1 ? sms : (sms + Q - 1) / Q;
+}
+
+extern "C" int64_t hq_rerank_sparse_topk_scratch_bytes(int Q, int k) {
+    if (Q <= 0 || k <= 0) return 0;
+    return (int64_t)Q * sparse_topk_ctas(Q) * k * 12 + (int64_t)Q * 8 + 64;
+}
+
+extern "C" int hq_rerank_sparse_topk_f32(const float* db, const float* db_norm, int64_t N, int64_t D, int64_t db_stride, const float* q,
+                                         const float* q_norm, int Q, int64_t q_stride, const uint32_t* mask, int64_t mask_stride, int k,
+                                         int64_t id_base, int64_t* ids, float* scores, void* scratch, int64_t scratch_bytes, void* stream) {
+    HQ_REQUIRE(N >= 0 && Q >= 0 && D > 0, "bad shape");
+    if (Q == 0) return HQ_OK;
+    HQ_REQUIRE(db && db_norm && q && q_norm && mask && ids && scores, "null pointer");
+    HQ_REQUIRE(hq_rerank_sparse_topk_supported(D, db_stride, q_stride, k), "needs D %% 4 == 0, D <= 8192, strides %% 4 == 0 and k <= %d",
+               kSparseTopkMaxK);
+    HQ_REQUIRE((reinterpret_cast<uintptr_t>(db) & 15) == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0, "rows must be 16-byte aligned");
+    HQ_REQUIRE(db_stride >= D && q_stride >= D && mask_stride * 32 >= N, "stride too small");
+    HQ_REQUIRE(N < ((int64_t)1 << 31), "N too large for one shard");
+    HQ_REQUIRE(scratch && scratch_bytes >= hq_rerank_sparse_topk_scratch_bytes(Q, k), "scratch too small");
+    const int P = sparse_topk_ctas(Q);
+    int64_t* p_ids = reinterpret_cast<int64_t*>(scratch);                        // [Q][P][k]
+    float* p_sc = reinterpret_cast<float*>(p_ids + (int64_t)Q * P * k);
+    uint32_t* counters = reinterpret_cast<uint32_t*>(p_sc + (((int64_t)Q * P * k + 3) & ~(int64_t)3));
+    cudaStream_t st = (cudaStream_t)stream;
+    HQ_CUDA_OK(cudaMemsetAsync(counters, 0, (size_t)Q * 8, st));
+    // shared memory: the query + S row slots (rows padded to 128 bytes), as many as fit 200 KB
+    const size_t buf = ((size_t)D * 4 + 127) & ~(size_t)127;
+    int S = (int)((200 * 1024 - buf) / buf);
+    if (S > kSparseTopkSlots) S = kSparseTopkSlots;
+    HQ_REQUIRE(S >= 1, "D too large");
+    // one producer warp and up to 15 consumer warps.  (2 / 3 / 4 producer warps with 14 / 12 / 12 consumers: 93-103 us for a
+    // query against 1 M x 1536 where this split takes 85-100 us -- 57 K scattered 6 KB rows arrive at ~4 TB/s either way.)
+    const int NP = 1;
+    const int NC = S < kSparseTopkThreads / 32 - 1 ? S : kSparseTopkThreads / 32 - 1;
+    const int depth = S / NC >= 4 ? 4 : (S / NC >= 2 ? 2 : 1);                  // slots per consumer: a power of two
+    S = depth * NC;
+    size_t smem = buf + (size_t)S * buf;
+    if (smem < (size_t)kSparseTopkSel * 12) smem = (size_t)kSparseTopkSel * 12;
+    static bool attr = false;
+    if (!attr) {
+        HQ_CUDA_OK(cudaFuncSetAttribute(k_rerank_sparse_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+        attr = true;
+    }
+    k_rerank_sparse_topk<<<dim3(P, Q), (NP + NC) * 32, smem, st>>>(db, db_norm, N, D, db_stride, q, q_norm, Q, q_stride, mask, mask_stride, k,
+                                                                  id_base, p_ids, p_sc, counters, ids, scores, S, NP);
+    HQ_LAUNCH_OK("k_rerank_sparse_topk");
     return HQ_OK;
 }
 

@@ -676,7 +676,10 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
         budget = max(int(filter_scratch_bytes), 1 << 28)
         while qc > 128 and int(lib.hq_filter_fast_scratch_bytes(N, qc, C.byref(db.layout))) > budget:
             qc = max(128, (qc // 2 + 127) // 128 * 128)
-    need_scores = not (rerank == "bf16" and (fast or not use_filter))
+    # a handful of queries behind the filter: rerank + top-k of the survivors in one launch, no [Q, N] score row
+    fused_sparse = (rerank == "sparse" and use_filter and N > 0 and
+                    bool(lib.hq_rerank_sparse_topk_supported(db.D, db.emb.stride(0), q.stride(0), k)))
+    need_scores = not ((rerank == "bf16" and (fast or not use_filter)) or (fused_sparse and fast))    # the exact filter's scratch
     scores = torch.empty((qc, N), dtype=torch.float32, device=d) if need_scores else None
     # rows padded to whole 32-byte sectors: the window pass of the fast filter then writes its plane straight into the mask
     mask = torch.zeros((qc, (words + 7) // 8 * 8), dtype=torch.int32, device=d)[:, :words]
@@ -717,6 +720,16 @@ def search_batch(db: EmbeddingDatabase, queries, k: int = 10, *, use_filter: boo
                                               dev.stream_ptr()))
                 if guard_stats is not None:
                     guard_stats.append(guard)
+                _end(tok)
+                continue
+            if fused_sparse and m is not None:
+                tok = _phase("rerank_gemm")
+                sb = int(lib.hq_rerank_sparse_topk_scratch_bytes(nq, k))
+                scratch = torch.empty(sb, dtype=torch.uint8, device=d)
+                check(lib.hq_rerank_sparse_topk_f32(dev.ptr(db.emb), dev.ptr(db.norms), N, db.D, db.emb.stride(0),
+                                                    dev.ptr(q[s:e]), dev.ptr(q_norms[s:e]), nq, q.stride(0),
+                                                    dev.ptr(m), mask.stride(0), k, db.id_base,
+                                                    dev.ptr(ids[s:e]), dev.ptr(out_scores[s:e]), dev.ptr(scratch), sb, dev.stream_ptr()))
                 _end(tok)
                 continue
             tok = _phase("rerank_gemm")

@@ -308,3 +308,84 @@ def test_bf16_only_database_scores_the_stored_rows_exactly(hq, N, D, Q, k):
         assert np.abs(sc[valid] - scf.cpu().numpy()[valid]).max() < 2e-3
     with pytest.raises(ValueError, match="bf16-only"):
         hq.search_batch(lean, qs, k, rerank="f32")
+
+
+@pytest.mark.parametrize("N,D,Q,k,density", [(50_000, 1536, 1, 10, 0.06), (9_999, 768, 4, 32, 0.3), (4_097, 2048, 2, 1, 0.5),
+                                             (3_000, 4096, 3, 10, 0.02), (70_001, 100, 1, 10, 0.9), (1_000, 1024, 2, 20, 0.004),
+                                             (6_000, 1536, 1, 10, 0.97), (2_500, 8192, 2, 5, 0.6)])
+def test_fused_sparse_rerank_topk_equals_the_two_step_path(hq, N, D, Q, k, density):
+    """hq_rerank_sparse_topk_f32 (rows staged by bulk copies, per-warp lists, last-CTA merge) against
+    hq_rerank_scores_sparse_f32 + hq_topk_from_scores_chunked on random survivor masks: ids and scores identical, with
+    duplicate rows (exact ties -> lower id), zero rows, fewer than k survivors and a non-zero id_base."""
+    from hilbert_quantization_b200 import _device as dev
+    from hilbert_quantization_b200._lib import lib, check
+    g = torch.Generator(device="cuda").manual_seed(N + D + k)
+    db = torch.randn((N, D), device="cuda", generator=g)
+    db[N // 2] = db[3]
+    db[N - 1] = db[3]
+    db[7] = 0.0
+    qs = torch.randn((Q, D), device="cuda", generator=g)
+    qs[0] = db[3]
+    norms, qn = db.norm(dim=1), qs.norm(dim=1)
+    check(lib.hq_row_norms(dev.ptr(db), N, D, D, dev.ptr(norms), dev.stream_ptr()))
+    check(lib.hq_row_norms(dev.ptr(qs), Q, D, D, dev.ptr(qn), dev.stream_ptr()))
+    words = (N + 31) // 32
+    alive = torch.rand((Q, words * 32), device="cuda", generator=g) < density
+    alive[:, [3, 7, N // 2, N - 1]] = True
+    alive[:, N:] = True                                            # bits beyond N must be ignored
+    if Q > 1:
+        alive[Q - 1] = False
+        alive[Q - 1, :5] = True                                    # fewer than k survivors (k > 5)
+        alive[Q - 1, N:] = True
+    shifts = torch.arange(32, device="cuda", dtype=torch.int64)
+    mask = ((alive.view(Q, words, 32).to(torch.int64) << shifts).sum(dim=2) & 0xffffffff).to(torch.int64)
+    mask = torch.where(mask >= 2 ** 31, mask - 2 ** 32, mask).to(torch.int32).contiguous()
+    id_base = 1_000_000
+    assert lib.hq_rerank_sparse_topk_supported(D, D, D, k)
+    ids = torch.empty((Q, k), dtype=torch.int64, device="cuda")
+    sc = torch.empty((Q, k), dtype=torch.float32, device="cuda")
+    sb = int(lib.hq_rerank_sparse_topk_scratch_bytes(Q, k))
+    scratch = torch.empty(sb, dtype=torch.uint8, device="cuda")
+    for _ in range(2):                                             # the second call finds the counters as the first left them
+        check(lib.hq_rerank_sparse_topk_f32(dev.ptr(db), dev.ptr(norms), N, D, D, dev.ptr(qs), dev.ptr(qn), Q, D, dev.ptr(mask), words,
+                                            k, id_base, dev.ptr(ids), dev.ptr(sc), dev.ptr(scratch), sb, dev.stream_ptr()))
+    scores = torch.empty((Q, N), dtype=torch.float32, device="cuda")
+    check(lib.hq_rerank_scores_sparse_f32(dev.ptr(db), dev.ptr(norms), N, D, D, dev.ptr(qs), dev.ptr(qn), Q, D, dev.ptr(mask), words,
+                                          dev.ptr(scores), N, dev.stream_ptr()))
+    ids2 = torch.empty_like(ids)
+    sc2 = torch.empty_like(sc)
+    tb = max(int(lib.hq_topk_chunked_scratch_bytes(N, Q, k)), 8)
+    ts = torch.empty(tb, dtype=torch.uint8, device="cuda")
+    check(lib.hq_topk_from_scores_chunked(dev.ptr(scores), N, N, Q, k, id_base, dev.ptr(ids2), dev.ptr(sc2), dev.ptr(ts), tb, dev.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(ids, ids2), (ids, ids2)
+    assert torch.equal(sc, sc2)
+    if k >= 3:
+        assert ids[0, :3].tolist() == [id_base + 3, id_base + N // 2, id_base + N - 1]
+    if Q > 1 and k > 5:
+        assert (ids[Q - 1, 5:] == -1).all() and (sc[Q - 1, 5:] == -1.0).all()
+
+
+def test_fused_sparse_rerank_topk_with_all_scores_tied(hq):
+    """Every surviving row identical: all candidates tie, the merge must fall back to ranking by id."""
+    from hilbert_quantization_b200 import _device as dev
+    from hilbert_quantization_b200._lib import lib, check
+    N, D, k = 40_000, 768, 10
+    row = torch.randn(D, device="cuda")
+    db = row.repeat(N, 1).contiguous()
+    qs = row[None].clone()
+    norms, qn = torch.empty(N, device="cuda"), torch.empty(1, device="cuda")
+    check(lib.hq_row_norms(dev.ptr(db), N, D, D, dev.ptr(norms), dev.stream_ptr()))
+    check(lib.hq_row_norms(dev.ptr(qs), 1, D, D, dev.ptr(qn), dev.stream_ptr()))
+    words = (N + 31) // 32
+    mask = torch.full((1, words), -1, dtype=torch.int32, device="cuda")
+    mask[0, 0] = -4                                                 # rows 0 and 1 are dead
+    ids = torch.empty((1, k), dtype=torch.int64, device="cuda")
+    sc = torch.empty((1, k), dtype=torch.float32, device="cuda")
+    sb = int(lib.hq_rerank_sparse_topk_scratch_bytes(1, k))
+    scratch = torch.empty(sb, dtype=torch.uint8, device="cuda")
+    check(lib.hq_rerank_sparse_topk_f32(dev.ptr(db), dev.ptr(norms), N, D, D, dev.ptr(qs), dev.ptr(qn), 1, D, dev.ptr(mask), words,
+                                        k, 0, dev.ptr(ids), dev.ptr(sc), dev.ptr(scratch), sb, dev.stream_ptr()))
+    torch.cuda.synchronize()
+    assert ids[0].tolist() == list(range(2, 2 + k))
+    assert (sc[0] == sc[0, 0]).all()
