@@ -45,6 +45,11 @@ SIGNATURES = {
     "hq_filter_fast_mode": (_i32, [_i64, _i32, C.POINTER(IndexLayout)]),
     "hq_filter_fast_fallback_offset": (_i64, [_i64, _i32, C.POINTER(IndexLayout)]),
     "hq_filter_fast_window_layout": (_i32, [_i64, _i32, C.POINTER(IndexLayout), _p]),
+    "hq_filter_rows_max_queries": (_i32, []),
+    "hq_filter_rows_cols": (_i32, [C.POINTER(IndexLayout)]),
+    "hq_filter_rows_pack": (_i32, [_p, _p, _i64, C.POINTER(IndexLayout), _p, _p]),
+    "hq_filter_fast_rows": (_i32, [_p, _p, _i64, C.POINTER(IndexLayout), _p, _i32, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _i32, _p,
+                                   _p, _i64, _p, _p, _p, _i64, _p]),
     "hq_filter_fast": (_i32, [_p, _p, _i64, C.POINTER(IndexLayout), _p, _i32, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _i32, _p,
                               _p, _i64, _p, _p, _p, _i64, _p]),
     "hq_filter_tc_supported": (_i32, [C.POINTER(IndexLayout)]),

@@ -65,6 +65,10 @@ struct HqFtcOpts {              // variants of the threshold pass (see FtcParams
 };
 int hq_filter_tc_prepare(const hq_index_layout* layout, const float* q_idx, int Q, const float* xstar, float* q_packed, float* tq,
                          float* nq, cudaStream_t st);
+int hq_filter_rows_pass(const float* rows, const uint32_t* valid, int64_t valid_pitch, int64_t N, const hq_index_layout* layout,
+                        const float* q_idx, int Q, const float* tq, const float* win, uint32_t* alive, int64_t alive_pitch,
+                        int32_t* wcnt, const HqFilterLists* lists, cudaStream_t st);
+extern "C" int hq_filter_rows_max_queries(void);
 int hq_filter_tc_fold(const hq_index_layout* layout, const float* tq, const float* win, int Q, float* q_packed, cudaStream_t st);
 int hq_filter_tc_pass(const float* db_packed, const uint32_t* valid, int64_t valid_pitch, int64_t N, const hq_index_layout* layout, int Q,
                       const float* q_packed, const float* tq, uint32_t* bits, int64_t bits_pitch, const HqFilterLists* lists,

@@ -2039,6 +2039,18 @@ extern "C" int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, c
                               const float* db_packed, const uint32_t* valid, int64_t valid_pitch, const uint16_t* lens,
                               const int32_t* exc_rows, int n_exc, const double* thr, uint32_t* mask, int64_t mask_stride,
                               int32_t* n_out, int32_t* counts, void* scratch, int64_t scratch_bytes, void* stream) {
+    return hq_filter_fast_rows(idx, rnorm, N, layout, q_idx, Q, xstar, ratio, lvl_rows, lvl_pitch, db_packed, nullptr, valid, valid_pitch, lens,
+                               exc_rows, n_exc, thr, mask, mask_stride, n_out, counts, scratch, scratch_bytes, stream);
+}
+
+// hq_filter_fast with the scaled compact rows of hq_filter_rows_pack (`db_rows`, may be null): window-mode batches of up
+// to hq_filter_rows_max_queries() queries run their window pass on the CUDA cores over those rows (hq_filter_rows.cu).
+extern "C" int hq_filter_fast_rows(const float* idx, const float* rnorm, int64_t N, const hq_index_layout* layout, const float* q_idx, int Q,
+                                   const float* xstar, const double* ratio, const float* const* lvl_rows, const int32_t* lvl_pitch,
+                                   const float* db_packed, const float* db_rows, const uint32_t* valid, int64_t valid_pitch,
+                                   const uint16_t* lens, const int32_t* exc_rows, int n_exc, const double* thr, uint32_t* mask,
+                                   int64_t mask_stride, int32_t* n_out, int32_t* counts, void* scratch, int64_t scratch_bytes,
+                                   void* stream) {
     HQ_REQUIRE(hq_filter_fast_supported(layout), "index layout not supported by the fast filter");
     HQ_REQUIRE(N >= 0 && Q >= 0, "negative size");
     if (N == 0 || Q == 0) return HQ_OK;
@@ -2125,16 +2137,22 @@ extern "C" int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, c
         pp.c0_s = c0_s; pp.win = win; pp.pflag = pflag;
         k_filter_predict<<<Q, 256, 0, st>>>(pp);
         HQ_LAUNCH_OK("k_filter_predict");
-        // 3. window pass (its thresholds folded into the query operand first)
-        rc = hq_filter_tc_fold(layout, tq, win, Q, q_packed, st);
-        if (rc != HQ_OK) return rc;
+        // 3. window pass: a handful of queries over the scaled fp32 rows on the CUDA cores, a batch on the tensor cores (its
+        //    thresholds folded into the query operand first)
         HQ_CUDA_OK(cudaMemsetAsync(seg_n, 0, (size_t)Q * wg.n_segs_w * 4, st));
         HqFilterLists lw{};
         lw.rows = l_rows; lw.k1 = l_k1; lw.k2 = L > 2 ? l_k2 : nullptr; lw.seg_n = seg_n; lw.seg_cap = wg.seg_cap_w; lw.n_segs = wg.n_segs_w;
-        HqFtcOpts ow{};
-        ow.tile_stride = 1; ow.win = win; ow.wcnt = wcnt;
-        rc = hq_filter_tc_pass(db_packed, valid, valid_pitch, N, layout, Q, q_packed, tq, alive, pitch, &lw, &ow, st);
-        if (rc != HQ_OK) return rc;
+        if (db_rows && Q <= hq_filter_rows_max_queries()) {
+            rc = hq_filter_rows_pass(db_rows, valid, valid_pitch, N, layout, q_idx, Q, tq, win, alive, pitch, wcnt, &lw, st);
+            if (rc != HQ_OK) return rc;
+        } else {
+            rc = hq_filter_tc_fold(layout, tq, win, Q, q_packed, st);
+            if (rc != HQ_OK) return rc;
+            HqFtcOpts ow{};
+            ow.tile_stride = 1; ow.win = win; ow.wcnt = wcnt;
+            rc = hq_filter_tc_pass(db_packed, valid, valid_pitch, N, layout, Q, q_packed, tq, alive, pitch, &lw, &ow, st);
+            if (rc != HQ_OK) return rc;
+        }
         ExcParams ep{};
         if (n_exc > 0) {
             ep.idx = idx; ep.lens = lens; ep.lay = *layout; ep.q_idx = q_idx; ep.Q = Q; ep.exc_rows = exc_rows; ep.n_exc = n_exc;

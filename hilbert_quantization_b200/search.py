@@ -280,7 +280,7 @@ class EmbeddingDatabase:
         self._lvl_ptrs = (C.c_void_p * 3)(*([t.data_ptr() for t in self._lvl_rows[:3]] + [None] * (3 - min(3, len(self._lvl_rows)))))
         self._lvl_pitch = (C.c_int32 * 3)(*(pitches[:3] + [0] * (3 - min(3, len(pitches)))))
         # tensor-core threshold pass: tf32 hi/lo-split, norm-scaled copy of the index rows [N, 128] + validity words
-        self.tc_packed = self.tc_valid = None
+        self.tc_packed = self.tc_valid = self.tc_rows = None
         self.tc_valid_pitch = 0
         if tc_filter and self.fast_filter_ok and self.N > 0 and bool(lib.hq_filter_tc_supported(C.byref(self.layout))):
             self.tc_valid_pitch = int(lib.hq_filter_tc_valid_pitch(self.N))
@@ -297,6 +297,14 @@ class EmbeddingDatabase:
                 keep = ~torch.bitwise_left_shift(torch.ones_like(r), r & 31).to(torch.int32)
                 for w, m in zip((r >> 5).tolist(), keep.tolist()):     # a handful of rows: per-word read-modify-write
                     self.tc_valid[:, w] &= m
+            # latency path (a handful of queries): the used part of the index rows as plain fp32, scaled by 1 / |c_l|
+            # (144 bytes per 1536-D row) -- the window pass of such a batch runs over them on the CUDA cores
+            rcols = int(lib.hq_filter_rows_cols(C.byref(self.layout)))
+            if rcols and self.N * rcols * 4 <= ROW_PASS_MAX_BYTES:
+                self.tc_rows = torch.empty((self.N, rcols), dtype=torch.float32, device=d)
+                with torch.cuda.device(d):
+                    check(lib.hq_filter_rows_pack(dev.ptr(self.idx), dev.ptr(self.level_norms), self.N, C.byref(self.layout),
+                                                  dev.ptr(self.tc_rows), dev.stream_ptr()))
 
     @property
     def num_levels(self) -> int:
@@ -495,9 +503,10 @@ def progressive_filter_global(db: EmbeddingDatabase, q_idx: torch.Tensor, q_lens
 
 
 def progressive_filter_fast(db: EmbeddingDatabase, q_idx: torch.Tensor, mask: torch.Tensor,
-                            trace: Optional[FilterTrace] = None, tensor_cores: bool = True):
+                            trace: Optional[FilterTrace] = None, tensor_cores: bool = True, row_pass: bool = True):
     """All filter levels for a query batch through hq_filter_fast (no score matrix).  With
-    `tensor_cores` (and a packed operand on the shard) the threshold pass runs on tcgen05."""
+    `tensor_cores` (and a packed operand on the shard) the threshold pass runs on tcgen05; a handful of queries
+    (`row_pass`, hq_filter_rows_max_queries) run their window pass over the shard's scaled fp32 rows instead."""
     use_tc = tensor_cores and db.tc_packed is not None
     Q, N, d = q_idx.shape[0], db.N, db.device
     L = db.num_levels
@@ -507,10 +516,12 @@ def progressive_filter_fast(db: EmbeddingDatabase, q_idx: torch.Tensor, mask: to
     n_out = torch.empty(Q, dtype=torch.int32, device=d)
     counts = torch.zeros((L, 3, Q), dtype=torch.int32, device=d) if trace is not None else None
     with torch.cuda.device(d):
-        check(lib.hq_filter_fast(dev.ptr(db.idx), dev.ptr(db.level_norms), N, C.byref(db.layout), dev.ptr(q_idx), Q,
+        check(lib.hq_filter_fast_rows(dev.ptr(db.idx), dev.ptr(db.level_norms), N, C.byref(db.layout), dev.ptr(q_idx), Q,
                                  C.cast(db._xstar_host, C.c_void_p), C.cast(db._ratio_host, C.c_void_p),
                                  C.cast(db._lvl_ptrs, C.c_void_p), C.cast(db._lvl_pitch, C.c_void_p),
-                                 dev.ptr(db.tc_packed) if use_tc else None, dev.ptr(db.tc_valid) if use_tc else None,
+                                 dev.ptr(db.tc_packed) if use_tc else None,
+                                 dev.ptr(db.tc_rows) if (use_tc and db.tc_rows is not None and row_pass) else None,
+                                 dev.ptr(db.tc_valid) if use_tc else None,
                                  db.tc_valid_pitch if use_tc else 0,
                                  dev.ptr(db.lens), dev.ptr(db.exc_rows) if db.exc_rows.numel() else None, int(db.exc_rows.numel()),
                                  C.cast(db._thr_host, C.c_void_p),
@@ -539,6 +550,7 @@ def prepare_queries(db: EmbeddingDatabase, queries) -> Tuple[torch.Tensor, torch
     return q, q_idx, row_lengths(q_idx, db.layout), row_norms(q)
 
 
+ROW_PASS_MAX_BYTES = 4 << 30        # largest scaled-row copy a shard keeps for the CUDA-core window pass of small batches
 SPARSE_RERANK_MAX_QUERIES = 4       # batches up to this size score only the filter's survivors (exact fp32, one warp per row)
 _SIDE_STREAMS: dict = {}
 _FLAG_POOL: list = []          # pinned one-byte buffers (allocating pinned memory per call would synchronise the device)

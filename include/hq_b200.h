@@ -207,6 +207,23 @@ int hq_filter_fast(const float* idx, const float* rnorm, int64_t N, const hq_ind
                    const uint16_t* lens, const int32_t* exc_rows, int n_exc, const double* thr,
                    uint32_t* mask, int64_t mask_stride, int32_t* n_out, int32_t* counts,
                    void* scratch, int64_t scratch_bytes, void* stream);
+/* The same filter with one more database operand for the latency path: `db_rows` [N, hq_filter_rows_cols] float32 =
+ * the used part of every index row with each level scaled by 1 / |c_l| and padded to whole float4
+ * (hq_filter_rows_pack: 144 bytes per 1536-D row, 64 for 768-D).  Window-mode batches of at most
+ * hq_filter_rows_max_queries() queries then run their window pass as plain fp32 FMAs over those rows on the CUDA cores
+ * (a thread per row, rows staged by bulk copies; the tensor-core pass spends a 128-query tile on them): same outputs,
+ * same 2e-6 parity band.  db_rows == NULL: hq_filter_fast. */
+int hq_filter_rows_max_queries(void);
+int hq_filter_rows_cols(const hq_index_layout* layout);
+int hq_filter_rows_pack(const float* idx, const float* rnorm, int64_t N, const hq_index_layout* layout, float* rows,
+                        void* stream);
+int hq_filter_fast_rows(const float* idx, const float* rnorm, int64_t N, const hq_index_layout* layout,
+                        const float* q_idx, int Q, const float* xstar, const double* ratio,
+                        const float* const* lvl_rows, const int32_t* lvl_pitch,
+                        const float* db_packed, const float* db_rows, const uint32_t* valid, int64_t valid_pitch,
+                        const uint16_t* lens, const int32_t* exc_rows, int n_exc, const double* thr,
+                        uint32_t* mask, int64_t mask_stride, int32_t* n_out, int32_t* counts,
+                        void* scratch, int64_t scratch_bytes, void* stream);
 /* exc_rows [n_exc] (device int32): rows whose stored length differs from lvl_keff at some level (a block mean
  * that is exactly 0 at the end of an index row: ~1 row in 10 M at 768-D).  The reference normalises the query
  * over the shorter common prefix for them (rag/search/engine.py:216-227); they are excluded from the dense

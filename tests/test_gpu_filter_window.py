@@ -166,3 +166,32 @@ def test_second_stage_is_exact_when_the_windows_miss(hq, tmp_path):
     # borderline rows (a score within ~2e-6 of a threshold / cut score, rounded differently by the tensor-core pass and the
     # exact path) may differ in a few of the 160 queries, by single rows -- the same rule as _compare above
     assert differ <= 5 and worst <= 2 and ids_equal == 1, (stage1, stage2, differ, worst, ids_equal)
+
+
+@pytest.mark.parametrize("N,D,Q", [(150000, 1536, 1), (200001, 768, 3), (140000, 1024, 8), (70000, 2048, 2), (66000, 1536, 5)])
+def test_row_pass_of_small_batches_equals_exact_filter_and_tensor_pass(hq, N, D, Q):
+    """Batches of at most hq_filter_rows_max_queries() queries run their window pass on the CUDA cores over the shard's scaled
+    fp32 rows (csrc/hq_filter_rows.cu): same survivors as the exact per-level path (borderline rule as above) and as the
+    tensor-core window pass, with an exceptional (shortened) index row and a zero row in the shard."""
+    from hilbert_quantization_b200._lib import lib
+    from hilbert_quantization_b200.search import unpack_mask, prepare_queries, progressive_filter_fast
+    assert Q <= int(lib.hq_filter_rows_max_queries())
+    rng = np.random.default_rng(N + D + Q)
+    db = rng.standard_normal((N, D)).astype(np.float32)
+    qs = rng.standard_normal((Q, D)).astype(np.float32)
+    qs[0] = db[5] + 0.05 * rng.standard_normal(D).astype(np.float32)
+    db[N // 3] = db[5]
+    db[11] = 0.0
+    db[N - 3, D - 64:] = 0.0                                     # last level-0 block mean exactly 0: an exceptional row
+    _compare(hq, db, qs, borderline=1)
+    d = hq.EmbeddingDatabase(db)
+    assert d.tc_rows is not None and d.tc_rows.shape[1] == int(lib.hq_filter_rows_cols(C.byref(d.layout)))
+    q, q_idx, q_lens, q_norms = prepare_queries(d, qs)
+    words = (N + 31) // 32
+    masks = []
+    for row_pass in (True, False):
+        mask = torch.zeros((Q, (words + 7) // 8 * 8), dtype=torch.int32, device="cuda")[:, :words]
+        m = progressive_filter_fast(d, q_idx, mask, row_pass=row_pass)
+        masks.append(unpack_mask(m.clone(), N))
+    diff = (masks[0] != masks[1]).sum(axis=1)
+    assert (diff <= 2).all() and (diff > 0).sum() <= 1, diff
