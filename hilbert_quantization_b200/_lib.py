@@ -63,7 +63,7 @@ SIGNATURES = {
     "hq_paired_cosine01": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _p, _p]),
     "hq_rerank_sparse_topk_supported": (_i32, [_i64, _i64, _i64, _i32]),
     "hq_rerank_sparse_topk_scratch_bytes": (_i64, [_i32, _i32]),
-    "hq_rerank_sparse_topk_f32": (_i32, [_p, _p, _i64, _i64, _i64, _p, _p, _i32, _i64, _p, _i64, _i32, _i64, _p, _p, _p, _i64, _p]),
+    "hq_rerank_sparse_topk": (_i32, [_p, _p, _i64, _i64, _i64, _p, _i64, C.c_float, _p, _p, _i32, _i64, _p, _i64, _i32, _i64, _p, _p, _p, _i64, _p]),
     "hq_rerank_scores_sparse_f32": (_i32, [_p, _p, _i64, _i64, _i64, _p, _p, _i32, _i64, _p, _i64, _p, _i64, _p]),
     "hq_topk_from_scores": (_i32, [_p, _i64, _i64, _i32, _i32, _i64, _p, _p, _p]),
     "hq_topk_chunked_scratch_bytes": (_i64, [_i64, _i32, _i32]),

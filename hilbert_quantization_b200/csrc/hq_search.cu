@@ -4,6 +4,7 @@
 // Reference semantics: rag/search/engine.py:178-287 (filter), :622-660 (cosine), :512 (sort).
 #include "hq_common.cuh"
 #include "hq_tc.cuh"
+#include <cuda_bf16.h>
 #include <float.h>
 
 namespace {
@@ -709,12 +710,27 @@ constexpr int kSparseTopkSel = 1024;           // candidates the final merge ran
 
 __device__ __forceinline__ bool cand_better(float s, int64_t id, float s2, int64_t id2) { return s > s2 || (s == s2 && id < id2); }
 
+// B16: the rows of phase one are the shard's UNIT rows in bf16 (half the bytes: 57 K scattered rows arrive at ~4 TB/s whatever
+// their size); the lists then hold the accumulators a = q . c16 (which order the rows like the cosine up to the bf16
+// rounding of c), 32 per list, and the last CTA re-scores the best kSparseTopkR of the merged lists EXACTLY from the fp32
+// rows (same arithmetic as the fp32 pass: identical scores) and checks that the result is proven:
+//     t_k  >  max(a of everything that was not re-scored)  +  E,      E = |q| (dc_max + 1e-5 + 2.4e-7 D)
+// (t_k = k-th best exact value q . c / |c|; |a - t| <= |q| |c16 - c / |c|| + accumulation error, the bound of
+// k_rerank_tc_merge without the query's own rounding).  A query that fails the check -- a cluster of near duplicates around
+// rank k -- raises flags[q]; the fp32 kernel launched right behind (`only_flagged`) redoes exactly those queries.
+constexpr int kSparseTopkR = 32;               // rows re-scored exactly by the last CTA (B16)
+constexpr int kSparseTopkSelB = 512;           // candidates the B16 merge ranks in shared memory
+
+template <bool B16>
 __global__ void __launch_bounds__(kSparseTopkThreads) k_rerank_sparse_topk(
     const float* __restrict__ db, const float* __restrict__ db_norm, int64_t N, int64_t D, int64_t db_stride,
+    const __nv_bfloat16* __restrict__ db16, int64_t db16_pitch, float dc_max,
     const float* __restrict__ qm, const float* __restrict__ q_norm, int Q, int64_t q_stride, const uint32_t* __restrict__ mask,
     int64_t mask_stride, int k, int64_t id_base, int64_t* __restrict__ part_ids, float* __restrict__ part_scores,
-    uint32_t* __restrict__ counters, int64_t* __restrict__ out_ids, float* __restrict__ out_scores, int S, int NP) {
+    uint32_t* __restrict__ counters, uint32_t* __restrict__ flags, int only_flagged, int64_t* __restrict__ out_ids,
+    float* __restrict__ out_scores, int S, int NP, int R) {
     extern __shared__ __align__(128) unsigned char sm_raw[];
+    if (only_flagged && __ldcg(flags + blockIdx.y) == 0u) return;
     constexpr int NWMAX = kSparseTopkThreads / 32;
     __shared__ float s_ls[NWMAX * 32];
     __shared__ int64_t s_lid[NWMAX * 32];
@@ -722,22 +738,27 @@ __global__ void __launch_bounds__(kSparseTopkThreads) k_rerank_sparse_topk(
     __shared__ float s_wmax[NWMAX];
     __shared__ __align__(8) uint64_t s_full[kSparseTopkSlots], s_empty[kSparseTopkSlots];
     __shared__ int s_row[kSparseTopkSlots];
+    __shared__ __align__(8) uint64_t s_rbar;
+    __shared__ uint32_t s_scan[NWMAX];
+    __shared__ int s_cut;
     const int q = blockIdx.y, P = gridDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nw = nthr >> 5;
     const int NC = nw - NP, depth = S / NC;                                           // consumer warps, row slots of each (1, 2 or 4)
     const int NCg = NC / NP;                                                          // consumers served by one producer warp
     const uint32_t ldepth = depth == 4 ? 2u : (depth == 2 ? 1u : 0u);
     const int64_t words = (N + 31) / 32;
     const int n4 = (int)(D / 4);
-    const uint32_t row_bytes = (uint32_t)D * 4u;
+    const int kl = B16 ? 32 : k;                                                      // entries per list
+    const uint32_t row_bytes = B16 ? (uint32_t)D * 2u : (uint32_t)D * 4u;
     const uint32_t buf_bytes = (row_bytes + 127u) & ~127u;
+    const uint32_t q_bytes = ((uint32_t)D * 4u + 127u) & ~127u;
     float4* qs = reinterpret_cast<float4*>(sm_raw);                                   // the query
-    unsigned char* ring = sm_raw + buf_bytes;                                         // S row slots
+    unsigned char* ring = sm_raw + q_bytes;                                           // S row slots
     for (int i = tid; i < n4; i += nthr) qs[i] = __ldg(reinterpret_cast<const float4*>(qm + (int64_t)q * q_stride) + i);
-    if (tid == 0) { s_nvalid = 0; s_m = 0; }
+    if (tid == 0) { s_nvalid = 0; s_m = 0; hq_tc::mbar_init(&s_rbar, 1); }
     if (tid < S) { hq_tc::mbar_init(s_full + tid, 1); hq_tc::mbar_init(s_empty + tid, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    float my_s = -2.0f;                       // lane j: the warp's j-th best so far
+    float my_s = -INFINITY;                   // lane j: the warp's j-th best so far
     int64_t my_id = INT64_MAX;
     if (warp < NP) {
         // ================= producers: walk the mask, one bulk copy per surviving row =================
@@ -794,7 +815,8 @@ __global__ void __launch_bounds__(kSparseTopkThreads) k_rerank_sparse_topk(
                     hq_tc::mbar_expect_tx(s_full + slot, row_bytes);
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                                      hq_tc::smem_u32(ring + (size_t)slot * buf_bytes)),
-                                 "l"(db + row * db_stride), "r"(row_bytes), "r"(hq_tc::smem_u32(s_full + slot))
+                                 "l"(B16 ? reinterpret_cast<const void*>(db16 + row * db16_pitch) : reinterpret_cast<const void*>(db + row * db_stride)),
+                                 "r"(row_bytes), "r"(hq_tc::smem_u32(s_full + slot))
                                  : "memory");
                 }
                 c_next += min((uint32_t)__popc(bal), cap);
@@ -813,26 +835,43 @@ __global__ void __launch_bounds__(kSparseTopkThreads) k_rerank_sparse_topk(
     } else {
         // ================= consumers: sequence numbers warp - 1, warp - 1 + NC, ... =================
         const float nq = __ldg(q_norm + q);
-        float thr = -2.0f;                        // score of lane k - 1
+        float thr = -INFINITY;                    // value of lane kl - 1
         for (uint32_t turn = 0;; ++turn) {
             const uint32_t slot = (uint32_t)(warp - NP) + (uint32_t)NC * (turn & ((uint32_t)depth - 1u));
             hq_tc::mbar_wait(s_full + slot, (turn >> ldepth) & 1u);     // (a suspend-time hint here cost a microsecond per row)
             const int row = s_row[slot];
             if (row < 0) break;
             const float nc = __ldg(db_norm + row);
-            const float4* rv = reinterpret_cast<const float4*>(ring + (size_t)slot * buf_bytes);
-            float acc = 0.f;                                   // lane-strided fmaf chain: the order of k_rerank_sparse
+            float acc = 0.f;
+            if constexpr (B16) {
+                const uint4* rv = reinterpret_cast<const uint4*>(ring + (size_t)slot * buf_bytes);
+#pragma unroll 2
+                for (int i8 = lane; i8 < (n4 >> 1); i8 += 32) {
+                    const uint4 w = rv[i8];
+                    const float4 a0 = qs[2 * i8], a1 = qs[2 * i8 + 1];
+                    acc = fmaf(a0.x, __uint_as_float(w.x << 16), acc); acc = fmaf(a0.y, __uint_as_float(w.x & 0xffff0000u), acc);
+                    acc = fmaf(a0.z, __uint_as_float(w.y << 16), acc); acc = fmaf(a0.w, __uint_as_float(w.y & 0xffff0000u), acc);
+                    acc = fmaf(a1.x, __uint_as_float(w.z << 16), acc); acc = fmaf(a1.y, __uint_as_float(w.z & 0xffff0000u), acc);
+                    acc = fmaf(a1.z, __uint_as_float(w.w << 16), acc); acc = fmaf(a1.w, __uint_as_float(w.w & 0xffff0000u), acc);
+                }
+            } else {
+                const float4* rv = reinterpret_cast<const float4*>(ring + (size_t)slot * buf_bytes);
 #pragma unroll 4
-            for (int i4 = lane; i4 < n4; i4 += 32) {
-                const float4 a = qs[i4];
-                const float4 c = rv[i4];
-                acc = fmaf(a.x, c.x, acc); acc = fmaf(a.y, c.y, acc); acc = fmaf(a.z, c.z, acc); acc = fmaf(a.w, c.w, acc);
+                for (int i4 = lane; i4 < n4; i4 += 32) {      // lane-strided fmaf chain: the order of k_rerank_sparse
+                    const float4 a = qs[i4];
+                    const float4 c = rv[i4];
+                    acc = fmaf(a.x, c.x, acc); acc = fmaf(a.y, c.y, acc); acc = fmaf(a.z, c.z, acc); acc = fmaf(a.w, c.w, acc);
+                }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (lane == 0) hq_tc::mbar_arrive(s_empty + slot);                 // every lane's reads precede the shuffles
             float sc = 0.f;
-            if (nq != 0.f && nc != 0.f) sc = __fmul_rn(__fadd_rn(__fdiv_rn(acc, __fmul_rn(nq, nc)), 1.0f), 0.5f);
+            if constexpr (B16) {
+                sc = nc != 0.f ? acc : -1.0e30f;               // zero rows (exact score 0) rank below every other row
+            } else {
+                if (nq != 0.f && nc != 0.f) sc = __fmul_rn(__fadd_rn(__fdiv_rn(acc, __fmul_rn(nq, nc)), 1.0f), 0.5f);
+            }
             if (sc < thr) continue;                                   // warp-uniform
             const uint32_t bt = __ballot_sync(0xffffffffu, cand_better(sc, (int64_t)row, my_s, my_id));
             if (!bt) continue;
@@ -841,12 +880,12 @@ __global__ void __launch_bounds__(kSparseTopkThreads) k_rerank_sparse_topk(
             const int64_t up_id = __shfl_up_sync(0xffffffffu, my_id, 1);
             if (lane > pos) { my_s = up_s; my_id = up_id; }
             else if (lane == pos) { my_s = sc; my_id = row; }
-            thr = __shfl_sync(0xffffffffu, my_s, k - 1);
+            thr = __shfl_sync(0xffffffffu, my_s, kl - 1);
         }
     }
     // ---- the CTA's list: rank the warps' entries by counting ----
-    s_ls[tid] = lane < k ? my_s : -2.0f;
-    s_lid[tid] = lane < k ? my_id : INT64_MAX;
+    s_ls[tid] = lane < kl ? my_s : -INFINITY;
+    s_lid[tid] = lane < kl ? my_id : INT64_MAX;
     __syncthreads();
     {
         const float v = s_ls[tid];
@@ -855,16 +894,16 @@ __global__ void __launch_bounds__(kSparseTopkThreads) k_rerank_sparse_topk(
             int rank = 0;
             for (int j = 0; j < nthr; ++j) rank += cand_better(s_ls[j], s_lid[j], v, id) ? 1 : 0;
             atomicAdd(&s_nvalid, 1u);
-            if (rank < k) {
-                part_ids[((int64_t)q * P + blockIdx.x) * k + rank] = id;
-                part_scores[((int64_t)q * P + blockIdx.x) * k + rank] = v;
+            if (rank < kl) {
+                part_ids[((int64_t)q * P + blockIdx.x) * kl + rank] = id;
+                part_scores[((int64_t)q * P + blockIdx.x) * kl + rank] = v;
             }
         }
     }
     __syncthreads();
-    for (int j = (int)min(s_nvalid, (uint32_t)k) + tid; j < k; j += nthr) {
-        part_ids[((int64_t)q * P + blockIdx.x) * k + j] = -1;
-        part_scores[((int64_t)q * P + blockIdx.x) * k + j] = -1.0f;
+    for (int j = (int)min(s_nvalid, (uint32_t)kl) + tid; j < kl; j += nthr) {
+        part_ids[((int64_t)q * P + blockIdx.x) * kl + j] = -1;
+        part_scores[((int64_t)q * P + blockIdx.x) * kl + j] = -1.0f;
     }
     __threadfence();
     __syncthreads();
@@ -873,52 +912,199 @@ __global__ void __launch_bounds__(kSparseTopkThreads) k_rerank_sparse_topk(
     if (!s_last) return;
     __threadfence();
     // ---- last CTA of the query: merge the P lists ----
-    const int64_t* pi = part_ids + (int64_t)q * P * k;
-    const float* ps = part_scores + (int64_t)q * P * k;
-    const int M = P * k;
+    const int64_t* pi = part_ids + (int64_t)q * P * kl;
+    const float* ps = part_scores + (int64_t)q * P * kl;
+    const int M = P * kl;
     float tau = -INFINITY;
     for (int p = tid; p < P; p += nthr)
-        if (__ldcg(pi + (int64_t)p * k + k - 1) >= 0) tau = fmaxf(tau, __ldcg(ps + (int64_t)p * k + k - 1));   // sorted: last = minimum
+        if (__ldcg(pi + (int64_t)p * kl + kl - 1) >= 0) tau = fmaxf(tau, __ldcg(ps + (int64_t)p * kl + kl - 1));   // sorted: last = minimum
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tau = fmaxf(tau, __shfl_xor_sync(0xffffffffu, tau, o));
     if (lane == 0) s_wmax[warp] = tau;
     __syncthreads();
     tau = -INFINITY;
     for (int w = 0; w < nw; ++w) tau = fmaxf(tau, s_wmax[w]);
-    int64_t* c_id = reinterpret_cast<int64_t*>(sm_raw);                   // the query and the row buffers are no longer needed
-    float* c_s = reinterpret_cast<float*>(c_id + kSparseTopkSel);
+    const int sel_cap = B16 ? kSparseTopkSelB : kSparseTopkSel;
+    unsigned char* area = B16 ? sm_raw + q_bytes : sm_raw;                // fp32 pass: the query is no longer needed either
+    int64_t* c_id = reinterpret_cast<int64_t*>(area);
+    float* c_s = reinterpret_cast<float*>(c_id + sel_cap);
+    // The candidates that can still matter: the best `need` entries of the pool (the result, or the shortlist and the entry
+    // behind it), found with a 2048-bin histogram over [lo, hi] -- lo = tau (a full list proves that its whole length
+    // reaches its minimum) or the pool's minimum.  (Everything >= tau: 1 100 of the 1 480 entries of a query's lists.)
+    uint32_t* hist = reinterpret_cast<uint32_t*>(area + (((size_t)sel_cap * 12 + 127) & ~(size_t)127));   // [2048]
+    const uint32_t need = B16 ? (uint32_t)R + 1u : (uint32_t)k;
+    float vmax = -INFINITY, vmin = INFINITY;
+    for (int e = tid; e < M; e += nthr)
+        if (__ldcg(pi + e) >= 0) { const float v = __ldcg(ps + e); vmax = fmaxf(vmax, v); vmin = fminf(vmin, v); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+    }
+    __syncthreads();
+    if (lane == 0) { s_wmax[warp] = vmax; s_ls[warp] = vmin; }
+    for (int b = tid; b < 2048; b += nthr) hist[b] = 0;
+    if (tid == 0) s_cut = 0;
+    __syncthreads();
+    vmax = -INFINITY; vmin = INFINITY;
+    for (int w = 0; w < nw; ++w) { vmax = fmaxf(vmax, s_wmax[w]); vmin = fminf(vmin, s_ls[w]); }
+    const float lo = tau > -INFINITY ? tau : vmin;
+    const float bscale = vmax > lo ? 2047.0f / (vmax - lo) : 0.f;
+    auto bin_of = [&](float v) -> int {
+        const float x = (v - lo) * bscale;
+        return x >= 2047.0f ? 2047 : (x > 0.f ? (int)x : 0);
+    };
+    for (int e = tid; e < M; e += nthr) {
+        const float v = __ldcg(ps + e);
+        if (__ldcg(pi + e) >= 0 && !(v < lo)) atomicAdd(&hist[bin_of(v)], 1u);
+    }
+    __syncthreads();
+    {
+        // thread t owns the bins [2048 - (t + 1) per, 2048 - t per): suffix counts by a scan over the threads, top bins first
+        const int per = (2048 + nthr - 1) / nthr;
+        const int b_hi = 2048 - tid * per, b_lo = max(0, b_hi - per);
+        uint32_t sum = 0;
+        for (int b = b_hi - 1; b >= b_lo; --b) sum += hist[b];
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        uint32_t run = incl - sum;
+        for (int w = 0; w < warp; ++w) run += s_scan[w];
+        for (int b = b_hi - 1; b >= b_lo; --b) {
+            const uint32_t before = run;
+            run += hist[b];
+            if (before < need && run >= need) s_cut = b;          // the highest bin whose suffix count reaches `need`
+        }
+    }
+    __syncthreads();
+    const int cut = s_cut;
     for (int e = tid; e < M; e += nthr) {
         const int64_t id = __ldcg(pi + e);
         const float v = __ldcg(ps + e);
-        if (id >= 0 && !(v < tau)) {
+        if (id >= 0 && !(v < lo) && bin_of(v) >= cut) {
             const uint32_t slot = atomicAdd(&s_m, 1u);
-            if (slot < (uint32_t)kSparseTopkSel) { c_id[slot] = id; c_s[slot] = v; }
+            if (slot < (uint32_t)sel_cap) { c_id[slot] = id; c_s[slot] = v; }
         }
     }
     for (int j = tid; j < k; j += nthr) { out_ids[(int64_t)q * k + j] = -1; out_scores[(int64_t)q * k + j] = -1.0f; }
     __syncthreads();
     const int m = (int)s_m;
-    if (m <= kSparseTopkSel) {
-        for (int t = tid; t < m; t += nthr) {
-            const int64_t id = c_id[t];
-            const float v = c_s[t];
-            int rank = 0;
-            for (int u = 0; u < m; ++u) rank += cand_better(c_s[u], c_id[u], v, id) ? 1 : 0;
-            if (rank < k) { out_ids[(int64_t)q * k + rank] = id + id_base; out_scores[(int64_t)q * k + rank] = v; }
+    if constexpr (B16) {
+        // shortlist = the best R candidates by accumulator; everything else is bounded by max(tau, the (R + 1)-th accumulator)
+        __shared__ int32_t r_id[kSparseTopkR];
+        __shared__ float r_s[kSparseTopkR], r_t[kSparseTopkR];
+        __shared__ float s_next;
+        __shared__ int s_pass;
+        bool proven = m <= sel_cap;
+        const int n_sel = m < R ? m : R;
+        if (tid == 0) { s_next = -INFINITY; s_pass = 0; }
+        __syncthreads();
+        if (proven) {
+            for (int t = tid; t < m; t += nthr) {
+                const int64_t id = c_id[t];
+                const float v = c_s[t];
+                int rank = 0;
+                for (int u = 0; u < m; ++u) rank += cand_better(c_s[u], c_id[u], v, id) ? 1 : 0;
+                if (rank < R) r_id[rank] = (int32_t)id;
+                else if (rank == R) s_next = v;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the ring's slots are about to be overwritten by bulk copies
+            __syncthreads();
+            // exact values of the shortlist: the fp32 rows as bulk copies behind the candidate area, a warp per row
+            const uint32_t rb = (uint32_t)D * 4u;
+            unsigned char* rows_sm = area + (((size_t)sel_cap * 12 + 127) & ~(size_t)127);
+            if (tid == 0 && n_sel > 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                hq_tc::mbar_expect_tx(&s_rbar, (uint32_t)n_sel * rb);
+                for (int i = 0; i < n_sel; ++i)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     hq_tc::smem_u32(rows_sm + (size_t)i * q_bytes)),
+                                 "l"(db + (int64_t)r_id[i] * db_stride), "r"(rb), "r"(hq_tc::smem_u32(&s_rbar))
+                                 : "memory");
+            }
+            if (n_sel > 0) hq_tc::mbar_wait(&s_rbar, 0u);
+            const float nq = __ldg(q_norm + q);
+            for (int i = warp; i < n_sel; i += nw) {
+                const float4* rv = reinterpret_cast<const float4*>(rows_sm + (size_t)i * q_bytes);
+                float acc = 0.f;
+#pragma unroll 4
+                for (int i4 = lane; i4 < n4; i4 += 32) {      // the arithmetic of the fp32 pass: identical scores
+                    const float4 a = qs[i4];
+                    const float4 c = rv[i4];
+                    acc = fmaf(a.x, c.x, acc); acc = fmaf(a.y, c.y, acc); acc = fmaf(a.z, c.z, acc); acc = fmaf(a.w, c.w, acc);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) {
+                    const float nc = __ldg(db_norm + r_id[i]);
+                    float sc = 0.f;
+                    if (nq != 0.f && nc != 0.f) sc = __fmul_rn(__fadd_rn(__fdiv_rn(acc, __fmul_rn(nq, nc)), 1.0f), 0.5f);
+                    r_s[i] = sc;
+                    r_t[i] = nc != 0.f ? __fdiv_rn(acc, nc) : -1.0e30f;
+                }
+            }
+            __syncthreads();
+            if (warp == 0) {
+                const float bound = fmaxf(tau, s_next);                    // -inf: every surviving row was re-scored
+                int pass = 0;
+                if (bound == -INFINITY) pass = 1;
+                else if (n_sel >= k) {
+                    bool mine = false;                                     // lane i: is r_t[i] the k-th best exact value?
+                    if (lane < n_sel) {
+                        int rank = 0;
+                        for (int j = 0; j < n_sel; ++j) rank += (r_t[j] > r_t[lane] || (r_t[j] == r_t[lane] && j < lane)) ? 1 : 0;
+                        mine = rank == k - 1;
+                    }
+                    const uint32_t who = __ballot_sync(0xffffffffu, mine);
+                    const float tk = r_t[__ffs(who) - 1];
+                    const float E = nq * (dc_max + 1.0e-5f + (float)D * 2.4e-7f);
+                    pass = tk > bound + E ? 1 : 0;
+                }
+                if (lane == 0) s_pass = pass;
+            }
+            __syncthreads();
+            proven = s_pass != 0;
+        }
+        if (proven) {
+            if (tid < n_sel) {
+                const int32_t id = r_id[tid];
+                const float v = r_s[tid];
+                int rank = 0;
+                for (int j = 0; j < n_sel; ++j) rank += (r_s[j] > v || (r_s[j] == v && r_id[j] < id)) ? 1 : 0;
+                if (rank < k) { out_ids[(int64_t)q * k + rank] = (int64_t)id + id_base; out_scores[(int64_t)q * k + rank] = v; }
+            }
+        } else if (tid == 0) {
+            flags[q] = 1u;                                                 // the fp32 pass behind this launch redoes the query
         }
     } else {
-        // heavily tied scores: more candidates than the shared list holds -- rank them against the global lists
-        for (int e = tid; e < M; e += nthr) {
-            const int64_t id = __ldcg(pi + e);
-            const float v = __ldcg(ps + e);
-            if (id < 0 || v < tau) continue;
-            int rank = 0;
-            for (int u = 0; u < M && rank < k; ++u) {
-                const int64_t idu = __ldcg(pi + u);
-                rank += (idu >= 0 && cand_better(__ldcg(ps + u), idu, v, id)) ? 1 : 0;
+        if (m <= sel_cap) {
+            for (int t = tid; t < m; t += nthr) {
+                const int64_t id = c_id[t];
+                const float v = c_s[t];
+                int rank = 0;
+                for (int u = 0; u < m; ++u) rank += cand_better(c_s[u], c_id[u], v, id) ? 1 : 0;
+                if (rank < k) { out_ids[(int64_t)q * k + rank] = id + id_base; out_scores[(int64_t)q * k + rank] = v; }
             }
-            if (rank < k) { out_ids[(int64_t)q * k + rank] = id + id_base; out_scores[(int64_t)q * k + rank] = v; }
+        } else {
+            // heavily tied scores: more candidates than the shared list holds -- rank them against the global lists
+            for (int e = tid; e < M; e += nthr) {
+                const int64_t id = __ldcg(pi + e);
+                const float v = __ldcg(ps + e);
+                if (id < 0 || v < lo || bin_of(v) < cut) continue;
+                int rank = 0;
+                for (int u = 0; u < M && rank < k; ++u) {
+                    const int64_t idu = __ldcg(pi + u);
+                    rank += (idu >= 0 && cand_better(__ldcg(ps + u), idu, v, id)) ? 1 : 0;
+                }
+                if (rank < k) { out_ids[(int64_t)q * k + rank] = id + id_base; out_scores[(int64_t)q * k + rank] = v; }
+            }
         }
+        if (only_flagged && tid == 0) flags[q] = 0u;
     }
     if (tid == 0) { counters[2 * q] = 0; counters[2 * q + 1] = 0; }
 }
@@ -1321,12 +1507,52 @@ static int sparse_topk_ctas(int Q) {
 
 extern "C" int64_t hq_rerank_sparse_topk_scratch_bytes(int Q, int k) {
     if (Q <= 0 || k <= 0) return 0;
-    return (int64_t)Q * sparse_topk_ctas(Q) * k * 12 + (int64_t)Q * 8 + 64;
+    const int kl = k > 32 ? k : 32;
+    return (int64_t)Q * sparse_topk_ctas(Q) * kl * 12 + (int64_t)Q * 12 + 64;
 }
 
-extern "C" int hq_rerank_sparse_topk_f32(const float* db, const float* db_norm, int64_t N, int64_t D, int64_t db_stride, const float* q,
-                                         const float* q_norm, int Q, int64_t q_stride, const uint32_t* mask, int64_t mask_stride, int k,
-                                         int64_t id_base, int64_t* ids, float* scores, void* scratch, int64_t scratch_bytes, void* stream) {
+namespace {
+struct SparseGeom { int S, NP, NC, R; size_t smem; };
+
+// shared memory of a launch: the query + S row slots (rows padded to 128 bytes), as many as fit 200 KB, one producer warp
+// and up to 15 consumer warps with 1 / 2 / 4 slots each.  (2 / 3 / 4 producer warps with 14 / 12 / 12 consumers: 93-103 us
+// for a query against 1 M x 1536 where this split takes 85-100 us -- 57 K scattered 6 KB rows arrive at ~4 TB/s either way;
+// the bf16 variant with its 3 KB rows: 81-91 us with 1 to 4 producer warps, the fetch costs per ROW, not per byte.)
+bool sparse_geom(int64_t D, bool b16, SparseGeom& g) {
+    const size_t qb = ((size_t)D * 4 + 127) & ~(size_t)127;
+    const size_t buf = b16 ? (((size_t)D * 2 + 127) & ~(size_t)127) : qb;
+    const size_t budget = 200 * 1024;
+    if (qb + buf > budget) return false;
+    int S = (int)((budget - qb) / buf);
+    if (S > kSparseTopkSlots) S = kSparseTopkSlots;
+    if (S < 1) return false;
+    g.NP = 1;
+    g.NC = S < kSparseTopkThreads / 32 - 1 ? S : kSparseTopkThreads / 32 - 1;
+    const int depth = S / g.NC >= 4 ? 4 : (S / g.NC >= 2 ? 2 : 1);                 // slots per consumer: a power of two
+    g.S = depth * g.NC;
+    g.smem = qb + (size_t)g.S * buf;
+    g.R = 0;
+    if (b16) {                                      // the last CTA's exact re-score: candidates + R fp32 rows behind the query
+        const size_t cand = ((size_t)kSparseTopkSelB * 12 + 127) & ~(size_t)127;
+        int R = (int)((budget - qb - cand) / qb);
+        if (R > kSparseTopkR) R = kSparseTopkR;
+        g.R = R;
+        const size_t need = qb + cand + (size_t)R * qb;
+        if (need > g.smem) g.smem = need;
+    } else if (g.smem < (size_t)kSparseTopkSel * 12) {
+        g.smem = (size_t)kSparseTopkSel * 12;
+    }
+    return true;
+}
+}  // namespace
+
+// db_unit_bf16 (may be NULL): the shard's unit rows in bf16 (hq_to_bf16_unit) with dc_max = max |c16 - c / |c|| over the rows
+// (hq_bf16_unit_error_max): phase one then reads half the bytes, the best 32 rows are re-scored exactly and a query whose
+// result that does not prove is redone by the fp32 pass (second launch, a no-op otherwise).  Same ids and scores either way.
+extern "C" int hq_rerank_sparse_topk(const float* db, const float* db_norm, int64_t N, int64_t D, int64_t db_stride,
+                                     const void* db_unit_bf16, int64_t db_pitch, float dc_max, const float* q, const float* q_norm,
+                                     int Q, int64_t q_stride, const uint32_t* mask, int64_t mask_stride, int k, int64_t id_base,
+                                     int64_t* ids, float* scores, void* scratch, int64_t scratch_bytes, void* stream) {
     HQ_REQUIRE(N >= 0 && Q >= 0 && D > 0, "bad shape");
     if (Q == 0) return HQ_OK;
     HQ_REQUIRE(db && db_norm && q && q_norm && mask && ids && scores, "null pointer");
@@ -1337,31 +1563,33 @@ extern "C" int hq_rerank_sparse_topk_f32(const float* db, const float* db_norm, 
     HQ_REQUIRE(N < ((int64_t)1 << 31), "N too large for one shard");
     HQ_REQUIRE(scratch && scratch_bytes >= hq_rerank_sparse_topk_scratch_bytes(Q, k), "scratch too small");
     const int P = sparse_topk_ctas(Q);
-    int64_t* p_ids = reinterpret_cast<int64_t*>(scratch);                        // [Q][P][k]
-    float* p_sc = reinterpret_cast<float*>(p_ids + (int64_t)Q * P * k);
-    uint32_t* counters = reinterpret_cast<uint32_t*>(p_sc + (((int64_t)Q * P * k + 3) & ~(int64_t)3));
+    const int kl = k > 32 ? k : 32;
+    int64_t* p_ids = reinterpret_cast<int64_t*>(scratch);                        // [Q][P][kl]
+    float* p_sc = reinterpret_cast<float*>(p_ids + (int64_t)Q * P * kl);
+    uint32_t* counters = reinterpret_cast<uint32_t*>(p_sc + (((int64_t)Q * P * kl + 3) & ~(int64_t)3));   // [2 Q] tickets, done
+    uint32_t* flags = counters + 2 * Q;                                                                   // [Q]
     cudaStream_t st = (cudaStream_t)stream;
-    HQ_CUDA_OK(cudaMemsetAsync(counters, 0, (size_t)Q * 8, st));
-    // shared memory: the query + S row slots (rows padded to 128 bytes), as many as fit 200 KB
-    const size_t buf = ((size_t)D * 4 + 127) & ~(size_t)127;
-    int S = (int)((200 * 1024 - buf) / buf);
-    if (S > kSparseTopkSlots) S = kSparseTopkSlots;
-    HQ_REQUIRE(S >= 1, "D too large");
-    // one producer warp and up to 15 consumer warps.  (2 / 3 / 4 producer warps with 14 / 12 / 12 consumers: 93-103 us for a
-    // query against 1 M x 1536 where this split takes 85-100 us -- 57 K scattered 6 KB rows arrive at ~4 TB/s either way.)
-    const int NP = 1;
-    const int NC = S < kSparseTopkThreads / 32 - 1 ? S : kSparseTopkThreads / 32 - 1;
-    const int depth = S / NC >= 4 ? 4 : (S / NC >= 2 ? 2 : 1);                  // slots per consumer: a power of two
-    S = depth * NC;
-    size_t smem = buf + (size_t)S * buf;
-    if (smem < (size_t)kSparseTopkSel * 12) smem = (size_t)kSparseTopkSel * 12;
+    HQ_CUDA_OK(cudaMemsetAsync(counters, 0, (size_t)Q * 12, st));
     static bool attr = false;
     if (!attr) {
-        HQ_CUDA_OK(cudaFuncSetAttribute(k_rerank_sparse_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+        HQ_CUDA_OK(cudaFuncSetAttribute(k_rerank_sparse_topk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+        HQ_CUDA_OK(cudaFuncSetAttribute(k_rerank_sparse_topk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
         attr = true;
     }
-    k_rerank_sparse_topk<<<dim3(P, Q), (NP + NC) * 32, smem, st>>>(db, db_norm, N, D, db_stride, q, q_norm, Q, q_stride, mask, mask_stride, k,
-                                                                  id_base, p_ids, p_sc, counters, ids, scores, S, NP);
+    SparseGeom g32{}, g16{};
+    HQ_REQUIRE(sparse_geom(D, false, g32), "D too large");
+    const __nv_bfloat16* b16 = reinterpret_cast<const __nv_bfloat16*>(db_unit_bf16);
+    const bool use16 = b16 && D % 8 == 0 && db_pitch % 8 == 0 && db_pitch >= D && (reinterpret_cast<uintptr_t>(b16) & 15) == 0 &&
+                       dc_max >= 0.f && dc_max < 1.f && sparse_geom(D, true, g16) && g16.R >= k + 8;
+    if (use16) {
+        k_rerank_sparse_topk<true><<<dim3(P, Q), (g16.NP + g16.NC) * 32, g16.smem, st>>>(
+            db, db_norm, N, D, db_stride, b16, db_pitch, dc_max, q, q_norm, Q, q_stride, mask, mask_stride, k, id_base, p_ids, p_sc,
+            counters, flags, 0, ids, scores, g16.S, g16.NP, g16.R);
+        HQ_LAUNCH_OK("k_rerank_sparse_topk<bf16>");
+    }
+    k_rerank_sparse_topk<false><<<dim3(P, Q), (g32.NP + g32.NC) * 32, g32.smem, st>>>(
+        db, db_norm, N, D, db_stride, nullptr, 0, 0.f, q, q_norm, Q, q_stride, mask, mask_stride, k, id_base, p_ids, p_sc, counters,
+        flags, use16 ? 1 : 0, ids, scores, g32.S, g32.NP, 0);
     HQ_LAUNCH_OK("k_rerank_sparse_topk");
     return HQ_OK;
 }

@@ -285,13 +285,16 @@ int hq_rerank_scores_sparse_f32(const float* db, const float* db_norm, int64_t N
  * (the scores of hq_rerank_scores_sparse_f32, bit for bit) with the top-k (ties -> lower row id) taken on the way: no
  * [Q, N] score row, no separate top-k launches.  k <= 32, D % 4 == 0, 16-byte aligned rows
  * (hq_rerank_sparse_topk_supported); scratch: hq_rerank_sparse_topk_scratch_bytes(Q, k).  ids / scores [Q, k], -1 / -1.0f
- * when fewer than k rows survive. */
+ * when fewer than k rows survive.  db_unit_bf16 (optional, with dc_max as for hq_rerank_topk_unit_bf16): the survivors are
+ * first ranked by their bf16 unit rows (half the bytes), the best 32 re-scored exactly, and a query whose top-k that does not
+ * PROVE (error bound of the tensor-core rerank) is redone over the fp32 rows by a second launch: same results. */
 int hq_rerank_sparse_topk_supported(int64_t D, int64_t db_stride, int64_t q_stride, int k);
 int64_t hq_rerank_sparse_topk_scratch_bytes(int Q, int k);
-int hq_rerank_sparse_topk_f32(const float* db, const float* db_norm, int64_t N, int64_t D, int64_t db_stride,
-                              const float* q, const float* q_norm, int Q, int64_t q_stride,
-                              const uint32_t* mask, int64_t mask_stride, int k, int64_t id_base,
-                              int64_t* ids, float* scores, void* scratch, int64_t scratch_bytes, void* stream);
+int hq_rerank_sparse_topk(const float* db, const float* db_norm, int64_t N, int64_t D, int64_t db_stride,
+                          const void* db_unit_bf16, int64_t db_pitch, float dc_max,
+                          const float* q, const float* q_norm, int Q, int64_t q_stride,
+                          const uint32_t* mask, int64_t mask_stride, int k, int64_t id_base,
+                          int64_t* ids, float* scores, void* scratch, int64_t scratch_bytes, void* stream);
 int hq_topk_from_scores(const float* scores, int64_t scores_stride, int64_t N, int Q, int k, int64_t id_base,
                         int64_t* ids, float* out_scores, void* stream);
 /* hq_topk_from_scores for FEW queries over LONG rows: the row is cut into chunks (one CTA each), the chunk lists are

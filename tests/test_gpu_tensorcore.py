@@ -55,6 +55,8 @@ def test_sparse_rerank_equals_tensor_core_path(hq, N, D, Q):
     i_sp, s_sp = hq.search_batch(d, qs, 10, rerank="sparse")
     i_tc, s_tc = hq.search_batch(d, qs, 10, rerank="bf16")
     assert torch.equal(i_auto, i_sp) and torch.equal(s_auto, s_sp)
+    i_sb, s_sb = hq.search_batch(d, qs, 10, rerank="sparse_bf16")     # bf16 shortlist + exact re-score, proven or redone
+    assert torch.equal(i_sb, i_sp) and torch.equal(s_sb, s_sp)
     assert torch.equal(i_sp, i_tc), (i_sp, i_tc)
     assert torch.equal(s_sp, s_tc)
     assert set(i_sp[0, :2].tolist()) == {3, N // 2}
@@ -310,11 +312,24 @@ def test_bf16_only_database_scores_the_stored_rows_exactly(hq, N, D, Q, k):
         hq.search_batch(lean, qs, k, rerank="f32")
 
 
+def _unit_rows(lib, dev, check, db, norms):
+    """bf16 unit rows + dc_max of a device matrix (what EmbeddingDatabase keeps for the tensor-core rerank)."""
+    N, D = db.shape
+    pitch = (D + 7) // 8 * 8
+    unit = torch.zeros((N, pitch), dtype=torch.bfloat16, device="cuda")
+    check(lib.hq_to_bf16_unit(dev.ptr(db), N, D, D, dev.ptr(norms), dev.ptr(unit), pitch, dev.stream_ptr()))
+    worst = torch.zeros(1, dtype=torch.float32, device="cuda")
+    check(lib.hq_bf16_unit_error_max(dev.ptr(db), N, D, D, dev.ptr(norms), dev.ptr(unit), pitch, dev.ptr(worst), dev.stream_ptr()))
+    return unit, pitch, float(worst.item())
+
+
+@pytest.mark.parametrize("bf16", [False, True])
 @pytest.mark.parametrize("N,D,Q,k,density", [(50_000, 1536, 1, 10, 0.06), (9_999, 768, 4, 32, 0.3), (4_097, 2048, 2, 1, 0.5),
                                              (3_000, 4096, 3, 10, 0.02), (70_001, 100, 1, 10, 0.9), (1_000, 1024, 2, 20, 0.004),
                                              (6_000, 1536, 1, 10, 0.97), (2_500, 8192, 2, 5, 0.6)])
-def test_fused_sparse_rerank_topk_equals_the_two_step_path(hq, N, D, Q, k, density):
-    """hq_rerank_sparse_topk_f32 (rows staged by bulk copies, per-warp lists, last-CTA merge) against
+def test_fused_sparse_rerank_topk_equals_the_two_step_path(hq, N, D, Q, k, density, bf16):
+    """hq_rerank_sparse_topk (rows staged by bulk copies, per-warp lists, last-CTA merge; with `bf16` the survivors are ranked
+    by their bf16 unit rows first and the best 32 re-scored exactly, unproven queries redone over the fp32 rows) against
     hq_rerank_scores_sparse_f32 + hq_topk_from_scores_chunked on random survivor masks: ids and scores identical, with
     duplicate rows (exact ties -> lower id), zero rows, fewer than k survivors and a non-zero id_base."""
     from hilbert_quantization_b200 import _device as dev
@@ -342,13 +357,15 @@ def test_fused_sparse_rerank_topk_equals_the_two_step_path(hq, N, D, Q, k, densi
     mask = torch.where(mask >= 2 ** 31, mask - 2 ** 32, mask).to(torch.int32).contiguous()
     id_base = 1_000_000
     assert lib.hq_rerank_sparse_topk_supported(D, D, D, k)
+    unit, pitch, dc_max = _unit_rows(lib, dev, check, db, norms) if bf16 else (None, 0, 0.0)
     ids = torch.empty((Q, k), dtype=torch.int64, device="cuda")
     sc = torch.empty((Q, k), dtype=torch.float32, device="cuda")
     sb = int(lib.hq_rerank_sparse_topk_scratch_bytes(Q, k))
     scratch = torch.empty(sb, dtype=torch.uint8, device="cuda")
     for _ in range(2):                                             # the second call finds the counters as the first left them
-        check(lib.hq_rerank_sparse_topk_f32(dev.ptr(db), dev.ptr(norms), N, D, D, dev.ptr(qs), dev.ptr(qn), Q, D, dev.ptr(mask), words,
-                                            k, id_base, dev.ptr(ids), dev.ptr(sc), dev.ptr(scratch), sb, dev.stream_ptr()))
+        check(lib.hq_rerank_sparse_topk(dev.ptr(db), dev.ptr(norms), N, D, D, dev.ptr(unit), pitch, dc_max, dev.ptr(qs), dev.ptr(qn), Q, D,
+                                        dev.ptr(mask), words, k, id_base, dev.ptr(ids), dev.ptr(sc), dev.ptr(scratch), sb,
+                                        dev.stream_ptr()))
     scores = torch.empty((Q, N), dtype=torch.float32, device="cuda")
     check(lib.hq_rerank_scores_sparse_f32(dev.ptr(db), dev.ptr(norms), N, D, D, dev.ptr(qs), dev.ptr(qn), Q, D, dev.ptr(mask), words,
                                           dev.ptr(scores), N, dev.stream_ptr()))
@@ -364,6 +381,40 @@ def test_fused_sparse_rerank_topk_equals_the_two_step_path(hq, N, D, Q, k, densi
         assert ids[0, :3].tolist() == [id_base + 3, id_base + N // 2, id_base + N - 1]
     if Q > 1 and k > 5:
         assert (ids[Q - 1, 5:] == -1).all() and (sc[Q - 1, 5:] == -1.0).all()
+
+
+def test_fused_sparse_rerank_bf16_shortlist_on_a_near_duplicate_cluster(hq):
+    """20 000 rows within 1e-4 (cosine) of each other around the query: the bf16 accumulators cannot order them, the shortlist
+    check must fail and the fp32 pass behind it must return the exact top-k."""
+    from hilbert_quantization_b200 import _device as dev
+    from hilbert_quantization_b200._lib import lib, check
+    N, D, k = 60_000, 1536, 10
+    g = torch.Generator(device="cuda").manual_seed(5)
+    base = torch.randn(D, device="cuda", generator=g)
+    db = torch.randn((N, D), device="cuda", generator=g)
+    db[:20_000] = base + 0.01 * torch.randn((20_000, D), device="cuda", generator=g)
+    qs = (base + 0.01 * torch.randn(D, device="cuda", generator=g))[None].contiguous()
+    norms, qn = torch.empty(N, device="cuda"), torch.empty(1, device="cuda")
+    check(lib.hq_row_norms(dev.ptr(db), N, D, D, dev.ptr(norms), dev.stream_ptr()))
+    check(lib.hq_row_norms(dev.ptr(qs), 1, D, D, dev.ptr(qn), dev.stream_ptr()))
+    unit, pitch, dc_max = _unit_rows(lib, dev, check, db, norms)
+    words = (N + 31) // 32
+    mask = torch.full((1, words), -1, dtype=torch.int32, device="cuda")
+    out = []
+    for u in (unit, None):
+        ids = torch.empty((1, k), dtype=torch.int64, device="cuda")
+        sc = torch.empty((1, k), dtype=torch.float32, device="cuda")
+        sb = int(lib.hq_rerank_sparse_topk_scratch_bytes(1, k))
+        scratch = torch.empty(sb, dtype=torch.uint8, device="cuda")
+        check(lib.hq_rerank_sparse_topk(dev.ptr(db), dev.ptr(norms), N, D, D, dev.ptr(u), pitch if u is not None else 0, dc_max,
+                                        dev.ptr(qs), dev.ptr(qn), 1, D, dev.ptr(mask), words, k, 0, dev.ptr(ids), dev.ptr(sc),
+                                        dev.ptr(scratch), sb, dev.stream_ptr()))
+        out.append((ids, sc))
+    torch.cuda.synchronize()
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+    exact = ((db[:20_000].double() @ qs[0].double()) / (db[:20_000].double().norm(dim=1) * qs[0].double().norm()) + 1) / 2
+    want = torch.topk(exact, k).indices
+    assert set(out[0][0][0].tolist()) == set(want.tolist())
 
 
 def test_fused_sparse_rerank_topk_with_all_scores_tied(hq):
@@ -384,8 +435,8 @@ def test_fused_sparse_rerank_topk_with_all_scores_tied(hq):
     sc = torch.empty((1, k), dtype=torch.float32, device="cuda")
     sb = int(lib.hq_rerank_sparse_topk_scratch_bytes(1, k))
     scratch = torch.empty(sb, dtype=torch.uint8, device="cuda")
-    check(lib.hq_rerank_sparse_topk_f32(dev.ptr(db), dev.ptr(norms), N, D, D, dev.ptr(qs), dev.ptr(qn), 1, D, dev.ptr(mask), words,
-                                        k, 0, dev.ptr(ids), dev.ptr(sc), dev.ptr(scratch), sb, dev.stream_ptr()))
+    check(lib.hq_rerank_sparse_topk(dev.ptr(db), dev.ptr(norms), N, D, D, None, 0, 0.0, dev.ptr(qs), dev.ptr(qn), 1, D, dev.ptr(mask), words,
+                                    k, 0, dev.ptr(ids), dev.ptr(sc), dev.ptr(scratch), sb, dev.stream_ptr()))
     torch.cuda.synchronize()
     assert ids[0].tolist() == list(range(2, 2 + k))
     assert (sc[0] == sc[0, 0]).all()
