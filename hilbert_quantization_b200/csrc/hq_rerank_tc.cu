@@ -466,6 +466,9 @@ __global__ void __launch_bounds__(128) k_rerank_tc_merge(const TcParams p, const
     while (true) {
         if (warp == 0) {
             int c = cnt;
+            // (a first chunk of KP * 3 / 2 rows -- the 17th accumulator is rarely far enough below the 10th exact value, the
+            // 25th is -- made the kernel slower, 0.136 -> 0.166 ms: a chunk of 24 is two passes of the four warps, and the kernel
+            // is a chain of round trips per query, not a bandwidth problem)
             const int target = min(done + R_CHUNK, R_MAX);
             uint64_t nk;
             while (true) {
