@@ -502,6 +502,22 @@ __global__ void __launch_bounds__(128) k_rerank_tc_merge(const TcParams p, const
         cnt = s_cnt;
         const uint64_t next_key = s_next;
         const bool exhausted = next_key == 0ull;
+        {
+            // Every 128-byte line of the chunk's rows goes in flight NOW (prefetch.global.L2, fire and forget): the re-score loop
+            // below walks a row in D / 128 dependent steps (the loads of a step issue behind the FMAs of the step before), each a
+            // DRAM round trip of 1-3 us under the load of a thousand such chains; with the lines already on their way the
+            // later steps meet them in L2.
+            const int n_new = cnt - done;
+            const int64_t row_bytes = (int64_t)p.D * (B16 ? 2 : 4);
+            const int lines = (int)((row_bytes + 127) / 128) + 1;        // + the line of the row's last byte (unaligned rows)
+            for (int i = tid; i < n_new * lines; i += blockDim.x) {
+                const int r = i / lines, l = i - r * lines;
+                const int64_t id = sel_id[done + r];
+                const char* base = B16 ? reinterpret_cast<const char*>(db_b16 + id * db_pitch) : reinterpret_cast<const char*>(db_f32 + id * db_stride);
+                const int64_t off = l + 1 < lines ? (int64_t)l * 128 : row_bytes - 1;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+            }
+        }
         // ---- exact values of the chunk: a warp takes four rows at once ----
         for (int c0 = done + 4 * warp; c0 < cnt; c0 += 16) {
             const int nr = min(4, cnt - c0);
