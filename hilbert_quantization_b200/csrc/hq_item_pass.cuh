@@ -641,12 +641,21 @@ __global__ void __launch_bounds__(kBlock, 3) k_tile_pass_bulk(const __grid_const
     using P = typename PT<MODE>::type;
     using G = Geo<6>;
     constexpr uint32_t kImg = 4096;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* const s_img0 = reinterpret_cast<float*>(smem_raw);                     // kRing dense tile images
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
+    // The tile images are the source of 128-byte-SWIZZLED tensor stores (two 32-column halves per tile): the scatter of a
+    // warp's 32 quads into the dense image cost 4.75 shared-memory wavefronts per store (the cells of 128 consecutive curve
+    // positions share 8-16 columns = banks), 2.0 with the 16-byte chunks of a row XORed by (row & 7).  1024-byte aligned.
+    unsigned char* const smem_raw = smem_dyn + ((1024u - (hq_tc::smem_u32(smem_dyn) & 1023u)) & 1023u);
+    float* const s_img0 = reinterpret_cast<float*>(smem_raw);                     // kRing tile images (swizzled halves)
     float* const s_stage0 = s_img0 + kRing * kImg;                                // `stages` source staging buffers
     P* const s_pyr0 = reinterpret_cast<P*>(s_stage0 + (size_t)stages * kImg);     // two pyramids
     __shared__ __align__(8) uint64_t s_full[kMaxStages];
     __shared__ __align__(8) uint64_t s_free[2];
+    // byte offset of cell (x, y) inside a tile image: half (x >> 5) | row y of 128 bytes | 16-byte chunk ^ (y & 7) | (x & 3)
+    auto cell_off = [](uint32_t x, uint32_t y) -> uint32_t {
+        const uint32_t xx = x & 31u;
+        return (x >> 5) * 8192u + y * 128u + ((((xx >> 2) ^ (y & 7u)) << 4) | ((xx & 3u) << 2));
+    };
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool idx_warp = warp == kThreads / 32;
@@ -666,8 +675,8 @@ __global__ void __launch_bounds__(kBlock, 3) k_tile_pass_bulk(const __grid_const
         for (int i = 0; i < 4; ++i) {
             uint32_t x, y;
             hq_d2xy(6, 4ull * q + i, x, y);
-            a[i] = (y * 64 + x) * 4;                   // BYTE offsets inside the tile image (< 16384: 16 bits each)
-            b[i] = (x * 64 + y) * 4;
+            a[i] = cell_off(x, y);                     // BYTE offsets inside the tile image (< 16384: 16 bits each)
+            b[i] = cell_off(y, x);
         }
         slotA01[r] = a[0] | (a[1] << 16); slotA23[r] = a[2] | (a[3] << 16);
         slotB01[r] = b[0] | (b[1] << 16); slotB23[r] = b[2] | (b[3] << 16);
@@ -741,8 +750,9 @@ __global__ void __launch_bounds__(kBlock, 3) k_tile_pass_bulk(const __grid_const
             // iteration iter - 1, before that iteration's barrier)
             if (tid == 32 && chunk + (int64_t)gridDim.x < p.num_chunks) put_frame(chunk + gridDim.x, (iter + 1u) & 1u);
             // every cell of the tile is written (zeros beyond D): the images are reused by tiles with other fills.
-            // A flipped tile mirrors cell o to 4095 - o = o ^ 4095 (byte offset ^ 0x3ffc): one LOP3 per cell.
-            const uint32_t fx = flp ? 0x3ffcu : 0u;
+            // A flipped tile mirrors cell (x, y) to (63 - x, 63 - y): half, row and (x & 3) flip, the swizzled chunk stays
+            // (both of its XOR terms flip) -- byte offset ^ 0x3f8c: one LOP3 per cell.
+            const uint32_t fx = flp ? 0x3f8cu : 0u;
             char* const imgb = reinterpret_cast<char*>(img);
 #pragma unroll
             for (int r = 0; r < kQPT; ++r) {
@@ -760,10 +770,13 @@ __global__ void __launch_bounds__(kBlock, 3) k_tile_pass_bulk(const __grid_const
             asm volatile("bar.sync 2, %0;" ::"n"(kThreads) : "memory");
             if (tid == 0) {
                 if (p.grid_out) {
-                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                                     reinterpret_cast<uint64_t>(&map_grid)),
-                                 "r"(hq_tc::smem_u32(img)), "r"((int32_t)(X * 64)), "r"((int32_t)(item * ((int64_t)1 << p.log2n) + Y * 64))
-                                 : "memory");
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                         reinterpret_cast<uint64_t>(&map_grid)),
+                                     "r"(hq_tc::smem_u32(img) + 8192u * h), "r"((int32_t)(X * 64 + 32 * h)),
+                                     "r"((int32_t)(item * ((int64_t)1 << p.log2n) + Y * 64))
+                                     : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
                 const int64_t nx = chunk + (int64_t)stages * gridDim.x;
@@ -811,7 +824,7 @@ template <int MODE>
 int launch_tile_bulk(const TileParams& p, cudaStream_t st) {
     using G = Geo<6>;
     static const int ring = env_int("HQ_TILE_RING", 2), stages = env_int("HQ_TILE_STAGES", 2);
-    const size_t smem = (size_t)(ring + stages) * 4096 * 4 + (size_t)2 * G::pyr_vals * (MODE ? 8 : 4) + 64;
+    const size_t smem = (size_t)(ring + stages) * 4096 * 4 + (size_t)2 * G::pyr_vals * (MODE ? 8 : 4) + 64 + 1024;
     static size_t smem_set = 0;
     if (smem > smem_set) {
         HQ_CUDA_OK(cudaFuncSetAttribute(k_tile_pass_bulk<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -824,7 +837,7 @@ int launch_tile_bulk(const TileParams& p, cudaStream_t st) {
     memset(&map, 0, sizeof(map));
     if (p.grid_out) {
         const int64_t n = (int64_t)1 << p.log2n;
-        const int rc = hq_tc::make_map_2d_plain(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.grid_out, p.N * n, n, n, 64, 64);
+        const int rc = hq_tc::make_map_2d(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.grid_out, p.N * n, n, n, 32, 64);   // 128-byte swizzle
         if (rc != HQ_OK) return rc;
     }
     int64_t blocks = (int64_t)hq_cached_sm_count() * per_sm;
