@@ -85,14 +85,33 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock / throttle reasons during the timed region: NVML polled every 10 ms from a thread (a timed region of a few
+    tens of milliseconds -- 40 steps of a 125 K-row shard -- fell between two samples of `nvidia-smi -lms 100`), with
+    `nvidia-smi` as the fallback when pynvml cannot be used."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
+        self.nvml, self.handle, self.stop = None, None, threading.Event()
 
     def __enter__(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = self.index
+            if vis:                                    # torch's device `index` is a position in CUDA_VISIBLE_DEVICES
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if self.index < len(ids) and ids[self.index].isdigit():
+                    phys = int(ids[self.index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -102,11 +121,49 @@ class ClockSampler:
             self.proc = None
         return self
 
+    def _poll(self):
+        n = self.nvml
+        try:
+            mx = float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM))
+        except Exception:
+            mx = 0.0
+        bits = (("hw_slowdown", n.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksEventReasonHwThermalSlowdown),
+                ("sw_thermal_slowdown", n.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksEventReasonSwPowerCap))
+        while not self.stop.is_set():
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                self.rows.append([sm, mx, 0.0] + ["Active" if r & b else "Not Active" for _, b in bits])
+            except Exception:
+                pass
+            self.stop.wait(0.01)
+
+    def sample_now(self):
+        """One synchronous sample from the calling thread (NVML only).  Called right after the last launch of the timed region,
+        while the queued work is still running: a region of a few tens of milliseconds can end before the polling thread
+        gets a query through (an NVML query takes 3-10 ms, longer under load)."""
+        n = self.nvml
+        if n is None:
+            return
+        try:
+            sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+            mx = float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM))
+            r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            bits = (n.nvmlClocksEventReasonHwSlowdown, n.nvmlClocksEventReasonHwThermalSlowdown,
+                    n.nvmlClocksEventReasonSwThermalSlowdown, n.nvmlClocksEventReasonSwPowerCap)
+            self.rows.append([sm, mx, 0.0] + ["Active" if r & b else "Not Active" for b in bits])
+        except Exception:
+            pass
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def __exit__(self, *a):
+        if self.nvml is not None:
+            self.stop.set()
+            self.thread.join(timeout=1)
+            return
         if self.proc is not None:
             time.sleep(0.15)
             self.proc.terminate()
@@ -123,7 +180,7 @@ class ClockSampler:
                 sm.append(float(r[0]))
                 mx = max(mx, float(r[1]))
                 for name, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
+                    if str(v).lower().startswith("active"):
                         reasons.add(name)
             except Exception:
                 pass
@@ -558,6 +615,7 @@ def main():
             step(q_dev, wait=False)
             e1.record()
             step_ms.append((e0, e1))
+        clocks.sample_now()                           # the queued steps are still running
         if pipe is not None:
             pipe.drain()                              # the timed region ends when the last batch's merged result exists
         t_all1.record()
