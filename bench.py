@@ -84,34 +84,60 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "bf16_tflops_burst": None, "source": "fallback"}
 
 
+_CLOCK_POLLER = r"""
+import sys, time
+import pynvml as n
+n.nvmlInit()
+h = n.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+mx = float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM))
+bits = (n.nvmlClocksEventReasonHwSlowdown, n.nvmlClocksEventReasonHwThermalSlowdown,
+        n.nvmlClocksEventReasonSwThermalSlowdown, n.nvmlClocksEventReasonSwPowerCap)
+print("ready", flush=True)
+while True:
+    sm = float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM))
+    r = int(n.nvmlDeviceGetCurrentClocksEventReasons(h))
+    print(",".join([str(sm), str(mx), "0"] + ["Active" if r & b else "Not Active" for b in bits]), flush=True)
+    time.sleep(0.002)
+"""
+
+
 class ClockSampler:
-    """SM clock / throttle reasons during the timed region: NVML polled every 10 ms from a thread (a timed region of a few
-    tens of milliseconds -- 40 steps of a 125 K-row shard -- fell between two samples of `nvidia-smi -lms 100`), with
-    `nvidia-smi` as the fallback when pynvml cannot be used."""
+    """SM clock / throttle reasons during the timed region.  A child process polls NVML every few milliseconds (a query takes
+    3-10 ms) from before the region until after it: a timed region of a few tens of milliseconds -- 40 steps of a 125 K-row
+    shard -- fell between two samples of `nvidia-smi -lms 100`, and a polling THREAD of this process did not get a query
+    through either while the main thread held the interpreter in its launch loop.  `nvidia-smi -lms 100` is the fallback when
+    pynvml cannot be used.  Nothing is called from the timed thread: a synchronous NVML query before the end of a short region
+    would delay the host by more than the work still queued."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
-        self.nvml, self.handle, self.stop = None, None, threading.Event()
+        self.ready = threading.Event()
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        if vis:                                        # torch's device index is a position in CUDA_VISIBLE_DEVICES
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
 
     def __enter__(self):
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
-            phys = self.index
-            if vis:                                    # torch's device `index` is a position in CUDA_VISIBLE_DEVICES
-                ids = [v.strip() for v in vis.split(",") if v.strip()]
-                if self.index < len(ids) and ids[self.index].isdigit():
-                    phys = int(ids[self.index])
-            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
-            self.nvml = pynvml
-            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.proc = subprocess.Popen([sys.executable, "-c", _CLOCK_POLLER, str(self._physical_index())], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
-            return self
+            deadline = time.time() + 5.0
+            while not self.ready.is_set() and self.proc.poll() is None and time.time() < deadline:
+                self.ready.wait(0.05)
+            if self.ready.is_set():
+                return self
+            self.proc.kill()
         except Exception:
-            self.nvml = None
+            pass
+        self.rows = []
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -121,51 +147,17 @@ class ClockSampler:
             self.proc = None
         return self
 
-    def _poll(self):
-        n = self.nvml
-        try:
-            mx = float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM))
-        except Exception:
-            mx = 0.0
-        bits = (("hw_slowdown", n.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksEventReasonHwThermalSlowdown),
-                ("sw_thermal_slowdown", n.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksEventReasonSwPowerCap))
-        while not self.stop.is_set():
-            try:
-                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
-                r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
-                self.rows.append([sm, mx, 0.0] + ["Active" if r & b else "Not Active" for _, b in bits])
-            except Exception:
-                pass
-            self.stop.wait(0.01)
-
-    def sample_now(self):
-        """One synchronous sample from the calling thread (NVML only).  Called right after the last launch of the timed region,
-        while the queued work is still running: a region of a few tens of milliseconds can end before the polling thread
-        gets a query through (an NVML query takes 3-10 ms, longer under load)."""
-        n = self.nvml
-        if n is None:
-            return
-        try:
-            sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
-            mx = float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM))
-            r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
-            bits = (n.nvmlClocksEventReasonHwSlowdown, n.nvmlClocksEventReasonHwThermalSlowdown,
-                    n.nvmlClocksEventReasonSwThermalSlowdown, n.nvmlClocksEventReasonSwPowerCap)
-            self.rows.append([sm, mx, 0.0] + ["Active" if r & b else "Not Active" for b in bits])
-        except Exception:
-            pass
-
     def _read(self):
-        for line in self.proc.stdout:
+        proc = self.proc
+        for line in proc.stdout:
+            if line.startswith("ready"):
+                self.ready.set()
+                continue
             self.rows.append([c.strip() for c in line.split(",")])
 
     def __exit__(self, *a):
-        if self.nvml is not None:
-            self.stop.set()
-            self.thread.join(timeout=1)
-            return
         if self.proc is not None:
-            time.sleep(0.15)
+            time.sleep(0.02 if self.ready.is_set() else 0.15)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
@@ -615,7 +607,6 @@ def main():
             step(q_dev, wait=False)
             e1.record()
             step_ms.append((e0, e1))
-        clocks.sample_now()                           # the queued steps are still running
         if pipe is not None:
             pipe.drain()                              # the timed region ends when the last batch's merged result exists
         t_all1.record()
