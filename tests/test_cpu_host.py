@@ -28,6 +28,37 @@ def test_library_exports_every_declared_symbol():
     assert isinstance(_lib.last_error(), str)
 
 
+def test_ctypes_signatures_have_the_headers_parameter_counts():
+    """Every prototype of include/hq_b200.h against the argtypes list the Python side binds it with (a wrong count would
+    shift every later argument of a call silently)."""
+    from hilbert_quantization_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "hq_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)                       # comments quote prototypes too
+    protos = re.findall(r"\b(?:int|int64_t|const char\s*\*)\s+(hq_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S)
+    assert len(protos) >= 60
+    seen = set()
+    for name, params in protos:
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert name in _lib.SIGNATURES, name
+        assert len(_lib.SIGNATURES[name][1]) == n, f"{name}: header has {n} parameters, ctypes binds {len(_lib.SIGNATURES[name][1])}"
+        seen.add(name)
+    assert {"hq_rerank_sparse_topk", "hq_filter_fast_rows", "hq_filter_rows_pack", "hq_rerank_topk_unit_bf16"} <= seen
+
+
+def test_bench_clock_sampler_degrades_without_nvml():
+    """bench.ClockSampler on a box without a GPU: no samples, the summary keeps its keys, no long wait."""
+    import time
+    sys.path.insert(0, ROOT)
+    import bench
+    t0 = time.time()
+    with bench.ClockSampler(0) as c:
+        time.sleep(0.02)
+    out = c.summary()
+    assert set(out) == {"sm_mhz", "sm_max_mhz", "reasons", "samples"}
+    assert time.time() - t0 < 4.0
+
+
 def test_argument_validation_without_gpu():
     """HQ_EINVAL paths return before any CUDA call, so they are checkable on the CPU box."""
     from hilbert_quantization_b200._lib import lib, last_error, HQ_EINVAL
