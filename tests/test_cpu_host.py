@@ -28,9 +28,10 @@ def test_library_exports_every_declared_symbol():
     assert isinstance(_lib.last_error(), str)
 
 
-def test_ctypes_signatures_have_the_headers_parameter_counts():
-    """Every prototype of include/hq_b200.h against the argtypes list the Python side binds it with (a wrong count would
-    shift every later argument of a call silently)."""
+def test_ctypes_signatures_match_the_header():
+    """Every prototype of include/hq_b200.h against the argtypes list the Python side binds it with: parameter count and
+    parameter kind (a wrong count or width would shift or truncate every later argument of a call silently)."""
+    import ctypes
     from hilbert_quantization_b200 import _lib
     header = open(os.path.join(ROOT, "include", "hq_b200.h")).read()
     header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)                       # comments quote prototypes too
@@ -41,7 +42,22 @@ def test_ctypes_signatures_have_the_headers_parameter_counts():
         params = params.strip()
         n = 0 if params in ("", "void") else params.count(",") + 1
         assert name in _lib.SIGNATURES, name
-        assert len(_lib.SIGNATURES[name][1]) == n, f"{name}: header has {n} parameters, ctypes binds {len(_lib.SIGNATURES[name][1])}"
+        sig = _lib.SIGNATURES[name][1]
+        assert len(sig) == n, f"{name}: header has {n} parameters, ctypes binds {len(sig)}"
+        for i, (par, t) in enumerate(zip([x.strip() for x in params.split(",")] if n else [], sig)):
+            if "*" in par:
+                ok = t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "_type_")          # POINTER(IndexLayout)
+            elif re.match(r"(const\s+)?int64_t\b", par):
+                ok = t is ctypes.c_int64
+            elif re.match(r"(const\s+)?int\b", par):
+                ok = t in (ctypes.c_int32, ctypes.c_int)
+            elif re.match(r"(const\s+)?float\b", par):
+                ok = t is ctypes.c_float
+            elif re.match(r"(const\s+)?double\b", par):
+                ok = t is ctypes.c_double
+            else:
+                ok = False
+            assert ok, f"{name}: parameter {i} `{par}` is bound as {t}"
         seen.add(name)
     assert {"hq_rerank_sparse_topk", "hq_filter_fast_rows", "hq_filter_rows_pack", "hq_rerank_topk_unit_bf16"} <= seen
 
